@@ -1,0 +1,325 @@
+"""ctypes binding of include/dsvt_b200.h for torch CUDA tensors.
+
+PyTorch is plumbing here (device memory, streams); every function launches the hand-written
+sm_100a kernels through the C ABI and raises if the call fails.  No fallback path exists.
+"""
+import ctypes
+from ctypes import POINTER, Structure, c_float, c_int32, c_size_t, c_uint64, c_void_p
+
+import torch
+
+from ._lib import load_library
+
+DSVT_ATTN_FP32, DSVT_ATTN_TF32, DSVT_ATTN_BF16 = 0, 1, 2
+
+
+class P2FParams(Structure):
+    _fields_ = [("batch", c_int32), ("max_points_num", c_int32), ("max_points_num_voxel_filter", c_int32),
+                ("max_pillars_num", c_int32), ("point_feature_num", c_int32), ("feature_num", c_int32),
+                ("max_num_points_per_voxel", c_int32),
+                ("x_min", c_float), ("x_max", c_float), ("y_min", c_float), ("y_max", c_float),
+                ("z_min", c_float), ("z_max", c_float),
+                ("voxel_x", c_float), ("voxel_y", c_float), ("voxel_z", c_float),
+                ("grid_x", c_int32), ("grid_y", c_int32), ("grid_z", c_int32), ("zero_tails", c_int32)]
+
+
+class WPParams(Structure):
+    _fields_ = [("batch", c_int32), ("max_pillars_num", c_int32), ("max_win_num", c_int32),
+                ("max_voxel_num_per_win", c_int32),
+                ("sparse_shape_x", c_int32), ("sparse_shape_y", c_int32), ("sparse_shape_z", c_int32),
+                ("win_shape_x", c_int32), ("win_shape_y", c_int32), ("win_shape_z", c_int32),
+                ("shift_x", c_int32), ("shift_y", c_int32), ("shift_z", c_int32), ("zero_tails", c_int32)]
+
+
+class GSParams(Structure):
+    _fields_ = [("batch", c_int32), ("voxel_num_set", c_int32), ("max_win_num", c_int32),
+                ("max_voxel_num_per_win", c_int32),
+                ("win_shape_x", c_int32), ("win_shape_y", c_int32), ("win_shape_z", c_int32),
+                ("num_heads", c_int32), ("zero_tails", c_int32)]
+
+
+class GeluParams(Structure):
+    _fields_ = [("batch", c_int32), ("max_pillars_num", c_int32), ("channel_num", c_int32), ("zero_tails", c_int32)]
+
+
+class LNParams(Structure):
+    _fields_ = [("batch", c_int32), ("max_pillars_num", c_int32), ("channel_num", c_int32), ("eps", c_float),
+                ("zero_tails", c_int32)]
+
+
+class FBParams(Structure):
+    _fields_ = [("batch", c_int32), ("max_top_k", c_int32),
+                ("x_min", c_float), ("x_max", c_float), ("y_min", c_float), ("y_max", c_float),
+                ("z_min", c_float), ("z_max", c_float),
+                ("voxel_x", c_float), ("voxel_y", c_float), ("voxel_z", c_float),
+                ("score_threshold", c_float), ("zero_tails", c_int32)]
+
+
+class AttnParams(Structure):
+    _fields_ = [("batch", c_int32), ("max_set_num", c_int32), ("voxel_num_set", c_int32), ("channel_num", c_int32),
+                ("num_heads", c_int32), ("max_pillars_num", c_int32), ("axis_id", c_int32), ("precision", c_int32),
+                ("zero_tails", c_int32)]
+
+
+_sig_done = False
+
+
+def _lib():
+    global _sig_done
+    lib = load_library()
+    if not _sig_done:
+        lib.dsvt_last_error.restype = ctypes.c_char_p
+        lib.dsvt_launch_count.restype = c_uint64
+        lib.dsvt_points2features_workspace_size.restype = c_size_t
+        lib.dsvt_window_partition_workspace_size.restype = c_size_t
+        lib.dsvt_get_set_workspace_size.restype = c_size_t
+        lib.dsvt_set_attention_workspace_size.restype = c_size_t
+        lib.dsvt_attention_weights_create.restype = c_void_p
+        lib.dsvt_attention_weights_create.argtypes = [c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
+        lib.dsvt_attention_weights_destroy.argtypes = [c_void_p]
+        _sig_done = True
+    return lib
+
+
+class DsvtError(RuntimeError):
+    pass
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise DsvtError(f"{what} failed with code {rc}: {_lib().dsvt_last_error().decode()}")
+
+
+def _ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count():
+    return int(_lib().dsvt_launch_count())
+
+
+def _need(t, dtype, name):
+    if not (t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise DsvtError(f"{name}: expected a contiguous CUDA tensor of {dtype}")
+
+
+# ----------------------------------------------------------------------------------------------
+def p2f_params(cfg, batch=1, zero_tails=1):
+    return P2FParams(batch, cfg.max_points_num, cfg.max_points_num_voxel_filter, cfg.max_pillars_num,
+                     cfg.point_feature_num, cfg.feature_num, cfg.max_num_points_per_voxel,
+                     cfg.x_min, cfg.x_max, cfg.y_min, cfg.y_max, cfg.z_min, cfg.z_max,
+                     cfg.voxel_x, cfg.voxel_y, cfg.voxel_z, cfg.grid_x, cfg.grid_y, cfg.grid_z, zero_tails)
+
+
+class Points2Features:
+    """Voxeliser with pre-allocated outputs / workspace (reference: Points2FeaturesPlugin)."""
+
+    def __init__(self, cfg, batch=1, device="cuda", zero_tails=1):
+        self.cfg, self.batch = cfg, batch
+        self.p = p2f_params(cfg, batch, zero_tails)
+        lib = _lib()
+        self.ws_bytes = int(lib.dsvt_points2features_workspace_size(ctypes.byref(self.p)))
+        if self.ws_bytes == 0:
+            raise DsvtError("points2features: " + lib.dsvt_last_error().decode())
+        B = batch
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
+        self.point_features = torch.empty(B, cfg.max_points_num_voxel_filter, 10, dtype=torch.float32, device=device)
+        self.point_index_in_voxel = torch.empty(B, cfg.max_pillars_num, cfg.max_num_points_per_voxel,
+                                                dtype=torch.int32, device=device)
+        self.coords = torch.empty(B, cfg.max_pillars_num, 4, dtype=torch.int32, device=device)
+        self.point_num_in_voxel = torch.empty(B, cfg.max_pillars_num, dtype=torch.int32, device=device)
+        self.pillar_num = torch.empty(B, dtype=torch.int32, device=device)
+        self.point_num = torch.empty(B, dtype=torch.int32, device=device)
+
+    def __call__(self, points, points_size):
+        _need(points, torch.float32, "points")
+        _need(points_size, torch.int32, "points_size")
+        rc = _lib().dsvt_points2features_launch(
+            ctypes.byref(self.p), _ptr(points), _ptr(points_size), _ptr(self.point_features),
+            _ptr(self.point_index_in_voxel), _ptr(self.coords), _ptr(self.point_num_in_voxel),
+            _ptr(self.pillar_num), _ptr(self.point_num), _ptr(self.ws), c_size_t(self.ws_bytes), _stream())
+        _check(rc, "dsvt_points2features_launch")
+        return self
+
+
+class WindowPartition:
+    def __init__(self, cfg, which, batch=1, device="cuda", zero_tails=1):
+        wx, wy, wz = cfg.win_shapes[which]
+        sx, sy, sz = cfg.shifts[which]
+        self.cfg, self.batch = cfg, batch
+        self.p = WPParams(batch, cfg.max_pillars_num, cfg.max_win_num, cfg.max_voxel_num_per_win,
+                          cfg.grid_x, cfg.grid_y, cfg.grid_z, wx, wy, wz, sx, sy, sz, zero_tails)
+        lib = _lib()
+        self.ws_bytes = int(lib.dsvt_window_partition_workspace_size(ctypes.byref(self.p)))
+        if self.ws_bytes == 0:
+            raise DsvtError("window_partition: " + lib.dsvt_last_error().decode())
+        B, mw, mv, mp = batch, cfg.max_win_num, cfg.max_voxel_num_per_win, cfg.max_pillars_num
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
+        self.global_index = torch.empty(B, mw, mv, dtype=torch.int32, device=device)
+        self.coors_in_win = torch.empty(B, mw, mv, 3, dtype=torch.int32, device=device)
+        self.voxel_num_in_win = torch.empty(B, mw, dtype=torch.int32, device=device)
+        self.win_num = torch.empty(B, dtype=torch.int32, device=device)
+        self.coors_in_win_2d = torch.empty(B, mp, 3, dtype=torch.int32, device=device)
+        self.coors_in_win_x_y = torch.empty(B, mp, 2, dtype=torch.float32, device=device)
+
+    def __call__(self, coords, voxel_num):
+        _need(coords, torch.int32, "coords")
+        _need(voxel_num, torch.int32, "voxel_num")
+        rc = _lib().dsvt_window_partition_launch(
+            ctypes.byref(self.p), _ptr(coords), _ptr(voxel_num), _ptr(self.global_index), _ptr(self.coors_in_win),
+            _ptr(self.voxel_num_in_win), _ptr(self.win_num), _ptr(self.coors_in_win_2d), _ptr(self.coors_in_win_x_y),
+            _ptr(self.ws), c_size_t(self.ws_bytes), _stream())
+        _check(rc, "dsvt_window_partition_launch")
+        return self
+
+
+class GetSet:
+    def __init__(self, cfg, which, batch=1, device="cuda", zero_tails=1):
+        wx, wy, wz = cfg.win_shapes[which]
+        self.cfg, self.batch = cfg, batch
+        self.p = GSParams(batch, cfg.voxel_num_set, cfg.max_win_num, cfg.max_voxel_num_per_win, wx, wy, wz,
+                          cfg.num_heads, zero_tails)
+        B, mw, S, H = batch, cfg.max_win_num, cfg.voxel_num_set, cfg.num_heads
+        self.global_index_in_set = torch.empty(B, 2, mw, S, dtype=torch.int32, device=device)
+        self.set_voxel_mask = torch.empty(B, 2, mw, S, dtype=torch.float32, device=device)
+        self.set_num = torch.empty(B, dtype=torch.int32, device=device)
+        self.mask_expand_0 = torch.empty(B, mw, H, S, dtype=torch.float32, device=device)
+        self.mask_expand_1 = torch.empty(B, mw, H, S, dtype=torch.float32, device=device)
+
+    def __call__(self, global_index, coors_in_win, voxel_num_in_win, win_num):
+        for t, n in ((global_index, "global_index"), (coors_in_win, "coors_in_win"),
+                     (voxel_num_in_win, "voxel_num_in_win"), (win_num, "win_num")):
+            _need(t, torch.int32, n)
+        rc = _lib().dsvt_get_set_launch(
+            ctypes.byref(self.p), _ptr(global_index), _ptr(coors_in_win), _ptr(voxel_num_in_win), _ptr(win_num),
+            _ptr(self.global_index_in_set), _ptr(self.set_voxel_mask), _ptr(self.set_num),
+            _ptr(self.mask_expand_0), _ptr(self.mask_expand_1), c_void_p(0), c_size_t(0), _stream())
+        _check(rc, "dsvt_get_set_launch")
+        return self
+
+
+def gelu(x, voxel_num, out=None, zero_tails=1):
+    """x [B,max_pillars,C] (or [max_pillars,C])."""
+    _need(x, torch.float32, "x")
+    _need(voxel_num, torch.int32, "voxel_num")
+    B = x.shape[0] if x.dim() == 3 else 1
+    out = torch.empty_like(x) if out is None else out
+    p = GeluParams(B, x.shape[-2], x.shape[-1], zero_tails)
+    _check(_lib().dsvt_gelu_launch(ctypes.byref(p), _ptr(x), _ptr(voxel_num), _ptr(out), _stream()), "dsvt_gelu_launch")
+    return out
+
+
+def layer_norm(x, voxel_num, gamma, beta, eps=0.0, residual=None, out=None, zero_tails=1):
+    _need(x, torch.float32, "x")
+    _need(voxel_num, torch.int32, "voxel_num")
+    _need(gamma, torch.float32, "gamma")
+    _need(beta, torch.float32, "beta")
+    if residual is not None:
+        _need(residual, torch.float32, "residual")
+    B = x.shape[0] if x.dim() == 3 else 1
+    out = torch.empty_like(x) if out is None else out
+    p = LNParams(B, x.shape[-2], x.shape[-1], eps, zero_tails)
+    _check(_lib().dsvt_layer_norm_launch(ctypes.byref(p), _ptr(x), _ptr(residual), _ptr(voxel_num), _ptr(gamma),
+                                         _ptr(beta), _ptr(out), _stream()), "dsvt_layer_norm_launch")
+    return out
+
+
+def filter_box(cfg, scores, classes, xs, ys, center, center_z, angle, dim, boxes=None, valid=None, zero_tails=1):
+    B = scores.shape[0] if scores.dim() == 2 else 1
+    K = cfg.max_top_k
+    dev = scores.device
+    boxes = torch.empty(B, K, 9, dtype=torch.float32, device=dev) if boxes is None else boxes
+    valid = torch.empty(B, dtype=torch.int32, device=dev) if valid is None else valid
+    p = FBParams(B, K, cfg.x_min, cfg.x_max, cfg.y_min, cfg.y_max, cfg.z_min, cfg.z_max,
+                 cfg.voxel_x, cfg.voxel_y, cfg.voxel_z, cfg.score_threshold, zero_tails)
+    _check(_lib().dsvt_filter_box_launch(ctypes.byref(p), _ptr(scores), _ptr(classes), _ptr(xs), _ptr(ys),
+                                         _ptr(center), _ptr(center_z), _ptr(angle), _ptr(dim), _ptr(boxes),
+                                         _ptr(valid), _stream()), "dsvt_filter_box_launch")
+    return boxes, valid
+
+
+class AttentionWeights:
+    """Device-resident, pre-arranged weights of one attention layer (host float32 arrays in)."""
+
+    def __init__(self, in_proj_weight, in_proj_bias, out_proj_weight, out_proj_bias, channels=192, heads=8):
+        import numpy as np
+        arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in
+                (in_proj_weight, in_proj_bias, out_proj_weight, out_proj_bias)]
+        self.channels, self.heads = channels, heads
+        self.handle = _lib().dsvt_attention_weights_create(
+            channels, heads, *[a.ctypes.data_as(c_void_p) for a in arrs])
+        if not self.handle:
+            raise DsvtError("dsvt_attention_weights_create: " + _lib().dsvt_last_error().decode())
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib().dsvt_attention_weights_destroy(c_void_p(self.handle))
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def set_attention(weights, q, k, v, mask, set_num=None, out=None, precision=DSVT_ATTN_FP32, zero_tails=1):
+    """Plugin-shaped form: q,k,v [B,max_sets,S,C] (or without B), mask [B,max_sets,H,S]."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (mask, "mask")):
+        _need(t, torch.float32, n)
+    B = q.shape[0] if q.dim() == 4 else 1
+    max_sets, S, C = q.shape[-3], q.shape[-2], q.shape[-1]
+    out = torch.empty_like(q) if out is None else out
+    p = AttnParams(B, max_sets, S, C, weights.heads, 0, 0, precision, zero_tails)
+    rc = _lib().dsvt_set_attention_launch(ctypes.byref(p), c_void_p(weights.handle), _ptr(q), _ptr(k), _ptr(v),
+                                          _ptr(mask), _ptr(set_num), _ptr(out), c_void_p(0), c_size_t(0), _stream())
+    _check(rc, "dsvt_set_attention_launch")
+    return out
+
+
+def set_attention_fused(weights, x, pos, global_index_in_set, mask, set_num, voxel_num, axis, out=None,
+                        precision=DSVT_ATTN_FP32, zero_tails=1):
+    """Fused gather + attention + scatter: x,pos [B,max_pillars,C], global_index_in_set [B,2,max_sets,S]."""
+    _need(x, torch.float32, "x")
+    _need(pos, torch.float32, "pos")
+    _need(global_index_in_set, torch.int32, "global_index_in_set")
+    _need(mask, torch.float32, "mask")
+    B = x.shape[0] if x.dim() == 3 else 1
+    max_pillars, C = x.shape[-2], x.shape[-1]
+    max_sets, S = global_index_in_set.shape[-2], global_index_in_set.shape[-1]
+    out = torch.empty_like(x) if out is None else out
+    p = AttnParams(B, max_sets, S, C, weights.heads, max_pillars, axis, precision, zero_tails)
+    rc = _lib().dsvt_set_attention_fused_launch(ctypes.byref(p), c_void_p(weights.handle), _ptr(x), _ptr(pos),
+                                                _ptr(global_index_in_set), _ptr(mask), _ptr(set_num),
+                                                _ptr(voxel_num), _ptr(out), c_void_p(0), c_size_t(0), _stream())
+    _check(rc, "dsvt_set_attention_fused_launch")
+    return out
+
+
+def get_value_by_index(x, pos, global_index_in_set, set_num, axis, zero_tails=1):
+    B = x.shape[0] if x.dim() == 3 else 1
+    max_pillars, C = x.shape[-2], x.shape[-1]
+    max_sets, S = global_index_in_set.shape[-2], global_index_in_set.shape[-1]
+    shape = (B, max_sets, S, C) if x.dim() == 3 else (max_sets, S, C)
+    q, k, v = (torch.empty(shape, dtype=torch.float32, device=x.device) for _ in range(3))
+    p = AttnParams(B, max_sets, S, C, 8, max_pillars, axis, 0, zero_tails)
+    rc = _lib().dsvt_get_value_by_index_launch(ctypes.byref(p), _ptr(x), _ptr(pos), _ptr(global_index_in_set),
+                                               _ptr(set_num), _ptr(q), _ptr(k), _ptr(v), _stream())
+    _check(rc, "dsvt_get_value_by_index_launch")
+    return q, k, v
+
+
+def map_set_feature2voxel(feat, global_index_in_set, set_num, axis, max_pillars, zero_tails=1):
+    B = feat.shape[0] if feat.dim() == 4 else 1
+    max_sets, S, C = feat.shape[-3], feat.shape[-2], feat.shape[-1]
+    shape = (B, max_pillars, C) if feat.dim() == 4 else (max_pillars, C)
+    out = torch.empty(shape, dtype=torch.float32, device=feat.device)
+    p = AttnParams(B, max_sets, S, C, 8, max_pillars, axis, 0, zero_tails)
+    rc = _lib().dsvt_map_set_feature2voxel_launch(ctypes.byref(p), _ptr(feat), _ptr(global_index_in_set),
+                                                  _ptr(set_num), _ptr(out), _stream())
+    _check(rc, "dsvt_map_set_feature2voxel_launch")
+    return out

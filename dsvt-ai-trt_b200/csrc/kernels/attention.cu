@@ -1,0 +1,117 @@
+// a3 -- C ABI of the set attention: weight preparation and precision dispatch.
+#include "attention_common.cuh"
+#include <vector>
+
+using namespace dsvt;
+
+extern "C" dsvt_attention_weights* dsvt_attention_weights_create(int32_t C, int32_t heads,
+                                                                 const float* in_proj_weight,
+                                                                 const float* in_proj_bias,
+                                                                 const float* out_proj_weight,
+                                                                 const float* out_proj_bias)
+{
+    if (C != 192 || heads != 8 || !in_proj_weight || !in_proj_bias || !out_proj_weight || !out_proj_bias) {
+        set_last_error("dsvt_attention_weights_create: only channel_num=192, num_heads=8 with non-NULL weights "
+                       "is supported (got C=%d heads=%d)", C, heads);
+        return nullptr;
+    }
+    // PyTorch layout [out][in] (FC weight layout of the reference) -> k-major [in][out]
+    const size_t n_in = (size_t) C * 3 * C, n_out = (size_t) C * C;
+    std::vector<float> host(n_in + 3 * C + n_out + C);
+    float* w_in_t = host.data();
+    float* b_in = w_in_t + n_in;
+    float* w_out_t = b_in + 3 * C;
+    float* b_out = w_out_t + n_out;
+    for (int n = 0; n < 3 * C; ++n)
+        for (int k = 0; k < C; ++k) w_in_t[(size_t) k * 3 * C + n] = in_proj_weight[(size_t) n * C + k];
+    for (int n = 0; n < 3 * C; ++n) b_in[n] = in_proj_bias[n];
+    for (int n = 0; n < C; ++n)
+        for (int k = 0; k < C; ++k) w_out_t[(size_t) k * C + n] = out_proj_weight[(size_t) n * C + k];
+    for (int n = 0; n < C; ++n) b_out[n] = out_proj_bias[n];
+
+    auto* w = new (std::nothrow) dsvt_attention_weights();
+    if (!w) return nullptr;
+    w->channel_num = C;
+    w->num_heads = heads;
+    w->tc_blob = nullptr;
+    if (cudaGetDevice(&w->device) != cudaSuccess ||
+        cudaMalloc(&w->blob, host.size() * sizeof(float)) != cudaSuccess ||
+        cudaMemcpy(w->blob, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_last_error("dsvt_attention_weights_create: CUDA allocation/copy failed: %s",
+                       cudaGetErrorString(cudaGetLastError()));
+        delete w;
+        return nullptr;
+    }
+    w->dev.w_in_t = w->blob;
+    w->dev.b_in = w->blob + n_in;
+    w->dev.w_out_t = w->blob + n_in + 3 * C;
+    w->dev.b_out = w->blob + n_in + 3 * C + n_out;
+    w->dev.tc_blob = nullptr;
+    return w;
+}
+
+extern "C" void dsvt_attention_weights_destroy(dsvt_attention_weights* w) {
+    if (!w) return;
+    cudaFree(w->blob);
+    if (w->tc_blob) cudaFree(w->tc_blob);
+    delete w;
+}
+
+static int attn_check(const dsvt_set_attention_params* p, const dsvt_attention_weights* w) {
+    DSVT_CHECK_ARG(p != nullptr && w != nullptr, "params / weights is NULL");
+    DSVT_CHECK_ARG(p->batch >= 1 && p->max_set_num >= 1, "batch / max_set_num");
+    DSVT_CHECK_ARG(p->channel_num == w->channel_num && p->num_heads == w->num_heads,
+                   "channel_num / num_heads do not match the weights");
+    DSVT_CHECK_ARG(p->channel_num == 192 && p->num_heads == 8, "only C=192, heads=8 is built");
+    return DSVT_OK;
+}
+
+extern "C" size_t dsvt_set_attention_workspace_size(const dsvt_set_attention_params* p) {
+    (void) p;
+    return 0;   // everything between the token tile and the output row stays on chip
+}
+
+static int attn_dispatch(const dsvt_set_attention_params* p, const dsvt_attention_weights* w, bool fused,
+                         const float* q, const float* k, const float* v, const float* pos, const int* idx,
+                         const float* mask, const int* set_num, const int* voxel_num, float* out,
+                         cudaStream_t st)
+{
+    switch (p->precision) {
+        case DSVT_ATTN_FP32:
+            return set_attention_fp32(p, w->dev, fused, q, k, v, pos, idx, mask, set_num, voxel_num, out, st);
+        default:
+            set_last_error("set attention: precision %d is not available in this build", p->precision);
+            return DSVT_ERR_UNSUPPORTED;
+    }
+}
+
+extern "C" int dsvt_set_attention_launch(const dsvt_set_attention_params* p, const dsvt_attention_weights* w,
+                                         const float* q, const float* k, const float* v, const float* mask,
+                                         const int32_t* set_num, float* out,
+                                         void* workspace, size_t workspace_bytes, dsvt_stream_t stream)
+{
+    (void) workspace; (void) workspace_bytes;
+    int rc = attn_check(p, w);
+    if (rc != DSVT_OK) return rc;
+    DSVT_CHECK_ARG(q && k && v && mask && out, "NULL tensor pointer");
+    DSVT_CHECK_ARG(!(((uintptr_t) q | (uintptr_t) k | (uintptr_t) v | (uintptr_t) out) & 15), "16-B alignment");
+    return attn_dispatch(p, w, false, q, k, v, nullptr, nullptr, mask, set_num, nullptr, out,
+                         reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dsvt_set_attention_fused_launch(const dsvt_set_attention_params* p, const dsvt_attention_weights* w,
+                                               const float* x, const float* pos,
+                                               const int32_t* global_index_in_set, const float* mask,
+                                               const int32_t* set_num, const int32_t* voxel_num, float* out,
+                                               void* workspace, size_t workspace_bytes, dsvt_stream_t stream)
+{
+    (void) workspace; (void) workspace_bytes;
+    int rc = attn_check(p, w);
+    if (rc != DSVT_OK) return rc;
+    DSVT_CHECK_ARG(x && pos && global_index_in_set && mask && set_num && voxel_num && out, "NULL tensor pointer");
+    DSVT_CHECK_ARG(p->max_pillars_num >= 1, "max_pillars_num");
+    DSVT_CHECK_ARG(p->axis_id == 0 || p->axis_id == 1, "axis_id");
+    DSVT_CHECK_ARG(!(((uintptr_t) x | (uintptr_t) pos | (uintptr_t) out) & 15), "16-B alignment");
+    return attn_dispatch(p, w, true, x, nullptr, nullptr, pos, global_index_in_set, mask, set_num, voxel_num,
+                         out, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,29 @@
+// Shared declarations of the set-attention implementations.
+#pragma once
+#include "common.cuh"
+
+namespace dsvt {
+
+// device-resident, pre-arranged weights of one attention layer
+struct AttnWeightsDev {
+    const float* w_in_t;    // [C][3C]  in_proj_weight transposed (k-major: coalesced over output columns)
+    const float* b_in;      // [3C]
+    const float* w_out_t;   // [C][C]
+    const float* b_out;     // [C]
+    const void* tc_blob;    // operand images for the tcgen05 path (attention_tc.cu), or nullptr
+};
+
+int set_attention_fp32(const dsvt_set_attention_params* p, const AttnWeightsDev& w, bool fused,
+                       const float* q, const float* k, const float* v, const float* pos, const int* idx,
+                       const float* mask, const int* set_num, const int* voxel_num, float* out, cudaStream_t st);
+
+}  // namespace dsvt
+
+struct dsvt_attention_weights {
+    int channel_num;
+    int num_heads;
+    int device;
+    float* blob;            // one cudaMalloc: w_in_t | b_in | w_out_t | b_out
+    void* tc_blob;
+    dsvt::AttnWeightsDev dev;
+};

@@ -1,0 +1,99 @@
+// Shared helpers for the sm_100a kernels of the DSVT hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <atomic>
+#include "dsvt_b200.h"
+
+namespace dsvt {
+
+// --- error plumbing ---------------------------------------------------------
+void set_last_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launch_count;
+
+inline void count_launch(int n = 1) { g_launch_count.fetch_add((uint64_t) n, std::memory_order_relaxed); }
+
+#define DSVT_CHECK_ARG(cond, msg)                                                  \
+    do {                                                                           \
+        if (!(cond)) {                                                             \
+            ::dsvt::set_last_error("%s: invalid argument: %s", __func__, msg);     \
+            return DSVT_ERR_INVALID_ARGUMENT;                                      \
+        }                                                                          \
+    } while (0)
+
+#define DSVT_CUDA(call)                                                            \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess) {                                                  \
+            ::dsvt::set_last_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, \
+                                   cudaGetErrorString(e__));                       \
+            return DSVT_ERR_CUDA;                                                  \
+        }                                                                          \
+    } while (0)
+
+#define DSVT_LAUNCH_CHECK()                                                        \
+    do {                                                                           \
+        ::dsvt::count_launch();                                                    \
+        DSVT_CUDA(cudaGetLastError());                                             \
+    } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+constexpr size_t kWsAlign = 256;  // the reference aligns workspace sub-buffers to 256 B (points2Features.cu:70-102)
+
+// carve consecutive 256-B aligned sub-buffers out of a workspace
+struct WsCarver {
+    uint8_t* base;
+    size_t off = 0;
+    explicit WsCarver(void* p) : base(static_cast<uint8_t*>(p)) {}
+    template <typename T> T* take(size_t n) {
+        T* r = reinterpret_cast<T*>(base + off);
+        off += align_up(n * sizeof(T), kWsAlign);
+        return r;
+    }
+};
+
+int sm_count();
+
+// --- device helpers ---------------------------------------------------------
+__device__ __forceinline__ float4 ldg_stream4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream4(float4* p, const float4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// Block-wide exclusive scan of one int per thread (blockDim.x <= 1024, multiple of 32).
+// `warp_sums` must hold 32 ints of shared memory.  Returns the exclusive prefix; *total = block sum.
+__device__ __forceinline__ int block_excl_scan(int v, int* warp_sums, int* total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    int incl = warp_incl_scan(v, lane);
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int s = lane < nw ? warp_sums[lane] : 0;
+        int si = warp_incl_scan(s, lane);
+        warp_sums[lane] = si - s;           // exclusive warp offsets
+        if (lane == 31) warp_sums[32] = si; // total (needs 33 ints!)
+    }
+    __syncthreads();
+    int r = warp_sums[wid] + incl - v;
+    *total = warp_sums[32];
+    __syncthreads();
+    return r;
+}
+
+}  // namespace dsvt

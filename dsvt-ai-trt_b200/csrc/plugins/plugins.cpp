@@ -1,0 +1,746 @@
+// TensorRT IPluginV2DynamicExt shells of the DSVT hot path.  Each class mirrors one reference
+// plugin (same registered name, version "1", creator field names, output shapes / dtypes and
+// serialised byte layout) and forwards enqueue() to the C ABI in include/dsvt_b200.h.
+#include "plugin_base.h"
+
+#include <cuda_runtime_api.h>
+#include <new>
+
+namespace dsvt_plugins {
+
+static const DataType F = DataType::kFLOAT;
+static const DataType I = DataType::kINT32;
+
+static int batch_of(const PluginTensorDesc* in) { return in[0].dims.nbDims > 0 ? in[0].dims.d[0] : 1; }
+
+// =================================================================================================
+// Points2FeaturesPlugin -- reference plugins/include/points2Features.h:18-80, src/points2Features.cu
+// =================================================================================================
+class Points2FeaturesPlugin final : public PluginBase {
+public:
+    static constexpr const char* kName = "Points2FeaturesPlugin";
+    static FieldList field_list() {   // points2Features.cu:1084-1092
+        return {{"max_points_num", PluginFieldType::kINT32}, {"max_points_num_voxel_filter", PluginFieldType::kINT32},
+                {"max_pillars_num", PluginFieldType::kINT32}, {"point_feature_num", PluginFieldType::kINT32},
+                {"feature_num", PluginFieldType::kINT32}, {"max_num_points_per_voxel", PluginFieldType::kINT32},
+                {"point_cloud_range", PluginFieldType::kFLOAT32}, {"voxel_size", PluginFieldType::kFLOAT32},
+                {"grid_size", PluginFieldType::kINT32}};
+    }
+    explicit Points2FeaturesPlugin(const dsvt_points2features_params& p) : p_(p) {}
+    static IPluginV2* from_fields(const PluginFieldCollection* fc) {
+        dsvt_points2features_params p{};
+        p.batch = 1;
+        p.max_points_num = field_int(fc, "max_points_num");
+        p.max_points_num_voxel_filter = field_int(fc, "max_points_num_voxel_filter");
+        p.max_pillars_num = field_int(fc, "max_pillars_num");
+        p.point_feature_num = field_int(fc, "point_feature_num");
+        p.feature_num = field_int(fc, "feature_num");
+        p.max_num_points_per_voxel = field_int(fc, "max_num_points_per_voxel");
+        // point_cloud_range = (xmin,ymin,zmin,xmax,ymax,zmax)  (points2Features.cu:1161-1168)
+        p.x_min = field_float(fc, "point_cloud_range", 0); p.y_min = field_float(fc, "point_cloud_range", 1);
+        p.z_min = field_float(fc, "point_cloud_range", 2); p.x_max = field_float(fc, "point_cloud_range", 3);
+        p.y_max = field_float(fc, "point_cloud_range", 4); p.z_max = field_float(fc, "point_cloud_range", 5);
+        p.voxel_x = field_float(fc, "voxel_size", 0); p.voxel_y = field_float(fc, "voxel_size", 1);
+        p.voxel_z = field_float(fc, "voxel_size", 2);
+        p.grid_x = field_int(fc, "grid_size", 0); p.grid_y = field_int(fc, "grid_size", 1);
+        p.grid_z = field_int(fc, "grid_size", 2);
+        p.zero_tails = 1;
+        return new (std::nothrow) Points2FeaturesPlugin(p);
+    }
+    static IPluginV2* from_bytes(const void* data, size_t len) {   // points2Features.cu:119-143
+        Reader r(data, len);
+        dsvt_points2features_params p{};
+        p.batch = 1;
+        p.max_points_num = r.get<int>(); p.max_points_num_voxel_filter = r.get<int>(); p.max_pillars_num = r.get<int>();
+        p.point_feature_num = r.get<int>(); p.feature_num = r.get<int>(); p.max_num_points_per_voxel = r.get<int>();
+        p.x_min = r.get<float>(); p.x_max = r.get<float>(); p.y_min = r.get<float>(); p.y_max = r.get<float>();
+        p.z_min = r.get<float>(); p.z_max = r.get<float>();
+        p.voxel_x = r.get<float>(); p.voxel_y = r.get<float>(); p.voxel_z = r.get<float>();
+        p.grid_x = r.get<int>(); p.grid_y = r.get<int>(); p.grid_z = r.get<int>();
+        p.zero_tails = 1;
+        return r.ok() ? new (std::nothrow) Points2FeaturesPlugin(p) : nullptr;
+    }
+    size_t getSerializationSize() const noexcept override { return 9 * sizeof(int) + 9 * sizeof(float); }  // 72 B
+    void serialize(void* buf) const noexcept override {            // points2Features.cu:1037-1060
+        Writer w(buf);
+        w.put(p_.max_points_num); w.put(p_.max_points_num_voxel_filter); w.put(p_.max_pillars_num);
+        w.put(p_.point_feature_num); w.put(p_.feature_num); w.put(p_.max_num_points_per_voxel);
+        w.put(p_.x_min); w.put(p_.x_max); w.put(p_.y_min); w.put(p_.y_max); w.put(p_.z_min); w.put(p_.z_max);
+        w.put(p_.voxel_x); w.put(p_.voxel_y); w.put(p_.voxel_z);
+        w.put(p_.grid_x); w.put(p_.grid_y); w.put(p_.grid_z);
+    }
+    IPluginV2DynamicExt* clone() const noexcept override {
+        auto* c = new (std::nothrow) Points2FeaturesPlugin(p_);
+        if (c) c->setPluginNamespace(ns_.c_str());
+        return c;
+    }
+    const char* getPluginType() const noexcept override { return kName; }
+    int32_t getNbOutputs() const noexcept override { return 6; }
+    DimsExprs getOutputDimensions(int32_t i, const DimsExprs* in, int32_t, IExprBuilder& b) noexcept override {
+        const IDimensionExpr* B = in[0].d[0];                     // points2Features.cu:161-213
+        switch (i) {
+            case 0: return dims(b, B, {p_.max_points_num_voxel_filter, p_.feature_num});
+            case 1: return dims(b, B, {p_.max_pillars_num, p_.max_num_points_per_voxel});
+            case 2: return dims(b, B, {p_.max_pillars_num, 4});
+            case 3: return dims(b, B, {p_.max_pillars_num, 1});
+            default: return dims(b, B, {});
+        }
+    }
+    size_t getWorkspaceSize(const PluginTensorDesc* in, int32_t, const PluginTensorDesc*, int32_t) const noexcept override {
+        dsvt_points2features_params p = p_;
+        p.batch = batch_of(in);
+        return dsvt_points2features_workspace_size(&p);
+    }
+    int32_t enqueue(const PluginTensorDesc* in, const PluginTensorDesc*, const void* const* inputs,
+                    void* const* outputs, void* ws, cudaStream_t stream) noexcept override {
+        dsvt_points2features_params p = p_;
+        p.batch = batch_of(in);
+        return report(dsvt_points2features_launch(
+            &p, static_cast<const float*>(inputs[0]), static_cast<const int32_t*>(inputs[1]),
+            static_cast<float*>(outputs[0]), static_cast<int32_t*>(outputs[1]), static_cast<int32_t*>(outputs[2]),
+            static_cast<int32_t*>(outputs[3]), static_cast<int32_t*>(outputs[4]), static_cast<int32_t*>(outputs[5]),
+            ws, dsvt_points2features_workspace_size(&p), stream), kName);
+    }
+protected:
+    const std::vector<DataType>& io_types() const override {
+        static const std::vector<DataType> t{F, I, F, I, I, I, I, I};
+        return t;
+    }
+    size_t nb_inputs() const override { return 2; }
+private:
+    dsvt_points2features_params p_;
+};
+
+// =================================================================================================
+// WindowPartitionPlugin -- reference plugins/src/windowPartition.cu (next #1)
+// =================================================================================================
+class WindowPartitionPlugin final : public PluginBase {
+public:
+    static constexpr const char* kName = "WindowPartitionPlugin";
+    static FieldList field_list() {   // windowPartition.cu:549-553
+        return {{"max_win_num", PluginFieldType::kINT32}, {"max_voxel_num_per_win", PluginFieldType::kINT32},
+                {"sparse_shape", PluginFieldType::kINT32}, {"win_shape", PluginFieldType::kINT32},
+                {"shift_list", PluginFieldType::kINT32}};
+    }
+    explicit WindowPartitionPlugin(const dsvt_window_partition_params& p) : p_(p) {}
+    static IPluginV2* from_fields(const PluginFieldCollection* fc) {
+        dsvt_window_partition_params p{};
+        p.batch = 1;
+        p.max_win_num = field_int(fc, "max_win_num");
+        p.max_voxel_num_per_win = field_int(fc, "max_voxel_num_per_win");
+        p.sparse_shape_x = field_int(fc, "sparse_shape", 0); p.sparse_shape_y = field_int(fc, "sparse_shape", 1);
+        p.sparse_shape_z = field_int(fc, "sparse_shape", 2);
+        p.win_shape_x = field_int(fc, "win_shape", 0); p.win_shape_y = field_int(fc, "win_shape", 1);
+        p.win_shape_z = field_int(fc, "win_shape", 2);
+        p.shift_x = field_int(fc, "shift_list", 0); p.shift_y = field_int(fc, "shift_list", 1);
+        p.shift_z = field_int(fc, "shift_list", 2);
+        p.zero_tails = 1;
+        return new (std::nothrow) WindowPartitionPlugin(p);
+    }
+    static IPluginV2* from_bytes(const void* data, size_t len) {   // windowPartition.cu:115-128
+        Reader r(data, len);
+        dsvt_window_partition_params p{};
+        p.batch = 1;
+        p.sparse_shape_x = r.get<int>(); p.sparse_shape_y = r.get<int>(); p.sparse_shape_z = r.get<int>();
+        p.win_shape_x = r.get<int>(); p.win_shape_y = r.get<int>(); p.win_shape_z = r.get<int>();
+        p.shift_x = r.get<int>(); p.shift_y = r.get<int>(); p.shift_z = r.get<int>();
+        p.max_win_num = r.get<int>(); p.max_voxel_num_per_win = r.get<int>();
+        p.zero_tails = 1;
+        return r.ok() ? new (std::nothrow) WindowPartitionPlugin(p) : nullptr;
+    }
+    size_t getSerializationSize() const noexcept override { return 11 * sizeof(int); }
+    void serialize(void* buf) const noexcept override {            // windowPartition.cu:511-524
+        Writer w(buf);
+        w.put(p_.sparse_shape_x); w.put(p_.sparse_shape_y); w.put(p_.sparse_shape_z);
+        w.put(p_.win_shape_x); w.put(p_.win_shape_y); w.put(p_.win_shape_z);
+        w.put(p_.shift_x); w.put(p_.shift_y); w.put(p_.shift_z);
+        w.put(p_.max_win_num); w.put(p_.max_voxel_num_per_win);
+    }
+    IPluginV2DynamicExt* clone() const noexcept override {
+        auto* c = new (std::nothrow) WindowPartitionPlugin(p_);
+        if (c) c->setPluginNamespace(ns_.c_str());
+        return c;
+    }
+    const char* getPluginType() const noexcept override { return kName; }
+    int32_t getNbOutputs() const noexcept override { return 6; }
+    DimsExprs getOutputDimensions(int32_t i, const DimsExprs* in, int32_t, IExprBuilder& b) noexcept override {
+        const IDimensionExpr* B = in[0].d[0];
+        // the reference hard-codes MAX_PILLARS_NUM for outputs 4/5 (windowPartition.cu:181-198); it equals
+        // the pillar capacity of the coords input, which is what we use
+        const int maxv = in[0].nbDims > 1 && in[0].d[1]->isConstant() ? in[0].d[1]->getConstantValue() : 0;
+        switch (i) {
+            case 0: return dims(b, B, {p_.max_win_num, p_.max_voxel_num_per_win});
+            case 1: return dims(b, B, {p_.max_win_num, p_.max_voxel_num_per_win, 3});
+            case 2: return dims(b, B, {p_.max_win_num});
+            case 3: return dims(b, B, {});
+            case 4: return dims(b, B, {maxv, 3});
+            default: return dims(b, B, {maxv, 2});
+        }
+    }
+    size_t getWorkspaceSize(const PluginTensorDesc* in, int32_t, const PluginTensorDesc*, int32_t) const noexcept override {
+        dsvt_window_partition_params p = with_shapes(in);
+        return dsvt_window_partition_workspace_size(&p);
+    }
+    int32_t enqueue(const PluginTensorDesc* in, const PluginTensorDesc*, const void* const* inputs,
+                    void* const* outputs, void* ws, cudaStream_t stream) noexcept override {
+        dsvt_window_partition_params p = with_shapes(in);
+        return report(dsvt_window_partition_launch(
+            &p, static_cast<const int32_t*>(inputs[0]), static_cast<const int32_t*>(inputs[1]),
+            static_cast<int32_t*>(outputs[0]), static_cast<int32_t*>(outputs[1]), static_cast<int32_t*>(outputs[2]),
+            static_cast<int32_t*>(outputs[3]), static_cast<int32_t*>(outputs[4]), static_cast<float*>(outputs[5]),
+            ws, dsvt_window_partition_workspace_size(&p), stream), kName);
+    }
+protected:
+    const std::vector<DataType>& io_types() const override {
+        static const std::vector<DataType> t{I, I, I, I, I, I, I, F};
+        return t;
+    }
+    size_t nb_inputs() const override { return 2; }
+private:
+    dsvt_window_partition_params with_shapes(const PluginTensorDesc* in) const {
+        dsvt_window_partition_params p = p_;
+        p.batch = batch_of(in);
+        p.max_pillars_num = in[0].dims.d[1];
+        return p;
+    }
+    dsvt_window_partition_params p_;
+};
+
+// =================================================================================================
+// GetSetPlugin -- reference plugins/include/getSet.h:20-67, src/getSet.cu
+// =================================================================================================
+class GetSetPlugin final : public PluginBase {
+public:
+    static constexpr const char* kName = "GetSetPlugin";
+    static FieldList field_list() {   // getSet.cu:782-785
+        return {{"max_win_num", PluginFieldType::kINT32}, {"max_voxel_num_per_win", PluginFieldType::kINT32},
+                {"voxel_num_set", PluginFieldType::kINT32}, {"win_shape", PluginFieldType::kINT32}};
+    }
+    explicit GetSetPlugin(const dsvt_get_set_params& p) : p_(p) {}
+    static IPluginV2* from_fields(const PluginFieldCollection* fc) {
+        dsvt_get_set_params p{};
+        p.batch = 1;
+        p.max_win_num = field_int(fc, "max_win_num");
+        p.max_voxel_num_per_win = field_int(fc, "max_voxel_num_per_win");
+        p.voxel_num_set = field_int(fc, "voxel_num_set");
+        p.win_shape_x = field_int(fc, "win_shape", 0); p.win_shape_y = field_int(fc, "win_shape", 1);
+        p.win_shape_z = field_int(fc, "win_shape", 2);
+        p.num_heads = 8;   // NUM_HEADS, params.h:73
+        p.zero_tails = 1;
+        return new (std::nothrow) GetSetPlugin(p);
+    }
+    static IPluginV2* from_bytes(const void* data, size_t len) {   // getSet.cu:113-122
+        Reader r(data, len);
+        dsvt_get_set_params p{};
+        p.batch = 1;
+        p.voxel_num_set = r.get<int>(); p.max_win_num = r.get<int>(); p.max_voxel_num_per_win = r.get<int>();
+        p.win_shape_x = r.get<int>(); p.win_shape_y = r.get<int>(); p.win_shape_z = r.get<int>();
+        p.num_heads = 8;
+        p.zero_tails = 1;
+        return r.ok() ? new (std::nothrow) GetSetPlugin(p) : nullptr;
+    }
+    size_t getSerializationSize() const noexcept override { return 6 * sizeof(int); }
+    void serialize(void* buf) const noexcept override {            // getSet.cu:749-758
+        Writer w(buf);
+        w.put(p_.voxel_num_set); w.put(p_.max_win_num); w.put(p_.max_voxel_num_per_win);
+        w.put(p_.win_shape_x); w.put(p_.win_shape_y); w.put(p_.win_shape_z);
+    }
+    IPluginV2DynamicExt* clone() const noexcept override {
+        auto* c = new (std::nothrow) GetSetPlugin(p_);
+        if (c) c->setPluginNamespace(ns_.c_str());
+        return c;
+    }
+    const char* getPluginType() const noexcept override { return kName; }
+    int32_t getNbOutputs() const noexcept override { return 5; }
+    DimsExprs getOutputDimensions(int32_t i, const DimsExprs* in, int32_t, IExprBuilder& b) noexcept override {
+        const IDimensionExpr* B = in[0].d[0];                     // getSet.cu:140-184
+        switch (i) {
+            case 0: case 1: return dims(b, B, {2, p_.max_win_num, p_.voxel_num_set});
+            case 2: return dims(b, B, {});
+            default: return dims(b, B, {p_.max_win_num, p_.num_heads, p_.voxel_num_set});
+        }
+    }
+    int32_t enqueue(const PluginTensorDesc* in, const PluginTensorDesc*, const void* const* inputs,
+                    void* const* outputs, void* ws, cudaStream_t stream) noexcept override {
+        dsvt_get_set_params p = p_;
+        p.batch = batch_of(in);
+        return report(dsvt_get_set_launch(
+            &p, static_cast<const int32_t*>(inputs[0]), static_cast<const int32_t*>(inputs[1]),
+            static_cast<const int32_t*>(inputs[2]), static_cast<const int32_t*>(inputs[3]),
+            static_cast<int32_t*>(outputs[0]), static_cast<float*>(outputs[1]), static_cast<int32_t*>(outputs[2]),
+            static_cast<float*>(outputs[3]), static_cast<float*>(outputs[4]), ws, 0, stream), kName);
+    }
+protected:
+    const std::vector<DataType>& io_types() const override {
+        static const std::vector<DataType> t{I, I, I, I, I, F, I, F, F};
+        return t;
+    }
+    size_t nb_inputs() const override { return 4; }
+private:
+    dsvt_get_set_params p_;
+};
+
+// =================================================================================================
+// GeluPlugin -- reference plugins/include/gelu.h:17-62, src/gelu.cu
+// =================================================================================================
+class GeluPlugin final : public PluginBase {
+public:
+    static constexpr const char* kName = "GeluPlugin";
+    static FieldList field_list() {   // gelu.cu:325-326
+        return {{"max_pillars_num", PluginFieldType::kINT32}, {"channel_num", PluginFieldType::kINT32}};
+    }
+    explicit GeluPlugin(const dsvt_gelu_params& p) : p_(p) {}
+    static IPluginV2* from_fields(const PluginFieldCollection* fc) {
+        dsvt_gelu_params p{1, field_int(fc, "max_pillars_num"), field_int(fc, "channel_num"), 1};
+        return new (std::nothrow) GeluPlugin(p);
+    }
+    static IPluginV2* from_bytes(const void* data, size_t len) {
+        Reader r(data, len);
+        dsvt_gelu_params p{};
+        p.batch = 1; p.max_pillars_num = r.get<int>(); p.channel_num = r.get<int>(); p.zero_tails = 1;
+        return r.ok() ? new (std::nothrow) GeluPlugin(p) : nullptr;
+    }
+    size_t getSerializationSize() const noexcept override { return 2 * sizeof(int); }
+    void serialize(void* buf) const noexcept override {            // gelu.cu:296-302
+        Writer w(buf);
+        w.put(p_.max_pillars_num); w.put(p_.channel_num);
+    }
+    IPluginV2DynamicExt* clone() const noexcept override {
+        auto* c = new (std::nothrow) GeluPlugin(p_);
+        if (c) c->setPluginNamespace(ns_.c_str());
+        return c;
+    }
+    const char* getPluginType() const noexcept override { return kName; }
+    int32_t getNbOutputs() const noexcept override { return 1; }
+    DimsExprs getOutputDimensions(int32_t, const DimsExprs* in, int32_t, IExprBuilder& b) noexcept override {
+        return dims(b, in[0].d[0], {p_.max_pillars_num, p_.channel_num});   // gelu.cu:149-160
+    }
+    int32_t enqueue(const PluginTensorDesc* in, const PluginTensorDesc*, const void* const* inputs,
+                    void* const* outputs, void*, cudaStream_t stream) noexcept override {
+        dsvt_gelu_params p = p_;
+        p.batch = batch_of(in);
+        return report(dsvt_gelu_launch(&p, static_cast<const float*>(inputs[0]), static_cast<const int32_t*>(inputs[1]),
+                                       static_cast<float*>(outputs[0]), stream), kName);
+    }
+protected:
+    const std::vector<DataType>& io_types() const override {
+        static const std::vector<DataType> t{F, I, F};
+        return t;
+    }
+    size_t nb_inputs() const override { return 2; }
+private:
+    dsvt_gelu_params p_;
+};
+
+// =================================================================================================
+// LayerNormPlugin -- reference plugins/include/layerNorm.h:17-78, src/layerNorm.cu
+// Owns host copies of gamma/beta (serialised) and a device copy uploaded in initialize().
+// =================================================================================================
+class LayerNormPlugin final : public PluginBase {
+public:
+    static constexpr const char* kName = "LayerNormPlugin";
+    static FieldList field_list() {   // layerNorm.cu:494-500 -- "pes" (sic) is the advertised name of eps
+        return {{"max_pillars_num", PluginFieldType::kINT32}, {"channel_num", PluginFieldType::kINT32},
+                {"weights_size", PluginFieldType::kINT32}, {"pes", PluginFieldType::kFLOAT32},
+                {"weights", PluginFieldType::kFLOAT32}, {"bias", PluginFieldType::kFLOAT32}};
+    }
+    LayerNormPlugin(int max_pillars, int channels, int wsize, float eps, const float* gamma, const float* beta)
+        : max_pillars_(max_pillars), channels_(channels), wsize_(wsize), eps_(eps),
+          gamma_(gamma, gamma + wsize), beta_(beta, beta + wsize) {}
+    ~LayerNormPlugin() override { release(); }
+    static IPluginV2* from_fields(const PluginFieldCollection* fc) {
+        const int wsize = field_int(fc, "weights_size");
+        const PluginField* g = find_field(fc, "weights");
+        const PluginField* b = find_field(fc, "bias");
+        if (wsize <= 0 || !g || !b || !g->data || !b->data) return nullptr;
+        // the creator parses "eps" (layerNorm.cu:558) although it advertises "pes": the reference helper
+        // therefore never sends it and eps stays 0.0.  Same behaviour here.
+        return new (std::nothrow) LayerNormPlugin(field_int(fc, "max_pillars_num"), field_int(fc, "channel_num"), wsize,
+                                                  field_float(fc, "eps", 0, 0.0f),
+                                                  static_cast<const float*>(g->data), static_cast<const float*>(b->data));
+    }
+    static IPluginV2* from_bytes(const void* data, size_t len) {   // layerNorm.cu:160-190
+        Reader r(data, len);
+        const int mp = r.get<int>(), ch = r.get<int>(), ws = r.get<int>();
+        const float eps = r.get<float>();
+        if (!r.ok() || ws <= 0 || r.left() < (size_t) ws * 2 * sizeof(float)) return nullptr;
+        std::vector<float> g(ws), b(ws);
+        r.get_array(g.data(), ws);
+        r.get_array(b.data(), ws);
+        return new (std::nothrow) LayerNormPlugin(mp, ch, ws, eps, g.data(), b.data());
+    }
+    size_t getSerializationSize() const noexcept override {       // layerNorm.cu:446-449 (with ws == channels)
+        return 3 * sizeof(int) + sizeof(float) + (size_t) wsize_ * 2 * sizeof(float);
+    }
+    void serialize(void* buf) const noexcept override {            // layerNorm.cu:451-471
+        Writer w(buf);
+        w.put(max_pillars_); w.put(channels_); w.put(wsize_); w.put(eps_);
+        w.put_array(gamma_.data(), gamma_.size());
+        w.put_array(beta_.data(), beta_.size());
+    }
+    IPluginV2DynamicExt* clone() const noexcept override {
+        auto* c = new (std::nothrow) LayerNormPlugin(max_pillars_, channels_, wsize_, eps_, gamma_.data(), beta_.data());
+        if (c) c->setPluginNamespace(ns_.c_str());
+        return c;
+    }
+    int32_t initialize() noexcept override { return upload(); }
+    void terminate() noexcept override { release(); }
+    const char* getPluginType() const noexcept override { return kName; }
+    int32_t getNbOutputs() const noexcept override { return 1; }
+    DimsExprs getOutputDimensions(int32_t, const DimsExprs* in, int32_t, IExprBuilder& b) noexcept override {
+        return dims(b, in[0].d[0], {max_pillars_, channels_});     // layerNorm.cu:198-209
+    }
+    int32_t enqueue(const PluginTensorDesc* in, const PluginTensorDesc*, const void* const* inputs,
+                    void* const* outputs, void*, cudaStream_t stream) noexcept override {
+        if (upload() != 0) return DSVT_ERR_CUDA;
+        dsvt_layer_norm_params p{batch_of(in), max_pillars_, channels_, eps_, 1};
+        return report(dsvt_layer_norm_launch(&p, static_cast<const float*>(inputs[0]), nullptr,
+                                             static_cast<const int32_t*>(inputs[1]), dev_, dev_ + wsize_,
+                                             static_cast<float*>(outputs[0]), stream), kName);
+    }
+protected:
+    const std::vector<DataType>& io_types() const override {
+        static const std::vector<DataType> t{F, I, F};
+        return t;
+    }
+    size_t nb_inputs() const override { return 2; }
+private:
+    int upload() {
+        if (dev_) return 0;
+        if (cudaMalloc(reinterpret_cast<void**>(&dev_), (size_t) wsize_ * 2 * sizeof(float)) != cudaSuccess) return 1;
+        if (cudaMemcpy(dev_, gamma_.data(), wsize_ * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(dev_ + wsize_, beta_.data(), wsize_ * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+            release();
+            return 1;
+        }
+        return 0;
+    }
+    void release() {
+        if (dev_) { cudaFree(dev_); dev_ = nullptr; }
+    }
+    int max_pillars_, channels_, wsize_;
+    float eps_;
+    std::vector<float> gamma_, beta_;
+    float* dev_ = nullptr;
+};
+
+// =================================================================================================
+// FilterBoxByScorePlugin -- reference plugins/include/filterBoxByScore.h:17-70, src/filterBoxByScore.cu
+// =================================================================================================
+class FilterBoxByScorePlugin final : public PluginBase {
+public:
+    static constexpr const char* kName = "FilterBoxByScorePlugin";
+    static FieldList field_list() {   // filterBoxByScore.cu:459-462
+        return {{"max_top_k", PluginFieldType::kINT32}, {"point_cloud_range", PluginFieldType::kFLOAT32},
+                {"voxel_size", PluginFieldType::kFLOAT32}, {"score_threshold", PluginFieldType::kFLOAT32}};
+    }
+    explicit FilterBoxByScorePlugin(const dsvt_filter_box_params& p) : p_(p) {}
+    static IPluginV2* from_fields(const PluginFieldCollection* fc) {
+        dsvt_filter_box_params p{};
+        p.batch = 1;
+        p.max_top_k = field_int(fc, "max_top_k");
+        // NOTE the order differs from Points2Features: (xmin,xmax,ymin,ymax,zmin,zmax), filterBoxByScore.cu:504-512
+        p.x_min = field_float(fc, "point_cloud_range", 0); p.x_max = field_float(fc, "point_cloud_range", 1);
+        p.y_min = field_float(fc, "point_cloud_range", 2); p.y_max = field_float(fc, "point_cloud_range", 3);
+        p.z_min = field_float(fc, "point_cloud_range", 4); p.z_max = field_float(fc, "point_cloud_range", 5);
+        p.voxel_x = field_float(fc, "voxel_size", 0); p.voxel_y = field_float(fc, "voxel_size", 1);
+        p.voxel_z = field_float(fc, "voxel_size", 2);
+        p.score_threshold = field_float(fc, "score_threshold");
+        p.zero_tails = 1;
+        return new (std::nothrow) FilterBoxByScorePlugin(p);
+    }
+    static IPluginV2* from_bytes(const void* data, size_t len) {   // filterBoxByScore.cu:117-135
+        Reader r(data, len);
+        dsvt_filter_box_params p{};
+        p.batch = 1;
+        p.max_top_k = r.get<int>();
+        p.x_min = r.get<float>(); p.x_max = r.get<float>(); p.y_min = r.get<float>(); p.y_max = r.get<float>();
+        p.z_min = r.get<float>(); p.z_max = r.get<float>();
+        p.voxel_x = r.get<float>(); p.voxel_y = r.get<float>(); p.voxel_z = r.get<float>();
+        p.score_threshold = r.get<float>();
+        p.zero_tails = 1;
+        return r.ok() ? new (std::nothrow) FilterBoxByScorePlugin(p) : nullptr;
+    }
+    size_t getSerializationSize() const noexcept override { return sizeof(int) + 10 * sizeof(float); }   // 44 B
+    void serialize(void* buf) const noexcept override {            // filterBoxByScore.cu:418-434
+        Writer w(buf);
+        w.put(p_.max_top_k);
+        w.put(p_.x_min); w.put(p_.x_max); w.put(p_.y_min); w.put(p_.y_max); w.put(p_.z_min); w.put(p_.z_max);
+        w.put(p_.voxel_x); w.put(p_.voxel_y); w.put(p_.voxel_z);
+        w.put(p_.score_threshold);
+    }
+    IPluginV2DynamicExt* clone() const noexcept override {
+        auto* c = new (std::nothrow) FilterBoxByScorePlugin(p_);
+        if (c) c->setPluginNamespace(ns_.c_str());
+        return c;
+    }
+    const char* getPluginType() const noexcept override { return kName; }
+    int32_t getNbOutputs() const noexcept override { return 2; }
+    DimsExprs getOutputDimensions(int32_t i, const DimsExprs* in, int32_t, IExprBuilder& b) noexcept override {
+        if (i == 0) return dims(b, in[0].d[0], {p_.max_top_k, 9});   // filterBoxByScore.cu:144-195
+        return dims(b, in[0].d[0], {});
+    }
+    int32_t enqueue(const PluginTensorDesc* in, const PluginTensorDesc*, const void* const* inputs,
+                    void* const* outputs, void*, cudaStream_t stream) noexcept override {
+        dsvt_filter_box_params p = p_;
+        p.batch = batch_of(in);
+        return report(dsvt_filter_box_launch(
+            &p, static_cast<const float*>(inputs[0]), static_cast<const int32_t*>(inputs[1]),
+            static_cast<const int32_t*>(inputs[2]), static_cast<const int32_t*>(inputs[3]),
+            static_cast<const float*>(inputs[4]), static_cast<const float*>(inputs[5]),
+            static_cast<const float*>(inputs[6]), static_cast<const float*>(inputs[7]),
+            static_cast<float*>(outputs[0]), static_cast<int32_t*>(outputs[1]), stream), kName);
+    }
+protected:
+    const std::vector<DataType>& io_types() const override {
+        static const std::vector<DataType> t{F, I, I, I, F, F, F, F, F, I};
+        return t;
+    }
+    size_t nb_inputs() const override { return 8; }
+private:
+    dsvt_filter_box_params p_;
+};
+
+// =================================================================================================
+// GetValueByIndexPlugin / MapSetFeature2VoxelPlugin (next #2, standalone forms)
+// =================================================================================================
+class GetValueByIndexPlugin final : public PluginBase {
+public:
+    static constexpr const char* kName = "GetValueByIndexPlugin";
+    static FieldList field_list() {   // getValueByIndex.cu:427-430
+        return {{"max_win_num", PluginFieldType::kINT32}, {"voxel_num_set", PluginFieldType::kINT32},
+                {"channel_num", PluginFieldType::kINT32}, {"axis_id", PluginFieldType::kINT32}};
+    }
+    GetValueByIndexPlugin(int S, int max_win, int C, int axis) : S_(S), max_win_(max_win), C_(C), axis_(axis) {}
+    static IPluginV2* from_fields(const PluginFieldCollection* fc) {
+        return new (std::nothrow) GetValueByIndexPlugin(field_int(fc, "voxel_num_set"), field_int(fc, "max_win_num"),
+                                                        field_int(fc, "channel_num"), field_int(fc, "axis_id"));
+    }
+    static IPluginV2* from_bytes(const void* data, size_t len) {
+        Reader r(data, len);
+        const int S = r.get<int>(), mw = r.get<int>(), C = r.get<int>(), ax = r.get<int>();
+        return r.ok() ? new (std::nothrow) GetValueByIndexPlugin(S, mw, C, ax) : nullptr;
+    }
+    size_t getSerializationSize() const noexcept override { return 4 * sizeof(int); }
+    void serialize(void* buf) const noexcept override {            // getValueByIndex.cu:396-402
+        Writer w(buf);
+        w.put(S_); w.put(max_win_); w.put(C_); w.put(axis_);
+    }
+    IPluginV2DynamicExt* clone() const noexcept override {
+        auto* c = new (std::nothrow) GetValueByIndexPlugin(S_, max_win_, C_, axis_);
+        if (c) c->setPluginNamespace(ns_.c_str());
+        return c;
+    }
+    const char* getPluginType() const noexcept override { return kName; }
+    int32_t getNbOutputs() const noexcept override { return 3; }
+    DimsExprs getOutputDimensions(int32_t, const DimsExprs* in, int32_t, IExprBuilder& b) noexcept override {
+        return dims(b, in[0].d[0], {max_win_, S_, C_});
+    }
+    int32_t enqueue(const PluginTensorDesc* in, const PluginTensorDesc*, const void* const* inputs,
+                    void* const* outputs, void*, cudaStream_t stream) noexcept override {
+        dsvt_set_attention_params p{};
+        p.batch = batch_of(in); p.max_set_num = max_win_; p.voxel_num_set = S_; p.channel_num = C_; p.num_heads = 8;
+        p.max_pillars_num = in[0].dims.d[1]; p.axis_id = axis_; p.zero_tails = 1;
+        return report(dsvt_get_value_by_index_launch(
+            &p, static_cast<const float*>(inputs[0]), static_cast<const float*>(inputs[1]),
+            static_cast<const int32_t*>(inputs[2]), static_cast<const int32_t*>(inputs[3]),
+            static_cast<float*>(outputs[0]), static_cast<float*>(outputs[1]), static_cast<float*>(outputs[2]), stream),
+            kName);
+    }
+protected:
+    const std::vector<DataType>& io_types() const override {
+        static const std::vector<DataType> t{F, F, I, I, F, F, F};
+        return t;
+    }
+    size_t nb_inputs() const override { return 4; }
+private:
+    int S_, max_win_, C_, axis_;
+};
+
+class MapSetFeature2VoxelPlugin final : public PluginBase {
+public:
+    static constexpr const char* kName = "MapSetFeature2VoxelPlugin";
+    static FieldList field_list() {   // mapSetFeature2voxel.cu:393-397
+        return {{"max_win_num", PluginFieldType::kINT32}, {"voxel_num_set", PluginFieldType::kINT32},
+                {"channel_num", PluginFieldType::kINT32}, {"axis_id", PluginFieldType::kINT32},
+                {"max_pillars_num", PluginFieldType::kINT32}};
+    }
+    MapSetFeature2VoxelPlugin(int S, int max_win, int C, int max_pillars, int axis)
+        : S_(S), max_win_(max_win), C_(C), max_pillars_(max_pillars), axis_(axis) {}
+    static IPluginV2* from_fields(const PluginFieldCollection* fc) {
+        return new (std::nothrow) MapSetFeature2VoxelPlugin(field_int(fc, "voxel_num_set"), field_int(fc, "max_win_num"),
+                                                            field_int(fc, "channel_num"), field_int(fc, "max_pillars_num"),
+                                                            field_int(fc, "axis_id"));
+    }
+    static IPluginV2* from_bytes(const void* data, size_t len) {
+        Reader r(data, len);
+        const int S = r.get<int>(), mw = r.get<int>(), C = r.get<int>(), mp = r.get<int>(), ax = r.get<int>();
+        return r.ok() ? new (std::nothrow) MapSetFeature2VoxelPlugin(S, mw, C, mp, ax) : nullptr;
+    }
+    size_t getSerializationSize() const noexcept override { return 5 * sizeof(int); }
+    void serialize(void* buf) const noexcept override {            // mapSetFeature2voxel.cu:361-368
+        Writer w(buf);
+        w.put(S_); w.put(max_win_); w.put(C_); w.put(max_pillars_); w.put(axis_);
+    }
+    IPluginV2DynamicExt* clone() const noexcept override {
+        auto* c = new (std::nothrow) MapSetFeature2VoxelPlugin(S_, max_win_, C_, max_pillars_, axis_);
+        if (c) c->setPluginNamespace(ns_.c_str());
+        return c;
+    }
+    const char* getPluginType() const noexcept override { return kName; }
+    int32_t getNbOutputs() const noexcept override { return 1; }
+    DimsExprs getOutputDimensions(int32_t, const DimsExprs* in, int32_t, IExprBuilder& b) noexcept override {
+        return dims(b, in[0].d[0], {max_pillars_, C_});
+    }
+    int32_t enqueue(const PluginTensorDesc* in, const PluginTensorDesc*, const void* const* inputs,
+                    void* const* outputs, void*, cudaStream_t stream) noexcept override {
+        dsvt_set_attention_params p{};
+        p.batch = batch_of(in); p.max_set_num = max_win_; p.voxel_num_set = S_; p.channel_num = C_; p.num_heads = 8;
+        p.max_pillars_num = max_pillars_; p.axis_id = axis_; p.zero_tails = 1;
+        return report(dsvt_map_set_feature2voxel_launch(
+            &p, static_cast<const float*>(inputs[0]), static_cast<const int32_t*>(inputs[1]),
+            static_cast<const int32_t*>(inputs[2]), static_cast<float*>(outputs[0]), stream), kName);
+    }
+protected:
+    const std::vector<DataType>& io_types() const override {
+        static const std::vector<DataType> t{F, I, I, F};
+        return t;
+    }
+    size_t nb_inputs() const override { return 3; }
+private:
+    int S_, max_win_, C_, max_pillars_, axis_;
+};
+
+// =================================================================================================
+// SetAttentionPlugin -- NEW: replaces the ~25-layer TensorRT sub-graph built by multHeadAttention()
+// (src/dsvt-ai-trt.cpp:288-458).  Inputs q,k,v [B,max_sets,S,C], mask [B,max_sets,heads,S] and
+// (optional 5th input) set_num [B]; output [B,max_sets,S,C].  Weights travel as creator fields in
+// the PyTorch layouts the reference's loader produces (include/helper.h:367-433).
+// Serialised: max_set_num, voxel_num_set, channel_num, num_heads, precision (5 x i32) then
+// in_proj_weight[3C*C], in_proj_bias[3C], out_proj_weight[C*C], out_proj_bias[C] (f32).
+// =================================================================================================
+class SetAttentionPlugin final : public PluginBase {
+public:
+    static constexpr const char* kName = "SetAttentionPlugin";
+    static FieldList field_list() {
+        return {{"max_win_num", PluginFieldType::kINT32}, {"voxel_num_set", PluginFieldType::kINT32},
+                {"channel_num", PluginFieldType::kINT32}, {"num_heads", PluginFieldType::kINT32},
+                {"precision", PluginFieldType::kINT32},
+                {"in_proj_weight", PluginFieldType::kFLOAT32}, {"in_proj_bias", PluginFieldType::kFLOAT32},
+                {"out_proj_weight", PluginFieldType::kFLOAT32}, {"out_proj_bias", PluginFieldType::kFLOAT32}};
+    }
+    SetAttentionPlugin(int max_sets, int S, int C, int heads, int precision, const float* w_in, const float* b_in,
+                       const float* w_out, const float* b_out)
+        : max_sets_(max_sets), S_(S), C_(C), heads_(heads), precision_(precision),
+          w_in_(w_in, w_in + (size_t) 3 * C * C), b_in_(b_in, b_in + 3 * C),
+          w_out_(w_out, w_out + (size_t) C * C), b_out_(b_out, b_out + C) {}
+    ~SetAttentionPlugin() override { release(); }
+    static IPluginV2* from_fields(const PluginFieldCollection* fc) {
+        const PluginField* wi = find_field(fc, "in_proj_weight");
+        const PluginField* bi = find_field(fc, "in_proj_bias");
+        const PluginField* wo = find_field(fc, "out_proj_weight");
+        const PluginField* bo = find_field(fc, "out_proj_bias");
+        const int C = field_int(fc, "channel_num");
+        if (C <= 0 || !wi || !bi || !wo || !bo || !wi->data || !bi->data || !wo->data || !bo->data) return nullptr;
+        return new (std::nothrow) SetAttentionPlugin(
+            field_int(fc, "max_win_num"), field_int(fc, "voxel_num_set"), C, field_int(fc, "num_heads", 0, 8),
+            field_int(fc, "precision", 0, DSVT_ATTN_FP32), static_cast<const float*>(wi->data),
+            static_cast<const float*>(bi->data), static_cast<const float*>(wo->data), static_cast<const float*>(bo->data));
+    }
+    static IPluginV2* from_bytes(const void* data, size_t len) {
+        Reader r(data, len);
+        const int ms = r.get<int>(), S = r.get<int>(), C = r.get<int>(), H = r.get<int>(), prec = r.get<int>();
+        if (!r.ok() || C <= 0 || C > 4096 || r.left() < ((size_t) 4 * C * C + 4 * C) * sizeof(float)) return nullptr;
+        std::vector<float> wi((size_t) 3 * C * C), bi(3 * C), wo((size_t) C * C), bo(C);
+        r.get_array(wi.data(), wi.size()); r.get_array(bi.data(), bi.size());
+        r.get_array(wo.data(), wo.size()); r.get_array(bo.data(), bo.size());
+        return new (std::nothrow) SetAttentionPlugin(ms, S, C, H, prec, wi.data(), bi.data(), wo.data(), bo.data());
+    }
+    size_t getSerializationSize() const noexcept override {
+        return 5 * sizeof(int) + ((size_t) 4 * C_ * C_ + 4 * C_) * sizeof(float);
+    }
+    void serialize(void* buf) const noexcept override {
+        Writer w(buf);
+        w.put(max_sets_); w.put(S_); w.put(C_); w.put(heads_); w.put(precision_);
+        w.put_array(w_in_.data(), w_in_.size()); w.put_array(b_in_.data(), b_in_.size());
+        w.put_array(w_out_.data(), w_out_.size()); w.put_array(b_out_.data(), b_out_.size());
+    }
+    IPluginV2DynamicExt* clone() const noexcept override {
+        auto* c = new (std::nothrow) SetAttentionPlugin(max_sets_, S_, C_, heads_, precision_, w_in_.data(),
+                                                        b_in_.data(), w_out_.data(), b_out_.data());
+        if (c) c->setPluginNamespace(ns_.c_str());
+        return c;
+    }
+    int32_t initialize() noexcept override { return upload(); }
+    void terminate() noexcept override { release(); }
+    const char* getPluginType() const noexcept override { return kName; }
+    int32_t getNbOutputs() const noexcept override { return 1; }
+    DimsExprs getOutputDimensions(int32_t, const DimsExprs* in, int32_t, IExprBuilder& b) noexcept override {
+        return dims(b, in[0].d[0], {max_sets_, S_, C_});
+    }
+    bool supportsFormatCombination(int32_t pos, const PluginTensorDesc* io, int32_t nbIn, int32_t nbOut) noexcept override {
+        if (pos < 0 || pos >= nbIn + nbOut || io[pos].format != TensorFormat::kLINEAR) return false;
+        if (nbIn == 5 && pos == 4) return io[pos].type == I;      // optional set_num
+        return io[pos].type == F;
+    }
+    DataType getOutputDataType(int32_t, const DataType*, int32_t) const noexcept override { return F; }
+    int32_t enqueue(const PluginTensorDesc* in, const PluginTensorDesc*, const void* const* inputs,
+                    void* const* outputs, void* ws, cudaStream_t stream) noexcept override {
+        if (upload() != 0) return DSVT_ERR_CUDA;
+        dsvt_set_attention_params p{};
+        p.batch = batch_of(in); p.max_set_num = max_sets_; p.voxel_num_set = S_; p.channel_num = C_;
+        p.num_heads = heads_; p.precision = precision_; p.zero_tails = 1;
+        // a 5th input (set_num) is detected by the mask descriptor being followed by a rank-1 int tensor;
+        // TensorRT passes nbInputs only to the build-time calls, so the shell records it in configurePlugin
+        const int32_t* set_num = nb_inputs_seen_ == 5 ? static_cast<const int32_t*>(inputs[4]) : nullptr;
+        return report(dsvt_set_attention_launch(&p, dev_, static_cast<const float*>(inputs[0]),
+                                                static_cast<const float*>(inputs[1]), static_cast<const float*>(inputs[2]),
+                                                static_cast<const float*>(inputs[3]), set_num,
+                                                static_cast<float*>(outputs[0]), ws, 0, stream), kName);
+    }
+    void configurePlugin(const DynamicPluginTensorDesc*, int32_t nbInputs, const DynamicPluginTensorDesc*,
+                         int32_t) noexcept override { nb_inputs_seen_ = nbInputs; }
+    void set_nb_inputs(int n) { nb_inputs_seen_ = n; }
+protected:
+    const std::vector<DataType>& io_types() const override {
+        static const std::vector<DataType> t{F, F, F, F, F};
+        return t;
+    }
+    size_t nb_inputs() const override { return 4; }
+private:
+    int upload() {
+        if (dev_) return 0;
+        dev_ = dsvt_attention_weights_create(C_, heads_, w_in_.data(), b_in_.data(), w_out_.data(), b_out_.data());
+        return dev_ ? 0 : 1;
+    }
+    void release() {
+        if (dev_) { dsvt_attention_weights_destroy(dev_); dev_ = nullptr; }
+    }
+    int max_sets_, S_, C_, heads_, precision_;
+    std::vector<float> w_in_, b_in_, w_out_, b_out_;
+    dsvt_attention_weights* dev_ = nullptr;
+    int nb_inputs_seen_ = 4;
+};
+
+// registration: from the library only (the reference registers from two images)
+using Points2FeaturesPluginCreator = CreatorBase<Points2FeaturesPlugin>;
+using WindowPartitionPluginCreator = CreatorBase<WindowPartitionPlugin>;
+using GetSetPluginCreator = CreatorBase<GetSetPlugin>;
+using GeluPluginCreator = CreatorBase<GeluPlugin>;
+using LayerNormPluginCreator = CreatorBase<LayerNormPlugin>;
+using FilterBoxByScorePluginCreator = CreatorBase<FilterBoxByScorePlugin>;
+using GetValueByIndexPluginCreator = CreatorBase<GetValueByIndexPlugin>;
+using MapSetFeature2VoxelPluginCreator = CreatorBase<MapSetFeature2VoxelPlugin>;
+using SetAttentionPluginCreator = CreatorBase<SetAttentionPlugin>;
+
+REGISTER_TENSORRT_PLUGIN(Points2FeaturesPluginCreator);
+REGISTER_TENSORRT_PLUGIN(WindowPartitionPluginCreator);
+REGISTER_TENSORRT_PLUGIN(GetSetPluginCreator);
+REGISTER_TENSORRT_PLUGIN(GeluPluginCreator);
+REGISTER_TENSORRT_PLUGIN(LayerNormPluginCreator);
+REGISTER_TENSORRT_PLUGIN(FilterBoxByScorePluginCreator);
+REGISTER_TENSORRT_PLUGIN(GetValueByIndexPluginCreator);
+REGISTER_TENSORRT_PLUGIN(MapSetFeature2VoxelPluginCreator);
+REGISTER_TENSORRT_PLUGIN(SetAttentionPluginCreator);
+
+}  // namespace dsvt_plugins

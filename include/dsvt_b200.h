@@ -1,0 +1,266 @@
+/*
+ * dsvt_b200.h -- C ABI of the B200-native DSVT hot path.
+ *
+ * Every entry point replaces the device work of ONE reference TensorRT plugin
+ * `enqueue` (or, for the set attention, of the TensorRT layer sub-graph built by
+ * multHeadAttention()).  Tensors are plain device pointers with exactly the
+ * reference's layouts; valid counts travel as device-side int32 (never synced
+ * to the host); all work is enqueued on the caller's stream; nothing throws.
+ * File:line citations are relative to the reference tree (jingyue202205/DSVT-AI-TRT
+ * @15b31c3).
+ *
+ * The `batch` member of every params struct is an extension: the reference
+ * kernels are batch-1.  With batch = B every tensor carries a
+ * leading B dimension with the reference's static capacities as strides and the
+ * count tensors hold B entries; B = 1 is the reference contract.
+ *
+ * Return value: DSVT_OK (0) on success, non-zero otherwise (the reference
+ * abort()s on CUDA errors -- getSet.cu:8-19; we return a code instead).
+ */
+#ifndef DSVT_B200_H
+#define DSVT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSVT_B200_ABI_VERSION 1
+
+typedef struct CUstream_st* dsvt_stream_t; /* == cudaStream_t */
+
+enum {
+    DSVT_OK = 0,
+    DSVT_ERR_INVALID_ARGUMENT = 1,
+    DSVT_ERR_CUDA = 2,
+    DSVT_ERR_WORKSPACE_TOO_SMALL = 3,
+    DSVT_ERR_UNSUPPORTED = 4
+};
+
+/* version / diagnostics */
+int dsvt_abi_version(void);
+const char* dsvt_last_error(void);          /* thread-local, human readable */
+int dsvt_device_sm_count(void);
+/* number of kernel launches (incl. memset nodes) issued by this library in this process */
+uint64_t dsvt_launch_count(void);
+
+/* ------------------------------------------------------------------------ *
+ * a1  Points2FeaturesPlugin::enqueue           plugins/src/points2Features.cu:896-990
+ *     (kernels :669-705, :732-766, :792-865)
+ * ------------------------------------------------------------------------ */
+typedef struct dsvt_points2features_params {
+    int32_t batch;
+    int32_t max_points_num;              /* rows of `points` per frame          (MAX_POINTS_NUM 50000)   */
+    int32_t max_points_num_voxel_filter; /* rows of `point_features` per frame  (MAX_POINTS_NUM_1 30000) */
+    int32_t max_pillars_num;             /* (MAX_PILLARS_NUM 10000) */
+    int32_t point_feature_num;           /* must be 4  */
+    int32_t feature_num;                 /* must be 10 */
+    int32_t max_num_points_per_voxel;    /* <= 64; reference 48 */
+    float x_min, x_max, y_min, y_max, z_min, z_max;
+    float voxel_x, voxel_y, voxel_z;
+    int32_t grid_x, grid_y, grid_z;      /* grid_z must be 1 (pillars) */
+    int32_t zero_tails;                  /* 1: rows beyond the valid counts are zero-filled (reference contract) */
+} dsvt_points2features_params;
+
+size_t dsvt_points2features_workspace_size(const dsvt_points2features_params* p);
+/*
+ * in : points [B,max_points_num,4] f32 ; points_size [B] i32
+ * out: point_features [B,max_points_num_voxel_filter,10] f32
+ *      point_index_in_voxel [B,max_pillars_num,max_num_points_per_voxel] i32 (row ids into point_features)
+ *      coords [B,max_pillars_num,4] i32 = (0,0,y,x)
+ *      point_num_in_voxel [B,max_pillars_num] i32 ; pillar_num [B] i32 ; point_num [B] i32
+ * Order is canonical and deterministic: pillars ascending y*grid_x+x,
+ * points of a pillar ascending input index (lowest 48 kept), rows pillar-major.
+ */
+int dsvt_points2features_launch(const dsvt_points2features_params* p,
+                                const float* points, const int32_t* points_size,
+                                float* point_features, int32_t* point_index_in_voxel, int32_t* coords,
+                                int32_t* point_num_in_voxel, int32_t* pillar_num, int32_t* point_num,
+                                void* workspace, size_t workspace_bytes, dsvt_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * (next #1) WindowPartitionPlugin::enqueue     plugins/src/windowPartition.cu:397-470 (kernel :278-381)
+ * ------------------------------------------------------------------------ */
+typedef struct dsvt_window_partition_params {
+    int32_t batch;
+    int32_t max_pillars_num;
+    int32_t max_win_num;
+    int32_t max_voxel_num_per_win;
+    int32_t sparse_shape_x, sparse_shape_y, sparse_shape_z;
+    int32_t win_shape_x, win_shape_y, win_shape_z;
+    int32_t shift_x, shift_y, shift_z;
+    int32_t zero_tails;
+} dsvt_window_partition_params;
+
+size_t dsvt_window_partition_workspace_size(const dsvt_window_partition_params* p);
+/*
+ * in : coords [B,max_pillars_num,4] i32 (0,z,y,x) ; voxel_num [B]
+ * out: global_index [B,max_win_num,max_voxel_num_per_win] i32
+ *      coors_in_win [B,max_win_num,max_voxel_num_per_win,3] i32 (z,y,x)
+ *      voxel_num_in_win [B,max_win_num] i32 ; win_num [B] i32
+ *      coors_in_win_2d [B,max_pillars_num,3] i32 ; coors_in_win_x_y [B,max_pillars_num,2] f32
+ * Canonical order: windows ascending dense window index, voxels ascending voxel id.
+ */
+int dsvt_window_partition_launch(const dsvt_window_partition_params* p,
+                                 const int32_t* coords, const int32_t* voxel_num,
+                                 int32_t* global_index, int32_t* coors_in_win, int32_t* voxel_num_in_win,
+                                 int32_t* win_num, int32_t* coors_in_win_2d, float* coors_in_win_x_y,
+                                 void* workspace, size_t workspace_bytes, dsvt_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * a2  GetSetPlugin::enqueue                    plugins/src/getSet.cu:629-704
+ *     (kernels :326-350, :369-422, :444-495, :517-567, :589-609)
+ * ------------------------------------------------------------------------ */
+typedef struct dsvt_get_set_params {
+    int32_t batch;
+    int32_t voxel_num_set;          /* 36 */
+    int32_t max_win_num;            /* capacity of windows AND of sets (SURVEY.md A-6 vii) */
+    int32_t max_voxel_num_per_win;  /* 576 */
+    int32_t win_shape_x, win_shape_y, win_shape_z;
+    int32_t num_heads;              /* NUM_HEADS 8 (params.h:73) */
+    int32_t zero_tails;
+} dsvt_get_set_params;
+
+size_t dsvt_get_set_workspace_size(const dsvt_get_set_params* p);
+/*
+ * in : global_index [B,max_win_num,max_voxel_num_per_win] i32 ; coors_in_win [..,3] i32 (z,y,x)
+ *      voxel_num_in_win [B,max_win_num] i32 ; win_num [B] i32
+ * out: global_index_in_set [B,2,max_win_num,S] i32 (plane 0 Y-major order, plane 1 X-major)
+ *      set_voxel_mask [B,2,max_win_num,S] f32 (0 or -FLT_MAX)
+ *      set_num [B] i32
+ *      mask_expand_0 / mask_expand_1 [B,max_win_num,num_heads,S] f32
+ * Sets are numbered window-major in ascending window slot (canonical form of the
+ * reference's atomicAdd race, getSet.cu:337).
+ */
+int dsvt_get_set_launch(const dsvt_get_set_params* p,
+                        const int32_t* global_index, const int32_t* coors_in_win,
+                        const int32_t* voxel_num_in_win, const int32_t* win_num,
+                        int32_t* global_index_in_set, float* set_voxel_mask, int32_t* set_num,
+                        float* mask_expand_0, float* mask_expand_1,
+                        void* workspace, size_t workspace_bytes, dsvt_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * a4  GeluPlugin::enqueue                      plugins/src/gelu.cu:227-251 (kernel :201-211)
+ * ------------------------------------------------------------------------ */
+typedef struct dsvt_gelu_params {
+    int32_t batch;
+    int32_t max_pillars_num;
+    int32_t channel_num;            /* 384 */
+    int32_t zero_tails;
+} dsvt_gelu_params;
+/* in: x [B,max_pillars_num,C] f32 ; voxel_num [B] i32 -> out same shape */
+int dsvt_gelu_launch(const dsvt_gelu_params* p, const float* x, const int32_t* voxel_num, float* out,
+                     dsvt_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * a5  LayerNormPlugin::enqueue                 plugins/src/layerNorm.cu:357-402
+ *     (kernels :261-279, :297-309, :326-338)
+ * ------------------------------------------------------------------------ */
+typedef struct dsvt_layer_norm_params {
+    int32_t batch;
+    int32_t max_pillars_num;
+    int32_t channel_num;            /* 192 */
+    float eps;                      /* the reference runs with 0.0 */
+    int32_t zero_tails;
+} dsvt_layer_norm_params;
+/*
+ * in: x [B,max_pillars_num,C] f32 ; voxel_num [B] ; gamma, beta [C] f32 (device)
+ * residual: optional second addend with x's shape (NULL = reference behaviour).  When given the
+ * kernel normalises x + residual, i.e. it absorbs the addElementWise(kSUM) that precedes every
+ * LayerNorm in the reference graph (src/dsvt-ai-trt.cpp:669-697).
+ */
+int dsvt_layer_norm_launch(const dsvt_layer_norm_params* p, const float* x, const float* residual,
+                           const int32_t* voxel_num, const float* gamma, const float* beta, float* out,
+                           dsvt_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * a6  FilterBoxByScorePlugin::enqueue          plugins/src/filterBoxByScore.cu:328-379 (kernel :266-309)
+ * ------------------------------------------------------------------------ */
+typedef struct dsvt_filter_box_params {
+    int32_t batch;
+    int32_t max_top_k;              /* 500 */
+    float x_min, x_max, y_min, y_max, z_min, z_max;
+    float voxel_x, voxel_y, voxel_z;
+    float score_threshold;
+    int32_t zero_tails;
+} dsvt_filter_box_params;
+/*
+ * in : scores [B,K] f32 ; classes, xs, ys [B,K] i32 ; center [B,K,2] ; center_z [B,K] ;
+ *      angle [B,K] ; dim [B,K,3] f32
+ * out: boxes [B,K,9] f32 (x,y,z,dx,dy,dz,angle,class,score), valid [B] i32.
+ * Kept candidates are appended in ascending candidate index (canonical form of the
+ * atomicAdd order, filterBoxByScore.cu:295).
+ */
+int dsvt_filter_box_launch(const dsvt_filter_box_params* p,
+                           const float* scores, const int32_t* classes, const int32_t* xs, const int32_t* ys,
+                           const float* center, const float* center_z, const float* angle, const float* dim,
+                           float* boxes, int32_t* valid, dsvt_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * a3  multHeadAttention()                      src/dsvt-ai-trt.cpp:288-458
+ *     (+ next #2: GetValueByIndex getValueByIndex.cu:282-303 and
+ *      MapSetFeature2Voxel mapSetFeature2voxel.cu:258-275 fused in)
+ * ------------------------------------------------------------------------ */
+enum {
+    DSVT_ATTN_FP32 = 0,      /* CUDA-core FP32 contractions (exact-mode reference path on the GPU) */
+    DSVT_ATTN_TF32 = 1,      /* tcgen05 kind::tf32, FP32 accumulate in TMEM                        */
+    DSVT_ATTN_BF16 = 2       /* tcgen05 kind::f16 with BF16 operands, FP32 accumulate (USE_FP16 config) */
+};
+
+typedef struct dsvt_set_attention_params {
+    int32_t batch;
+    int32_t max_set_num;            /* MAX_WIN_NUM 800 */
+    int32_t voxel_num_set;          /* 36 */
+    int32_t channel_num;            /* 192 */
+    int32_t num_heads;              /* 8 */
+    int32_t max_pillars_num;        /* only for the fused entry point */
+    int32_t axis_id;                /* plane of global_index_in_set used by the fused entry point */
+    int32_t precision;              /* DSVT_ATTN_* */
+    int32_t zero_tails;
+} dsvt_set_attention_params;
+
+/* Opaque, device-resident, pre-arranged copy of one attention layer's weights. */
+typedef struct dsvt_attention_weights dsvt_attention_weights;
+/* host pointers, PyTorch layouts: in_proj_weight [3C,C], in_proj_bias [3C], out_proj.weight [C,C], out_proj.bias [C]
+ * (rows 0..C-1 = query, C..2C-1 = key, 2C..3C-1 = value; include/helper.h:367-433) */
+dsvt_attention_weights* dsvt_attention_weights_create(int32_t channel_num, int32_t num_heads,
+                                                      const float* in_proj_weight, const float* in_proj_bias,
+                                                      const float* out_proj_weight, const float* out_proj_bias);
+void dsvt_attention_weights_destroy(dsvt_attention_weights* w);
+
+size_t dsvt_set_attention_workspace_size(const dsvt_set_attention_params* p);
+/*
+ * Plugin-shaped form (drop-in for the multHeadAttention() sub-graph):
+ * in : q, k, v [B,max_set_num,S,C] f32 ; mask [B,max_set_num,num_heads,S] f32 (additive key mask)
+ *      set_num [B] i32 or NULL (NULL = all max_set_num sets, as the reference graph does)
+ * out: [B,max_set_num,S,C] f32
+ */
+int dsvt_set_attention_launch(const dsvt_set_attention_params* p, const dsvt_attention_weights* w,
+                              const float* q, const float* k, const float* v, const float* mask,
+                              const int32_t* set_num, float* out,
+                              void* workspace, size_t workspace_bytes, dsvt_stream_t stream);
+/*
+ * Fused form: q = k = x[idx] + pos[idx], v = x[idx]; result rows are scattered back to voxel rows.
+ * in : x, pos [B,max_pillars_num,C] f32 ; global_index_in_set [B,2,max_set_num,S] i32 ;
+ *      mask [B,max_set_num,num_heads,S] f32 ; set_num [B] ; voxel_num [B]
+ * out: [B,max_pillars_num,C] f32 (rows >= voxel_num zero when zero_tails)
+ */
+int dsvt_set_attention_fused_launch(const dsvt_set_attention_params* p, const dsvt_attention_weights* w,
+                                    const float* x, const float* pos, const int32_t* global_index_in_set,
+                                    const float* mask, const int32_t* set_num, const int32_t* voxel_num,
+                                    float* out, void* workspace, size_t workspace_bytes, dsvt_stream_t stream);
+
+/* standalone forms of the two gather/scatter plugins (next #2), kept for graph compatibility */
+int dsvt_get_value_by_index_launch(const dsvt_set_attention_params* p, const float* x, const float* pos,
+                                   const int32_t* global_index_in_set, const int32_t* set_num,
+                                   float* q, float* k, float* v, dsvt_stream_t stream);
+int dsvt_map_set_feature2voxel_launch(const dsvt_set_attention_params* p, const float* set_features,
+                                      const int32_t* global_index_in_set, const int32_t* set_num,
+                                      float* voxel_features, dsvt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSVT_B200_H */

@@ -1,0 +1,100 @@
+"""Build recipe for the oracle.
+
+* ``build_oracle()``  -- gcc-compiles ``dsvt_oracle.c`` (the C restatement) into
+  ``oracle/_build/libdsvt_oracle.so``.
+* ``build_reference()`` -- when ``/root/reference`` is present (authoring container only),
+  nvcc-compiles the reference's OWN plugin sources, unmodified and in place, against the in-repo
+  TensorRT scaffold header, one shared object per plugin (they define clashing global helpers,
+  SURVEY.md 2.1), each linked with ``oracle/ref_harness.cpp`` (a C harness that drives the plugin
+  through its IPluginCreator / IPluginV2DynamicExt interface).  Outputs go only to ``oracle/_ref/``
+  (git-ignored, shipped to the GPU box by gpurun).  No reference source is copied into the repo.
+  The reference's own CMake build is NOT used (it needs TensorRT + Boost, both absent).
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = "/root/reference"
+STUB = os.path.join(ROOT, "dsvt-ai-trt_b200", "csrc", "trt_stub")
+PLUGIN_DIR = os.path.join(ROOT, "dsvt-ai-trt_b200", "csrc", "plugins")
+
+REF_PLUGINS = [
+    # (source stem, plugin name registered by the reference)
+    ("points2Features", "Points2FeaturesPlugin"),
+    ("windowPartition", "WindowPartitionPlugin"),
+    ("getSet", "GetSetPlugin"),
+    ("getValueByIndex", "GetValueByIndexPlugin"),
+    ("mapSetFeature2voxel", "MapSetFeature2VoxelPlugin"),
+    ("layerNorm", "LayerNormPlugin"),
+    ("gelu", "GeluPlugin"),
+    ("filterBoxByScore", "FilterBoxByScorePlugin"),
+]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources if os.path.exists(s))
+
+
+def build_oracle(verbose=False):
+    out_dir = os.path.join(HERE, "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    src = os.path.join(HERE, "dsvt_oracle.c")
+    out = os.path.join(out_dir, "libdsvt_oracle.so")
+    if _newer(out, [src]):
+        cmd = ["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
+               "-fvisibility=hidden", "-Wall", "-o", out, src, "-lm"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+    return out
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REF, "plugins", "src"))
+
+
+def build_reference(verbose=False):
+    """Returns {plugin stem: path to .so}; only stems that built."""
+    out_dir = os.path.join(HERE, "_ref")
+    built = {}
+    if not reference_available():
+        # GPU box: use whatever was prebuilt and shipped
+        for stem, _ in REF_PLUGINS:
+            so = os.path.join(out_dir, f"libref_{stem}.so")
+            if os.path.exists(so):
+                built[stem] = so
+        return built
+    if shutil.which("nvcc") is None:
+        return built
+    os.makedirs(out_dir, exist_ok=True)
+    harness = os.path.join(PLUGIN_DIR, "plugin_c_api.cpp")
+    for stem, _ in REF_PLUGINS:
+        src = os.path.join(REF, "plugins", "src", f"{stem}.cu")
+        so = os.path.join(out_dir, f"libref_{stem}.so")
+        if _newer(so, [src, harness, os.path.join(STUB, "NvInfer.h")]):
+            cmd = ["nvcc", "-std=c++14", "-O2", "-w", "-gencode", "arch=compute_100a,code=sm_100a",
+                   "-Xcompiler", "-fPIC", "-shared",
+                   "-I" + STUB, "-I" + os.path.join(REF, "include"), "-I" + os.path.join(REF, "plugins", "include"),
+                   "-I" + os.path.join(ROOT, "include"),
+                   "-DDSVT_HARNESS_FOR_REFERENCE=1",
+                   "-x", "cu", src, harness, "-o", so, "-lcudart", "-Xlinker", "-Bsymbolic"]
+            if verbose:
+                print(" ".join(cmd))
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                sys.stderr.write(f"[oracle/_ref] {stem}: build failed\n{r.stderr[-2000:]}\n")
+                continue
+        built[stem] = so
+    return built
+
+
+if __name__ == "__main__":
+    print(build_oracle(verbose=True))
+    for k, v in build_reference(verbose=True).items():
+        print(k, v)
