@@ -164,13 +164,17 @@ vox_scan_kernel(const unsigned int* __restrict__ cell_count, const int* __restri
                 const int y = cell / gx, x = cell - y * gx;
                 *reinterpret_cast<int4*>(coords_b + (size_t) pid * 4) = make_int4(0, 0, y, x);  // :755
                 pnv_b[pid] = keep;
+            } else if (pid == max_pillars) {
+                // pillars beyond the capacity are the highest cells, so their rows all lie behind this base:
+                // the emitted rows are exactly [0, e2)
+                point_num[b] = min(e2, max_rows);
             }
             e0 += 1; e1 += (int) a[j]; e2 += min((int) a[j], npv);
         }
     }
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
         pillar_num[b] = min(prefix[0] + tot0, max_pillars);
-        point_num[b] = min(prefix[2] + tot2, max_rows);
+        if (prefix[0] + tot0 <= max_pillars) point_num[b] = min(prefix[2] + tot2, max_rows);
     }
 }
 

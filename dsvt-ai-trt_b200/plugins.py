@@ -161,7 +161,7 @@ class Plugin:
                 shape = [o.dims[i] for i in range(o.nb_dims)]
                 t = torch.empty(shape, dtype=_TORCH[o.dtype], device=dev)
                 if poison is not None:
-                    t.fill_(poison)
+                    t.fill_(poison if t.dtype.is_floating_point else -7)
                 outputs.append(t)
         ia = (_Desc * len(in_descs))(*in_descs)
         oa = (_Desc * len(out_descs))(*out_descs)

@@ -66,7 +66,7 @@ ORACLE_API int oracle_points2features(
         if (!(count > 0)) continue;                                          /* :747 */
         if (count > npv) count = npv;                                        /* :748 */
         const int pid = V++;                                                 /* :751 atomicAdd(pillar_num) */
-        if (pid >= max_pillars) { rows += count; continue; }                 /* capacity guard (SURVEY A-5) */
+        if (pid >= max_pillars) continue;                                    /* capacity guard (SURVEY A-5): dropped pillars emit no rows */
         if (count > max_rows - rows) count = max_rows - rows > 0 ? max_rows - rows : 0;
         point_num_in_voxel[pid] = count;                                     /* :753 */
         coords[pid * 4 + 0] = 0; coords[pid * 4 + 1] = 0;                    /* :755 */

@@ -1,0 +1,347 @@
+"""GPU parity: the sm_100a kernels, called through the C ABI (include/dsvt_b200.h), against the CPU oracle on
+identical inputs.  Integer / index outputs must be BIT-EXACT; float outputs within the stated tolerance."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import pad_points
+from oracle import cpu
+
+pytestmark = pytest.mark.gpu
+
+capi = None
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _capi():
+    global capi
+    capi = importlib.import_module("dsvt-ai-trt_b200.capi")
+    yield
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def voxelise(points, n, cfg, poison=True):
+    vox = capi.Points2Features(cfg)
+    if poison:   # outputs must be fully defined by the kernel (zero tails included)
+        for t in (vox.point_features, vox.point_index_in_voxel, vox.coords, vox.point_num_in_voxel):
+            t.fill_(-7 if t.dtype == torch.int32 else float("nan"))
+    vox(dev(pad_points(points, cfg.max_points_num))[None], torch.tensor([n], dtype=torch.int32, device="cuda"))
+    torch.cuda.synchronize()
+    return vox
+
+
+def check_voxeliser(points, n, cfg, feat_tol=1e-5):
+    vox = voxelise(points, n, cfg)
+    o = cpu.points2features(pad_points(points, cfg.max_points_num), n, cfg)
+    assert int(vox.pillar_num[0]) == o["pillar_num"]
+    assert int(vox.point_num[0]) == o["point_num"]
+    assert np.array_equal(vox.coords[0].cpu().numpy(), o["coords"])
+    assert np.array_equal(vox.point_num_in_voxel[0].cpu().numpy(), o["point_num_in_voxel"])
+    assert np.array_equal(vox.point_index_in_voxel[0].cpu().numpy(), o["point_index_in_voxel"])
+    f = vox.point_features[0].cpu().numpy()
+    assert not np.isnan(f).any()
+    # channels 0..3 are copies of the kept input points -> bit exact; 4..9 are f32/f64 arithmetic
+    assert np.array_equal(f[:, :4], o["point_features"][:, :4])
+    assert np.abs(f - o["point_features"]).max() <= feat_tol
+    return vox, o
+
+
+# ------------------------------------------------------------------------------------------------
+def test_voxeliser_reference_frame(frame0, cfgs, kat):
+    vox, o = check_voxeliser(frame0, len(frame0), cfgs.REFERENCE)
+    assert int(vox.pillar_num[0]) == kat["000000"]["pillars"] == 5504
+    assert int(vox.point_num[0]) == kat["000000"]["kept_points"]
+
+
+@pytest.mark.parametrize("gen,n", [("ring_lidar", 200000), ("uniform_disc", 200000), ("ring_lidar", 50000)])
+def test_voxeliser_waymo_shape(pkg, cfgs, gen, n):
+    cfg = cfgs.WAYMO.with_(max_pillars_num=110000)
+    pts = getattr(pkg.synth, gen)(n, seed=1)
+    check_voxeliser(pts, n, cfg)
+
+
+def test_voxeliser_pillar_030(pkg, cfgs):
+    check_voxeliser(pkg.synth.ring_lidar(200000, seed=2), 200000, cfgs.WAYMO_030)
+
+
+def test_voxeliser_edge_cases(cfgs):
+    cfg = cfgs.REFERENCE
+    rng = np.random.default_rng(5)
+    # empty cloud
+    vox, _ = check_voxeliser(np.zeros((0, 4), np.float32), 0, cfg)
+    assert int(vox.pillar_num[0]) == 0 and float(vox.point_features.abs().sum()) == 0
+    # every point out of range (z too high / on the exclusive upper edges)
+    pts = np.array([[0, 0, 3.0, 1], [74.88, 0, 0, 1], [0, 74.88, 0, 1], [-74.89, 0, 0, 1], [0, 0, -5.01, 1]], np.float32)
+    vox, _ = check_voxeliser(pts, len(pts), cfg)
+    assert int(vox.pillar_num[0]) == 0
+    # inclusive lower edges, duplicates, one pillar with far more than 48 points (keeps the lowest indices)
+    heavy = np.tile(np.array([[10.01, -3.33, 0.5, 9]], np.float32), (5000, 1))
+    heavy[:, 3] = np.arange(5000)
+    heavy[:, 2] = rng.uniform(-4, 2, 5000)
+    pts = np.concatenate([np.array([[-74.88, -74.88, -5.0, 3]], np.float32), heavy,
+                          rng.uniform(-70, 70, (3000, 4)).astype(np.float32) * np.array([1, 1, 0.03, 1], np.float32)])
+    check_voxeliser(pts, len(pts), cfg)
+    # points_size smaller than the data present and larger than the capacity
+    check_voxeliser(pts, 100, cfg)
+    big = rng.uniform(-70, 70, (60000, 4)).astype(np.float32) * np.array([1, 1, 0.03, 1], np.float32)
+    check_voxeliser(big, 60000, cfg)   # > MAX_POINTS_NUM: truncated like the reference (points2Features.cu:716)
+    # pillar and row capacities exceeded -> deterministic clamp, no out-of-bounds writes
+    vox, o = check_voxeliser(big, 50000, cfg.with_(max_pillars_num=1000))
+    assert int(vox.pillar_num[0]) == 1000 and 1000 <= int(vox.point_num[0]) < 2000   # dropped pillars emit no rows
+    vox, o = check_voxeliser(big, 50000, cfg.with_(max_pillars_num=40000, max_points_num_voxel_filter=1500))
+    assert int(vox.point_num[0]) == 1500 and int(vox.pillar_num[0]) > 1500          # later pillars keep 0 points
+
+
+def test_voxeliser_batched(pkg, cfgs):
+    """Batch extension: B frames in one launch == B single-frame launches."""
+    cfg = cfgs.WAYMO
+    B = 3
+    clouds = [pkg.synth.ring_lidar(180000 - 7000 * i, seed=10 + i) for i in range(B)]
+    pts = np.stack([pad_points(c, cfg.max_points_num) for c in clouds])
+    sizes = torch.tensor([len(c) for c in clouds], dtype=torch.int32, device="cuda")
+    vb = capi.Points2Features(cfg, batch=B)
+    vb(dev(pts), sizes)
+    torch.cuda.synchronize()
+    for i, c in enumerate(clouds):
+        o = cpu.points2features(pad_points(c, cfg.max_points_num), len(c), cfg)
+        assert int(vb.pillar_num[i]) == o["pillar_num"] and int(vb.point_num[i]) == o["point_num"]
+        assert np.array_equal(vb.coords[i].cpu().numpy(), o["coords"])
+        assert np.array_equal(vb.point_index_in_voxel[i].cpu().numpy(), o["point_index_in_voxel"])
+        assert np.abs(vb.point_features[i].cpu().numpy() - o["point_features"]).max() <= 1e-5
+
+
+def test_voxeliser_deterministic(pkg, cfgs):
+    cfg = cfgs.WAYMO
+    pts = pkg.synth.uniform_disc(250000, seed=4)
+    a = voxelise(pts, len(pts), cfg.with_(max_pillars_num=110000))
+    ref = [t.clone() for t in (a.point_features, a.point_index_in_voxel, a.coords, a.point_num_in_voxel)]
+    for _ in range(3):
+        b = voxelise(pts, len(pts), cfg.with_(max_pillars_num=110000))
+        for r, t in zip(ref, (b.point_features, b.point_index_in_voxel, b.coords, b.point_num_in_voxel)):
+            assert torch.equal(r, t)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_partition(o, cfg, which):
+    wp = capi.WindowPartition(cfg, which)
+    for t in (wp.global_index, wp.coors_in_win, wp.voxel_num_in_win, wp.coors_in_win_2d):
+        t.fill_(-7)
+    wp.coors_in_win_x_y.fill_(float("nan"))
+    wp(dev(o["coords"])[None], torch.tensor([o["pillar_num"]], dtype=torch.int32, device="cuda"))
+    gs = capi.GetSet(cfg, which)
+    gs.global_index_in_set.fill_(-7)
+    for t in (gs.set_voxel_mask, gs.mask_expand_0, gs.mask_expand_1):
+        t.fill_(float("nan"))
+    gs(wp.global_index, wp.coors_in_win, wp.voxel_num_in_win, wp.win_num)
+    torch.cuda.synchronize()
+    return wp, gs
+
+
+def check_partition(o, cfg, which):
+    wp, gs = run_partition(o, cfg, which)
+    owp = cpu.window_partition(o["coords"], o["pillar_num"], cfg, which)
+    assert int(wp.win_num[0]) == owp["win_num"]
+    for name in ("global_index", "coors_in_win", "voxel_num_in_win", "coors_in_win_2d", "coors_in_win_x_y"):
+        assert np.array_equal(getattr(wp, name)[0].cpu().numpy(), owp[name]), name
+    ogs = cpu.get_set(owp["global_index"], owp["coors_in_win"], owp["voxel_num_in_win"], owp["win_num"], cfg, which)
+    assert int(gs.set_num[0]) == ogs["set_num"]
+    assert np.array_equal(gs.global_index_in_set[0].cpu().numpy(), ogs["global_index_in_set"])
+    for name in ("set_voxel_mask", "mask_expand_0", "mask_expand_1"):   # compare bit patterns (0 / -FLT_MAX)
+        assert np.array_equal(getattr(gs, name)[0].cpu().numpy().view(np.uint32), ogs[name].view(np.uint32)), name
+    return owp, ogs
+
+
+def test_partition_reference_frame(frame0, cfgs, kat):
+    cfg = cfgs.REFERENCE
+    o = cpu.points2features(pad_points(frame0, cfg.max_points_num), len(frame0), cfg)
+    for which, tag in ((0, "win12"), (1, "win24_shift6")):
+        owp, ogs = check_partition(o, cfg, which)
+        assert owp["win_num"] == kat["000000"][tag]["windows"] and ogs["set_num"] == kat["000000"][tag]["sets"]
+
+
+@pytest.mark.parametrize("S", [24, 36, 48])
+def test_partition_waymo_shape(pkg, cfgs, S):
+    cfg = cfgs.WAYMO.with_(voxel_num_set=S, max_pillars_num=110000, max_win_num=8192)
+    pts = pkg.synth.uniform_disc(200000, seed=3)
+    o = cpu.points2features(pad_points(pts, cfg.max_points_num), len(pts), cfg)
+    for which in (0, 1):
+        check_partition(o, cfg, which)
+
+
+def test_get_set_edge_cases(cfgs):
+    cfg = cfgs.REFERENCE.with_(max_win_num=64)
+    rng = np.random.default_rng(2)
+
+    def run(gi, cw, vn, wn, which=0):
+        gs = capi.GetSet(cfg, which)
+        gs.global_index_in_set.fill_(-7)
+        gs(dev(gi)[None], dev(cw)[None], dev(vn)[None], torch.tensor([wn], dtype=torch.int32, device="cuda"))
+        torch.cuda.synchronize()
+        ref = cpu.get_set(gi, cw, vn, wn, cfg, which)
+        assert int(gs.set_num[0]) == ref["set_num"]
+        assert np.array_equal(gs.global_index_in_set[0].cpu().numpy(), ref["global_index_in_set"])
+        assert np.array_equal(gs.mask_expand_1[0].cpu().numpy().view(np.uint32), ref["mask_expand_1"].view(np.uint32))
+        return ref
+
+    mw, mv = cfg.max_win_num, cfg.max_voxel_num_per_win
+    gi = np.zeros((mw, mv), np.int32)
+    cw = np.zeros((mw, mv, 3), np.int32)
+    vn = np.zeros((mw,), np.int32)
+    assert run(gi, cw, vn, 0)["set_num"] == 0                               # no windows at all
+    # windows with 1, exactly S, S+1 and the maximum 144 voxels (12x12 window completely full)
+    nid = 0
+    for w, n in enumerate([1, 36, 37, 144, 35, 72, 73]):
+        cells = rng.permutation(144)[:n]                                   # unsorted on purpose
+        cw[w, :n, 1], cw[w, :n, 2] = cells // 12, cells % 12
+        gi[w, :n] = nid + rng.permutation(n)
+        vn[w] = n
+        nid += n
+    ref = run(gi, cw, vn, 7)
+    assert ref["set_num"] == 1 + 1 + 2 + 4 + 1 + 2 + 3
+    # more sets than max_win_num: clamped, nothing written out of bounds
+    for w in range(mw):
+        n = 40
+        cells = rng.permutation(144)[:n]
+        cw[w, :n, 1], cw[w, :n, 2] = cells // 12, cells % 12
+        gi[w, :n] = w * 40 + np.arange(n)
+        vn[w] = n
+    assert run(gi, cw, vn, mw)["set_num"] == mw
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("V,cap", [(5504, 10000), (0, 10000), (10000, 10000), (30611, 40000), (1, 7)])
+def test_gelu(V, cap):
+    rng = np.random.default_rng(V)
+    x = (rng.standard_normal((cap, 384)) * 4).astype(np.float32)
+    x[0, :8] = [0.0, -0.0, 1e-30, -1e-30, 30.0, -30.0, 88.0, -88.0]
+    out = torch.full((cap, 384), float("nan"), device="cuda")
+    capi.gelu(dev(x), torch.tensor([V], dtype=torch.int32, device="cuda"), out=out)
+    ref = cpu.gelu(x, V)
+    got = out.cpu().numpy()
+    assert np.all(got[V:] == 0)
+    # tolerance: f32 logistic form vs the reference's double tanh -- 1e-6 abs + 2e-6 rel (<< 1e-3 bar)
+    assert np.all(np.abs(got - ref) <= 1e-6 + 2e-6 * np.abs(ref))
+
+
+@pytest.mark.parametrize("V,cap,C", [(5504, 10000, 192), (0, 10000, 192), (10000, 10000, 192), (30611, 40000, 192),
+                                     (77, 100, 96)])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_layer_norm(V, cap, C, with_res):
+    rng = np.random.default_rng(V + C)
+    x = (rng.standard_normal((cap, C)) * 3 + 0.7).astype(np.float32)
+    res = rng.standard_normal((cap, C)).astype(np.float32) if with_res else None
+    gamma, beta = rng.standard_normal(C).astype(np.float32), rng.standard_normal(C).astype(np.float32)
+    out = torch.full((cap, C), float("nan"), device="cuda")
+    capi.layer_norm(dev(x), torch.tensor([V], dtype=torch.int32, device="cuda"), dev(gamma), dev(beta), eps=0.0,
+                    residual=dev(res) if with_res else None, out=out)
+    ref = cpu.layer_norm(x, V, gamma, beta, 0.0, residual=res)
+    got = out.cpu().numpy()
+    assert np.all(got[V:] == 0)
+    # tolerance: the reference sums sequentially in f32, we tree-reduce; 2e-5 abs on O(1..10) outputs
+    assert np.abs(got - ref).max() <= 2e-5 if V else True
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_filter_box(pkg, cfgs, seed):
+    cfg = cfgs.REFERENCE
+    arrs = list(pkg.synth.head_candidates(cfg.max_top_k, seed=seed))
+    if seed == 1:
+        arrs[0][:] = 0.0            # nothing passes the score threshold
+    if seed == 2:
+        arrs[0][:] = 0.9            # everything in range passes
+        arrs[4][:] = 0.5
+        arrs[5][:] = 0.0
+    boxes = torch.full((1, cfg.max_top_k, 9), float("nan"), device="cuda")
+    _, valid = capi.filter_box(cfg, *[dev(a)[None] for a in arrs], boxes=boxes)
+    ref_boxes, ref_valid, _ = cpu.filter_box(*arrs, cfg)
+    assert int(valid[0]) == ref_valid
+    assert np.array_equal(boxes[0].cpu().numpy(), ref_boxes)    # one FMA + copies: bit exact
+
+
+# ------------------------------------------------------------------------------------------------
+def _attn_inputs(n_sets, max_sets, S=36, C=192, H=8, seed=0):
+    rng = np.random.default_rng(seed)
+    q = rng.standard_normal((max_sets, S, C)).astype(np.float32)
+    k = q.copy()
+    v = rng.standard_normal((max_sets, S, C)).astype(np.float32)
+    mask = np.zeros((max_sets, H, S), np.float32)
+    for s in range(max_sets):
+        pad = rng.permutation(S - 1)[: rng.integers(0, S - 1)] + 1
+        mask[s, :, pad] = -np.finfo(np.float32).max
+    w = dict(w_in=(rng.standard_normal((3 * C, C)) * 0.06).astype(np.float32),
+             b_in=(rng.standard_normal(3 * C) * 0.1).astype(np.float32),
+             w_out=(rng.standard_normal((C, C)) * 0.06).astype(np.float32),
+             b_out=(rng.standard_normal(C) * 0.1).astype(np.float32))
+    return q, k, v, mask, w
+
+
+ATTN_TOL = {0: 2e-5}    # DSVT_ATTN_FP32: same f32 arithmetic, different summation order
+
+
+@pytest.mark.parametrize("S", [24, 36, 48])
+def test_set_attention_plugin_form(S):
+    n_sets, max_sets = 37, 50
+    q, k, v, mask, w = _attn_inputs(n_sets, max_sets, S=S, seed=S)
+    k = (k + 0.25 * np.random.default_rng(1).standard_normal(k.shape)).astype(np.float32)   # q != k in general
+    W = capi.AttentionWeights(w["w_in"], w["b_in"], w["w_out"], w["b_out"])
+    out = torch.full((max_sets, S, 192), float("nan"), device="cuda")
+    capi.set_attention(W, dev(q), dev(k), dev(v), dev(mask), torch.tensor([n_sets], dtype=torch.int32, device="cuda"),
+                       out=out, precision=0)
+    ref = cpu.set_attention(q, k, v, mask, n_sets, **w)
+    got = out.cpu().numpy()
+    assert np.all(got[n_sets:] == 0)
+    assert np.abs(got[:n_sets] - ref[:n_sets]).max() <= ATTN_TOL[0]
+    # set_num == NULL -> all max_sets sets are computed, as the reference graph does
+    out2 = capi.set_attention(W, dev(q), dev(k), dev(v), dev(mask), None, precision=0)
+    ref2 = cpu.set_attention(q, k, v, mask, max_sets, **w)
+    assert np.abs(out2.cpu().numpy() - ref2).max() <= ATTN_TOL[0]
+
+
+def test_set_attention_golden(attention_case):
+    c = attention_case
+    W = capi.AttentionWeights(c["w_in"], c["b_in"], c["w_out"], c["b_out"])
+    out = capi.set_attention(W, dev(c["q"]), dev(c["k"]), dev(c["v"]), dev(c["mask"]), None, precision=0)
+    assert np.abs(out.cpu().numpy() - c["out"]).max() <= 2e-5      # torch MHA fixture
+
+
+def test_set_attention_fused_frame(frame0, cfgs):
+    """Fused gather + attention + scatter on the reference frame == oracle gather -> attention -> scatter."""
+    cfg = cfgs.REFERENCE
+    o = cpu.points2features(pad_points(frame0, cfg.max_points_num), len(frame0), cfg)
+    V = o["pillar_num"]
+    rng = np.random.default_rng(11)
+    x = np.zeros((cfg.max_pillars_num, 192), np.float32)
+    pos = np.zeros_like(x)
+    x[:V] = rng.standard_normal((V, 192))
+    pos[:V] = rng.standard_normal((V, 192)) * 0.5
+    _, _, _, _, w = _attn_inputs(1, 1, seed=5)
+    W = capi.AttentionWeights(w["w_in"], w["b_in"], w["w_out"], w["b_out"])
+    for which in (0, 1):
+        owp = cpu.window_partition(o["coords"], V, cfg, which)
+        ogs = cpu.get_set(owp["global_index"], owp["coors_in_win"], owp["voxel_num_in_win"], owp["win_num"], cfg, which)
+        ns = ogs["set_num"]
+        for axis in (0, 1):
+            q, k, v = cpu.get_value_by_index(x, pos, ogs["global_index_in_set"], ns, axis)
+            a = cpu.set_attention(q, k, v, ogs["mask_expand_0"], ns, **w)
+            ref = cpu.map_set_feature2voxel(a, ogs["global_index_in_set"], ns, axis, cfg.max_pillars_num)
+            out = torch.full((cfg.max_pillars_num, 192), float("nan"), device="cuda")
+            capi.set_attention_fused(W, dev(x), dev(pos), dev(ogs["global_index_in_set"]), dev(ogs["mask_expand_0"]),
+                                     torch.tensor([ns], dtype=torch.int32, device="cuda"),
+                                     torch.tensor([V], dtype=torch.int32, device="cuda"), axis, out=out, precision=0)
+            got = out.cpu().numpy()
+            assert np.all(got[V:] == 0)
+            assert np.abs(got - ref).max() <= ATTN_TOL[0]
+            # standalone gather / scatter plugins
+            gq, gk, gv = capi.get_value_by_index(dev(x), dev(pos), dev(ogs["global_index_in_set"]),
+                                                 torch.tensor([ns], dtype=torch.int32, device="cuda"), axis)
+            assert np.array_equal(gq.cpu().numpy(), q) and np.array_equal(gk.cpu().numpy(), k)
+            assert np.array_equal(gv.cpu().numpy(), v)
+            sc = capi.map_set_feature2voxel(dev(a), dev(ogs["global_index_in_set"]),
+                                            torch.tensor([ns], dtype=torch.int32, device="cuda"), axis,
+                                            cfg.max_pillars_num)
+            assert np.array_equal(sc.cpu().numpy(), ref)

@@ -1,0 +1,161 @@
+"""The TensorRT plugin shells, driven through the C harness the way TensorRT drives them
+(creator lookup -> createPlugin(fields) -> getOutputDimensions -> getWorkspaceSize -> enqueue ->
+serialize -> deserializePlugin -> clone), against the CPU oracle."""
+import importlib
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import pad_points
+from oracle import cpu
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def plg():
+    return importlib.import_module("dsvt-ai-trt_b200.plugins")
+
+
+@pytest.fixture(scope="module")
+def lib(plg):
+    return plg.PluginLibrary()
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def i32(v):
+    return torch.tensor([v], dtype=torch.int32, device="cuda")
+
+
+def roundtrip(lib, plugin):
+    """serialize -> deserialize -> clone: returns the re-created plugin."""
+    blob = plugin.serialize()
+    again = lib.deserialize(plugin.type, blob)
+    assert again.serialize() == blob
+    c = again.clone()
+    assert c.serialize() == blob and c.type == plugin.type and c.version == "1"
+    return c, blob
+
+
+def test_voxel_generator_plugin(lib, plg, frame0, cfgs):
+    cfg = cfgs.REFERENCE
+    p = plg.add_voxel_generator(lib, cfg.max_points_num, cfg.max_points_num_voxel_filter, cfg.max_pillars_num, 4, 10,
+                                cfg.max_num_points_per_voxel, cfg.x_min, cfg.x_max, cfg.y_min, cfg.y_max, cfg.z_min,
+                                cfg.z_max, cfg.voxel_x, cfg.voxel_y, cfg.voxel_z, cfg.grid_x, cfg.grid_y, cfg.grid_z)
+    assert p.type == "Points2FeaturesPlugin" and p.nb_outputs == 6
+    p2, blob = roundtrip(lib, p)
+    # serialised layout of the reference: 6 x i32, 9 x f32 (xmin,xmax,ymin,ymax,zmin,zmax,vx,vy,vz), 3 x i32
+    assert blob == struct.pack("<6i9f3i", 50000, 30000, 10000, 4, 10, 48, -74.88, 74.88, -74.88, 74.88, -5.0, 3.0,
+                               0.32, 0.32, 8.0, 468, 468, 1)
+    pts = pad_points(frame0, cfg.max_points_num)
+    o = cpu.points2features(pts, len(frame0), cfg)
+    for plugin in (p, p2):
+        outs = plugin.enqueue([dev(pts)[None], i32(len(frame0))], poison=-3)
+        torch.cuda.synchronize()
+        assert [tuple(t.shape) for t in outs] == [(1, 30000, 10), (1, 10000, 48), (1, 10000, 4), (1, 10000, 1), (1,), (1,)]
+        assert [t.dtype for t in outs] == [torch.float32] + [torch.int32] * 5
+        assert int(outs[4][0]) == 5504 and int(outs[5][0]) == o["point_num"]
+        assert np.array_equal(outs[2][0].cpu().numpy(), o["coords"])
+        assert np.array_equal(outs[1][0].cpu().numpy(), o["point_index_in_voxel"])
+        assert np.array_equal(outs[3][0, :, 0].cpu().numpy(), o["point_num_in_voxel"])
+        assert np.abs(outs[0][0].cpu().numpy() - o["point_features"]).max() <= 1e-5
+
+
+def test_window_partition_and_get_set_plugins(lib, plg, frame0, cfgs):
+    cfg = cfgs.REFERENCE
+    o = cpu.points2features(pad_points(frame0, cfg.max_points_num), len(frame0), cfg)
+    for which in (0, 1):
+        wp = plg.add_window_partition(lib, cfg.max_win_num, cfg.max_voxel_num_per_win,
+                                      (cfg.grid_x, cfg.grid_y, cfg.grid_z), cfg.win_shapes[which], cfg.shifts[which])
+        gs = plg.add_get_set_op(lib, cfg.max_win_num, cfg.max_voxel_num_per_win, cfg.voxel_num_set, cfg.win_shapes[which])
+        wp, wblob = roundtrip(lib, wp)
+        gs, gblob = roundtrip(lib, gs)
+        w = cfg.win_shapes[which]
+        s = cfg.shifts[which]
+        assert wblob == struct.pack("<11i", 468, 468, 1, *w, *s, 800, 576)
+        assert gblob == struct.pack("<6i", 36, 800, 576, *w)
+        wouts = wp.enqueue([dev(o["coords"])[None], i32(o["pillar_num"])], poison=-3)
+        gouts = gs.enqueue(wouts[:4], poison=-3)
+        torch.cuda.synchronize()
+        assert [tuple(t.shape) for t in wouts] == [(1, 800, 576), (1, 800, 576, 3), (1, 800), (1,), (1, 10000, 3), (1, 10000, 2)]
+        assert [tuple(t.shape) for t in gouts] == [(1, 2, 800, 36), (1, 2, 800, 36), (1,), (1, 800, 8, 36), (1, 800, 8, 36)]
+        assert [t.dtype for t in gouts] == [torch.int32, torch.float32, torch.int32, torch.float32, torch.float32]
+        owp = cpu.window_partition(o["coords"], o["pillar_num"], cfg, which)
+        ogs = cpu.get_set(owp["global_index"], owp["coors_in_win"], owp["voxel_num_in_win"], owp["win_num"], cfg, which)
+        assert np.array_equal(wouts[0][0].cpu().numpy(), owp["global_index"])
+        assert np.array_equal(wouts[1][0].cpu().numpy(), owp["coors_in_win"])
+        assert np.array_equal(wouts[5][0].cpu().numpy(), owp["coors_in_win_x_y"])
+        assert int(gouts[2][0]) == ogs["set_num"]
+        assert np.array_equal(gouts[0][0].cpu().numpy(), ogs["global_index_in_set"])
+        assert np.array_equal(gouts[1][0].cpu().numpy().view(np.uint32), ogs["set_voxel_mask"].view(np.uint32))
+        assert np.array_equal(gouts[3][0].cpu().numpy().view(np.uint32), ogs["mask_expand_0"].view(np.uint32))
+        assert np.array_equal(gouts[4][0].cpu().numpy().view(np.uint32), ogs["mask_expand_1"].view(np.uint32))
+
+
+def test_gelu_and_layer_norm_plugins(lib, plg, cfgs):
+    cfg = cfgs.REFERENCE
+    rng = np.random.default_rng(0)
+    V = 5504
+    g = plg.add_gelu_op(lib, cfg.max_pillars_num, 384)
+    g, blob = roundtrip(lib, g)
+    assert blob == struct.pack("<2i", 10000, 384)
+    x = (rng.standard_normal((1, cfg.max_pillars_num, 384)) * 3).astype(np.float32)
+    (out,) = g.enqueue([dev(x), i32(V)], poison=float("nan"))
+    ref = cpu.gelu(x[0], V)
+    assert np.all(np.abs(out[0].cpu().numpy() - ref) <= 1e-6 + 2e-6 * np.abs(ref))
+
+    gamma, beta = rng.standard_normal(192).astype(np.float32), rng.standard_normal(192).astype(np.float32)
+    ln = plg.add_layer_norm_op(lib, cfg.max_pillars_num, 192, gamma, beta, eps=1e-5)
+    ln2, blob = roundtrip(lib, ln)
+    # eps is never forwarded by the reference helper ("pes" quirk): serialised eps must be 0.0
+    assert blob[:16] == struct.pack("<3if", 10000, 192, 192, 0.0)
+    assert blob[16:] == gamma.tobytes() + beta.tobytes()
+    x = (rng.standard_normal((1, cfg.max_pillars_num, 192)) * 2 + 1).astype(np.float32)
+    ref = cpu.layer_norm(x[0], V, gamma, beta, 0.0)
+    for plugin in (ln, ln2):
+        (out,) = plugin.enqueue([dev(x), i32(V)], poison=float("nan"))
+        assert np.abs(out[0].cpu().numpy() - ref).max() <= 2e-5
+    assert "pes" in lib.field_names("LayerNormPlugin") and "eps" not in lib.field_names("LayerNormPlugin")
+
+
+def test_filter_box_plugin(lib, plg, pkg, cfgs):
+    cfg = cfgs.REFERENCE
+    fb = plg.add_filter_box_by_score_op(lib, cfg.max_top_k, cfg.x_min, cfg.x_max, cfg.y_min, cfg.y_max, cfg.z_min,
+                                        cfg.z_max, cfg.voxel_x, cfg.voxel_y, cfg.voxel_z, cfg.score_threshold)
+    fb, blob = roundtrip(lib, fb)
+    assert blob == struct.pack("<i10f", 500, -74.88, 74.88, -74.88, 74.88, -5.0, 3.0, 0.32, 0.32, 8.0, 0.3)
+    sc, cl, xs, ys, ce, cz, an, dm = pkg.synth.head_candidates(cfg.max_top_k, seed=4)
+    ins = [dev(sc)[None], dev(cl)[None], dev(xs)[None], dev(ys)[None], dev(ce)[None, None], dev(cz)[None, None, :, None],
+           dev(an)[None, None, :, None], dev(dm)[None, None]]
+    boxes, valid = fb.enqueue(ins, poison=float("nan"))
+    rb, rv, _ = cpu.filter_box(sc, cl, xs, ys, ce, cz, an, dm, cfg)
+    assert tuple(boxes.shape) == (1, 500, 9) and int(valid[0]) == rv
+    assert np.array_equal(boxes[0].cpu().numpy(), rb)
+
+
+def test_set_attention_plugin(lib, plg, attention_case):
+    c = attention_case
+    n, S, C = c["q"].shape
+    p = plg.add_set_attention_op(lib, n, S, C, 8, c["w_in"], c["b_in"], c["w_out"], c["b_out"], precision=0)
+    p2, blob = roundtrip(lib, p)
+    assert len(blob) == 5 * 4 + (4 * C * C + 4 * C) * 4
+    for plugin in (p, p2):
+        (out,) = plugin.enqueue([dev(c["q"])[None], dev(c["k"])[None], dev(c["v"])[None], dev(c["mask"])[None]],
+                                poison=float("nan"))
+        assert np.abs(out[0].cpu().numpy() - c["out"]).max() <= 2e-5
+    # optional 5th input: valid set count
+    (out,) = p.enqueue([dev(c["q"])[None], dev(c["k"])[None], dev(c["v"])[None], dev(c["mask"])[None], i32(2)],
+                       poison=float("nan"))
+    got = out[0].cpu().numpy()
+    assert np.abs(got[:2] - c["out"][:2]).max() <= 2e-5 and np.all(got[2:] == 0)
+
+
+def test_registry_and_formats(lib):
+    names = set(lib.registered())
+    assert {"Points2FeaturesPlugin", "GetSetPlugin", "GeluPlugin", "LayerNormPlugin", "FilterBoxByScorePlugin",
+            "WindowPartitionPlugin", "GetValueByIndexPlugin", "MapSetFeature2VoxelPlugin", "SetAttentionPlugin"} <= names
