@@ -1,0 +1,110 @@
+"""One "hot-path frame": the plugin sequence of SURVEY.md section 8(a) in the reference's graph order
+(src/dsvt-ai-trt.cpp:571-1120, :1684) for ONE point cloud, every launch going through the C ABI.
+
+    a1 Points2Features -> WindowPartition x2 -> a2 GetSet x2
+    4 DSVT blocks x 2 encoders: a3 set attention (gather/scatter fused) -> a5 LayerNorm(y + x)
+                                -> [FFN linear 192->384: TensorRT-native glue, NOT part of the hot path]
+                                -> a4 GELU -> [FFN linear 384->192: glue] -> a5 LayerNorm -> a5 LayerNorm
+                 + a5 LayerNorm per block                                   (7 LayerNorms per block, 28 per frame)
+    a6 FilterBoxByScore on the CenterHead's top-500 candidates
+
+The TensorRT-native layers between the plugins (PFN, pos-embed MLPs, FFN linears, BEV backbone, head; SURVEY.md
+section 8(f) "next" rows) are not executed: their outputs are stood in by fixed synthetic tensors of the right
+shape, so every hot-path plugin runs on full-size, data-dependent inputs (voxel counts, set indices and masks
+come from the real voxeliser / partition of the frame's cloud).
+"""
+import numpy as np
+import torch
+
+from . import capi
+
+
+class FrameWeights:
+    """Random-init weights of the 8 attention layers and 28 LayerNorms (no checkpoint is reachable offline)."""
+
+    def __init__(self, cfg, seed=0, device="cuda"):
+        rng = np.random.default_rng(seed)
+        C = cfg.channel_num
+        self.attn = []
+        for _ in range(cfg.num_blocks * 2):
+            self.attn.append(capi.AttentionWeights(
+                (rng.standard_normal((3 * C, C)) * 0.06).astype(np.float32),
+                (rng.standard_normal(3 * C) * 0.02).astype(np.float32),
+                (rng.standard_normal((C, C)) * 0.06).astype(np.float32),
+                (rng.standard_normal(C) * 0.02).astype(np.float32), C, cfg.num_heads))
+        n_ln = cfg.num_blocks * 7
+        self.gamma = torch.from_numpy((1.0 + 0.1 * rng.standard_normal((n_ln, C))).astype(np.float32)).to(device)
+        self.beta = torch.from_numpy((0.1 * rng.standard_normal((n_ln, C))).astype(np.float32)).to(device)
+
+
+class HotPathFrame:
+    """Buffers + launch sequence for one frame slot (one CUDA stream owns one slot)."""
+
+    def __init__(self, cfg, weights, precision=capi.DSVT_ATTN_FP32, seed=0, device="cuda"):
+        self.cfg, self.w, self.precision = cfg, weights, precision
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        mp, C, F = cfg.max_pillars_num, cfg.channel_num, cfg.ffn_channel_num
+        self.points = torch.zeros(1, cfg.max_points_num, 4, dtype=torch.float32, device=device)
+        self.points_size = torch.zeros(1, dtype=torch.int32, device=device)
+        self.vox = capi.Points2Features(cfg, device=device)
+        self.wp = [capi.WindowPartition(cfg, i, device=device) for i in (0, 1)]
+        self.gs = [capi.GetSet(cfg, i, device=device) for i in (0, 1)]
+        # stand-ins for the outputs of TensorRT-native glue layers
+        self.x0 = torch.randn(mp, C, generator=g).to(device)                       # VFE / PFN output
+        self.pos = [[torch.randn(mp, C, generator=g).mul_(0.5).to(device) for _ in range(2)]
+                    for _ in range(cfg.num_blocks)]                                 # 8 pos-embed MLP outputs
+        self.ffn_hidden = torch.randn(mp, F, generator=g).to(device)               # FFN linear 192->384 output
+        self.ffn_out = torch.randn(mp, C, generator=g).mul_(0.5).to(device)        # FFN linear 384->192 output
+        cand = __import__("importlib").import_module(__package__ + ".synth").head_candidates(cfg.max_top_k, seed)
+        self.cand = [torch.from_numpy(c).to(device)[None] for c in cand]           # CenterHead top-K outputs
+        # activations
+        self.attn_out = torch.empty(mp, C, device=device)
+        self.src = torch.empty(mp, C, device=device)
+        self.src_b = torch.empty(mp, C, device=device)
+        self.gelu_out = torch.empty(mp, F, device=device)
+        self.x_a = torch.empty(mp, C, device=device)
+        self.x_b = torch.empty(mp, C, device=device)
+        self.blk_out = [torch.empty(mp, C, device=device) for _ in range(2)]
+        self.boxes = torch.empty(1, cfg.max_top_k, 9, device=device)
+        self.valid = torch.empty(1, dtype=torch.int32, device=device)
+        self.launches_per_frame = None
+
+    def load_points(self, pts_np):
+        n = min(len(pts_np), self.cfg.max_points_num)
+        self.points[0, :n].copy_(torch.from_numpy(np.ascontiguousarray(pts_np[:n])))
+        self.points_size.fill_(n)
+
+    def run(self):
+        """Enqueue the frame's 49 plugin invocations on the current stream."""
+        cfg, w = self.cfg, self.w
+        before = capi.launch_count()
+        vox = self.vox(self.points, self.points_size)
+        V = vox.pillar_num
+        for i in (0, 1):
+            self.wp[i](vox.coords, V)
+            self.gs[i](self.wp[i].global_index, self.wp[i].coors_in_win, self.wp[i].voxel_num_in_win,
+                       self.wp[i].win_num)
+        x, ln = self.x0, 0
+        for blk in range(cfg.num_blocks):
+            gs = self.gs[blk % 2]                      # blocks 0,2: 12x12 windows; 1,3: 24x24 shifted (:654-:1018)
+            x_in = x
+            for enc in (0, 1):
+                capi.set_attention_fused(w.attn[blk * 2 + enc], x, self.pos[blk][enc], gs.global_index_in_set[0],
+                                         gs.mask_expand_0[0], gs.set_num, V, axis=enc, out=self.attn_out,
+                                         precision=self.precision)
+                capi.layer_norm(self.attn_out, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=x,
+                                out=self.src); ln += 1                                     # norm1(y + x)   :669-676
+                capi.gelu(self.ffn_hidden, V, out=self.gelu_out)                           # :519 (inside the FFN)
+                capi.layer_norm(self.src, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=self.ffn_out,
+                                out=self.src_b); ln += 1                                   # norm2(src + src2) :685-690
+                nxt = self.x_a if enc == 0 else self.x_b
+                capi.layer_norm(self.src_b, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=x,
+                                out=nxt); ln += 1                                          # norm(src + x)  :691-697
+                x = nxt
+            capi.layer_norm(x, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=x_in,
+                            out=self.blk_out[blk % 2]); ln += 1                            # residual norm  :750-756
+            x = self.blk_out[blk % 2]
+        self.final = x
+        capi.filter_box(cfg, *self.cand, boxes=self.boxes, valid=self.valid)
+        self.launches_per_frame = capi.launch_count() - before
+        return self

@@ -59,9 +59,15 @@ def reference_available():
     return os.path.isdir(os.path.join(REF, "plugins", "src"))
 
 
-def build_reference(verbose=False):
-    """Returns {plugin stem: path to .so}; only stems that built."""
-    out_dir = os.path.join(HERE, "_ref")
+def build_reference(verbose=False, variant=None):
+    """Returns {plugin stem: path to .so}; only stems that built.
+
+    variant=None    : the reference exactly as shipped (its own include/params.h; 50k points / 10k pillars / 800 sets)
+    variant="waymo" : same unmodified sources, configured through oracle/ref_config_waymo/params.h placed first on
+                      the include path (320k points / 40k pillars / 4096 sets) -> oracle/_ref/waymo/
+    """
+    out_dir = os.path.join(HERE, "_ref") if variant is None else os.path.join(HERE, "_ref", variant)
+    cfg_inc = [] if variant is None else ["-I" + os.path.join(HERE, "ref_config_" + variant)]
     built = {}
     if not reference_available():
         # GPU box: use whatever was prebuilt and shipped
@@ -77,9 +83,12 @@ def build_reference(verbose=False):
     for stem, _ in REF_PLUGINS:
         src = os.path.join(REF, "plugins", "src", f"{stem}.cu")
         so = os.path.join(out_dir, f"libref_{stem}.so")
-        if _newer(so, [src, harness, os.path.join(STUB, "NvInfer.h")]):
+        deps = [src, harness, os.path.join(STUB, "NvInfer.h")]
+        if variant is not None:
+            deps.append(os.path.join(HERE, "ref_config_" + variant, "params.h"))
+        if _newer(so, deps):
             cmd = ["nvcc", "-std=c++14", "-O2", "-w", "-gencode", "arch=compute_100a,code=sm_100a",
-                   "-Xcompiler", "-fPIC", "-shared",
+                   "-Xcompiler", "-fPIC", "-shared", *cfg_inc,
                    "-I" + STUB, "-I" + os.path.join(REF, "include"), "-I" + os.path.join(REF, "plugins", "include"),
                    "-I" + os.path.join(ROOT, "include"),
                    "-DDSVT_HARNESS_FOR_REFERENCE=1",
@@ -96,5 +105,6 @@ def build_reference(verbose=False):
 
 if __name__ == "__main__":
     print(build_oracle(verbose=True))
-    for k, v in build_reference(verbose=True).items():
-        print(k, v)
+    for variant in (None, "waymo"):
+        for k, v in build_reference(verbose=True, variant=variant).items():
+            print(variant, k, v)
