@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=16, help="frames per GPU per step")
     ap.add_argument("--streams", type=int, default=4, help="concurrent frame streams per GPU")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "fp16"])
     ap.add_argument("--points", type=int, default=N_POINTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -308,7 +308,7 @@ def main():
     pipeline = importlib.import_module("dsvt-ai-trt_b200.pipeline")
     cfg = pkg.config.WAYMO
     peaks = load_peaks()
-    precision = {"fp32": capi.DSVT_ATTN_FP32, "tf32": capi.DSVT_ATTN_TF32, "bf16": capi.DSVT_ATTN_BF16}[args.precision]
+    precision = {"fp32": capi.DSVT_ATTN_FP32, "tf32": capi.DSVT_ATTN_TF32, "fp16": capi.DSVT_ATTN_FP16}[args.precision]
 
     F, S = args.frames_per_step, max(1, min(args.streams, args.frames_per_step))
     weights = pipeline.FrameWeights(cfg, seed=0)

@@ -10,7 +10,7 @@ import torch
 
 from ._lib import load_library
 
-DSVT_ATTN_FP32, DSVT_ATTN_TF32, DSVT_ATTN_BF16 = 0, 1, 2
+DSVT_ATTN_FP32, DSVT_ATTN_TF32, DSVT_ATTN_FP16 = 0, 1, 2
 
 
 class P2FParams(Structure):
@@ -77,6 +77,9 @@ def _lib():
         lib.dsvt_attention_weights_create.restype = c_void_p
         lib.dsvt_attention_weights_create.argtypes = [c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
         lib.dsvt_attention_weights_destroy.argtypes = [c_void_p]
+        lib.dsvt_linear_weights_create.restype = c_void_p
+        lib.dsvt_linear_weights_create.argtypes = [c_int32, c_int32, c_void_p, c_void_p, c_int32]
+        lib.dsvt_linear_weights_destroy.argtypes = [c_void_p]
         _sig_done = True
     return lib
 
@@ -323,3 +326,37 @@ def map_set_feature2voxel(feat, global_index_in_set, set_num, axis, max_pillars,
                                                   _ptr(set_num), _ptr(out), _stream())
     _check(rc, "dsvt_map_set_feature2voxel_launch")
     return out
+
+
+class Linear:
+    """y = x W^T + b on the tensor cores (tcgen05); W [N,K] float32 host array."""
+
+    def __init__(self, W, b=None, precision=DSVT_ATTN_TF32):
+        import numpy as np
+        W = np.ascontiguousarray(W, dtype=np.float32)
+        self.N, self.K = W.shape
+        bb = np.ascontiguousarray(b, dtype=np.float32) if b is not None else None
+        self.handle = _lib().dsvt_linear_weights_create(self.N, self.K, W.ctypes.data_as(c_void_p),
+                                                        bb.ctypes.data_as(c_void_p) if bb is not None else None,
+                                                        precision)
+        if not self.handle:
+            raise DsvtError("dsvt_linear_weights_create: " + _lib().dsvt_last_error().decode())
+
+    def __call__(self, x, out=None):
+        _need(x, torch.float32, "x")
+        M = x.shape[0]
+        out = torch.empty(M, self.N, dtype=torch.float32, device=x.device) if out is None else out
+        _check(_lib().dsvt_linear_launch(c_void_p(self.handle), _ptr(x), c_int32(M), _ptr(out), _stream()),
+               "dsvt_linear_launch")
+        return out
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib().dsvt_linear_weights_destroy(c_void_p(self.handle))
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -46,7 +46,14 @@ extern "C" dsvt_attention_weights* dsvt_attention_weights_create(int32_t C, int3
     w->dev.b_in = w->blob + n_in;
     w->dev.w_out_t = w->blob + n_in + 3 * C;
     w->dev.b_out = w->blob + n_in + 3 * C + n_out;
-    w->dev.tc_blob = nullptr;
+    w->tc_blob = attention_tc_prepare(C, heads, in_proj_weight, in_proj_bias, out_proj_weight, out_proj_bias);
+    if (!w->tc_blob) {
+        set_last_error("dsvt_attention_weights_create: preparing the tensor-core operand images failed");
+        cudaFree(w->blob);
+        delete w;
+        return nullptr;
+    }
+    w->dev.tc_blob = w->tc_blob;
     return w;
 }
 
@@ -79,6 +86,13 @@ static int attn_dispatch(const dsvt_set_attention_params* p, const dsvt_attentio
     switch (p->precision) {
         case DSVT_ATTN_FP32:
             return set_attention_fp32(p, w->dev, fused, q, k, v, pos, idx, mask, set_num, voxel_num, out, st);
+        case DSVT_ATTN_FP16:
+            if (!fused) {
+                set_last_error("set attention: the FP16 tensor-core path is built for the fused entry point "
+                               "(dsvt_set_attention_fused_launch) only");
+                return DSVT_ERR_UNSUPPORTED;
+            }
+            return set_attention_tc_fused(p, w->tc_blob, q, pos, idx, mask, set_num, voxel_num, out, st);
         default:
             set_last_error("set attention: precision %d is not available in this build", p->precision);
             return DSVT_ERR_UNSUPPORTED;

@@ -17,6 +17,12 @@ int set_attention_fp32(const dsvt_set_attention_params* p, const AttnWeightsDev&
                        const float* q, const float* k, const float* v, const float* pos, const int* idx,
                        const float* mask, const int* set_num, const int* voxel_num, float* out, cudaStream_t st);
 
+// FP16 tensor-core path (attention_tc.cu)
+void* attention_tc_prepare(int C, int H, const float* w_in, const float* b_in, const float* w_out, const float* b_out);
+int set_attention_tc_fused(const dsvt_set_attention_params* p, const void* tc_blob,
+                           const float* x, const float* pos, const int* idx, const float* mask,
+                           const int* set_num, const int* voxel_num, float* out, cudaStream_t st);
+
 }  // namespace dsvt
 
 struct dsvt_attention_weights {

@@ -1,0 +1,506 @@
+// a3 -- set attention on the 5th-generation tensor cores (DSVT_ATTN_FP16: the reference's USE_FP16
+// configuration; FP16 operands, FP32 accumulation in TMEM, FP32 softmax, FP32 tensors in HBM).
+//
+// Fused form of  GetValueByIndex -> multHeadAttention() -> MapSetFeature2Voxel
+// (getValueByIndex.cu:282-303, src/dsvt-ai-trt.cpp:288-458, mapSetFeature2voxel.cu:258-275).
+//
+// Work decomposition: a persistent CTA per SM loops over tiles of 3 sets = 108 token rows padded to the
+// 128-row UMMA M.  Per tile, with everything between the gathered token rows and the scattered output rows
+// held in shared memory / tensor memory:
+//   stage   : gather x[idx]+pos[idx] and x[idx], convert to FP16, write the K-major interleaved operand tiles
+//   per head h (8x):
+//     proj  : tcgen05.mma  [128x48] = A_qk . Wqk_h^T   and   [128x32] = A_v . Wv_h^T      (K = 192)
+//             (1/sqrt(24) is folded into Wq, bq; W tiles stream from L2 with one cp.async.bulk per head)
+//     epi   : TMEM -> registers, + bias, -> FP16 operand tiles Q_h, K_h (K-major) and V_h (MN-major)
+//     S     : tcgen05.mma  [128x112] = Q_h . K_h^T  (K = 24 padded to 32): all 3 sets at once, only the
+//             block diagonal is used
+//     smax  : one thread per row: + key mask, max, exp2, sum  -> P (FP16) written back to TENSOR MEMORY
+//     PV    : tcgen05.mma  [128x32] = P(TMEM) . V_h   (K = 112 keys), accumulating head h's slice of O
+//   out     : O (TMEM) -> FP16 operand tile, tcgen05.mma [128x192] = O . Wout^T, + bias, scatter rows
+// TMEM map (512 columns): proj [0,80) | S [80,192) | P [192,248) | O [256,512); out-proj reuses [0,192).
+#include "attention_common.cuh"
+#include "tc_common.cuh"
+#include <cuda_fp16.h>
+#include <cstring>
+#include <vector>
+
+namespace dsvt {
+namespace {
+
+using namespace tc;
+
+constexpr int kC = 192, kH = 8, kD = 24, kS = 36;
+constexpr int kSetsPerTile = 3;
+constexpr int kRows = 128;                 // UMMA M
+constexpr int kValidRows = kSetsPerTile * kS;   // 108
+constexpr int kKeys = 112;                 // S-MMA N / PV-MMA K (108 padded to a multiple of 16)
+constexpr int kThreads = 256;
+
+// tensor-memory columns
+constexpr uint32_t C_QK = 0, C_V = 48, C_S = 80, C_P = 192, C_O = 256, C_OUT = 0;
+
+// shared memory map (bytes)
+constexpr int kChunkStride = kRows * 16;                 // 2048: one 16-byte K chunk for all 128 rows
+constexpr int SM_AQK = 0;                                // [24 chunks][128][16] = 49152   (later: O operand tile)
+constexpr int SM_AV = SM_AQK + 24 * kChunkStride;        // 49152                          (later: Wout rows 0..95)
+constexpr int SM_W = SM_AV + 24 * kChunkStride;          // 36864: per-head weights (30720) / Wout rows 96..191
+constexpr int SM_Q = SM_W + 36864;                       // [4][128][16] = 8192
+constexpr int SM_K = SM_Q + 4 * kChunkStride;            // 8192
+constexpr int SM_V = SM_K + 4 * kChunkStride;            // [16 key groups][4 d groups][8][16 B] = 8192
+constexpr int SM_TOTAL = SM_V + 8192;                    // 159744
+
+// weight image (device, bytes): 8 x [Wqk_h 48x192 | Wv_h 32x192] then Wout as two 96-row halves
+constexpr int kWqkBytes = 48 * kC * 2;                   // 18432
+constexpr int kWvBytes = 32 * kC * 2;                    // 12288
+constexpr int kWHeadBytes = kWqkBytes + kWvBytes;        // 30720
+constexpr int kWoutHalfBytes = 96 * kC * 2;              // 36864
+constexpr int kWImgBytes = kH * kWHeadBytes + 2 * kWoutHalfBytes;
+
+struct TcBlobView {
+    const uint8_t* w_img;      // kWImgBytes
+    const float* b_q;          // [192] already divided by sqrt(24)
+    const float* b_k;          // [192]
+    const float* b_v;          // [192]
+    const float* b_out;        // [192]
+};
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+set_attention_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const int* __restrict__ idx,
+                        const float* __restrict__ mask, const int* __restrict__ set_num,
+                        const int* __restrict__ voxel_num, float* __restrict__ out, TcBlobView wb,
+                        int max_sets, int max_pillars, int axis, int zero_tails)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar_mma, bar_w, bar_w2;
+    __shared__ uint32_t tmem_slot;
+    __shared__ int s_rows[kRows];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y;
+    int ns = set_num[b];
+    ns = ns < max_sets ? ns : max_sets;
+    const int n_tiles = (ns + kSetsPerTile - 1) / kSetsPerTile;
+    x += (size_t) b * max_pillars * kC;
+    pos += (size_t) b * max_pillars * kC;
+    out += (size_t) b * max_pillars * kC;
+    idx += ((size_t) b * 2 + axis) * max_sets * kS;
+    mask += (size_t) b * max_sets * kH * kS;
+
+    // ---- zero-tail duty: rows [voxel_num, max_pillars) of the output (mapSetFeature2voxel.cu:312 memset) ----
+    if (zero_tails) {
+        int V = voxel_num[b];
+        V = V < max_pillars ? V : max_pillars;
+        float4* o4 = reinterpret_cast<float4*>(out + (size_t) V * kC);
+        const long long n4 = (long long) (max_pillars - V) * (kC / 4);
+        for (long long t = (long long) blockIdx.x * kThreads + tid; t < n4; t += (long long) gridDim.x * kThreads)
+            o4[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if ((int) blockIdx.x >= n_tiles) return;
+
+    if (tid == 0) {
+        mbar_init(&bar_mma, 1);
+        mbar_init(&bar_w, 1);
+        mbar_init(&bar_w2, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc<512>(&tmem_slot);
+    // zero padding that stays zero for the whole kernel: chunk 3 of Q/K (dims 24..31), d-group 3 of V
+    for (int t = tid; t < kRows; t += kThreads) {
+        *reinterpret_cast<uint4*>(smem + SM_Q + 3 * kChunkStride + t * 16) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(smem + SM_K + 3 * kChunkStride + t * 16) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(smem + SM_V + (t >> 3) * 512 + 3 * 128 + (t & 7) * 16) = make_uint4(0, 0, 0, 0);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    // P = 0 everywhere once: rows only ever rewrite their own set's 18 packed columns
+    if (warp < 4) {
+        uint32_t z[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) z[i] = 0;
+        const uint32_t base = tmem + ((uint32_t) (warp * 32) << 16) + C_P;
+        tmem_st16(base, z); tmem_st16(base + 16, z); tmem_st16(base + 32, z);
+        tmem_st2(base + 48, 0, 0); tmem_st2(base + 50, 0, 0); tmem_st2(base + 52, 0, 0); tmem_st2(base + 54, 0, 0);
+        tmem_st_wait();
+    }
+
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t idesc_qk = make_idesc(kFmtF16, kRows, 48);
+    const uint32_t idesc_v = make_idesc(kFmtF16, kRows, 32);
+    const uint32_t idesc_s = make_idesc(kFmtF16, kRows, kKeys);
+    const uint32_t idesc_pv = make_idesc(kFmtF16, kRows, 32, 0, 1);     // B = V_h is MN-major
+    const uint32_t idesc_out = make_idesc(kFmtF16, kRows, 96);
+    uint32_t ph_mma = 0, ph_w = 0, ph_w2 = 0;                            // mbarrier parities
+
+    const int q4 = warp & 3, hf = warp >> 2;
+    const int row = q4 * 32 + lane;                                      // this thread's TMEM lane / token row
+    const uint32_t tlane = tmem + ((uint32_t) (q4 * 32) << 16);
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int set0 = tile * kSetsPerTile;
+        // ---- per-head weight prefetch for head 0 (sW is free: the previous tile's out-proj has completed) ----
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&bar_w, kWHeadBytes);
+            bulk_g2s(smem + SM_W, wb.w_img, kWHeadBytes, &bar_w);
+        }
+        // ---- stage the token tile ----------------------------------------------------------------------------
+        if (tid < kRows) {
+            const int r = tid, st = set0 + r / kS;
+            s_rows[r] = (r < kValidRows && st < ns) ? idx[(size_t) st * kS + (r % kS)] : -1;
+        }
+        __syncthreads();
+        {
+            const int r = tid & (kRows - 1);
+            const int g = s_rows[r];
+            const float4* xr = reinterpret_cast<const float4*>(x + (size_t) (g < 0 ? 0 : g) * kC);
+            const float4* pr = reinterpret_cast<const float4*>(pos + (size_t) (g < 0 ? 0 : g) * kC);
+            for (int c = tid >> 7; c < 24; c += 2) {                     // chunk c = channels [8c, 8c+8)
+                uint4 vq = make_uint4(0, 0, 0, 0), vv = vq;
+                if (g >= 0) {
+                    const float4 a0 = __ldg(xr + 2 * c), a1 = __ldg(xr + 2 * c + 1);
+                    const float4 p0 = __ldg(pr + 2 * c), p1 = __ldg(pr + 2 * c + 1);
+                    vv = make_uint4(pack_h2(a0.x, a0.y), pack_h2(a0.z, a0.w), pack_h2(a1.x, a1.y), pack_h2(a1.z, a1.w));
+                    vq = make_uint4(pack_h2(a0.x + p0.x, a0.y + p0.y), pack_h2(a0.z + p0.z, a0.w + p0.w),
+                                    pack_h2(a1.x + p1.x, a1.y + p1.y), pack_h2(a1.z + p1.z, a1.w + p1.w));
+                }
+                *reinterpret_cast<uint4*>(smem + SM_AQK + c * kChunkStride + r * 16) = vq;
+                *reinterpret_cast<uint4*>(smem + SM_AV + c * kChunkStride + r * 16) = vv;
+            }
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+
+        // issue the projection MMAs of head `h` (thread 0 only; weights of head h must have landed in sW)
+        auto issue_proj = [&](int h) {
+            (void) h;
+            mbar_wait(&bar_w, ph_w);
+            ph_w ^= 1;
+            tc_fence_after_sync();
+#pragma unroll 1
+            for (int ks = 0; ks < 12; ++ks) {                            // K = 192 = 12 x 16
+                const uint64_t aq = make_smem_desc(sbase + SM_AQK + ks * 2 * kChunkStride, kChunkStride, 128);
+                const uint64_t av = make_smem_desc(sbase + SM_AV + ks * 2 * kChunkStride, kChunkStride, 128);
+                const uint64_t bq = make_smem_desc(sbase + SM_W + ks * 2 * (48 * 16), 48 * 16, 128);
+                const uint64_t bv = make_smem_desc(sbase + SM_W + kWqkBytes + ks * 2 * (32 * 16), 32 * 16, 128);
+                umma_f16(tmem + C_QK, aq, bq, idesc_qk, ks > 0);
+                umma_f16(tmem + C_V, av, bv, idesc_v, ks > 0);
+            }
+        };
+        if (tid == 0) {
+            issue_proj(0);
+            umma_commit(&bar_mma);
+        }
+
+        for (int h = 0; h < kH; ++h) {
+            // ---- wait: proj(h) (and PV(h-1)) complete -------------------------------------------------------------
+            mbar_wait(&bar_mma, ph_mma);
+            ph_mma ^= 1;
+            tc_fence_after_sync();
+            if (tid == 0) {                                              // sW is free again: prefetch the next weights
+                if (h + 1 < kH) {
+                    mbar_arrive_expect_tx(&bar_w, kWHeadBytes);
+                    bulk_g2s(smem + SM_W, wb.w_img + (size_t) (h + 1) * kWHeadBytes, kWHeadBytes, &bar_w);
+                } else {                                                 // Wout rows 96..191 -> sW (rows 0..95 go to sAv later)
+                    mbar_arrive_expect_tx(&bar_w, kWoutHalfBytes);
+                    bulk_g2s(smem + SM_W, wb.w_img + (size_t) kH * kWHeadBytes + kWoutHalfBytes, kWoutHalfBytes, &bar_w);
+                }
+            }
+            // ---- projection epilogue: TMEM -> +bias -> FP16 operand tiles ---------------------------------------------
+            {
+                uint32_t a[16], c8[8];
+                if (hf == 0) {                                           // Q (24) and V d-group 0
+                    tmem_ld16(tlane + C_QK, a); tmem_ld8(tlane + C_QK + 16, c8);
+                    tmem_ld_wait();
+                    const float* bq = wb.b_q + h * kD;
+                    uint4 v0 = make_uint4(pack_h2(__uint_as_float(a[0]) + __ldg(bq + 0), __uint_as_float(a[1]) + __ldg(bq + 1)),
+                                          pack_h2(__uint_as_float(a[2]) + __ldg(bq + 2), __uint_as_float(a[3]) + __ldg(bq + 3)),
+                                          pack_h2(__uint_as_float(a[4]) + __ldg(bq + 4), __uint_as_float(a[5]) + __ldg(bq + 5)),
+                                          pack_h2(__uint_as_float(a[6]) + __ldg(bq + 6), __uint_as_float(a[7]) + __ldg(bq + 7)));
+                    uint4 v1 = make_uint4(pack_h2(__uint_as_float(a[8]) + __ldg(bq + 8), __uint_as_float(a[9]) + __ldg(bq + 9)),
+                                          pack_h2(__uint_as_float(a[10]) + __ldg(bq + 10), __uint_as_float(a[11]) + __ldg(bq + 11)),
+                                          pack_h2(__uint_as_float(a[12]) + __ldg(bq + 12), __uint_as_float(a[13]) + __ldg(bq + 13)),
+                                          pack_h2(__uint_as_float(a[14]) + __ldg(bq + 14), __uint_as_float(a[15]) + __ldg(bq + 15)));
+                    uint4 v2 = make_uint4(pack_h2(__uint_as_float(c8[0]) + __ldg(bq + 16), __uint_as_float(c8[1]) + __ldg(bq + 17)),
+                                          pack_h2(__uint_as_float(c8[2]) + __ldg(bq + 18), __uint_as_float(c8[3]) + __ldg(bq + 19)),
+                                          pack_h2(__uint_as_float(c8[4]) + __ldg(bq + 20), __uint_as_float(c8[5]) + __ldg(bq + 21)),
+                                          pack_h2(__uint_as_float(c8[6]) + __ldg(bq + 22), __uint_as_float(c8[7]) + __ldg(bq + 23)));
+                    *reinterpret_cast<uint4*>(smem + SM_Q + 0 * kChunkStride + row * 16) = v0;
+                    *reinterpret_cast<uint4*>(smem + SM_Q + 1 * kChunkStride + row * 16) = v1;
+                    *reinterpret_cast<uint4*>(smem + SM_Q + 2 * kChunkStride + row * 16) = v2;
+                    tmem_ld8(tlane + C_V, c8);
+                    tmem_ld_wait();
+                    const float* bv = wb.b_v + h * kD;
+                    uint4 w0 = make_uint4(pack_h2(__uint_as_float(c8[0]) + __ldg(bv + 0), __uint_as_float(c8[1]) + __ldg(bv + 1)),
+                                          pack_h2(__uint_as_float(c8[2]) + __ldg(bv + 2), __uint_as_float(c8[3]) + __ldg(bv + 3)),
+                                          pack_h2(__uint_as_float(c8[4]) + __ldg(bv + 4), __uint_as_float(c8[5]) + __ldg(bv + 5)),
+                                          pack_h2(__uint_as_float(c8[6]) + __ldg(bv + 6), __uint_as_float(c8[7]) + __ldg(bv + 7)));
+                    *reinterpret_cast<uint4*>(smem + SM_V + (row >> 3) * 512 + 0 * 128 + (row & 7) * 16) = w0;
+                } else {                                                 // K (24) and V d-groups 1, 2
+                    tmem_ld16(tlane + C_QK + 24, a); tmem_ld8(tlane + C_QK + 40, c8);
+                    tmem_ld_wait();
+                    const float* bk = wb.b_k + h * kD;
+                    uint4 v0 = make_uint4(pack_h2(__uint_as_float(a[0]) + __ldg(bk + 0), __uint_as_float(a[1]) + __ldg(bk + 1)),
+                                          pack_h2(__uint_as_float(a[2]) + __ldg(bk + 2), __uint_as_float(a[3]) + __ldg(bk + 3)),
+                                          pack_h2(__uint_as_float(a[4]) + __ldg(bk + 4), __uint_as_float(a[5]) + __ldg(bk + 5)),
+                                          pack_h2(__uint_as_float(a[6]) + __ldg(bk + 6), __uint_as_float(a[7]) + __ldg(bk + 7)));
+                    uint4 v1 = make_uint4(pack_h2(__uint_as_float(a[8]) + __ldg(bk + 8), __uint_as_float(a[9]) + __ldg(bk + 9)),
+                                          pack_h2(__uint_as_float(a[10]) + __ldg(bk + 10), __uint_as_float(a[11]) + __ldg(bk + 11)),
+                                          pack_h2(__uint_as_float(a[12]) + __ldg(bk + 12), __uint_as_float(a[13]) + __ldg(bk + 13)),
+                                          pack_h2(__uint_as_float(a[14]) + __ldg(bk + 14), __uint_as_float(a[15]) + __ldg(bk + 15)));
+                    uint4 v2 = make_uint4(pack_h2(__uint_as_float(c8[0]) + __ldg(bk + 16), __uint_as_float(c8[1]) + __ldg(bk + 17)),
+                                          pack_h2(__uint_as_float(c8[2]) + __ldg(bk + 18), __uint_as_float(c8[3]) + __ldg(bk + 19)),
+                                          pack_h2(__uint_as_float(c8[4]) + __ldg(bk + 20), __uint_as_float(c8[5]) + __ldg(bk + 21)),
+                                          pack_h2(__uint_as_float(c8[6]) + __ldg(bk + 22), __uint_as_float(c8[7]) + __ldg(bk + 23)));
+                    *reinterpret_cast<uint4*>(smem + SM_K + 0 * kChunkStride + row * 16) = v0;
+                    *reinterpret_cast<uint4*>(smem + SM_K + 1 * kChunkStride + row * 16) = v1;
+                    *reinterpret_cast<uint4*>(smem + SM_K + 2 * kChunkStride + row * 16) = v2;
+                    tmem_ld16(tlane + C_V + 8, a);
+                    tmem_ld_wait();
+                    const float* bv = wb.b_v + h * kD + 8;
+                    uint4 w1 = make_uint4(pack_h2(__uint_as_float(a[0]) + __ldg(bv + 0), __uint_as_float(a[1]) + __ldg(bv + 1)),
+                                          pack_h2(__uint_as_float(a[2]) + __ldg(bv + 2), __uint_as_float(a[3]) + __ldg(bv + 3)),
+                                          pack_h2(__uint_as_float(a[4]) + __ldg(bv + 4), __uint_as_float(a[5]) + __ldg(bv + 5)),
+                                          pack_h2(__uint_as_float(a[6]) + __ldg(bv + 6), __uint_as_float(a[7]) + __ldg(bv + 7)));
+                    uint4 w2 = make_uint4(pack_h2(__uint_as_float(a[8]) + __ldg(bv + 8), __uint_as_float(a[9]) + __ldg(bv + 9)),
+                                          pack_h2(__uint_as_float(a[10]) + __ldg(bv + 10), __uint_as_float(a[11]) + __ldg(bv + 11)),
+                                          pack_h2(__uint_as_float(a[12]) + __ldg(bv + 12), __uint_as_float(a[13]) + __ldg(bv + 13)),
+                                          pack_h2(__uint_as_float(a[14]) + __ldg(bv + 14), __uint_as_float(a[15]) + __ldg(bv + 15)));
+                    *reinterpret_cast<uint4*>(smem + SM_V + (row >> 3) * 512 + 1 * 128 + (row & 7) * 16) = w1;
+                    *reinterpret_cast<uint4*>(smem + SM_V + (row >> 3) * 512 + 2 * 128 + (row & 7) * 16) = w2;
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+            // ---- S = Q_h K_h^T -------------------------------------------------------------------------------------------
+            if (tid == 0) {
+                tc_fence_after_sync();
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {                         // K = 32 (24 + zero padding)
+                    const uint64_t ad = make_smem_desc(sbase + SM_Q + ks * 2 * kChunkStride, kChunkStride, 128);
+                    const uint64_t bd = make_smem_desc(sbase + SM_K + ks * 2 * kChunkStride, kChunkStride, 128);
+                    umma_f16(tmem + C_S, ad, bd, idesc_s, ks > 0);
+                }
+                umma_commit(&bar_mma);
+            }
+            mbar_wait(&bar_mma, ph_mma);
+            ph_mma ^= 1;
+            tc_fence_after_sync();
+            // ---- softmax over the row's own set (warps 0..3: one thread per token row) ----------------------------------
+            if (warp < 4) {
+                const int a_set = warp == 0 ? 0 : warp - 1;              // first set touched by this warp's 32 rows
+                const bool two = (warp == 1) || (warp == 2);             // rows of this warp span two sets
+                const int sl = row / kS;                                 // this row's set within the tile (3 = padding row)
+                const bool use_b = two && (sl == a_set + 1);
+                uint32_t ra[32], ra4[4], rb[32], rb4[4];
+                tmem_ld32(tlane + C_S + a_set * kS, ra);
+                tmem_ld4(tlane + C_S + a_set * kS + 32, ra4);
+                if (two) {
+                    tmem_ld32(tlane + C_S + a_set * kS + kS, rb);
+                    tmem_ld4(tlane + C_S + a_set * kS + kS + 32, rb4);
+                }
+                tmem_ld_wait();
+                float s[kS];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) s[k] = __uint_as_float(use_b ? rb[k] : ra[k]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) s[32 + k] = __uint_as_float(use_b ? rb4[k] : ra4[k]);
+                const int st = set0 + sl;
+                const bool live = (row < kValidRows) && (st < ns);
+                if (live) {
+                    const float4* mk = reinterpret_cast<const float4*>(mask + ((size_t) st * kH + h) * kS);
+#pragma unroll
+                    for (int k4 = 0; k4 < kS / 4; ++k4) {
+                        const float4 m = __ldg(mk + k4);
+                        s[4 * k4 + 0] += m.x; s[4 * k4 + 1] += m.y; s[4 * k4 + 2] += m.z; s[4 * k4 + 3] += m.w;
+                    }
+                }
+                float mx = s[0];
+#pragma unroll
+                for (int k = 1; k < kS; ++k) mx = fmaxf(mx, s[k]);
+                float sum = 0.f;
+#pragma unroll
+                for (int k = 0; k < kS; ++k) { s[k] = exp2f((s[k] - mx) * 1.4426950408889634f); sum += s[k]; }
+                const float inv = live ? 1.0f / sum : 0.f;               // padding rows carry an all-zero P row
+                uint32_t pk[18];
+#pragma unroll
+                for (int k = 0; k < 18; ++k) pk[k] = pack_h2(s[2 * k] * inv, s[2 * k + 1] * inv);
+                // write the row's 18 packed columns; a two-set warp writes both windows (zeros in the other set's)
+                uint32_t w0[16], w1[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) { w0[k] = use_b ? 0u : pk[k]; w1[k] = use_b ? pk[k] : 0u; }
+                const uint32_t pbase = tlane + C_P + a_set * 18;
+                tmem_st16(pbase, w0);
+                tmem_st2(pbase + 16, use_b ? 0u : pk[16], use_b ? 0u : pk[17]);
+                if (two) {
+                    tmem_st16(pbase + 18, w1);
+                    tmem_st2(pbase + 34, use_b ? pk[16] : 0u, use_b ? pk[17] : 0u);
+                }
+                tmem_st_wait();
+            }
+            tc_fence_before_sync();
+            __syncthreads();
+            // ---- O_h = P V_h, then (pipelined behind it) the next head's projections ------------------------------------
+            if (tid == 0) {
+                tc_fence_after_sync();
+#pragma unroll
+                for (int ks = 0; ks < kKeys / 16; ++ks) {                // K = 112 keys = 7 x 16
+                    const uint64_t bd = make_smem_desc(sbase + SM_V + ks * 1024, 512, 128);
+                    umma_f16_ts(tmem + C_O + 32 * h, tmem + C_P + 8 * ks, bd, idesc_pv, ks > 0);
+                }
+                if (h + 1 < kH) issue_proj(h + 1);
+                umma_commit(&bar_mma);
+            }
+        }
+        // ---- all heads done: O (TMEM) -> FP16 operand tile (aliases sAqk); Wout rows 0..95 -> sAv ------------------------
+        mbar_wait(&bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after_sync();
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&bar_w2, kWoutHalfBytes);              // own barrier: bar_w may still be mid-phase
+            bulk_g2s(smem + SM_AV, wb.w_img + (size_t) kH * kWHeadBytes, kWoutHalfBytes, &bar_w2);
+        }
+        for (int hh = 0; hh < 4; ++hh) {
+            const int h = hf * 4 + hh;
+            uint32_t a[16], c8[8];
+            tmem_ld16(tlane + C_O + 32 * h, a);
+            tmem_ld8(tlane + C_O + 32 * h + 16, c8);
+            tmem_ld_wait();
+            *reinterpret_cast<uint4*>(smem + SM_AQK + (3 * h + 0) * kChunkStride + row * 16) =
+                make_uint4(pack_h2(__uint_as_float(a[0]), __uint_as_float(a[1])), pack_h2(__uint_as_float(a[2]), __uint_as_float(a[3])),
+                           pack_h2(__uint_as_float(a[4]), __uint_as_float(a[5])), pack_h2(__uint_as_float(a[6]), __uint_as_float(a[7])));
+            *reinterpret_cast<uint4*>(smem + SM_AQK + (3 * h + 1) * kChunkStride + row * 16) =
+                make_uint4(pack_h2(__uint_as_float(a[8]), __uint_as_float(a[9])), pack_h2(__uint_as_float(a[10]), __uint_as_float(a[11])),
+                           pack_h2(__uint_as_float(a[12]), __uint_as_float(a[13])), pack_h2(__uint_as_float(a[14]), __uint_as_float(a[15])));
+            *reinterpret_cast<uint4*>(smem + SM_AQK + (3 * h + 2) * kChunkStride + row * 16) =
+                make_uint4(pack_h2(__uint_as_float(c8[0]), __uint_as_float(c8[1])), pack_h2(__uint_as_float(c8[2]), __uint_as_float(c8[3])),
+                           pack_h2(__uint_as_float(c8[4]), __uint_as_float(c8[5])), pack_h2(__uint_as_float(c8[6]), __uint_as_float(c8[7])));
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        // ---- out-projection: [128x192] = O . Wout^T as two N = 96 halves ---------------------------------------------------
+        if (tid == 0) {
+            tc_fence_after_sync();
+            mbar_wait(&bar_w, ph_w); ph_w ^= 1;                          // Wout rows 96..191 (sW), issued during head 7
+            mbar_wait(&bar_w2, ph_w2); ph_w2 ^= 1;                       // Wout rows 0..95 (sAv)
+            tc_fence_after_sync();
+#pragma unroll 1
+            for (int ks = 0; ks < 12; ++ks) {
+                const uint64_t ad = make_smem_desc(sbase + SM_AQK + ks * 2 * kChunkStride, kChunkStride, 128);
+                const uint64_t b0 = make_smem_desc(sbase + SM_AV + ks * 2 * (96 * 16), 96 * 16, 128);
+                const uint64_t b1 = make_smem_desc(sbase + SM_W + ks * 2 * (96 * 16), 96 * 16, 128);
+                umma_f16(tmem + C_OUT, ad, b0, idesc_out, ks > 0);
+                umma_f16(tmem + C_OUT + 96, ad, b1, idesc_out, ks > 0);
+            }
+            umma_commit(&bar_mma);
+        }
+        mbar_wait(&bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after_sync();
+        // ---- final epilogue: + bias, scatter the row to its voxel (MapSetFeature2Voxel) ------------------------------------
+        {
+            const int g = s_rows[row];
+            float* dst = out + (size_t) (g < 0 ? 0 : g) * kC + hf * 96;
+            const float* bo = wb.b_out + hf * 96;
+#pragma unroll 1
+            for (int j0 = 0; j0 < 96; j0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tlane + C_OUT + hf * 96 + j0, r);
+                tmem_ld_wait();
+                if (g >= 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o;
+                        o.x = __uint_as_float(r[j + 0]) + __ldg(bo + j0 + j + 0);
+                        o.y = __uint_as_float(r[j + 1]) + __ldg(bo + j0 + j + 1);
+                        o.z = __uint_as_float(r[j + 2]) + __ldg(bo + j0 + j + 2);
+                        o.w = __uint_as_float(r[j + 3]) + __ldg(bo + j0 + j + 3);
+                        *reinterpret_cast<float4*>(dst + j0 + j) = o;
+                    }
+                }
+            }
+        }
+        tc_fence_before_sync();
+        __syncthreads();          // smem tiles, s_rows and the TMEM accumulators are recycled by the next tile
+        tc_fence_after_sync();
+    }
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace
+
+// ---- host: FP16 operand images of one attention layer ----------------------------------------------------------
+void* attention_tc_prepare(int C, int H, const float* w_in, const float* b_in, const float* w_out, const float* b_out)
+{
+    if (C != kC || H != kH) return nullptr;
+    const float inv_scale = 1.0f / sqrtf((float) kD);
+    std::vector<uint8_t> blob(kWImgBytes + 4 * kC * sizeof(float), 0);
+    auto put = [&](uint8_t* tile, int rows, int n, int k, float v) {   // [chunk][row][8 halves]
+        const __half hv = __float2half_rn(v);
+        memcpy(tile + ((size_t) (k / 8) * rows + n) * 16 + (k % 8) * 2, &hv, 2);
+    };
+    for (int h = 0; h < kH; ++h) {
+        uint8_t* qk = blob.data() + (size_t) h * kWHeadBytes;
+        uint8_t* vv = qk + kWqkBytes;
+        for (int d = 0; d < kD; ++d)
+            for (int k = 0; k < kC; ++k) {
+                put(qk, 48, d, k, w_in[(size_t) (0 * kC + h * kD + d) * kC + k] * inv_scale);      // query rows, pre-scaled
+                put(qk, 48, 24 + d, k, w_in[(size_t) (1 * kC + h * kD + d) * kC + k]);             // key rows
+                put(vv, 32, d, k, w_in[(size_t) (2 * kC + h * kD + d) * kC + k]);                  // value rows (+8 zero rows)
+            }
+    }
+    for (int half = 0; half < 2; ++half) {
+        uint8_t* t = blob.data() + (size_t) kH * kWHeadBytes + (size_t) half * kWoutHalfBytes;
+        for (int n = 0; n < 96; ++n)
+            for (int k = 0; k < kC; ++k) put(t, 96, n, k, w_out[(size_t) (half * 96 + n) * kC + k]);
+    }
+    float* fb = reinterpret_cast<float*>(blob.data() + kWImgBytes);
+    for (int i = 0; i < kC; ++i) {
+        fb[i] = b_in[i] * inv_scale;
+        fb[kC + i] = b_in[kC + i];
+        fb[2 * kC + i] = b_in[2 * kC + i];
+        fb[3 * kC + i] = b_out[i];
+    }
+    void* dev = nullptr;
+    if (cudaMalloc(&dev, blob.size()) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(dev, blob.data(), blob.size(), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(dev); return nullptr; }
+    return dev;
+}
+
+int set_attention_tc_fused(const dsvt_set_attention_params* p, const void* tc_blob,
+                           const float* x, const float* pos, const int* idx, const float* mask,
+                           const int* set_num, const int* voxel_num, float* out, cudaStream_t st)
+{
+    if (p->voxel_num_set != kS || p->channel_num != kC || p->num_heads != kH) {
+        set_last_error("set attention (FP16 tensor-core path): only set=36, C=192, heads=8 is built");
+        return DSVT_ERR_UNSUPPORTED;
+    }
+    if (!tc_blob) {
+        set_last_error("set attention (FP16 tensor-core path): weights were not prepared");
+        return DSVT_ERR_INVALID_ARGUMENT;
+    }
+    TcBlobView wb;
+    wb.w_img = static_cast<const uint8_t*>(tc_blob);
+    const float* fb = reinterpret_cast<const float*>(wb.w_img + kWImgBytes);
+    wb.b_q = fb; wb.b_k = fb + kC; wb.b_v = fb + 2 * kC; wb.b_out = fb + 3 * kC;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DSVT_CUDA(cudaFuncSetAttribute(set_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        attr_set = true;
+    }
+    const int max_tiles = (p->max_set_num + kSetsPerTile - 1) / kSetsPerTile;
+    const int grid = max_tiles < sm_count() ? max_tiles : sm_count();
+    set_attention_tc_kernel<<<dim3(grid, p->batch), kThreads, SM_TOTAL, st>>>(
+        x, pos, idx, mask, set_num, voxel_num, out, wb, p->max_set_num, p->max_pillars_num, p->axis_id, p->zero_tails);
+    DSVT_LAUNCH_CHECK();
+    return DSVT_OK;
+}
+
+}  // namespace dsvt

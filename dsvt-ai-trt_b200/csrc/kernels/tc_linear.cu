@@ -1,0 +1,213 @@
+// Dense linear layer on the 5th-generation tensor cores: Y[M,N] = X[M,K] * W[N,K]^T + b  (FP32 in/out).
+// This is the building block the set-attention kernel's projections use, exposed on its own as the
+// replacement of the TensorRT FullyConnected layers around the plugins (FFN linears).
+//
+// One CTA owns a 128-row tile of X.  Rows are converted (FP16 or TF32) and staged by the threads into the
+// UMMA K-major interleaved layout (tc_common.cuh); W tiles are pre-arranged on the host in that same order
+// and arrive with one cp.async.bulk per N tile; one elected thread issues tcgen05.mma over K with the
+// accumulator in TMEM; all four warps read their TMEM lane quarter back with tcgen05.ld, add the bias and
+// store.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <cuda_fp16.h>
+#include <vector>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+namespace dsvt {
+namespace {
+
+using namespace tc;
+
+constexpr int kTileM = 128;
+constexpr int kTileN = 64;
+
+template <int ESIZE> struct Elem;
+template <> struct Elem<2> { static constexpr int per_chunk = 8; static constexpr uint32_t fmt = kFmtF16; };
+template <> struct Elem<4> { static constexpr int per_chunk = 4; static constexpr uint32_t fmt = kFmtTF32; };
+
+// smem: A tile [K/per_chunk chunks][128 rows][16 B] | B tile [chunks][64 rows][16 B] | barriers
+template <int ESIZE>
+__global__ void __launch_bounds__(128, 1)
+tc_linear_kernel(const float* __restrict__ X, const uint8_t* __restrict__ Wimg, const float* __restrict__ bias,
+                 float* __restrict__ Y, int M, int N, int K)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int EPC = Elem<ESIZE>::per_chunk;
+    const int chunks = K / EPC;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (size_t) chunks * kTileM * 16;
+    __shared__ __align__(8) uint64_t bar_b, bar_mma;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row0 = blockIdx.x * kTileM;
+
+    if (tid == 0) {
+        mbar_init(&bar_b, 1);
+        mbar_init(&bar_mma, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc<64>(&tmem_base_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_base_slot;
+
+    // ---- stage A: thread t handles (row = t, all chunks): lanes of a warp write 32 consecutive rows of a chunk
+    for (int c = 0; c < chunks; ++c) {
+        const int r = tid;
+        const int grow = row0 + r;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (grow < M) {
+            const float* src = X + (size_t) grow * K + c * EPC;
+            if (ESIZE == 4) {
+                const float4 f = *reinterpret_cast<const float4*>(src);
+                v.x = __float_as_uint(to_tf32(f.x)); v.y = __float_as_uint(to_tf32(f.y));
+                v.z = __float_as_uint(to_tf32(f.z)); v.w = __float_as_uint(to_tf32(f.w));
+            } else {
+                const float4 f0 = *reinterpret_cast<const float4*>(src);
+                const float4 f1 = *reinterpret_cast<const float4*>(src + 4);
+                __half2 h0 = __floats2half2_rn(f0.x, f0.y), h1 = __floats2half2_rn(f0.z, f0.w);
+                __half2 h2 = __floats2half2_rn(f1.x, f1.y), h3 = __floats2half2_rn(f1.z, f1.w);
+                v.x = *reinterpret_cast<uint32_t*>(&h0); v.y = *reinterpret_cast<uint32_t*>(&h1);
+                v.z = *reinterpret_cast<uint32_t*>(&h2); v.w = *reinterpret_cast<uint32_t*>(&h3);
+            }
+        }
+        *reinterpret_cast<uint4*>(sA + ((size_t) c * kTileM + r) * 16) = v;
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+
+    const uint32_t idesc = make_idesc(Elem<ESIZE>::fmt, kTileM, kTileN);
+    const uint32_t b_tile_bytes = (uint32_t) chunks * kTileN * 16;
+    uint32_t phase = 0;
+    for (int n0 = 0; n0 < N; n0 += kTileN) {
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&bar_b, b_tile_bytes);
+            bulk_g2s(sB, Wimg + (size_t) (n0 / kTileN) * b_tile_bytes, b_tile_bytes, &bar_b);
+            mbar_wait(&bar_b, phase);
+            tc_fence_after_sync();
+            const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+            const int ksteps = chunks / 2;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const uint64_t ad = make_smem_desc(a_addr + ks * 2 * kTileM * 16, kTileM * 16, 128);
+                const uint64_t bd = make_smem_desc(b_addr + ks * 2 * kTileN * 16, kTileN * 16, 128);
+                if (ESIZE == 4) umma_tf32(tmem, ad, bd, idesc, ks > 0);
+                else umma_f16(tmem, ad, bd, idesc, ks > 0);
+            }
+            umma_commit(&bar_mma);
+        }
+        mbar_wait(&bar_mma, phase);
+        tc_fence_after_sync();
+        phase ^= 1;
+        // ---- epilogue: warp w reads lanes [32w, 32w+32), 64 columns
+        const int grow = row0 + warp * 32 + lane;
+        uint32_t r[32];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            tmem_ld32(tmem + ((uint32_t) (warp * 32) << 16) + half * 32, r);
+            tmem_ld_wait();
+            if (grow < M) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int n = n0 + half * 32 + j;
+                    float4 o;
+                    o.x = __uint_as_float(r[j + 0]) + bias[n + 0];
+                    o.y = __uint_as_float(r[j + 1]) + bias[n + 1];
+                    o.z = __uint_as_float(r[j + 2]) + bias[n + 2];
+                    o.w = __uint_as_float(r[j + 3]) + bias[n + 3];
+                    *reinterpret_cast<float4*>(Y + (size_t) grow * N + n) = o;
+                }
+            }
+        }
+        tc_fence_before_sync();
+        __syncthreads();      // TMEM accumulator and sB are reused by the next N tile
+        tc_fence_after_sync();
+    }
+    if (warp == 0) tmem_dealloc<64>(tmem);
+}
+
+}  // namespace
+}  // namespace dsvt
+
+using namespace dsvt;
+
+struct dsvt_linear_weights {
+    int N, K, precision;
+    uint8_t* img;     // device: [N/64 tiles][K chunks][64 rows][16 B]
+    float* bias;      // device [N]
+};
+
+static uint16_t f32_to_f16_bits(float f) { return __half_as_ushort(__float2half_rn(f)); }
+static uint32_t f32_to_tf32_bits(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7F800000u) != 0x7F800000u) u += 0x1000u;   // round to nearest (ties away), like cvt.rna.tf32.f32
+    return u & 0xFFFFE000u;
+}
+
+extern "C" dsvt_linear_weights* dsvt_linear_weights_create(int32_t N, int32_t K, const float* W, const float* b,
+                                                           int32_t precision)
+{
+    const int esize = precision == DSVT_ATTN_FP16 ? 2 : 4;
+    const int epc = 16 / esize;
+    if (N <= 0 || K <= 0 || N % kTileN || K % (2 * epc) || !W || (precision != DSVT_ATTN_FP16 && precision != DSVT_ATTN_TF32)) {
+        set_last_error("dsvt_linear_weights_create: need N %% 64 == 0, K %% %d == 0, precision TF32 or FP16", 2 * epc);
+        return nullptr;
+    }
+    const int chunks = K / epc;
+    std::vector<uint8_t> img((size_t) N * K * esize);
+    for (int n = 0; n < N; ++n) {
+        const int tile = n / kTileN, nl = n % kTileN;
+        for (int c = 0; c < chunks; ++c) {
+            uint8_t* dst = img.data() + (((size_t) tile * chunks + c) * kTileN + nl) * 16;
+            for (int e = 0; e < epc; ++e) {
+                const float w = W[(size_t) n * K + c * epc + e];
+                if (esize == 2) { uint16_t h = f32_to_f16_bits(w); memcpy(dst + e * 2, &h, 2); }
+                else { uint32_t t = f32_to_tf32_bits(w); memcpy(dst + e * 4, &t, 4); }
+            }
+        }
+    }
+    auto* lw = new (std::nothrow) dsvt_linear_weights{N, K, precision, nullptr, nullptr};
+    if (!lw) return nullptr;
+    std::vector<float> zero(N, 0.f);
+    if (cudaMalloc(&lw->img, img.size()) != cudaSuccess || cudaMalloc(&lw->bias, N * sizeof(float)) != cudaSuccess ||
+        cudaMemcpy(lw->img, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(lw->bias, b ? b : zero.data(), N * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_last_error("dsvt_linear_weights_create: CUDA allocation/copy failed");
+        cudaFree(lw->img); cudaFree(lw->bias);
+        delete lw;
+        return nullptr;
+    }
+    return lw;
+}
+
+extern "C" void dsvt_linear_weights_destroy(dsvt_linear_weights* w) {
+    if (!w) return;
+    cudaFree(w->img);
+    cudaFree(w->bias);
+    delete w;
+}
+
+extern "C" int dsvt_linear_launch(const dsvt_linear_weights* w, const float* x, int32_t M, float* y, dsvt_stream_t stream)
+{
+    DSVT_CHECK_ARG(w && x && y && M >= 0, "NULL argument");
+    DSVT_CHECK_ARG(!(((uintptr_t) x | (uintptr_t) y) & 15), "16-B alignment");
+    if (M == 0) return DSVT_OK;
+    const int esize = w->precision == DSVT_ATTN_FP16 ? 2 : 4;
+    const size_t smem = (size_t) w->K * esize * (kTileM + kTileN);
+    DSVT_CHECK_ARG(smem <= 220 * 1024, "K too large for a single-stage tile");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = (M + kTileM - 1) / kTileM;
+    if (esize == 4) {
+        DSVT_CUDA(cudaFuncSetAttribute(tc_linear_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        tc_linear_kernel<4><<<grid, 128, smem, st>>>(x, w->img, w->bias, y, M, w->N, w->K);
+    } else {
+        DSVT_CUDA(cudaFuncSetAttribute(tc_linear_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        tc_linear_kernel<2><<<grid, 128, smem, st>>>(x, w->img, w->bias, y, M, w->N, w->K);
+    }
+    DSVT_LAUNCH_CHECK();
+    return DSVT_OK;
+}

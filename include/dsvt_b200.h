@@ -204,9 +204,10 @@ int dsvt_filter_box_launch(const dsvt_filter_box_params* p,
  *      MapSetFeature2Voxel mapSetFeature2voxel.cu:258-275 fused in)
  * ------------------------------------------------------------------------ */
 enum {
-    DSVT_ATTN_FP32 = 0,      /* CUDA-core FP32 contractions (exact-mode reference path on the GPU) */
-    DSVT_ATTN_TF32 = 1,      /* tcgen05 kind::tf32, FP32 accumulate in TMEM                        */
-    DSVT_ATTN_BF16 = 2       /* tcgen05 kind::f16 with BF16 operands, FP32 accumulate (USE_FP16 config) */
+    DSVT_ATTN_FP32 = 0,      /* CUDA-core FP32 contractions: the FP32 configuration (tolerance 1e-3)                */
+    DSVT_ATTN_TF32 = 1,      /* tcgen05 kind::tf32 operands, FP32 accumulate in TMEM (dense linear layers only)      */
+    DSVT_ATTN_FP16 = 2       /* tcgen05 kind::f16, FP16 operands, FP32 accumulate: the reference's USE_FP16
+                                configuration (params.h:332; tolerance 1e-2)                                        */
 };
 
 typedef struct dsvt_set_attention_params {
@@ -251,6 +252,18 @@ int dsvt_set_attention_fused_launch(const dsvt_set_attention_params* p, const ds
                                     const float* x, const float* pos, const int32_t* global_index_in_set,
                                     const float* mask, const int32_t* set_num, const int32_t* voxel_num,
                                     float* out, void* workspace, size_t workspace_bytes, dsvt_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * (next #4) dense linear layer  y = x * W^T + b on tcgen05 -- replaces the TensorRT FullyConnected
+ * layers next to the plugins (fullyConnected_gelu_fullyConnected, src/dsvt-ai-trt.cpp:494-529).
+ * W [N,K] row-major (PyTorch [out,in]), N % 64 == 0, K % 16 == 0; precision DSVT_ATTN_TF32 or _FP16.
+ * ------------------------------------------------------------------------ */
+typedef struct dsvt_linear_weights dsvt_linear_weights;
+dsvt_linear_weights* dsvt_linear_weights_create(int32_t N, int32_t K, const float* W, const float* b,
+                                                int32_t precision);
+void dsvt_linear_weights_destroy(dsvt_linear_weights* w);
+/* x [M,K] f32 (device) -> y [M,N] f32 (device) */
+int dsvt_linear_launch(const dsvt_linear_weights* w, const float* x, int32_t M, float* y, dsvt_stream_t stream);
 
 /* standalone forms of the two gather/scatter plugins (next #2), kept for graph compatibility */
 int dsvt_get_value_by_index_launch(const dsvt_set_attention_params* p, const float* x, const float* pos,

@@ -345,3 +345,51 @@ def test_set_attention_fused_frame(frame0, cfgs):
                                             torch.tensor([ns], dtype=torch.int32, device="cuda"), axis,
                                             cfg.max_pillars_num)
             assert np.array_equal(sc.cpu().numpy(), ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# FP16 tensor-core configuration (reference: USE_FP16, params.h:332).  Tolerance 1e-2 abs (BASELINE.json
+# configs[2]); FP16 operands carry 11-bit significands, the measured error is ~1e-3.
+@pytest.mark.parametrize("n_sets", [1, 2, 3, 4, 100, 454, 1450])
+def test_set_attention_fused_fp16_tensor_cores(n_sets):
+    rng = np.random.default_rng(n_sets)
+    max_sets, S, C, H = max(8, n_sets + 3), 36, 192, 8
+    sizes = rng.integers(1, S + 1, n_sets)        # every voxel belongs to exactly one set (as getSet guarantees)
+    V = int(sizes.sum())
+    max_pillars = V + 37
+    x = np.zeros((max_pillars, C), np.float32)
+    pos = np.zeros_like(x)
+    x[:V] = rng.standard_normal((V, C))
+    pos[:V] = rng.standard_normal((V, C)) * 0.5
+    idx = np.zeros((2, max_sets, S), np.int32)
+    mask = np.zeros((max_sets, H, S), np.float32)
+    perm = rng.permutation(V)
+    start = 0
+    for s in range(n_sets):                       # ranks with repeats, like DSVT eq.(3)
+        n = int(sizes[s])
+        members = np.sort(perm[start:start + n])
+        start += n
+        r = (np.arange(S) * n) // S
+        idx[0, s] = members[r]
+        idx[1, s] = members[::-1][r]
+        mask[s, :, 1:][:, r[1:] == r[:-1]] = -np.finfo(np.float32).max
+    _, _, _, _, w = _attn_inputs(1, 1, seed=3)
+    W = capi.AttentionWeights(w["w_in"], w["b_in"], w["w_out"], w["b_out"])
+    ns_t = torch.tensor([n_sets], dtype=torch.int32, device="cuda")
+    v_t = torch.tensor([V], dtype=torch.int32, device="cuda")
+    for axis in (0, 1):
+        ref = capi.set_attention_fused(W, dev(x), dev(pos), dev(idx), dev(mask), ns_t, v_t, axis, precision=0)
+        out = torch.full((max_pillars, C), float("nan"), device="cuda")
+        capi.set_attention_fused(W, dev(x), dev(pos), dev(idx), dev(mask), ns_t, v_t, axis, out=out, precision=2)
+        torch.cuda.synchronize()
+        got, want = out.cpu().numpy(), ref.cpu().numpy()
+        touched = np.unique(idx[axis, :n_sets])
+        assert not np.isnan(got[touched]).any()
+        assert np.all(got[V:] == 0)
+        err = np.abs(got[touched] - want[touched]).max()
+        assert err <= 1e-2, err
+        if n_sets <= 4:        # and against the CPU oracle directly
+            q, k, v = cpu.get_value_by_index(x, pos, idx, n_sets, axis)
+            a = cpu.set_attention(q, k, v, mask, n_sets, **w)
+            o = cpu.map_set_feature2voxel(a, idx, n_sets, axis, max_pillars)
+            assert np.abs(got[touched] - o[touched]).max() <= 1e-2
