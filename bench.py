@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "fp16"])
     ap.add_argument("--points", type=int, default=N_POINTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp16-config", action="store_true",
+                    help="skip the extra BASELINE.json configs[2] (FP16 tensor-core attention) measurement")
     return ap.parse_args()
 
 
@@ -124,13 +126,8 @@ def barrier(world):
 
 
 def max_over_ranks(x, world):
-    import torch
-    if world == 1:
-        return x
-    import torch.distributed as dist
-    t = torch.tensor([x], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t[0])
+    sharding = importlib.import_module("dsvt-ai-trt_b200.sharding")
+    return sharding.reduce_max(x, device="cuda")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -314,8 +311,9 @@ def main():
     weights = pipeline.FrameWeights(cfg, seed=0)
     streams = [torch.cuda.Stream() for _ in range(S)]
     slots = []
+    sharding = importlib.import_module("dsvt-ai-trt_b200.sharding")
     for i in range(F):
-        seed = rank * F + i                      # frame f -> rank f mod N (weak scaling: F frames per rank)
+        seed = sharding.global_frame_id(rank, world, i)   # frame f -> rank f mod N (weak scaling: F frames per rank)
         cloud = pkg.synth.ring_lidar(args.points, seed=seed)
         slot = Slot(pipeline, cfg, weights, precision, cloud, seed)
         slot.capture(streams[i % S])
@@ -342,10 +340,38 @@ def main():
 
     # gather the results of the last step on rank 0 (the "trivial NCCL result gather")
     boxes = torch.stack([s.frame.boxes[0] for s in slots])
-    if world > 1:
-        import torch.distributed as dist
-        out = [torch.empty_like(boxes) for _ in range(world)] if rank == 0 else None
-        dist.gather(boxes, out, dst=0)
+    valid = torch.cat([s.frame.valid for s in slots])
+    gathered = sharding.gather_results(boxes, valid, dst=0)
+
+    # ---- BASELINE.json configs[2]: same frames, FP16 tensor-core set attention (tolerance 1e-2) ----------------
+    fp16_cfg = None
+    if args.precision == "fp32" and not args.no_fp16_config:
+        slots16 = []
+        for i, s in enumerate(slots):
+            fr = pipeline.HotPathFrame(cfg, weights, precision=capi.DSVT_ATTN_FP16, seed=sharding.global_frame_id(rank, world, i))
+            s16 = Slot.__new__(Slot)
+            s16.frame, s16.n = fr, s.n
+            s16.host_points, s16.host_n, s16.host_boxes, s16.host_valid = s.host_points, s.host_n, s.host_boxes, s.host_valid
+            fr.points.copy_(s.frame.points)
+            fr.points_size.copy_(s.frame.points_size)
+            s16.graph = None
+            s16.capture(streams[i % S])
+            slots16.append(s16)
+        run_steps(slots16, streams, args.warmup, host=False)
+        barrier(world)
+        ms16 = max_over_ranks(run_steps(slots16, streams, args.steps, host=False), world)
+        run_steps(slots16, streams, 1, host=True)
+        barrier(world)
+        e2e16 = max_over_ranks(run_steps(slots16, streams, args.steps, host=True), world)
+        barrier(world)
+        fp16_cfg = {"value": round(F * world * args.steps / (ms16 * 1e-3), 2),
+                    "e2e": round(F * world * args.steps / (e2e16 * 1e-3), 2), "unit": UNIT, "dtype": "f16 operands / f32 accumulate",
+                    "workload": "BASELINE.json configs[2]: same frames, set attention on tcgen05 (FP16), tolerance 1e-2"}
+        if rank == 0:
+            pl16, us16, _ = plugin_breakdown(slots16[0], cfg, peaks)
+            fp16_cfg["set_attention"] = {k: v for k, v in pl16.items() if k.startswith("set_attention")}
+            fp16_cfg["frame_us_sum_of_plugins"] = round(us16, 1)
+        del slots16
 
     if rank != 0:
         return 0
@@ -385,6 +411,8 @@ def main():
         "roofline": roof,
         "plugins": plugins,
         "frame_us_sum_of_plugins": round(frame_us, 1),
+        "fp16_config": fp16_cfg,
+        "gathered_boxes": None if gathered is None else int(gathered[1].sum()),
     }
     if not args.no_cpu_baseline:
         try:

@@ -64,6 +64,10 @@ struct TcBlobView {
     const float* b_out;        // [192]
 };
 
+// phase timestamps of CTA 0's first tile (thread 0): a cheap always-on profile, read with dsvt_debug_tc_profile()
+__device__ long long g_tc_prof[64];
+#define TC_PROF(i) do { if (blockIdx.x == 0 && tid == 0 && tile == (int) blockIdx.x) g_tc_prof[i] = clock64(); } while (0)
+
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -79,6 +83,8 @@ set_attention_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
     __shared__ __align__(8) uint64_t bar_mma, bar_w, bar_w2;
     __shared__ uint32_t tmem_slot;
     __shared__ int s_rows[kRows];
+    __shared__ __align__(16) float s_bias[4 * kC];                   // b_q (pre-scaled) | b_k | b_v | b_out
+    __shared__ __align__(16) float s_mask[kSetsPerTile * kH * kS];   // this tile's additive key masks
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y;
@@ -115,6 +121,7 @@ set_attention_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
         *reinterpret_cast<uint4*>(smem + SM_K + 3 * kChunkStride + t * 16) = make_uint4(0, 0, 0, 0);
         *reinterpret_cast<uint4*>(smem + SM_V + (t >> 3) * 512 + 3 * 128 + (t & 7) * 16) = make_uint4(0, 0, 0, 0);
     }
+    for (int t = tid; t < 4 * kC; t += kThreads) s_bias[t] = __ldg(wb.b_q + t);   // the four bias vectors are contiguous
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -138,12 +145,24 @@ set_attention_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
     const uint32_t idesc_out = make_idesc(kFmtF16, kRows, 96);
     uint32_t ph_mma = 0, ph_w = 0, ph_w2 = 0;                            // mbarrier parities
 
+    // base descriptors (constant for the whole kernel); a K step adds a constant to the address field
+    const uint64_t d_aqk = make_smem_desc(sbase + SM_AQK, kChunkStride, 128);
+    const uint64_t d_av = make_smem_desc(sbase + SM_AV, kChunkStride, 128);
+    const uint64_t d_wqk = make_smem_desc(sbase + SM_W, 48 * 16, 128);
+    const uint64_t d_wv = make_smem_desc(sbase + SM_W + kWqkBytes, 32 * 16, 128);
+    const uint64_t d_q = make_smem_desc(sbase + SM_Q, kChunkStride, 128);
+    const uint64_t d_k = make_smem_desc(sbase + SM_K, kChunkStride, 128);
+    const uint64_t d_v = make_smem_desc(sbase + SM_V, 512, 128);
+    const uint64_t d_wo0 = make_smem_desc(sbase + SM_AV, 96 * 16, 128);
+    const uint64_t d_wo1 = make_smem_desc(sbase + SM_W, 96 * 16, 128);
+
     const int q4 = warp & 3, hf = warp >> 2;
     const int row = q4 * 32 + lane;                                      // this thread's TMEM lane / token row
     const uint32_t tlane = tmem + ((uint32_t) (q4 * 32) << 16);
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int set0 = tile * kSetsPerTile;
+        TC_PROF(0);
         // ---- per-head weight prefetch for head 0 (sW is free: the previous tile's out-proj has completed) ----
         if (tid == 0) {
             mbar_arrive_expect_tx(&bar_w, kWHeadBytes);
@@ -154,27 +173,45 @@ set_attention_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
             const int r = tid, st = set0 + r / kS;
             s_rows[r] = (r < kValidRows && st < ns) ? idx[(size_t) st * kS + (r % kS)] : -1;
         }
+        for (int t = tid; t < kSetsPerTile * kH * kS; t += kThreads) {
+            const int st = set0 + t / (kH * kS);
+            s_mask[t] = st < ns ? __ldg(mask + (size_t) set0 * kH * kS + t) : 0.f;
+        }
         __syncthreads();
         {
             const int r = tid & (kRows - 1);
             const int g = s_rows[r];
             const float4* xr = reinterpret_cast<const float4*>(x + (size_t) (g < 0 ? 0 : g) * kC);
             const float4* pr = reinterpret_cast<const float4*>(pos + (size_t) (g < 0 ? 0 : g) * kC);
-            for (int c = tid >> 7; c < 24; c += 2) {                     // chunk c = channels [8c, 8c+8)
-                uint4 vq = make_uint4(0, 0, 0, 0), vv = vq;
+            // chunk c = channels [8c, 8c+8); 3 chunks (12 independent 16-byte loads) in flight per thread
+            for (int c0 = tid >> 7; c0 < 24; c0 += 6) {
+                float4 a[3][2], p[3][2];
                 if (g >= 0) {
-                    const float4 a0 = __ldg(xr + 2 * c), a1 = __ldg(xr + 2 * c + 1);
-                    const float4 p0 = __ldg(pr + 2 * c), p1 = __ldg(pr + 2 * c + 1);
-                    vv = make_uint4(pack_h2(a0.x, a0.y), pack_h2(a0.z, a0.w), pack_h2(a1.x, a1.y), pack_h2(a1.z, a1.w));
-                    vq = make_uint4(pack_h2(a0.x + p0.x, a0.y + p0.y), pack_h2(a0.z + p0.z, a0.w + p0.w),
-                                    pack_h2(a1.x + p1.x, a1.y + p1.y), pack_h2(a1.z + p1.z, a1.w + p1.w));
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const int c = c0 + 2 * j;
+                        a[j][0] = __ldg(xr + 2 * c); a[j][1] = __ldg(xr + 2 * c + 1);
+                        p[j][0] = __ldg(pr + 2 * c); p[j][1] = __ldg(pr + 2 * c + 1);
+                    }
                 }
-                *reinterpret_cast<uint4*>(smem + SM_AQK + c * kChunkStride + r * 16) = vq;
-                *reinterpret_cast<uint4*>(smem + SM_AV + c * kChunkStride + r * 16) = vv;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int c = c0 + 2 * j;
+                    uint4 vq = make_uint4(0, 0, 0, 0), vv = vq;
+                    if (g >= 0) {
+                        const float4 a0 = a[j][0], a1 = a[j][1], p0 = p[j][0], p1 = p[j][1];
+                        vv = make_uint4(pack_h2(a0.x, a0.y), pack_h2(a0.z, a0.w), pack_h2(a1.x, a1.y), pack_h2(a1.z, a1.w));
+                        vq = make_uint4(pack_h2(a0.x + p0.x, a0.y + p0.y), pack_h2(a0.z + p0.z, a0.w + p0.w),
+                                        pack_h2(a1.x + p1.x, a1.y + p1.y), pack_h2(a1.z + p1.z, a1.w + p1.w));
+                    }
+                    *reinterpret_cast<uint4*>(smem + SM_AQK + c * kChunkStride + r * 16) = vq;
+                    *reinterpret_cast<uint4*>(smem + SM_AV + c * kChunkStride + r * 16) = vv;
+                }
             }
         }
         fence_proxy_async_smem();
         __syncthreads();
+        TC_PROF(1);
 
         // issue the projection MMAs of head `h` (thread 0 only; weights of head h must have landed in sW)
         auto issue_proj = [&](int h) {
@@ -182,14 +219,13 @@ set_attention_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
             mbar_wait(&bar_w, ph_w);
             ph_w ^= 1;
             tc_fence_after_sync();
-#pragma unroll 1
+            uint64_t aq = d_aqk, av = d_av, bq = d_wqk, bv = d_wv;
+#pragma unroll
             for (int ks = 0; ks < 12; ++ks) {                            // K = 192 = 12 x 16
-                const uint64_t aq = make_smem_desc(sbase + SM_AQK + ks * 2 * kChunkStride, kChunkStride, 128);
-                const uint64_t av = make_smem_desc(sbase + SM_AV + ks * 2 * kChunkStride, kChunkStride, 128);
-                const uint64_t bq = make_smem_desc(sbase + SM_W + ks * 2 * (48 * 16), 48 * 16, 128);
-                const uint64_t bv = make_smem_desc(sbase + SM_W + kWqkBytes + ks * 2 * (32 * 16), 32 * 16, 128);
                 umma_f16(tmem + C_QK, aq, bq, idesc_qk, ks > 0);
                 umma_f16(tmem + C_V, av, bv, idesc_v, ks > 0);
+                aq += 2 * kChunkStride / 16; av += 2 * kChunkStride / 16;
+                bq += 2 * 48; bv += 2 * 32;
             }
         };
         if (tid == 0) {
@@ -202,6 +238,7 @@ set_attention_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
             mbar_wait(&bar_mma, ph_mma);
             ph_mma ^= 1;
             tc_fence_after_sync();
+            if (h < 2) TC_PROF(2 + 5 * h);
             if (tid == 0) {                                              // sW is free again: prefetch the next weights
                 if (h + 1 < kH) {
                     mbar_arrive_expect_tx(&bar_w, kWHeadBytes);
@@ -217,60 +254,60 @@ set_attention_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
                 if (hf == 0) {                                           // Q (24) and V d-group 0
                     tmem_ld16(tlane + C_QK, a); tmem_ld8(tlane + C_QK + 16, c8);
                     tmem_ld_wait();
-                    const float* bq = wb.b_q + h * kD;
-                    uint4 v0 = make_uint4(pack_h2(__uint_as_float(a[0]) + __ldg(bq + 0), __uint_as_float(a[1]) + __ldg(bq + 1)),
-                                          pack_h2(__uint_as_float(a[2]) + __ldg(bq + 2), __uint_as_float(a[3]) + __ldg(bq + 3)),
-                                          pack_h2(__uint_as_float(a[4]) + __ldg(bq + 4), __uint_as_float(a[5]) + __ldg(bq + 5)),
-                                          pack_h2(__uint_as_float(a[6]) + __ldg(bq + 6), __uint_as_float(a[7]) + __ldg(bq + 7)));
-                    uint4 v1 = make_uint4(pack_h2(__uint_as_float(a[8]) + __ldg(bq + 8), __uint_as_float(a[9]) + __ldg(bq + 9)),
-                                          pack_h2(__uint_as_float(a[10]) + __ldg(bq + 10), __uint_as_float(a[11]) + __ldg(bq + 11)),
-                                          pack_h2(__uint_as_float(a[12]) + __ldg(bq + 12), __uint_as_float(a[13]) + __ldg(bq + 13)),
-                                          pack_h2(__uint_as_float(a[14]) + __ldg(bq + 14), __uint_as_float(a[15]) + __ldg(bq + 15)));
-                    uint4 v2 = make_uint4(pack_h2(__uint_as_float(c8[0]) + __ldg(bq + 16), __uint_as_float(c8[1]) + __ldg(bq + 17)),
-                                          pack_h2(__uint_as_float(c8[2]) + __ldg(bq + 18), __uint_as_float(c8[3]) + __ldg(bq + 19)),
-                                          pack_h2(__uint_as_float(c8[4]) + __ldg(bq + 20), __uint_as_float(c8[5]) + __ldg(bq + 21)),
-                                          pack_h2(__uint_as_float(c8[6]) + __ldg(bq + 22), __uint_as_float(c8[7]) + __ldg(bq + 23)));
+                    const float* bq = s_bias + h * kD;
+                    uint4 v0 = make_uint4(pack_h2(__uint_as_float(a[0]) + bq[0], __uint_as_float(a[1]) + bq[1]),
+                                          pack_h2(__uint_as_float(a[2]) + bq[2], __uint_as_float(a[3]) + bq[3]),
+                                          pack_h2(__uint_as_float(a[4]) + bq[4], __uint_as_float(a[5]) + bq[5]),
+                                          pack_h2(__uint_as_float(a[6]) + bq[6], __uint_as_float(a[7]) + bq[7]));
+                    uint4 v1 = make_uint4(pack_h2(__uint_as_float(a[8]) + bq[8], __uint_as_float(a[9]) + bq[9]),
+                                          pack_h2(__uint_as_float(a[10]) + bq[10], __uint_as_float(a[11]) + bq[11]),
+                                          pack_h2(__uint_as_float(a[12]) + bq[12], __uint_as_float(a[13]) + bq[13]),
+                                          pack_h2(__uint_as_float(a[14]) + bq[14], __uint_as_float(a[15]) + bq[15]));
+                    uint4 v2 = make_uint4(pack_h2(__uint_as_float(c8[0]) + bq[16], __uint_as_float(c8[1]) + bq[17]),
+                                          pack_h2(__uint_as_float(c8[2]) + bq[18], __uint_as_float(c8[3]) + bq[19]),
+                                          pack_h2(__uint_as_float(c8[4]) + bq[20], __uint_as_float(c8[5]) + bq[21]),
+                                          pack_h2(__uint_as_float(c8[6]) + bq[22], __uint_as_float(c8[7]) + bq[23]));
                     *reinterpret_cast<uint4*>(smem + SM_Q + 0 * kChunkStride + row * 16) = v0;
                     *reinterpret_cast<uint4*>(smem + SM_Q + 1 * kChunkStride + row * 16) = v1;
                     *reinterpret_cast<uint4*>(smem + SM_Q + 2 * kChunkStride + row * 16) = v2;
                     tmem_ld8(tlane + C_V, c8);
                     tmem_ld_wait();
-                    const float* bv = wb.b_v + h * kD;
-                    uint4 w0 = make_uint4(pack_h2(__uint_as_float(c8[0]) + __ldg(bv + 0), __uint_as_float(c8[1]) + __ldg(bv + 1)),
-                                          pack_h2(__uint_as_float(c8[2]) + __ldg(bv + 2), __uint_as_float(c8[3]) + __ldg(bv + 3)),
-                                          pack_h2(__uint_as_float(c8[4]) + __ldg(bv + 4), __uint_as_float(c8[5]) + __ldg(bv + 5)),
-                                          pack_h2(__uint_as_float(c8[6]) + __ldg(bv + 6), __uint_as_float(c8[7]) + __ldg(bv + 7)));
+                    const float* bv = s_bias + 2 * kC + h * kD;
+                    uint4 w0 = make_uint4(pack_h2(__uint_as_float(c8[0]) + bv[0], __uint_as_float(c8[1]) + bv[1]),
+                                          pack_h2(__uint_as_float(c8[2]) + bv[2], __uint_as_float(c8[3]) + bv[3]),
+                                          pack_h2(__uint_as_float(c8[4]) + bv[4], __uint_as_float(c8[5]) + bv[5]),
+                                          pack_h2(__uint_as_float(c8[6]) + bv[6], __uint_as_float(c8[7]) + bv[7]));
                     *reinterpret_cast<uint4*>(smem + SM_V + (row >> 3) * 512 + 0 * 128 + (row & 7) * 16) = w0;
                 } else {                                                 // K (24) and V d-groups 1, 2
                     tmem_ld16(tlane + C_QK + 24, a); tmem_ld8(tlane + C_QK + 40, c8);
                     tmem_ld_wait();
-                    const float* bk = wb.b_k + h * kD;
-                    uint4 v0 = make_uint4(pack_h2(__uint_as_float(a[0]) + __ldg(bk + 0), __uint_as_float(a[1]) + __ldg(bk + 1)),
-                                          pack_h2(__uint_as_float(a[2]) + __ldg(bk + 2), __uint_as_float(a[3]) + __ldg(bk + 3)),
-                                          pack_h2(__uint_as_float(a[4]) + __ldg(bk + 4), __uint_as_float(a[5]) + __ldg(bk + 5)),
-                                          pack_h2(__uint_as_float(a[6]) + __ldg(bk + 6), __uint_as_float(a[7]) + __ldg(bk + 7)));
-                    uint4 v1 = make_uint4(pack_h2(__uint_as_float(a[8]) + __ldg(bk + 8), __uint_as_float(a[9]) + __ldg(bk + 9)),
-                                          pack_h2(__uint_as_float(a[10]) + __ldg(bk + 10), __uint_as_float(a[11]) + __ldg(bk + 11)),
-                                          pack_h2(__uint_as_float(a[12]) + __ldg(bk + 12), __uint_as_float(a[13]) + __ldg(bk + 13)),
-                                          pack_h2(__uint_as_float(a[14]) + __ldg(bk + 14), __uint_as_float(a[15]) + __ldg(bk + 15)));
-                    uint4 v2 = make_uint4(pack_h2(__uint_as_float(c8[0]) + __ldg(bk + 16), __uint_as_float(c8[1]) + __ldg(bk + 17)),
-                                          pack_h2(__uint_as_float(c8[2]) + __ldg(bk + 18), __uint_as_float(c8[3]) + __ldg(bk + 19)),
-                                          pack_h2(__uint_as_float(c8[4]) + __ldg(bk + 20), __uint_as_float(c8[5]) + __ldg(bk + 21)),
-                                          pack_h2(__uint_as_float(c8[6]) + __ldg(bk + 22), __uint_as_float(c8[7]) + __ldg(bk + 23)));
+                    const float* bk = s_bias + kC + h * kD;
+                    uint4 v0 = make_uint4(pack_h2(__uint_as_float(a[0]) + bk[0], __uint_as_float(a[1]) + bk[1]),
+                                          pack_h2(__uint_as_float(a[2]) + bk[2], __uint_as_float(a[3]) + bk[3]),
+                                          pack_h2(__uint_as_float(a[4]) + bk[4], __uint_as_float(a[5]) + bk[5]),
+                                          pack_h2(__uint_as_float(a[6]) + bk[6], __uint_as_float(a[7]) + bk[7]));
+                    uint4 v1 = make_uint4(pack_h2(__uint_as_float(a[8]) + bk[8], __uint_as_float(a[9]) + bk[9]),
+                                          pack_h2(__uint_as_float(a[10]) + bk[10], __uint_as_float(a[11]) + bk[11]),
+                                          pack_h2(__uint_as_float(a[12]) + bk[12], __uint_as_float(a[13]) + bk[13]),
+                                          pack_h2(__uint_as_float(a[14]) + bk[14], __uint_as_float(a[15]) + bk[15]));
+                    uint4 v2 = make_uint4(pack_h2(__uint_as_float(c8[0]) + bk[16], __uint_as_float(c8[1]) + bk[17]),
+                                          pack_h2(__uint_as_float(c8[2]) + bk[18], __uint_as_float(c8[3]) + bk[19]),
+                                          pack_h2(__uint_as_float(c8[4]) + bk[20], __uint_as_float(c8[5]) + bk[21]),
+                                          pack_h2(__uint_as_float(c8[6]) + bk[22], __uint_as_float(c8[7]) + bk[23]));
                     *reinterpret_cast<uint4*>(smem + SM_K + 0 * kChunkStride + row * 16) = v0;
                     *reinterpret_cast<uint4*>(smem + SM_K + 1 * kChunkStride + row * 16) = v1;
                     *reinterpret_cast<uint4*>(smem + SM_K + 2 * kChunkStride + row * 16) = v2;
                     tmem_ld16(tlane + C_V + 8, a);
                     tmem_ld_wait();
-                    const float* bv = wb.b_v + h * kD + 8;
-                    uint4 w1 = make_uint4(pack_h2(__uint_as_float(a[0]) + __ldg(bv + 0), __uint_as_float(a[1]) + __ldg(bv + 1)),
-                                          pack_h2(__uint_as_float(a[2]) + __ldg(bv + 2), __uint_as_float(a[3]) + __ldg(bv + 3)),
-                                          pack_h2(__uint_as_float(a[4]) + __ldg(bv + 4), __uint_as_float(a[5]) + __ldg(bv + 5)),
-                                          pack_h2(__uint_as_float(a[6]) + __ldg(bv + 6), __uint_as_float(a[7]) + __ldg(bv + 7)));
-                    uint4 w2 = make_uint4(pack_h2(__uint_as_float(a[8]) + __ldg(bv + 8), __uint_as_float(a[9]) + __ldg(bv + 9)),
-                                          pack_h2(__uint_as_float(a[10]) + __ldg(bv + 10), __uint_as_float(a[11]) + __ldg(bv + 11)),
-                                          pack_h2(__uint_as_float(a[12]) + __ldg(bv + 12), __uint_as_float(a[13]) + __ldg(bv + 13)),
-                                          pack_h2(__uint_as_float(a[14]) + __ldg(bv + 14), __uint_as_float(a[15]) + __ldg(bv + 15)));
+                    const float* bv = s_bias + 2 * kC + h * kD + 8;
+                    uint4 w1 = make_uint4(pack_h2(__uint_as_float(a[0]) + bv[0], __uint_as_float(a[1]) + bv[1]),
+                                          pack_h2(__uint_as_float(a[2]) + bv[2], __uint_as_float(a[3]) + bv[3]),
+                                          pack_h2(__uint_as_float(a[4]) + bv[4], __uint_as_float(a[5]) + bv[5]),
+                                          pack_h2(__uint_as_float(a[6]) + bv[6], __uint_as_float(a[7]) + bv[7]));
+                    uint4 w2 = make_uint4(pack_h2(__uint_as_float(a[8]) + bv[8], __uint_as_float(a[9]) + bv[9]),
+                                          pack_h2(__uint_as_float(a[10]) + bv[10], __uint_as_float(a[11]) + bv[11]),
+                                          pack_h2(__uint_as_float(a[12]) + bv[12], __uint_as_float(a[13]) + bv[13]),
+                                          pack_h2(__uint_as_float(a[14]) + bv[14], __uint_as_float(a[15]) + bv[15]));
                     *reinterpret_cast<uint4*>(smem + SM_V + (row >> 3) * 512 + 1 * 128 + (row & 7) * 16) = w1;
                     *reinterpret_cast<uint4*>(smem + SM_V + (row >> 3) * 512 + 2 * 128 + (row & 7) * 16) = w2;
                 }
@@ -278,20 +315,19 @@ set_attention_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
             fence_proxy_async_smem();
             tc_fence_before_sync();
             __syncthreads();
+            if (h < 2) TC_PROF(3 + 5 * h);
             // ---- S = Q_h K_h^T -------------------------------------------------------------------------------------------
             if (tid == 0) {
                 tc_fence_after_sync();
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {                         // K = 32 (24 + zero padding)
-                    const uint64_t ad = make_smem_desc(sbase + SM_Q + ks * 2 * kChunkStride, kChunkStride, 128);
-                    const uint64_t bd = make_smem_desc(sbase + SM_K + ks * 2 * kChunkStride, kChunkStride, 128);
-                    umma_f16(tmem + C_S, ad, bd, idesc_s, ks > 0);
-                }
+                for (int ks = 0; ks < 2; ++ks)                           // K = 32 (24 + zero padding)
+                    umma_f16(tmem + C_S, d_q + ks * (2 * kChunkStride / 16), d_k + ks * (2 * kChunkStride / 16), idesc_s, ks > 0);
                 umma_commit(&bar_mma);
             }
             mbar_wait(&bar_mma, ph_mma);
             ph_mma ^= 1;
             tc_fence_after_sync();
+            if (h < 2) TC_PROF(4 + 5 * h);
             // ---- softmax over the row's own set (warps 0..3: one thread per token row) ----------------------------------
             if (warp < 4) {
                 const int a_set = warp == 0 ? 0 : warp - 1;              // first set touched by this warp's 32 rows
@@ -314,19 +350,21 @@ set_attention_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
                 const int st = set0 + sl;
                 const bool live = (row < kValidRows) && (st < ns);
                 if (live) {
-                    const float4* mk = reinterpret_cast<const float4*>(mask + ((size_t) st * kH + h) * kS);
+                    const float4* mk = reinterpret_cast<const float4*>(s_mask + (sl * kH + h) * kS);
 #pragma unroll
                     for (int k4 = 0; k4 < kS / 4; ++k4) {
-                        const float4 m = __ldg(mk + k4);
+                        const float4 m = mk[k4];
                         s[4 * k4 + 0] += m.x; s[4 * k4 + 1] += m.y; s[4 * k4 + 2] += m.z; s[4 * k4 + 3] += m.w;
                     }
                 }
-                float mx = s[0];
+                float m4[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
-                for (int k = 1; k < kS; ++k) mx = fmaxf(mx, s[k]);
-                float sum = 0.f;
+                for (int k = 4; k < kS; ++k) m4[k & 3] = fmaxf(m4[k & 3], s[k]);
+                const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                float a4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int k = 0; k < kS; ++k) { s[k] = exp2f((s[k] - mx) * 1.4426950408889634f); sum += s[k]; }
+                for (int k = 0; k < kS; ++k) { s[k] = exp2f((s[k] - mx) * 1.4426950408889634f); a4[k & 3] += s[k]; }
+                const float sum = (a4[0] + a4[1]) + (a4[2] + a4[3]);
                 const float inv = live ? 1.0f / sum : 0.f;               // padding rows carry an all-zero P row
                 uint32_t pk[18];
 #pragma unroll
@@ -346,22 +384,23 @@ set_attention_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
             }
             tc_fence_before_sync();
             __syncthreads();
+            if (h < 2) TC_PROF(5 + 5 * h);
             // ---- O_h = P V_h, then (pipelined behind it) the next head's projections ------------------------------------
             if (tid == 0) {
                 tc_fence_after_sync();
 #pragma unroll
-                for (int ks = 0; ks < kKeys / 16; ++ks) {                // K = 112 keys = 7 x 16
-                    const uint64_t bd = make_smem_desc(sbase + SM_V + ks * 1024, 512, 128);
-                    umma_f16_ts(tmem + C_O + 32 * h, tmem + C_P + 8 * ks, bd, idesc_pv, ks > 0);
-                }
+                for (int ks = 0; ks < kKeys / 16; ++ks)                  // K = 112 keys = 7 x 16
+                    umma_f16_ts(tmem + C_O + 32 * h, tmem + C_P + 8 * ks, d_v + ks * (1024 / 16), idesc_pv, ks > 0);
                 if (h + 1 < kH) issue_proj(h + 1);
                 umma_commit(&bar_mma);
             }
+            if (h < 2) TC_PROF(6 + 5 * h);
         }
         // ---- all heads done: O (TMEM) -> FP16 operand tile (aliases sAqk); Wout rows 0..95 -> sAv ------------------------
         mbar_wait(&bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after_sync();
+        TC_PROF(20);
         if (tid == 0) {
             mbar_arrive_expect_tx(&bar_w2, kWoutHalfBytes);              // own barrier: bar_w may still be mid-phase
             bulk_g2s(smem + SM_AV, wb.w_img + (size_t) kH * kWHeadBytes, kWoutHalfBytes, &bar_w2);
@@ -385,51 +424,60 @@ set_attention_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
         fence_proxy_async_smem();
         tc_fence_before_sync();
         __syncthreads();
+        TC_PROF(21);
         // ---- out-projection: [128x192] = O . Wout^T as two N = 96 halves ---------------------------------------------------
         if (tid == 0) {
             tc_fence_after_sync();
             mbar_wait(&bar_w, ph_w); ph_w ^= 1;                          // Wout rows 96..191 (sW), issued during head 7
             mbar_wait(&bar_w2, ph_w2); ph_w2 ^= 1;                       // Wout rows 0..95 (sAv)
             tc_fence_after_sync();
-#pragma unroll 1
+#pragma unroll
             for (int ks = 0; ks < 12; ++ks) {
-                const uint64_t ad = make_smem_desc(sbase + SM_AQK + ks * 2 * kChunkStride, kChunkStride, 128);
-                const uint64_t b0 = make_smem_desc(sbase + SM_AV + ks * 2 * (96 * 16), 96 * 16, 128);
-                const uint64_t b1 = make_smem_desc(sbase + SM_W + ks * 2 * (96 * 16), 96 * 16, 128);
-                umma_f16(tmem + C_OUT, ad, b0, idesc_out, ks > 0);
-                umma_f16(tmem + C_OUT + 96, ad, b1, idesc_out, ks > 0);
+                umma_f16(tmem + C_OUT, d_aqk + ks * (2 * kChunkStride / 16), d_wo0 + ks * (2 * 96), idesc_out, ks > 0);
+                umma_f16(tmem + C_OUT + 96, d_aqk + ks * (2 * kChunkStride / 16), d_wo1 + ks * (2 * 96), idesc_out, ks > 0);
             }
             umma_commit(&bar_mma);
         }
         mbar_wait(&bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after_sync();
-        // ---- final epilogue: + bias, scatter the row to its voxel (MapSetFeature2Voxel) ------------------------------------
+        TC_PROF(22);
+        // ---- final epilogue: + bias -> FP32 tile in shared memory (sAqk|sAv are free), then coalesced row scatter
+        //      to the voxel rows (MapSetFeature2Voxel) --------------------------------------------------------------------
         {
-            const int g = s_rows[row];
-            float* dst = out + (size_t) (g < 0 ? 0 : g) * kC + hf * 96;
-            const float* bo = wb.b_out + hf * 96;
+            constexpr int kOutStride = 196;                              // floats; conflict-free 16-byte row writes
+            float* s_out = reinterpret_cast<float*>(smem + SM_AQK);     // 108 x 196 x 4 B = 84672 <= 98304
+            const float* bo = s_bias + 3 * kC + hf * 96;
 #pragma unroll 1
             for (int j0 = 0; j0 < 96; j0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tlane + C_OUT + hf * 96 + j0, r);
                 tmem_ld_wait();
-                if (g >= 0) {
+                if (row < kValidRows) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         float4 o;
-                        o.x = __uint_as_float(r[j + 0]) + __ldg(bo + j0 + j + 0);
-                        o.y = __uint_as_float(r[j + 1]) + __ldg(bo + j0 + j + 1);
-                        o.z = __uint_as_float(r[j + 2]) + __ldg(bo + j0 + j + 2);
-                        o.w = __uint_as_float(r[j + 3]) + __ldg(bo + j0 + j + 3);
-                        *reinterpret_cast<float4*>(dst + j0 + j) = o;
+                        o.x = __uint_as_float(r[j + 0]) + bo[j0 + j + 0];
+                        o.y = __uint_as_float(r[j + 1]) + bo[j0 + j + 1];
+                        o.z = __uint_as_float(r[j + 2]) + bo[j0 + j + 2];
+                        o.w = __uint_as_float(r[j + 3]) + bo[j0 + j + 3];
+                        *reinterpret_cast<float4*>(s_out + row * kOutStride + hf * 96 + j0 + j) = o;
                     }
                 }
+            }
+            __syncthreads();
+            for (int i = tid; i < kValidRows * (kC / 4); i += kThreads) {
+                const int rr = i / (kC / 4), c4 = i - rr * (kC / 4);
+                const int g = s_rows[rr];
+                if (g >= 0)
+                    *reinterpret_cast<float4*>(out + (size_t) g * kC + c4 * 4) =
+                        *reinterpret_cast<const float4*>(s_out + rr * kOutStride + c4 * 4);
             }
         }
         tc_fence_before_sync();
         __syncthreads();          // smem tiles, s_rows and the TMEM accumulators are recycled by the next tile
         tc_fence_after_sync();
+        TC_PROF(23);
     }
     if (warp == 0) tmem_dealloc<512>(tmem);
 }
@@ -504,3 +552,7 @@ int set_attention_tc_fused(const dsvt_set_attention_params* p, const void* tc_bl
 }
 
 }  // namespace dsvt
+
+extern "C" int dsvt_debug_tc_profile(long long* out64) {
+    return cudaMemcpyFromSymbol(out64, dsvt::g_tc_prof, sizeof(long long) * 64) == cudaSuccess ? 0 : 1;
+}
