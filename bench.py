@@ -230,7 +230,17 @@ def plugin_breakdown(slot, cfg, peaks, reps=3):
     res["layer_norm"] = {"us": us, "bytes": 2 * 4 * C * V + 2 * 4 * C, "calls_per_frame": 0}
     us = timed(lambda: capi.layer_norm(f.attn_out, f.vox.pillar_num, w.gamma[0], w.beta[0], cfg.layer_norm_eps,
                                        residual=f.x0, out=f.src))
-    res["layer_norm_residual"] = {"us": us, "bytes": 3 * 4 * C * V + 2 * 4 * C, "calls_per_frame": 28}
+    fused = getattr(f, "fuse_ln", False)
+    res["layer_norm_residual"] = {"us": us, "bytes": 3 * 4 * C * V + 2 * 4 * C, "calls_per_frame": 8 if fused else 28}
+    if fused:      # 20 of the 28 LayerNorm plugins run as 4 two-stage + 4 three-stage chained launches per frame
+        st2 = [(f.ffn_out, w.gamma[1], w.beta[1]), (f.x0, w.gamma[2], w.beta[2])]
+        st3 = st2 + [(f.x0, w.gamma[3], w.beta[3])]
+        us = timed(lambda: capi.layer_norm_chain(f.src, f.vox.pillar_num, st2, cfg.layer_norm_eps, out=f.src_b))
+        res["layer_norm_chain2"] = {"us": us, "bytes": 2 * (2 * 4 * C * V + 2 * 4 * C), "calls_per_frame": 4,
+                                    "note": "bytes = 2 LayerNorm plugins' algorithmic bytes; the chain moves 4 row passes"}
+        us = timed(lambda: capi.layer_norm_chain(f.src, f.vox.pillar_num, st3, cfg.layer_norm_eps, out=f.src_b))
+        res["layer_norm_chain3"] = {"us": us, "bytes": 3 * (2 * 4 * C * V + 2 * 4 * C), "calls_per_frame": 4,
+                                    "note": "bytes = 3 LayerNorm plugins' algorithmic bytes; the chain moves 5 row passes"}
     us = timed(lambda: capi.filter_box(cfg, *f.cand, boxes=f.boxes, valid=f.valid))
     res["filter_box"] = {"us": us, "bytes": 22000 + 18004, "calls_per_frame": 1}
     for i in (0, 1):

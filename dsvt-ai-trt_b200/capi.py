@@ -231,6 +231,24 @@ def layer_norm(x, voxel_num, gamma, beta, eps=0.0, residual=None, out=None, zero
     return out
 
 
+class LnStage(Structure):
+    _fields_ = [("residual", c_void_p), ("gamma", c_void_p), ("beta", c_void_p)]
+
+
+def layer_norm_chain(x, voxel_num, stages, eps=0.0, out=None, zero_tails=1):
+    """stages: list of (residual_or_None, gamma, beta); y = LN_n(...LN_1(x + r_1)... + r_n) in one launch."""
+    _need(x, torch.float32, "x")
+    B = x.shape[0] if x.dim() == 3 else 1
+    out = torch.empty_like(x) if out is None else out
+    arr = (LnStage * len(stages))()
+    for i, (r, g, b) in enumerate(stages):
+        arr[i] = LnStage(r.data_ptr() if r is not None else None, g.data_ptr(), b.data_ptr())
+    p = LNParams(B, x.shape[-2], x.shape[-1], eps, zero_tails)
+    _check(_lib().dsvt_layer_norm_chain_launch(ctypes.byref(p), _ptr(x), _ptr(voxel_num), arr, c_int32(len(stages)),
+                                               _ptr(out), _stream()), "dsvt_layer_norm_chain_launch")
+    return out
+
+
 def filter_box(cfg, scores, classes, xs, ys, center, center_z, angle, dim, boxes=None, valid=None, zero_tails=1):
     B = scores.shape[0] if scores.dim() == 2 else 1
     K = cfg.max_top_k

@@ -16,61 +16,96 @@ namespace dsvt {
 namespace {
 
 constexpr int kC = 192;
-constexpr int kThreadsA = 384;
-constexpr int kXs = 196;   // token-tile row stride (float4 aligned, broadcast reads)
-constexpr int kQs = 193;   // Q/K/V row stride (odd: conflict-free column walks)
+constexpr int kThreadsA = 288;            // 48 column groups (4 columns each) x 6 row groups
+constexpr int kColGroups = kC / 4;        // 48
+constexpr int kRowGroups = kThreadsA / kColGroups;   // 6
+constexpr int kXs = 196;                  // row stride (floats) of every tile: 49 x 16 B, odd in 16-byte units ->
+                                          // conflict-free 128-bit accesses whether lanes walk rows or columns
+constexpr int kHeadGroup = 4;             // heads whose score matrices are resident at a time
 
+// Per set: X (token tile) and the score buffer of one head group share a region (X is dead once V is projected);
+// the attention output O is written in place over Q (head h's Q columns are dead after head h's scores).
+// S = 36: 4 x 28.2 KB = 112.9 KB per CTA -> two CTAs (18 warps) per SM.  (A variant with two sets per CTA and one CTA
+// per SM was measured 20 % slower: halving the warps hurts the score / softmax / PV phases more than sharing the
+// weight stream helps.)
 template <int S> struct AttnSmem {
-    static constexpr int x = 0;
-    static constexpr int q = x + S * kXs;
-    static constexpr int k = q + S * kQs;
-    static constexpr int v = k + S * kQs;
-    static constexpr int s = v + S * kQs;
-    static constexpr int total = s + 8 * S * (S + 1);
+    static constexpr int NS = 1;     // sets per CTA (2 was measured slower: 9 warps/SM starve the non-GEMM phases)
+    static constexpr int tile = S * kXs;
+    static constexpr int sc_floats = kHeadGroup * S * (S + 1);
+    static constexpr int xreg = tile > sc_floats ? tile : sc_floats;
+    static constexpr int x = 0;                       // [NS][xreg]
+    static constexpr int q = x + NS * xreg;           // [NS][tile]
+    static constexpr int k = q + NS * tile;
+    static constexpr int v = k + NS * tile;
+    static constexpr int total = v + NS * tile;
 };
 
-// out[r][n] = (sum_k X[r][k] * Wt[k][n] + bias[n]) / div   for r in this thread's half of the rows
-template <int S, bool TO_GLOBAL>
-__device__ __forceinline__ void project(const float* __restrict__ Xs, const float* __restrict__ Wt, int ldw,
-                                        const float* __restrict__ bias, float div, float* out_s,
-                                        float* out_g, const int* row_map, int C)
+// out[s][r][4cg..4cg+3] = (sum_k X[s][r][k] * Wt[k][4cg..] + bias) / div for this thread's R rows of each of the NS sets.
+// Register tile (NS*R) x 4: per 4 k-values a thread issues NS*R broadcast LDS.128 (x) + 4 coalesced LDG.128 (weights,
+// prefetched TWO steps ahead) for 16*NS*R FMAs, so neither the shared-memory crossbar nor the L2 latency limits the
+// FMA pipe (version 1 of this kernel: 4 FMAs per LDS.128, crossbar-bound at 15 TFLOP/s).
+template <int S, int NS, bool TO_GLOBAL>
+__device__ __forceinline__ void project(const float* __restrict__ Xs, int x_set_stride, const float* __restrict__ Wt,
+                                        int ldw, const float* __restrict__ bias, float div, float* out_s,
+                                        float* const* out_g, const int* row_map, const bool* live)
 {
-    constexpr int R = S / 2;
-    const int n = threadIdx.x % kC;
-    const int r0 = (threadIdx.x / kC) * R;
-    float acc[R];
+    constexpr int R = S / kRowGroups;
+    const int cg = threadIdx.x % kColGroups;
+    const int r0 = (threadIdx.x / kColGroups) * R;
+    float acc[NS][R][4];
 #pragma unroll
-    for (int r = 0; r < R; ++r) acc[r] = 0.f;
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int r = 0; r < R; ++r) { acc[s][r][0] = 0.f; acc[s][r][1] = 0.f; acc[s][r][2] = 0.f; acc[s][r][3] = 0.f; }
+    const float4* wp = reinterpret_cast<const float4*>(Wt) + cg;
+    const int ld4 = ldw / 4;
+    float4 w0[4], w1[4];                       // weights of the next two k-steps
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) { w0[kk] = __ldg(wp + (size_t) kk * ld4); w1[kk] = __ldg(wp + (size_t) (4 + kk) * ld4); }
+#pragma unroll 1
     for (int k = 0; k < kC; k += 4) {
-        const float w0 = __ldg(Wt + (size_t) (k + 0) * ldw + n);
-        const float w1 = __ldg(Wt + (size_t) (k + 1) * ldw + n);
-        const float w2 = __ldg(Wt + (size_t) (k + 2) * ldw + n);
-        const float w3 = __ldg(Wt + (size_t) (k + 3) * ldw + n);
+        float4 wc[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) { wc[kk] = w0[kk]; w0[kk] = w1[kk]; }
+        if (k + 8 < kC) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) w1[kk] = __ldg(wp + (size_t) (k + 8 + kk) * ld4);
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float4 xv = *reinterpret_cast<const float4*>(Xs + s * x_set_stride + (r0 + r) * kXs + k);
+                const float xk[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    acc[s][r][0] = fmaf(xk[kk], wc[kk].x, acc[s][r][0]);
+                    acc[s][r][1] = fmaf(xk[kk], wc[kk].y, acc[s][r][1]);
+                    acc[s][r][2] = fmaf(xk[kk], wc[kk].z, acc[s][r][2]);
+                    acc[s][r][3] = fmaf(xk[kk], wc[kk].w, acc[s][r][3]);
+                }
+            }
+    }
+    const float4 bn = __ldg(reinterpret_cast<const float4*>(bias) + cg);
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const float4 xv = *reinterpret_cast<const float4*>(Xs + (r0 + r) * kXs + k);
-            acc[r] = fmaf(xv.x, w0, acc[r]);
-            acc[r] = fmaf(xv.y, w1, acc[r]);
-            acc[r] = fmaf(xv.z, w2, acc[r]);
-            acc[r] = fmaf(xv.w, w3, acc[r]);
+            float4 o = make_float4(acc[s][r][0] + bn.x, acc[s][r][1] + bn.y, acc[s][r][2] + bn.z, acc[s][r][3] + bn.w);
+            if (div != 1.0f) { o.x = o.x / div; o.y = o.y / div; o.z = o.z / div; o.w = o.w / div; }
+            if (TO_GLOBAL) {
+                if (live[s]) {
+                    const int row = row_map ? row_map[s * S + r0 + r] : (r0 + r);
+                    *reinterpret_cast<float4*>(out_g[s] + (size_t) row * kC + cg * 4) = o;
+                }
+            } else {
+                *reinterpret_cast<float4*>(out_s + s * (S * kXs) + (r0 + r) * kXs + cg * 4) = o;
+            }
         }
-    }
-    const float bn = __ldg(bias + n);
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        float o = acc[r] + bn;
-        if (div != 1.0f) o = o / div;
-        if (TO_GLOBAL) {
-            const int row = row_map ? row_map[r0 + r] : (r0 + r);
-            out_g[(size_t) row * C + n] = o;
-        } else {
-            out_s[(r0 + r) * kQs + n] = o;
-        }
-    }
 }
 
 template <int S, bool FUSED>
-__global__ void __launch_bounds__(kThreadsA, 1)
+__global__ void __launch_bounds__(kThreadsA, (S <= 36) ? 2 : 1)
 set_attention_fp32_kernel(const float* __restrict__ qin, const float* __restrict__ kin, const float* __restrict__ vin,
                           const float* __restrict__ pos, const int* __restrict__ idx,
                           const float* __restrict__ mask, const int* __restrict__ set_num,
@@ -79,59 +114,79 @@ set_attention_fp32_kernel(const float* __restrict__ qin, const float* __restrict
 {
     extern __shared__ __align__(16) float sm[];
     using L = AttnSmem<S>;
-    float* Xs = sm + L::x;
-    float* Qs = sm + L::q;
+    constexpr int NS = L::NS;
+    constexpr int TILE = L::tile;
+    float* Xs = sm + L::x;      // [NS][xreg]
+    float* Qs = sm + L::q;      // [NS][tile]; becomes the attention output O in place
     float* Ks = sm + L::k;
     float* Vs = sm + L::v;
-    float* Ss = sm + L::s;
-    __shared__ int s_rows[S];
+    float* Ss = sm + L::x;      // scores of one head group per set, aliases the (dead) token tile
+    __shared__ int s_rows[NS * S];
 
     constexpr int H = 8, D = kC / H;
     const int b = blockIdx.y;
-    const int set = blockIdx.x;
+    const int set0 = blockIdx.x * NS;
     const int tid = threadIdx.x;
     int ns = set_num ? set_num[b] : max_sets;
     ns = ns < max_sets ? ns : max_sets;
 
-    if (set >= ns) {
+    if (set0 >= ns) {
         if (!zero_tails) return;
         if (!FUSED) {
-            float4* o = reinterpret_cast<float4*>(out + ((size_t) b * max_sets + set) * S * kC);
-            for (int t = tid; t < S * kC / 4; t += kThreadsA) o[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s = 0; s < NS; ++s) {
+                if (set0 + s >= max_sets) break;
+                float4* o = reinterpret_cast<float4*>(out + ((size_t) b * max_sets + set0 + s) * S * kC);
+                for (int t = tid; t < S * kC / 4; t += kThreadsA) o[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         } else {
             // tail rows [voxel_num, max_pillars) are split over the idle CTAs
             int V = voxel_num[b];
             V = V < max_pillars ? V : max_pillars;
-            const int idle = max_sets - ns;
+            const int first_idle = (ns + NS - 1) / NS;
+            const int idle = (int) gridDim.x - first_idle;
             const long long tail = (long long) (max_pillars - V) * (kC / 4);
             const long long per = (tail + idle - 1) / idle;
-            long long lo = (long long) (set - ns) * per, hi = lo + per;
+            long long lo = (long long) ((int) blockIdx.x - first_idle) * per, hi = lo + per;
             if (hi > tail) hi = tail;
             float4* o = reinterpret_cast<float4*>(out + ((size_t) b * max_pillars + V) * kC);
             for (long long t = lo + tid; t < hi; t += kThreadsA) o[t] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         return;
     }
+    bool live[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) live[s] = set0 + s < ns;
+    if (!FUSED && zero_tails) {                       // an odd trailing set of the pair: zero its output rows
+        for (int s = 0; s < NS; ++s) {
+            if (live[s] || set0 + s >= max_sets) continue;
+            float4* o = reinterpret_cast<float4*>(out + ((size_t) b * max_sets + set0 + s) * S * kC);
+            for (int t = tid; t < S * kC / 4; t += kThreadsA) o[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
 
-    const int* my_idx = FUSED ? idx + (((size_t) b * 2 + axis) * max_sets + set) * S : nullptr;
-    if (FUSED && tid < S) s_rows[tid] = my_idx[tid];
+    if (FUSED) {
+        const int* my_idx = idx + (((size_t) b * 2 + axis) * max_sets + set0) * S;
+        for (int t = tid; t < NS * S; t += kThreadsA) s_rows[t] = live[t / S] ? my_idx[t] : 0;
+    }
     __syncthreads();
 
     auto load_tile = [&](const float* src_plain, bool add_pos) {
-        for (int t = tid; t < S * (kC / 4); t += kThreadsA) {
-            const int r = t / (kC / 4), c4 = t - r * (kC / 4);
-            float4 val;
-            if (FUSED) {
-                const size_t row = (size_t) b * max_pillars + s_rows[r];
-                val = __ldg(reinterpret_cast<const float4*>(qin + row * kC) + c4);
-                if (add_pos) {
-                    const float4 pp = __ldg(reinterpret_cast<const float4*>(pos + row * kC) + c4);
-                    val.x += pp.x; val.y += pp.y; val.z += pp.z; val.w += pp.w;
+        for (int t = tid; t < NS * S * (kC / 4); t += kThreadsA) {
+            const int sr = t / (kC / 4), c4 = t - sr * (kC / 4), s = sr / S, r = sr - s * S;
+            float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live[s]) {
+                if (FUSED) {
+                    const size_t row = (size_t) b * max_pillars + s_rows[sr];
+                    val = __ldg(reinterpret_cast<const float4*>(qin + row * kC) + c4);
+                    if (add_pos) {
+                        const float4 pp = __ldg(reinterpret_cast<const float4*>(pos + row * kC) + c4);
+                        val.x += pp.x; val.y += pp.y; val.z += pp.z; val.w += pp.w;
+                    }
+                } else {
+                    val = __ldg(reinterpret_cast<const float4*>(src_plain + (((size_t) b * max_sets + set0 + s) * S + r) * kC) + c4);
                 }
-            } else {
-                val = __ldg(reinterpret_cast<const float4*>(src_plain + (((size_t) b * max_sets + set) * S + r) * kC) + c4);
             }
-            *reinterpret_cast<float4*>(Xs + r * kXs + c4 * 4) = val;
+            *reinterpret_cast<float4*>(Xs + s * L::xreg + r * kXs + c4 * 4) = val;
         }
     };
 
@@ -139,59 +194,90 @@ set_attention_fp32_kernel(const float* __restrict__ qin, const float* __restrict
     const float scale = sqrtf((float) D);     // sqrt(dim_3 / num_heads), integer division (:386)
     load_tile(qin, true);
     __syncthreads();
-    project<S, false>(Xs, w.w_in_t + 0 * kC, 3 * kC, w.b_in + 0 * kC, scale, Qs, nullptr, nullptr, kC);
+    project<S, NS, false>(Xs, L::xreg, w.w_in_t + 0 * kC, 3 * kC, w.b_in + 0 * kC, scale, Qs, nullptr, nullptr, nullptr);
     if (!FUSED) {
         __syncthreads();
         load_tile(kin, true);
         __syncthreads();
     }
-    project<S, false>(Xs, w.w_in_t + 1 * kC, 3 * kC, w.b_in + 1 * kC, 1.0f, Ks, nullptr, nullptr, kC);
+    project<S, NS, false>(Xs, L::xreg, w.w_in_t + 1 * kC, 3 * kC, w.b_in + 1 * kC, 1.0f, Ks, nullptr, nullptr, nullptr);
     __syncthreads();
     load_tile(vin, false);
     __syncthreads();
-    project<S, false>(Xs, w.w_in_t + 2 * kC, 3 * kC, w.b_in + 2 * kC, 1.0f, Vs, nullptr, nullptr, kC);
+    project<S, NS, false>(Xs, L::xreg, w.w_in_t + 2 * kC, 3 * kC, w.b_in + 2 * kC, 1.0f, Vs, nullptr, nullptr, nullptr);
     __syncthreads();
 
-    // ---- scores + mask (:410-412) ---------------------------------------------
-    const float* mk = mask + ((size_t) b * max_sets + set) * H * S;
-    for (int t = tid; t < H * S * S; t += kThreadsA) {
-        const int h = t / (S * S), rem = t - h * S * S, i = rem / S, j = rem - i * S;
-        const float* qp = Qs + i * kQs + h * D;
-        const float* kp = Ks + j * kQs + h * D;
-        float a = 0.f;
+    for (int hg = 0; hg < H; hg += kHeadGroup) {
+        // ---- scores + mask (:410-412): thread (set, head, key j, half of the queries) keeps K[j] in registers -----
+        for (int t = tid; t < NS * kHeadGroup * S * 2; t += kThreadsA) {
+            const int s = t / (kHeadGroup * S * 2), t1 = t - s * (kHeadGroup * S * 2);
+            const int half = t1 / (kHeadGroup * S), rem = t1 - half * (kHeadGroup * S);
+            const int hl = rem / S, j = rem - hl * S, h = hg + hl;
+            const float* Kt = Ks + s * TILE;
+            const float* Qt = Qs + s * TILE;
+            float* St = Ss + s * L::xreg;
+            float4 kr[D / 4];
 #pragma unroll
-        for (int d = 0; d < D; ++d) a = fmaf(qp[d], kp[d], a);
-        Ss[(h * S + i) * (S + 1) + j] = a + __ldg(mk + h * S + j);
-    }
-    __syncthreads();
-    // ---- softmax over keys (:414-415) -----------------------------------------
-    for (int t = tid; t < H * S; t += kThreadsA) {
-        float* row = Ss + t * (S + 1);
-        float mx = row[0];
-        for (int j = 1; j < S; ++j) mx = fmaxf(mx, row[j]);
-        float sum = 0.f;
-        for (int j = 0; j < S; ++j) { const float e = expf(row[j] - mx); row[j] = e; sum += e; }
-        const float inv = 1.0f / sum;
-        for (int j = 0; j < S; ++j) row[j] *= inv;
-    }
-    __syncthreads();
-    // ---- P.V (:417), head-major channel concat -> token tile -------------------
-    for (int t = tid; t < S * kC; t += kThreadsA) {
-        const int i = t / kC, c = t - i * kC, h = c / D;
-        const float* pr = Ss + (h * S + i) * (S + 1);
-        float a = 0.f;
+            for (int d4 = 0; d4 < D / 4; ++d4) kr[d4] = *reinterpret_cast<const float4*>(Kt + j * kXs + h * D + d4 * 4);
+            const float mj = live[s] ? __ldg(mask + (((size_t) b * max_sets + set0 + s) * H + h) * S + j) : 0.f;
+            const int i0 = half * (S / 2);
+#pragma unroll 2
+            for (int i = i0; i < i0 + S / 2; ++i) {
+                const float4* qp = reinterpret_cast<const float4*>(Qt + i * kXs + h * D);
+                float a = 0.f;
+#pragma unroll
+                for (int d4 = 0; d4 < D / 4; ++d4) {
+                    const float4 qv = qp[d4];
+                    a = fmaf(qv.x, kr[d4].x, a); a = fmaf(qv.y, kr[d4].y, a);
+                    a = fmaf(qv.z, kr[d4].z, a); a = fmaf(qv.w, kr[d4].w, a);
+                }
+                St[(hl * S + i) * (S + 1) + j] = a + mj;
+            }
+        }
+        __syncthreads();
+        // ---- softmax over keys (:414-415) -----------------------------------------------------------------------
+        for (int t = tid; t < NS * kHeadGroup * S; t += kThreadsA) {
+            const int s = t / (kHeadGroup * S);
+            float* row = Ss + s * L::xreg + (t - s * (kHeadGroup * S)) * (S + 1);
+            float mx = row[0];
+            for (int j = 1; j < S; ++j) mx = fmaxf(mx, row[j]);
+            float sum = 0.f;
+            for (int j = 0; j < S; ++j) { const float e = expf(row[j] - mx); row[j] = e; sum += e; }
+            const float inv = 1.0f / sum;
+            for (int j = 0; j < S; ++j) row[j] *= inv;
+        }
+        __syncthreads();
+        // ---- P.V (:417): head-major channel concat, written in place over this head group's Q columns ---------
+        {
+            constexpr int GC = kHeadGroup * D;               // 96 channels in this head group
+            constexpr int IG = kThreadsA / GC;               // 3 query groups
+            constexpr int RI = S / IG;                       // 12 queries per thread
+            const int cl = tid % GC, i0 = (tid / GC) * RI, hl = cl / D, c = hg * D + cl;
+#pragma unroll 1
+            for (int s = 0; s < NS; ++s) {
+                float acc[RI];
+#pragma unroll
+                for (int r = 0; r < RI; ++r) acc[r] = 0.f;
+                const float* pr = Ss + s * L::xreg + (hl * S + i0) * (S + 1);
+                const float* Vt = Vs + s * TILE;
 #pragma unroll 4
-        for (int j = 0; j < S; ++j) a = fmaf(pr[j], Vs[j * kQs + c], a);
-        Xs[i * kXs + c] = a;
+                for (int j = 0; j < S; ++j) {
+                    const float vj = Vt[j * kXs + c];
+#pragma unroll
+                    for (int r = 0; r < RI; ++r) acc[r] = fmaf(pr[r * (S + 1) + j], vj, acc[r]);
+                }
+#pragma unroll
+                for (int r = 0; r < RI; ++r) Qs[s * TILE + (i0 + r) * kXs + c] = acc[r];
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
     // ---- out-projection (:448) + (fused) scatter to voxel rows -----------------
-    if (FUSED) {
-        project<S, true>(Xs, w.w_out_t, kC, w.b_out, 1.0f, nullptr, out + (size_t) b * max_pillars * kC, s_rows, kC);
-    } else {
-        project<S, true>(Xs, w.w_out_t, kC, w.b_out, 1.0f, nullptr,
-                         out + ((size_t) b * max_sets + set) * S * kC, nullptr, kC);
-    }
+    float* dst[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+        dst[s] = FUSED ? out + (size_t) b * max_pillars * kC : out + ((size_t) b * max_sets + set0 + s) * S * kC;
+    project<S, NS, true>(Qs, TILE, w.w_out_t, kC, w.b_out, 1.0f, nullptr, dst, FUSED ? s_rows : nullptr, live);
 }
 
 template <int S, bool FUSED>
@@ -206,7 +292,8 @@ int launch_fp32(const dsvt_set_attention_params* p, const AttnWeightsDev& w,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         attr_set = true;
     }
-    set_attention_fp32_kernel<S, FUSED><<<dim3(p->max_set_num, p->batch), kThreadsA, smem, st>>>(
+    constexpr int NS = AttnSmem<S>::NS;
+    set_attention_fp32_kernel<S, FUSED><<<dim3((p->max_set_num + NS - 1) / NS, p->batch), kThreadsA, smem, st>>>(
         q, k, v, pos, idx, mask, set_num, voxel_num, out, w, p->max_set_num, p->max_pillars_num, p->axis_id,
         p->zero_tails);
     DSVT_LAUNCH_CHECK();

@@ -183,19 +183,20 @@ set_attention_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
             const int g = s_rows[r];
             const float4* xr = reinterpret_cast<const float4*>(x + (size_t) (g < 0 ? 0 : g) * kC);
             const float4* pr = reinterpret_cast<const float4*>(pos + (size_t) (g < 0 ? 0 : g) * kC);
-            // chunk c = channels [8c, 8c+8); 3 chunks (12 independent 16-byte loads) in flight per thread
-            for (int c0 = tid >> 7; c0 < 24; c0 += 6) {
-                float4 a[3][2], p[3][2];
+            // chunk c = channels [8c, 8c+8); 6 chunks (24 independent 16-byte loads) in flight per thread
+            constexpr int NJ = 6;
+            for (int c0 = tid >> 7; c0 < 24; c0 += 2 * NJ) {
+                float4 a[NJ][2], p[NJ][2];
                 if (g >= 0) {
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) {
+                    for (int j = 0; j < NJ; ++j) {
                         const int c = c0 + 2 * j;
                         a[j][0] = __ldg(xr + 2 * c); a[j][1] = __ldg(xr + 2 * c + 1);
                         p[j][0] = __ldg(pr + 2 * c); p[j][1] = __ldg(pr + 2 * c + 1);
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
+                for (int j = 0; j < NJ; ++j) {
                     const int c = c0 + 2 * j;
                     uint4 vq = make_uint4(0, 0, 0, 0), vv = vq;
                     if (g >= 0) {
@@ -215,10 +216,11 @@ set_attention_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
 
         // issue the projection MMAs of head `h` (thread 0 only; weights of head h must have landed in sW)
         auto issue_proj = [&](int h) {
-            (void) h;
+            if (h == 1) TC_PROF(30);
             mbar_wait(&bar_w, ph_w);
             ph_w ^= 1;
             tc_fence_after_sync();
+            if (h == 1) TC_PROF(31);
             uint64_t aq = d_aqk, av = d_av, bq = d_wqk, bv = d_wv;
 #pragma unroll
             for (int ks = 0; ks < 12; ++ks) {                            // K = 192 = 12 x 16
@@ -388,10 +390,13 @@ set_attention_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
             // ---- O_h = P V_h, then (pipelined behind it) the next head's projections ------------------------------------
             if (tid == 0) {
                 tc_fence_after_sync();
+                if (h == 0) TC_PROF(34);
 #pragma unroll
                 for (int ks = 0; ks < kKeys / 16; ++ks)                  // K = 112 keys = 7 x 16
                     umma_f16_ts(tmem + C_O + 32 * h, tmem + C_P + 8 * ks, d_v + ks * (1024 / 16), idesc_pv, ks > 0);
+                if (h == 0) TC_PROF(33);
                 if (h + 1 < kH) issue_proj(h + 1);
+                if (h == 0) TC_PROF(32);
                 umma_commit(&bar_mma);
             }
             if (h < 2) TC_PROF(6 + 5 * h);

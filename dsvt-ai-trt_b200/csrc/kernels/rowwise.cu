@@ -131,6 +131,72 @@ layer_norm192_kernel(const float4* __restrict__ x, const float4* __restrict__ re
     }
 }
 
+// Chain of N LayerNorms (C = 192) with residual adds in between; same arithmetic per stage as layer_norm192_kernel.
+struct LnChain {
+    const float4* res[3];
+    const float4* gamma[3];
+    const float4* beta[3];
+};
+template <int N>
+__global__ void __launch_bounds__(256)
+layer_norm192_chain_kernel(const float4* __restrict__ x, LnChain ch, const int* __restrict__ voxel_num,
+                           float4* __restrict__ out, int max_pillars, float eps, int zero_tails)
+{
+    const int b = blockIdx.y;
+    int V = voxel_num[b];
+    V = V < max_pillars ? V : max_pillars;
+    const int sub = threadIdx.x & 15;
+    const int rows_per_block = blockDim.x >> 4;
+    const int end_row = zero_tails ? max_pillars : V;
+    for (int row = blockIdx.x * rows_per_block + (threadIdx.x >> 4); row < end_row;
+         row += gridDim.x * rows_per_block) {
+        const size_t off = ((size_t) b * max_pillars + row) * 48;
+        if (row >= V) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) stg_stream4(out + off + k * 16 + sub, make_float4(0.f, 0.f, 0.f, 0.f));
+            continue;
+        }
+        float4 v[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[k] = ldg_stream4(x + off + k * 16 + sub);
+#pragma unroll
+        for (int st = 0; st < N; ++st) {
+            if (ch.res[st] != nullptr) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float4 r = ldg_stream4(ch.res[st] + off + k * 16 + sub);
+                    v[k].x += r.x; v[k].y += r.y; v[k].z += r.z; v[k].w += r.w;
+                }
+            }
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float mean = s / 192.f;
+            float q = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float a = v[k].x - mean, c = v[k].y - mean, d = v[k].z - mean, e = v[k].w - mean;
+                q += (a * a + c * c) + (d * d + e * e);
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+            const float sd = sqrtf(q / 192.f + eps);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float4 g = __ldg(ch.gamma[st] + k * 16 + sub), be = __ldg(ch.beta[st] + k * 16 + sub);
+                v[k].x = (v[k].x - mean) / sd * g.x + be.x;
+                v[k].y = (v[k].y - mean) / sd * g.y + be.y;
+                v[k].z = (v[k].z - mean) / sd * g.z + be.z;
+                v[k].w = (v[k].w - mean) / sd * g.w + be.w;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) stg_stream4(out + off + k * 16 + sub, v[k]);
+    }
+}
+
 // generic channel count: one warp per row, scalar accesses
 __global__ void __launch_bounds__(256)
 layer_norm_generic_kernel(const float* __restrict__ x, const float* __restrict__ res,
@@ -340,6 +406,36 @@ extern "C" int dsvt_layer_norm_launch(const dsvt_layer_norm_params* p, const flo
         layer_norm_generic_kernel<<<dim3(grid, p->batch), 256, 0, st>>>(x, residual, voxel_num, gamma, beta, out,
                                                                         p->max_pillars_num, p->channel_num,
                                                                         p->eps, p->zero_tails);
+    }
+    DSVT_LAUNCH_CHECK();
+    return DSVT_OK;
+}
+
+extern "C" int dsvt_layer_norm_chain_launch(const dsvt_layer_norm_params* p, const float* x, const int32_t* voxel_num,
+                                            const dsvt_ln_stage* stages, int32_t n_stages, float* out,
+                                            dsvt_stream_t stream)
+{
+    DSVT_CHECK_ARG(p && p->batch >= 1 && p->max_pillars_num >= 1, "params");
+    DSVT_CHECK_ARG(p->channel_num == 192, "the fused chain is built for channel_num = 192");
+    DSVT_CHECK_ARG(x && voxel_num && stages && out && n_stages >= 1 && n_stages <= 3, "arguments");
+    LnChain ch{};
+    uintptr_t align = (uintptr_t) x | (uintptr_t) out;
+    for (int i = 0; i < n_stages; ++i) {
+        DSVT_CHECK_ARG(stages[i].gamma && stages[i].beta, "stage gamma/beta is NULL");
+        ch.res[i] = reinterpret_cast<const float4*>(stages[i].residual);
+        ch.gamma[i] = reinterpret_cast<const float4*>(stages[i].gamma);
+        ch.beta[i] = reinterpret_cast<const float4*>(stages[i].beta);
+        align |= (uintptr_t) stages[i].residual | (uintptr_t) stages[i].gamma | (uintptr_t) stages[i].beta;
+    }
+    DSVT_CHECK_ARG(!(align & 15), "16-B alignment");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = grid_for((size_t) p->max_pillars_num * 16, 256, 8);
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* o4 = reinterpret_cast<float4*>(out);
+    switch (n_stages) {
+        case 1: layer_norm192_chain_kernel<1><<<dim3(grid, p->batch), 256, 0, st>>>(x4, ch, voxel_num, o4, p->max_pillars_num, p->eps, p->zero_tails); break;
+        case 2: layer_norm192_chain_kernel<2><<<dim3(grid, p->batch), 256, 0, st>>>(x4, ch, voxel_num, o4, p->max_pillars_num, p->eps, p->zero_tails); break;
+        default: layer_norm192_chain_kernel<3><<<dim3(grid, p->batch), 256, 0, st>>>(x4, ch, voxel_num, o4, p->max_pillars_num, p->eps, p->zero_tails); break;
     }
     DSVT_LAUNCH_CHECK();
     return DSVT_OK;

@@ -210,6 +210,7 @@ vox_emit_kernel(const float4* __restrict__ points, int max_points, VoxGeom g,
     __shared__ int s_idx[WARPS][kMaxNpv];
     __shared__ float s_pts[WARPS][kMaxNpv][4];
     __shared__ float s_feat[WARPS][kMaxNpv * 10];
+    __shared__ int s_hist[WARPS][256];
 
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -219,28 +220,7 @@ vox_emit_kernel(const float4* __restrict__ points, int max_points, VoxGeom g,
     float* feat_b = point_features + (size_t) b * max_rows * 10;
     int* piv_b = point_index_in_voxel + (size_t) b * max_pillars * npv;
 
-    // ---- zero-fill duty: tail rows of point_features are split evenly over all warps ----
-    if (zero_tails) {
-        const long long total_warps = (long long) gridDim.x * WARPS;
-        const long long tail_floats = (long long) (max_rows - Pc) * 10;
-        const long long per = (tail_floats + total_warps - 1) / total_warps;
-        const long long gw = (long long) blockIdx.x * WARPS + w;
-        long long lo = (long long) Pc * 10 + gw * per;
-        long long hi = lo + per;
-        const long long end = (long long) max_rows * 10;
-        if (hi > end) hi = end;
-        for (long long t = lo + lane; t < hi; t += 32) feat_b[t] = 0.f;
-    }
-    if (pid >= max_pillars) return;
-    if (pid >= V) {
-        if (zero_tails) {
-            for (int s = lane; s < npv; s += 32) piv_b[(size_t) pid * npv + s] = 0;
-            if (lane < 4) coords[((size_t) b * max_pillars + pid) * 4 + lane] = 0;
-            if (lane == 0) point_num_in_voxel_out[(size_t) b * max_pillars + pid] = 0;
-        }
-        return;
-    }
-
+    if (pid >= V) return;          // tails are zero-filled by vox_zero_tails_kernel
     const int base = pillar_base[(size_t) b * ws_stride + pid];
     const int n = pillar_n[(size_t) b * ws_stride + pid];
     const int row0 = pillar_row[(size_t) b * ws_stride + pid];
@@ -254,19 +234,41 @@ vox_emit_kernel(const float4* __restrict__ points, int max_points, VoxGeom g,
         e0 = lane < n ? lst[lane] : 0x7fffffff;
         e1 = lane + 32 < n ? lst[lane + 32] : 0x7fffffff;
     } else {
-        // radix-select the kk-th smallest input index T, then gather the kk elements <= T
+        // radix-select (8-bit digits, per-warp shared-memory histogram) the kk-th smallest input index T,
+        // then gather the kk elements <= T
         int prefix_v = 0, k = kk;
         const int nbits = 32 - __clz(max_points | 1);
-        for (int bit = nbits - 1; bit >= 0; --bit) {
-            const int himask = (int) ~((2u << bit) - 1u);
-            int c0 = 0;
+        for (int shift = ((nbits - 1) / 8) * 8; shift >= 0; shift -= 8) {
+            for (int bn = lane; bn < 256; bn += 32) s_hist[w][bn] = 0;
+            __syncwarp();
+            const unsigned himask = shift + 8 >= 32 ? 0u : ~((1u << (shift + 8)) - 1u);
             for (int t = lane; t < n; t += 32) {
-                const int e = lst[t];
-                c0 += ((e & himask) == prefix_v) && !(((unsigned) e >> bit) & 1u);
+                const unsigned e = (unsigned) lst[t];
+                if ((e & himask) == (unsigned) prefix_v) atomicAdd(&s_hist[w][(e >> shift) & 255u], 1);
             }
+            __syncwarp();
+            int c[8], lsum = 0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) c0 += __shfl_xor_sync(0xffffffffu, c0, o);
-            if (k > c0) { k -= c0; prefix_v |= (int) (1u << bit); }
+            for (int i = 0; i < 8; ++i) { c[i] = s_hist[w][lane * 8 + i]; lsum += c[i]; }
+            const int incl = warp_incl_scan(lsum, lane);
+            const int excl = incl - lsum;
+            // the lane whose bin range contains the k-th element
+            const unsigned hit = __ballot_sync(0xffffffffu, incl >= k);
+            const int src = __ffs(hit) - 1;
+            int digit = 0, below = 0;
+            if (lane == src) {
+                int run = excl;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (run + c[i] >= k) { digit = lane * 8 + i; below = run; break; }
+                    run += c[i];
+                }
+            }
+            digit = __shfl_sync(0xffffffffu, digit, src);
+            below = __shfl_sync(0xffffffffu, below, src);
+            k -= below;
+            prefix_v |= digit << shift;
+            __syncwarp();
         }
         const int T = prefix_v;
         int filled = 0;
@@ -332,6 +334,37 @@ vox_emit_kernel(const float4* __restrict__ points, int max_points, VoxGeom g,
     for (int s = lane; s < npv; s += 32) {
         if (s < keep) piv_b[(size_t) pid * npv + s] = row0 + s;
         else if (zero_tails) piv_b[(size_t) pid * npv + s] = 0;
+    }
+}
+
+// Zero-fill of everything beyond the valid counts (the reference memsets all outputs, points2Features.cu:944-952).
+// A plain grid-stride streaming kernel: keeping this out of vox_emit removes ~half of that kernel's instructions.
+__global__ void __launch_bounds__(256)
+vox_zero_tails_kernel(const int* __restrict__ pillar_num, const int* __restrict__ point_num,
+                      float* __restrict__ point_features, int* __restrict__ point_index_in_voxel,
+                      int* __restrict__ coords, int* __restrict__ point_num_in_voxel,
+                      int npv, int max_pillars, int max_rows)
+{
+    const int b = blockIdx.y;
+    const int V = pillar_num[b], Pc = point_num[b];
+    const unsigned stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    // feature rows [Pc, max_rows): 10 floats per row = 5 float2 (rows are 8-byte aligned)
+    {
+        float2* f = reinterpret_cast<float2*>(point_features + ((size_t) b * max_rows + Pc) * 10);
+        const unsigned n = (unsigned) (max_rows - Pc) * 5u;
+        for (unsigned t = t0; t < n; t += stride) f[t] = make_float2(0.f, 0.f);
+    }
+    {
+        int* q = point_index_in_voxel + ((size_t) b * max_pillars + V) * npv;
+        const unsigned n = (unsigned) (max_pillars - V) * (unsigned) npv;
+        for (unsigned t = t0; t < n; t += stride) q[t] = 0;
+    }
+    {
+        int* c = coords + ((size_t) b * max_pillars + V) * 4;
+        const unsigned n = (unsigned) (max_pillars - V) * 4u;
+        for (unsigned t = t0; t < n; t += stride) c[t] = 0;
+        int* m = point_num_in_voxel + (size_t) b * max_pillars + V;
+        for (unsigned t = t0; t < (unsigned) (max_pillars - V); t += stride) m[t] = 0;
     }
 }
 
@@ -442,5 +475,11 @@ extern "C" int dsvt_points2features_launch(const dsvt_points2features_params* p,
         point_num_in_voxel, stride, p->max_num_points_per_voxel, p->max_pillars_num,
         p->max_points_num_voxel_filter, p->zero_tails);
     DSVT_LAUNCH_CHECK();
+    if (p->zero_tails) {
+        vox_zero_tails_kernel<<<dim3(sm_count() * 4, B), 256, 0, st>>>(
+            pillar_num, point_num, point_features, point_index_in_voxel, coords, point_num_in_voxel,
+            p->max_num_points_per_voxel, p->max_pillars_num, p->max_points_num_voxel_filter);
+        DSVT_LAUNCH_CHECK();
+    }
     return DSVT_OK;
 }

@@ -40,8 +40,8 @@ class FrameWeights:
 class HotPathFrame:
     """Buffers + launch sequence for one frame slot (one CUDA stream owns one slot)."""
 
-    def __init__(self, cfg, weights, precision=capi.DSVT_ATTN_FP32, seed=0, device="cuda"):
-        self.cfg, self.w, self.precision = cfg, weights, precision
+    def __init__(self, cfg, weights, precision=capi.DSVT_ATTN_FP32, seed=0, device="cuda", fuse_ln=True):
+        self.cfg, self.w, self.precision, self.fuse_ln = cfg, weights, precision, fuse_ln
         g = torch.Generator(device="cpu").manual_seed(seed)
         mp, C, F = cfg.max_pillars_num, cfg.channel_num, cfg.ffn_channel_num
         self.points = torch.zeros(1, cfg.max_points_num, 4, dtype=torch.float32, device=device)
@@ -95,14 +95,24 @@ class HotPathFrame:
                 capi.layer_norm(self.attn_out, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=x,
                                 out=self.src); ln += 1                                     # norm1(y + x)   :669-676
                 capi.gelu(self.ffn_hidden, V, out=self.gelu_out)                           # :519 (inside the FFN)
-                capi.layer_norm(self.src, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=self.ffn_out,
-                                out=self.src_b); ln += 1                                   # norm2(src + src2) :685-690
                 nxt = self.x_a if enc == 0 else self.x_b
-                capi.layer_norm(self.src_b, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=x,
-                                out=nxt); ln += 1                                          # norm(src + x)  :691-697
+                if not self.fuse_ln:
+                    capi.layer_norm(self.src, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=self.ffn_out,
+                                    out=self.src_b); ln += 1                               # norm2(src + src2) :685-690
+                    capi.layer_norm(self.src_b, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=x,
+                                    out=nxt); ln += 1                                      # norm(src + x)  :691-697
+                    if enc == 1:
+                        capi.layer_norm(nxt, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=x_in,
+                                        out=self.blk_out[blk % 2]); ln += 1                # residual norm  :750-756
+                else:
+                    # the same LayerNorms as one chained launch (rows stay in registers between stages)
+                    stages = [(self.ffn_out, w.gamma[ln], w.beta[ln]), (x, w.gamma[ln + 1], w.beta[ln + 1])]
+                    ln += 2
+                    if enc == 1:
+                        stages.append((x_in, w.gamma[ln], w.beta[ln])); ln += 1
+                    capi.layer_norm_chain(self.src, V, stages, cfg.layer_norm_eps,
+                                          out=nxt if enc == 0 else self.blk_out[blk % 2])
                 x = nxt
-            capi.layer_norm(x, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=x_in,
-                            out=self.blk_out[blk % 2]); ln += 1                            # residual norm  :750-756
             x = self.blk_out[blk % 2]
         self.final = x
         capi.filter_box(cfg, *self.cand, boxes=self.boxes, valid=self.valid)

@@ -175,6 +175,21 @@ int dsvt_layer_norm_launch(const dsvt_layer_norm_params* p, const float* x, cons
                            const int32_t* voxel_num, const float* gamma, const float* beta, float* out,
                            dsvt_stream_t stream);
 
+/*
+ * Chain of up to 3 consecutive LayerNorms whose only intermediate op is a residual add -- e.g. norm2 -> norm ->
+ * residual_norm at the end of a DSVT block (src/dsvt-ai-trt.cpp:685-697, :750-756):
+ *   y = LN_n( ... LN_2( LN_1(x + r_1) + r_2 ) ... + r_n ).   The row stays in registers between stages, so the
+ * chain costs one read of x, one read per residual and ONE write instead of n read-write round trips.
+ * Results are identical to n calls of dsvt_layer_norm_launch.  residual may be NULL per stage.
+ */
+typedef struct dsvt_ln_stage {
+    const float* residual;   /* [B,max_pillars_num,C] or NULL */
+    const float* gamma;      /* [C] device */
+    const float* beta;       /* [C] device */
+} dsvt_ln_stage;
+int dsvt_layer_norm_chain_launch(const dsvt_layer_norm_params* p, const float* x, const int32_t* voxel_num,
+                                 const dsvt_ln_stage* stages, int32_t n_stages, float* out, dsvt_stream_t stream);
+
 /* ------------------------------------------------------------------------ *
  * a6  FilterBoxByScorePlugin::enqueue          plugins/src/filterBoxByScore.cu:328-379 (kernel :266-309)
  * ------------------------------------------------------------------------ */

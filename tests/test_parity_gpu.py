@@ -246,6 +246,32 @@ def test_layer_norm(V, cap, C, with_res):
     assert np.abs(got - ref).max() <= 2e-5 if V else True
 
 
+@pytest.mark.parametrize("n_stages", [1, 2, 3])
+def test_layer_norm_chain(n_stages):
+    """Chained LayerNorms == the same LayerNorm plugins applied one after the other (oracle composition)."""
+    rng = np.random.default_rng(n_stages)
+    V, cap, C = 16566, 20000, 192
+    x = (rng.standard_normal((cap, C)) * 2).astype(np.float32)
+    res = [(rng.standard_normal((cap, C))).astype(np.float32) if i != 1 or n_stages == 3 else None for i in range(n_stages)]
+    gam = [rng.standard_normal(C).astype(np.float32) for _ in range(n_stages)]
+    bet = [rng.standard_normal(C).astype(np.float32) for _ in range(n_stages)]
+    ref = x
+    for i in range(n_stages):
+        ref = cpu.layer_norm(ref, V, gam[i], bet[i], 0.0, residual=res[i])
+    vn = torch.tensor([V], dtype=torch.int32, device="cuda")
+    out = torch.full((cap, C), float("nan"), device="cuda")
+    capi.layer_norm_chain(dev(x), vn, [(dev(r) if r is not None else None, dev(g), dev(b)) for r, g, b in zip(res, gam, bet)],
+                          0.0, out=out)
+    got = out.cpu().numpy()
+    assert np.all(got[V:] == 0)
+    assert np.abs(got - ref).max() <= 5e-5 * n_stages
+    # and bit-identical to the un-fused kernels of this library
+    seq = dev(x)
+    for i in range(n_stages):
+        seq = capi.layer_norm(seq, vn, dev(gam[i]), dev(bet[i]), 0.0, residual=dev(res[i]) if res[i] is not None else None)
+    assert torch.equal(seq, out)
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_filter_box(pkg, cfgs, seed):
     cfg = cfgs.REFERENCE

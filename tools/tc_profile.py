@@ -21,6 +21,8 @@ t = np.array(buf[:], dtype=np.int64)
 names = {0: "tile start", 1: "staged", 20: "heads done (PV7)", 21: "O tile written", 22: "out-proj done", 23: "tile end"}
 for h in range(2):
     names.update({2+5*h: f"h{h} proj done", 3+5*h: f"h{h} epilogue+sync", 4+5*h: f"h{h} S done", 5+5*h: f"h{h} softmax+sync", 6+5*h: f"h{h} PV/proj issued"})
+names.update({34: "  h0 PV issue start", 33: "  h0 PV issued", 30: "  h1 proj: before weight wait", 31: "  h1 proj: weights landed", 32: "  h1 proj issued"})
+order = [0,1,2,3,4,5,34,33,30,31,32,6,7,8,9,10,11,20,21,22,23]
 prev = t[0]
-for i in sorted(names):
+for i in order:
     print(f"{names[i]:24s} +{t[i]-prev:7d}  (t={t[i]-t[0]})"); prev = t[i]
