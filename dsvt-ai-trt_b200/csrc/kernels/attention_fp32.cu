@@ -40,69 +40,105 @@ template <int S> struct AttnSmem {
     static constexpr int total = v + NS * tile;
 };
 
-// out[s][r][4cg..4cg+3] = (sum_k X[s][r][k] * Wt[k][4cg..] + bias) / div for this thread's R rows of each of the NS sets.
-// Register tile (NS*R) x 4: per 4 k-values a thread issues NS*R broadcast LDS.128 (x) + 4 coalesced LDG.128 (weights,
-// prefetched TWO steps ahead) for 16*NS*R FMAs, so neither the shared-memory crossbar nor the L2 latency limits the
-// FMA pipe (version 1 of this kernel: 4 FMAs per LDS.128, crossbar-bound at 15 TFLOP/s).
-template <int S, int NS, bool TO_GLOBAL>
-__device__ __forceinline__ void project(const float* __restrict__ Xs, int x_set_stride, const float* __restrict__ Wt,
-                                        int ldw, const float* __restrict__ bias, float div, float* out_s,
-                                        float* const* out_g, const int* row_map, const bool* live)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t) __cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kStageK = 8;                          // k-values per weight stage
+constexpr int kStageFloats = kStageK * kC;          // 1536 floats = 6 KB
+// ring depth: 4 stages (24 KB) fit the 28 KB destination tile of S >= 36, 3 stages (18 KB) that of S = 24
+template <int S> struct RingDepth { static constexpr int value = (S * kXs >= 4 * kStageFloats) ? 4 : 3; };
+
+// out[r][4cg..4cg+3] = (sum_k X[r][k] * Wt[k][4cg..] + bias) / div for this thread's R rows.
+// The 147 KB weight slice streams from L2 ONCE per CTA through a 4-stage cp.async ring in shared memory (the ring
+// lives in the projection's own destination tile, which is only written after the k loop), so neither the L2
+// latency (~1000 cycles under load: the previous register-prefetch version was bound by it) nor the six-fold
+// re-read by the six row groups is on the critical path.  Register tile R x 4; row groups whose rows are all
+// >= n_rows (token compaction) skip the FMAs but still help with the copies.
+template <int S, bool TO_GLOBAL>
+__device__ __forceinline__ void project(const float* __restrict__ Xs, const float* __restrict__ Wt, int ldw,
+                                        const float* __restrict__ bias, float div, float* ring, float* out_s,
+                                        float* out_g, const int* row_map, int n_rows)
 {
     constexpr int R = S / kRowGroups;
-    const int cg = threadIdx.x % kColGroups;
-    const int r0 = (threadIdx.x / kColGroups) * R;
-    float acc[NS][R][4];
+    constexpr int kStages = RingDepth<S>::value;
+    constexpr int kNumStages = kC / kStageK;        // 24
+    const int tid = threadIdx.x;
+    const int cg = tid % kColGroups;
+    const int r0 = (tid / kColGroups) * R;
+    const bool active = r0 < n_rows;
+    // (walking k from a per-CTA offset, to de-correlate the CTAs' L2 requests, was measured: no gain; not kept so
+    // that a set's result does not depend on which CTA computes it)
+    constexpr int rot = 0;
+    float acc[R][4];
 #pragma unroll
-    for (int s = 0; s < NS; ++s)
-#pragma unroll
-        for (int r = 0; r < R; ++r) { acc[s][r][0] = 0.f; acc[s][r][1] = 0.f; acc[s][r][2] = 0.f; acc[s][r][3] = 0.f; }
-    const float4* wp = reinterpret_cast<const float4*>(Wt) + cg;
-    const int ld4 = ldw / 4;
-    float4 w0[4], w1[4];                       // weights of the next two k-steps
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) { w0[kk] = __ldg(wp + (size_t) kk * ld4); w1[kk] = __ldg(wp + (size_t) (4 + kk) * ld4); }
-#pragma unroll 1
-    for (int k = 0; k < kC; k += 4) {
-        float4 wc[4];
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) { wc[kk] = w0[kk]; w0[kk] = w1[kk]; }
-        if (k + 8 < kC) {
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) w1[kk] = __ldg(wp + (size_t) (k + 8 + kk) * ld4);
+    for (int r = 0; r < R; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
+
+    auto issue = [&](int st) {                      // copy 8 weight rows x 192 columns into ring slot st % kStages
+        if (st < kNumStages) {
+            float* dst = ring + (st % kStages) * kStageFloats;
+            const int slab = (st + rot) % kNumStages;
+            for (int c = tid; c < kStageFloats / 4; c += kThreadsA) {
+                const int kk = c / (kC / 4), j = c - kk * (kC / 4);
+                cp_async16(dst + kk * kC + j * 4, Wt + (size_t) (slab * kStageK + kk) * ldw + j * 4);
+            }
         }
+        cp_async_commit();
+    };
 #pragma unroll
-        for (int s = 0; s < NS; ++s)
+    for (int st = 0; st < kStages - 1; ++st) issue(st);
+#pragma unroll 1
+    for (int st = 0; st < kNumStages; ++st) {
+        cp_async_wait<kStages - 2>();               // this thread's copies of stage st have landed
+        __syncthreads();                            // ... everyone's have, and slot (st-1)%kStages is no longer being read
+        issue(st + kStages - 1);
+        if (active) {
+            const float* wst = ring + (st % kStages) * kStageFloats + cg * 4;
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const float4 xv = *reinterpret_cast<const float4*>(Xs + s * x_set_stride + (r0 + r) * kXs + k);
-                const float xk[4] = {xv.x, xv.y, xv.z, xv.w};
+            for (int k4 = 0; k4 < kStageK / 4; ++k4) {
+                float4 wc[4];
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    acc[s][r][0] = fmaf(xk[kk], wc[kk].x, acc[s][r][0]);
-                    acc[s][r][1] = fmaf(xk[kk], wc[kk].y, acc[s][r][1]);
-                    acc[s][r][2] = fmaf(xk[kk], wc[kk].z, acc[s][r][2]);
-                    acc[s][r][3] = fmaf(xk[kk], wc[kk].w, acc[s][r][3]);
+                for (int kk = 0; kk < 4; ++kk) wc[kk] = *reinterpret_cast<const float4*>(wst + (k4 * 4 + kk) * kC);
+                const int k = ((st + rot) % kNumStages) * kStageK + k4 * 4;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (r0 + r >= n_rows) break;
+                    const float4 xv = *reinterpret_cast<const float4*>(Xs + (r0 + r) * kXs + k);
+                    const float xk[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        acc[r][0] = fmaf(xk[kk], wc[kk].x, acc[r][0]);
+                        acc[r][1] = fmaf(xk[kk], wc[kk].y, acc[r][1]);
+                        acc[r][2] = fmaf(xk[kk], wc[kk].z, acc[r][2]);
+                        acc[r][3] = fmaf(xk[kk], wc[kk].w, acc[r][3]);
+                    }
                 }
             }
+        }
     }
+    cp_async_wait<0>();
+    __syncthreads();                                // the ring (== the destination tile) is free to be overwritten
+    if (!active) return;
     const float4 bn = __ldg(reinterpret_cast<const float4*>(bias) + cg);
 #pragma unroll
-    for (int s = 0; s < NS; ++s)
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            float4 o = make_float4(acc[s][r][0] + bn.x, acc[s][r][1] + bn.y, acc[s][r][2] + bn.z, acc[s][r][3] + bn.w);
-            if (div != 1.0f) { o.x = o.x / div; o.y = o.y / div; o.z = o.z / div; o.w = o.w / div; }
-            if (TO_GLOBAL) {
-                if (live[s]) {
-                    const int row = row_map ? row_map[s * S + r0 + r] : (r0 + r);
-                    *reinterpret_cast<float4*>(out_g[s] + (size_t) row * kC + cg * 4) = o;
-                }
-            } else {
-                *reinterpret_cast<float4*>(out_s + s * (S * kXs) + (r0 + r) * kXs + cg * 4) = o;
-            }
+    for (int r = 0; r < R; ++r) {
+        const int lr = r0 + r;
+        if (lr >= n_rows) break;
+        float4 o = make_float4(acc[r][0] + bn.x, acc[r][1] + bn.y, acc[r][2] + bn.z, acc[r][3] + bn.w);
+        if (div != 1.0f) { o.x = o.x / div; o.y = o.y / div; o.z = o.z / div; o.w = o.w / div; }
+        if (TO_GLOBAL) {
+            const int row = row_map ? row_map[lr] : lr;
+            *reinterpret_cast<float4*>(out_g + (size_t) row * kC + cg * 4) = o;
+        } else {
+            *reinterpret_cast<float4*>(out_s + lr * kXs + cg * 4) = o;
         }
+    }
 }
+
+__device__ long long g_fp32_prof[32];
+#define F32_PROF(i) do { if (blockIdx.x == 5 && blockIdx.y == 0 && threadIdx.x == 0) g_fp32_prof[i] = clock64(); } while (0)
 
 template <int S, bool FUSED>
 __global__ void __launch_bounds__(kThreadsA, (S <= 36) ? 2 : 1)
@@ -121,12 +157,15 @@ set_attention_fp32_kernel(const float* __restrict__ qin, const float* __restrict
     float* Ks = sm + L::k;
     float* Vs = sm + L::v;
     float* Ss = sm + L::x;      // scores of one head group per set, aliases the (dead) token tile
-    __shared__ int s_rows[NS * S];
+    __shared__ int s_rows[NS * S];      // voxel row of compact token u
+    __shared__ int s_slot[NS * S];      // original slot of compact token u (for the key mask)
+    __shared__ int s_nu;
 
     constexpr int H = 8, D = kC / H;
     const int b = blockIdx.y;
     const int set0 = blockIdx.x * NS;
     const int tid = threadIdx.x;
+    F32_PROF(0);
     int ns = set_num ? set_num[b] : max_sets;
     ns = ns < max_sets ? ns : max_sets;
 
@@ -164,15 +203,50 @@ set_attention_fp32_kernel(const float* __restrict__ qin, const float* __restrict
         }
     }
 
+    // Token compaction (fused form).  getSet pads a set by repeating the previous voxel and masks the repeats
+    // (getSet.cu:546-563).  A repeated slot is the SAME token: as a query it yields the same row as its twin (and
+    // scatters to the same voxel row), as a key it is masked out exactly (exp underflows to 0).  So only slots that
+    // are a new voxel -- or that are not fully masked -- need projecting: work drops from 36 rows to the n_u
+    // distinct tokens of the set (~1/2 at Waymo densities, ~1/3 on the reference frame) with identical results.
     if (FUSED) {
+        static_assert(NS == 1, "token compaction assumes one set per CTA");
         const int* my_idx = idx + (((size_t) b * 2 + axis) * max_sets + set0) * S;
-        for (int t = tid; t < NS * S; t += kThreadsA) s_rows[t] = live[t / S] ? my_idx[t] : 0;
+        if (tid < 32) {
+            int base_u = 0;
+            for (int k0 = 0; k0 < S; k0 += 32) {
+                const int k = k0 + tid;
+                bool keep = false;
+                int g = 0;
+                if (k < S) {
+                    g = my_idx[k];
+                    keep = (k == 0) || (g != my_idx[k - 1]);
+                    if (!keep) {            // a repeat: droppable only if every head masks it as a key
+                        const float* mrow = mask + ((size_t) b * max_sets + set0) * H * S + k;
+                        for (int h = 0; h < H; ++h) keep |= !(mrow[h * S] < -1e30f);
+                    }
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    const int u = base_u + __popc(bal & ((1u << tid) - 1u));
+                    s_rows[u] = g;
+                    s_slot[u] = k;
+                }
+                base_u += __popc(bal);
+            }
+            if (tid == 0) s_nu = base_u;
+        }
+    } else {
+        if (tid < NS * S) s_slot[tid] = tid % S;
+        if (tid == 0) s_nu = S;
     }
     __syncthreads();
+    const int nu = s_nu;
+    F32_PROF(1);
+    if (blockIdx.x == 5 && blockIdx.y == 0 && threadIdx.x == 0) g_fp32_prof[20] = nu;
 
     auto load_tile = [&](const float* src_plain, bool add_pos) {
-        for (int t = tid; t < NS * S * (kC / 4); t += kThreadsA) {
-            const int sr = t / (kC / 4), c4 = t - sr * (kC / 4), s = sr / S, r = sr - s * S;
+        for (int t = tid; t < nu * (kC / 4); t += kThreadsA) {
+            const int sr = t / (kC / 4), c4 = t - sr * (kC / 4), s = 0, r = sr;
             float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
             if (live[s]) {
                 if (FUSED) {
@@ -194,35 +268,41 @@ set_attention_fp32_kernel(const float* __restrict__ qin, const float* __restrict
     const float scale = sqrtf((float) D);     // sqrt(dim_3 / num_heads), integer division (:386)
     load_tile(qin, true);
     __syncthreads();
-    project<S, NS, false>(Xs, L::xreg, w.w_in_t + 0 * kC, 3 * kC, w.b_in + 0 * kC, scale, Qs, nullptr, nullptr, nullptr);
+    F32_PROF(2);
+    project<S, false>(Xs, w.w_in_t + 0 * kC, 3 * kC, w.b_in + 0 * kC, scale, Qs, Qs, nullptr, nullptr, nu);
     if (!FUSED) {
         __syncthreads();
         load_tile(kin, true);
         __syncthreads();
     }
-    project<S, NS, false>(Xs, L::xreg, w.w_in_t + 1 * kC, 3 * kC, w.b_in + 1 * kC, 1.0f, Ks, nullptr, nullptr, nullptr);
+    F32_PROF(3);
+    project<S, false>(Xs, w.w_in_t + 1 * kC, 3 * kC, w.b_in + 1 * kC, 1.0f, Ks, Ks, nullptr, nullptr, nu);
     __syncthreads();
+    F32_PROF(4);
     load_tile(vin, false);
     __syncthreads();
-    project<S, NS, false>(Xs, L::xreg, w.w_in_t + 2 * kC, 3 * kC, w.b_in + 2 * kC, 1.0f, Vs, nullptr, nullptr, nullptr);
+    F32_PROF(5);
+    project<S, false>(Xs, w.w_in_t + 2 * kC, 3 * kC, w.b_in + 2 * kC, 1.0f, Vs, Vs, nullptr, nullptr, nu);
     __syncthreads();
 
+    F32_PROF(6);
     for (int hg = 0; hg < H; hg += kHeadGroup) {
         // ---- scores + mask (:410-412): thread (set, head, key j, half of the queries) keeps K[j] in registers -----
         for (int t = tid; t < NS * kHeadGroup * S * 2; t += kThreadsA) {
             const int s = t / (kHeadGroup * S * 2), t1 = t - s * (kHeadGroup * S * 2);
             const int half = t1 / (kHeadGroup * S), rem = t1 - half * (kHeadGroup * S);
             const int hl = rem / S, j = rem - hl * S, h = hg + hl;
+            if (j >= nu) continue;
             const float* Kt = Ks + s * TILE;
             const float* Qt = Qs + s * TILE;
             float* St = Ss + s * L::xreg;
             float4 kr[D / 4];
 #pragma unroll
             for (int d4 = 0; d4 < D / 4; ++d4) kr[d4] = *reinterpret_cast<const float4*>(Kt + j * kXs + h * D + d4 * 4);
-            const float mj = live[s] ? __ldg(mask + (((size_t) b * max_sets + set0 + s) * H + h) * S + j) : 0.f;
-            const int i0 = half * (S / 2);
+            const float mj = live[s] ? __ldg(mask + (((size_t) b * max_sets + set0 + s) * H + h) * S + s_slot[j]) : 0.f;
+            const int ih = (nu + 1) / 2, i0 = half * ih, i1 = half ? nu : ih;
 #pragma unroll 2
-            for (int i = i0; i < i0 + S / 2; ++i) {
+            for (int i = i0; i < i1; ++i) {
                 const float4* qp = reinterpret_cast<const float4*>(Qt + i * kXs + h * D);
                 float a = 0.f;
 #pragma unroll
@@ -235,18 +315,21 @@ set_attention_fp32_kernel(const float* __restrict__ qin, const float* __restrict
             }
         }
         __syncthreads();
+        if (hg == 0) F32_PROF(7);
         // ---- softmax over keys (:414-415) -----------------------------------------------------------------------
         for (int t = tid; t < NS * kHeadGroup * S; t += kThreadsA) {
             const int s = t / (kHeadGroup * S);
+            if ((t - s * (kHeadGroup * S)) % S >= nu) continue;
             float* row = Ss + s * L::xreg + (t - s * (kHeadGroup * S)) * (S + 1);
             float mx = row[0];
-            for (int j = 1; j < S; ++j) mx = fmaxf(mx, row[j]);
+            for (int j = 1; j < nu; ++j) mx = fmaxf(mx, row[j]);
             float sum = 0.f;
-            for (int j = 0; j < S; ++j) { const float e = expf(row[j] - mx); row[j] = e; sum += e; }
+            for (int j = 0; j < nu; ++j) { const float e = expf(row[j] - mx); row[j] = e; sum += e; }
             const float inv = 1.0f / sum;
-            for (int j = 0; j < S; ++j) row[j] *= inv;
+            for (int j = 0; j < nu; ++j) row[j] *= inv;
         }
         __syncthreads();
+        if (hg == 0) F32_PROF(8);
         // ---- P.V (:417): head-major channel concat, written in place over this head group's Q columns ---------
         {
             constexpr int GC = kHeadGroup * D;               // 96 channels in this head group
@@ -258,26 +341,29 @@ set_attention_fp32_kernel(const float* __restrict__ qin, const float* __restrict
                 float acc[RI];
 #pragma unroll
                 for (int r = 0; r < RI; ++r) acc[r] = 0.f;
+                if (i0 >= nu) continue;
                 const float* pr = Ss + s * L::xreg + (hl * S + i0) * (S + 1);
                 const float* Vt = Vs + s * TILE;
 #pragma unroll 4
-                for (int j = 0; j < S; ++j) {
+                for (int j = 0; j < nu; ++j) {
                     const float vj = Vt[j * kXs + c];
 #pragma unroll
-                    for (int r = 0; r < RI; ++r) acc[r] = fmaf(pr[r * (S + 1) + j], vj, acc[r]);
+                    for (int r = 0; r < RI; ++r) acc[r] = fmaf(pr[r * (S + 1) + j], vj, acc[r]);   // rows >= nu: unused
                 }
 #pragma unroll
-                for (int r = 0; r < RI; ++r) Qs[s * TILE + (i0 + r) * kXs + c] = acc[r];
+                for (int r = 0; r < RI; ++r)
+                    if (i0 + r < nu) Qs[s * TILE + (i0 + r) * kXs + c] = acc[r];
             }
         }
         __syncthreads();
+        if (hg == 0) F32_PROF(9);
     }
+    F32_PROF(10);
     // ---- out-projection (:448) + (fused) scatter to voxel rows -----------------
-    float* dst[NS];
-#pragma unroll
-    for (int s = 0; s < NS; ++s)
-        dst[s] = FUSED ? out + (size_t) b * max_pillars * kC : out + ((size_t) b * max_sets + set0 + s) * S * kC;
-    project<S, NS, true>(Qs, TILE, w.w_out_t, kC, w.b_out, 1.0f, nullptr, dst, FUSED ? s_rows : nullptr, live);
+    float* dst = FUSED ? out + (size_t) b * max_pillars * kC : out + ((size_t) b * max_sets + set0) * S * kC;
+    project<S, true>(Qs, w.w_out_t, kC, w.b_out, 1.0f, Ks /* K is dead: weight ring */, nullptr, dst,
+                     FUSED ? s_rows : nullptr, nu);
+    F32_PROF(11);
 }
 
 template <int S, bool FUSED>
@@ -285,6 +371,7 @@ int launch_fp32(const dsvt_set_attention_params* p, const AttnWeightsDev& w,
                 const float* q, const float* k, const float* v, const float* pos, const int* idx,
                 const float* mask, const int* set_num, const int* voxel_num, float* out, cudaStream_t st)
 {
+    // (one CTA per SM with half of the SM left to L1 for the weight stream was measured 40 % slower)
     const size_t smem = (size_t) AttnSmem<S>::total * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
@@ -322,3 +409,7 @@ int set_attention_fp32(const dsvt_set_attention_params* p, const AttnWeightsDev&
 }
 
 }  // namespace dsvt
+
+extern "C" int dsvt_debug_fp32_profile(long long* out32) {
+    return cudaMemcpyFromSymbol(out32, dsvt::g_fp32_prof, sizeof(long long) * 32) == cudaSuccess ? 0 : 1;
+}
