@@ -99,7 +99,8 @@ def load_peaks():
     if os.path.exists(path):
         p = json.load(open(path))
         return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
-                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "sm_max_mhz": p.get("sm_max_mhz", 1965.0), "source": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
@@ -399,6 +400,19 @@ def main():
         roof = {"kernel": dom_key, "bound": "hbm", "achieved": round(dom["gbs"], 2), "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": round(dom["hbm_frac"], 5), "traffic": None}
     roof["peak_source"] = peaks["source"] + (" burst cuBLAS bf16 / copy bandwidth (MEASURED_PEAKS.json)")
+    if dom.get("flops") and args.precision == "fp32":
+        # the FP32 configuration runs its contractions on the FP32 FMA pipe (exact arithmetic, tolerance 1e-3), so the
+        # tensor-core peak above is not attainable by construction; the FMA-pipe peak is given for orientation
+        sm = capi._lib().dsvt_device_sm_count()
+        fma_peak = sm * 128 * 2 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) * 1e-12
+        roof["fp32_fma_peak_tflops_nominal"] = round(fma_peak, 1)
+        roof["frac_of_fp32_fma_peak"] = round(dom["tflops"] / fma_peak, 4)
+        roof["note"] = ("flops = 11 612 160 x sets (SURVEY 8d, all 36 slots); the kernel only computes the distinct tokens "
+                        "of each set, so achieved counts algorithmic, not executed, flops")
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/), per launch
+    traffic = {"set_attention_0": {"fp32": 27.1e6, "fp16": 26.7e6}}.get(dom_key, {}).get(args.precision)
+    roof["traffic"] = traffic
+    roof["traffic_source"] = "dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_set_attention_*.txt" if traffic else None
     roof["share_of_frame"] = round(dom["us"] * dom["calls_per_frame"] / frame_us, 3)
     roof["timing"] = "CUDA events around single launches, L2 flushed, instrumented pass on the bench's frame 0"
     line = {

@@ -23,6 +23,10 @@ int set_attention_tc_fused(const dsvt_set_attention_params* p, const void* tc_bl
                            const float* x, const float* pos, const int* idx, const float* mask,
                            const int* set_num, const int* voxel_num, float* out, cudaStream_t st);
 
+int set_attention_tc2_fused(const dsvt_set_attention_params* p, const void* tc_blob,
+                            const float* x, const float* pos, const int* idx, const float* mask,
+                            const int* set_num, const int* voxel_num, float* out, cudaStream_t st);
+
 }  // namespace dsvt
 
 struct dsvt_attention_weights {

@@ -26,3 +26,14 @@ order = [0,1,2,3,4,5,34,33,30,31,32,6,7,8,9,10,11,20,21,22,23]
 prev = t[0]
 for i in order:
     print(f"{names[i]:24s} +{t[i]-prev:7d}  (t={t[i]-t[0]})"); prev = t[i]
+
+print("---- warp-specialised kernel (attention_tc2.cu) ----")
+capi._lib().dsvt_debug_tc2_profile(buf)
+t = np.array(buf[:], dtype=np.int64)
+t0 = t[0]
+lab = {0: "issuer: tile start", 1: "issuer: A tiles staged", 10: "issuer: PV(7) issued", 11: "issuer: Wout+O tile ready", 12: "issuer: out-proj issued",
+       16: "E: staging done", 26: "workers: out-proj done", 27: "workers: tile end"}
+for h in range(8):
+    lab[2 + h] = f"issuer: step {h} done"; lab[17 + h] = f"E: qkv({h}) written"; lab[32 + h] = f"S: P({h}) written"
+for i in sorted(lab, key=lambda i: t[i]):
+    print(f"{lab[i]:28s} t={t[i]-t0:7d}")
