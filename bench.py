@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=16, help="frames per GPU per step")
     ap.add_argument("--streams", type=int, default=4, help="concurrent frame streams per GPU")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "fp16"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32_cuda", "fp32_tc", "tf32", "fp16", "fp16_gemm"])
     ap.add_argument("--points", type=int, default=N_POINTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp16-config", action="store_true",
@@ -248,7 +248,7 @@ def plugin_breakdown(slot, cfg, peaks, reps=3):
         gs = f.gs[i]
         us = timed(lambda: capi.set_attention_fused(w.attn[i], f.x0, f.pos[i][0], gs.global_index_in_set[0],
                                                     gs.mask_expand_0[0], gs.set_num, f.vox.pillar_num, axis=0,
-                                                    out=f.attn_out, precision=f.precision))
+                                                    out=f.attn_out, precision=f.precision, workspace=f.attn_ws))
         flops = 11612160 * NS[i] if S == 36 else None
         res[f"set_attention_{i}"] = {"us": us, "flops": flops, "bytes": 83088 * NS[i] + 590000, "calls_per_frame": 4}
     for k, r in res.items():
@@ -316,7 +316,8 @@ def main():
     pipeline = importlib.import_module("dsvt-ai-trt_b200.pipeline")
     cfg = pkg.config.WAYMO
     peaks = load_peaks()
-    precision = {"fp32": capi.DSVT_ATTN_FP32, "tf32": capi.DSVT_ATTN_TF32, "fp16": capi.DSVT_ATTN_FP16}[args.precision]
+    precision = {"fp32": capi.DSVT_ATTN_FP32, "fp32_cuda": capi.DSVT_ATTN_FP32, "fp32_tc": capi.DSVT_ATTN_FP32_TC,
+                 "tf32": capi.DSVT_ATTN_TF32, "fp16": capi.DSVT_ATTN_FP16, "fp16_gemm": capi.DSVT_ATTN_FP16_GEMM}[args.precision]
 
     F, S = args.frames_per_step, max(1, min(args.streams, args.frames_per_step))
     weights = pipeline.FrameWeights(cfg, seed=0)

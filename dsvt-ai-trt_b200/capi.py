@@ -10,7 +10,7 @@ import torch
 
 from ._lib import load_library
 
-DSVT_ATTN_FP32, DSVT_ATTN_TF32, DSVT_ATTN_FP16 = 0, 1, 2
+DSVT_ATTN_FP32, DSVT_ATTN_TF32, DSVT_ATTN_FP16, DSVT_ATTN_FP32_TC, DSVT_ATTN_FP16_GEMM = 0, 1, 2, 3, 4
 
 
 class P2FParams(Structure):
@@ -302,9 +302,16 @@ def set_attention(weights, q, k, v, mask, set_num=None, out=None, precision=DSVT
     return out
 
 
+def set_attention_workspace_bytes(B, max_sets, S, C, heads, max_pillars, precision):
+    p = AttnParams(B, max_sets, S, C, heads, max_pillars, 0, precision, 1)
+    return int(_lib().dsvt_set_attention_workspace_size(ctypes.byref(p)))
+
+
 def set_attention_fused(weights, x, pos, global_index_in_set, mask, set_num, voxel_num, axis, out=None,
-                        precision=DSVT_ATTN_FP32, zero_tails=1):
-    """Fused gather + attention + scatter: x,pos [B,max_pillars,C], global_index_in_set [B,2,max_sets,S]."""
+                        precision=DSVT_ATTN_FP32, zero_tails=1, workspace=None):
+    """Fused gather + attention + scatter: x,pos [B,max_pillars,C], global_index_in_set [B,2,max_sets,S].
+    `workspace`: uint8 device tensor of dsvt_set_attention_workspace_size bytes (allocated here when None and the
+    precision needs one; pass a persistent buffer when capturing CUDA graphs)."""
     _need(x, torch.float32, "x")
     _need(pos, torch.float32, "pos")
     _need(global_index_in_set, torch.int32, "global_index_in_set")
@@ -314,9 +321,13 @@ def set_attention_fused(weights, x, pos, global_index_in_set, mask, set_num, vox
     max_sets, S = global_index_in_set.shape[-2], global_index_in_set.shape[-1]
     out = torch.empty_like(x) if out is None else out
     p = AttnParams(B, max_sets, S, C, weights.heads, max_pillars, axis, precision, zero_tails)
+    ws_bytes = int(_lib().dsvt_set_attention_workspace_size(ctypes.byref(p)))
+    if ws_bytes and workspace is None:
+        workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
     rc = _lib().dsvt_set_attention_fused_launch(ctypes.byref(p), c_void_p(weights.handle), _ptr(x), _ptr(pos),
                                                 _ptr(global_index_in_set), _ptr(mask), _ptr(set_num),
-                                                _ptr(voxel_num), _ptr(out), c_void_p(0), c_size_t(0), _stream())
+                                                _ptr(voxel_num), _ptr(out), _ptr(workspace),
+                                                c_size_t(workspace.numel() if workspace is not None else 0), _stream())
     _check(rc, "dsvt_set_attention_fused_launch")
     return out
 

@@ -35,6 +35,7 @@ extern "C" dsvt_attention_weights* dsvt_attention_weights_create(int32_t C, int3
     w->channel_num = C;
     w->num_heads = heads;
     w->tc_blob = nullptr;
+    w->split_blob = nullptr;
     if (cudaGetDevice(&w->device) != cudaSuccess ||
         cudaMalloc(&w->blob, host.size() * sizeof(float)) != cudaSuccess ||
         cudaMemcpy(w->blob, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -55,6 +56,15 @@ extern "C" dsvt_attention_weights* dsvt_attention_weights_create(int32_t C, int3
         return nullptr;
     }
     w->dev.tc_blob = w->tc_blob;
+    w->split_blob = attention_split_prepare(in_proj_weight, in_proj_bias, out_proj_weight, out_proj_bias,
+                                            w->split_out_mul);
+    if (!w->split_blob) {
+        set_last_error("dsvt_attention_weights_create: preparing the split-precision weight images failed");
+        cudaFree(w->blob);
+        cudaFree(w->tc_blob);
+        delete w;
+        return nullptr;
+    }
     return w;
 }
 
@@ -62,6 +72,7 @@ extern "C" void dsvt_attention_weights_destroy(dsvt_attention_weights* w) {
     if (!w) return;
     cudaFree(w->blob);
     if (w->tc_blob) cudaFree(w->tc_blob);
+    if (w->split_blob) cudaFree(w->split_blob);
     delete w;
 }
 
@@ -75,16 +86,26 @@ static int attn_check(const dsvt_set_attention_params* p, const dsvt_attention_w
 }
 
 extern "C" size_t dsvt_set_attention_workspace_size(const dsvt_set_attention_params* p) {
-    (void) p;
-    return 0;   // everything between the token tile and the output row stays on chip
+    if (p && (p->precision == DSVT_ATTN_FP32_TC || p->precision == DSVT_ATTN_FP16_GEMM))
+        return attention_split_workspace(p);   // qkv [B,max_pillars,3C] + o [B,max_pillars,C], f32
+    return 0;   // single-kernel paths: everything between the token tile and the output row stays on chip
 }
 
 static int attn_dispatch(const dsvt_set_attention_params* p, const dsvt_attention_weights* w, bool fused,
                          const float* q, const float* k, const float* v, const float* pos, const int* idx,
                          const float* mask, const int* set_num, const int* voxel_num, float* out,
-                         cudaStream_t st)
+                         void* workspace, size_t workspace_bytes, cudaStream_t st)
 {
     switch (p->precision) {
+        case DSVT_ATTN_FP32_TC:
+        case DSVT_ATTN_FP16_GEMM:
+            if (!fused) {
+                set_last_error("set attention: the GEMM pipeline is built for the fused entry point "
+                               "(dsvt_set_attention_fused_launch) only");
+                return DSVT_ERR_UNSUPPORTED;
+            }
+            return set_attention_split_fused(p, w->split_blob, w->split_out_mul, p->precision == DSVT_ATTN_FP32_TC,
+                                             q, pos, idx, mask, set_num, voxel_num, out, workspace, workspace_bytes, st);
         case DSVT_ATTN_FP32:
             return set_attention_fp32(p, w->dev, fused, q, k, v, pos, idx, mask, set_num, voxel_num, out, st);
         case DSVT_ATTN_FP16:
@@ -110,13 +131,12 @@ extern "C" int dsvt_set_attention_launch(const dsvt_set_attention_params* p, con
                                          const int32_t* set_num, float* out,
                                          void* workspace, size_t workspace_bytes, dsvt_stream_t stream)
 {
-    (void) workspace; (void) workspace_bytes;
     int rc = attn_check(p, w);
     if (rc != DSVT_OK) return rc;
     DSVT_CHECK_ARG(q && k && v && mask && out, "NULL tensor pointer");
     DSVT_CHECK_ARG(!(((uintptr_t) q | (uintptr_t) k | (uintptr_t) v | (uintptr_t) out) & 15), "16-B alignment");
     return attn_dispatch(p, w, false, q, k, v, nullptr, nullptr, mask, set_num, nullptr, out,
-                         reinterpret_cast<cudaStream_t>(stream));
+                         workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int dsvt_set_attention_fused_launch(const dsvt_set_attention_params* p, const dsvt_attention_weights* w,
@@ -125,7 +145,6 @@ extern "C" int dsvt_set_attention_fused_launch(const dsvt_set_attention_params* 
                                                const int32_t* set_num, const int32_t* voxel_num, float* out,
                                                void* workspace, size_t workspace_bytes, dsvt_stream_t stream)
 {
-    (void) workspace; (void) workspace_bytes;
     int rc = attn_check(p, w);
     if (rc != DSVT_OK) return rc;
     DSVT_CHECK_ARG(x && pos && global_index_in_set && mask && set_num && voxel_num && out, "NULL tensor pointer");
@@ -133,5 +152,5 @@ extern "C" int dsvt_set_attention_fused_launch(const dsvt_set_attention_params* 
     DSVT_CHECK_ARG(p->axis_id == 0 || p->axis_id == 1, "axis_id");
     DSVT_CHECK_ARG(!(((uintptr_t) x | (uintptr_t) pos | (uintptr_t) out) & 15), "16-B alignment");
     return attn_dispatch(p, w, true, x, nullptr, nullptr, pos, global_index_in_set, mask, set_num, voxel_num,
-                         out, reinterpret_cast<cudaStream_t>(stream));
+                         out, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -27,6 +27,15 @@ int set_attention_tc2_fused(const dsvt_set_attention_params* p, const void* tc_b
                             const float* x, const float* pos, const int* idx, const float* mask,
                             const int* set_num, const int* voxel_num, float* out, cudaStream_t st);
 
+// GEMM pipeline (attention_split.cu): DSVT_ATTN_FP32_TC (split = true) and DSVT_ATTN_FP16_GEMM (split = false)
+void* attention_split_prepare(const float* w_in, const float* b_in, const float* w_out, const float* b_out,
+                              float* out_mul);
+size_t attention_split_workspace(const dsvt_set_attention_params* p);
+int set_attention_split_fused(const dsvt_set_attention_params* p, const void* split_blob, const float* out_mul,
+                              bool split, const float* x, const float* pos, const int* idx, const float* mask,
+                              const int* set_num, const int* voxel_num, float* out, void* workspace,
+                              size_t workspace_bytes, cudaStream_t st);
+
 }  // namespace dsvt
 
 struct dsvt_attention_weights {
@@ -35,5 +44,7 @@ struct dsvt_attention_weights {
     int device;
     float* blob;            // one cudaMalloc: w_in_t | b_in | w_out_t | b_out
     void* tc_blob;
+    void* split_blob;       // weight images + biases of the GEMM pipeline
+    float split_out_mul[4]; // per role (Q, K, V, O): power of two undoing the weight pre-scaling
     dsvt::AttnWeightsDev dev;
 };

@@ -1,0 +1,608 @@
+// a3 -- set attention as a three-kernel pipeline (DSVT_ATTN_FP32_TC and DSVT_ATTN_FP16_GEMM):
+//
+//   1. proj_gemm_kernel (roles Q, K, V): per VOXEL (not per set slot) projections on tcgen05,
+//        Q = ((x+pos) Wq^T + bq) / sqrt(24),  K = (x+pos) Wk^T + bk,  V = x Wv^T + bv        -> qkv [V, 576] f32
+//      Every voxel belongs to exactly one set per axis (getSet's rank formula never lets two sets share a voxel),
+//      so projecting voxels instead of the 36 slots of every set removes the padding repeats (2/3 of the slots on the
+//      reference frame, ~1/2 at Waymo density) before any arithmetic happens.
+//   2. attn_core_kernel: one CTA per set gathers the K/V rows of the set's distinct tokens into shared memory and
+//      evaluates scores + key mask -> softmax -> PV in FP32 on the CUDA cores (8.6 % of the FLOPs, 36x36x24 per head:
+//      too small for a 128-row UMMA tile)                                                            -> o [V, 192] f32
+//   3. proj_gemm_kernel (role O): out = o Wout^T + bout, tail rows zero-filled                   -> out [V, 192] f32
+//
+// Restates multHeadAttention() (reference src/dsvt-ai-trt.cpp:288-458) with GetValueByIndex
+// (getValueByIndex.cu:282-303) and MapSetFeature2Voxel (mapSetFeature2voxel.cu:258-275) folded in.
+//
+// FP32 accuracy on FP16 tensor cores (DSVT_ATTN_FP32_TC): every operand a is split as a = hi + lo with
+// hi = fp16(a), lo = fp16(a - hi) (22 significand bits), and a product is evaluated as hi*hi + hi*lo + lo*hi -- three
+// tcgen05.mma.kind::f16 per K step accumulating in FP32 in TMEM; the dropped lo*lo term is 2^-22 relative.  Weights
+// are pre-scaled by a power of two per role so hi/lo stay in FP16's normal range (undone exactly in the epilogue);
+// activations must satisfy |x + pos| < 65504 (they are LayerNorm outputs).  DSVT_ATTN_FP16_GEMM uses the hi terms only.
+//
+// GEMM kernel: CTA tile 128 rows x 192 columns, K = 192 streamed in 6 chunks of 32 through a 2-stage ring
+// (A: 8 producer warps read FP32 rows with coalesced 128-bit loads, add pos, split, and write the UMMA K-major
+// interleaved layout of tc_common.cuh conflict-free; B: one cp.async.bulk per chunk of the pre-arranged weight
+// image); one thread issues the MMAs; the 8 producer warps then drain the 192 accumulator columns from TMEM.
+// 100 KB shared memory and 256 TMEM columns per CTA -> two CTAs per SM overlap each other's phases.
+#include "attention_common.cuh"
+#include "tc_common.cuh"
+#include <cuda_fp16.h>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace dsvt {
+namespace {
+
+using namespace tc;
+
+constexpr int kC = 192, kH = 8, kD = 24;
+constexpr int kBM = 128, kBN = 192, kBK = 32;
+constexpr int kNumK = kC / kBK;                      // 6 K chunks
+constexpr int kAStages = 3;                          // ring of A chunks
+constexpr int kProducers = 256;                      // warps 0-7 : A producers
+constexpr int kEpiWarps = 8;                         // warps 8-15: epilogue (TMEM lane quarter = warp % 4, column half = (warp-8)/4)
+constexpr int kIssuerWarp = 8 + kEpiWarps;           // warp 16  : weight copies + MMA issue
+constexpr int kThreadsG = (8 + kEpiWarps + 1) * 32;  // 544
+constexpr int kATerm = kBM * kBK * 2;                // 8192 B: one precision term of an A chunk
+constexpr int kBTerm = kBN * kBK * 2;                // 12288 B
+constexpr int kWChunkBytes = 2 * kBTerm;             // weight image per (role, K chunk): hi | lo
+constexpr int kWRoleBytes = kNumK * kWChunkBytes;    // 147456
+constexpr int kRoles = 4;                            // Q, K, V, O
+constexpr int kEpiScratch = 32 * 32 * 4;             // 4096 B per epilogue warp: 32 rows x 32 columns, XOR-swizzled float4s
+constexpr int kAccCols = 256;                        // TMEM column stride between the two accumulators
+
+template <bool SPLIT> struct Lay {
+    static constexpr int terms = SPLIT ? 2 : 1;
+    static constexpr int w_chunk = terms * kBTerm;                 // resident weight bytes per K chunk
+    static constexpr int w = 0;                                    // [6][hi | lo]
+    static constexpr int a = w + kNumK * w_chunk;                  // [kAStages][hi | lo]
+    static constexpr int a_stage = terms * kATerm;
+    static constexpr int epi = a + kAStages * a_stage;             // [4 warps][32][36] f32
+    static constexpr int total = epi + kEpiWarps * kEpiScratch;    // 229376 / 131072
+};
+
+struct GemmRole {
+    const float* a0;        // [rows, 192] f32
+    const float* a1;        // optional addend (pos), or nullptr
+    const uint8_t* wimg;    // this role's weight image
+    const float* bias;      // [192]
+    float* out;             // row-major, ld_out floats per row
+    int ld_out, col0;
+    float out_mul;          // 2^-s: undoes the weight pre-scaling
+    float post_mul;         // 1/sqrt(C/heads) for q, applied AFTER the biased projection like the reference's division
+                            // (:386-405; multiplying by the rounded reciprocal differs from dividing by <= 1 ulp)
+};
+struct GemmRoles { GemmRole r[3]; };
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) {
+    return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ long long g_split_prof[64];
+#define SP(i) do { if (blockIdx.x == 3 && blockIdx.y == 0) g_split_prof[(n_roles == 1 ? 40 : 0) + (i)] = clock64(); } while (0)
+
+// Persistent: grid = (n_roles * ctas_per_role, batch).  A CTA owns ONE role: its 147 KB weight image (hi + lo) is copied
+// into shared memory once and stays there while the CTA walks over row tiles t0, t0 + ctas_per_role, ...  Three engines
+// overlap through mbarriers: 8 producer warps fill a 3-stage ring of A chunks (FP32 rows -> (+pos) -> FP16 hi/lo,
+// loads for step g+2 in flight while step g is converted, across tile boundaries), one thread issues the MMAs into one
+// of two TMEM accumulators, 4 epilogue warps drain the other one (TMEM -> registers -> per-warp transposition scratch
+// -> full 128-byte row segments to global memory).
+template <bool SPLIT>
+__global__ void __launch_bounds__(kThreadsG, 1)
+proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num, int max_pillars, int zero_tails)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t w_full[kNumK], a_full[kAStages], a_empty[kAStages], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+    using L = Lay<SPLIT>;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y;
+    const int role_id = blockIdx.x % n_roles, t0 = blockIdx.x / n_roles, stride = gridDim.x / n_roles;
+    const GemmRole g = roles.r[role_id];
+    int V = voxel_num[b];
+    V = V < max_pillars ? V : max_pillars;
+    const int n_tiles = (max_pillars + kBM - 1) / kBM, valid_tiles = (V + kBM - 1) / kBM;
+    const int cnt = valid_tiles > t0 ? (valid_tiles - t0 + stride - 1) / stride : 0;    // row tiles this CTA computes
+    if (cnt == 0 && !zero_tails) return;
+    float* out = g.out + (size_t) b * max_pillars * g.ld_out + g.col0;
+    const float* a0 = g.a0 + (size_t) b * max_pillars * kC;
+    const float* a1 = g.a1 ? g.a1 + (size_t) b * max_pillars * kC : nullptr;
+    if (tid == 0) SP(0);
+
+    if (tid == 0) {
+        for (int s = 0; s < kNumK; ++s) mbar_init(&w_full[s], 1);
+        for (int s = 0; s < kAStages; ++s) { mbar_init(&a_full[s], kProducers); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
+        fence_barrier_init();
+    }
+    if (warp == kIssuerWarp) tmem_alloc<512>(&tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    if (tid == 0) SP(1);
+
+    if (warp < 8) {
+        // =========================== A PRODUCERS =========================================================
+        // step g = (tile n, K chunk kc, half): rows half*64 + warp*8 + (lane & 7), 16-byte K piece c16 = lane >> 3.
+        // A quarter-warp (8 lanes) writes 8 consecutive rows of one piece (128 contiguous bytes: conflict-free);
+        // the four lanes that share a row read one full 128-byte line of it.
+        constexpr int kStepsPerTile = kNumK * 2, kDepth = 3;
+        const int total = cnt * kStepsPerTile;
+        const int rl = warp * 8 + (lane & 7), c16 = lane >> 3;
+        float4 buf[kDepth][4];
+        auto issue = [&](int gs, float4 (&d)[4]) {
+            const int n = gs / kStepsPerTile, s = gs - n * kStepsPerTile;
+            const int kc = s >> 1, row = (t0 + n * stride) * kBM + (s & 1) * 64 + rl;
+            if (row < V) {
+                const float4* p0 = reinterpret_cast<const float4*>(a0 + (size_t) row * kC + kc * kBK + c16 * 8);
+                d[0] = __ldg(p0); d[1] = __ldg(p0 + 1);
+                if (a1) {
+                    const float4* p1 = reinterpret_cast<const float4*>(a1 + (size_t) row * kC + kc * kBK + c16 * 8);
+                    d[2] = __ldg(p1); d[3] = __ldg(p1 + 1);
+                } else {
+                    d[2] = d[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+                d[0] = d[1] = d[2] = d[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+#pragma unroll
+        for (int s = 0; s < kDepth - 1; ++s)
+            if (s < total) issue(s, buf[s]);
+#pragma unroll 1
+        for (int g0 = 0; g0 < total; g0 += 6) {           // 6 = lcm(2 halves, kDepth): buffer / half indices stay static
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+                const int gs = g0 + u;
+                if (gs + kDepth - 1 < total) issue(gs + kDepth - 1, buf[(u + kDepth - 1) % kDepth]);
+                const int cc = gs >> 1, st = cc % kAStages, r = (u & 1) * 64 + rl;
+                if ((u & 1) == 0 && cc >= kAStages) mbar_wait(&a_empty[st], ((cc / kAStages) - 1) & 1);
+                float4 (&d)[4] = buf[u % kDepth];
+                const float v[8] = {d[0].x + d[2].x, d[0].y + d[2].y, d[0].z + d[2].z, d[0].w + d[2].w,
+                                    d[1].x + d[3].x, d[1].y + d[3].y, d[1].z + d[3].z, d[1].w + d[3].w};
+                const uint4 hi = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+                uint8_t* stage = smem + L::a + st * L::a_stage;
+                *reinterpret_cast<uint4*>(stage + c16 * (kBM * 16) + r * 16) = hi;
+                if (SPLIT) {
+                    const float2 h0 = unpack_h2(hi.x), h1 = unpack_h2(hi.y), h2 = unpack_h2(hi.z), h3 = unpack_h2(hi.w);
+                    const uint4 lo = make_uint4(pack_h2(v[0] - h0.x, v[1] - h0.y), pack_h2(v[2] - h1.x, v[3] - h1.y),
+                                                pack_h2(v[4] - h2.x, v[5] - h2.y), pack_h2(v[6] - h3.x, v[7] - h3.y));
+                    *reinterpret_cast<uint4*>(stage + kATerm + c16 * (kBM * 16) + r * 16) = lo;
+                }
+                if (u & 1) {
+                    fence_proxy_async_smem();
+                    mbar_arrive(&a_full[st]);
+                    if (tid == 0 && cc < 6) SP(2 + cc);
+                }
+            }
+        }
+        if (tid == 0) SP(14);
+    } else if (warp < 8 + kEpiWarps) {
+        // =========================== EPILOGUE ============================================================
+        // warp = (TMEM lane quarter q4, column half hf): 3 slabs of 32 columns.  Slab: TMEM -> registers (lane = row)
+        // -> swizzled scratch -> (lane = 4 columns of 8 rows) scale + bias -> full 128-byte row segments to global.
+        const int q4 = warp & 3, hf = (warp - 8) >> 2;
+        float4* scr = reinterpret_cast<float4*>(smem + L::epi + (warp - 8) * kEpiScratch);
+        const uint32_t tlane = tmem + ((uint32_t) (q4 * 32) << 16) + hf * 96;
+        const int rg = lane >> 3, c4 = lane & 7;
+        const float* bias = g.bias + hf * 96 + c4 * 4;
+        float* outc = out + hf * 96 + c4 * 4;
+        for (int n = 0;; ++n) {
+            const int t = t0 + n * stride;
+            if (t >= n_tiles) break;
+            const int row0 = t * kBM + q4 * 32;                    // first row of this warp's lane quarter
+            if (n < cnt) {
+                const int acc = n & 1;
+                mbar_wait(&acc_full[acc], (n >> 1) & 1);
+                tc_fence_after_sync();
+                if (lane == 0 && warp == 8 && n == 0) SP(20);
+#pragma unroll 1
+                for (int j0 = 0; j0 < 96; j0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(tlane + acc * kAccCols + j0, r);
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + j0));
+                    tmem_ld_wait();
+                    if (j0 == 64) {                                // accumulator drained: hand it back to the issuer
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)                    // float4 j of row `lane` lands in slot j ^ (lane & 7)
+                        scr[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                                       __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                    __syncwarp();
+                    float4 v[8];
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const int rloc = rr * 4 + rg;
+                        v[rr] = scr[rloc * 8 + (c4 ^ (rloc & 7))];
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {               // 4 rows x 128 contiguous bytes per store instruction
+                        const int grow = row0 + rr * 4 + rg;
+                        // out_mul is a power of two: the product is exact, so this is one rounding of (acc + bias)
+                        float4 ov = make_float4((v[rr].x * g.out_mul + bb.x) * g.post_mul, (v[rr].y * g.out_mul + bb.y) * g.post_mul,
+                                                (v[rr].z * g.out_mul + bb.z) * g.post_mul, (v[rr].w * g.out_mul + bb.w) * g.post_mul);
+                        if (grow >= V) ov = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (grow < V || (zero_tails && grow < max_pillars))
+                            *reinterpret_cast<float4*>(outc + (size_t) grow * g.ld_out + j0) = ov;
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0 && warp == 8 && n == 0) SP(16);
+                if (lane == 0 && warp == 8 && n == cnt - 1) SP(17);
+            } else if (zero_tails) {                               // a tile of tail rows
+                for (int i = lane; i < 32 * 24; i += 32) {
+                    const int rloc = i / 24, cc4 = i - rloc * 24;
+                    if (row0 + rloc < max_pillars)
+                        *reinterpret_cast<float4*>(out + (size_t) (row0 + rloc) * g.ld_out + hf * 96 + cc4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+    } else {
+        // =========================== WEIGHT COPIES + MMA ISSUE ===========================================
+        if (lane == 0 && cnt > 0) {
+            for (int kc = 0; kc < kNumK; ++kc) {
+                mbar_arrive_expect_tx(&w_full[kc], L::w_chunk);
+                bulk_g2s(smem + L::w + kc * L::w_chunk, g.wimg + (size_t) kc * kWChunkBytes, L::w_chunk, &w_full[kc]);
+            }
+            const uint32_t idesc = make_idesc(kFmtF16, kBM, kBN);
+            const uint32_t sbase = smem_u32(smem);
+            int cc = 0;
+#pragma unroll 1
+            for (int n = 0; n < cnt; ++n) {
+                const int acc = n & 1;
+                if (n >= 2) { mbar_wait(&acc_empty[acc], ((n >> 1) - 1) & 1); tc_fence_after_sync(); }
+                const uint32_t d_tmem = tmem + acc * kAccCols;
+#pragma unroll 1
+                for (int kc = 0; kc < kNumK; ++kc, ++cc) {
+                    if (n == 0) mbar_wait(&w_full[kc], 0);
+                    const int st = cc % kAStages;
+                    mbar_wait(&a_full[st], (cc / kAStages) & 1);
+                    tc_fence_after_sync();
+                    if (n == 0) SP(8 + kc);
+                    const uint32_t sa = sbase + L::a + st * L::a_stage, sw = sbase + L::w + kc * L::w_chunk;
+#pragma unroll
+                    for (int ks = 0; ks < kBK / 16; ++ks) {
+                        const uint64_t a_hi = make_smem_desc(sa + ks * 2 * (kBM * 16), kBM * 16, 128);
+                        const uint64_t b_hi = make_smem_desc(sw + ks * 2 * (kBN * 16), kBN * 16, 128);
+                        if (SPLIT) {
+                            const uint64_t a_lo = make_smem_desc(sa + kATerm + ks * 2 * (kBM * 16), kBM * 16, 128);
+                            const uint64_t b_lo = make_smem_desc(sw + kBTerm + ks * 2 * (kBN * 16), kBN * 16, 128);
+                            umma_f16(d_tmem, a_lo, b_hi, idesc, (kc | ks) != 0);
+                            umma_f16(d_tmem, a_hi, b_lo, idesc, 1);
+                            umma_f16(d_tmem, a_hi, b_hi, idesc, 1);
+                        } else {
+                            umma_f16(d_tmem, a_hi, b_hi, idesc, (kc | ks) != 0);
+                        }
+                    }
+                    umma_commit(&a_empty[st]);
+                }
+                umma_commit(&acc_full[acc]);
+            }
+            SP(15);
+        }
+        __syncwarp();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (tid == 0) SP(21);
+    if (warp == kIssuerWarp) tmem_dealloc<512>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-set attention core.  One CTA per set, warp = head, lane = query token (a second round covers tokens 32..S-1).
+// K/V rows of the set's distinct tokens live in shared memory; every K/V read is a warp-wide broadcast of one row
+// segment.  Online softmax over key chunks of 4 (one rescale per chunk): K and V are each read once per query.
+constexpr int kCoreThreads = kH * 32;
+
+template <int S>
+__global__ void __launch_bounds__(kCoreThreads, (S <= 36) ? 3 : 2)
+attn_core_kernel(const float* __restrict__ qkv, const int* __restrict__ idx, const float* __restrict__ mask,
+                 const int* __restrict__ set_num, float* __restrict__ o, int max_sets, int max_pillars, int axis)
+{
+    static_assert(S % 4 == 0 && S <= 64, "set size");
+    extern __shared__ __align__(16) float sm[];
+    float* Ks = sm;                     // [S][192]
+    float* Vs = sm + S * kC;            // [S][192]
+    __shared__ int s_idx[S], s_rows[S], s_slot[S], s_nu;
+    __shared__ float s_mask[kH * S];    // the set's additive key mask as given: [head][slot]
+    __shared__ float s_cmask[kH][S];    // ... compacted: [head][token]
+
+    const int b = blockIdx.y, set = blockIdx.x, tid = threadIdx.x;
+    const int n_roles = 0; (void) n_roles;
+#define CP(i) do { if (blockIdx.x == 5 && blockIdx.y == 0 && threadIdx.x == 0) g_split_prof[32 + i] = clock64(); } while (0)
+    CP(0);
+    int ns = set_num[b];
+    ns = ns < max_sets ? ns : max_sets;
+    if (set >= ns) return;
+    qkv += (size_t) b * max_pillars * (3 * kC);
+    o += (size_t) b * max_pillars * kC;
+    const int h = tid >> 5, lane = tid & 31;
+    for (int t = tid; t < kH * S; t += kCoreThreads) s_mask[t] = mask[((size_t) b * max_sets + set) * kH * S + t];
+    if (tid < S) s_idx[tid] = idx[(((size_t) b * 2 + axis) * max_sets + set) * S + tid];
+    __syncthreads();
+
+    // token compaction, same rule as attention_fp32.cu: a slot that repeats the previous voxel AND is masked as a key
+    // by every head (getSet.cu:546-563) is the same token as its twin -- it is neither scored nor written twice
+    if (tid < 32) {
+        int base_u = 0;
+        for (int k0 = 0; k0 < S; k0 += 32) {
+            const int k = k0 + tid;
+            bool keep = false;
+            if (k < S) {
+                keep = (k == 0) || (s_idx[k] != s_idx[k - 1]);
+                if (!keep)
+#pragma unroll
+                    for (int hh = 0; hh < kH; ++hh) keep |= !(s_mask[hh * S + k] < -1e30f);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int u = base_u + __popc(bal & ((1u << tid) - 1u));
+                s_rows[u] = s_idx[k];
+                s_slot[u] = k;
+            }
+            base_u += __popc(bal);
+        }
+        if (tid == 0) s_nu = base_u;
+    }
+    __syncthreads();
+    CP(1);
+    const int nu = s_nu;
+    for (int t = tid; t < nu * (kC / 4) * 2; t += kCoreThreads) {          // K and V rows -> shared memory
+        const int which = t / (nu * (kC / 4)), t1 = t - which * (nu * (kC / 4));
+        const int j = t1 / (kC / 4), c4 = t1 - j * (kC / 4);
+        const float4 val = __ldg(reinterpret_cast<const float4*>(qkv + (size_t) s_rows[j] * (3 * kC) + (1 + which) * kC) + c4);
+        *reinterpret_cast<float4*>((which ? Vs : Ks) + j * kC + c4 * 4) = val;
+    }
+    for (int t = tid; t < kH * nu; t += kCoreThreads) {
+        const int hh = t / nu, j = t - hh * nu;
+        s_cmask[hh][j] = s_mask[hh * S + s_slot[j]];
+    }
+    float4 q[kD / 4];
+    if (lane < nu) {
+        const float4* qp = reinterpret_cast<const float4*>(qkv + (size_t) s_rows[lane] * (3 * kC) + h * kD);
+#pragma unroll
+        for (int d4 = 0; d4 < kD / 4; ++d4) q[d4] = __ldg(qp + d4);
+    }
+    __syncthreads();
+    CP(2);
+
+    for (int i0 = 0; i0 < nu; i0 += 32) {
+        const int i = i0 + lane;
+        if (i >= nu) break;
+        if (i0 > 0) {
+            const float4* qp = reinterpret_cast<const float4*>(qkv + (size_t) s_rows[i] * (3 * kC) + h * kD);
+#pragma unroll
+            for (int d4 = 0; d4 < kD / 4; ++d4) q[d4] = __ldg(qp + d4);
+        }
+        float m = -INFINITY, l = 0.f;
+        float4 acc[kD / 4];
+#pragma unroll
+        for (int d4 = 0; d4 < kD / 4; ++d4) acc[d4] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int j0 = 0; j0 < nu; j0 += 4) {
+            float sc[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = j0 + jj;                       // j < S always (S % 4 == 0): in bounds; rows >= nu are not used
+                const float4* kp = reinterpret_cast<const float4*>(Ks + j * kC + h * kD);
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                for (int d4 = 0; d4 < kD / 4; ++d4) {
+                    const float4 kv = kp[d4];
+                    a0 = fmaf(q[d4].x, kv.x, a0); a1 = fmaf(q[d4].y, kv.y, a1);
+                    a2 = fmaf(q[d4].z, kv.z, a2); a3 = fmaf(q[d4].w, kv.w, a3);
+                }
+                sc[jj] = j < nu ? ((a0 + a1) + (a2 + a3)) + s_cmask[h][j] : -INFINITY;
+            }
+            const float m_new = fmaxf(fmaxf(m, fmaxf(sc[0], sc[1])), fmaxf(sc[2], sc[3]));
+            const float alpha = expf(m - m_new);             // first chunk: exp(-inf) = 0
+            l *= alpha;
+#pragma unroll
+            for (int d4 = 0; d4 < kD / 4; ++d4) { acc[d4].x *= alpha; acc[d4].y *= alpha; acc[d4].z *= alpha; acc[d4].w *= alpha; }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = j0 + jj;
+                if (j < nu) {                                // warp-uniform
+                    const float p = expf(sc[jj] - m_new);
+                    l += p;
+                    const float4* vp = reinterpret_cast<const float4*>(Vs + j * kC + h * kD);
+#pragma unroll
+                    for (int d4 = 0; d4 < kD / 4; ++d4) {
+                        const float4 vv = vp[d4];
+                        acc[d4].x = fmaf(p, vv.x, acc[d4].x); acc[d4].y = fmaf(p, vv.y, acc[d4].y);
+                        acc[d4].z = fmaf(p, vv.z, acc[d4].z); acc[d4].w = fmaf(p, vv.w, acc[d4].w);
+                    }
+                }
+            }
+            m = m_new;
+        }
+        const float inv = 1.0f / l;
+        float4* op = reinterpret_cast<float4*>(o + (size_t) s_rows[i] * kC + h * kD);
+#pragma unroll
+        for (int d4 = 0; d4 < kD / 4; ++d4)
+            op[d4] = make_float4(acc[d4].x * inv, acc[d4].y * inv, acc[d4].z * inv, acc[d4].w * inv);
+    }
+    CP(3);
+}
+
+template <int S>
+int launch_core(const dsvt_set_attention_params* p, const float* qkv, const int* idx, const float* mask,
+                const int* set_num, float* o, cudaStream_t st)
+{
+    const size_t smem = (size_t) 2 * S * kC * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        DSVT_CUDA(cudaFuncSetAttribute(attn_core_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        DSVT_CUDA(cudaFuncSetAttribute(attn_core_kernel<S>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (int) cudaSharedmemCarveoutMaxShared));
+        attr_set = true;
+    }
+    attn_core_kernel<S><<<dim3(p->max_set_num, p->batch), kCoreThreads, smem, st>>>(qkv, idx, mask, set_num, o, p->max_set_num,
+                                                                          p->max_pillars_num, p->axis_id);
+    DSVT_LAUNCH_CHECK();
+    return DSVT_OK;
+}
+
+// split-image header kept in front of the device blob
+struct SplitBlobHeader {
+    float out_mul[kRoles];
+};
+
+}  // namespace
+
+// Device blob: [kRoles][kNumK][hi 12288 | lo 12288] weight images, then bias [kRoles][192] f32.
+// out_mul[] (host) receives the per-role power-of-two that undoes the weight pre-scaling.
+void* attention_split_prepare(const float* w_in, const float* b_in, const float* w_out, const float* b_out,
+                              float* out_mul)
+{
+    const size_t img_bytes = (size_t) kRoles * kWRoleBytes;
+    std::vector<uint8_t> host(img_bytes + (size_t) kRoles * kC * sizeof(float));
+    for (int role = 0; role < kRoles; ++role) {
+        const float* W = role < 3 ? w_in + (size_t) role * kC * kC : w_out;       // [192 out][192 in]
+        float maxabs = 0.f;
+        for (int t = 0; t < kC * kC; ++t) maxabs = fmaxf(maxabs, fabsf(W[t]));
+        int sh = 0;
+        if (maxabs > 0.f && std::isfinite(maxabs)) {
+            int e;
+            frexpf(maxabs, &e);              // maxabs = m * 2^e, m in [0.5, 1)
+            sh = 14 - e;                     // maxabs * 2^sh in [2^13, 2^14)
+            if (sh > 60) sh = 60;
+            if (sh < -60) sh = -60;
+        }
+        const float ws = ldexpf(1.0f, sh);
+        out_mul[role] = ldexpf(1.0f, -sh);
+        for (int kc = 0; kc < kNumK; ++kc) {
+            uint8_t* hi_img = host.data() + (size_t) role * kWRoleBytes + (size_t) kc * kWChunkBytes;
+            uint8_t* lo_img = hi_img + kBTerm;
+            for (int n = 0; n < kBN; ++n)
+                for (int c16 = 0; c16 < kBK / 8; ++c16)
+                    for (int e = 0; e < 8; ++e) {
+                        const float w = W[(size_t) n * kC + kc * kBK + c16 * 8 + e] * ws;
+                        const __half h = __float2half_rn(w);
+                        const __half l = __float2half_rn(w - __half2float(h));
+                        const uint16_t hb = __half_as_ushort(h), lb = __half_as_ushort(l);
+                        const size_t off = (size_t) c16 * (kBN * 16) + (size_t) n * 16 + e * 2;
+                        memcpy(hi_img + off, &hb, 2);
+                        memcpy(lo_img + off, &lb, 2);
+                    }
+        }
+        float* bias = reinterpret_cast<float*>(host.data() + img_bytes) + role * kC;
+        const float* bsrc = role < 3 ? b_in + role * kC : b_out;
+        for (int n = 0; n < kC; ++n) bias[n] = bsrc[n];
+    }
+    void* dev = nullptr;
+    if (cudaMalloc(&dev, host.size()) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(dev, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(dev);
+        return nullptr;
+    }
+    return dev;
+}
+
+size_t attention_split_workspace(const dsvt_set_attention_params* p) {
+    // qkv [B, max_pillars, 576] f32 | o [B, max_pillars, 192] f32
+    return align_up((size_t) p->batch * p->max_pillars_num * 3 * kC * sizeof(float), kWsAlign) +
+           align_up((size_t) p->batch * p->max_pillars_num * kC * sizeof(float), kWsAlign);
+}
+
+int set_attention_split_fused(const dsvt_set_attention_params* p, const void* split_blob, const float* out_mul,
+                              bool split, const float* x, const float* pos, const int* idx, const float* mask,
+                              const int* set_num, const int* voxel_num, float* out, void* workspace,
+                              size_t workspace_bytes, cudaStream_t st)
+{
+    if (p->channel_num != kC || p->num_heads != kH ||
+        (p->voxel_num_set != 24 && p->voxel_num_set != 36 && p->voxel_num_set != 48)) {
+        set_last_error("set attention (GEMM pipeline): only C=192, heads=8, set in {24,36,48} is built");
+        return DSVT_ERR_UNSUPPORTED;
+    }
+    if (!split_blob) {
+        set_last_error("set attention (GEMM pipeline): weights were not prepared");
+        return DSVT_ERR_INVALID_ARGUMENT;
+    }
+    if (!workspace || workspace_bytes < attention_split_workspace(p)) {
+        set_last_error("set attention (GEMM pipeline): workspace of %zu bytes required (dsvt_set_attention_workspace_size)",
+                       attention_split_workspace(p));
+        return DSVT_ERR_INVALID_ARGUMENT;
+    }
+    WsCarver ws(workspace);
+    float* qkv = ws.take<float>((size_t) p->batch * p->max_pillars_num * 3 * kC);
+    float* o = ws.take<float>((size_t) p->batch * p->max_pillars_num * kC);
+    const uint8_t* img = static_cast<const uint8_t*>(split_blob);
+    const float* bias = reinterpret_cast<const float*>(img + (size_t) kRoles * kWRoleBytes);
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        DSVT_CUDA(cudaFuncSetAttribute(proj_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<true>::total));
+        DSVT_CUDA(cudaFuncSetAttribute(proj_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<false>::total));
+        attr_set = true;
+    }
+    // persistent grids: one CTA per SM (divided among the batch), a multiple of the number of roles
+    const int per_b = sm_count() / p->batch;
+    const int grid_in = per_b >= 3 ? per_b / 3 * 3 : 3, grid_out = per_b >= 1 ? per_b : 1;
+    GemmRoles in_roles, out_roles;
+    for (int r = 0; r < 3; ++r) {
+        GemmRole& g = in_roles.r[r];
+        g.a0 = x;
+        g.a1 = r < 2 ? pos : nullptr;
+        g.wimg = img + (size_t) r * kWRoleBytes;
+        g.bias = bias + r * kC;
+        g.out = qkv;
+        g.ld_out = 3 * kC;
+        g.col0 = r * kC;
+        g.out_mul = out_mul[r];
+        g.post_mul = r == 0 ? 1.0f / sqrtf((float) (kC / kH)) : 1.0f;
+    }
+    {
+        GemmRole& g = out_roles.r[0];
+        g.a0 = o; g.a1 = nullptr;
+        g.wimg = img + (size_t) 3 * kWRoleBytes;
+        g.bias = bias + 3 * kC;
+        g.out = out; g.ld_out = kC; g.col0 = 0;
+        g.out_mul = out_mul[3];
+        g.post_mul = 1.0f;
+        out_roles.r[1] = out_roles.r[2] = g;
+    }
+    if (split) {
+        proj_gemm_kernel<true><<<dim3(grid_in, p->batch), kThreadsG, Lay<true>::total, st>>>(
+            in_roles, 3, voxel_num, p->max_pillars_num, 0);
+    } else {
+        proj_gemm_kernel<false><<<dim3(grid_in, p->batch), kThreadsG, Lay<false>::total, st>>>(
+            in_roles, 3, voxel_num, p->max_pillars_num, 0);
+    }
+    DSVT_LAUNCH_CHECK();
+    int rc;
+    switch (p->voxel_num_set) {
+        case 24: rc = launch_core<24>(p, qkv, idx, mask, set_num, o, st); break;
+        case 36: rc = launch_core<36>(p, qkv, idx, mask, set_num, o, st); break;
+        default: rc = launch_core<48>(p, qkv, idx, mask, set_num, o, st); break;
+    }
+    if (rc != DSVT_OK) return rc;
+    if (split) {
+        proj_gemm_kernel<true><<<dim3(grid_out, p->batch), kThreadsG, Lay<true>::total, st>>>(
+            out_roles, 1, voxel_num, p->max_pillars_num, p->zero_tails);
+    } else {
+        proj_gemm_kernel<false><<<dim3(grid_out, p->batch), kThreadsG, Lay<false>::total, st>>>(
+            out_roles, 1, voxel_num, p->max_pillars_num, p->zero_tails);
+    }
+    DSVT_LAUNCH_CHECK();
+    return DSVT_OK;
+}
+
+}  // namespace dsvt
+
+extern "C" int dsvt_debug_split_profile(long long* out64) {
+    return cudaMemcpyFromSymbol(out64, dsvt::g_split_prof, sizeof(long long) * 64) == cudaSuccess ? 0 : 1;
+}

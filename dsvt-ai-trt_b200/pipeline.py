@@ -59,6 +59,8 @@ class HotPathFrame:
         self.cand = [torch.from_numpy(c).to(device)[None] for c in cand]           # CenterHead top-K outputs
         # activations
         self.attn_out = torch.empty(mp, C, device=device)
+        ws = capi.set_attention_workspace_bytes(1, cfg.max_win_num, cfg.voxel_num_set, C, cfg.num_heads, mp, precision)
+        self.attn_ws = torch.empty(ws, dtype=torch.uint8, device=device) if ws else None   # qkv + o of the GEMM pipeline
         self.src = torch.empty(mp, C, device=device)
         self.src_b = torch.empty(mp, C, device=device)
         self.gelu_out = torch.empty(mp, F, device=device)
@@ -91,7 +93,7 @@ class HotPathFrame:
             for enc in (0, 1):
                 capi.set_attention_fused(w.attn[blk * 2 + enc], x, self.pos[blk][enc], gs.global_index_in_set[0],
                                          gs.mask_expand_0[0], gs.set_num, V, axis=enc, out=self.attn_out,
-                                         precision=self.precision)
+                                         precision=self.precision, workspace=self.attn_ws)
                 capi.layer_norm(self.attn_out, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=x,
                                 out=self.src); ln += 1                                     # norm1(y + x)   :669-676
                 capi.gelu(self.ffn_hidden, V, out=self.gelu_out)                           # :519 (inside the FFN)

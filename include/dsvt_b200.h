@@ -221,8 +221,13 @@ int dsvt_filter_box_launch(const dsvt_filter_box_params* p,
 enum {
     DSVT_ATTN_FP32 = 0,      /* CUDA-core FP32 contractions: the FP32 configuration (tolerance 1e-3)                */
     DSVT_ATTN_TF32 = 1,      /* tcgen05 kind::tf32 operands, FP32 accumulate in TMEM (dense linear layers only)      */
-    DSVT_ATTN_FP16 = 2       /* tcgen05 kind::f16, FP16 operands, FP32 accumulate: the reference's USE_FP16
-                                configuration (params.h:332; tolerance 1e-2)                                        */
+    DSVT_ATTN_FP16 = 2,      /* tcgen05 kind::f16, FP16 operands, FP32 accumulate: the reference's USE_FP16
+                                configuration (params.h:332; tolerance 1e-2); one fused kernel, QK^T / PV on tcgen05 */
+    DSVT_ATTN_FP32_TC = 3,   /* FP32-accurate on tcgen05 (fused entry point, needs a workspace): per-voxel projection
+                                GEMMs with every operand split into FP16 hi + lo and three kind::f16 MMAs per product
+                                (2^-22 relative), FP32 accumulate; per-set QK^T / softmax / PV in FP32 on CUDA cores.
+                                Same tolerance as DSVT_ATTN_FP32.  Domain: |x + pos| < 65504.                        */
+    DSVT_ATTN_FP16_GEMM = 4  /* the pipeline of DSVT_ATTN_FP32_TC with single FP16 operands (tolerance 1e-2)         */
 };
 
 typedef struct dsvt_set_attention_params {
