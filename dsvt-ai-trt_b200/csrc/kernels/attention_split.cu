@@ -82,6 +82,15 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 __device__ __forceinline__ float2 unpack_h2(uint32_t u) {
     return __half22float2(*reinterpret_cast<__half2*>(&u));
 }
+// 256-bit read-only global load (sm_100: LDG.E.256): p must be 32-byte aligned
+__device__ __forceinline__ void ldg256(const float* p, float* d) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]), "=f"(d[4]), "=f"(d[5]), "=f"(d[6]), "=f"(d[7]) : "l"(p));
+}
+// asynchronous L2 prefetch of a contiguous range (bytes: multiple of 16)
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -139,21 +148,20 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
         constexpr int kStepsPerTile = kNumK * 2, kDepth = 3;
         const int total = cnt * kStepsPerTile;
         const int rl = warp * 8 + (lane & 7), c16 = lane >> 3;
-        float4 buf[kDepth][4];
-        auto issue = [&](int gs, float4 (&d)[4]) {
+        float buf[kDepth][16];                                  // [0..7] = a0 row piece, [8..15] = a1 (pos) row piece
+        auto issue = [&](int gs, float (&d)[16]) {
             const int n = gs / kStepsPerTile, s = gs - n * kStepsPerTile;
             const int kc = s >> 1, row = (t0 + n * stride) * kBM + (s & 1) * 64 + rl;
             if (row < V) {
-                const float4* p0 = reinterpret_cast<const float4*>(a0 + (size_t) row * kC + kc * kBK + c16 * 8);
-                d[0] = __ldg(p0); d[1] = __ldg(p0 + 1);
-                if (a1) {
-                    const float4* p1 = reinterpret_cast<const float4*>(a1 + (size_t) row * kC + kc * kBK + c16 * 8);
-                    d[2] = __ldg(p1); d[3] = __ldg(p1 + 1);
-                } else {
-                    d[2] = d[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+                ldg256(a0 + (size_t) row * kC + kc * kBK + c16 * 8, &d[0]);      // one 256-bit load: full 32-byte sectors
+                if (a1) ldg256(a1 + (size_t) row * kC + kc * kBK + c16 * 8, &d[8]);
+                else {
+#pragma unroll
+                    for (int e = 8; e < 16; ++e) d[e] = 0.f;
                 }
             } else {
-                d[0] = d[1] = d[2] = d[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) d[e] = 0.f;
             }
         };
 #pragma unroll
@@ -167,9 +175,9 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
                 if (gs + kDepth - 1 < total) issue(gs + kDepth - 1, buf[(u + kDepth - 1) % kDepth]);
                 const int cc = gs >> 1, st = cc % kAStages, r = (u & 1) * 64 + rl;
                 if ((u & 1) == 0 && cc >= kAStages) mbar_wait(&a_empty[st], ((cc / kAStages) - 1) & 1);
-                float4 (&d)[4] = buf[u % kDepth];
-                const float v[8] = {d[0].x + d[2].x, d[0].y + d[2].y, d[0].z + d[2].z, d[0].w + d[2].w,
-                                    d[1].x + d[3].x, d[1].y + d[3].y, d[1].z + d[3].z, d[1].w + d[3].w};
+                float (&d)[16] = buf[u % kDepth];
+                const float v[8] = {d[0] + d[8], d[1] + d[9], d[2] + d[10], d[3] + d[11],
+                                    d[4] + d[12], d[5] + d[13], d[6] + d[14], d[7] + d[15]};
                 const uint4 hi = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
                 uint8_t* stage = smem + L::a + st * L::a_stage;
                 *reinterpret_cast<uint4*>(stage + c16 * (kBM * 16) + r * 16) = hi;
@@ -253,6 +261,14 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
     } else {
         // =========================== WEIGHT COPIES + MMA ISSUE ===========================================
         if (lane == 0 && cnt > 0) {
+            // pull this CTA's row tiles into L2 as large sequential requests (a tile is 96 KB contiguous per source); the
+            // producers then read them in 128-byte-per-row K chunks, a pattern that wastes DRAM pages when it misses L2
+            for (int n = 0; n < cnt; ++n) {
+                const int row0 = (t0 + n * stride) * kBM;
+                const uint32_t bytes = (uint32_t) ((V - row0 < kBM ? V - row0 : kBM) * kC * sizeof(float));
+                l2_prefetch(a0 + (size_t) row0 * kC, bytes);
+                if (a1) l2_prefetch(a1 + (size_t) row0 * kC, bytes);
+            }
             for (int kc = 0; kc < kNumK; ++kc) {
                 mbar_arrive_expect_tx(&w_full[kc], L::w_chunk);
                 bulk_g2s(smem + L::w + kc * L::w_chunk, g.wimg + (size_t) kc * kWChunkBytes, L::w_chunk, &w_full[kc]);
@@ -302,147 +318,205 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Per-set attention core.  One CTA per set, warp = head, lane = query token (a second round covers tokens 32..S-1).
-// K/V rows of the set's distinct tokens live in shared memory; every K/V read is a warp-wide broadcast of one row
-// segment.  Online softmax over key chunks of 4 (one rescale per chunk): K and V are each read once per query.
-constexpr int kCoreThreads = kH * 32;
+// Per-set attention core.  One CTA per set (grid-stride), thread = (token pair, head h) with h fastest: a warp is 4 token
+// pairs x 8 heads.  Each K/V piece read from shared memory feeds TWO queries (register tiling: the kernel is bound by
+// instruction issue, not by FLOPs), the dot products and the PV update use the packed FFMA2 (two FP32 FMAs per
+// instruction, same IEEE arithmetic).  A K/V read is 8 distinct 16-byte pieces (one per head) broadcast to the 4 pairs;
+// heads are padded to 28 floats in shared memory (7 x 16 B: odd, so the 8 pieces fall into 8 different bank groups).
+// Online softmax over key chunks of 4 (one rescale per chunk): K and V are each read once per query pair.
+constexpr int kHP = 28;                 // padded head stride (floats)
+constexpr int kRowP = kH * kHP;         // 224 floats per token row in shared memory
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+constexpr float kLog2e = 1.4426950408889634f;
+// 2^x on the SFU (one MUFU.EX2; 2^-inf = +0): the softmax runs in the log2 domain, exp(s - m) = 2^((s - m) log2 e)
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 template <int S>
-__global__ void __launch_bounds__(kCoreThreads, (S <= 36) ? 3 : 2)
+__global__ void __launch_bounds__(S / 2 * kH, 2)
 attn_core_kernel(const float* __restrict__ qkv, const int* __restrict__ idx, const float* __restrict__ mask,
                  const int* __restrict__ set_num, float* __restrict__ o, int max_sets, int max_pillars, int axis)
 {
     static_assert(S % 4 == 0 && S <= 64, "set size");
+    constexpr int NT = S / 2 * kH;      // 144 threads for S = 36
     extern __shared__ __align__(16) float sm[];
-    float* Ks = sm;                     // [S][192]
-    float* Vs = sm + S * kC;            // [S][192]
+    float* Ks = sm;                     // [S][8][28]
+    float* Vs = sm + S * kRowP;
     __shared__ int s_idx[S], s_rows[S], s_slot[S], s_nu;
     __shared__ float s_mask[kH * S];    // the set's additive key mask as given: [head][slot]
     __shared__ float s_cmask[kH][S];    // ... compacted: [head][token]
 
-    const int b = blockIdx.y, set = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.y, tid = threadIdx.x;
     const int n_roles = 0; (void) n_roles;
 #define CP(i) do { if (blockIdx.x == 5 && blockIdx.y == 0 && threadIdx.x == 0) g_split_prof[32 + i] = clock64(); } while (0)
     CP(0);
-    int ns = set_num[b];
-    ns = ns < max_sets ? ns : max_sets;
-    if (set >= ns) return;
     qkv += (size_t) b * max_pillars * (3 * kC);
     o += (size_t) b * max_pillars * kC;
-    const int h = tid >> 5, lane = tid & 31;
-    for (int t = tid; t < kH * S; t += kCoreThreads) s_mask[t] = mask[((size_t) b * max_sets + set) * kH * S + t];
-    if (tid < S) s_idx[tid] = idx[(((size_t) b * 2 + axis) * max_sets + set) * S + tid];
-    __syncthreads();
+    const int pr = tid >> 3, h = tid & 7;
+    const int i0 = 2 * pr, i1 = i0 + 1;
+    // the first set's mask / index block is fetched BEFORE set_num is known (blockIdx.x < max_sets: always in bounds), so
+    // the CTA's chain of dependent global round trips is  {set_num, mask, idx} -> rows -> K/V  instead of four deep
+    float mreg[(kH * S + NT - 1) / NT];
+    int ireg = 0;
+    {
+        const int set = blockIdx.x;
+#pragma unroll
+        for (int t = 0; t < (kH * S + NT - 1) / NT; ++t)
+            mreg[t] = tid + t * NT < kH * S ? __ldg(mask + ((size_t) b * max_sets + set) * kH * S + tid + t * NT) : 0.f;
+        if (tid < S) ireg = __ldg(idx + (((size_t) b * 2 + axis) * max_sets + set) * S + tid);
+    }
+    int ns = set_num[b];
+    ns = ns < max_sets ? ns : max_sets;
 
-    // token compaction, same rule as attention_fp32.cu: a slot that repeats the previous voxel AND is masked as a key
-    // by every head (getSet.cu:546-563) is the same token as its twin -- it is neither scored nor written twice
-    if (tid < 32) {
-        int base_u = 0;
-        for (int k0 = 0; k0 < S; k0 += 32) {
-            const int k = k0 + tid;
-            bool keep = false;
-            if (k < S) {
-                keep = (k == 0) || (s_idx[k] != s_idx[k - 1]);
-                if (!keep)
+    for (int set = blockIdx.x; set < ns; set += gridDim.x) {
+        if (set != (int) blockIdx.x) {
 #pragma unroll
-                    for (int hh = 0; hh < kH; ++hh) keep |= !(s_mask[hh * S + k] < -1e30f);
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            if (keep) {
-                const int u = base_u + __popc(bal & ((1u << tid) - 1u));
-                s_rows[u] = s_idx[k];
-                s_slot[u] = k;
-            }
-            base_u += __popc(bal);
+            for (int t = 0; t < (kH * S + NT - 1) / NT; ++t)
+                mreg[t] = tid + t * NT < kH * S ? __ldg(mask + ((size_t) b * max_sets + set) * kH * S + tid + t * NT) : 0.f;
+            if (tid < S) ireg = __ldg(idx + (((size_t) b * 2 + axis) * max_sets + set) * S + tid);
         }
-        if (tid == 0) s_nu = base_u;
-    }
-    __syncthreads();
-    CP(1);
-    const int nu = s_nu;
-    for (int t = tid; t < nu * (kC / 4) * 2; t += kCoreThreads) {          // K and V rows -> shared memory
-        const int which = t / (nu * (kC / 4)), t1 = t - which * (nu * (kC / 4));
-        const int j = t1 / (kC / 4), c4 = t1 - j * (kC / 4);
-        const float4 val = __ldg(reinterpret_cast<const float4*>(qkv + (size_t) s_rows[j] * (3 * kC) + (1 + which) * kC) + c4);
-        *reinterpret_cast<float4*>((which ? Vs : Ks) + j * kC + c4 * 4) = val;
-    }
-    for (int t = tid; t < kH * nu; t += kCoreThreads) {
-        const int hh = t / nu, j = t - hh * nu;
-        s_cmask[hh][j] = s_mask[hh * S + s_slot[j]];
-    }
-    float4 q[kD / 4];
-    if (lane < nu) {
-        const float4* qp = reinterpret_cast<const float4*>(qkv + (size_t) s_rows[lane] * (3 * kC) + h * kD);
 #pragma unroll
-        for (int d4 = 0; d4 < kD / 4; ++d4) q[d4] = __ldg(qp + d4);
-    }
-    __syncthreads();
-    CP(2);
+        for (int t = 0; t < (kH * S + NT - 1) / NT; ++t)
+            if (tid + t * NT < kH * S) s_mask[tid + t * NT] = mreg[t];
+        if (tid < S) s_idx[tid] = ireg;
+        __syncthreads();
 
-    for (int i0 = 0; i0 < nu; i0 += 32) {
-        const int i = i0 + lane;
-        if (i >= nu) break;
-        if (i0 > 0) {
-            const float4* qp = reinterpret_cast<const float4*>(qkv + (size_t) s_rows[i] * (3 * kC) + h * kD);
+        // token compaction, same rule as attention_fp32.cu: a slot that repeats the previous voxel AND is masked as a
+        // key by every head (getSet.cu:546-563) is the same token as its twin -- it is neither scored nor written twice
+        if (tid < 32) {
+            int base_u = 0;
+            for (int k0 = 0; k0 < S; k0 += 32) {
+                const int k = k0 + tid;
+                bool keep = false;
+                if (k < S) {
+                    keep = (k == 0) || (s_idx[k] != s_idx[k - 1]);
+                    if (!keep)
 #pragma unroll
-            for (int d4 = 0; d4 < kD / 4; ++d4) q[d4] = __ldg(qp + d4);
-        }
-        float m = -INFINITY, l = 0.f;
-        float4 acc[kD / 4];
-#pragma unroll
-        for (int d4 = 0; d4 < kD / 4; ++d4) acc[d4] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-        for (int j0 = 0; j0 < nu; j0 += 4) {
-            float sc[4];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const int j = j0 + jj;                       // j < S always (S % 4 == 0): in bounds; rows >= nu are not used
-                const float4* kp = reinterpret_cast<const float4*>(Ks + j * kC + h * kD);
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-                for (int d4 = 0; d4 < kD / 4; ++d4) {
-                    const float4 kv = kp[d4];
-                    a0 = fmaf(q[d4].x, kv.x, a0); a1 = fmaf(q[d4].y, kv.y, a1);
-                    a2 = fmaf(q[d4].z, kv.z, a2); a3 = fmaf(q[d4].w, kv.w, a3);
+                        for (int hh = 0; hh < kH; ++hh) keep |= !(s_mask[hh * S + k] < -1e30f);
                 }
-                sc[jj] = j < nu ? ((a0 + a1) + (a2 + a3)) + s_cmask[h][j] : -INFINITY;
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    const int u = base_u + __popc(bal & ((1u << tid) - 1u));
+                    s_rows[u] = s_idx[k];
+                    s_slot[u] = k;
+                }
+                base_u += __popc(bal);
             }
-            const float m_new = fmaxf(fmaxf(m, fmaxf(sc[0], sc[1])), fmaxf(sc[2], sc[3]));
-            const float alpha = expf(m - m_new);             // first chunk: exp(-inf) = 0
-            l *= alpha;
+            if (tid == 0) s_nu = base_u;
+        }
+        __syncthreads();
+        CP(1);
+        const int nu = s_nu;
+        {   // K and V rows -> shared memory: thread = (float4 column c4 of a 192-float row, row phase); no runtime
+            // divisions in the loops
+            constexpr int kCols = kC / 4, kPhases = NT / kCols;            // 48 columns, 3 phases (S = 36)
+            static_assert(NT % kCols == 0, "staging layout");
+            const int c4 = tid % kCols, hh = c4 / (kD / 4), d4 = c4 % (kD / 4);
+            const int off = hh * kHP + d4 * 4;
+            const int nu4 = (nu + 3) & ~3;                                 // keys are processed in chunks of 4
+            for (int j = tid / kCols; j < nu4; j += kPhases) {
+                float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;      // pad keys: zero rows, masked with -inf below
+                if (j < nu) {
+                    const float4* src = reinterpret_cast<const float4*>(qkv + (size_t) s_rows[j] * (3 * kC) + kC) + c4;
+                    kk = __ldg(src); vv = __ldg(src + kCols);
+                }
+                *reinterpret_cast<float4*>(Ks + j * kRowP + off) = kk;
+                *reinterpret_cast<float4*>(Vs + j * kRowP + off) = vv;
+            }
+        }
+        for (int t = tid; t < kH * S; t += NT) {                           // key mask in the log2 domain of the softmax
+            const int hh = t / S, j = t % S;
+            s_cmask[hh][j] = j < nu ? s_mask[hh * S + s_slot[j]] * kLog2e : -INFINITY;
+        }
+        float2 q0[kD / 2], q1[kD / 2];
+        if (i0 < nu) {
+            const float4* qp = reinterpret_cast<const float4*>(qkv + (size_t) s_rows[i0] * (3 * kC) + h * kD);
+            const float4* qp1 = reinterpret_cast<const float4*>(qkv + (size_t) s_rows[i1 < nu ? i1 : i0] * (3 * kC) + h * kD);
 #pragma unroll
-            for (int d4 = 0; d4 < kD / 4; ++d4) { acc[d4].x *= alpha; acc[d4].y *= alpha; acc[d4].z *= alpha; acc[d4].w *= alpha; }
+            for (int d4 = 0; d4 < kD / 4; ++d4) {
+                const float4 t = __ldg(qp + d4), u = __ldg(qp1 + d4);
+                q0[2 * d4] = f2(t.x, t.y); q0[2 * d4 + 1] = f2(t.z, t.w);
+                q1[2 * d4] = f2(u.x, u.y); q1[2 * d4 + 1] = f2(u.z, u.w);
+            }
+        }
+        __syncthreads();
+        CP(2);
+
+        if (i0 < nu) {
+            float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+            float2 acc0[kD / 2], acc1[kD / 2];
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const int j = j0 + jj;
-                if (j < nu) {                                // warp-uniform
-                    const float p = expf(sc[jj] - m_new);
-                    l += p;
-                    const float4* vp = reinterpret_cast<const float4*>(Vs + j * kC + h * kD);
+            for (int d2 = 0; d2 < kD / 2; ++d2) { acc0[d2] = f2(0.f, 0.f); acc1[d2] = f2(0.f, 0.f); }
+#pragma unroll 1
+            for (int j0 = 0; j0 < nu; j0 += 4) {
+                // branch-free chunk of 4 keys (pad keys carry zero rows and a -inf mask): scores in the log2 domain
+                float sc0[4], sc1[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = j0 + jj;
+                    const float4* kp = reinterpret_cast<const float4*>(Ks + j * kRowP + h * kHP);
+                    float2 a0 = f2(0.f, 0.f), a1 = f2(0.f, 0.f), b0 = f2(0.f, 0.f), b1 = f2(0.f, 0.f);
+#pragma unroll
+                    for (int d4 = 0; d4 < kD / 4; ++d4) {
+                        const float4 kv = kp[d4];
+                        const float2 klo = f2(kv.x, kv.y), khi = f2(kv.z, kv.w);
+                        a0 = __ffma2_rn(q0[2 * d4], klo, a0); a1 = __ffma2_rn(q0[2 * d4 + 1], khi, a1);
+                        b0 = __ffma2_rn(q1[2 * d4], klo, b0); b1 = __ffma2_rn(q1[2 * d4 + 1], khi, b1);
+                    }
+                    const float mk = s_cmask[h][j];
+                    sc0[jj] = fmaf((a0.x + a0.y) + (a1.x + a1.y), kLog2e, mk);
+                    sc1[jj] = fmaf((b0.x + b0.y) + (b1.x + b1.y), kLog2e, mk);
+                }
+                const float m0n = fmaxf(fmaxf(m0, fmaxf(sc0[0], sc0[1])), fmaxf(sc0[2], sc0[3]));
+                const float m1n = fmaxf(fmaxf(m1, fmaxf(sc1[0], sc1[1])), fmaxf(sc1[2], sc1[3]));
+                const float al0 = ex2(m0 - m0n), al1 = ex2(m1 - m1n);            // first chunk: 2^-inf = 0
+                l0 *= al0; l1 *= al1;
+                const float2 al02 = f2(al0, al0), al12 = f2(al1, al1);
+#pragma unroll
+                for (int d2 = 0; d2 < kD / 2; ++d2) { acc0[d2] = __fmul2_rn(acc0[d2], al02); acc1[d2] = __fmul2_rn(acc1[d2], al12); }
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = j0 + jj;
+                    const float p0 = ex2(sc0[jj] - m0n), p1 = ex2(sc1[jj] - m1n);
+                    l0 += p0; l1 += p1;
+                    const float2 p02 = f2(p0, p0), p12 = f2(p1, p1);
+                    const float4* vp = reinterpret_cast<const float4*>(Vs + j * kRowP + h * kHP);
 #pragma unroll
                     for (int d4 = 0; d4 < kD / 4; ++d4) {
                         const float4 vv = vp[d4];
-                        acc[d4].x = fmaf(p, vv.x, acc[d4].x); acc[d4].y = fmaf(p, vv.y, acc[d4].y);
-                        acc[d4].z = fmaf(p, vv.z, acc[d4].z); acc[d4].w = fmaf(p, vv.w, acc[d4].w);
+                        const float2 vlo = f2(vv.x, vv.y), vhi = f2(vv.z, vv.w);
+                        acc0[2 * d4] = __ffma2_rn(p02, vlo, acc0[2 * d4]); acc0[2 * d4 + 1] = __ffma2_rn(p02, vhi, acc0[2 * d4 + 1]);
+                        acc1[2 * d4] = __ffma2_rn(p12, vlo, acc1[2 * d4]); acc1[2 * d4 + 1] = __ffma2_rn(p12, vhi, acc1[2 * d4 + 1]);
                     }
                 }
+                m0 = m0n; m1 = m1n;
             }
-            m = m_new;
-        }
-        const float inv = 1.0f / l;
-        float4* op = reinterpret_cast<float4*>(o + (size_t) s_rows[i] * kC + h * kD);
+            const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+            float4* op = reinterpret_cast<float4*>(o + (size_t) s_rows[i0] * kC + h * kD);
 #pragma unroll
-        for (int d4 = 0; d4 < kD / 4; ++d4)
-            op[d4] = make_float4(acc[d4].x * inv, acc[d4].y * inv, acc[d4].z * inv, acc[d4].w * inv);
+            for (int d4 = 0; d4 < kD / 4; ++d4)
+                op[d4] = make_float4(acc0[2 * d4].x * inv0, acc0[2 * d4].y * inv0, acc0[2 * d4 + 1].x * inv0, acc0[2 * d4 + 1].y * inv0);
+            if (i1 < nu) {
+                float4* op1 = reinterpret_cast<float4*>(o + (size_t) s_rows[i1] * kC + h * kD);
+#pragma unroll
+                for (int d4 = 0; d4 < kD / 4; ++d4)
+                    op1[d4] = make_float4(acc1[2 * d4].x * inv1, acc1[2 * d4].y * inv1, acc1[2 * d4 + 1].x * inv1, acc1[2 * d4 + 1].y * inv1);
+            }
+        }
+        CP(3);
+        __syncthreads();        // shared memory is recycled by the next set
     }
-    CP(3);
 }
 
 template <int S>
 int launch_core(const dsvt_set_attention_params* p, const float* qkv, const int* idx, const float* mask,
                 const int* set_num, float* o, cudaStream_t st)
 {
-    const size_t smem = (size_t) 2 * S * kC * sizeof(float);
+    const size_t smem = (size_t) 2 * S * kRowP * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         DSVT_CUDA(cudaFuncSetAttribute(attn_core_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -450,8 +524,10 @@ int launch_core(const dsvt_set_attention_params* p, const float* qkv, const int*
                                        (int) cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
-    attn_core_kernel<S><<<dim3(p->max_set_num, p->batch), kCoreThreads, smem, st>>>(qkv, idx, mask, set_num, o, p->max_set_num,
-                                                                          p->max_pillars_num, p->axis_id);
+    const int cap = 12 * sm_count();        // idle CTAs (sets >= set_num) cost a launch slot each: do not start thousands
+    const int grid = p->max_set_num < cap ? p->max_set_num : cap;
+    attn_core_kernel<S><<<dim3(grid, p->batch), S / 2 * kH, smem, st>>>(qkv, idx, mask, set_num, o, p->max_set_num,
+                                                                       p->max_pillars_num, p->axis_id);
     DSVT_LAUNCH_CHECK();
     return DSVT_OK;
 }
@@ -512,6 +588,17 @@ void* attention_split_prepare(const float* w_in, const float* b_in, const float*
     return dev;
 }
 
+// Optional per-kernel timing of the pipeline (bench.py's roofline block): when enabled, CUDA events are recorded on the
+// launch stream between the three kernels.  Not for use under stream capture.
+static bool g_stage_timing = false;
+static cudaEvent_t g_stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+static int stage_mark(int i, cudaStream_t st) {
+    if (!g_stage_timing) return DSVT_OK;
+    if (!g_stage_ev[i]) DSVT_CUDA(cudaEventCreate(&g_stage_ev[i]));
+    DSVT_CUDA(cudaEventRecord(g_stage_ev[i], st));
+    return DSVT_OK;
+}
+
 size_t attention_split_workspace(const dsvt_set_attention_params* p) {
     // qkv [B, max_pillars, 576] f32 | o [B, max_pillars, 192] f32
     return align_up((size_t) p->batch * p->max_pillars_num * 3 * kC * sizeof(float), kWsAlign) +
@@ -530,6 +617,10 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
     }
     if (!split_blob) {
         set_last_error("set attention (GEMM pipeline): weights were not prepared");
+        return DSVT_ERR_INVALID_ARGUMENT;
+    }
+    if (((uintptr_t) x | (uintptr_t) pos | (uintptr_t) workspace) & 31) {
+        set_last_error("set attention (GEMM pipeline): x, pos and workspace must be 32-byte aligned (256-bit loads)");
         return DSVT_ERR_INVALID_ARGUMENT;
     }
     if (!workspace || workspace_bytes < attention_split_workspace(p)) {
@@ -575,6 +666,8 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
         g.post_mul = 1.0f;
         out_roles.r[1] = out_roles.r[2] = g;
     }
+    int rc = stage_mark(0, st);
+    if (rc != DSVT_OK) return rc;
     if (split) {
         proj_gemm_kernel<true><<<dim3(grid_in, p->batch), kThreadsG, Lay<true>::total, st>>>(
             in_roles, 3, voxel_num, p->max_pillars_num, 0);
@@ -583,13 +676,14 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
             in_roles, 3, voxel_num, p->max_pillars_num, 0);
     }
     DSVT_LAUNCH_CHECK();
-    int rc;
+    if ((rc = stage_mark(1, st)) != DSVT_OK) return rc;
     switch (p->voxel_num_set) {
         case 24: rc = launch_core<24>(p, qkv, idx, mask, set_num, o, st); break;
         case 36: rc = launch_core<36>(p, qkv, idx, mask, set_num, o, st); break;
         default: rc = launch_core<48>(p, qkv, idx, mask, set_num, o, st); break;
     }
     if (rc != DSVT_OK) return rc;
+    if ((rc = stage_mark(2, st)) != DSVT_OK) return rc;
     if (split) {
         proj_gemm_kernel<true><<<dim3(grid_out, p->batch), kThreadsG, Lay<true>::total, st>>>(
             out_roles, 1, voxel_num, p->max_pillars_num, p->zero_tails);
@@ -598,11 +692,22 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
             out_roles, 1, voxel_num, p->max_pillars_num, p->zero_tails);
     }
     DSVT_LAUNCH_CHECK();
-    return DSVT_OK;
+    return stage_mark(3, st);
 }
 
 }  // namespace dsvt
 
+extern "C" void dsvt_debug_attention_stage_timing(int enable) { dsvt::g_stage_timing = enable != 0; }
+// microseconds of {QKV projection GEMM, per-set core, out-projection GEMM} of the last timed call (after a stream sync)
+extern "C" int dsvt_debug_attention_stage_us(float* out3) {
+    for (int i = 0; i < 3; ++i) {
+        float ms = 0.f;
+        if (!dsvt::g_stage_ev[i] || !dsvt::g_stage_ev[i + 1] ||
+            cudaEventElapsedTime(&ms, dsvt::g_stage_ev[i], dsvt::g_stage_ev[i + 1]) != cudaSuccess) return 1;
+        out3[i] = ms * 1000.f;
+    }
+    return 0;
+}
 extern "C" int dsvt_debug_split_profile(long long* out64) {
     return cudaMemcpyFromSymbol(out64, dsvt::g_split_prof, sizeof(long long) * 64) == cudaSuccess ? 0 : 1;
 }

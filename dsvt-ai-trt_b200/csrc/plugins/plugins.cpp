@@ -722,6 +722,119 @@ private:
     int nb_inputs_seen_ = 4;
 };
 
+// SetAttentionFusedPlugin -- one node for GetValueByIndexPlugin -> multHeadAttention() -> MapSetFeature2VoxelPlugin
+// (src/dsvt-ai-trt.cpp:653-668 and the 7 sibling call sites).  This is the form every tensor-core
+// precision is built for.
+// Inputs : x [B,max_pillars,C] f32, pos [B,max_pillars,C] f32, global_index_in_set [B,2,max_sets,S] i32,
+//          mask [B,max_sets,heads,S] f32, set_num [B] i32, voxel_num [B] i32.   Output: [B,max_pillars,C] f32.
+// Fields : SetAttentionPlugin's + max_pillars_num, axis_id.  Serialised: 7 x i32 then the four weight arrays.
+class SetAttentionFusedPlugin final : public PluginBase {
+public:
+    static constexpr const char* kName = "SetAttentionFusedPlugin";
+    static FieldList field_list() {
+        return {{"max_win_num", PluginFieldType::kINT32}, {"voxel_num_set", PluginFieldType::kINT32},
+                {"channel_num", PluginFieldType::kINT32}, {"num_heads", PluginFieldType::kINT32},
+                {"precision", PluginFieldType::kINT32}, {"max_pillars_num", PluginFieldType::kINT32},
+                {"axis_id", PluginFieldType::kINT32},
+                {"in_proj_weight", PluginFieldType::kFLOAT32}, {"in_proj_bias", PluginFieldType::kFLOAT32},
+                {"out_proj_weight", PluginFieldType::kFLOAT32}, {"out_proj_bias", PluginFieldType::kFLOAT32}};
+    }
+    SetAttentionFusedPlugin(int max_sets, int S, int C, int heads, int precision, int max_pillars, int axis,
+                            const float* w_in, const float* b_in, const float* w_out, const float* b_out)
+        : max_sets_(max_sets), S_(S), C_(C), heads_(heads), precision_(precision), max_pillars_(max_pillars), axis_(axis),
+          w_in_(w_in, w_in + (size_t) 3 * C * C), b_in_(b_in, b_in + 3 * C),
+          w_out_(w_out, w_out + (size_t) C * C), b_out_(b_out, b_out + C) {}
+    ~SetAttentionFusedPlugin() override { release(); }
+    static IPluginV2* from_fields(const PluginFieldCollection* fc) {
+        const PluginField* wi = find_field(fc, "in_proj_weight");
+        const PluginField* bi = find_field(fc, "in_proj_bias");
+        const PluginField* wo = find_field(fc, "out_proj_weight");
+        const PluginField* bo = find_field(fc, "out_proj_bias");
+        const int C = field_int(fc, "channel_num");
+        if (C <= 0 || !wi || !bi || !wo || !bo || !wi->data || !bi->data || !wo->data || !bo->data) return nullptr;
+        return new (std::nothrow) SetAttentionFusedPlugin(
+            field_int(fc, "max_win_num"), field_int(fc, "voxel_num_set"), C, field_int(fc, "num_heads", 0, 8),
+            field_int(fc, "precision", 0, DSVT_ATTN_FP32_TC), field_int(fc, "max_pillars_num"), field_int(fc, "axis_id"),
+            static_cast<const float*>(wi->data), static_cast<const float*>(bi->data),
+            static_cast<const float*>(wo->data), static_cast<const float*>(bo->data));
+    }
+    static IPluginV2* from_bytes(const void* data, size_t len) {
+        Reader r(data, len);
+        const int ms = r.get<int>(), S = r.get<int>(), C = r.get<int>(), H = r.get<int>(), prec = r.get<int>();
+        const int mp = r.get<int>(), axis = r.get<int>();
+        if (!r.ok() || C <= 0 || C > 4096 || r.left() < ((size_t) 4 * C * C + 4 * C) * sizeof(float)) return nullptr;
+        std::vector<float> wi((size_t) 3 * C * C), bi(3 * C), wo((size_t) C * C), bo(C);
+        r.get_array(wi.data(), wi.size()); r.get_array(bi.data(), bi.size());
+        r.get_array(wo.data(), wo.size()); r.get_array(bo.data(), bo.size());
+        return new (std::nothrow) SetAttentionFusedPlugin(ms, S, C, H, prec, mp, axis, wi.data(), bi.data(), wo.data(), bo.data());
+    }
+    size_t getSerializationSize() const noexcept override {
+        return 7 * sizeof(int) + ((size_t) 4 * C_ * C_ + 4 * C_) * sizeof(float);
+    }
+    void serialize(void* buf) const noexcept override {
+        Writer w(buf);
+        w.put(max_sets_); w.put(S_); w.put(C_); w.put(heads_); w.put(precision_); w.put(max_pillars_); w.put(axis_);
+        w.put_array(w_in_.data(), w_in_.size()); w.put_array(b_in_.data(), b_in_.size());
+        w.put_array(w_out_.data(), w_out_.size()); w.put_array(b_out_.data(), b_out_.size());
+    }
+    IPluginV2DynamicExt* clone() const noexcept override {
+        auto* c = new (std::nothrow) SetAttentionFusedPlugin(max_sets_, S_, C_, heads_, precision_, max_pillars_, axis_,
+                                                             w_in_.data(), b_in_.data(), w_out_.data(), b_out_.data());
+        if (c) c->setPluginNamespace(ns_.c_str());
+        return c;
+    }
+    int32_t initialize() noexcept override { return upload(); }
+    void terminate() noexcept override { release(); }
+    const char* getPluginType() const noexcept override { return kName; }
+    int32_t getNbOutputs() const noexcept override { return 1; }
+    DimsExprs getOutputDimensions(int32_t, const DimsExprs* in, int32_t, IExprBuilder& b) noexcept override {
+        return dims(b, in[0].d[0], {max_pillars_, C_});
+    }
+    bool supportsFormatCombination(int32_t pos, const PluginTensorDesc* io, int32_t nbIn, int32_t nbOut) noexcept override {
+        if (pos < 0 || pos >= nbIn + nbOut || io[pos].format != TensorFormat::kLINEAR) return false;
+        return io[pos].type == ((pos == 2 || pos == 4 || pos == 5) ? I : F);
+    }
+    DataType getOutputDataType(int32_t, const DataType*, int32_t) const noexcept override { return F; }
+    size_t getWorkspaceSize(const PluginTensorDesc* in, int32_t, const PluginTensorDesc*, int32_t) const noexcept override {
+        const dsvt_set_attention_params p = params(batch_of(in));
+        return dsvt_set_attention_workspace_size(&p);
+    }
+    int32_t enqueue(const PluginTensorDesc* in, const PluginTensorDesc*, const void* const* inputs,
+                    void* const* outputs, void* ws, cudaStream_t stream) noexcept override {
+        if (upload() != 0) return DSVT_ERR_CUDA;
+        const dsvt_set_attention_params p = params(batch_of(in));
+        return report(dsvt_set_attention_fused_launch(
+                          &p, dev_, static_cast<const float*>(inputs[0]), static_cast<const float*>(inputs[1]),
+                          static_cast<const int32_t*>(inputs[2]), static_cast<const float*>(inputs[3]),
+                          static_cast<const int32_t*>(inputs[4]), static_cast<const int32_t*>(inputs[5]),
+                          static_cast<float*>(outputs[0]), ws, dsvt_set_attention_workspace_size(&p), stream), kName);
+    }
+protected:
+    const std::vector<DataType>& io_types() const override {
+        static const std::vector<DataType> t{F, F, I, F, I, I, F};
+        return t;
+    }
+    size_t nb_inputs() const override { return 6; }
+private:
+    dsvt_set_attention_params params(int batch) const {
+        dsvt_set_attention_params p{};
+        p.batch = batch; p.max_set_num = max_sets_; p.voxel_num_set = S_; p.channel_num = C_; p.num_heads = heads_;
+        p.max_pillars_num = max_pillars_; p.axis_id = axis_; p.precision = precision_; p.zero_tails = 1;
+        return p;
+    }
+    int upload() {
+        if (dev_) return 0;
+        dev_ = dsvt_attention_weights_create(C_, heads_, w_in_.data(), b_in_.data(), w_out_.data(), b_out_.data());
+        return dev_ ? 0 : 1;
+    }
+    void release() {
+        if (dev_) { dsvt_attention_weights_destroy(dev_); dev_ = nullptr; }
+    }
+    int max_sets_, S_, C_, heads_, precision_, max_pillars_, axis_;
+    std::vector<float> w_in_, b_in_, w_out_, b_out_;
+    dsvt_attention_weights* dev_ = nullptr;
+};
+
 // registration: from the library only (the reference registers from two images)
 using Points2FeaturesPluginCreator = CreatorBase<Points2FeaturesPlugin>;
 using WindowPartitionPluginCreator = CreatorBase<WindowPartitionPlugin>;
@@ -732,6 +845,7 @@ using FilterBoxByScorePluginCreator = CreatorBase<FilterBoxByScorePlugin>;
 using GetValueByIndexPluginCreator = CreatorBase<GetValueByIndexPlugin>;
 using MapSetFeature2VoxelPluginCreator = CreatorBase<MapSetFeature2VoxelPlugin>;
 using SetAttentionPluginCreator = CreatorBase<SetAttentionPlugin>;
+using SetAttentionFusedPluginCreator = CreatorBase<SetAttentionFusedPlugin>;
 
 REGISTER_TENSORRT_PLUGIN(Points2FeaturesPluginCreator);
 REGISTER_TENSORRT_PLUGIN(WindowPartitionPluginCreator);
@@ -742,5 +856,6 @@ REGISTER_TENSORRT_PLUGIN(FilterBoxByScorePluginCreator);
 REGISTER_TENSORRT_PLUGIN(GetValueByIndexPluginCreator);
 REGISTER_TENSORRT_PLUGIN(MapSetFeature2VoxelPluginCreator);
 REGISTER_TENSORRT_PLUGIN(SetAttentionPluginCreator);
+REGISTER_TENSORRT_PLUGIN(SetAttentionFusedPluginCreator);
 
 }  // namespace dsvt_plugins

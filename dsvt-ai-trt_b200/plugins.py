@@ -255,3 +255,15 @@ def add_set_attention_op(lib, max_win_num, voxel_num_set, channel_num, num_heads
         "in_proj_weight": np.asarray(in_proj_weight, np.float32), "in_proj_bias": np.asarray(in_proj_bias, np.float32),
         "out_proj_weight": np.asarray(out_proj_weight, np.float32),
         "out_proj_bias": np.asarray(out_proj_bias, np.float32)})
+
+
+def add_set_attention_fused_op(lib, max_win_num, voxel_num_set, channel_num, num_heads, max_pillars_num, axis_id,
+                               in_proj_weight, in_proj_bias, out_proj_weight, out_proj_bias, precision=3):
+    """One node for GetValueByIndexPlugin -> multHeadAttention() -> MapSetFeature2VoxelPlugin
+    (src/dsvt-ai-trt.cpp:653-668).  precision: DSVT_ATTN_* (3 = FP32-accurate tcgen05 GEMM pipeline)."""
+    return lib.create("SetAttentionFusedPlugin", {
+        "max_win_num": max_win_num, "voxel_num_set": voxel_num_set, "channel_num": channel_num,
+        "num_heads": num_heads, "precision": precision, "max_pillars_num": max_pillars_num, "axis_id": axis_id,
+        "in_proj_weight": np.asarray(in_proj_weight, np.float32), "in_proj_bias": np.asarray(in_proj_bias, np.float32),
+        "out_proj_weight": np.asarray(out_proj_weight, np.float32),
+        "out_proj_bias": np.asarray(out_proj_bias, np.float32)})

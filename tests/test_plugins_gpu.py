@@ -155,7 +155,48 @@ def test_set_attention_plugin(lib, plg, attention_case):
     assert np.abs(got[:2] - c["out"][:2]).max() <= 2e-5 and np.all(got[2:] == 0)
 
 
+@pytest.mark.parametrize("precision", [0, 2, 3, 4])
+def test_set_attention_fused_plugin(lib, plg, precision):
+    """SetAttentionFusedPlugin (gather + MHA + scatter in one node) through the plugin interface: creator fields,
+    serialise / deserialise round trip, getWorkspaceSize, enqueue -- against the CPU oracle chain."""
+    rng = np.random.default_rng(5)
+    n_sets, max_sets, S, C, H = 40, 48, 36, 192, 8
+    sizes = rng.integers(1, S + 1, n_sets)
+    V = int(sizes.sum())
+    max_pillars = V + 21
+    x = np.zeros((max_pillars, C), np.float32); pos = np.zeros_like(x)
+    x[:V] = rng.standard_normal((V, C)); pos[:V] = rng.standard_normal((V, C)) * 0.5
+    idx = np.zeros((2, max_sets, S), np.int32)
+    mask = np.zeros((max_sets, H, S), np.float32)
+    perm, start = rng.permutation(V), 0
+    for s in range(n_sets):
+        n = int(sizes[s])
+        members = np.sort(perm[start:start + n]); start += n
+        r = (np.arange(S) * n) // S
+        idx[0, s] = members[r]; idx[1, s] = members[::-1][r]
+        mask[s, :, 1:][:, r[1:] == r[:-1]] = -np.finfo(np.float32).max
+    w_in = (rng.standard_normal((3 * C, C)) * 0.06).astype(np.float32); b_in = (rng.standard_normal(3 * C) * 0.1).astype(np.float32)
+    w_out = (rng.standard_normal((C, C)) * 0.06).astype(np.float32); b_out = (rng.standard_normal(C) * 0.1).astype(np.float32)
+    tol = {0: 2e-5, 3: 2e-5}.get(precision, 1e-2)
+    for axis in (0, 1):
+        p = plg.add_set_attention_fused_op(lib, max_sets, S, C, H, max_pillars, axis, w_in, b_in, w_out, b_out,
+                                           precision=precision)
+        p2, blob = roundtrip(lib, p)
+        assert blob[:28] == struct.pack("<7i", max_sets, S, C, H, precision, max_pillars, axis)
+        assert len(blob) == 7 * 4 + (4 * C * C + 4 * C) * 4
+        q, k, v = cpu.get_value_by_index(x, pos, idx, n_sets, axis)
+        a = cpu.set_attention(q, k, v, mask, n_sets, w_in, b_in, w_out, b_out)
+        ref = cpu.map_set_feature2voxel(a, idx, n_sets, axis, max_pillars)
+        for plugin in (p, p2):
+            (out,) = plugin.enqueue([dev(x)[None], dev(pos)[None], dev(idx)[None], dev(mask)[None], i32(n_sets), i32(V)],
+                                    poison=float("nan"))
+            got = out[0].cpu().numpy()
+            assert np.all(got[V:] == 0)
+            assert np.abs(got[:V] - ref[:V]).max() <= tol
+
+
 def test_registry_and_formats(lib):
     names = set(lib.registered())
     assert {"Points2FeaturesPlugin", "GetSetPlugin", "GeluPlugin", "LayerNormPlugin", "FilterBoxByScorePlugin",
-            "WindowPartitionPlugin", "GetValueByIndexPlugin", "MapSetFeature2VoxelPlugin", "SetAttentionPlugin"} <= names
+            "WindowPartitionPlugin", "GetValueByIndexPlugin", "MapSetFeature2VoxelPlugin", "SetAttentionPlugin",
+            "SetAttentionFusedPlugin"} <= names

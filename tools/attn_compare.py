@@ -6,7 +6,8 @@ import numpy as np, torch
 pkg = importlib.import_module("dsvt-ai-trt_b200"); capi = importlib.import_module("dsvt-ai-trt_b200.capi")
 pipeline = importlib.import_module("dsvt-ai-trt_b200.pipeline")
 cfg = pkg.config.WAYMO
-points = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
+points = 200000
+noflush = "--noflush" in sys.argv
 w = pipeline.FrameWeights(cfg)
 f = pipeline.HotPathFrame(cfg, w)
 f.load_points(pkg.synth.ring_lidar(points, 0))
@@ -26,7 +27,7 @@ for which in (0, 1):
         for _ in range(3): call()
         ts = []
         for _ in range(20):
-            flush.zero_()
+            if not noflush: flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); call(); e1.record(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e3)
