@@ -7,9 +7,13 @@
 //   scan     : two-kernel (reduce, then scan) exclusive scan over the cell grid -> canonical
 //              pillar ids (ascending y*gx+x), list bases and output-row bases.  No spin-waits.
 //   scatter  : counting-sort step: each in-range point claims a slot in its cell's segment.
-//   emit     : one warp per pillar sorts its (tiny) segment by input index, keeps the lowest
-//              `npv`, computes the sequential-order f32 mean exactly like the reference and
-//              writes rows with coalesced stores.  Tail rows are zeroed by the same grid.
+//   rank     : one THREAD per point: its slot is the number of smaller input indices in its pillar's segment
+//              (segments are ~10 points, the scan stops once `npv` smaller ones are seen); the lowest `npv` get an
+//              output row.  Pillars with more than 64 points go through a warp-per-pillar radix-select instead.
+//   mean     : one thread per pillar: sequential-order f32 sum of the kept points, exactly like the reference.
+//   feat     : one thread per output row: the 10-channel decoration, written through shared memory as full lines.
+//   (The first version ran one WARP per pillar for all of this: ~1160 warp instructions per pillar at 31 % lane
+//    utilisation made the voxeliser issue-bound at 6 % of the HBM roofline on batched frames.)
 // Results are deterministic: the reference's three atomicAdd races (:697, :751, :829) are
 // replaced by their canonical serial-order outcome.
 #include "common.cuh"
@@ -21,6 +25,7 @@ constexpr int kThreads = 256;
 constexpr int kCellsPerThread = 4;
 constexpr int kCellsPerBlock = kThreads * kCellsPerThread;  // 1024
 constexpr int kMaxNpv = 64;
+constexpr int kBigN = kMaxNpv;   // pillars with more points are ranked by vox_rank_big_kernel (radix select)
 
 struct VoxGeom {
     float x_min, x_max, y_min, y_max, z_min, z_max;
@@ -82,10 +87,10 @@ vox_block_reduce_kernel(const unsigned int* __restrict__ cell_count, int* __rest
         const uint4 v = *reinterpret_cast<const uint4*>(cc + c0);
         const unsigned int a[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { ne += a[j] > 0; sa += a[j]; sk += min((int) a[j], npv); }
+        for (int j = 0; j < 4; ++j) { ne += a[j] > 0; sa += (a[j] + 3u) & ~3u; sk += min((int) a[j], npv); }
     } else {
         for (int j = 0; j < kCellsPerThread; ++j) {
-            if (c0 + j < G) { unsigned int a = cc[c0 + j]; ne += a > 0; sa += a; sk += min((int) a, npv); }
+            if (c0 + j < G) { unsigned int a = cc[c0 + j]; ne += a > 0; sa += (a + 3u) & ~3u; sk += min((int) a, npv); }
         }
     }
 #pragma unroll
@@ -107,11 +112,11 @@ vox_block_reduce_kernel(const unsigned int* __restrict__ cell_count, int* __rest
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 vox_scan_kernel(const unsigned int* __restrict__ cell_count, const int* __restrict__ block_sums,
-                unsigned int* __restrict__ cursor, int* __restrict__ pillar_base, int* __restrict__ pillar_n,
-                int* __restrict__ pillar_row,
+                unsigned int* __restrict__ cursor, int* __restrict__ pillar_base /* int4 records */,
                 int* __restrict__ coords, int* __restrict__ point_num_in_voxel,
                 int* __restrict__ pillar_num, int* __restrict__ point_num,
-                size_t ws_stride, int G, int gx, int npv, int max_pillars, int max_rows)
+                int* __restrict__ cell_pid, int* __restrict__ big_list, unsigned int* __restrict__ big_count_base,
+                int* __restrict__ list, size_t ws_stride, int G, int gx, int npv, int max_pillars, int max_rows)
 {
     __shared__ int warp_sums[33];
     __shared__ int prefix[3];
@@ -141,7 +146,7 @@ vox_scan_kernel(const unsigned int* __restrict__ cell_count, const int* __restri
     for (int j = 0; j < kCellsPerThread; ++j) a[j] = (c0 + j < G) ? cc[c0 + j] : 0u;
     int ne = 0, sa = 0, sk = 0;
 #pragma unroll
-    for (int j = 0; j < kCellsPerThread; ++j) { ne += a[j] > 0; sa += a[j]; sk += min((int) a[j], npv); }
+    for (int j = 0; j < kCellsPerThread; ++j) { ne += a[j] > 0; sa += (a[j] + 3u) & ~3u; sk += min((int) a[j], npv); }
     int tot0, tot1, tot2;
     int e0 = block_excl_scan(ne, warp_sums, &tot0) + prefix[0];
     int e1 = block_excl_scan(sa, warp_sums, &tot1) + prefix[1];
@@ -155,12 +160,14 @@ vox_scan_kernel(const unsigned int* __restrict__ cell_count, const int* __restri
         if (cell < G && a[j] > 0) {
             const int pid = e0;
             cursor[(size_t) b * ws_stride + cell] = (unsigned int) e1;
+            cell_pid[(size_t) b * ws_stride + cell] = pid < max_pillars ? pid : -1;
+            if (pid < max_pillars && (int) a[j] > kBigN)        // ranked by a warp (vox_rank_big_kernel)
+                big_list[(size_t) b * ws_stride + atomicAdd(big_count_base + (size_t) b * ws_stride + G, 1u)] = pid;
             if (pid < max_pillars) {
                 int keep = min((int) a[j], npv);
                 keep = max(0, min(keep, max_rows - e2));  // row-capacity guard (reference has none, SURVEY A-5)
-                pillar_base[(size_t) b * ws_stride + pid] = e1;
-                pillar_n[(size_t) b * ws_stride + pid] = (int) a[j];
-                pillar_row[(size_t) b * ws_stride + pid] = e2;
+                // one 16-byte record per pillar: list base, point count, first output row, rows kept
+                reinterpret_cast<int4*>(pillar_base)[((size_t) b * ws_stride >> 2) + pid] = make_int4(e1, (int) a[j], e2, keep);
                 const int y = cell / gx, x = cell - y * gx;
                 *reinterpret_cast<int4*>(coords_b + (size_t) pid * 4) = make_int4(0, 0, y, x);  // :755
                 pnv_b[pid] = keep;
@@ -169,7 +176,10 @@ vox_scan_kernel(const unsigned int* __restrict__ cell_count, const int* __restri
                 // the emitted rows are exactly [0, e2)
                 point_num[b] = min(e2, max_rows);
             }
-            e0 += 1; e1 += (int) a[j]; e2 += min((int) a[j], npv);
+            // list segments start on 16-byte boundaries (vox_rank_kernel reads them as int4); the <= 3 pad entries
+            // compare greater than every input index
+            for (int q = (int) a[j]; q < (((int) a[j] + 3) & ~3); ++q) list[(size_t) b * ws_stride + e1 + q] = 0x7fffffff;
+            e0 += 1; e1 += ((int) a[j] + 3) & ~3; e2 += min((int) a[j], npv);
         }
     }
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
@@ -179,9 +189,10 @@ vox_scan_kernel(const unsigned int* __restrict__ cell_count, const int* __restri
 }
 
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
-vox_scatter_kernel(const int* __restrict__ points_size, int max_points, const int* __restrict__ pcell,
-                   unsigned int* __restrict__ cursor, int* __restrict__ list, size_t ws_stride)
+__device__ __forceinline__ void
+vox_scatter_body(const int* __restrict__ points_size, int max_points, int* __restrict__ pcell,
+                 const int* __restrict__ cell_pid, unsigned int* __restrict__ cursor, int* __restrict__ list,
+                 size_t ws_stride)
 {
     const int b = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -192,50 +203,56 @@ vox_scatter_kernel(const int* __restrict__ points_size, int max_points, const in
     if (cell < 0) return;
     const unsigned int pos = atomicAdd(cursor + (size_t) b * ws_stride + cell, 1u);
     list[(size_t) b * ws_stride + pos] = i;
+    pcell[(size_t) b * ws_stride + i] = cell_pid[(size_t) b * ws_stride + cell];     // cell -> pillar id (-1: beyond capacity)
 }
 
 // ---------------------------------------------------------------------------
-// One warp per pillar slot (valid pillars emit, the rest zero-fill their rows).
+// One thread per input point: slot = number of smaller input indices among the pillar's points.
+__device__ __forceinline__ void
+vox_rank_body(const int* __restrict__ points_size, int max_points, const int* __restrict__ ppid,
+              const int* __restrict__ list, const int4* __restrict__ pinfo, int2* __restrict__ row_info,
+              size_t ws_stride)
+{
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n_pts = points_size[b];
+    n_pts = n_pts < max_points ? n_pts : max_points;
+    if (i >= n_pts) return;
+    const size_t wb = (size_t) b * ws_stride;
+    const int pid = ppid[wb + i];                         // written by vox_scatter_kernel; < 0: dropped point
+    if (pid < 0) return;
+    const int4 pi = __ldg(pinfo + (wb >> 2) + pid);       // list base, n, first row, keep = min(n, npv) after the capacity guard
+    const int n = pi.y, keep = pi.w;
+    if (n > kBigN) return;                                // ranked by vox_rank_big_kernel
+    const int4* lst = reinterpret_cast<const int4*>(list + wb + pi.x);    // padded to a multiple of 4
+    int rank = 0;
+    for (int j = 0; j < n && rank < keep; j += 4) {       // a point with `keep` smaller indices before it is dropped
+        const int4 v = __ldg(lst + (j >> 2));
+        rank += (v.x < i) + (v.y < i) + (v.z < i) + (v.w < i);
+    }
+    if (rank < keep) row_info[(wb >> 1) + pi.z + rank] = make_int2(i, pid);
+}
+
+// One warp per pillar with more than kBigN points (tens to hundreds per frame; thousands of points each near the
+// sensor): radix-select the `npv` lowest input indices (8-bit digits, per-warp shared-memory histogram), rank-sort them.
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
-vox_emit_kernel(const float4* __restrict__ points, int max_points, VoxGeom g,
-                const int* __restrict__ list, const int* __restrict__ pillar_base,
-                const int* __restrict__ pillar_n, const int* __restrict__ pillar_row,
-                const int* __restrict__ pillar_num, const int* __restrict__ point_num,
-                const int* point_num_in_voxel,  // aliases point_num_in_voxel_out (disjoint rows)
-                float* __restrict__ point_features, int* __restrict__ point_index_in_voxel,
-                int* __restrict__ coords, int* point_num_in_voxel_out,
-                size_t ws_stride, int npv, int max_pillars, int max_rows, int zero_tails)
+__device__ __forceinline__ void
+vox_rank_big_body(int cta, int n_ctas, int max_points, const int* __restrict__ list, const int4* __restrict__ pinfo,
+                  const int* __restrict__ big_list, const unsigned int* __restrict__ big_count_base,
+                  int2* __restrict__ row_info, size_t ws_stride, int G, int npv)
 {
     __shared__ int s_idx[WARPS][kMaxNpv];
-    __shared__ float s_pts[WARPS][kMaxNpv][4];
-    __shared__ float s_feat[WARPS][kMaxNpv * 10];
     __shared__ int s_hist[WARPS][256];
-
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int pid = blockIdx.x * WARPS + w;
-    const int V = pillar_num[b];
-    const int Pc = point_num[b];
-    float* feat_b = point_features + (size_t) b * max_rows * 10;
-    int* piv_b = point_index_in_voxel + (size_t) b * max_pillars * npv;
-
-    if (pid >= V) return;          // tails are zero-filled by vox_zero_tails_kernel
-    const int base = pillar_base[(size_t) b * ws_stride + pid];
-    const int n = pillar_n[(size_t) b * ws_stride + pid];
-    const int row0 = pillar_row[(size_t) b * ws_stride + pid];
-    const int keep = point_num_in_voxel[(size_t) b * max_pillars + pid];  // min(n, npv) after capacity guard
-    const int* lst = list + (size_t) b * ws_stride + base;
-    const int kk = min(n, npv);  // how many lowest indices we need sorted
-
-    int e0, e1, m;  // up to 64 candidate indices in registers, m = how many
-    if (n <= 64) {
-        m = n;
-        e0 = lane < n ? lst[lane] : 0x7fffffff;
-        e1 = lane + 32 < n ? lst[lane + 32] : 0x7fffffff;
-    } else {
-        // radix-select (8-bit digits, per-warp shared-memory histogram) the kk-th smallest input index T,
-        // then gather the kk elements <= T
+    const size_t wb = (size_t) b * ws_stride;
+    const int n_big = (int) big_count_base[wb + G];
+    for (int bi = cta * WARPS + w; bi < n_big; bi += n_ctas * WARPS) {
+        const int pid = big_list[wb + bi];
+        const int4 pi = pinfo[(wb >> 2) + pid];
+        const int n = pi.y, row0 = pi.z, keep = pi.w;
+        const int* lst = list + wb + pi.x;
+        const int kk = min(n, npv);
         int prefix_v = 0, k = kk;
         const int nbits = 32 - __clz(max_points | 1);
         for (int shift = ((nbits - 1) / 8) * 8; shift >= 0; shift -= 8) {
@@ -252,8 +269,7 @@ vox_emit_kernel(const float4* __restrict__ points, int max_points, VoxGeom g,
             for (int i = 0; i < 8; ++i) { c[i] = s_hist[w][lane * 8 + i]; lsum += c[i]; }
             const int incl = warp_incl_scan(lsum, lane);
             const int excl = incl - lsum;
-            // the lane whose bin range contains the k-th element
-            const unsigned hit = __ballot_sync(0xffffffffu, incl >= k);
+            const unsigned hit = __ballot_sync(0xffffffffu, incl >= k);     // the lane whose bins contain the k-th element
             const int src = __ffs(hit) - 1;
             int digit = 0, below = 0;
             if (lane == src) {
@@ -270,7 +286,7 @@ vox_emit_kernel(const float4* __restrict__ points, int max_points, VoxGeom g,
             prefix_v |= digit << shift;
             __syncwarp();
         }
-        const int T = prefix_v;
+        const int T = prefix_v;                               // the kk-th smallest input index (indices are unique)
         int filled = 0;
         for (int t0 = 0; t0 < n; t0 += 32) {
             const int t = t0 + lane;
@@ -281,41 +297,69 @@ vox_emit_kernel(const float4* __restrict__ points, int max_points, VoxGeom g,
             filled += __popc(bal);
         }
         __syncwarp();
-        m = kk;
-        e0 = lane < m ? s_idx[w][lane] : 0x7fffffff;
-        e1 = lane + 32 < m ? s_idx[w][lane + 32] : 0x7fffffff;
+        const int e0 = lane < kk ? s_idx[w][lane] : 0x7fffffff;
+        const int e1 = lane + 32 < kk ? s_idx[w][lane + 32] : 0x7fffffff;
+        int r0 = 0, r1 = 0;                                   // rank-sort kk (<= 64) unique indices
+        for (int j = 0; j < kk; ++j) {
+            const int v = j < 32 ? __shfl_sync(0xffffffffu, e0, j) : __shfl_sync(0xffffffffu, e1, j - 32);
+            r0 += v < e0;
+            r1 += v < e1;
+        }
+        if (lane < kk && r0 < keep) row_info[(wb >> 1) + row0 + r0] = make_int2(e0, pid);
+        if (lane + 32 < kk && r1 < keep) row_info[(wb >> 1) + row0 + r1] = make_int2(e1, pid);
         __syncwarp();
     }
-    // rank-sort m (<= 64) unique indices
-    int r0 = 0, r1 = 0;
-    for (int j = 0; j < m; ++j) {
-        const int v = j < 32 ? __shfl_sync(0xffffffffu, e0, j) : __shfl_sync(0xffffffffu, e1, j - 32);
-        r0 += v < e0;
-        r1 += v < e1;
-    }
-    if (lane < m && r0 < kMaxNpv) s_idx[w][r0] = e0;
-    if (lane + 32 < m && r1 < kMaxNpv) s_idx[w][r1] = e1;
-    __syncwarp();
+}
 
-    // load the kept points in slot order
-    for (int s = lane; s < keep; s += 32) {
-        const float4 p = points[(size_t) b * max_points + s_idx[w][s]];
-        s_pts[w][s][0] = p.x; s_pts[w][s][1] = p.y; s_pts[w][s][2] = p.z; s_pts[w][s][3] = p.w;
+// One thread per pillar: sequential-order f32 sums of the kept points (points2Features.cu:809-824).
+__global__ void __launch_bounds__(kThreads)
+vox_mean_kernel(const float4* __restrict__ points, int max_points, const int* __restrict__ pillar_num,
+                const int4* __restrict__ pinfo, const int2* __restrict__ row_info, float4* __restrict__ mean,
+                size_t ws_stride)
+{
+    const int b = blockIdx.y;
+    const int pid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pid >= pillar_num[b]) return;
+    const size_t wb = (size_t) b * ws_stride;
+    const int4 pi = __ldg(pinfo + (wb >> 2) + pid);
+    const int keep = pi.w;
+    const int2* src = row_info + (wb >> 1) + pi.z;
+    const float4* pts = points + (size_t) b * max_points;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    constexpr int kChunk = 4;                                 // loads of 4 slots in flight, sums strictly in slot order
+    for (int s0 = 0; s0 < keep; s0 += kChunk) {
+        float4 pbuf[kChunk];
+#pragma unroll
+        for (int u = 0; u < kChunk; ++u)                      // clamped, not predicated: a repeat of the last slot is harmless
+            pbuf[u] = __ldg(pts + __ldg(&src[min(s0 + u, keep - 1)].x));
+#pragma unroll
+        for (int u = 0; u < kChunk; ++u)
+            if (s0 + u < keep) { ax += pbuf[u].x; ay += pbuf[u].y; az += pbuf[u].z; }
     }
-    __syncwarp();
-    // sequential-order f32 sums, one lane per axis (points2Features.cu:809-824)
-    float mean = 0.f;
-    if (lane < 3) {
-        float acc = 0.f;
-        for (int s = 0; s < keep; ++s) acc += s_pts[w][s][lane];
-        mean = acc / keep;
-    }
-    const float mx = __shfl_sync(0xffffffffu, mean, 0);
-    const float my = __shfl_sync(0xffffffffu, mean, 1);
-    const float mz = __shfl_sync(0xffffffffu, mean, 2);
+    mean[(wb >> 2) + pid] = make_float4(ax / keep, ay / keep, az / keep, 0.f);
+}
 
-    for (int s = lane; s < keep; s += 32) {
-        const float x = s_pts[w][s][0], y = s_pts[w][s][1], z = s_pts[w][s][2], it = s_pts[w][s][3];
+// One thread per output row: the 10-channel decoration; a CTA's 256 rows leave through shared memory as 10 KB of
+// contiguous, 16-byte vectorised stores.
+__global__ void __launch_bounds__(kThreads)
+vox_feat_kernel(const float4* __restrict__ points, int max_points, VoxGeom g, const int* __restrict__ point_num,
+                const int4* __restrict__ pinfo, const int2* __restrict__ row_info,
+                const float4* __restrict__ mean, float* __restrict__ point_features,
+                int* __restrict__ point_index_in_voxel, size_t ws_stride, int npv, int max_pillars, int max_rows)
+{
+    __shared__ __align__(16) float s_feat[kThreads * 10];
+    const int b = blockIdx.y;
+    const int Pc = point_num[b];
+    const int r0 = blockIdx.x * kThreads;
+    if (r0 >= Pc) return;
+    const size_t wb = (size_t) b * ws_stride;
+    const int r = r0 + threadIdx.x;
+    if (r < Pc) {
+        const int2 info = row_info[(wb >> 1) + r];
+        const int pid = info.y;
+        const float4 p = points[(size_t) b * max_points + info.x];
+        const float4 m = mean[(wb >> 2) + pid];
+        const float x = p.x, y = p.y, z = p.z;
         const int ix = (int) floorf((x - g.x_min) / g.vx);
         const int iy = (int) floorf((y - g.y_min) / g.vy);
         const int iz = (int) floorf((z - g.z_min) / g.vz);
@@ -323,41 +367,44 @@ vox_emit_kernel(const float4* __restrict__ points, int max_points, VoxGeom g,
         const float fx = x - ((ix + 0.5) * g.vx + g.x_min);
         const float fy = y - ((iy + 0.5) * g.vy + g.y_min);
         const float fz = z - ((iz + 0.5) * g.vz + g.z_min);
-        float* f = &s_feat[w][s * 10];
-        f[0] = x; f[1] = y; f[2] = z; f[3] = it;
-        f[4] = x - mx; f[5] = y - my; f[6] = z - mz;
+        float* f = &s_feat[threadIdx.x * 10];
+        f[0] = x; f[1] = y; f[2] = z; f[3] = p.w;
+        f[4] = x - m.x; f[5] = y - m.y; f[6] = z - m.z;
         f[7] = fx; f[8] = fy; f[9] = fz;
+        point_index_in_voxel[((size_t) b * max_pillars + pid) * npv + (r - __ldg(pinfo + (wb >> 2) + pid).z)] = r;
     }
-    __syncwarp();
-    float* dst = feat_b + (size_t) row0 * 10;
-    for (int t = lane; t < keep * 10; t += 32) dst[t] = s_feat[w][t];
-    for (int s = lane; s < npv; s += 32) {
-        if (s < keep) piv_b[(size_t) pid * npv + s] = row0 + s;
-        else if (zero_tails) piv_b[(size_t) pid * npv + s] = 0;
-    }
+    __syncthreads();
+    const int rows = Pc - r0 < kThreads ? Pc - r0 : kThreads;
+    float* dst = point_features + ((size_t) b * max_rows + r0) * 10;      // 256 rows x 40 B: 16-byte aligned
+    const int n4 = (reinterpret_cast<uintptr_t>(dst) & 15) ? 0 : rows * 10 / 4;    // odd capacities: scalar path
+    for (int t = threadIdx.x; t < n4; t += kThreads)
+        reinterpret_cast<float4*>(dst)[t] = reinterpret_cast<const float4*>(s_feat)[t];
+    for (int t = n4 * 4 + threadIdx.x; t < rows * 10; t += kThreads) dst[t] = s_feat[t];
 }
 
 // Zero-fill of everything beyond the valid counts (the reference memsets all outputs, points2Features.cu:944-952).
 // A plain grid-stride streaming kernel: keeping this out of vox_emit removes ~half of that kernel's instructions.
-__global__ void __launch_bounds__(256)
-vox_zero_tails_kernel(const int* __restrict__ pillar_num, const int* __restrict__ point_num,
-                      float* __restrict__ point_features, int* __restrict__ point_index_in_voxel,
-                      int* __restrict__ coords, int* __restrict__ point_num_in_voxel,
-                      int npv, int max_pillars, int max_rows)
+__device__ __forceinline__ void
+vox_zero_tails_body(int cta, int n_ctas, const int* __restrict__ pillar_num, const int* __restrict__ point_num,
+                    float* __restrict__ point_features, int* __restrict__ point_index_in_voxel,
+                    int* __restrict__ coords, int* __restrict__ point_num_in_voxel,
+                    int npv, int max_pillars, int max_rows)
 {
     const int b = blockIdx.y;
     const int V = pillar_num[b], Pc = point_num[b];
-    const unsigned stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned stride = n_ctas * blockDim.x, t0 = cta * blockDim.x + threadIdx.x;
     // feature rows [Pc, max_rows): 10 floats per row = 5 float2 (rows are 8-byte aligned)
     {
         float2* f = reinterpret_cast<float2*>(point_features + ((size_t) b * max_rows + Pc) * 10);
         const unsigned n = (unsigned) (max_rows - Pc) * 5u;
         for (unsigned t = t0; t < n; t += stride) f[t] = make_float2(0.f, 0.f);
     }
-    {
-        int* q = point_index_in_voxel + ((size_t) b * max_pillars + V) * npv;
-        const unsigned n = (unsigned) (max_pillars - V) * (unsigned) npv;
-        for (unsigned t = t0; t < n; t += stride) q[t] = 0;
+    {   // the whole index tensor: tail pillars and the unused slots of valid ones (vox_feat_kernel fills the used slots)
+        int4* q = reinterpret_cast<int4*>(point_index_in_voxel + (size_t) b * max_pillars * npv);
+        const unsigned n = (reinterpret_cast<uintptr_t>(q) & 15) ? 0u : (unsigned) (((size_t) max_pillars * npv) / 4);
+        for (unsigned t = t0; t < n; t += stride) q[t] = make_int4(0, 0, 0, 0);
+        for (unsigned t = n * 4 + t0; t < (unsigned) max_pillars * (unsigned) npv; t += stride)
+            point_index_in_voxel[(size_t) b * max_pillars * npv + t] = 0;
     }
     {
         int* c = coords + ((size_t) b * max_pillars + V) * 4;
@@ -366,6 +413,36 @@ vox_zero_tails_kernel(const int* __restrict__ pillar_num, const int* __restrict_
         int* m = point_num_in_voxel + (size_t) b * max_pillars + V;
         for (unsigned t = t0; t < (unsigned) (max_pillars - V); t += stride) m[t] = 0;
     }
+}
+
+// Two independent stages share one launch each (fewer launches on the single-frame latency path): the first
+// `pts_ctas` CTAs of a row run the per-point stage, the rest the other one.
+__global__ void __launch_bounds__(kThreads)
+vox_scatter_zero_kernel(int pts_ctas, const int* __restrict__ points_size, int max_points, int* __restrict__ pcell,
+                        const int* __restrict__ cell_pid, unsigned int* __restrict__ cursor, int* __restrict__ list,
+                        size_t ws_stride, const int* __restrict__ pillar_num, const int* __restrict__ point_num,
+                        float* __restrict__ point_features, int* __restrict__ point_index_in_voxel,
+                        int* __restrict__ coords, int* __restrict__ point_num_in_voxel, int npv, int max_pillars,
+                        int max_rows)
+{
+    if ((int) blockIdx.x < pts_ctas)
+        vox_scatter_body(points_size, max_points, pcell, cell_pid, cursor, list, ws_stride);
+    else
+        vox_zero_tails_body((int) blockIdx.x - pts_ctas, (int) gridDim.x - pts_ctas, pillar_num, point_num, point_features,
+                            point_index_in_voxel, coords, point_num_in_voxel, npv, max_pillars, max_rows);
+}
+
+__global__ void __launch_bounds__(kThreads)
+vox_rank_kernel(int pts_ctas, const int* __restrict__ points_size, int max_points, const int* __restrict__ ppid,
+                const int* __restrict__ list, const int4* __restrict__ pinfo, int2* __restrict__ row_info,
+                size_t ws_stride, const int* __restrict__ big_list, const unsigned int* __restrict__ big_count_base,
+                int G, int npv)
+{
+    if ((int) blockIdx.x < pts_ctas)
+        vox_rank_body(points_size, max_points, ppid, list, pinfo, row_info, ws_stride);
+    else
+        vox_rank_big_body<kThreads / 32>((int) blockIdx.x - pts_ctas, (int) gridDim.x - pts_ctas, max_points, list, pinfo,
+                                         big_list, big_count_base, row_info, ws_stride, G, npv);
 }
 
 }  // namespace
@@ -389,14 +466,19 @@ static int vox_check(const dsvt_points2features_params* p) {
     return DSVT_OK;
 }
 
-static size_t vox_frame_stride_words(const dsvt_points2features_params* p, size_t* offs /*8*/) {
+constexpr int kWsArrays = 13;
+static size_t vox_frame_stride_words(const dsvt_points2features_params* p, size_t* offs /*kWsArrays*/) {
     const size_t G = (size_t) p->grid_x * p->grid_y;
     const size_t nblk = (G + kCellsPerBlock - 1) / kCellsPerBlock;
-    const size_t sizes[8] = {G, G, (size_t) p->max_points_num, (size_t) p->max_points_num,
-                             (size_t) p->max_pillars_num, (size_t) p->max_pillars_num,
-                             (size_t) p->max_pillars_num, nblk * 3};
+    // cell_count (+ the big-pillar counter right behind it, cleared by the same memset) | cursor | pcell | list |
+    // pillar records (int4: list base, n, first row, rows kept) | (unused) | (unused) | block_sums | cell_pid | row_info (int2: point index, pillar) | (unused) | mean (float4) | big_list
+    const size_t list_cap = (size_t) p->max_points_num + 3 * (G < (size_t) p->max_points_num ? G : (size_t) p->max_points_num);
+    const size_t sizes[kWsArrays] = {G + 8, G, (size_t) p->max_points_num, list_cap,
+                                     (size_t) p->max_pillars_num * 4, 0, 0, nblk * 3, G,
+                                     (size_t) p->max_points_num_voxel_filter * 2, 0,
+                                     (size_t) p->max_pillars_num * 4, (size_t) p->max_pillars_num};
     size_t off = 0;
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < kWsArrays; ++i) {
         if (offs) offs[i] = off;
         off += align_up(sizes[i] * 4, kWsAlign) / 4;
     }
@@ -420,7 +502,7 @@ extern "C" int dsvt_points2features_launch(const dsvt_points2features_params* p,
                    point_num_in_voxel && pillar_num && point_num && workspace, "NULL tensor pointer");
     DSVT_CHECK_ARG(((uintptr_t) points & 15) == 0 && ((uintptr_t) coords & 15) == 0 &&
                    ((uintptr_t) workspace & 255) == 0, "points/coords must be 16-B, workspace 256-B aligned");
-    size_t offs[8];
+    size_t offs[kWsArrays];
     const size_t stride = vox_frame_stride_words(p, offs);
     if (workspace_bytes < stride * 4 * (size_t) p->batch) {
         set_last_error("dsvt_points2features_launch: workspace too small (%zu < %zu)", workspace_bytes,
@@ -433,9 +515,11 @@ extern "C" int dsvt_points2features_launch(const dsvt_points2features_params* p,
     int* pcell = reinterpret_cast<int*>(w32 + offs[2]);
     int* list = reinterpret_cast<int*>(w32 + offs[3]);
     int* pillar_base = reinterpret_cast<int*>(w32 + offs[4]);
-    int* pillar_n = reinterpret_cast<int*>(w32 + offs[5]);
-    int* pillar_row = reinterpret_cast<int*>(w32 + offs[6]);
     int* block_sums = reinterpret_cast<int*>(w32 + offs[7]);
+    int* cell_pid = reinterpret_cast<int*>(w32 + offs[8]);
+    int2* row_info = reinterpret_cast<int2*>(w32 + offs[9]);
+    float4* mean = reinterpret_cast<float4*>(w32 + offs[11]);
+    int* big_list = reinterpret_cast<int*>(w32 + offs[12]);
 
     const int B = p->batch;
     const int G = p->grid_x * p->grid_y;
@@ -446,9 +530,9 @@ extern "C" int dsvt_points2features_launch(const dsvt_points2features_params* p,
 
     // only the counter grid needs clearing (876 KB/frame at 468^2); everything else is fully overwritten
     if (B == 1) {
-        DSVT_CUDA(cudaMemsetAsync(cell_count, 0, (size_t) G * 4, st));
+        DSVT_CUDA(cudaMemsetAsync(cell_count, 0, (size_t) (G + 8) * 4, st));
     } else {
-        DSVT_CUDA(cudaMemset2DAsync(cell_count, stride * 4, 0, (size_t) G * 4, B, st));
+        DSVT_CUDA(cudaMemset2DAsync(cell_count, stride * 4, 0, (size_t) (G + 8) * 4, B, st));
     }
     count_launch();
 
@@ -459,27 +543,31 @@ extern "C" int dsvt_points2features_launch(const dsvt_points2features_params* p,
     vox_block_reduce_kernel<<<dim3(nblk, B), kThreads, 0, st>>>(cell_count, block_sums, stride, G,
                                                                 p->max_num_points_per_voxel);
     DSVT_LAUNCH_CHECK();
-    vox_scan_kernel<<<dim3(nblk, B), kThreads, 0, st>>>(cell_count, block_sums, cursor, pillar_base, pillar_n,
-                                                        pillar_row, coords, point_num_in_voxel, pillar_num,
-                                                        point_num, stride, G, p->grid_x,
+    vox_scan_kernel<<<dim3(nblk, B), kThreads, 0, st>>>(cell_count, block_sums, cursor, pillar_base, coords, point_num_in_voxel, pillar_num,
+                                                        point_num, cell_pid, big_list, cell_count, list, stride, G, p->grid_x,
                                                         p->max_num_points_per_voxel, p->max_pillars_num,
                                                         p->max_points_num_voxel_filter);
     DSVT_LAUNCH_CHECK();
-    vox_scatter_kernel<<<grid_pts, kThreads, 0, st>>>(points_size, p->max_points_num, pcell, cursor, list, stride);
+    // scatter (per point) + zero-fill of the outputs beyond the valid counts (before vox_feat_kernel, which fills the
+    // used slots of point_index_in_voxel)
+    const int zero_ctas = p->zero_tails ? sm_count() * 4 : 0;
+    vox_scatter_zero_kernel<<<dim3(grid_pts.x + zero_ctas, B), kThreads, 0, st>>>(
+        (int) grid_pts.x, points_size, p->max_points_num, pcell, cell_pid, cursor, list, stride, pillar_num, point_num,
+        point_features, point_index_in_voxel, coords, point_num_in_voxel, p->max_num_points_per_voxel,
+        p->max_pillars_num, p->max_points_num_voxel_filter);
     DSVT_LAUNCH_CHECK();
-    constexpr int kWarps = 8;
-    const dim3 grid_emit((p->max_pillars_num + kWarps - 1) / kWarps, B);
-    vox_emit_kernel<kWarps><<<grid_emit, kWarps * 32, 0, st>>>(
-        reinterpret_cast<const float4*>(points), p->max_points_num, g, list, pillar_base, pillar_n, pillar_row,
-        pillar_num, point_num, point_num_in_voxel, point_features, point_index_in_voxel, coords,
-        point_num_in_voxel, stride, p->max_num_points_per_voxel, p->max_pillars_num,
-        p->max_points_num_voxel_filter, p->zero_tails);
+    const int4* pinfo = reinterpret_cast<const int4*>(pillar_base);
+    vox_rank_kernel<<<dim3(grid_pts.x + 64, B), kThreads, 0, st>>>(
+        (int) grid_pts.x, points_size, p->max_points_num, pcell, list, pinfo, row_info, stride, big_list, cell_count, G,
+        p->max_num_points_per_voxel);
     DSVT_LAUNCH_CHECK();
-    if (p->zero_tails) {
-        vox_zero_tails_kernel<<<dim3(sm_count() * 4, B), 256, 0, st>>>(
-            pillar_num, point_num, point_features, point_index_in_voxel, coords, point_num_in_voxel,
-            p->max_num_points_per_voxel, p->max_pillars_num, p->max_points_num_voxel_filter);
-        DSVT_LAUNCH_CHECK();
-    }
+    vox_mean_kernel<<<dim3((p->max_pillars_num + kThreads - 1) / kThreads, B), kThreads, 0, st>>>(
+        reinterpret_cast<const float4*>(points), p->max_points_num, pillar_num, pinfo, row_info, mean, stride);
+    DSVT_LAUNCH_CHECK();
+    vox_feat_kernel<<<dim3((p->max_points_num_voxel_filter + kThreads - 1) / kThreads, B), kThreads, 0, st>>>(
+        reinterpret_cast<const float4*>(points), p->max_points_num, g, point_num, pinfo, row_info, mean,
+        point_features, point_index_in_voxel, stride, p->max_num_points_per_voxel, p->max_pillars_num,
+        p->max_points_num_voxel_filter);
+    DSVT_LAUNCH_CHECK();
     return DSVT_OK;
 }
