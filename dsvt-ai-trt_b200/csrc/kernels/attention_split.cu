@@ -195,6 +195,20 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
             }
         }
         if (tid == 0) SP(14);
+        // tiles of tail rows (>= voxel_num) assigned to this CTA are zero-filled by the producers, which are idle from
+        // here on -- the epilogue warps only zero the invalid rows of the last partial tile
+        if (zero_tails) {
+            for (int n = cnt;; ++n) {
+                const int t = t0 + n * stride;
+                if (t >= n_tiles) break;
+                const int row0 = t * kBM;
+                for (int i = tid; i < kBM * (kBN / 4); i += kProducers) {
+                    const int rloc = i / (kBN / 4), cc4 = i - rloc * (kBN / 4);
+                    if (row0 + rloc < max_pillars)
+                        *reinterpret_cast<float4*>(out + (size_t) (row0 + rloc) * g.ld_out + cc4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
     } else if (warp < 8 + kEpiWarps) {
         // =========================== EPILOGUE ============================================================
         // warp = (TMEM lane quarter q4, column half hf): 3 slabs of 32 columns.  Slab: TMEM -> registers (lane = row)
@@ -250,12 +264,8 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
                 }
                 if (lane == 0 && warp == 8 && n == 0) SP(16);
                 if (lane == 0 && warp == 8 && n == cnt - 1) SP(17);
-            } else if (zero_tails) {                               // a tile of tail rows
-                for (int i = lane; i < 32 * 24; i += 32) {
-                    const int rloc = i / 24, cc4 = i - rloc * 24;
-                    if (row0 + rloc < max_pillars)
-                        *reinterpret_cast<float4*>(out + (size_t) (row0 + rloc) * g.ld_out + hf * 96 + cc4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+            } else {
+                break;                                             // tail tiles: zero-filled by the producer warps
             }
         }
     } else {
