@@ -249,10 +249,16 @@ def plugin_breakdown(slot, cfg, peaks, reps=3):
     lib = capi._lib()
     for i in (0, 1):
         gs = f.gs[i]
+        plan = f.plans.get((i, 0)) if getattr(f, "plans", None) else None
         call = lambda: capi.set_attention_fused(w.attn[i], f.x0, f.pos[i][0], gs.global_index_in_set[0],
                                                 gs.mask_expand_0[0], gs.set_num, f.vox.pillar_num, axis=0,
-                                                out=f.attn_out, precision=f.precision, workspace=f.attn_ws)
+                                                out=f.attn_out, precision=f.precision, workspace=f.attn_ws, plan=plan)
         us = timed(call)
+        if plan is not None:      # one plan per (partition, axis) serves two layers: 4 plan builds per frame
+            pus = timed(lambda: capi.set_attention_plan(gs.global_index_in_set[0], gs.mask_expand_0[0], gs.set_num, 0,
+                                                        cfg.max_pillars_num, cfg.num_heads, cfg.channel_num, out=plan))
+            res[f"set_attention_plan_{i}"] = {"us": pus, "bytes": NS[i] * (S * 4 + 8 * S * 4) + 4 * V + NS[i] * S * 8,
+                                              "calls_per_frame": 2}
         flops = 11612160 * NS[i] if S == 36 else None
         res[f"set_attention_{i}"] = {"us": us, "flops": flops, "bytes": 83088 * NS[i] + 590000, "calls_per_frame": 4}
         if pipeline_prec:

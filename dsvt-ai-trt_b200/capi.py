@@ -307,8 +307,26 @@ def set_attention_workspace_bytes(B, max_sets, S, C, heads, max_pillars, precisi
     return int(_lib().dsvt_set_attention_workspace_size(ctypes.byref(p)))
 
 
+def set_attention_plan(global_index_in_set, mask, set_num, axis, max_pillars, heads=8, channels=192, out=None):
+    """Builds the attention plan of one (window partition, axis) -- dsvt_set_attention_plan_launch.  The returned uint8
+    tensor can be passed as `plan=` to every set_attention_fused call (GEMM-pipeline precisions) on that partition."""
+    _need(global_index_in_set, torch.int32, "global_index_in_set")
+    _need(mask, torch.float32, "mask")
+    B = global_index_in_set.shape[0] if global_index_in_set.dim() == 4 else 1
+    max_sets, S = global_index_in_set.shape[-2], global_index_in_set.shape[-1]
+    p = AttnParams(B, max_sets, S, channels, heads, max_pillars, axis, DSVT_ATTN_FP32_TC, 1)
+    lib = _lib()
+    lib.dsvt_set_attention_plan_size.restype = c_size_t
+    n = int(lib.dsvt_set_attention_plan_size(ctypes.byref(p)))
+    out = torch.empty(n, dtype=torch.uint8, device=mask.device) if out is None else out
+    rc = lib.dsvt_set_attention_plan_launch(ctypes.byref(p), _ptr(global_index_in_set), _ptr(mask), _ptr(set_num),
+                                            _ptr(out), c_size_t(out.numel()), _stream())
+    _check(rc, "dsvt_set_attention_plan_launch")
+    return out
+
+
 def set_attention_fused(weights, x, pos, global_index_in_set, mask, set_num, voxel_num, axis, out=None,
-                        precision=DSVT_ATTN_FP32, zero_tails=1, workspace=None):
+                        precision=DSVT_ATTN_FP32, zero_tails=1, workspace=None, plan=None):
     """Fused gather + attention + scatter: x,pos [B,max_pillars,C], global_index_in_set [B,2,max_sets,S].
     `workspace`: uint8 device tensor of dsvt_set_attention_workspace_size bytes (allocated here when None and the
     precision needs one; pass a persistent buffer when capturing CUDA graphs)."""
@@ -324,6 +342,12 @@ def set_attention_fused(weights, x, pos, global_index_in_set, mask, set_num, vox
     ws_bytes = int(_lib().dsvt_set_attention_workspace_size(ctypes.byref(p)))
     if ws_bytes and workspace is None:
         workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    if plan is not None and ws_bytes:
+        rc = _lib().dsvt_set_attention_fused_planned_launch(
+            ctypes.byref(p), c_void_p(weights.handle), _ptr(x), _ptr(pos), _ptr(global_index_in_set), _ptr(mask),
+            _ptr(set_num), _ptr(voxel_num), _ptr(out), _ptr(plan), _ptr(workspace), c_size_t(workspace.numel()), _stream())
+        _check(rc, "dsvt_set_attention_fused_planned_launch")
+        return out
     rc = _lib().dsvt_set_attention_fused_launch(ctypes.byref(p), c_void_p(weights.handle), _ptr(x), _ptr(pos),
                                                 _ptr(global_index_in_set), _ptr(mask), _ptr(set_num),
                                                 _ptr(voxel_num), _ptr(out), _ptr(workspace),

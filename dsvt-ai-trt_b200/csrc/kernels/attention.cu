@@ -93,7 +93,7 @@ extern "C" size_t dsvt_set_attention_workspace_size(const dsvt_set_attention_par
 
 static int attn_dispatch(const dsvt_set_attention_params* p, const dsvt_attention_weights* w, bool fused,
                          const float* q, const float* k, const float* v, const float* pos, const int* idx,
-                         const float* mask, const int* set_num, const int* voxel_num, float* out,
+                         const float* mask, const int* set_num, const int* voxel_num, float* out, const void* plan,
                          void* workspace, size_t workspace_bytes, cudaStream_t st)
 {
     switch (p->precision) {
@@ -105,7 +105,7 @@ static int attn_dispatch(const dsvt_set_attention_params* p, const dsvt_attentio
                 return DSVT_ERR_UNSUPPORTED;
             }
             return set_attention_split_fused(p, w->split_blob, w->split_out_mul, p->precision == DSVT_ATTN_FP32_TC,
-                                             q, pos, idx, mask, set_num, voxel_num, out, workspace, workspace_bytes, st);
+                                             q, pos, idx, mask, set_num, voxel_num, out, plan, workspace, workspace_bytes, st);
         case DSVT_ATTN_FP32:
             return set_attention_fp32(p, w->dev, fused, q, k, v, pos, idx, mask, set_num, voxel_num, out, st);
         case DSVT_ATTN_FP16:
@@ -135,15 +135,14 @@ extern "C" int dsvt_set_attention_launch(const dsvt_set_attention_params* p, con
     if (rc != DSVT_OK) return rc;
     DSVT_CHECK_ARG(q && k && v && mask && out, "NULL tensor pointer");
     DSVT_CHECK_ARG(!(((uintptr_t) q | (uintptr_t) k | (uintptr_t) v | (uintptr_t) out) & 15), "16-B alignment");
-    return attn_dispatch(p, w, false, q, k, v, nullptr, nullptr, mask, set_num, nullptr, out,
+    return attn_dispatch(p, w, false, q, k, v, nullptr, nullptr, mask, set_num, nullptr, out, nullptr,
                          workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int dsvt_set_attention_fused_launch(const dsvt_set_attention_params* p, const dsvt_attention_weights* w,
-                                               const float* x, const float* pos,
-                                               const int32_t* global_index_in_set, const float* mask,
-                                               const int32_t* set_num, const int32_t* voxel_num, float* out,
-                                               void* workspace, size_t workspace_bytes, dsvt_stream_t stream)
+static int fused_common(const dsvt_set_attention_params* p, const dsvt_attention_weights* w,
+                        const float* x, const float* pos, const int32_t* global_index_in_set, const float* mask,
+                        const int32_t* set_num, const int32_t* voxel_num, float* out, const void* plan,
+                        void* workspace, size_t workspace_bytes, dsvt_stream_t stream)
 {
     int rc = attn_check(p, w);
     if (rc != DSVT_OK) return rc;
@@ -152,5 +151,41 @@ extern "C" int dsvt_set_attention_fused_launch(const dsvt_set_attention_params* 
     DSVT_CHECK_ARG(p->axis_id == 0 || p->axis_id == 1, "axis_id");
     DSVT_CHECK_ARG(!(((uintptr_t) x | (uintptr_t) pos | (uintptr_t) out) & 15), "16-B alignment");
     return attn_dispatch(p, w, true, x, nullptr, nullptr, pos, global_index_in_set, mask, set_num, voxel_num,
-                         out, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+                         out, plan, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dsvt_set_attention_fused_launch(const dsvt_set_attention_params* p, const dsvt_attention_weights* w,
+                                               const float* x, const float* pos,
+                                               const int32_t* global_index_in_set, const float* mask,
+                                               const int32_t* set_num, const int32_t* voxel_num, float* out,
+                                               void* workspace, size_t workspace_bytes, dsvt_stream_t stream)
+{
+    return fused_common(p, w, x, pos, global_index_in_set, mask, set_num, voxel_num, out, nullptr, workspace,
+                        workspace_bytes, stream);
+}
+
+extern "C" int dsvt_set_attention_fused_planned_launch(const dsvt_set_attention_params* p,
+                                                       const dsvt_attention_weights* w, const float* x, const float* pos,
+                                                       const int32_t* global_index_in_set, const float* mask,
+                                                       const int32_t* set_num, const int32_t* voxel_num, float* out,
+                                                       const void* plan, void* workspace, size_t workspace_bytes,
+                                                       dsvt_stream_t stream)
+{
+    return fused_common(p, w, x, pos, global_index_in_set, mask, set_num, voxel_num, out, plan, workspace,
+                        workspace_bytes, stream);
+}
+
+extern "C" size_t dsvt_set_attention_plan_size(const dsvt_set_attention_params* p) {
+    return p ? attention_split_plan_bytes(p) : 0;
+}
+
+extern "C" int dsvt_set_attention_plan_launch(const dsvt_set_attention_params* p, const int32_t* global_index_in_set,
+                                              const float* mask, const int32_t* set_num, void* plan, size_t plan_bytes,
+                                              dsvt_stream_t stream)
+{
+    DSVT_CHECK_ARG(p && global_index_in_set && mask && set_num, "NULL argument");
+    DSVT_CHECK_ARG(p->batch >= 1 && p->max_set_num >= 1 && p->max_pillars_num >= 1, "batch / capacities");
+    DSVT_CHECK_ARG(p->axis_id == 0 || p->axis_id == 1, "axis_id");
+    return attention_split_plan(p, global_index_in_set, mask, set_num, plan, plan_bytes,
+                                reinterpret_cast<cudaStream_t>(stream));
 }

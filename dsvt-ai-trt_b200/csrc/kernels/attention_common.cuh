@@ -31,10 +31,13 @@ int set_attention_tc2_fused(const dsvt_set_attention_params* p, const void* tc_b
 void* attention_split_prepare(const float* w_in, const float* b_in, const float* w_out, const float* b_out,
                               float* out_mul);
 size_t attention_split_workspace(const dsvt_set_attention_params* p);
+size_t attention_split_plan_bytes(const dsvt_set_attention_params* p);
+int attention_split_plan(const dsvt_set_attention_params* p, const int* idx, const float* mask, const int* set_num,
+                         void* plan, size_t plan_bytes, cudaStream_t st);
 int set_attention_split_fused(const dsvt_set_attention_params* p, const void* split_blob, const float* out_mul,
                               bool split, const float* x, const float* pos, const int* idx, const float* mask,
-                              const int* set_num, const int* voxel_num, float* out, void* workspace,
-                              size_t workspace_bytes, cudaStream_t st);
+                              const int* set_num, const int* voxel_num, float* out, const void* plan,
+                              void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 }  // namespace dsvt
 

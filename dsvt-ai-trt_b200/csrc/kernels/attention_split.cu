@@ -62,6 +62,26 @@ template <bool SPLIT> struct Lay {
     static constexpr int total = epi + kEpiWarps * kEpiScratch;    // 229376 / 131072
 };
 
+// ---- attention plan: the set partition of one (frame, window partition, axis) in token order ----------------------
+// Built once by dsvt_set_attention_plan_launch and shared by every attention layer that uses the partition.
+// Per batch item, in ints (each array padded to 64): hdr[64] (hdr[0] = T, number of distinct tokens) |
+// set_off[max_sets + 1] (exclusive prefix of tokens per set) | nu[max_sets] | vox_su[max_pillars] (voxel -> set * 64 + u,
+// -1 if the voxel is in no set) | tok[max_sets * S] as int2 (voxel row, slot) of the u-th distinct token of each set.
+__host__ __device__ inline size_t pad64(size_t n) { return (n + 63) & ~(size_t) 63; }
+struct PlanView { int* hdr; int* set_off; int* nu; int* vox_su; int2* tok; };
+__host__ __device__ inline size_t plan_words(int max_sets, int S, int max_pillars) {
+    return 64 + pad64((size_t) max_sets + 1) + pad64(max_sets) + pad64(max_pillars) + pad64((size_t) 2 * max_sets * S);
+}
+__host__ __device__ inline PlanView plan_view(int* base, int max_sets, int max_pillars) {
+    PlanView v;
+    v.hdr = base;
+    v.set_off = base + 64;
+    v.nu = v.set_off + pad64((size_t) max_sets + 1);
+    v.vox_su = v.nu + pad64(max_sets);
+    v.tok = reinterpret_cast<int2*>(v.vox_su + pad64(max_pillars));
+    return v;
+}
+
 struct GemmRole {
     const float* a0;        // [rows, 192] f32
     const float* a1;        // optional addend (pos), or nullptr
@@ -72,6 +92,9 @@ struct GemmRole {
     float out_mul;          // 2^-s: undoes the weight pre-scaling
     float post_mul;         // 1/sqrt(C/heads) for q, applied AFTER the biased projection like the reference's division
                             // (:386-405; multiplying by the rounded reciprocal differs from dividing by <= 1 ulp)
+    const int* plan;        // attention plan (per-batch stride plan_stride ints) or nullptr: when set, output row of voxel v
+    size_t plan_stride;     //   is its TOKEN position set_off[set(v)] + u(v) (set-major order), not v
+    int pad_hi;             // floats inserted in front of columns 96..191 (K / V rows: bank-conflict-free head layout)
 };
 struct GemmRoles { GemmRole r[3]; };
 
@@ -106,7 +129,8 @@ __device__ long long g_split_prof[64];
 // -> full 128-byte row segments to global memory).
 template <bool SPLIT>
 __global__ void __launch_bounds__(kThreadsG, 1)
-proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num, int max_pillars, int zero_tails)
+proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num, int max_pillars, int max_sets,
+                 int zero_tails)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t w_full[kNumK], a_full[kAStages], a_empty[kAStages], acc_full[2], acc_empty[2];
@@ -121,6 +145,9 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
     V = V < max_pillars ? V : max_pillars;
     const int n_tiles = (max_pillars + kBM - 1) / kBM, valid_tiles = (V + kBM - 1) / kBM;
     const int cnt = valid_tiles > t0 ? (valid_tiles - t0 + stride - 1) / stride : 0;    // row tiles this CTA computes
+    // (walking the K chunks from a per-CTA starting chunk, so that the CTAs of a role do not all want the same weight
+    //  lines at kernel start, was measured: no change -- the weight copies are bandwidth-, not hot-line-bound)
+    constexpr int rot = 0;
     if (cnt == 0 && !zero_tails) return;
     float* out = g.out + (size_t) b * max_pillars * g.ld_out + g.col0;
     const float* a0 = g.a0 + (size_t) b * max_pillars * kC;
@@ -151,7 +178,7 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
         float buf[kDepth][16];                                  // [0..7] = a0 row piece, [8..15] = a1 (pos) row piece
         auto issue = [&](int gs, float (&d)[16]) {
             const int n = gs / kStepsPerTile, s = gs - n * kStepsPerTile;
-            const int kc = s >> 1, row = (t0 + n * stride) * kBM + (s & 1) * 64 + rl;
+            const int kc = ((s >> 1) + rot) % kNumK, row = (t0 + n * stride) * kBM + (s & 1) * 64 + rl;
             if (row < V) {
                 ldg256(a0 + (size_t) row * kC + kc * kBK + c16 * 8, &d[0]);      // one 256-bit load: full 32-byte sectors
                 if (a1) ldg256(a1 + (size_t) row * kC + kc * kBK + c16 * 8, &d[8]);
@@ -218,13 +245,32 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
         const uint32_t tlane = tmem + ((uint32_t) (q4 * 32) << 16) + hf * 96;
         const int rg = lane >> 3, c4 = lane & 7;
         const float* bias = g.bias + hf * 96 + c4 * 4;
-        float* outc = out + hf * 96 + c4 * 4;
+        float* outc = out + hf * (96 + g.pad_hi) + c4 * 4;
+        const PlanView pv = plan_view(const_cast<int*>(g.plan) + (size_t) b * g.plan_stride, max_sets, max_pillars);
         for (int n = 0;; ++n) {
             const int t = t0 + n * stride;
             if (t >= n_tiles) break;
             const int row0 = t * kBM + q4 * 32;                    // first row of this warp's lane quarter
             if (n < cnt) {
                 const int acc = n & 1;
+                // (the row map does not depend on the accumulators: its two dependent loads overlap the MMA wait)
+                int orow[8];                                       // output row of this lane's 8 rows, -1: not written
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) {
+                    const int grow = row0 + rr * 4 + rg;
+                    if (g.plan) {                                  // voxel row -> token position (set-major order)
+                        orow[rr] = -1;
+                        if (grow < V) {
+                            const int su = __ldg(pv.vox_su + grow);
+                            if (su >= 0) {
+                                const int t = __ldg(pv.set_off + (su >> 6)) + (su & 63);
+                                if (t < max_pillars) orow[rr] = t;
+                            }
+                        }
+                    } else {
+                        orow[rr] = (grow < V || (zero_tails && grow < max_pillars)) ? grow : -1;
+                    }
+                }
                 mbar_wait(&acc_full[acc], (n >> 1) & 1);
                 tc_fence_after_sync();
                 if (lane == 0 && warp == 8 && n == 0) SP(20);
@@ -257,8 +303,7 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
                         float4 ov = make_float4((v[rr].x * g.out_mul + bb.x) * g.post_mul, (v[rr].y * g.out_mul + bb.y) * g.post_mul,
                                                 (v[rr].z * g.out_mul + bb.z) * g.post_mul, (v[rr].w * g.out_mul + bb.w) * g.post_mul);
                         if (grow >= V) ov = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (grow < V || (zero_tails && grow < max_pillars))
-                            *reinterpret_cast<float4*>(outc + (size_t) grow * g.ld_out + j0) = ov;
+                        if (orow[rr] >= 0) *reinterpret_cast<float4*>(outc + (size_t) orow[rr] * g.ld_out + j0) = ov;
                     }
                     __syncwarp();
                 }
@@ -279,7 +324,8 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
                 l2_prefetch(a0 + (size_t) row0 * kC, bytes);
                 if (a1) l2_prefetch(a1 + (size_t) row0 * kC, bytes);
             }
-            for (int kc = 0; kc < kNumK; ++kc) {
+            for (int i = 0; i < kNumK; ++i) {
+                const int kc = (i + rot) % kNumK;
                 mbar_arrive_expect_tx(&w_full[kc], L::w_chunk);
                 bulk_g2s(smem + L::w + kc * L::w_chunk, g.wimg + (size_t) kc * kWChunkBytes, L::w_chunk, &w_full[kc]);
             }
@@ -293,12 +339,13 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
                 const uint32_t d_tmem = tmem + acc * kAccCols;
 #pragma unroll 1
                 for (int kc = 0; kc < kNumK; ++kc, ++cc) {
-                    if (n == 0) mbar_wait(&w_full[kc], 0);
+                    const int kcw = (kc + rot) % kNumK;            // the chunk the producers staged at ring position cc
+                    if (n == 0) mbar_wait(&w_full[kcw], 0);
                     const int st = cc % kAStages;
                     mbar_wait(&a_full[st], (cc / kAStages) & 1);
                     tc_fence_after_sync();
                     if (n == 0) SP(8 + kc);
-                    const uint32_t sa = sbase + L::a + st * L::a_stage, sw = sbase + L::w + kc * L::w_chunk;
+                    const uint32_t sa = sbase + L::a + st * L::a_stage, sw = sbase + L::w + kcw * L::w_chunk;
 #pragma unroll
                     for (int ks = 0; ks < kBK / 16; ++ks) {
                         const uint64_t a_hi = make_smem_desc(sa + ks * 2 * (kBM * 16), kBM * 16, 128);
@@ -328,14 +375,90 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------------
+// Plan kernel 1: one warp per set.  Token compaction, same rule as attention_fp32.cu: a slot that repeats the previous
+// voxel AND is masked as a key by every head (getSet.cu:546-563) is the same token as its twin.
+template <int S>
+__global__ void __launch_bounds__(256)
+attn_plan_sets_kernel(const int* __restrict__ idx, const float* __restrict__ mask, const int* __restrict__ set_num,
+                      int* __restrict__ plan, size_t plan_stride, int max_sets, int max_pillars, int axis)
+{
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int set = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (set >= max_sets) return;
+    const PlanView pv = plan_view(plan + (size_t) b * plan_stride, max_sets, max_pillars);
+    int ns = set_num[b];
+    ns = ns < max_sets ? ns : max_sets;
+    if (set >= ns) { if (lane == 0) pv.nu[set] = 0; return; }
+    const int* my_idx = idx + (((size_t) b * 2 + axis) * max_sets + set) * S;
+    const float* my_mask = mask + ((size_t) b * max_sets + set) * kH * S;
+    int base_u = 0;
+#pragma unroll
+    for (int k0 = 0; k0 < S; k0 += 32) {
+        const int k = k0 + lane;
+        bool keep = false;
+        int gidx = 0;
+        if (k < S) {
+            gidx = my_idx[k];
+            keep = (k == 0) || (gidx != my_idx[k - 1]);
+            if (!keep)
+#pragma unroll
+                for (int hh = 0; hh < kH; ++hh) keep |= !(my_mask[hh * S + k] < -1e30f);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int u = base_u + __popc(bal & ((1u << lane) - 1u));
+            pv.tok[(size_t) set * S + u] = make_int2(gidx, k);
+            if (gidx >= 0 && gidx < max_pillars) pv.vox_su[gidx] = set * 64 + u;
+        }
+        base_u += __popc(bal);
+    }
+    if (lane == 0) pv.nu[set] = base_u;
+}
+
+// Plan kernel 2: exclusive prefix of the tokens per set (one CTA per batch item), clamped to the row capacity.
+__global__ void __launch_bounds__(1024)
+attn_plan_scan_kernel(const int* __restrict__ set_num, int* __restrict__ plan, size_t plan_stride, int max_sets,
+                      int max_pillars)
+{
+    __shared__ int warp_sums[33];
+    const int b = blockIdx.x;
+    const PlanView pv = plan_view(plan + (size_t) b * plan_stride, max_sets, max_pillars);
+    int ns = set_num[b];
+    ns = ns < max_sets ? ns : max_sets;
+    int carry = 0;
+    for (int i0 = 0; i0 < ns; i0 += 1024) {
+        const int i = i0 + threadIdx.x;
+        const int v = i < ns ? pv.nu[i] : 0;
+        int total;
+        const int excl = block_excl_scan(v, warp_sums, &total) + carry;
+        if (i < ns) pv.set_off[i] = excl < max_pillars ? excl : max_pillars;
+        carry += total;
+    }
+    if (threadIdx.x == 0) {
+        const int T = carry < max_pillars ? carry : max_pillars;
+        pv.set_off[ns] = T;
+        pv.hdr[0] = T;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Per-set attention core.  One CTA per set (grid-stride), thread = (token pair, head h) with h fastest: a warp is 4 token
-// pairs x 8 heads.  Each K/V piece read from shared memory feeds TWO queries (register tiling: the kernel is bound by
-// instruction issue, not by FLOPs), the dot products and the PV update use the packed FFMA2 (two FP32 FMAs per
-// instruction, same IEEE arithmetic).  A K/V read is 8 distinct 16-byte pieces (one per head) broadcast to the 4 pairs;
-// heads are padded to 28 floats in shared memory (7 x 16 B: odd, so the 8 pieces fall into 8 different bank groups).
-// Online softmax over key chunks of 4 (one rescale per chunk): K and V are each read once per query pair.
-constexpr int kHP = 28;                 // padded head stride (floats)
-constexpr int kRowP = kH * kHP;         // 224 floats per token row in shared memory
+// pairs x 8 heads.  The QKV GEMM has written Q and [K | V] rows in TOKEN order (set-major), so a set's keys and values
+// are ONE contiguous block that lands in shared memory with a single cp.async.bulk; the chain of dependent global
+// round trips per CTA is  plan entry -> {bulk copy, q rows, token list, mask}  (the first version gathered rows by
+// voxel id after compacting the set itself: four dependent trips, which made the kernel latency-bound).
+// Each K/V piece read from shared memory feeds TWO queries (register tiling: the kernel is bound by instruction issue,
+// not by FLOPs), the dot products and the PV update use the packed FFMA2 (two FP32 FMAs per instruction, same IEEE
+// arithmetic).  A K/V read is 8 distinct 16-byte pieces (one per head) broadcast to the 4 pairs; heads 4..7 sit 16 bytes
+// further (row = 96 | 4 pad | 96 floats), which puts the 8 pieces into 8 different bank groups.
+// Online softmax over key chunks of 4 in the log2 domain (one rescale per chunk): K, V are read once per query pair.
+#ifndef DSVT_CORE_MINB
+#define DSVT_CORE_MINB 3   // 128 registers: three CTAs (15 warps) per SM measured faster than two at 168 registers
+#endif
+constexpr int kKvHalf = 96 + 4;          // floats: heads 0-3 | pad
+constexpr int kKvRow = 2 * kKvHalf - 4;  // 196 floats per K (or V) row
+constexpr int kKvTok = 2 * kKvRow;       // 392 floats per token: K row | V row
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 constexpr float kLog2e = 1.4426950408889634f;
@@ -347,105 +470,59 @@ __device__ __forceinline__ float ex2(float x) {
 }
 
 template <int S>
-__global__ void __launch_bounds__(S / 2 * kH, 2)
-attn_core_kernel(const float* __restrict__ qkv, const int* __restrict__ idx, const float* __restrict__ mask,
-                 const int* __restrict__ set_num, float* __restrict__ o, int max_sets, int max_pillars, int axis)
+__global__ void __launch_bounds__(S / 2 * kH, DSVT_CORE_MINB)
+attn_core_kernel(const float* __restrict__ qbuf, const float* __restrict__ kvbuf, const int* __restrict__ plan,
+                 size_t plan_stride, const float* __restrict__ mask, const int* __restrict__ set_num,
+                 float* __restrict__ o, int max_sets, int max_pillars)
 {
     static_assert(S % 4 == 0 && S <= 64, "set size");
     constexpr int NT = S / 2 * kH;      // 144 threads for S = 36
-    extern __shared__ __align__(16) float sm[];
-    float* Ks = sm;                     // [S][8][28]
-    float* Vs = sm + S * kRowP;
-    __shared__ int s_idx[S], s_rows[S], s_slot[S], s_nu;
+    extern __shared__ __align__(128) float sm[];        // [S][392]: K row | V row per token
+    __shared__ __align__(8) uint64_t kv_bar;
+    __shared__ int s_rows[S], s_slot[S];
     __shared__ float s_mask[kH * S];    // the set's additive key mask as given: [head][slot]
-    __shared__ float s_cmask[kH][S];    // ... compacted: [head][token]
+    __shared__ float s_cmask[kH][S];    // ... compacted, log2 domain: [head][token]
 
     const int b = blockIdx.y, tid = threadIdx.x;
     const int n_roles = 0; (void) n_roles;
 #define CP(i) do { if (blockIdx.x == 5 && blockIdx.y == 0 && threadIdx.x == 0) g_split_prof[32 + i] = clock64(); } while (0)
     CP(0);
-    qkv += (size_t) b * max_pillars * (3 * kC);
+    const PlanView pv = plan_view(const_cast<int*>(plan) + (size_t) b * plan_stride, max_sets, max_pillars);
+    qbuf += (size_t) b * max_pillars * kC;
+    kvbuf += (size_t) b * max_pillars * kKvTok;
     o += (size_t) b * max_pillars * kC;
     const int pr = tid >> 3, h = tid & 7;
     const int i0 = 2 * pr, i1 = i0 + 1;
-    // the first set's mask / index block is fetched BEFORE set_num is known (blockIdx.x < max_sets: always in bounds), so
-    // the CTA's chain of dependent global round trips is  {set_num, mask, idx} -> rows -> K/V  instead of four deep
-    float mreg[(kH * S + NT - 1) / NT];
-    int ireg = 0;
-    {
-        const int set = blockIdx.x;
-#pragma unroll
-        for (int t = 0; t < (kH * S + NT - 1) / NT; ++t)
-            mreg[t] = tid + t * NT < kH * S ? __ldg(mask + ((size_t) b * max_sets + set) * kH * S + tid + t * NT) : 0.f;
-        if (tid < S) ireg = __ldg(idx + (((size_t) b * 2 + axis) * max_sets + set) * S + tid);
-    }
+    const int hoff = h * kD + (h >= 4 ? 4 : 0);
+    if (tid == 0) { mbar_init(&kv_bar, 1); fence_barrier_init(); }
+    __syncthreads();
     int ns = set_num[b];
     ns = ns < max_sets ? ns : max_sets;
+    uint32_t phase = 0;
 
-    for (int set = blockIdx.x; set < ns; set += gridDim.x) {
-        if (set != (int) blockIdx.x) {
-#pragma unroll
-            for (int t = 0; t < (kH * S + NT - 1) / NT; ++t)
-                mreg[t] = tid + t * NT < kH * S ? __ldg(mask + ((size_t) b * max_sets + set) * kH * S + tid + t * NT) : 0.f;
-            if (tid < S) ireg = __ldg(idx + (((size_t) b * 2 + axis) * max_sets + set) * S + tid);
+    for (int set = blockIdx.x; set < ns; set += gridDim.x, phase ^= 1) {
+#ifdef DSVT_CORE_PHASE_PROFILE
+        const long long t_begin = clock64();
+#endif
+        const int off = __ldg(pv.set_off + set);
+        const int nu = __ldg(pv.set_off + set + 1) - off;          // distinct tokens of the set (clamped to the row capacity)
+        if (nu <= 0) { phase ^= 1; continue; }
+        const int nu4 = (nu + 3) & ~3;                              // keys are processed in chunks of 4
+        if (tid == 0) {
+            fence_proxy_async_smem();                               // earlier generic accesses to the tile -> async-proxy write
+            mbar_arrive_expect_tx(&kv_bar, (uint32_t) nu * kKvTok * 4);
+            bulk_g2s(sm, kvbuf + (size_t) off * kKvTok, (uint32_t) nu * kKvTok * 4, &kv_bar);
         }
-#pragma unroll
-        for (int t = 0; t < (kH * S + NT - 1) / NT; ++t)
-            if (tid + t * NT < kH * S) s_mask[tid + t * NT] = mreg[t];
-        if (tid < S) s_idx[tid] = ireg;
-        __syncthreads();
-
-        // token compaction, same rule as attention_fp32.cu: a slot that repeats the previous voxel AND is masked as a
-        // key by every head (getSet.cu:546-563) is the same token as its twin -- it is neither scored nor written twice
-        if (tid < 32) {
-            int base_u = 0;
-            for (int k0 = 0; k0 < S; k0 += 32) {
-                const int k = k0 + tid;
-                bool keep = false;
-                if (k < S) {
-                    keep = (k == 0) || (s_idx[k] != s_idx[k - 1]);
-                    if (!keep)
-#pragma unroll
-                        for (int hh = 0; hh < kH; ++hh) keep |= !(s_mask[hh * S + k] < -1e30f);
-                }
-                const unsigned bal = __ballot_sync(0xffffffffu, keep);
-                if (keep) {
-                    const int u = base_u + __popc(bal & ((1u << tid) - 1u));
-                    s_rows[u] = s_idx[k];
-                    s_slot[u] = k;
-                }
-                base_u += __popc(bal);
-            }
-            if (tid == 0) s_nu = base_u;
-        }
-        __syncthreads();
-        CP(1);
-        const int nu = s_nu;
-        {   // K and V rows -> shared memory: thread = (float4 column c4 of a 192-float row, row phase); no runtime
-            // divisions in the loops
-            constexpr int kCols = kC / 4, kPhases = NT / kCols;            // 48 columns, 3 phases (S = 36)
-            static_assert(NT % kCols == 0, "staging layout");
-            const int c4 = tid % kCols, hh = c4 / (kD / 4), d4 = c4 % (kD / 4);
-            const int off = hh * kHP + d4 * 4;
-            const int nu4 = (nu + 3) & ~3;                                 // keys are processed in chunks of 4
-            for (int j = tid / kCols; j < nu4; j += kPhases) {
-                float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;      // pad keys: zero rows, masked with -inf below
-                if (j < nu) {
-                    const float4* src = reinterpret_cast<const float4*>(qkv + (size_t) s_rows[j] * (3 * kC) + kC) + c4;
-                    kk = __ldg(src); vv = __ldg(src + kCols);
-                }
-                *reinterpret_cast<float4*>(Ks + j * kRowP + off) = kk;
-                *reinterpret_cast<float4*>(Vs + j * kRowP + off) = vv;
-            }
-        }
-        for (int t = tid; t < kH * S; t += NT) {                           // key mask in the log2 domain of the softmax
-            const int hh = t / S, j = t % S;
-            s_cmask[hh][j] = j < nu ? s_mask[hh * S + s_slot[j]] * kLog2e : -INFINITY;
+        for (int t = tid; t < kH * S; t += NT) s_mask[t] = __ldg(mask + ((size_t) b * max_sets + set) * kH * S + t);
+        if (tid < nu) {
+            const int2 tk = __ldg(pv.tok + (size_t) set * S + tid);
+            s_rows[tid] = tk.x;
+            s_slot[tid] = tk.y;
         }
         float2 q0[kD / 2], q1[kD / 2];
         if (i0 < nu) {
-            const float4* qp = reinterpret_cast<const float4*>(qkv + (size_t) s_rows[i0] * (3 * kC) + h * kD);
-            const float4* qp1 = reinterpret_cast<const float4*>(qkv + (size_t) s_rows[i1 < nu ? i1 : i0] * (3 * kC) + h * kD);
+            const float4* qp = reinterpret_cast<const float4*>(qbuf + (size_t) (off + i0) * kC + h * kD);
+            const float4* qp1 = reinterpret_cast<const float4*>(qbuf + (size_t) (off + (i1 < nu ? i1 : i0)) * kC + h * kD);
 #pragma unroll
             for (int d4 = 0; d4 < kD / 4; ++d4) {
                 const float4 t = __ldg(qp + d4), u = __ldg(qp1 + d4);
@@ -453,8 +530,20 @@ attn_core_kernel(const float* __restrict__ qkv, const int* __restrict__ idx, con
                 q1[2 * d4] = f2(u.x, u.y); q1[2 * d4 + 1] = f2(u.z, u.w);
             }
         }
+        for (int t = tid; t < (nu4 - nu) * (kKvTok / 4); t += NT)   // pad keys: zero rows (masked with -inf below)
+            reinterpret_cast<float4*>(sm + (size_t) nu * kKvTok)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
-        CP(2);
+        for (int t = tid; t < kH * S; t += NT) {                    // key mask in the log2 domain of the softmax
+            const int hh = t / S, j = t % S;
+            s_cmask[hh][j] = j < nu ? s_mask[hh * S + s_slot[j]] * kLog2e : -INFINITY;
+        }
+        mbar_wait(&kv_bar, phase);
+        __syncthreads();
+        if (set == (int) blockIdx.x) CP(2);
+#ifdef DSVT_CORE_PHASE_PROFILE
+        long long t_staged = 0;
+        if (tid == 0) { t_staged = clock64(); atomicAdd((unsigned long long*) &g_split_prof[36], (unsigned long long) (t_staged - t_begin)); }
+#endif
 
         if (i0 < nu) {
             float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
@@ -468,7 +557,7 @@ attn_core_kernel(const float* __restrict__ qkv, const int* __restrict__ idx, con
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     const int j = j0 + jj;
-                    const float4* kp = reinterpret_cast<const float4*>(Ks + j * kRowP + h * kHP);
+                    const float4* kp = reinterpret_cast<const float4*>(sm + j * kKvTok + hoff);
                     float2 a0 = f2(0.f, 0.f), a1 = f2(0.f, 0.f), b0 = f2(0.f, 0.f), b1 = f2(0.f, 0.f);
 #pragma unroll
                     for (int d4 = 0; d4 < kD / 4; ++d4) {
@@ -494,7 +583,7 @@ attn_core_kernel(const float* __restrict__ qkv, const int* __restrict__ idx, con
                     const float p0 = ex2(sc0[jj] - m0n), p1 = ex2(sc1[jj] - m1n);
                     l0 += p0; l1 += p1;
                     const float2 p02 = f2(p0, p0), p12 = f2(p1, p1);
-                    const float4* vp = reinterpret_cast<const float4*>(Vs + j * kRowP + h * kHP);
+                    const float4* vp = reinterpret_cast<const float4*>(sm + j * kKvTok + kKvRow + hoff);
 #pragma unroll
                     for (int d4 = 0; d4 < kD / 4; ++d4) {
                         const float4 vv = vp[d4];
@@ -506,27 +595,55 @@ attn_core_kernel(const float* __restrict__ qkv, const int* __restrict__ idx, con
                 m0 = m0n; m1 = m1n;
             }
             const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
-            float4* op = reinterpret_cast<float4*>(o + (size_t) s_rows[i0] * kC + h * kD);
+            const int r0 = s_rows[i0];
+            if (r0 >= 0 && r0 < max_pillars) {
+                float4* op = reinterpret_cast<float4*>(o + (size_t) r0 * kC + h * kD);
 #pragma unroll
-            for (int d4 = 0; d4 < kD / 4; ++d4)
-                op[d4] = make_float4(acc0[2 * d4].x * inv0, acc0[2 * d4].y * inv0, acc0[2 * d4 + 1].x * inv0, acc0[2 * d4 + 1].y * inv0);
-            if (i1 < nu) {
-                float4* op1 = reinterpret_cast<float4*>(o + (size_t) s_rows[i1] * kC + h * kD);
+                for (int d4 = 0; d4 < kD / 4; ++d4)
+                    op[d4] = make_float4(acc0[2 * d4].x * inv0, acc0[2 * d4].y * inv0, acc0[2 * d4 + 1].x * inv0, acc0[2 * d4 + 1].y * inv0);
+            }
+            const int r1 = i1 < nu ? s_rows[i1] : -1;
+            if (r1 >= 0 && r1 < max_pillars) {
+                float4* op1 = reinterpret_cast<float4*>(o + (size_t) r1 * kC + h * kD);
 #pragma unroll
                 for (int d4 = 0; d4 < kD / 4; ++d4)
                     op1[d4] = make_float4(acc1[2 * d4].x * inv1, acc1[2 * d4].y * inv1, acc1[2 * d4 + 1].x * inv1, acc1[2 * d4 + 1].y * inv1);
             }
         }
-        CP(3);
+        if (set == (int) blockIdx.x) CP(3);
         __syncthreads();        // shared memory is recycled by the next set
+#ifdef DSVT_CORE_PHASE_PROFILE
+        if (tid == 0) {
+            atomicAdd((unsigned long long*) &g_split_prof[37], (unsigned long long) (clock64() - t_staged));
+            atomicAdd((unsigned long long*) &g_split_prof[38], 1ull);
+            atomicAdd((unsigned long long*) &g_split_prof[39], (unsigned long long) nu);
+        }
+#endif
     }
 }
 
 template <int S>
-int launch_core(const dsvt_set_attention_params* p, const float* qkv, const int* idx, const float* mask,
-                const int* set_num, float* o, cudaStream_t st)
+int launch_plan(const dsvt_set_attention_params* p, const int* idx, const float* mask, const int* set_num, int* plan,
+                cudaStream_t st)
 {
-    const size_t smem = (size_t) 2 * S * kRowP * sizeof(float);
+    const size_t stride = plan_words(p->max_set_num, S, p->max_pillars_num);
+    const PlanView pv = plan_view(plan, p->max_set_num, p->max_pillars_num);
+    // voxel -> (set, u) map: -1 for voxels that are in no set
+    DSVT_CUDA(cudaMemset2DAsync(pv.vox_su, stride * sizeof(int), 0xFF, (size_t) p->max_pillars_num * sizeof(int), p->batch, st));
+    count_launch();
+    attn_plan_sets_kernel<S><<<dim3((p->max_set_num + 7) / 8, p->batch), 256, 0, st>>>(
+        idx, mask, set_num, plan, stride, p->max_set_num, p->max_pillars_num, p->axis_id);
+    DSVT_LAUNCH_CHECK();
+    attn_plan_scan_kernel<<<p->batch, 1024, 0, st>>>(set_num, plan, stride, p->max_set_num, p->max_pillars_num);
+    DSVT_LAUNCH_CHECK();
+    return DSVT_OK;
+}
+
+template <int S>
+int launch_core(const dsvt_set_attention_params* p, const float* qbuf, const float* kvbuf, const int* plan,
+                const float* mask, const int* set_num, float* o, cudaStream_t st)
+{
+    const size_t smem = (size_t) S * kKvTok * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         DSVT_CUDA(cudaFuncSetAttribute(attn_core_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -536,8 +653,9 @@ int launch_core(const dsvt_set_attention_params* p, const float* qkv, const int*
     }
     const int cap = 12 * sm_count();        // idle CTAs (sets >= set_num) cost a launch slot each: do not start thousands
     const int grid = p->max_set_num < cap ? p->max_set_num : cap;
-    attn_core_kernel<S><<<dim3(grid, p->batch), S / 2 * kH, smem, st>>>(qkv, idx, mask, set_num, o, p->max_set_num,
-                                                                       p->max_pillars_num, p->axis_id);
+    attn_core_kernel<S><<<dim3(grid, p->batch), S / 2 * kH, smem, st>>>(
+        qbuf, kvbuf, plan, plan_words(p->max_set_num, S, p->max_pillars_num), mask, set_num, o, p->max_set_num,
+        p->max_pillars_num);
     DSVT_LAUNCH_CHECK();
     return DSVT_OK;
 }
@@ -609,22 +727,52 @@ static int stage_mark(int i, cudaStream_t st) {
     return DSVT_OK;
 }
 
+static size_t plan_bytes_of(const dsvt_set_attention_params* p) {
+    return align_up((size_t) p->batch * plan_words(p->max_set_num, p->voxel_num_set, p->max_pillars_num) * sizeof(int), kWsAlign);
+}
+size_t attention_split_plan_bytes(const dsvt_set_attention_params* p) { return plan_bytes_of(p); }
+
 size_t attention_split_workspace(const dsvt_set_attention_params* p) {
-    // qkv [B, max_pillars, 576] f32 | o [B, max_pillars, 192] f32
-    return align_up((size_t) p->batch * p->max_pillars_num * 3 * kC * sizeof(float), kWsAlign) +
-           align_up((size_t) p->batch * p->max_pillars_num * kC * sizeof(float), kWsAlign);
+    // q [B, max_pillars, 192] | kv [B, max_pillars, 392] | o [B, max_pillars, 192] (f32) | a plan (used when the caller
+    // does not pass one)
+    const size_t rows = (size_t) p->batch * p->max_pillars_num;
+    return align_up(rows * kC * sizeof(float), kWsAlign) + align_up(rows * kKvTok * sizeof(float), kWsAlign) +
+           align_up(rows * kC * sizeof(float), kWsAlign) + plan_bytes_of(p);
 }
 
-int set_attention_split_fused(const dsvt_set_attention_params* p, const void* split_blob, const float* out_mul,
-                              bool split, const float* x, const float* pos, const int* idx, const float* mask,
-                              const int* set_num, const int* voxel_num, float* out, void* workspace,
-                              size_t workspace_bytes, cudaStream_t st)
-{
+static int split_check(const dsvt_set_attention_params* p) {
     if (p->channel_num != kC || p->num_heads != kH ||
         (p->voxel_num_set != 24 && p->voxel_num_set != 36 && p->voxel_num_set != 48)) {
         set_last_error("set attention (GEMM pipeline): only C=192, heads=8, set in {24,36,48} is built");
         return DSVT_ERR_UNSUPPORTED;
     }
+    return DSVT_OK;
+}
+
+int attention_split_plan(const dsvt_set_attention_params* p, const int* idx, const float* mask, const int* set_num,
+                         void* plan, size_t plan_bytes, cudaStream_t st)
+{
+    int rc = split_check(p);
+    if (rc != DSVT_OK) return rc;
+    if (!plan || ((uintptr_t) plan & 255) || plan_bytes < plan_bytes_of(p)) {
+        set_last_error("set attention plan: a 256-byte aligned buffer of %zu bytes is required (dsvt_set_attention_plan_size)",
+                       plan_bytes_of(p));
+        return DSVT_ERR_INVALID_ARGUMENT;
+    }
+    switch (p->voxel_num_set) {
+        case 24: return launch_plan<24>(p, idx, mask, set_num, static_cast<int*>(plan), st);
+        case 36: return launch_plan<36>(p, idx, mask, set_num, static_cast<int*>(plan), st);
+        default: return launch_plan<48>(p, idx, mask, set_num, static_cast<int*>(plan), st);
+    }
+}
+
+int set_attention_split_fused(const dsvt_set_attention_params* p, const void* split_blob, const float* out_mul,
+                              bool split, const float* x, const float* pos, const int* idx, const float* mask,
+                              const int* set_num, const int* voxel_num, float* out, const void* plan_in,
+                              void* workspace, size_t workspace_bytes, cudaStream_t st)
+{
+    int rc = split_check(p);
+    if (rc != DSVT_OK) return rc;
     if (!split_blob) {
         set_last_error("set attention (GEMM pipeline): weights were not prepared");
         return DSVT_ERR_INVALID_ARGUMENT;
@@ -638,9 +786,12 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
                        attention_split_workspace(p));
         return DSVT_ERR_INVALID_ARGUMENT;
     }
+    const size_t rows = (size_t) p->batch * p->max_pillars_num;
     WsCarver ws(workspace);
-    float* qkv = ws.take<float>((size_t) p->batch * p->max_pillars_num * 3 * kC);
-    float* o = ws.take<float>((size_t) p->batch * p->max_pillars_num * kC);
+    float* qbuf = ws.take<float>(rows * kC);
+    float* kvbuf = ws.take<float>(rows * kKvTok);
+    float* o = ws.take<float>(rows * kC);
+    int* own_plan = ws.take<int>(plan_bytes_of(p) / sizeof(int));
     const uint8_t* img = static_cast<const uint8_t*>(split_blob);
     const float* bias = reinterpret_cast<const float*>(img + (size_t) kRoles * kWRoleBytes);
 
@@ -650,6 +801,13 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
         DSVT_CUDA(cudaFuncSetAttribute(proj_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<false>::total));
         attr_set = true;
     }
+    if ((rc = stage_mark(0, st)) != DSVT_OK) return rc;
+    const int* plan = static_cast<const int*>(plan_in);
+    if (!plan) {                                   // stateless call: build the partition's plan first
+        if ((rc = attention_split_plan(p, idx, mask, set_num, own_plan, plan_bytes_of(p), st)) != DSVT_OK) return rc;
+        plan = own_plan;
+    }
+    const size_t plan_stride = plan_words(p->max_set_num, p->voxel_num_set, p->max_pillars_num);
     // persistent grids: one CTA per SM (divided among the batch), a multiple of the number of roles
     const int per_b = sm_count() / p->batch;
     const int grid_in = per_b >= 3 ? per_b / 3 * 3 : 3, grid_out = per_b >= 1 ? per_b : 1;
@@ -660,11 +818,14 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
         g.a1 = r < 2 ? pos : nullptr;
         g.wimg = img + (size_t) r * kWRoleBytes;
         g.bias = bias + r * kC;
-        g.out = qkv;
-        g.ld_out = 3 * kC;
-        g.col0 = r * kC;
+        g.out = r == 0 ? qbuf : kvbuf;             // rows in token order (set-major): see attn_core_kernel
+        g.ld_out = r == 0 ? kC : kKvTok;
+        g.col0 = r == 2 ? kKvRow : 0;
         g.out_mul = out_mul[r];
         g.post_mul = r == 0 ? 1.0f / sqrtf((float) (kC / kH)) : 1.0f;
+        g.plan = plan;
+        g.plan_stride = plan_stride;
+        g.pad_hi = r == 0 ? 0 : 4;
     }
     {
         GemmRole& g = out_roles.r[0];
@@ -674,32 +835,31 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
         g.out = out; g.ld_out = kC; g.col0 = 0;
         g.out_mul = out_mul[3];
         g.post_mul = 1.0f;
+        g.plan = nullptr; g.plan_stride = 0; g.pad_hi = 0;
         out_roles.r[1] = out_roles.r[2] = g;
     }
-    int rc = stage_mark(0, st);
-    if (rc != DSVT_OK) return rc;
     if (split) {
         proj_gemm_kernel<true><<<dim3(grid_in, p->batch), kThreadsG, Lay<true>::total, st>>>(
-            in_roles, 3, voxel_num, p->max_pillars_num, 0);
+            in_roles, 3, voxel_num, p->max_pillars_num, p->max_set_num, 0);
     } else {
         proj_gemm_kernel<false><<<dim3(grid_in, p->batch), kThreadsG, Lay<false>::total, st>>>(
-            in_roles, 3, voxel_num, p->max_pillars_num, 0);
+            in_roles, 3, voxel_num, p->max_pillars_num, p->max_set_num, 0);
     }
     DSVT_LAUNCH_CHECK();
     if ((rc = stage_mark(1, st)) != DSVT_OK) return rc;
     switch (p->voxel_num_set) {
-        case 24: rc = launch_core<24>(p, qkv, idx, mask, set_num, o, st); break;
-        case 36: rc = launch_core<36>(p, qkv, idx, mask, set_num, o, st); break;
-        default: rc = launch_core<48>(p, qkv, idx, mask, set_num, o, st); break;
+        case 24: rc = launch_core<24>(p, qbuf, kvbuf, plan, mask, set_num, o, st); break;
+        case 36: rc = launch_core<36>(p, qbuf, kvbuf, plan, mask, set_num, o, st); break;
+        default: rc = launch_core<48>(p, qbuf, kvbuf, plan, mask, set_num, o, st); break;
     }
     if (rc != DSVT_OK) return rc;
     if ((rc = stage_mark(2, st)) != DSVT_OK) return rc;
     if (split) {
         proj_gemm_kernel<true><<<dim3(grid_out, p->batch), kThreadsG, Lay<true>::total, st>>>(
-            out_roles, 1, voxel_num, p->max_pillars_num, p->zero_tails);
+            out_roles, 1, voxel_num, p->max_pillars_num, p->max_set_num, p->zero_tails);
     } else {
         proj_gemm_kernel<false><<<dim3(grid_out, p->batch), kThreadsG, Lay<false>::total, st>>>(
-            out_roles, 1, voxel_num, p->max_pillars_num, p->zero_tails);
+            out_roles, 1, voxel_num, p->max_pillars_num, p->max_set_num, p->zero_tails);
     }
     DSVT_LAUNCH_CHECK();
     return stage_mark(3, st);

@@ -40,8 +40,11 @@ class FrameWeights:
 class HotPathFrame:
     """Buffers + launch sequence for one frame slot (one CUDA stream owns one slot)."""
 
-    def __init__(self, cfg, weights, precision=capi.DSVT_ATTN_FP32, seed=0, device="cuda", fuse_ln=True):
+    def __init__(self, cfg, weights, precision=capi.DSVT_ATTN_FP32, seed=0, device="cuda", fuse_ln=True, share_plans=True):
         self.cfg, self.w, self.precision, self.fuse_ln = cfg, weights, precision, fuse_ln
+        # GEMM-pipeline attention: one plan per (window partition, axis), shared by the two layers that use it
+        self.share_plans = share_plans and precision in (capi.DSVT_ATTN_FP32_TC, capi.DSVT_ATTN_FP16_GEMM)
+        self.plans = {}
         g = torch.Generator(device="cpu").manual_seed(seed)
         mp, C, F = cfg.max_pillars_num, cfg.channel_num, cfg.ffn_channel_num
         self.points = torch.zeros(1, cfg.max_points_num, 4, dtype=torch.float32, device=device)
@@ -86,6 +89,13 @@ class HotPathFrame:
             self.wp[i](vox.coords, V)
             self.gs[i](self.wp[i].global_index, self.wp[i].coors_in_win, self.wp[i].voxel_num_in_win,
                        self.wp[i].win_num)
+        if self.share_plans:
+            for part in (0, 1):
+                for axis in (0, 1):
+                    gs = self.gs[part]
+                    self.plans[(part, axis)] = capi.set_attention_plan(
+                        gs.global_index_in_set[0], gs.mask_expand_0[0], gs.set_num, axis, cfg.max_pillars_num,
+                        cfg.num_heads, cfg.channel_num, out=self.plans.get((part, axis)))
         x, ln = self.x0, 0
         for blk in range(cfg.num_blocks):
             gs = self.gs[blk % 2]                      # blocks 0,2: 12x12 windows; 1,3: 24x24 shifted (:654-:1018)
@@ -93,7 +103,8 @@ class HotPathFrame:
             for enc in (0, 1):
                 capi.set_attention_fused(w.attn[blk * 2 + enc], x, self.pos[blk][enc], gs.global_index_in_set[0],
                                          gs.mask_expand_0[0], gs.set_num, V, axis=enc, out=self.attn_out,
-                                         precision=self.precision, workspace=self.attn_ws)
+                                         precision=self.precision, workspace=self.attn_ws,
+                                         plan=self.plans.get((blk % 2, enc)))
                 capi.layer_norm(self.attn_out, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=x,
                                 out=self.src); ln += 1                                     # norm1(y + x)   :669-676
                 capi.gelu(self.ffn_hidden, V, out=self.gelu_out)                           # :519 (inside the FFN)

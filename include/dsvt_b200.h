@@ -273,6 +273,24 @@ int dsvt_set_attention_fused_launch(const dsvt_set_attention_params* p, const ds
                                     const float* mask, const int32_t* set_num, const int32_t* voxel_num,
                                     float* out, void* workspace, size_t workspace_bytes, dsvt_stream_t stream);
 
+/*
+ * Attention plan (GEMM-pipeline precisions DSVT_ATTN_FP32_TC / DSVT_ATTN_FP16_GEMM): the set partition of one
+ * (frame, window partition, axis_id) in token order -- distinct tokens per set, their prefix sums and the voxel -> token
+ * map.  It depends only on global_index_in_set / mask / set_num, i.e. on the GetSetPlugin outputs, so ONE plan serves
+ * every attention layer that uses the partition (2 of the 8 layers each in the reference graph,
+ * src/dsvt-ai-trt.cpp:653-1116).  dsvt_set_attention_fused_launch builds it internally on every call (stateless);
+ * dsvt_set_attention_fused_planned_launch takes a prebuilt one (256-byte aligned, dsvt_set_attention_plan_size bytes).
+ */
+size_t dsvt_set_attention_plan_size(const dsvt_set_attention_params* p);
+int dsvt_set_attention_plan_launch(const dsvt_set_attention_params* p, const int32_t* global_index_in_set,
+                                   const float* mask, const int32_t* set_num, void* plan, size_t plan_bytes,
+                                   dsvt_stream_t stream);
+int dsvt_set_attention_fused_planned_launch(const dsvt_set_attention_params* p, const dsvt_attention_weights* w,
+                                            const float* x, const float* pos, const int32_t* global_index_in_set,
+                                            const float* mask, const int32_t* set_num, const int32_t* voxel_num,
+                                            float* out, const void* plan, void* workspace, size_t workspace_bytes,
+                                            dsvt_stream_t stream);
+
 /* ------------------------------------------------------------------------ *
  * (next #4) dense linear layer  y = x * W^T + b on tcgen05 -- replaces the TensorRT FullyConnected
  * layers next to the plugins (fullyConnected_gelu_fullyConnected, src/dsvt-ai-trt.cpp:494-529).

@@ -380,6 +380,32 @@ def test_set_attention_fused_frame(frame0, cfgs, precision):
             assert np.array_equal(sc.cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("precision", [3, 4])
+def test_set_attention_plan_reuse(frame0, cfgs, precision):
+    """A plan built once per (partition, axis) and passed to several layers gives exactly the stateless result."""
+    cfg = cfgs.REFERENCE
+    o = cpu.points2features(pad_points(frame0, cfg.max_points_num), len(frame0), cfg)
+    V = o["pillar_num"]
+    rng = np.random.default_rng(3)
+    owp = cpu.window_partition(o["coords"], V, cfg, 1)
+    ogs = cpu.get_set(owp["global_index"], owp["coors_in_win"], owp["voxel_num_in_win"], owp["win_num"], cfg, 1)
+    ns_t = torch.tensor([ogs["set_num"]], dtype=torch.int32, device="cuda")
+    v_t = torch.tensor([V], dtype=torch.int32, device="cuda")
+    idx, mask = dev(ogs["global_index_in_set"]), dev(ogs["mask_expand_0"])
+    for axis in (0, 1):
+        plan = capi.set_attention_plan(idx, mask, ns_t, axis, cfg.max_pillars_num)
+        for layer in range(2):                       # two layers, different weights / activations, same plan
+            x = np.zeros((cfg.max_pillars_num, 192), np.float32); pos = np.zeros_like(x)
+            x[:V] = rng.standard_normal((V, 192)); pos[:V] = rng.standard_normal((V, 192)) * 0.5
+            _, _, _, _, w = _attn_inputs(1, 1, seed=20 + layer)
+            W = capi.AttentionWeights(w["w_in"], w["b_in"], w["w_out"], w["b_out"])
+            a = capi.set_attention_fused(W, dev(x), dev(pos), idx, mask, ns_t, v_t, axis, precision=precision)
+            b = capi.set_attention_fused(W, dev(x), dev(pos), idx, mask, ns_t, v_t, axis, precision=precision, plan=plan)
+            assert torch.equal(a, b)
+            ref = capi.set_attention_fused(W, dev(x), dev(pos), idx, mask, ns_t, v_t, axis, precision=0)
+            assert (a[:V] - ref[:V]).abs().max().item() <= ATTN_TOL[precision]
+
+
 # ------------------------------------------------------------------------------------------------
 # FP16 tensor-core configuration (reference: USE_FP16, params.h:332).  Tolerance 1e-2 abs (BASELINE.json
 # configs[2]); FP16 operands carry 11-bit significands, the measured error is ~1e-3.

@@ -20,10 +20,12 @@ for which in (0, 1):
     gs = f.gs[which]
     ns = int(gs.set_num[0])
     ref = None
-    for prec in (0, 2, 3, 4):
+    plan = capi.set_attention_plan(gs.global_index_in_set[0], gs.mask_expand_0[0], gs.set_num, 0, cfg.max_pillars_num)
+    for prec, planned in ((0, False), (2, False), (3, False), (3, True), (4, True)):
         out = torch.zeros_like(f.attn_out)
         call = lambda: capi.set_attention_fused(w.attn[0], f.x0, f.pos[0][0], gs.global_index_in_set[0], gs.mask_expand_0[0],
-                                                gs.set_num, f.vox.pillar_num, axis=0, out=out, precision=prec, workspace=ws)
+                                                gs.set_num, f.vox.pillar_num, axis=0, out=out, precision=prec, workspace=ws,
+                                                plan=plan if planned else None)
         for _ in range(3): call()
         ts = []
         for _ in range(20):
@@ -33,4 +35,11 @@ for which in (0, 1):
             ts.append(e0.elapsed_time(e1) * 1e3)
         if prec == 0: ref = out.clone()
         err = (out[:V] - ref[:V]).abs().max().item()
-        print(f"partition {which}: {V} voxels {ns} sets  {names[prec]:26s} median {np.median(ts):8.1f} us  min {min(ts):8.1f} us  max|d| vs fp32 {err:.3e}")
+        stage = ""
+        if prec in (3, 4):
+            import ctypes
+            lib = capi._lib(); lib.dsvt_debug_attention_stage_timing(1)
+            flush.zero_(); call(); torch.cuda.synchronize()
+            buf = (ctypes.c_float * 3)(); lib.dsvt_debug_attention_stage_us(buf); lib.dsvt_debug_attention_stage_timing(0)
+            stage = f"  stages [plan+]qkv/core/out = {buf[0]:.1f}/{buf[1]:.1f}/{buf[2]:.1f} us" + (" (plan reused)" if planned else " (plan built per call)")
+        print(f"partition {which}: {V} voxels {ns} sets  {names[prec]:26s} median {np.median(ts):8.1f} us  min {min(ts):8.1f} us  max|d| vs fp32 {err:.3e}{stage}")

@@ -30,3 +30,6 @@ show(0, "QKV projection GEMM, CTA 3 (role Q, tiles 1, 50, 99):")
 show(40, "out-projection GEMM, CTA 3 (tile 3 + tail tiles):")
 c = t[32:36]
 print("core kernel, set 5:", "compaction", c[1]-c[0], "K/V staged", c[2]-c[0], "done", c[3]-c[0])
+
+if t[38] > 0 and t[38] < 10**7:
+    print(f"core kernel, sums over {t[38]} set iterations (all launches so far): avg staging {t[36]/t[38]:.0f} cycles, avg compute+store {t[37]/t[38]:.0f} cycles, avg tokens {t[39]/t[38]:.1f}")
