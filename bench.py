@@ -226,6 +226,16 @@ def plugin_breakdown(slot, cfg, peaks, reps=3):
         us = timed(lambda: f.wp[i](f.vox.coords, f.vox.pillar_num))
         res[f"window_partition_{i}"] = {"us": us, "bytes": 16 * V + 16 * V + 20 * V + 4 * W[i], "calls_per_frame": 1,
                                         "scope": "next"}
+    Pf = cfg.max_points_num_voxel_filter
+    for k, fch in enumerate(cfg.pfn_channels):
+        us = timed(lambda: capi.torch_scatter_max(w.pfn_out[k], f.vox.point_index_in_voxel[0], f.vox.point_num_in_voxel[0],
+                                                  f.vox.pillar_num, f.vox.point_num, max_point=f.max_point[k],
+                                                  max_voxel=f.max_voxel[k]))
+        res[f"torch_scatter_max_{fch}"] = {"us": us, "bytes": 4 * fch * (2 * Pc + V) + 4 * (Pc + V), "calls_per_frame": 1,
+                                           "scope": "next", "contract_bytes": 4 * fch * (Pc + Pf + cfg.max_pillars_num)}
+    us = timed(lambda: capi.map2bev(f.final, f.vox.coords[0], f.vox.pillar_num, cfg.grid_x, cfg.grid_y, out=f.bev))
+    res["map2bev"] = {"us": us, "bytes": 2 * 4 * C * V + 16 * V, "calls_per_frame": 1, "scope": "next",
+                      "contract_bytes": 4 * C * (cfg.grid_x * cfg.grid_y + V)}
     us = timed(lambda: capi.gelu(f.ffn_hidden, f.vox.pillar_num, out=f.gelu_out))
     res["gelu"] = {"us": us, "bytes": 2 * 4 * Fc * V, "calls_per_frame": 8}
     us = timed(lambda: capi.layer_norm(f.attn_out, f.vox.pillar_num, w.gamma[0], w.beta[0], cfg.layer_norm_eps, out=f.src))
@@ -484,8 +494,9 @@ def main():
         "data": "synthetic",
         "config": {"workload": f"BASELINE.json configs[1]: {args.points}-pt synthetic ring-lidar clouds, pillar "
                                f"{cfg.voxel_x:g}x{cfg.voxel_y:g} (grid {cfg.grid_x}), 4 DSVT blocks, set={cfg.voxel_num_set}, "
-                               f"{args.precision.upper()}; hot-path plugin sequence a1..a6 (+windowPartition), "
-                               "TensorRT-native glue (PFN, pos-embed, FFN linears, BEV backbone, head) NOT executed",
+                               f"{args.precision.upper()}; all ten reference plugins (a1..a6 + windowPartition, scatter-max x2, map2bev; gather / scatter "
+                               "fused into the set attention), TensorRT-native glue (PFN / pos-embed / FFN linears, BEV backbone, "
+                               "head) NOT executed",
                    "frames_per_step_per_gpu": F, "streams_per_gpu": S, "parallelism": f"frame-parallel x{world}",
                    "frame_stats": stats,
                    "l2": "no explicit flush: each step touches F frames x ~0.5 GB of distinct buffers >> 126 MB L2"},

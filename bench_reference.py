@@ -43,6 +43,9 @@ class ReferenceFrame:
         self.gather = [plg.add_get_value_by_index_op(gv, mw, S, C, a) for a in (0, 1)]
         self.scatter = [plg.add_map_set_feature2voxel_op(ms, mw, S, C, a, mp) for a in (0, 1)]
         self.gelu = plg.add_gelu_op(lib("gelu"), mp, F)
+        sml = lib("torchScatterMax")
+        self.smax = [plg.add_torch_scatter_max(sml, cfg.max_points_num_voxel_filter, mp, f) for f in cfg.pfn_channels]
+        self.m2b = plg.add_map_2_bev_op(lib("map2bev"), mp, C, cfg.grid_x, cfg.grid_y)
         ll = lib("layerNorm")
         self.ln = [plg.add_layer_norm_op(ll, mp, C, (1.0 + 0.1 * rng.standard_normal(C)).astype(np.float32),
                                          (0.1 * rng.standard_normal(C)).astype(np.float32))
@@ -59,6 +62,8 @@ class ReferenceFrame:
         self.host_points = torch.from_numpy(cloud).pin_memory()
         self.host_boxes = torch.empty(cfg.max_top_k, 9).pin_memory()
         self.host_valid = torch.empty(1, dtype=torch.int32).pin_memory()
+        g2 = torch.Generator().manual_seed(1)
+        self.pfn_out = [torch.randn(1, cfg.max_points_num_voxel_filter, f, generator=g2).to(dev) for f in cfg.pfn_channels]
         self.x0 = torch.randn(1, mp, C, generator=g).to(dev)
         self.pos = [[torch.randn(1, mp, C, generator=g).mul_(0.5).to(dev) for _ in range(2)] for _ in range(cfg.num_blocks)]
         self.ffn_hidden = torch.randn(1, mp, F, generator=g).to(dev)
@@ -100,6 +105,8 @@ class ReferenceFrame:
         cfg, torch = self.cfg, self.torch
         vo = self.call("vox", self.vox, [self.points, self.points_size])
         V = vo[4]
+        for k in range(len(self.smax)):
+            self.call(f"sm{k}", self.smax[k], [self.pfn_out[k], vo[1], vo[3], V])
         parts = []
         for i in (0, 1):
             w = self.call(f"wp{i}", self.wp[i], [vo[2], V])
@@ -117,6 +124,7 @@ class ReferenceFrame:
                 src = self.call(f"ln{ln}", self.ln[ln], [src + self.ffn_out, V])[0]; ln += 1
                 x = self.call(f"ln{ln}", self.ln[ln], [src + x, V])[0]; ln += 1
             x = self.call(f"ln{ln}", self.ln[ln], [x + x_in, V])[0]; ln += 1
+        self.call("m2b", self.m2b, [x, vo[2], V])
         self.boxes, self.valid = self.call("fb", self.fb, self.cand)
         return self
 

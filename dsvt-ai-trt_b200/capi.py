@@ -413,3 +413,46 @@ class Linear:
             self.close()
         except Exception:
             pass
+
+
+class ScatterMaxParams(Structure):
+    _fields_ = [("batch", c_int32), ("max_points_num", c_int32), ("max_pillars_num", c_int32), ("feature_num", c_int32),
+                ("max_num_points_per_voxel", c_int32), ("zero_tails", c_int32)]
+
+
+class Map2BevParams(Structure):
+    _fields_ = [("batch", c_int32), ("max_pillars_num", c_int32), ("channel_num", c_int32), ("grid_size_x", c_int32),
+                ("grid_size_y", c_int32)]
+
+
+def torch_scatter_max(point_features, point_index_in_voxel, point_num_in_voxel, voxel_num, point_num=None,
+                      max_point=None, max_voxel=None, zero_tails=1):
+    """TorchScatterMaxPlugin: per-pillar channel-wise max, broadcast back to the pillar's point rows."""
+    _need(point_features, torch.float32, "point_features")
+    _need(point_index_in_voxel, torch.int32, "point_index_in_voxel")
+    B = point_features.shape[0] if point_features.dim() == 3 else 1
+    max_points, F = point_features.shape[-2], point_features.shape[-1]
+    max_pillars, npv = point_index_in_voxel.shape[-2], point_index_in_voxel.shape[-1]
+    max_point = torch.empty_like(point_features) if max_point is None else max_point
+    vshape = (B, max_pillars, F) if point_features.dim() == 3 else (max_pillars, F)
+    max_voxel = torch.empty(vshape, dtype=torch.float32, device=point_features.device) if max_voxel is None else max_voxel
+    p = ScatterMaxParams(B, max_points, max_pillars, F, npv, zero_tails)
+    rc = _lib().dsvt_torch_scatter_max_launch(ctypes.byref(p), _ptr(point_features), _ptr(point_index_in_voxel),
+                                              _ptr(point_num_in_voxel), _ptr(voxel_num), _ptr(point_num),
+                                              _ptr(max_point), _ptr(max_voxel), _stream())
+    _check(rc, "dsvt_torch_scatter_max_launch")
+    return max_point, max_voxel
+
+
+def map2bev(voxel_features, coords, voxel_num, grid_x, grid_y, out=None):
+    """Map2BevPlugin: dense [grid_y, grid_x, C] BEV map from the pillar rows."""
+    _need(voxel_features, torch.float32, "voxel_features")
+    _need(coords, torch.int32, "coords")
+    B = voxel_features.shape[0] if voxel_features.dim() == 3 else 1
+    max_pillars, C = voxel_features.shape[-2], voxel_features.shape[-1]
+    shape = (B, grid_y, grid_x, C) if voxel_features.dim() == 3 else (grid_y, grid_x, C)
+    out = torch.empty(shape, dtype=torch.float32, device=voxel_features.device) if out is None else out
+    p = Map2BevParams(B, max_pillars, C, grid_x, grid_y)
+    rc = _lib().dsvt_map2bev_launch(ctypes.byref(p), _ptr(voxel_features), _ptr(coords), _ptr(voxel_num), _ptr(out), _stream())
+    _check(rc, "dsvt_map2bev_launch")
+    return out

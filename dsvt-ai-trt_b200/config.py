@@ -34,6 +34,7 @@ class HotPathConfig:
     channel_num: int = 192
     ffn_channel_num: int = 384
     num_blocks: int = 4
+    pfn_channels: tuple = (96, 192)     # PFN_LAYER_0/1_OUT_CHANNEL (params.h:43-44): feature widths of the two scatter-max calls
     layer_norm_eps: float = 0.0          # effective value in the reference
     # post-processing (params.h:327-328)
     max_top_k: int = 500

@@ -835,6 +835,131 @@ private:
     dsvt_attention_weights* dev_ = nullptr;
 };
 
+// =================================================================================================
+// TorchScatterMaxPlugin  (reference plugins/src/torchScatterMax.cu; fields :388-390, serialised 3 x i32 :346-352)
+// Inputs : point_features [B,max_points,F] f32, point_index_in_voxel [B,max_pillars,npv] i32,
+//          point_num_in_voxel [B,max_pillars] i32, voxel_num [B] i32  (+ optional 5th input: point_num [B] i32, the
+//          voxeliser's row count -- lets the plugin zero-fill only the unused rows instead of the whole tensor)
+// Outputs: max_point_features [B,max_points,F], max_voxel_features [B,max_pillars,F]  (:116-141)
+class TorchScatterMaxPlugin final : public PluginBase {
+public:
+    static constexpr const char* kName = "TorchScatterMaxPlugin";
+    static FieldList field_list() {
+        return {{"max_points_num", PluginFieldType::kINT32}, {"max_pillars_num", PluginFieldType::kINT32},
+                {"feature_num", PluginFieldType::kINT32}};
+    }
+    TorchScatterMaxPlugin(int max_points, int max_pillars, int feature_num)
+        : max_points_(max_points), max_pillars_(max_pillars), feature_num_(feature_num) {}
+    static IPluginV2* from_fields(const PluginFieldCollection* fc) {
+        return new (std::nothrow) TorchScatterMaxPlugin(field_int(fc, "max_points_num"), field_int(fc, "max_pillars_num"),
+                                                        field_int(fc, "feature_num"));
+    }
+    static IPluginV2* from_bytes(const void* data, size_t len) {
+        Reader r(data, len);
+        const int a = r.get<int>(), b = r.get<int>(), c = r.get<int>();
+        return r.ok() ? new (std::nothrow) TorchScatterMaxPlugin(a, b, c) : nullptr;
+    }
+    size_t getSerializationSize() const noexcept override { return 3 * sizeof(int); }
+    void serialize(void* buf) const noexcept override {
+        Writer w(buf);
+        w.put(max_points_); w.put(max_pillars_); w.put(feature_num_);
+    }
+    IPluginV2DynamicExt* clone() const noexcept override {
+        auto* c = new (std::nothrow) TorchScatterMaxPlugin(max_points_, max_pillars_, feature_num_);
+        if (c) { c->setPluginNamespace(ns_.c_str()); c->nb_inputs_seen_ = nb_inputs_seen_; }
+        return c;
+    }
+    const char* getPluginType() const noexcept override { return kName; }
+    int32_t getNbOutputs() const noexcept override { return 2; }
+    DimsExprs getOutputDimensions(int32_t index, const DimsExprs* in, int32_t, IExprBuilder& b) noexcept override {
+        return dims(b, in[0].d[0], {index == 0 ? max_points_ : max_pillars_, feature_num_});
+    }
+    bool supportsFormatCombination(int32_t pos, const PluginTensorDesc* io, int32_t nbIn, int32_t nbOut) noexcept override {
+        if (pos < 0 || pos >= nbIn + nbOut || io[pos].format != TensorFormat::kLINEAR) return false;
+        return io[pos].type == ((pos >= 1 && pos < nbIn) ? I : F);
+    }
+    DataType getOutputDataType(int32_t, const DataType*, int32_t) const noexcept override { return F; }
+    void configurePlugin(const DynamicPluginTensorDesc*, int32_t nbInputs, const DynamicPluginTensorDesc*,
+                         int32_t) noexcept override { nb_inputs_seen_ = nbInputs; }
+    int32_t enqueue(const PluginTensorDesc* in, const PluginTensorDesc*, const void* const* inputs,
+                    void* const* outputs, void*, cudaStream_t stream) noexcept override {
+        dsvt_torch_scatter_max_params p{};
+        p.batch = batch_of(in); p.max_points_num = max_points_; p.max_pillars_num = max_pillars_;
+        p.feature_num = feature_num_; p.zero_tails = 1;
+        p.max_num_points_per_voxel = in[1].dims.nbDims >= 3 ? in[1].dims.d[2] : 48;    // POINTS_NUM_PER_VOXEL
+        const int32_t* point_num = nb_inputs_seen_ == 5 ? static_cast<const int32_t*>(inputs[4]) : nullptr;
+        return report(dsvt_torch_scatter_max_launch(&p, static_cast<const float*>(inputs[0]),
+                                                    static_cast<const int32_t*>(inputs[1]), static_cast<const int32_t*>(inputs[2]),
+                                                    static_cast<const int32_t*>(inputs[3]), point_num,
+                                                    static_cast<float*>(outputs[0]), static_cast<float*>(outputs[1]), stream), kName);
+    }
+protected:
+    const std::vector<DataType>& io_types() const override {
+        static const std::vector<DataType> t{F, I, I, I, F, F};
+        return t;
+    }
+    size_t nb_inputs() const override { return 4; }
+private:
+    int max_points_, max_pillars_, feature_num_;
+    int nb_inputs_seen_ = 4;
+};
+
+// =================================================================================================
+// Map2BevPlugin  (reference plugins/src/map2bev.cu; fields :383-386, serialised 4 x i32 :352-359)
+// Inputs : voxel_features [B,max_pillars,C] f32, coords [B,max_pillars,4] i32, valid_voxel_num [B] i32
+// Output : map [B,grid_size_x,grid_size_y,C] f32 as the reference declares it (:141-145); indexed y-major (:263)
+class Map2BevPlugin final : public PluginBase {
+public:
+    static constexpr const char* kName = "Map2BevPlugin";
+    static FieldList field_list() {
+        return {{"max_pillars_num", PluginFieldType::kINT32}, {"channel_num", PluginFieldType::kINT32},
+                {"grid_size_x", PluginFieldType::kINT32}, {"grid_size_y", PluginFieldType::kINT32}};
+    }
+    explicit Map2BevPlugin(const dsvt_map2bev_params& p) : p_(p) {}
+    static IPluginV2* from_fields(const PluginFieldCollection* fc) {
+        dsvt_map2bev_params p{1, field_int(fc, "max_pillars_num"), field_int(fc, "channel_num"),
+                              field_int(fc, "grid_size_x"), field_int(fc, "grid_size_y")};
+        return new (std::nothrow) Map2BevPlugin(p);
+    }
+    static IPluginV2* from_bytes(const void* data, size_t len) {
+        Reader r(data, len);
+        dsvt_map2bev_params p{};
+        p.batch = 1; p.max_pillars_num = r.get<int>(); p.channel_num = r.get<int>();
+        p.grid_size_x = r.get<int>(); p.grid_size_y = r.get<int>();
+        return r.ok() ? new (std::nothrow) Map2BevPlugin(p) : nullptr;
+    }
+    size_t getSerializationSize() const noexcept override { return 4 * sizeof(int); }
+    void serialize(void* buf) const noexcept override {
+        Writer w(buf);
+        w.put(p_.max_pillars_num); w.put(p_.channel_num); w.put(p_.grid_size_x); w.put(p_.grid_size_y);
+    }
+    IPluginV2DynamicExt* clone() const noexcept override {
+        auto* c = new (std::nothrow) Map2BevPlugin(p_);
+        if (c) c->setPluginNamespace(ns_.c_str());
+        return c;
+    }
+    const char* getPluginType() const noexcept override { return kName; }
+    int32_t getNbOutputs() const noexcept override { return 1; }
+    DimsExprs getOutputDimensions(int32_t, const DimsExprs* in, int32_t, IExprBuilder& b) noexcept override {
+        return dims(b, in[0].d[0], {p_.grid_size_x, p_.grid_size_y, p_.channel_num});
+    }
+    int32_t enqueue(const PluginTensorDesc* in, const PluginTensorDesc*, const void* const* inputs,
+                    void* const* outputs, void*, cudaStream_t stream) noexcept override {
+        dsvt_map2bev_params p = p_;
+        p.batch = batch_of(in);
+        return report(dsvt_map2bev_launch(&p, static_cast<const float*>(inputs[0]), static_cast<const int32_t*>(inputs[1]),
+                                          static_cast<const int32_t*>(inputs[2]), static_cast<float*>(outputs[0]), stream), kName);
+    }
+protected:
+    const std::vector<DataType>& io_types() const override {
+        static const std::vector<DataType> t{F, I, I, F};
+        return t;
+    }
+    size_t nb_inputs() const override { return 3; }
+private:
+    dsvt_map2bev_params p_;
+};
+
 // registration: from the library only (the reference registers from two images)
 using Points2FeaturesPluginCreator = CreatorBase<Points2FeaturesPlugin>;
 using WindowPartitionPluginCreator = CreatorBase<WindowPartitionPlugin>;
@@ -846,6 +971,8 @@ using GetValueByIndexPluginCreator = CreatorBase<GetValueByIndexPlugin>;
 using MapSetFeature2VoxelPluginCreator = CreatorBase<MapSetFeature2VoxelPlugin>;
 using SetAttentionPluginCreator = CreatorBase<SetAttentionPlugin>;
 using SetAttentionFusedPluginCreator = CreatorBase<SetAttentionFusedPlugin>;
+using TorchScatterMaxPluginCreator = CreatorBase<TorchScatterMaxPlugin>;
+using Map2BevPluginCreator = CreatorBase<Map2BevPlugin>;
 
 REGISTER_TENSORRT_PLUGIN(Points2FeaturesPluginCreator);
 REGISTER_TENSORRT_PLUGIN(WindowPartitionPluginCreator);
@@ -857,5 +984,7 @@ REGISTER_TENSORRT_PLUGIN(GetValueByIndexPluginCreator);
 REGISTER_TENSORRT_PLUGIN(MapSetFeature2VoxelPluginCreator);
 REGISTER_TENSORRT_PLUGIN(SetAttentionPluginCreator);
 REGISTER_TENSORRT_PLUGIN(SetAttentionFusedPluginCreator);
+REGISTER_TENSORRT_PLUGIN(TorchScatterMaxPluginCreator);
+REGISTER_TENSORRT_PLUGIN(Map2BevPluginCreator);
 
 }  // namespace dsvt_plugins

@@ -1,11 +1,13 @@
 """One "hot-path frame": the plugin sequence of SURVEY.md section 8(a) in the reference's graph order
 (src/dsvt-ai-trt.cpp:571-1120, :1684) for ONE point cloud, every launch going through the C ABI.
 
-    a1 Points2Features -> WindowPartition x2 -> a2 GetSet x2
+    a1 Points2Features -> [PFN linear 10->96: glue] -> TorchScatterMax(96) -> [PFN linear 192->192: glue]
+                       -> TorchScatterMax(192) -> WindowPartition x2 -> a2 GetSet x2
     4 DSVT blocks x 2 encoders: a3 set attention (gather/scatter fused) -> a5 LayerNorm(y + x)
                                 -> [FFN linear 192->384: TensorRT-native glue, NOT part of the hot path]
                                 -> a4 GELU -> [FFN linear 384->192: glue] -> a5 LayerNorm -> a5 LayerNorm
                  + a5 LayerNorm per block                                   (7 LayerNorms per block, 28 per frame)
+    Map2Bev (dense BEV map for the 2-D backbone)
     a6 FilterBoxByScore on the CenterHead's top-500 candidates
 
 The TensorRT-native layers between the plugins (PFN, pos-embed MLPs, FFN linears, BEV backbone, head; SURVEY.md
@@ -32,6 +34,9 @@ class FrameWeights:
                 (rng.standard_normal(3 * C) * 0.02).astype(np.float32),
                 (rng.standard_normal((C, C)) * 0.06).astype(np.float32),
                 (rng.standard_normal(C) * 0.02).astype(np.float32), C, cfg.num_heads))
+        # stand-ins for the two PFN layer outputs (src/dsvt-ai-trt.cpp:577-590), shared by all frame slots (read-only)
+        g = torch.Generator(device="cpu").manual_seed(seed + 1)
+        self.pfn_out = [torch.randn(cfg.max_points_num_voxel_filter, f, generator=g).to(device) for f in cfg.pfn_channels]
         n_ln = cfg.num_blocks * 7
         self.gamma = torch.from_numpy((1.0 + 0.1 * rng.standard_normal((n_ln, C))).astype(np.float32)).to(device)
         self.beta = torch.from_numpy((0.1 * rng.standard_normal((n_ln, C))).astype(np.float32)).to(device)
@@ -70,6 +75,10 @@ class HotPathFrame:
         self.x_a = torch.empty(mp, C, device=device)
         self.x_b = torch.empty(mp, C, device=device)
         self.blk_out = [torch.empty(mp, C, device=device) for _ in range(2)]
+        # VFE glue plugins (TorchScatterMaxPlugin x2) and the BEV map (Map2BevPlugin)
+        self.max_point = [torch.empty(cfg.max_points_num_voxel_filter, f, device=device) for f in cfg.pfn_channels]
+        self.max_voxel = [torch.empty(mp, f, device=device) for f in cfg.pfn_channels]
+        self.bev = torch.empty(cfg.grid_y, cfg.grid_x, C, device=device)
         self.boxes = torch.empty(1, cfg.max_top_k, 9, device=device)
         self.valid = torch.empty(1, dtype=torch.int32, device=device)
         self.launches_per_frame = None
@@ -80,11 +89,14 @@ class HotPathFrame:
         self.points_size.fill_(n)
 
     def run(self):
-        """Enqueue the frame's 49 plugin invocations on the current stream."""
+        """Enqueue the frame's plugin invocations on the current stream."""
         cfg, w = self.cfg, self.w
         before = capi.launch_count()
         vox = self.vox(self.points, self.points_size)
         V = vox.pillar_num
+        for k in range(len(cfg.pfn_channels)):             # :580-590 (the voxeliser's row count lets it skip the full clear)
+            capi.torch_scatter_max(self.w.pfn_out[k], vox.point_index_in_voxel[0], vox.point_num_in_voxel[0], V,
+                                   vox.point_num, max_point=self.max_point[k], max_voxel=self.max_voxel[k])
         for i in (0, 1):
             self.wp[i](vox.coords, V)
             self.gs[i](self.wp[i].global_index, self.wp[i].coors_in_win, self.wp[i].voxel_num_in_win,
@@ -128,6 +140,7 @@ class HotPathFrame:
                 x = nxt
             x = self.blk_out[blk % 2]
         self.final = x
+        capi.map2bev(x, vox.coords[0], V, cfg.grid_x, cfg.grid_y, out=self.bev)          # :1128
         capi.filter_box(cfg, *self.cand, boxes=self.boxes, valid=self.valid)
         self.launches_per_frame = capi.launch_count() - before
         return self

@@ -267,3 +267,16 @@ def add_set_attention_fused_op(lib, max_win_num, voxel_num_set, channel_num, num
         "in_proj_weight": np.asarray(in_proj_weight, np.float32), "in_proj_bias": np.asarray(in_proj_bias, np.float32),
         "out_proj_weight": np.asarray(out_proj_weight, np.float32),
         "out_proj_bias": np.asarray(out_proj_bias, np.float32)})
+
+
+def add_torch_scatter_max(lib, max_points_num, max_pillars_num, feature_num):
+    """include/plugin_helper.h:125 (inputs: point_features, point_index_in_voxel, point_num_in_voxel, voxel_num)."""
+    return lib.create("TorchScatterMaxPlugin", {
+        "max_points_num": max_points_num, "max_pillars_num": max_pillars_num, "feature_num": feature_num})
+
+
+def add_map_2_bev_op(lib, max_pillars_num, channel_num, grid_size_x, grid_size_y):
+    """include/plugin_helper.h:371 (inputs: voxel_features, coords, valid_voxel_num)."""
+    return lib.create("Map2BevPlugin", {
+        "max_pillars_num": max_pillars_num, "channel_num": channel_num, "grid_size_x": grid_size_x,
+        "grid_size_y": grid_size_y})

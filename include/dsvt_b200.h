@@ -303,6 +303,43 @@ void dsvt_linear_weights_destroy(dsvt_linear_weights* w);
 /* x [M,K] f32 (device) -> y [M,N] f32 (device) */
 int dsvt_linear_launch(const dsvt_linear_weights* w, const float* x, int32_t M, float* y, dsvt_stream_t stream);
 
+/* ------------------------------------------------------------------------ *
+ * (next #3) TorchScatterMaxPlugin::enqueue     plugins/src/torchScatterMax.cu:282-309 (kernel :201-262)
+ *           Map2BevPlugin::enqueue             plugins/src/map2bev.cu:283-312 (kernel :250-265)
+ * ------------------------------------------------------------------------ */
+typedef struct dsvt_torch_scatter_max_params {
+    int32_t batch;
+    int32_t max_points_num;            /* rows of point_features (MAX_POINTS_NUM_1 30000) */
+    int32_t max_pillars_num;
+    int32_t feature_num;               /* 96 / 192 (PFN layer outputs); multiple of 4, <= 256 */
+    int32_t max_num_points_per_voxel;  /* row stride of point_index_in_voxel (POINTS_NUM_PER_VOXEL 48) */
+    int32_t zero_tails;
+} dsvt_torch_scatter_max_params;
+/*
+ * in : point_features [B,max_points_num,F] f32 ; point_index_in_voxel [B,max_pillars_num,npv] i32 ;
+ *      point_num_in_voxel [B,max_pillars_num] i32 ; voxel_num [B] i32 ;
+ *      point_num [B] i32 or NULL -- the voxeliser's row count (Points2Features output 5).  With it only the rows
+ *      [point_num, max_points_num) are zero-filled; without it the whole tensor is cleared first, as the reference does.
+ * out: max_point_features [B,max_points_num,F] (every point row = its pillar's channel-wise max) ;
+ *      max_voxel_features [B,max_pillars_num,F]
+ */
+int dsvt_torch_scatter_max_launch(const dsvt_torch_scatter_max_params* p, const float* point_features,
+                                  const int32_t* point_index_in_voxel, const int32_t* point_num_in_voxel,
+                                  const int32_t* voxel_num, const int32_t* point_num,
+                                  float* max_point_features, float* max_voxel_features, dsvt_stream_t stream);
+
+typedef struct dsvt_map2bev_params {
+    int32_t batch;
+    int32_t max_pillars_num;
+    int32_t channel_num;
+    int32_t grid_size_x, grid_size_y;
+} dsvt_map2bev_params;
+/* in : voxel_features [B,max_pillars_num,C] f32 ; coords [B,max_pillars_num,4] i32 (0,0,y,x) ; voxel_num [B]
+ * out: map_features [B,grid_size_y,grid_size_x,C] f32, zero where no pillar (the reference declares the shape as
+ *      [B,grid_size_x,grid_size_y,C] and indexes it y-major, map2bev.cu:141-145,:263) */
+int dsvt_map2bev_launch(const dsvt_map2bev_params* p, const float* voxel_features, const int32_t* coords,
+                        const int32_t* voxel_num, float* map_features, dsvt_stream_t stream);
+
 /* standalone forms of the two gather/scatter plugins (next #2), kept for graph compatibility */
 int dsvt_get_value_by_index_launch(const dsvt_set_attention_params* p, const float* x, const float* pos,
                                    const int32_t* global_index_in_set, const int32_t* set_num,

@@ -31,6 +31,8 @@ REF_PLUGINS = [
     ("layerNorm", "LayerNormPlugin"),
     ("gelu", "GeluPlugin"),
     ("filterBoxByScore", "FilterBoxByScorePlugin"),
+    ("torchScatterMax", "TorchScatterMaxPlugin"),
+    ("map2bev", "Map2BevPlugin"),
 ]
 
 

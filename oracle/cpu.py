@@ -151,3 +151,22 @@ def set_attention(q, k, v, mask, n_sets, w_in, b_in, w_out, b_out, heads=8):
                                     _p(_f32(b_out)), _p(out))
     assert rc == 0
     return out
+
+
+def torch_scatter_max(point_features, point_index_in_voxel, point_num_in_voxel, voxel_num):
+    f, piv, pnv = _f32(point_features), _i32(point_index_in_voxel), _i32(point_num_in_voxel)
+    max_points, F = f.shape
+    max_pillars, npv = piv.shape
+    mp = np.zeros((max_points, F), np.float32)
+    mv = np.zeros((max_pillars, F), np.float32)
+    lib().oracle_torch_scatter_max(_p(f), _p(piv), _p(pnv), c_int(int(voxel_num)), c_int(max_points), c_int(max_pillars),
+                                   c_int(npv), c_int(F), _p(mp), _p(mv))
+    return mp, mv
+
+
+def map2bev(voxel_features, coords, voxel_num, gx, gy):
+    f, co = _f32(voxel_features), _i32(coords)
+    max_pillars, C = f.shape
+    out = np.zeros((gy, gx, C), np.float32)
+    lib().oracle_map2bev(_p(f), _p(co), c_int(int(voxel_num)), c_int(max_pillars), c_int(C), c_int(gx), c_int(gy), _p(out))
+    return out

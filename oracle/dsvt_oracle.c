@@ -431,3 +431,44 @@ ORACLE_API int oracle_set_attention(const float* q, const float* k, const float*
 }
 
 ORACLE_API int oracle_abi_version(void) { return 1; }
+
+/* ------------------------------------------------------------------------- *
+ * next #3  torchScatterMax.cu:201-262 (generateMax_kernel) after the memsets of :300-301
+ * ------------------------------------------------------------------------- */
+ORACLE_API void oracle_torch_scatter_max(const float* point_features, const int* point_index_in_voxel,
+                                         const int* point_num_in_voxel, int voxel_num, int max_points, int max_pillars,
+                                         int npv, int F, float* max_point_features, float* max_voxel_features)
+{
+    memset(max_point_features, 0, (size_t) max_points * F * sizeof(float));        /* :300 */
+    memset(max_voxel_features, 0, (size_t) max_pillars * F * sizeof(float));       /* :301 */
+    if (voxel_num > max_pillars) voxel_num = max_pillars;
+    for (int v = 0; v < voxel_num; ++v) {
+        const int* idx = point_index_in_voxel + (size_t) v * npv;
+        const int n = point_num_in_voxel[v];
+        for (int k = 0; k < F; ++k) {
+            float m = -1000000.0f;                                                 /* :216 */
+            for (int i = 0; i < n; ++i) {
+                const float f = point_features[(size_t) idx[i] * F + k];
+                if (f > m) m = f;                                                  /* :230-238 */
+            }
+            max_voxel_features[(size_t) v * F + k] = m;                            /* :245 */
+            for (int i = 0; i < n; ++i) max_point_features[(size_t) idx[i] * F + k] = m;   /* :251-259 */
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------- *
+ * next #3  map2bev.cu:250-265 (Map2Bev_kernel) after the memset of :305
+ * ------------------------------------------------------------------------- */
+ORACLE_API void oracle_map2bev(const float* voxel_features, const int* coords, int voxel_num, int max_pillars, int C,
+                               int gx, int gy, float* map)
+{
+    memset(map, 0, (size_t) gx * gy * C * sizeof(float));                          /* :305 */
+    if (voxel_num > max_pillars) voxel_num = max_pillars;
+    for (int v = 0; v < voxel_num; ++v) {
+        const unsigned y = (unsigned) coords[(size_t) v * 4 + 2], x = (unsigned) coords[(size_t) v * 4 + 3];   /* :258-260 */
+        if (y >= (unsigned) gy || x >= (unsigned) gx) continue;                    /* the reference writes out of bounds */
+        for (int c = 0; c < C; ++c)
+            map[((size_t) y * gx + x) * C + c] = voxel_features[(size_t) v * C + c];   /* :263 */
+    }
+}

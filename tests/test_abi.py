@@ -44,6 +44,8 @@ REFERENCE_FIELDS = {   # creator field lists of the reference (plugins/src/*.cu,
     "WindowPartitionPlugin": ["max_win_num", "max_voxel_num_per_win", "sparse_shape", "win_shape", "shift_list"],
     "GetValueByIndexPlugin": ["max_win_num", "voxel_num_set", "channel_num", "axis_id"],
     "MapSetFeature2VoxelPlugin": ["max_win_num", "voxel_num_set", "channel_num", "axis_id", "max_pillars_num"],
+    "TorchScatterMaxPlugin": ["max_points_num", "max_pillars_num", "feature_num"],      # torchScatterMax.cu:388-390
+    "Map2BevPlugin": ["max_pillars_num", "channel_num", "grid_size_x", "grid_size_y"],  # map2bev.cu:383-386
 }
 
 
@@ -77,6 +79,11 @@ def test_serialisation_layouts_without_gpu():
     assert f.serialize() == struct.pack("<i10f", 500, -74.88, 74.88, -74.88, 74.88, -5.0, 3.0, 0.32, 0.32, 8.0, 0.3)
     with pytest.raises(RuntimeError):
         lib.deserialize("GetSetPlugin", blob[:10])      # truncated plan data is rejected, not read out of bounds
+    sm = plg.add_torch_scatter_max(lib, 30000, 10000, 96)
+    assert sm.serialize() == struct.pack("<3i", 30000, 10000, 96) and sm.nb_outputs == 2    # torchScatterMax.cu:346-352
+    mb = plg.add_map_2_bev_op(lib, 10000, 192, 468, 468)
+    assert mb.serialize() == struct.pack("<4i", 10000, 192, 468, 468)                       # map2bev.cu:352-359
+    assert lib.deserialize("Map2BevPlugin", mb.serialize()).serialize() == mb.serialize()
     # static output shapes (getOutputDimensions) and I/O formats (supportsFormatCombination)
     D = plg._Desc
     def desc(dims, dt):

@@ -457,3 +457,67 @@ def test_set_attention_fused_fp16_tensor_cores(n_sets, precision):
             a = cpu.set_attention(q, k, v, mask, n_sets, **w)
             o = cpu.map_set_feature2voxel(a, idx, n_sets, axis, max_pillars)
             assert np.abs(got[touched] - o[touched]).max() <= tol
+
+
+# ------------------------------------------------------------------------------------------------
+# next #3: TorchScatterMaxPlugin / Map2BevPlugin (pure max / copy arithmetic: bit exact)
+@pytest.mark.parametrize("F", [96, 192])
+def test_torch_scatter_max(frame0, cfgs, F):
+    cfg = cfgs.REFERENCE
+    o = cpu.points2features(pad_points(frame0, cfg.max_points_num), len(frame0), cfg)
+    V, Pc = o["pillar_num"], o["point_num"]
+    rng = np.random.default_rng(F)
+    feat = np.zeros((cfg.max_points_num_voxel_filter, F), np.float32)
+    feat[:Pc] = rng.standard_normal((Pc, F)) * 3
+    feat[:Pc][rng.random((Pc, F)) < 0.01] = -2000000.0           # below the reference's -1000000 start value
+    ref_mp, ref_mv = cpu.torch_scatter_max(feat, o["point_index_in_voxel"], o["point_num_in_voxel"], V)
+    piv, pnv = dev(o["point_index_in_voxel"]), dev(o["point_num_in_voxel"].reshape(-1))
+    v_t = torch.tensor([V], dtype=torch.int32, device="cuda")
+    for point_num in (None, torch.tensor([Pc], dtype=torch.int32, device="cuda")):     # reference form / with the row count
+        mp = torch.full((cfg.max_points_num_voxel_filter, F), float("nan"), device="cuda")
+        mv = torch.full((cfg.max_pillars_num, F), float("nan"), device="cuda")
+        capi.torch_scatter_max(dev(feat), piv, pnv, v_t, point_num, max_point=mp, max_voxel=mv)
+        assert np.array_equal(mp.cpu().numpy(), ref_mp) and np.array_equal(mv.cpu().numpy(), ref_mv)
+    # no pillars at all: both outputs are all zero
+    mp, mv = capi.torch_scatter_max(dev(feat), piv, pnv, torch.zeros(1, dtype=torch.int32, device="cuda"),
+                                    torch.zeros(1, dtype=torch.int32, device="cuda"))
+    assert float(mp.abs().max()) == 0.0 and float(mv.abs().max()) == 0.0
+
+
+def test_torch_scatter_max_batched_waymo(pkg, cfgs):
+    cfg = cfgs.WAYMO.with_(max_points_num=120000, max_points_num_voxel_filter=120000)
+    B, F = 2, 96
+    rng = np.random.default_rng(0)
+    feats = np.zeros((B, cfg.max_points_num_voxel_filter, F), np.float32)
+    pivs, pnvs, Vs, Pcs, refs = [], [], [], [], []
+    for b in range(B):
+        pts = pkg.synth.ring_lidar(100000, seed=10 + b)
+        o = cpu.points2features(pad_points(pts, cfg.max_points_num), len(pts), cfg)
+        feats[b, : o["point_num"]] = rng.standard_normal((o["point_num"], F))
+        pivs.append(o["point_index_in_voxel"]); pnvs.append(o["point_num_in_voxel"].reshape(-1))
+        Vs.append(o["pillar_num"]); Pcs.append(o["point_num"])
+        refs.append(cpu.torch_scatter_max(feats[b], o["point_index_in_voxel"], o["point_num_in_voxel"], o["pillar_num"]))
+    mp, mv = capi.torch_scatter_max(dev(feats), dev(np.stack(pivs)), dev(np.stack(pnvs)),
+                                    torch.tensor(Vs, dtype=torch.int32, device="cuda"),
+                                    torch.tensor(Pcs, dtype=torch.int32, device="cuda"))
+    for b in range(B):
+        assert np.array_equal(mp[b].cpu().numpy(), refs[b][0]) and np.array_equal(mv[b].cpu().numpy(), refs[b][1])
+
+
+def test_map2bev(frame0, cfgs):
+    cfg = cfgs.REFERENCE
+    o = cpu.points2features(pad_points(frame0, cfg.max_points_num), len(frame0), cfg)
+    V = o["pillar_num"]
+    rng = np.random.default_rng(2)
+    x = np.zeros((cfg.max_pillars_num, 192), np.float32)
+    x[:V] = rng.standard_normal((V, 192))
+    ref = cpu.map2bev(x, o["coords"], V, cfg.grid_x, cfg.grid_y)
+    out = torch.full((cfg.grid_y, cfg.grid_x, 192), float("nan"), device="cuda")
+    capi.map2bev(dev(x), dev(o["coords"]), torch.tensor([V], dtype=torch.int32, device="cuda"), cfg.grid_x, cfg.grid_y, out=out)
+    got = out.cpu().numpy()
+    assert np.array_equal(got, ref)
+    assert int((np.abs(got).sum(axis=2) > 0).sum()) == V             # one occupied cell per pillar
+    # a coordinate outside the grid is ignored (the reference would write out of bounds)
+    bad = o["coords"].copy(); bad[0, 2] = cfg.grid_y + 5
+    out2 = capi.map2bev(dev(x), dev(bad), torch.tensor([V], dtype=torch.int32, device="cuda"), cfg.grid_x, cfg.grid_y)
+    assert np.array_equal(out2.cpu().numpy(), cpu.map2bev(x, bad, V, cfg.grid_x, cfg.grid_y))

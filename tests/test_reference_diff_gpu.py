@@ -240,3 +240,29 @@ def test_gather_scatter_vs_reference_kernels(plg, ours, cfgs, frame0):
         sm = plg.add_map_set_feature2voxel_op(ours, *a, cfg.max_pillars_num).enqueue([feat, idx, ns], poison=float("nan"))[0]
         sr = plg.add_map_set_feature2voxel_op(ref_lib(plg, "mapSetFeature2voxel"), *a, cfg.max_pillars_num).enqueue([feat, idx, ns])[0]
         assert torch.equal(sm, sr)
+
+
+def test_scatter_max_and_map2bev_vs_reference_kernels(plg, ours, cfgs, frame0):
+    """TorchScatterMaxPlugin / Map2BevPlugin against the reference's own kernels, created from the same fields."""
+    cfg = cfgs.REFERENCE
+    o = cpu.points2features(pad_points(frame0, cfg.max_points_num), len(frame0), cfg)
+    V, Pc = o["pillar_num"], o["point_num"]
+    rng = np.random.default_rng(9)
+    for F in (96, 192):
+        feat = np.zeros((1, cfg.max_points_num_voxel_filter, F), np.float32)
+        feat[0, :Pc] = rng.standard_normal((Pc, F)) * 2
+        ins = [dev(feat), dev(o["point_index_in_voxel"])[None], dev(o["point_num_in_voxel"].reshape(1, -1, 1)), i32(V)]
+        a = (cfg.max_points_num_voxel_filter, cfg.max_pillars_num, F)
+        mine = plg.add_torch_scatter_max(ours, *a).enqueue(ins, poison=float("nan"))
+        ref = plg.add_torch_scatter_max(ref_lib(plg, "torchScatterMax"), *a).enqueue(ins)
+        assert torch.equal(mine[0], ref[0]) and torch.equal(mine[1], ref[1])
+        # optional 5th input (the voxeliser's row count): same result without the full clear
+        mine5 = plg.add_torch_scatter_max(ours, *a).enqueue(ins + [i32(Pc)], poison=float("nan"))
+        assert torch.equal(mine5[0], ref[0]) and torch.equal(mine5[1], ref[1])
+    x = np.zeros((1, cfg.max_pillars_num, 192), np.float32)
+    x[0, :V] = rng.standard_normal((V, 192))
+    ins = [dev(x), dev(o["coords"])[None], i32(V)]
+    a = (cfg.max_pillars_num, 192, cfg.grid_x, cfg.grid_y)
+    mine = plg.add_map_2_bev_op(ours, *a).enqueue(ins, poison=float("nan"))[0]
+    ref = plg.add_map_2_bev_op(ref_lib(plg, "map2bev"), *a).enqueue(ins)[0]
+    assert tuple(mine.shape) == (1, cfg.grid_x, cfg.grid_y, 192) and torch.equal(mine, ref)
