@@ -726,7 +726,9 @@ private:
 // (src/dsvt-ai-trt.cpp:653-668 and the 7 sibling call sites).  This is the form every tensor-core
 // precision is built for.
 // Inputs : x [B,max_pillars,C] f32, pos [B,max_pillars,C] f32, global_index_in_set [B,2,max_sets,S] i32,
-//          mask [B,max_sets,heads,S] f32, set_num [B] i32, voxel_num [B] i32.   Output: [B,max_pillars,C] f32.
+//          mask [B,max_sets,heads,S] f32, set_num [B] i32, voxel_num [B] i32  (+ optional 7th input: the attention
+//          plan of this (partition, axis) from SetAttentionPlanPlugin -- without it the plan is rebuilt on every
+//          enqueue).   Output: [B,max_pillars,C] f32.
 // Fields : SetAttentionPlugin's + max_pillars_num, axis_id.  Serialised: 7 x i32 then the four weight arrays.
 class SetAttentionFusedPlugin final : public PluginBase {
 public:
@@ -780,7 +782,7 @@ public:
     IPluginV2DynamicExt* clone() const noexcept override {
         auto* c = new (std::nothrow) SetAttentionFusedPlugin(max_sets_, S_, C_, heads_, precision_, max_pillars_, axis_,
                                                              w_in_.data(), b_in_.data(), w_out_.data(), b_out_.data());
-        if (c) c->setPluginNamespace(ns_.c_str());
+        if (c) { c->setPluginNamespace(ns_.c_str()); c->nb_inputs_seen_ = nb_inputs_seen_; }
         return c;
     }
     int32_t initialize() noexcept override { return upload(); }
@@ -792,8 +794,11 @@ public:
     }
     bool supportsFormatCombination(int32_t pos, const PluginTensorDesc* io, int32_t nbIn, int32_t nbOut) noexcept override {
         if (pos < 0 || pos >= nbIn + nbOut || io[pos].format != TensorFormat::kLINEAR) return false;
-        return io[pos].type == ((pos == 2 || pos == 4 || pos == 5) ? I : F);
+        const bool is_int = pos == 2 || pos == 4 || pos == 5 || (nbIn == 7 && pos == 6);
+        return io[pos].type == (is_int ? I : F);
     }
+    void configurePlugin(const DynamicPluginTensorDesc*, int32_t nbInputs, const DynamicPluginTensorDesc*,
+                         int32_t) noexcept override { nb_inputs_seen_ = nbInputs; }
     DataType getOutputDataType(int32_t, const DataType*, int32_t) const noexcept override { return F; }
     size_t getWorkspaceSize(const PluginTensorDesc* in, int32_t, const PluginTensorDesc*, int32_t) const noexcept override {
         const dsvt_set_attention_params p = params(batch_of(in));
@@ -803,11 +808,12 @@ public:
                     void* const* outputs, void* ws, cudaStream_t stream) noexcept override {
         if (upload() != 0) return DSVT_ERR_CUDA;
         const dsvt_set_attention_params p = params(batch_of(in));
-        return report(dsvt_set_attention_fused_launch(
+        const void* plan = nb_inputs_seen_ == 7 ? inputs[6] : nullptr;
+        return report(dsvt_set_attention_fused_planned_launch(
                           &p, dev_, static_cast<const float*>(inputs[0]), static_cast<const float*>(inputs[1]),
                           static_cast<const int32_t*>(inputs[2]), static_cast<const float*>(inputs[3]),
                           static_cast<const int32_t*>(inputs[4]), static_cast<const int32_t*>(inputs[5]),
-                          static_cast<float*>(outputs[0]), ws, dsvt_set_attention_workspace_size(&p), stream), kName);
+                          static_cast<float*>(outputs[0]), plan, ws, dsvt_set_attention_workspace_size(&p), stream), kName);
     }
 protected:
     const std::vector<DataType>& io_types() const override {
@@ -833,6 +839,71 @@ private:
     int max_sets_, S_, C_, heads_, precision_, max_pillars_, axis_;
     std::vector<float> w_in_, b_in_, w_out_, b_out_;
     dsvt_attention_weights* dev_ = nullptr;
+    int nb_inputs_seen_ = 6;
+};
+
+// SetAttentionPlanPlugin -- the set partition of one (window partition, axis) in token order, built ONCE from the
+// GetSetPlugin outputs and fed to the SetAttentionFusedPlugin nodes of the layers that share the partition (2 of the 8
+// in the reference graph each).  Inputs: global_index_in_set [B,2,max_sets,S] i32, mask [B,max_sets,heads,S] f32,
+// set_num [B] i32.  Output: plan [B, plan_ints] i32 (opaque).  Fields / serialised: max_win_num, voxel_num_set,
+// num_heads, max_pillars_num, axis_id (5 x i32).
+class SetAttentionPlanPlugin final : public PluginBase {
+public:
+    static constexpr const char* kName = "SetAttentionPlanPlugin";
+    static FieldList field_list() {
+        return {{"max_win_num", PluginFieldType::kINT32}, {"voxel_num_set", PluginFieldType::kINT32},
+                {"num_heads", PluginFieldType::kINT32}, {"max_pillars_num", PluginFieldType::kINT32},
+                {"axis_id", PluginFieldType::kINT32}};
+    }
+    SetAttentionPlanPlugin(int max_sets, int S, int heads, int max_pillars, int axis)
+        : max_sets_(max_sets), S_(S), heads_(heads), max_pillars_(max_pillars), axis_(axis) {}
+    static IPluginV2* from_fields(const PluginFieldCollection* fc) {
+        return new (std::nothrow) SetAttentionPlanPlugin(field_int(fc, "max_win_num"), field_int(fc, "voxel_num_set"),
+                                                         field_int(fc, "num_heads", 0, 8), field_int(fc, "max_pillars_num"),
+                                                         field_int(fc, "axis_id"));
+    }
+    static IPluginV2* from_bytes(const void* data, size_t len) {
+        Reader r(data, len);
+        const int a = r.get<int>(), b = r.get<int>(), c = r.get<int>(), d = r.get<int>(), e = r.get<int>();
+        return r.ok() ? new (std::nothrow) SetAttentionPlanPlugin(a, b, c, d, e) : nullptr;
+    }
+    size_t getSerializationSize() const noexcept override { return 5 * sizeof(int); }
+    void serialize(void* buf) const noexcept override {
+        Writer w(buf);
+        w.put(max_sets_); w.put(S_); w.put(heads_); w.put(max_pillars_); w.put(axis_);
+    }
+    IPluginV2DynamicExt* clone() const noexcept override {
+        auto* c = new (std::nothrow) SetAttentionPlanPlugin(max_sets_, S_, heads_, max_pillars_, axis_);
+        if (c) c->setPluginNamespace(ns_.c_str());
+        return c;
+    }
+    const char* getPluginType() const noexcept override { return kName; }
+    int32_t getNbOutputs() const noexcept override { return 1; }
+    DimsExprs getOutputDimensions(int32_t, const DimsExprs* in, int32_t, IExprBuilder& b) noexcept override {
+        const dsvt_set_attention_params p = params(1);
+        return dims(b, in[0].d[0], {(int) (dsvt_set_attention_plan_size(&p) / sizeof(int32_t))});
+    }
+    int32_t enqueue(const PluginTensorDesc* in, const PluginTensorDesc*, const void* const* inputs,
+                    void* const* outputs, void*, cudaStream_t stream) noexcept override {
+        const dsvt_set_attention_params p = params(batch_of(in));
+        return report(dsvt_set_attention_plan_launch(&p, static_cast<const int32_t*>(inputs[0]),
+                                                     static_cast<const float*>(inputs[1]), static_cast<const int32_t*>(inputs[2]),
+                                                     outputs[0], dsvt_set_attention_plan_size(&p), stream), kName);
+    }
+protected:
+    const std::vector<DataType>& io_types() const override {
+        static const std::vector<DataType> t{I, F, I, I};
+        return t;
+    }
+    size_t nb_inputs() const override { return 3; }
+private:
+    dsvt_set_attention_params params(int batch) const {
+        dsvt_set_attention_params p{};
+        p.batch = batch; p.max_set_num = max_sets_; p.voxel_num_set = S_; p.channel_num = 192; p.num_heads = heads_;
+        p.max_pillars_num = max_pillars_; p.axis_id = axis_; p.precision = DSVT_ATTN_FP32_TC; p.zero_tails = 1;
+        return p;
+    }
+    int max_sets_, S_, heads_, max_pillars_, axis_;
 };
 
 // =================================================================================================
@@ -973,6 +1044,7 @@ using SetAttentionPluginCreator = CreatorBase<SetAttentionPlugin>;
 using SetAttentionFusedPluginCreator = CreatorBase<SetAttentionFusedPlugin>;
 using TorchScatterMaxPluginCreator = CreatorBase<TorchScatterMaxPlugin>;
 using Map2BevPluginCreator = CreatorBase<Map2BevPlugin>;
+using SetAttentionPlanPluginCreator = CreatorBase<SetAttentionPlanPlugin>;
 
 REGISTER_TENSORRT_PLUGIN(Points2FeaturesPluginCreator);
 REGISTER_TENSORRT_PLUGIN(WindowPartitionPluginCreator);
@@ -986,5 +1058,6 @@ REGISTER_TENSORRT_PLUGIN(SetAttentionPluginCreator);
 REGISTER_TENSORRT_PLUGIN(SetAttentionFusedPluginCreator);
 REGISTER_TENSORRT_PLUGIN(TorchScatterMaxPluginCreator);
 REGISTER_TENSORRT_PLUGIN(Map2BevPluginCreator);
+REGISTER_TENSORRT_PLUGIN(SetAttentionPlanPluginCreator);
 
 }  // namespace dsvt_plugins

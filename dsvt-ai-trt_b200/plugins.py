@@ -280,3 +280,11 @@ def add_map_2_bev_op(lib, max_pillars_num, channel_num, grid_size_x, grid_size_y
     return lib.create("Map2BevPlugin", {
         "max_pillars_num": max_pillars_num, "channel_num": channel_num, "grid_size_x": grid_size_x,
         "grid_size_y": grid_size_y})
+
+
+def add_set_attention_plan_op(lib, max_win_num, voxel_num_set, num_heads, max_pillars_num, axis_id):
+    """Token-order plan of one (window partition, axis): inputs global_index_in_set, mask, set_num (GetSetPlugin outputs
+    0, 3, 2); its output is the optional 7th input of SetAttentionFusedPlugin."""
+    return lib.create("SetAttentionPlanPlugin", {
+        "max_win_num": max_win_num, "voxel_num_set": voxel_num_set, "num_heads": num_heads,
+        "max_pillars_num": max_pillars_num, "axis_id": axis_id})

@@ -193,10 +193,18 @@ def test_set_attention_fused_plugin(lib, plg, precision):
             got = out[0].cpu().numpy()
             assert np.all(got[V:] == 0)
             assert np.abs(got[:V] - ref[:V]).max() <= tol
+        if precision in (3, 4):     # planned form: SetAttentionPlanPlugin output as the optional 7th input
+            pl = plg.add_set_attention_plan_op(lib, max_sets, S, H, max_pillars, axis)
+            pl, pblob = roundtrip(lib, pl)
+            assert pblob == struct.pack("<5i", max_sets, S, H, max_pillars, axis)
+            (plan,) = pl.enqueue([dev(idx)[None], dev(mask)[None], i32(n_sets)])
+            (out7,) = p.enqueue([dev(x)[None], dev(pos)[None], dev(idx)[None], dev(mask)[None], i32(n_sets), i32(V), plan],
+                                poison=float("nan"))
+            assert torch.equal(out7, out)
 
 
 def test_registry_and_formats(lib):
     names = set(lib.registered())
     assert {"Points2FeaturesPlugin", "GetSetPlugin", "GeluPlugin", "LayerNormPlugin", "FilterBoxByScorePlugin",
             "WindowPartitionPlugin", "GetValueByIndexPlugin", "MapSetFeature2VoxelPlugin", "SetAttentionPlugin",
-            "SetAttentionFusedPlugin"} <= names
+            "SetAttentionFusedPlugin", "SetAttentionPlanPlugin", "TorchScatterMaxPlugin", "Map2BevPlugin"} <= names
