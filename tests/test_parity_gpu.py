@@ -459,6 +459,68 @@ def test_set_attention_fused_fp16_tensor_cores(n_sets, precision):
             assert np.abs(got[touched] - o[touched]).max() <= tol
 
 
+def _synthetic_partition(rng, n_sets, max_sets, S, H=8):
+    """Sets of 1..S distinct voxels with DSVT eq.(3)-style repeats; every voxel belongs to exactly one set."""
+    sizes = rng.integers(1, S + 1, n_sets)
+    V = int(sizes.sum())
+    idx = np.zeros((2, max_sets, S), np.int32)
+    mask = np.zeros((max_sets, H, S), np.float32)
+    perm, start = rng.permutation(V), 0
+    for s in range(n_sets):
+        n = int(sizes[s])
+        members = np.sort(perm[start:start + n]); start += n
+        r = (np.arange(S) * n) // S
+        idx[0, s] = members[r]; idx[1, s] = members[::-1][r]
+        mask[s, :, 1:][:, r[1:] == r[:-1]] = -np.finfo(np.float32).max
+    return idx, mask, V
+
+
+@pytest.mark.parametrize("S", [24, 48])
+def test_set_attention_pipeline_other_set_sizes(S):
+    """GEMM pipeline (precision 3) for set sizes 24 / 48 (BASELINE.json config 5) against the CPU oracle chain."""
+    rng = np.random.default_rng(S)
+    n_sets, max_sets, C = 30, 40, 192
+    idx, mask, V = _synthetic_partition(rng, n_sets, max_sets, S)
+    max_pillars = V + 19
+    x = np.zeros((max_pillars, C), np.float32); pos = np.zeros_like(x)
+    x[:V] = rng.standard_normal((V, C)); pos[:V] = rng.standard_normal((V, C)) * 0.5
+    _, _, _, _, w = _attn_inputs(1, 1, seed=9)
+    W = capi.AttentionWeights(w["w_in"], w["b_in"], w["w_out"], w["b_out"])
+    ns_t = torch.tensor([n_sets], dtype=torch.int32, device="cuda"); v_t = torch.tensor([V], dtype=torch.int32, device="cuda")
+    for axis in (0, 1):
+        out = torch.full((max_pillars, C), float("nan"), device="cuda")
+        capi.set_attention_fused(W, dev(x), dev(pos), dev(idx), dev(mask), ns_t, v_t, axis, out=out, precision=3)
+        q, k, v = cpu.get_value_by_index(x, pos, idx, n_sets, axis)
+        a = cpu.set_attention(q, k, v, mask, n_sets, **w)
+        ref = cpu.map_set_feature2voxel(a, idx, n_sets, axis, max_pillars)
+        got = out.cpu().numpy()
+        assert np.all(got[V:] == 0)
+        assert np.abs(got[:V] - ref[:V]).max() <= ATTN_TOL[3]
+
+
+@pytest.mark.parametrize("precision", [3, 2])
+def test_set_attention_fused_batched(precision):
+    """batch = 3 frames with different set / voxel counts in one launch sequence == the three single-frame results."""
+    rng = np.random.default_rng(77)
+    B, max_sets, S, C = 3, 64, 36, 192
+    parts = [_synthetic_partition(rng, n, max_sets, S) for n in (50, 7, 33)]
+    max_pillars = max(p[2] for p in parts) + 40
+    x = np.zeros((B, max_pillars, C), np.float32); pos = np.zeros_like(x)
+    for b, (_, _, V) in enumerate(parts):
+        x[b, :V] = rng.standard_normal((V, C)); pos[b, :V] = rng.standard_normal((V, C)) * 0.5
+    idx = np.stack([p[0] for p in parts]); mask = np.stack([p[1] for p in parts])
+    ns = torch.tensor([50, 7, 33], dtype=torch.int32, device="cuda")
+    vn = torch.tensor([p[2] for p in parts], dtype=torch.int32, device="cuda")
+    _, _, _, _, w = _attn_inputs(1, 1, seed=4)
+    W = capi.AttentionWeights(w["w_in"], w["b_in"], w["w_out"], w["b_out"])
+    out = torch.full((B, max_pillars, C), float("nan"), device="cuda")
+    capi.set_attention_fused(W, dev(x), dev(pos), dev(idx), dev(mask), ns, vn, 1, out=out, precision=precision)
+    for b, (_, _, V) in enumerate(parts):
+        one = capi.set_attention_fused(W, dev(x[b]), dev(pos[b]), dev(idx[b]), dev(mask[b]), ns[b:b + 1], vn[b:b + 1], 1,
+                                       precision=precision)
+        assert torch.equal(out[b, :V], one[:V]) and float(out[b, V:].abs().max()) == 0.0
+
+
 # ------------------------------------------------------------------------------------------------
 # next #3: TorchScatterMaxPlugin / Map2BevPlugin (pure max / copy arithmetic: bit exact)
 @pytest.mark.parametrize("F", [96, 192])
