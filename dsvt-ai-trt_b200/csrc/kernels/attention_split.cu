@@ -28,6 +28,7 @@
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -809,7 +810,10 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
     }
     const size_t plan_stride = plan_words(p->max_set_num, p->voxel_num_set, p->max_pillars_num);
     // persistent grids: one CTA per SM (divided among the batch), a multiple of the number of roles
-    const int per_b = sm_count() / p->batch;
+    // DSVT_GEMM_SM_FRACTION=<percent> (tuning knob): CTAs per launch as a share of the SMs.  Fewer CTAs amortise the
+    // resident weight image over more row tiles and leave SMs to the kernels of concurrently running frames.
+    static const int frac = [] { const char* e = getenv("DSVT_GEMM_SM_FRACTION"); int v = e ? atoi(e) : 100; return v < 5 ? 5 : (v > 100 ? 100 : v); }();
+    const int per_b = sm_count() * frac / 100 / p->batch;
     const int grid_in = per_b >= 3 ? per_b / 3 * 3 : 3, grid_out = per_b >= 1 ? per_b : 1;
     GemmRoles in_roles, out_roles;
     for (int r = 0; r < 3; ++r) {
