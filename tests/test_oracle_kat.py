@@ -176,3 +176,32 @@ def test_attention_oracle_matches_torch_mha(attention_case):
     out = cpu.set_attention(c["q"], c["k"], c["v"], c["mask"], c["q"].shape[0], c["w_in"], c["b_in"], c["w_out"],
                             c["b_out"])
     assert np.abs(out - c["out"]).max() < 2e-5
+
+
+def test_scatter_max_and_map2bev_against_numpy(frame0, cfgs):
+    """Oracle restatements of torchScatterMax.cu:201-262 and map2bev.cu:250-265 against independent numpy code."""
+    cfg = cfgs.REFERENCE
+    o = cpu.points2features(pad_points(frame0, cfg.max_points_num), len(frame0), cfg)
+    V, Pc = o["pillar_num"], o["point_num"]
+    rng = np.random.default_rng(0)
+    F = 96
+    feat = np.zeros((cfg.max_points_num_voxel_filter, F), np.float32)
+    feat[:Pc] = rng.standard_normal((Pc, F)) * 2
+    feat[0] = -3000000.0                       # below the -1000000 start value: the max of a 1-point pillar is then -1000000
+    mp, mv = cpu.torch_scatter_max(feat, o["point_index_in_voxel"], o["point_num_in_voxel"], V)
+    piv, pnv = o["point_index_in_voxel"], o["point_num_in_voxel"].reshape(-1)
+    for v in list(range(0, V, 97)) + [V - 1]:
+        rows = piv[v, : pnv[v]]
+        want = np.maximum(feat[rows].max(axis=0), np.float32(-1000000.0))
+        assert np.array_equal(mv[v], want)
+        assert np.array_equal(mp[rows], np.broadcast_to(want, (len(rows), F)))
+    assert np.all(mv[V:] == 0) and np.all(mp[Pc:] == 0)
+    # every kept point row is covered by exactly one pillar
+    assert sorted(np.concatenate([piv[v, : pnv[v]] for v in range(V)]).tolist()) == list(range(Pc))
+
+    x = np.zeros((cfg.max_pillars_num, 192), np.float32)
+    x[:V] = rng.standard_normal((V, 192))
+    bev = cpu.map2bev(x, o["coords"], V, cfg.grid_x, cfg.grid_y)
+    want = np.zeros((cfg.grid_y, cfg.grid_x, 192), np.float32)
+    want[o["coords"][:V, 2], o["coords"][:V, 3]] = x[:V]
+    assert np.array_equal(bev, want)
