@@ -257,6 +257,8 @@ def plugin_breakdown(slot, cfg, peaks, reps=3):
     res["filter_box"] = {"us": us, "bytes": 22000 + 18004, "calls_per_frame": 1}
     pipeline_prec = f.precision in (capi.DSVT_ATTN_FP32_TC, capi.DSVT_ATTN_FP16_GEMM)
     lib = capi._lib()
+    # kernels are timed ALONE here: the attention GEMMs get every SM (the throughput runs above use half per launch)
+    prev_frac = lib.dsvt_debug_set_gemm_sm_fraction(100)
     for i in (0, 1):
         gs = f.gs[i]
         plan = f.plans.get((i, 0)) if getattr(f, "plans", None) else None
@@ -294,6 +296,7 @@ def plugin_breakdown(slot, cfg, peaks, reps=3):
                                   "flops": None},
                     "out_proj_gemm": {"us": round(c, 2), "flops": 2 * C * C * V, "mma_flops_issued": split * 2 * C * C * V,
                                       "bytes": 4 * V * 2 * C + 2 * split * 2 * C * C}}
+    lib.dsvt_debug_set_gemm_sm_fraction(prev_frac)
     for k, r in res.items():
         if r.get("bytes"):
             r["gbs"] = r["bytes"] / r["us"] * 1e-3

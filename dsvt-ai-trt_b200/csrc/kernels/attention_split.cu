@@ -728,6 +728,16 @@ static int stage_mark(int i, cudaStream_t st) {
     return DSVT_OK;
 }
 
+static int g_gemm_sm_fraction = -1;
+static int gemm_sm_fraction() {
+    if (g_gemm_sm_fraction < 0) {
+        const char* e = getenv("DSVT_GEMM_SM_FRACTION");
+        const int v = e ? atoi(e) : 100;
+        g_gemm_sm_fraction = v < 5 ? 5 : (v > 100 ? 100 : v);
+    }
+    return g_gemm_sm_fraction;
+}
+
 static size_t plan_bytes_of(const dsvt_set_attention_params* p) {
     return align_up((size_t) p->batch * plan_words(p->max_set_num, p->voxel_num_set, p->max_pillars_num) * sizeof(int), kWsAlign);
 }
@@ -812,8 +822,7 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
     // persistent grids: one CTA per SM (divided among the batch), a multiple of the number of roles
     // DSVT_GEMM_SM_FRACTION=<percent> (tuning knob): CTAs per launch as a share of the SMs.  Fewer CTAs amortise the
     // resident weight image over more row tiles and leave SMs to the kernels of concurrently running frames.
-    static const int frac = [] { const char* e = getenv("DSVT_GEMM_SM_FRACTION"); int v = e ? atoi(e) : 100; return v < 5 ? 5 : (v > 100 ? 100 : v); }();
-    const int per_b = sm_count() * frac / 100 / p->batch;
+    const int per_b = sm_count() * gemm_sm_fraction() / 100 / p->batch;
     const int grid_in = per_b >= 3 ? per_b / 3 * 3 : 3, grid_out = per_b >= 1 ? per_b : 1;
     GemmRoles in_roles, out_roles;
     for (int r = 0; r < 3; ++r) {
@@ -872,6 +881,13 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
 }  // namespace dsvt
 
 extern "C" void dsvt_debug_attention_stage_timing(int enable) { dsvt::g_stage_timing = enable != 0; }
+// share of the SMs (percent, 5..100) the attention GEMMs launch CTAs on; initial value: DSVT_GEMM_SM_FRACTION or 100.
+// Returns the previous value.  100 = lowest latency of a single call, ~50 = best throughput with several frames in flight.
+extern "C" int dsvt_debug_set_gemm_sm_fraction(int percent) {
+    const int prev = dsvt::gemm_sm_fraction();
+    dsvt::g_gemm_sm_fraction = percent < 5 ? 5 : (percent > 100 ? 100 : percent);
+    return prev;
+}
 // microseconds of {QKV projection GEMM, per-set core, out-projection GEMM} of the last timed call (after a stream sync)
 extern "C" int dsvt_debug_attention_stage_us(float* out3) {
     for (int i = 0; i < 3; ++i) {

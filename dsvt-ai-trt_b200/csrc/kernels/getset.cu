@@ -93,23 +93,68 @@ get_set_kernel(const int* __restrict__ global_index, const int* __restrict__ coo
     const int* gi = global_index + ((size_t) b * max_win + w) * max_vpw;
     const int* cw = coors_in_win + ((size_t) b * max_win + w) * max_vpw * 3;
 
-    for (int m = tid; m < N; m += kGsThreads) {
-        const int z = cw[m * 3 + 0], y = cw[m * 3 + 1], x = cw[m * 3 + 2];
-        key_y[m] = y * wx * wz + x * wz + z;    // getSet.cu:388-389
-        key_x[m] = x * wy * wz + y * wz + z;    // getSet.cu:463-464
-    }
+    // In-window keys are unique (one voxel per cell), so a voxel's rank in either ordering is the number of OCCUPIED
+    // cells with a smaller key: a bitmap over the wx*wy*wz cells + word prefix sums gives it in O(1) per voxel
+    // (the reference quicksorts per window on one thread, getSet.cu:274-324; our first version counted pairs, O(N^2)).
+    // Out-of-range coordinates or duplicate keys (malformed input) fall back to the pair count below.
+    const int cells = wx * wy * wz, words = (cells + 31) >> 5;
+    unsigned* occ_y = reinterpret_cast<unsigned*>(sorted_x + max_vpw);   // [words]
+    unsigned* occ_x = occ_y + words;                                     // [words]
+    int* pre_y = reinterpret_cast<int*>(occ_x + words);                  // [words] exclusive popcount prefix
+    int* pre_x = pre_y + words;
+    __shared__ int s_bad;
+    for (int i = tid; i < words; i += kGsThreads) { occ_y[i] = 0u; occ_x[i] = 0u; }
+    if (tid == 0) s_bad = 0;
     __syncthreads();
     for (int m = tid; m < N; m += kGsThreads) {
-        const int ky = key_y[m], kx = key_x[m];
-        int ry = 0, rx = 0;
-        for (int q = 0; q < N; ++q) {
-            const int qy = key_y[q], qx = key_x[q];
-            ry += (qy < ky) || (qy == ky && q < m);
-            rx += (qx < kx) || (qx == kx && q < m);
+        const int z = cw[m * 3 + 0], y = cw[m * 3 + 1], x = cw[m * 3 + 2];
+        const int ky = y * wx * wz + x * wz + z;    // getSet.cu:388-389
+        const int kx = x * wy * wz + y * wz + z;    // getSet.cu:463-464
+        key_y[m] = ky;
+        key_x[m] = kx;
+        if ((unsigned) x >= (unsigned) wx || (unsigned) y >= (unsigned) wy || (unsigned) z >= (unsigned) wz) {
+            s_bad = 1;
+        } else {
+            const unsigned oy = atomicOr(&occ_y[ky >> 5], 1u << (ky & 31));
+            atomicOr(&occ_x[kx >> 5], 1u << (kx & 31));
+            if (oy & (1u << (ky & 31))) s_bad = 1;  // two voxels in one cell
         }
-        const int g = gi[m];
-        sorted_y[ry] = g;
-        sorted_x[rx] = g;
+    }
+    __syncthreads();
+    if (!s_bad) {
+        if (tid < 32) {                             // exclusive prefix of the word popcounts (<= 18 words at 24x24)
+            int cy = 0, cx = 0;
+            for (int i0 = 0; i0 < words; i0 += 32) {
+                const int i = i0 + tid;
+                const int py = i < words ? __popc(occ_y[i]) : 0, px = i < words ? __popc(occ_x[i]) : 0;
+                const int iy = warp_incl_scan(py, lane), ix = warp_incl_scan(px, lane);
+                if (i < words) { pre_y[i] = cy + iy - py; pre_x[i] = cx + ix - px; }
+                cy += __shfl_sync(0xffffffffu, iy, 31);
+                cx += __shfl_sync(0xffffffffu, ix, 31);
+            }
+        }
+        __syncthreads();
+        for (int m = tid; m < N; m += kGsThreads) {
+            const int ky = key_y[m], kx = key_x[m];
+            const int ry = pre_y[ky >> 5] + __popc(occ_y[ky >> 5] & ((1u << (ky & 31)) - 1u));
+            const int rx = pre_x[kx >> 5] + __popc(occ_x[kx >> 5] & ((1u << (kx & 31)) - 1u));
+            const int g = gi[m];
+            sorted_y[ry] = g;
+            sorted_x[rx] = g;
+        }
+    } else {
+        for (int m = tid; m < N; m += kGsThreads) {
+            const int ky = key_y[m], kx = key_x[m];
+            int ry = 0, rx = 0;
+            for (int q = 0; q < N; ++q) {
+                const int qy = key_y[q], qx = key_x[q];
+                ry += (qy < ky) || (qy == ky && q < m);
+                rx += (qx < kx) || (qx == kx && q < m);
+            }
+            const int g = gi[m];
+            sorted_y[ry] = g;
+            sorted_x[rx] = g;
+        }
     }
     __syncthreads();
 
@@ -251,13 +296,56 @@ wp_finalize_kernel(const int* __restrict__ coords, int max_pillars, const int* _
     int N = 0;
     if (w < W) {
         N = voxel_num_in_win[(size_t) b * max_win + w];
+        // Ascending voxel id.  With canonical pillar ids (ascending y*gx+x, what our voxeliser emits) that is also the
+        // ascending order of the in-window cell key, and the key's rank is the number of occupied cells below it: a
+        // bitmap over the window's cells gives the order in O(N).  The result is verified (ids ascending in that order);
+        // any other input -- e.g. the reference voxeliser's race-ordered ids -- falls back to the O(N^2) pair count.
+        const int cells = wx * wy * wz, words = (cells + 31) >> 5;
+        unsigned* occ = reinterpret_cast<unsigned*>(sorted + max_vpw);   // [words]
+        int* pre = reinterpret_cast<int*>(occ + words);                  // [words]
+        int* keys = pre + words;                                         // [max_vpw]
+        __shared__ int s_bad;
+        for (int i = tid; i < words; i += kGsThreads) occ[i] = 0u;
+        if (tid == 0) s_bad = 0;
         for (int m = tid; m < N; m += kGsThreads) ids[m] = gi[m];
         __syncthreads();
         for (int m = tid; m < N; m += kGsThreads) {
-            const int e = ids[m];
-            int r = 0;
-            for (int q = 0; q < N; ++q) r += ids[q] < e;
-            sorted[r] = e;
+            const int4 c = *reinterpret_cast<const int4*>(coords + ((size_t) b * max_pillars + ids[m]) * 4);
+            const unsigned sx = (unsigned) c.w + sx_, sy = (unsigned) c.z + sy_, sz = (unsigned) c.y + sz_;
+            const int k = (int) (sy % wy) * wx * wz + (int) (sx % wx) * wz + (int) (sz % wz);
+            keys[m] = k;
+            if (atomicOr(&occ[k >> 5], 1u << (k & 31)) & (1u << (k & 31))) s_bad = 1;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            int carry = 0;
+            const int lane = tid;
+            for (int i0 = 0; i0 < words; i0 += 32) {
+                const int i = i0 + lane;
+                const int pc = i < words ? __popc(occ[i]) : 0;
+                const int inc = warp_incl_scan(pc, lane);
+                if (i < words) pre[i] = carry + inc - pc;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+        }
+        __syncthreads();
+        if (!s_bad)
+            for (int m = tid; m < N; m += kGsThreads) {
+                const int k = keys[m];
+                sorted[pre[k >> 5] + __popc(occ[k >> 5] & ((1u << (k & 31)) - 1u))] = ids[m];
+            }
+        __syncthreads();
+        if (!s_bad)
+            for (int m = tid; m + 1 < N; m += kGsThreads)
+                if (sorted[m] >= sorted[m + 1]) s_bad = 1;              // not the ascending-id order: redo below
+        __syncthreads();
+        if (s_bad) {
+            for (int m = tid; m < N; m += kGsThreads) {
+                const int e = ids[m];
+                int r = 0;
+                for (int q = 0; q < N; ++q) r += ids[q] < e;
+                sorted[r] = e;
+            }
         }
         __syncthreads();
         for (int m = tid; m < N; m += kGsThreads) {
@@ -312,7 +400,10 @@ extern "C" int dsvt_get_set_launch(const dsvt_get_set_params* p,
     if (rc != DSVT_OK) return rc;
     DSVT_CHECK_ARG(global_index && coors_in_win && voxel_num_in_win && win_num && global_index_in_set &&
                    set_voxel_mask && set_num && mask_expand_0 && mask_expand_1, "NULL tensor pointer");
-    const size_t smem = (size_t) p->max_voxel_num_per_win * 4 * sizeof(int);
+    // keys + sorted ids (4 x max_vpw ints) + two occupancy bitmaps and their popcount prefixes over the window's cells
+    const size_t cell_words = ((size_t) p->win_shape_x * p->win_shape_y * p->win_shape_z + 31) / 32;
+    const size_t smem = ((size_t) p->max_voxel_num_per_win * 4 + 4 * cell_words) * sizeof(int);
+    DSVT_CHECK_ARG(smem <= 200 * 1024, "window too large for shared memory");
     static bool attr_set = false;
     if (smem > 48 * 1024 && !attr_set) {
         DSVT_CUDA(cudaFuncSetAttribute(get_set_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -406,7 +497,9 @@ extern "C" int dsvt_window_partition_launch(const dsvt_window_partition_params* 
                                                      dense_cursor, global_index, stride, p->max_win_num,
                                                      p->max_voxel_num_per_win);
     DSVT_LAUNCH_CHECK();
-    const size_t smem = (size_t) p->max_voxel_num_per_win * 2 * sizeof(int);
+    // ids + sorted + keys (3 x max_vpw ints) + the occupancy bitmap and its popcount prefix over the window's cells
+    const size_t wp_cell_words = ((size_t) p->win_shape_x * p->win_shape_y * p->win_shape_z + 31) / 32;
+    const size_t smem = ((size_t) p->max_voxel_num_per_win * 3 + 2 * wp_cell_words) * sizeof(int);
     static bool attr_set = false;
     if (smem > 48 * 1024 && !attr_set) {
         DSVT_CUDA(cudaFuncSetAttribute(wp_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
