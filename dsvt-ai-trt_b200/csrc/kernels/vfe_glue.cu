@@ -46,11 +46,12 @@ scatter_max_kernel(const float4* __restrict__ feat, const int* __restrict__ piv,
         float4 m[NF4];
 #pragma unroll
         for (int k = 0; k < NF4; ++k) m[k] = make_float4(kMaxInit, kMaxInit, kMaxInit, kMaxInit);
-        // four rows in flight per step (the pillar's rows are independent loads; only the max is a chain)
-        for (int i0 = 0; i0 < n; i0 += 4) {
-            float4 a[4][NF4];
+        // kRows rows in flight per step (the pillar's rows are independent loads; only the max is a chain)
+        constexpr int kRows = 8;
+        for (int i0 = 0; i0 < n; i0 += kRows) {
+            float4 a[kRows][NF4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kRows; ++u) {
                 const int i = i0 + u < n ? i0 + u : n - 1;           // clamped: a repeated row does not change the max
                 const int row = i < 32 ? __shfl_sync(0xffffffffu, id0, i) : __shfl_sync(0xffffffffu, id1, i - 32);
 #pragma unroll
@@ -60,7 +61,7 @@ scatter_max_kernel(const float4* __restrict__ feat, const int* __restrict__ piv,
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < kRows; ++u)
 #pragma unroll
                 for (int k = 0; k < NF4; ++k) {
                     // strict '>' like the reference (:230): a NaN never replaces the running maximum
