@@ -66,19 +66,21 @@ template <bool SPLIT> struct Lay {
 // ---- attention plan: the set partition of one (frame, window partition, axis) in token order ----------------------
 // Built once by dsvt_set_attention_plan_launch and shared by every attention layer that uses the partition.
 // Per batch item, in ints (each array padded to 64): hdr[64] (hdr[0] = T, number of distinct tokens) |
-// set_off[max_sets + 1] (exclusive prefix of tokens per set) | nu[max_sets] | vox_su[max_pillars] (voxel -> set * 64 + u,
+// set_off[max_sets + 1] (exclusive prefix of tokens per set) | nu[max_sets] | order[max_sets] (sets by descending token
+// count: the core kernel starts the longest sets first) | vox_su[max_pillars] (voxel -> set * 64 + u,
 // -1 if the voxel is in no set) | tok[max_sets * S] as int2 (voxel row, slot) of the u-th distinct token of each set.
 __host__ __device__ inline size_t pad64(size_t n) { return (n + 63) & ~(size_t) 63; }
-struct PlanView { int* hdr; int* set_off; int* nu; int* vox_su; int2* tok; };
+struct PlanView { int* hdr; int* set_off; int* nu; int* order; int* vox_su; int2* tok; };
 __host__ __device__ inline size_t plan_words(int max_sets, int S, int max_pillars) {
-    return 64 + pad64((size_t) max_sets + 1) + pad64(max_sets) + pad64(max_pillars) + pad64((size_t) 2 * max_sets * S);
+    return 64 + pad64((size_t) max_sets + 1) + 2 * pad64(max_sets) + pad64(max_pillars) + pad64((size_t) 2 * max_sets * S);
 }
 __host__ __device__ inline PlanView plan_view(int* base, int max_sets, int max_pillars) {
     PlanView v;
     v.hdr = base;
     v.set_off = base + 64;
     v.nu = v.set_off + pad64((size_t) max_sets + 1);
-    v.vox_su = v.nu + pad64(max_sets);
+    v.order = v.nu + pad64(max_sets);
+    v.vox_su = v.order + pad64(max_sets);
     v.tok = reinterpret_cast<int2*>(v.vox_su + pad64(max_pillars));
     return v;
 }
@@ -441,6 +443,19 @@ attn_plan_scan_kernel(const int* __restrict__ set_num, int* __restrict__ plan, s
         pv.set_off[ns] = T;
         pv.hdr[0] = T;
     }
+    // order[]: sets by descending token count (counting sort over the <= 65 possible counts; any order within a count).
+    // The core kernel's cost per set grows with the square of the count: longest-first removes its tail.
+    __shared__ int bucket[65];
+    if (threadIdx.x < 65) bucket[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < ns; i += 1024) atomicAdd(&bucket[min(pv.nu[i], 64)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int c = 64; c >= 0; --c) { const int n = bucket[c]; bucket[c] = run; run += n; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ns; i += 1024) pv.order[atomicAdd(&bucket[min(pv.nu[i], 64)], 1)] = i;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -501,7 +516,8 @@ attn_core_kernel(const float* __restrict__ qbuf, const float* __restrict__ kvbuf
     ns = ns < max_sets ? ns : max_sets;
     uint32_t phase = 0;
 
-    for (int set = blockIdx.x; set < ns; set += gridDim.x, phase ^= 1) {
+    for (int si = blockIdx.x; si < ns; si += gridDim.x, phase ^= 1) {
+        const int set = __ldg(pv.order + si);                          // longest sets first
 #ifdef DSVT_CORE_PHASE_PROFILE
         const long long t_begin = clock64();
 #endif
@@ -540,7 +556,7 @@ attn_core_kernel(const float* __restrict__ qbuf, const float* __restrict__ kvbuf
         }
         mbar_wait(&kv_bar, phase);
         __syncthreads();
-        if (set == (int) blockIdx.x) CP(2);
+        if (si == (int) blockIdx.x) CP(2);
 #ifdef DSVT_CORE_PHASE_PROFILE
         long long t_staged = 0;
         if (tid == 0) { t_staged = clock64(); atomicAdd((unsigned long long*) &g_split_prof[36], (unsigned long long) (t_staged - t_begin)); }
@@ -611,7 +627,7 @@ attn_core_kernel(const float* __restrict__ qbuf, const float* __restrict__ kvbuf
                     op1[d4] = make_float4(acc1[2 * d4].x * inv1, acc1[2 * d4].y * inv1, acc1[2 * d4 + 1].x * inv1, acc1[2 * d4 + 1].y * inv1);
             }
         }
-        if (set == (int) blockIdx.x) CP(3);
+        if (si == (int) blockIdx.x) CP(3);
         __syncthreads();        // shared memory is recycled by the next set
 #ifdef DSVT_CORE_PHASE_PROFILE
         if (tid == 0) {
