@@ -192,6 +192,7 @@ def run_steps(slots, streams, n_steps, host):
 
 def plugin_breakdown(slot, cfg, peaks, reps=3):
     """Per-plugin device time (CUDA events, eager launches on the slot's buffers) + roofline numbers."""
+    import numpy as np
     import torch
     capi = importlib.import_module("dsvt-ai-trt_b200.capi")
     f = slot.frame
@@ -296,6 +297,22 @@ def plugin_breakdown(slot, cfg, peaks, reps=3):
                                   "flops": None},
                     "out_proj_gemm": {"us": round(c, 2), "flops": 2 * C * C * V, "mma_flops_issued": split * 2 * C * C * V,
                                       "bytes": 4 * V * 2 * C + 2 * split * 2 * C * C}}
+    # next #4 (not part of the frame): the FFN's two linear layers (src/dsvt-ai-trt.cpp:494-529) on the FP32-accurate
+    # tensor-core GEMM, with the GeluPlugin fused into the first one's epilogue
+    if pipeline_prec:
+        rng = np.random.default_rng(5)
+        l1 = capi.Linear((rng.standard_normal((Fc, C)) * 0.06).astype(np.float32), (rng.standard_normal(Fc) * 0.02).astype(np.float32),
+                         precision=f.precision)
+        l2 = capi.Linear((rng.standard_normal((C, Fc)) * 0.06).astype(np.float32), (rng.standard_normal(C) * 0.02).astype(np.float32),
+                         precision=f.precision)
+        hid = torch.empty(cfg.max_pillars_num, Fc, device="cuda")
+        us1 = timed(lambda: l1.rows(f.src, f.vox.pillar_num, activation=1, out=hid))
+        us2 = timed(lambda: l2.rows(hid, f.vox.pillar_num, out=f.src_b))
+        res["ffn_linear1_gelu"] = {"us": us1, "flops": 2 * C * Fc * V, "bytes": 4 * V * (C + Fc), "calls_per_frame": 0,
+                                   "scope": "next#4: TensorRT FullyConnected 192->384 + GeluPlugin in one kernel; not in the frame"}
+        res["ffn_linear2"] = {"us": us2, "flops": 2 * C * Fc * V, "bytes": 4 * V * (C + Fc) + 4 * V * C, "calls_per_frame": 0,
+                              "scope": "next#4: TensorRT FullyConnected 384->192 (two 192-wide K blocks); not in the frame"}
+        del l1, l2, hid
     lib.dsvt_debug_set_gemm_sm_fraction(prev_frac)
     for k, r in res.items():
         if r.get("bytes"):

@@ -403,6 +403,18 @@ class Linear:
                "dsvt_linear_launch")
         return out
 
+    def rows(self, x, rows, activation=0, out=None, zero_tails=1):
+        """Plugin-style form (FP32_TC / FP16_GEMM weights): valid row count on the device, optional fused GELU
+        (activation=1), rows [rows, max_rows) zero-filled.  x [max_rows, K] -> [max_rows, N]."""
+        _need(x, torch.float32, "x")
+        _need(rows, torch.int32, "rows")
+        max_rows = x.shape[0]
+        out = torch.empty(max_rows, self.N, dtype=torch.float32, device=x.device) if out is None else out
+        _check(_lib().dsvt_linear_rows_launch(c_void_p(self.handle), _ptr(x), _ptr(rows), c_int32(max_rows),
+                                              c_int32(activation), _ptr(out), c_int32(zero_tails), _stream()),
+               "dsvt_linear_rows_launch")
+        return out
+
     def close(self):
         if getattr(self, "handle", None):
             _lib().dsvt_linear_weights_destroy(c_void_p(self.handle))

@@ -98,6 +98,9 @@ struct GemmRole {
     const int* plan;        // attention plan (per-batch stride plan_stride ints) or nullptr: when set, output row of voxel v
     size_t plan_stride;     //   is its TOKEN position set_off[set(v)] + u(v) (set-major order), not v
     int pad_hi;             // floats inserted in front of columns 96..191 (K / V rows: bank-conflict-free head layout)
+    int lda;                // floats per row of a0 / a1 (192 for the attention tensors; K for a wider linear layer)
+    int accumulate;         // 1: add to the rows already in `out` (second 192-wide K block of a linear layer)
+    int act;                // 0: none, 1: GELU (tanh form, gelu.cu:201-211) on the finished value
 };
 struct GemmRoles { GemmRole r[3]; };
 
@@ -117,6 +120,12 @@ __device__ __forceinline__ void ldg256(const float* p, float* d) {
 __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+// GELU, tanh form with the reference's constants (gelu.cu:201-211, params.h:75-77) as the logistic identity
+// 0.5 + 0.5 tanh(u) = 1 / (1 + e^(-2u)) -- the same f32 formulation as rowwise.cu's GeluPlugin kernel
+__device__ __forceinline__ float gelu_tanh(float x) {
+    const float u = x * (0.035677408136300125f * x * x + 0.7978845608028654f);
+    return x / (1.0f + __expf(-2.0f * u));
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -132,8 +141,8 @@ __device__ long long g_split_prof[64];
 // -> full 128-byte row segments to global memory).
 template <bool SPLIT>
 __global__ void __launch_bounds__(kThreadsG, 1)
-proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num, int max_pillars, int max_sets,
-                 int zero_tails)
+proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num, int rows_host, int max_pillars,
+                 int max_sets, int zero_tails)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t w_full[kNumK], a_full[kAStages], a_empty[kAStages], acc_full[2], acc_empty[2];
@@ -144,7 +153,7 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
     const int b = blockIdx.y;
     const int role_id = blockIdx.x % n_roles, t0 = blockIdx.x / n_roles, stride = gridDim.x / n_roles;
     const GemmRole g = roles.r[role_id];
-    int V = voxel_num[b];
+    int V = voxel_num ? voxel_num[b] : rows_host;       // valid rows: device-side count, or the host's (plain linear layer)
     V = V < max_pillars ? V : max_pillars;
     const int n_tiles = (max_pillars + kBM - 1) / kBM, valid_tiles = (V + kBM - 1) / kBM;
     const int cnt = valid_tiles > t0 ? (valid_tiles - t0 + stride - 1) / stride : 0;    // row tiles this CTA computes
@@ -153,8 +162,8 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
     constexpr int rot = 0;
     if (cnt == 0 && !zero_tails) return;
     float* out = g.out + (size_t) b * max_pillars * g.ld_out + g.col0;
-    const float* a0 = g.a0 + (size_t) b * max_pillars * kC;
-    const float* a1 = g.a1 ? g.a1 + (size_t) b * max_pillars * kC : nullptr;
+    const float* a0 = g.a0 + (size_t) b * max_pillars * g.lda;
+    const float* a1 = g.a1 ? g.a1 + (size_t) b * max_pillars * g.lda : nullptr;
     if (tid == 0) SP(0);
 
     if (tid == 0) {
@@ -183,8 +192,8 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
             const int n = gs / kStepsPerTile, s = gs - n * kStepsPerTile;
             const int kc = ((s >> 1) + rot) % kNumK, row = (t0 + n * stride) * kBM + (s & 1) * 64 + rl;
             if (row < V) {
-                ldg256(a0 + (size_t) row * kC + kc * kBK + c16 * 8, &d[0]);      // one 256-bit load: full 32-byte sectors
-                if (a1) ldg256(a1 + (size_t) row * kC + kc * kBK + c16 * 8, &d[8]);
+                ldg256(a0 + (size_t) row * g.lda + kc * kBK + c16 * 8, &d[0]);   // one 256-bit load: full 32-byte sectors
+                if (a1) ldg256(a1 + (size_t) row * g.lda + kc * kBK + c16 * 8, &d[8]);
                 else {
 #pragma unroll
                     for (int e = 8; e < 16; ++e) d[e] = 0.f;
@@ -305,6 +314,11 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
                         // out_mul is a power of two: the product is exact, so this is one rounding of (acc + bias)
                         float4 ov = make_float4((v[rr].x * g.out_mul + bb.x) * g.post_mul, (v[rr].y * g.out_mul + bb.y) * g.post_mul,
                                                 (v[rr].z * g.out_mul + bb.z) * g.post_mul, (v[rr].w * g.out_mul + bb.w) * g.post_mul);
+                        if (g.accumulate && orow[rr] >= 0 && grow < V) {   // second K block: add to the first block's rows
+                            const float4 pv4 = *reinterpret_cast<const float4*>(outc + (size_t) orow[rr] * g.ld_out + j0);
+                            ov.x += pv4.x; ov.y += pv4.y; ov.z += pv4.z; ov.w += pv4.w;
+                        }
+                        if (g.act == 1) { ov.x = gelu_tanh(ov.x); ov.y = gelu_tanh(ov.y); ov.z = gelu_tanh(ov.z); ov.w = gelu_tanh(ov.w); }
                         if (grow >= V) ov = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (orow[rr] >= 0) *reinterpret_cast<float4*>(outc + (size_t) orow[rr] * g.ld_out + j0) = ov;
                     }
@@ -321,7 +335,7 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
         if (lane == 0 && cnt > 0) {
             // pull this CTA's row tiles into L2 as large sequential requests (a tile is 96 KB contiguous per source); the
             // producers then read them in 128-byte-per-row K chunks, a pattern that wastes DRAM pages when it misses L2
-            for (int n = 0; n < cnt; ++n) {
+            for (int n = 0; n < cnt && g.lda == kC; ++n) {           // (a tile is contiguous only when rows are 192 wide)
                 const int row0 = (t0 + n * stride) * kBM;
                 const uint32_t bytes = (uint32_t) ((V - row0 < kBM ? V - row0 : kBM) * kC * sizeof(float));
                 l2_prefetch(a0 + (size_t) row0 * kC, bytes);
@@ -684,6 +698,103 @@ struct SplitBlobHeader {
 
 }  // namespace
 
+static int gemm_sm_fraction();
+
+// One 192 x 192 weight block W[n0 .. n0+192][k0 .. k0+192] (row stride ldw) as the kernel's image: six K chunks of
+// [hi 192x32 | lo 192x32] FP16, pre-scaled by 2^sh.
+static void build_block_image(const float* W, int ldw, int n0, int k0, int sh, uint8_t* img) {
+    const float ws = ldexpf(1.0f, sh);
+    for (int kc = 0; kc < kNumK; ++kc) {
+        uint8_t* hi_img = img + (size_t) kc * kWChunkBytes;
+        uint8_t* lo_img = hi_img + kBTerm;
+        for (int n = 0; n < kBN; ++n)
+            for (int c16 = 0; c16 < kBK / 8; ++c16)
+                for (int e = 0; e < 8; ++e) {
+                    const float w = W[(size_t) (n0 + n) * ldw + k0 + kc * kBK + c16 * 8 + e] * ws;
+                    const __half h = __float2half_rn(w);
+                    const __half l = __float2half_rn(w - __half2float(h));
+                    const uint16_t hb = __half_as_ushort(h), lb = __half_as_ushort(l);
+                    const size_t off = (size_t) c16 * (kBN * 16) + (size_t) n * 16 + e * 2;
+                    memcpy(hi_img + off, &hb, 2);
+                    memcpy(lo_img + off, &lb, 2);
+                }
+    }
+}
+static int scale_shift(const float* W, size_t n) {
+    float maxabs = 0.f;
+    for (size_t t = 0; t < n; ++t) maxabs = fmaxf(maxabs, fabsf(W[t]));
+    if (!(maxabs > 0.f) || !std::isfinite(maxabs)) return 0;
+    int e;
+    frexpf(maxabs, &e);              // maxabs = m * 2^e, m in [0.5, 1)
+    int sh = 14 - e;                 // maxabs * 2^sh in [2^13, 2^14)
+    return sh > 60 ? 60 : (sh < -60 ? -60 : sh);
+}
+
+// ---- dense linear layer on the same kernel: y[M,N] = act(x[M,K] W[N,K]^T + b), K and N multiples of 192 -------------
+// Device blob: [N/192][K/192] block images (147456 B each), then bias [N] f32.  One launch per 192-wide K block (the
+// CTA's resident weight image is one block); the second and later K blocks add to the rows written by the first.
+void* linear_split_prepare(int N, int K, const float* W, const float* b, float* out_mul) {
+    const int nb = N / kBN, kb = K / kC;
+    const size_t img_bytes = (size_t) nb * kb * kWRoleBytes;
+    std::vector<uint8_t> host(img_bytes + (size_t) N * sizeof(float));
+    const int sh = scale_shift(W, (size_t) N * K);
+    *out_mul = ldexpf(1.0f, -sh);
+    for (int i = 0; i < nb; ++i)
+        for (int j = 0; j < kb; ++j)
+            build_block_image(W, K, i * kBN, j * kC, sh, host.data() + ((size_t) i * kb + j) * kWRoleBytes);
+    float* bias = reinterpret_cast<float*>(host.data() + img_bytes);
+    for (int n = 0; n < N; ++n) bias[n] = b ? b[n] : 0.f;
+    void* dev = nullptr;
+    if (cudaMalloc(&dev, host.size()) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(dev, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(dev); return nullptr; }
+    return dev;
+}
+
+int linear_split_launch(const void* blob, int N, int K, float out_mul, bool split, int act, const float* x,
+                        const int* rows_dev, int rows_host, int max_rows, float* y, int zero_tails, cudaStream_t st)
+{
+    const int nb = N / kBN, kb = K / kC;
+    const uint8_t* img = static_cast<const uint8_t*>(blob);
+    const float* bias = reinterpret_cast<const float*>(img + (size_t) nb * kb * kWRoleBytes);
+    static float* zero_bias = nullptr;          // K blocks after the first add no bias
+    if (!zero_bias) {
+        DSVT_CUDA(cudaMalloc(&zero_bias, kBN * sizeof(float)));
+        DSVT_CUDA(cudaMemset(zero_bias, 0, kBN * sizeof(float)));
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        DSVT_CUDA(cudaFuncSetAttribute(proj_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<true>::total));
+        DSVT_CUDA(cudaFuncSetAttribute(proj_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<false>::total));
+        attr_set = true;
+    }
+    for (int j = 0; j < kb; ++j)
+        for (int i0 = 0; i0 < nb; i0 += 3) {            // up to three 192-column output blocks (roles) per launch
+            const int n_roles = nb - i0 < 3 ? nb - i0 : 3;
+            GemmRoles roles;
+            for (int r = 0; r < 3; ++r) {
+                const int i = i0 + (r < n_roles ? r : 0);
+                GemmRole& g = roles.r[r];
+                g.a0 = x + (size_t) j * kC; g.a1 = nullptr; g.lda = K;
+                g.wimg = img + ((size_t) i * kb + j) * kWRoleBytes;
+                g.bias = j == 0 ? bias + i * kBN : zero_bias;
+                g.out = y; g.ld_out = N; g.col0 = i * kBN;
+                g.out_mul = out_mul; g.post_mul = 1.0f;
+                g.plan = nullptr; g.plan_stride = 0; g.pad_hi = 0;
+                g.accumulate = j > 0;
+                g.act = j == kb - 1 ? act : 0;
+            }
+            const int per = sm_count() * gemm_sm_fraction() / 100;
+            const int grid = per >= n_roles ? per / n_roles * n_roles : n_roles;
+            const int zt = (zero_tails && j == 0) ? 1 : 0;
+            if (split)
+                proj_gemm_kernel<true><<<dim3(grid, 1), kThreadsG, Lay<true>::total, st>>>(roles, n_roles, rows_dev, rows_host, max_rows, 1, zt);
+            else
+                proj_gemm_kernel<false><<<dim3(grid, 1), kThreadsG, Lay<false>::total, st>>>(roles, n_roles, rows_dev, rows_host, max_rows, 1, zt);
+            DSVT_LAUNCH_CHECK();
+        }
+    return DSVT_OK;
+}
+
 // Device blob: [kRoles][kNumK][hi 12288 | lo 12288] weight images, then bias [kRoles][192] f32.
 // out_mul[] (host) receives the per-role power-of-two that undoes the weight pre-scaling.
 void* attention_split_prepare(const float* w_in, const float* b_in, const float* w_out, const float* b_out,
@@ -855,6 +966,7 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
         g.plan = plan;
         g.plan_stride = plan_stride;
         g.pad_hi = r == 0 ? 0 : 4;
+        g.lda = kC; g.accumulate = 0; g.act = 0;
     }
     {
         GemmRole& g = out_roles.r[0];
@@ -865,14 +977,15 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
         g.out_mul = out_mul[3];
         g.post_mul = 1.0f;
         g.plan = nullptr; g.plan_stride = 0; g.pad_hi = 0;
+        g.lda = kC; g.accumulate = 0; g.act = 0;
         out_roles.r[1] = out_roles.r[2] = g;
     }
     if (split) {
         proj_gemm_kernel<true><<<dim3(grid_in, p->batch), kThreadsG, Lay<true>::total, st>>>(
-            in_roles, 3, voxel_num, p->max_pillars_num, p->max_set_num, 0);
+            in_roles, 3, voxel_num, 0, p->max_pillars_num, p->max_set_num, 0);
     } else {
         proj_gemm_kernel<false><<<dim3(grid_in, p->batch), kThreadsG, Lay<false>::total, st>>>(
-            in_roles, 3, voxel_num, p->max_pillars_num, p->max_set_num, 0);
+            in_roles, 3, voxel_num, 0, p->max_pillars_num, p->max_set_num, 0);
     }
     DSVT_LAUNCH_CHECK();
     if ((rc = stage_mark(1, st)) != DSVT_OK) return rc;
@@ -885,10 +998,10 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
     if ((rc = stage_mark(2, st)) != DSVT_OK) return rc;
     if (split) {
         proj_gemm_kernel<true><<<dim3(grid_out, p->batch), kThreadsG, Lay<true>::total, st>>>(
-            out_roles, 1, voxel_num, p->max_pillars_num, p->max_set_num, p->zero_tails);
+            out_roles, 1, voxel_num, 0, p->max_pillars_num, p->max_set_num, p->zero_tails);
     } else {
         proj_gemm_kernel<false><<<dim3(grid_out, p->batch), kThreadsG, Lay<false>::total, st>>>(
-            out_roles, 1, voxel_num, p->max_pillars_num, p->max_set_num, p->zero_tails);
+            out_roles, 1, voxel_num, 0, p->max_pillars_num, p->max_set_num, p->zero_tails);
     }
     DSVT_LAUNCH_CHECK();
     return stage_mark(3, st);

@@ -134,10 +134,18 @@ tc_linear_kernel(const float* __restrict__ X, const uint8_t* __restrict__ Wimg, 
 
 using namespace dsvt;
 
+namespace dsvt {   // attention_split.cu: the persistent split-precision GEMM as a plain linear layer
+void* linear_split_prepare(int N, int K, const float* W, const float* b, float* out_mul);
+int linear_split_launch(const void* blob, int N, int K, float out_mul, bool split, int act, const float* x,
+                        const int* rows_dev, int rows_host, int max_rows, float* y, int zero_tails, cudaStream_t st);
+}
+
 struct dsvt_linear_weights {
     int N, K, precision;
-    uint8_t* img;     // device: [N/64 tiles][K chunks][64 rows][16 B]
+    uint8_t* img;     // device: [N/64 tiles][K chunks][64 rows][16 B]           (TF32 / FP16 single-tile kernel)
     float* bias;      // device [N]
+    void* split_blob; // device: 192 x 192 block images + bias                   (FP32_TC / FP16_GEMM persistent kernel)
+    float out_mul;
 };
 
 static uint16_t f32_to_f16_bits(float f) { return __half_as_ushort(__float2half_rn(f)); }
@@ -151,6 +159,21 @@ static uint32_t f32_to_tf32_bits(float f) {
 extern "C" dsvt_linear_weights* dsvt_linear_weights_create(int32_t N, int32_t K, const float* W, const float* b,
                                                            int32_t precision)
 {
+    if (precision == DSVT_ATTN_FP32_TC || precision == DSVT_ATTN_FP16_GEMM) {
+        if (N <= 0 || K <= 0 || N % 192 || K % 192 || !W) {
+            set_last_error("dsvt_linear_weights_create: the FP32_TC / FP16_GEMM linear layer needs N %% 192 == 0 and K %% 192 == 0");
+            return nullptr;
+        }
+        auto* lw = new (std::nothrow) dsvt_linear_weights{N, K, precision, nullptr, nullptr, nullptr, 1.0f};
+        if (!lw) return nullptr;
+        lw->split_blob = dsvt::linear_split_prepare(N, K, W, b, &lw->out_mul);
+        if (!lw->split_blob) {
+            set_last_error("dsvt_linear_weights_create: CUDA allocation/copy failed");
+            delete lw;
+            return nullptr;
+        }
+        return lw;
+    }
     const int esize = precision == DSVT_ATTN_FP16 ? 2 : 4;
     const int epc = 16 / esize;
     if (N <= 0 || K <= 0 || N % kTileN || K % (2 * epc) || !W || (precision != DSVT_ATTN_FP16 && precision != DSVT_ATTN_TF32)) {
@@ -170,7 +193,7 @@ extern "C" dsvt_linear_weights* dsvt_linear_weights_create(int32_t N, int32_t K,
             }
         }
     }
-    auto* lw = new (std::nothrow) dsvt_linear_weights{N, K, precision, nullptr, nullptr};
+    auto* lw = new (std::nothrow) dsvt_linear_weights{N, K, precision, nullptr, nullptr, nullptr, 1.0f};
     if (!lw) return nullptr;
     std::vector<float> zero(N, 0.f);
     if (cudaMalloc(&lw->img, img.size()) != cudaSuccess || cudaMalloc(&lw->bias, N * sizeof(float)) != cudaSuccess ||
@@ -188,6 +211,7 @@ extern "C" void dsvt_linear_weights_destroy(dsvt_linear_weights* w) {
     if (!w) return;
     cudaFree(w->img);
     cudaFree(w->bias);
+    cudaFree(w->split_blob);
     delete w;
 }
 
@@ -196,6 +220,11 @@ extern "C" int dsvt_linear_launch(const dsvt_linear_weights* w, const float* x, 
     DSVT_CHECK_ARG(w && x && y && M >= 0, "NULL argument");
     DSVT_CHECK_ARG(!(((uintptr_t) x | (uintptr_t) y) & 15), "16-B alignment");
     if (M == 0) return DSVT_OK;
+    if (w->split_blob) {
+        DSVT_CHECK_ARG(!((uintptr_t) x & 31), "32-B alignment of x (256-bit loads)");
+        return dsvt::linear_split_launch(w->split_blob, w->N, w->K, w->out_mul, w->precision == DSVT_ATTN_FP32_TC, 0, x,
+                                         nullptr, M, M, y, 0, reinterpret_cast<cudaStream_t>(stream));
+    }
     const int esize = w->precision == DSVT_ATTN_FP16 ? 2 : 4;
     const size_t smem = (size_t) w->K * esize * (kTileM + kTileN);
     DSVT_CHECK_ARG(smem <= 220 * 1024, "K too large for a single-stage tile");
@@ -210,4 +239,15 @@ extern "C" int dsvt_linear_launch(const dsvt_linear_weights* w, const float* x, 
     }
     DSVT_LAUNCH_CHECK();
     return DSVT_OK;
+}
+
+extern "C" int dsvt_linear_rows_launch(const dsvt_linear_weights* w, const float* x, const int32_t* rows, int32_t max_rows,
+                                       int32_t activation, float* y, int32_t zero_tails, dsvt_stream_t stream)
+{
+    DSVT_CHECK_ARG(w && x && y && rows && max_rows >= 1, "NULL argument");
+    DSVT_CHECK_ARG(w->split_blob != nullptr, "built for precision DSVT_ATTN_FP32_TC / DSVT_ATTN_FP16_GEMM weights only");
+    DSVT_CHECK_ARG(activation == 0 || activation == 1, "activation: 0 none, 1 GELU");
+    DSVT_CHECK_ARG(!(((uintptr_t) x & 31) | ((uintptr_t) y & 15)), "alignment (x 32 B, y 16 B)");
+    return dsvt::linear_split_launch(w->split_blob, w->N, w->K, w->out_mul, w->precision == DSVT_ATTN_FP32_TC, activation, x,
+                                     rows, 0, max_rows, y, zero_tails, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -302,6 +302,15 @@ dsvt_linear_weights* dsvt_linear_weights_create(int32_t N, int32_t K, const floa
 void dsvt_linear_weights_destroy(dsvt_linear_weights* w);
 /* x [M,K] f32 (device) -> y [M,N] f32 (device) */
 int dsvt_linear_launch(const dsvt_linear_weights* w, const float* x, int32_t M, float* y, dsvt_stream_t stream);
+/*
+ * Weights created with precision DSVT_ATTN_FP32_TC (FP32-accurate: FP16 hi+lo split operands, 3 tcgen05 MMAs per product)
+ * or DSVT_ATTN_FP16_GEMM run on the attention pipeline's persistent GEMM kernel; they need N % 192 == 0, K % 192 == 0
+ * (the FFN 192->384->192 and PFN / pos-embed 192->192 layers).  This form takes the valid row count from the device
+ * (rows [1] i32, as the plugins do), optionally applies GELU (activation = 1: the FFN's first linear + GeluPlugin in one
+ * pass) and zero-fills rows [rows, max_rows).  x [max_rows,K] -> y [max_rows,N].
+ */
+int dsvt_linear_rows_launch(const dsvt_linear_weights* w, const float* x, const int32_t* rows, int32_t max_rows,
+                            int32_t activation, float* y, int32_t zero_tails, dsvt_stream_t stream);
 
 /* ------------------------------------------------------------------------ *
  * (next #3) TorchScatterMaxPlugin::enqueue     plugins/src/torchScatterMax.cu:282-309 (kernel :201-262)
