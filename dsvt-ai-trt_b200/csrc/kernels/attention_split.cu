@@ -514,7 +514,6 @@ attn_core_kernel(const float* __restrict__ qbuf, const float* __restrict__ kvbuf
     __shared__ float s_cmask[kH][S];    // ... compacted, log2 domain: [head][token]
 
     const int b = blockIdx.y, tid = threadIdx.x;
-    const int n_roles = 0; (void) n_roles;
 #define CP(i) do { if (blockIdx.x == 5 && blockIdx.y == 0 && threadIdx.x == 0) g_split_prof[32 + i] = clock64(); } while (0)
     CP(0);
     const PlanView pv = plan_view(const_cast<int*>(plan) + (size_t) b * plan_stride, max_sets, max_pillars);
