@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32_cuda", "fp32_tc", "tf32", "fp16", "fp16_gemm"])
     ap.add_argument("--points", type=int, default=N_POINTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ffn-leg", action="store_true",
+                    help="skip the extra leg that runs the FFN linears (SURVEY 8(f) #4) inside the frame")
     ap.add_argument("--no-fp16-config", action="store_true",
                     help="skip the extra BASELINE.json configs[2] (FP16 tensor-core attention) measurement")
     return ap.parse_args()
@@ -465,6 +467,41 @@ def main():
         best = max(("fused_tcgen05_kernel", "gemm_pipeline"), key=lambda k: fp16_cfg[k]["value"])
         fp16_cfg["value"], fp16_cfg["e2e"], fp16_cfg["best"] = fp16_cfg[best]["value"], fp16_cfg[best]["e2e"], best
 
+    # ---- the same frames with the FFN linears executed (every DSVT block a real data flow) ----------
+    ffn_cfg = None
+    if args.precision == "fp32" and not args.no_ffn_leg:
+        ffn_cfg = {"unit": UNIT,
+                   "workload": "same frames and plugins + the 16 FFN linears (192->384, 384->192 per encoder layer, "
+                               "src/dsvt-ai-trt.cpp:494-529) on the FP32-accurate tcgen05 linear kernel; PFN / pos-embed MLPs, "
+                               "BEV backbone and head still not executed"}
+        for name in ("graph", "fused"):
+            slots_f = []
+            for i, s in enumerate(slots):
+                fr = pipeline.HotPathFrame(cfg, weights, precision=precision, seed=sharding.global_frame_id(rank, world, i),
+                                           ffn=name)
+                sf = Slot.__new__(Slot)
+                sf.frame, sf.n = fr, s.n
+                sf.host_points, sf.host_n, sf.host_boxes, sf.host_valid = s.host_points, s.host_n, s.host_boxes, s.host_valid
+                fr.points.copy_(s.frame.points)
+                fr.points_size.copy_(s.frame.points_size)
+                sf.graph = None
+                sf.capture(streams[i % S])
+                slots_f.append(sf)
+            run_steps(slots_f, streams, args.warmup, host=False)
+            barrier(world)
+            ms_f = max_over_ranks(run_steps(slots_f, streams, args.steps, host=False), world)
+            run_steps(slots_f, streams, 1, host=True)
+            barrier(world)
+            e2e_f = max_over_ranks(run_steps(slots_f, streams, args.steps, host=True), world)
+            barrier(world)
+            ffn_cfg[name] = {"value": round(F * world * args.steps / (ms_f * 1e-3), 2),
+                             "e2e": round(F * world * args.steps / (e2e_f * 1e-3), 2),
+                             "launches_per_frame": int(slots_f[0].frame.launches_per_frame),
+                             "form": {"graph": "FC -> GeluPlugin -> FC (the reference graph's nodes)",
+                                      "fused": "FC with GELU epilogue -> FC (GeluPlugin folded into the linear)"}[name]}
+            del slots_f
+        torch.cuda.empty_cache()
+
     if rank != 0:
         return 0
     frames = F * world * args.steps
@@ -555,6 +592,7 @@ def main():
         "plugins": plugins,
         "frame_us_sum_of_plugins": round(frame_us, 1),
         "fp16_config": fp16_cfg,
+        "ffn_in_frame": ffn_cfg,
         "gathered_boxes": None if gathered is None else int(gathered[1].sum()),
     }
     if not args.no_cpu_baseline:

@@ -14,6 +14,12 @@ The TensorRT-native layers between the plugins (PFN, pos-embed MLPs, FFN linears
 section 8(f) "next" rows) are not executed: their outputs are stood in by fixed synthetic tensors of the right
 shape, so every hot-path plugin runs on full-size, data-dependent inputs (voxel counts, set indices and masks
 come from the real voxeliser / partition of the frame's cloud).
+
+``ffn`` widens the frame by SURVEY.md 8(f) #4: the two FFN linears of every encoder layer
+(fullyConnected_gelu_fullyConnected, src/dsvt-ai-trt.cpp:494-529) run on the FP32-accurate tensor-core linear
+kernel (dsvt_linear_rows_launch), so a DSVT block becomes a real data flow from its input rows to its output rows:
+    "graph": FC 192->384 -> GeluPlugin -> FC 384->192        (the reference graph's three nodes)
+    "fused": FC 192->384 with the GELU in its epilogue -> FC 384->192   (one pass less over the 384-wide rows)
 """
 import numpy as np
 import torch
@@ -27,26 +33,42 @@ class FrameWeights:
     def __init__(self, cfg, seed=0, device="cuda"):
         rng = np.random.default_rng(seed)
         C = cfg.channel_num
-        self.attn = []
+        self.attn, self.attn_host = [], []          # device images / the host arrays they were made from (for the tests)
         for _ in range(cfg.num_blocks * 2):
-            self.attn.append(capi.AttentionWeights(
-                (rng.standard_normal((3 * C, C)) * 0.06).astype(np.float32),
-                (rng.standard_normal(3 * C) * 0.02).astype(np.float32),
-                (rng.standard_normal((C, C)) * 0.06).astype(np.float32),
-                (rng.standard_normal(C) * 0.02).astype(np.float32), C, cfg.num_heads))
+            self.attn_host.append(((rng.standard_normal((3 * C, C)) * 0.06).astype(np.float32),
+                                   (rng.standard_normal(3 * C) * 0.02).astype(np.float32),
+                                   (rng.standard_normal((C, C)) * 0.06).astype(np.float32),
+                                   (rng.standard_normal(C) * 0.02).astype(np.float32)))
+            self.attn.append(capi.AttentionWeights(*self.attn_host[-1], C, cfg.num_heads))
         # stand-ins for the two PFN layer outputs (src/dsvt-ai-trt.cpp:577-590), shared by all frame slots (read-only)
         g = torch.Generator(device="cpu").manual_seed(seed + 1)
         self.pfn_out = [torch.randn(cfg.max_points_num_voxel_filter, f, generator=g).to(device) for f in cfg.pfn_channels]
         n_ln = cfg.num_blocks * 7
         self.gamma = torch.from_numpy((1.0 + 0.1 * rng.standard_normal((n_ln, C))).astype(np.float32)).to(device)
         self.beta = torch.from_numpy((0.1 * rng.standard_normal((n_ln, C))).astype(np.float32)).to(device)
+        # FFN linears (fullyConnected_gelu_fullyConnected, src/dsvt-ai-trt.cpp:494-529): created on first use
+        self._ffn_host = [((rng.standard_normal((cfg.ffn_channel_num, C)) * 0.07).astype(np.float32),
+                           (rng.standard_normal(cfg.ffn_channel_num) * 0.02).astype(np.float32),
+                           (rng.standard_normal((C, cfg.ffn_channel_num)) * 0.05).astype(np.float32),
+                           (rng.standard_normal(C) * 0.02).astype(np.float32)) for _ in range(cfg.num_blocks * 2)]
+        self._ffn = None
+
+    @property
+    def ffn(self):
+        """[(Linear 192->384, Linear 384->192)] per encoder layer, FP32-accurate tensor-core weights images."""
+        if self._ffn is None:
+            self._ffn = [(capi.Linear(w1, b1, precision=capi.DSVT_ATTN_FP32_TC),
+                          capi.Linear(w2, b2, precision=capi.DSVT_ATTN_FP32_TC)) for w1, b1, w2, b2 in self._ffn_host]
+        return self._ffn
 
 
 class HotPathFrame:
     """Buffers + launch sequence for one frame slot (one CUDA stream owns one slot)."""
 
-    def __init__(self, cfg, weights, precision=capi.DSVT_ATTN_FP32, seed=0, device="cuda", fuse_ln=True, share_plans=True):
-        self.cfg, self.w, self.precision, self.fuse_ln = cfg, weights, precision, fuse_ln
+    def __init__(self, cfg, weights, precision=capi.DSVT_ATTN_FP32, seed=0, device="cuda", fuse_ln=True, share_plans=True,
+                 ffn="off"):
+        assert ffn in ("off", "graph", "fused")
+        self.cfg, self.w, self.precision, self.fuse_ln, self.ffn = cfg, weights, precision, fuse_ln, ffn
         # GEMM-pipeline attention: one plan per (window partition, axis), shared by the two layers that use it
         self.share_plans = share_plans and precision in (capi.DSVT_ATTN_FP32_TC, capi.DSVT_ATTN_FP16_GEMM)
         self.plans = {}
@@ -72,6 +94,9 @@ class HotPathFrame:
         self.src = torch.empty(mp, C, device=device)
         self.src_b = torch.empty(mp, C, device=device)
         self.gelu_out = torch.empty(mp, F, device=device)
+        if ffn != "off":
+            self.ffn_h = torch.empty(mp, F, device=device)      # FC 192->384 output (graph form only)
+            self.ffn_o = torch.empty(mp, C, device=device)      # FC 384->192 output
         self.x_a = torch.empty(mp, C, device=device)
         self.x_b = torch.empty(mp, C, device=device)
         self.blk_out = [torch.empty(mp, C, device=device) for _ in range(2)]
@@ -119,10 +144,20 @@ class HotPathFrame:
                                          plan=self.plans.get((blk % 2, enc)))
                 capi.layer_norm(self.attn_out, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=x,
                                 out=self.src); ln += 1                                     # norm1(y + x)   :669-676
-                capi.gelu(self.ffn_hidden, V, out=self.gelu_out)                           # :519 (inside the FFN)
+                ffn_out = self.ffn_out
+                if self.ffn == "off":
+                    capi.gelu(self.ffn_hidden, V, out=self.gelu_out)                       # :519 (inside the FFN)
+                else:
+                    fc1, fc2 = w.ffn[blk * 2 + enc]
+                    if self.ffn == "graph":
+                        fc1.rows(self.src, V, out=self.ffn_h)                              # :513  FC 192->384
+                        capi.gelu(self.ffn_h, V, out=self.gelu_out)                        # :519  GeluPlugin
+                    else:
+                        fc1.rows(self.src, V, activation=1, out=self.gelu_out)             # FC + GELU epilogue
+                    ffn_out = fc2.rows(self.gelu_out, V, out=self.ffn_o)                   # :524  FC 384->192
                 nxt = self.x_a if enc == 0 else self.x_b
                 if not self.fuse_ln:
-                    capi.layer_norm(self.src, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=self.ffn_out,
+                    capi.layer_norm(self.src, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=ffn_out,
                                     out=self.src_b); ln += 1                               # norm2(src + src2) :685-690
                     capi.layer_norm(self.src_b, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=x,
                                     out=nxt); ln += 1                                      # norm(src + x)  :691-697
@@ -131,7 +166,7 @@ class HotPathFrame:
                                         out=self.blk_out[blk % 2]); ln += 1                # residual norm  :750-756
                 else:
                     # the same LayerNorms as one chained launch (rows stay in registers between stages)
-                    stages = [(self.ffn_out, w.gamma[ln], w.beta[ln]), (x, w.gamma[ln + 1], w.beta[ln + 1])]
+                    stages = [(ffn_out, w.gamma[ln], w.beta[ln]), (x, w.gamma[ln + 1], w.beta[ln + 1])]
                     ln += 2
                     if enc == 1:
                         stages.append((x_in, w.gamma[ln], w.beta[ln])); ln += 1
