@@ -3,7 +3,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_DIR = os.path.join(_HERE, "lib")
+# DSVT_B200_LIBDIR: A/B builds of the same sources (tuning experiments); the default is the in-tree build
+_LIB_DIR = os.environ.get("DSVT_B200_LIBDIR") or os.path.join(_HERE, "lib")
 
 
 class LibraryMissing(RuntimeError):

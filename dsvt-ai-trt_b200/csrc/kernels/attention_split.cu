@@ -184,7 +184,12 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
         // step g = (tile n, K chunk kc, half): rows half*64 + warp*8 + (lane & 7), 16-byte K piece c16 = lane >> 3.
         // A quarter-warp (8 lanes) writes 8 consecutive rows of one piece (128 contiguous bytes: conflict-free);
         // the four lanes that share a row read one full 128-byte line of it.
-        constexpr int kStepsPerTile = kNumK * 2, kDepth = 3;
+#ifndef DSVT_GEMM_DEPTH
+#define DSVT_GEMM_DEPTH 3          // row-piece loads in flight per producer thread (3, 4 or 6: the unroll must divide 12)
+#endif
+        constexpr int kStepsPerTile = kNumK * 2, kDepth = DSVT_GEMM_DEPTH;
+        constexpr int kUnroll = kDepth % 2 == 0 ? kDepth : 2 * kDepth;      // lcm(2 halves, kDepth): static buffer / half indices
+        static_assert(kStepsPerTile % kUnroll == 0, "producer unroll must divide the steps of a tile");
         const int total = cnt * kStepsPerTile;
         const int rl = warp * 8 + (lane & 7), c16 = lane >> 3;
         float buf[kDepth][16];                                  // [0..7] = a0 row piece, [8..15] = a1 (pos) row piece
@@ -207,9 +212,9 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
         for (int s = 0; s < kDepth - 1; ++s)
             if (s < total) issue(s, buf[s]);
 #pragma unroll 1
-        for (int g0 = 0; g0 < total; g0 += 6) {           // 6 = lcm(2 halves, kDepth): buffer / half indices stay static
+        for (int g0 = 0; g0 < total; g0 += kUnroll) {
 #pragma unroll
-            for (int u = 0; u < 6; ++u) {
+            for (int u = 0; u < kUnroll; ++u) {
                 const int gs = g0 + u;
                 if (gs + kDepth - 1 < total) issue(gs + kDepth - 1, buf[(u + kDepth - 1) % kDepth]);
                 const int cc = gs >> 1, st = cc % kAStages, r = (u & 1) * 64 + rl;
@@ -854,6 +859,7 @@ static int stage_mark(int i, cudaStream_t st) {
     return DSVT_OK;
 }
 
+static int g_skip_mask = 0;   // diagnostic (tools/ablate.py): bit 0 / 1 / 2 = do not launch the QKV GEMM / core / out-projection
 static int g_gemm_sm_fraction = -1;
 static int gemm_sm_fraction() {
     if (g_gemm_sm_fraction < 0) {
@@ -979,7 +985,8 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
         g.lda = kC; g.accumulate = 0; g.act = 0;
         out_roles.r[1] = out_roles.r[2] = g;
     }
-    if (split) {
+    if (g_skip_mask & 1) {
+    } else if (split) {
         proj_gemm_kernel<true><<<dim3(grid_in, p->batch), kThreadsG, Lay<true>::total, st>>>(
             in_roles, 3, voxel_num, 0, p->max_pillars_num, p->max_set_num, 0);
     } else {
@@ -988,14 +995,15 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
     }
     DSVT_LAUNCH_CHECK();
     if ((rc = stage_mark(1, st)) != DSVT_OK) return rc;
-    switch (p->voxel_num_set) {
+    if (!(g_skip_mask & 2)) switch (p->voxel_num_set) {
         case 24: rc = launch_core<24>(p, qbuf, kvbuf, plan, mask, set_num, o, st); break;
         case 36: rc = launch_core<36>(p, qbuf, kvbuf, plan, mask, set_num, o, st); break;
         default: rc = launch_core<48>(p, qbuf, kvbuf, plan, mask, set_num, o, st); break;
     }
     if (rc != DSVT_OK) return rc;
     if ((rc = stage_mark(2, st)) != DSVT_OK) return rc;
-    if (split) {
+    if (g_skip_mask & 4) {
+    } else if (split) {
         proj_gemm_kernel<true><<<dim3(grid_out, p->batch), kThreadsG, Lay<true>::total, st>>>(
             out_roles, 1, voxel_num, 0, p->max_pillars_num, p->max_set_num, p->zero_tails);
     } else {
@@ -1009,6 +1017,9 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
 }  // namespace dsvt
 
 extern "C" void dsvt_debug_attention_stage_timing(int enable) { dsvt::g_stage_timing = enable != 0; }
+// diagnostic: kernels of the GEMM-pipeline attention that are NOT launched (bit 0 QKV GEMM, 1 core, 2 out-projection);
+// used by tools/ablate.py to measure each kernel's marginal cost with several frames in flight.  0 = normal operation.
+extern "C" void dsvt_debug_set_attention_skip_mask(int mask) { dsvt::g_skip_mask = mask & 7; }
 // share of the SMs (percent, 5..100) the attention GEMMs launch CTAs on; initial value: DSVT_GEMM_SM_FRACTION or 100.
 // Returns the previous value.  100 = lowest latency of a single call, ~50 = best throughput with several frames in flight.
 extern "C" int dsvt_debug_set_gemm_sm_fraction(int percent) {

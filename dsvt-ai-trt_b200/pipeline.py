@@ -66,8 +66,11 @@ class HotPathFrame:
     """Buffers + launch sequence for one frame slot (one CUDA stream owns one slot)."""
 
     def __init__(self, cfg, weights, precision=capi.DSVT_ATTN_FP32, seed=0, device="cuda", fuse_ln=True, share_plans=True,
-                 ffn="off"):
+                 ffn="off", skip=()):
         assert ffn in ("off", "graph", "fused")
+        # diagnostic only (tools/ablate.py): plugin groups left out of the launch sequence to measure their marginal
+        # cost with several frames in flight -- {"vox", "smax", "part", "plan", "attn", "ln", "gelu", "m2b", "fbox"}
+        self.skip = frozenset(skip)
         self.cfg, self.w, self.precision, self.fuse_ln, self.ffn = cfg, weights, precision, fuse_ln, ffn
         # GEMM-pipeline attention: one plan per (window partition, axis), shared by the two layers that use it
         self.share_plans = share_plans and precision in (capi.DSVT_ATTN_FP32_TC, capi.DSVT_ATTN_FP16_GEMM)
@@ -117,16 +120,17 @@ class HotPathFrame:
         """Enqueue the frame's plugin invocations on the current stream."""
         cfg, w = self.cfg, self.w
         before = capi.launch_count()
-        vox = self.vox(self.points, self.points_size)
+        skip = self.skip
+        vox = self.vox if "vox" in skip else self.vox(self.points, self.points_size)
         V = vox.pillar_num
-        for k in range(len(cfg.pfn_channels)):             # :580-590 (the voxeliser's row count lets it skip the full clear)
+        for k in range(0 if "smax" in skip else len(cfg.pfn_channels)):             # :580-590 (the voxeliser's row count lets it skip the full clear)
             capi.torch_scatter_max(self.w.pfn_out[k], vox.point_index_in_voxel[0], vox.point_num_in_voxel[0], V,
                                    vox.point_num, max_point=self.max_point[k], max_voxel=self.max_voxel[k])
-        for i in (0, 1):
+        for i in (() if "part" in skip else (0, 1)):
             self.wp[i](vox.coords, V)
             self.gs[i](self.wp[i].global_index, self.wp[i].coors_in_win, self.wp[i].voxel_num_in_win,
                        self.wp[i].win_num)
-        if self.share_plans:
+        if self.share_plans and not ("plan" in skip and self.plans):
             for part in (0, 1):
                 for axis in (0, 1):
                     gs = self.gs[part]
@@ -138,15 +142,22 @@ class HotPathFrame:
             gs = self.gs[blk % 2]                      # blocks 0,2: 12x12 windows; 1,3: 24x24 shifted (:654-:1018)
             x_in = x
             for enc in (0, 1):
-                capi.set_attention_fused(w.attn[blk * 2 + enc], x, self.pos[blk][enc], gs.global_index_in_set[0],
-                                         gs.mask_expand_0[0], gs.set_num, V, axis=enc, out=self.attn_out,
-                                         precision=self.precision, workspace=self.attn_ws,
-                                         plan=self.plans.get((blk % 2, enc)))
+                if "attn" not in skip:
+                    capi.set_attention_fused(w.attn[blk * 2 + enc], x, self.pos[blk][enc], gs.global_index_in_set[0],
+                                             gs.mask_expand_0[0], gs.set_num, V, axis=enc, out=self.attn_out,
+                                             precision=self.precision, workspace=self.attn_ws,
+                                             plan=self.plans.get((blk % 2, enc)))
+                if "ln" in skip:
+                    ln += 3 if enc == 0 else 4
+                    if "gelu" not in skip:
+                        capi.gelu(self.ffn_hidden, V, out=self.gelu_out)
+                    continue
                 capi.layer_norm(self.attn_out, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=x,
                                 out=self.src); ln += 1                                     # norm1(y + x)   :669-676
                 ffn_out = self.ffn_out
                 if self.ffn == "off":
-                    capi.gelu(self.ffn_hidden, V, out=self.gelu_out)                       # :519 (inside the FFN)
+                    if "gelu" not in skip:
+                        capi.gelu(self.ffn_hidden, V, out=self.gelu_out)                   # :519 (inside the FFN)
                 else:
                     fc1, fc2 = w.ffn[blk * 2 + enc]
                     if self.ffn == "graph":
@@ -175,7 +186,9 @@ class HotPathFrame:
                 x = nxt
             x = self.blk_out[blk % 2]
         self.final = x
-        capi.map2bev(x, vox.coords[0], V, cfg.grid_x, cfg.grid_y, out=self.bev)          # :1128
-        capi.filter_box(cfg, *self.cand, boxes=self.boxes, valid=self.valid)
+        if "m2b" not in skip:
+            capi.map2bev(x, vox.coords[0], V, cfg.grid_x, cfg.grid_y, out=self.bev)      # :1128
+        if "fbox" not in skip:
+            capi.filter_box(cfg, *self.cand, boxes=self.boxes, valid=self.valid)
         self.launches_per_frame = capi.launch_count() - before
         return self
