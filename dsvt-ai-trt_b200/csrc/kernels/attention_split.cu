@@ -196,7 +196,11 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
         auto issue = [&](int gs, float (&d)[16]) {
             const int n = gs / kStepsPerTile, s = gs - n * kStepsPerTile;
             const int kc = ((s >> 1) + rot) % kNumK, row = (t0 + n * stride) * kBM + (s & 1) * 64 + rl;
+#ifdef DSVT_DBG_NO_LOAD      // bottleneck probe (never in the product build): the producers convert zeros
+            if (false) {
+#else
             if (row < V) {
+#endif
                 ldg256(a0 + (size_t) row * g.lda + kc * kBK + c16 * 8, &d[0]);   // one 256-bit load: full 32-byte sectors
                 if (a1) ldg256(a1 + (size_t) row * g.lda + kc * kBK + c16 * 8, &d[8]);
                 else {
@@ -297,6 +301,9 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
                     tmem_ld32(tlane + acc * kAccCols + j0, r);
                     const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + j0));
                     tmem_ld_wait();
+#ifdef DSVT_EPI_PROBE        // phase stamps of the first tile's three slabs (tools/split_profile.py)
+                    if (lane == 0 && warp == 8 && n == 0 && n_roles != 1) SP(22 + (j0 >> 5) * 3);
+#endif
                     if (j0 == 64) {                                // accumulator drained: hand it back to the issuer
                         tc_fence_before_sync();
                         __syncwarp();
@@ -313,6 +320,9 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
                         const int rloc = rr * 4 + rg;
                         v[rr] = scr[rloc * 8 + (c4 ^ (rloc & 7))];
                     }
+#ifdef DSVT_EPI_PROBE
+                    if (lane == 0 && warp == 8 && n == 0 && n_roles != 1) SP(23 + (j0 >> 5) * 3);
+#endif
 #pragma unroll
                     for (int rr = 0; rr < 8; ++rr) {               // 4 rows x 128 contiguous bytes per store instruction
                         const int grow = row0 + rr * 4 + rg;
@@ -325,9 +335,16 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
                         }
                         if (g.act == 1) { ov.x = gelu_tanh(ov.x); ov.y = gelu_tanh(ov.y); ov.z = gelu_tanh(ov.z); ov.w = gelu_tanh(ov.w); }
                         if (grow >= V) ov = make_float4(0.f, 0.f, 0.f, 0.f);
+#ifdef DSVT_DBG_NO_STORE     // bottleneck probe (never in the product build): results are dropped (kept live by an impossible test)
+                        if (orow[rr] >= 0 && ov.x == 1.2345e-30f) *reinterpret_cast<float4*>(outc + (size_t) orow[rr] * g.ld_out + j0) = ov;
+#else
                         if (orow[rr] >= 0) *reinterpret_cast<float4*>(outc + (size_t) orow[rr] * g.ld_out + j0) = ov;
+#endif
                     }
                     __syncwarp();
+#ifdef DSVT_EPI_PROBE
+                    if (lane == 0 && warp == 8 && n == 0 && n_roles != 1) SP(24 + (j0 >> 5) * 3);
+#endif
                 }
                 if (lane == 0 && warp == 8 && n == 0) SP(16);
                 if (lane == 0 && warp == 8 && n == cnt - 1) SP(17);

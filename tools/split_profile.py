@@ -21,6 +21,10 @@ t = np.array(buf[:], dtype=np.int64)
 def show(base, title):
     lab = {0: "start", 1: "setup done (barriers, TMEM)", 14: "producers: all steps staged", 15: "issuer: all MMAs issued",
            16: "epilogue: tile 0 stored", 17: "epilogue: last valid tile stored", 20: "epilogue: tile 0 accumulators ready", 21: "CTA end"}
+    for sl in range(3):          # -DDSVT_EPI_PROBE builds only (QKV kernel)
+        if base == 0 and t[22 + sl * 3]:
+            lab[22 + sl * 3] = f"epilogue: slab {sl} tmem loaded"; lab[23 + sl * 3] = f"epilogue: slab {sl} transposed"
+            lab[24 + sl * 3] = f"epilogue: slab {sl} stored"
     for kc in range(6):
         lab[2 + kc] = f"producer: chunk {kc} staged"; lab[8 + kc] = f"issuer: chunk {kc} full (tile 0)"
     print(title)
