@@ -375,13 +375,30 @@ def cpu_baseline(cfg, cloud, stats):
 
 # ---------------------------------------------------------------------------------------------
 def main():
+    """Keeps stdout clean for the ONE JSON line: libraries (NCCL prints its version banner to stdout on the first
+    collective) write to fd 1, so fd 1 points at stderr while the bench runs and the line goes to the real stdout."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = _main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    if isinstance(line, dict):
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+def _main():
     args = parse()
     # throughput setting of the attention GEMMs: half the SMs per launch (each CTA amortises its resident weight image
     # over twice the row tiles and the other half serves the frames of the other streams); measured +3 % frames/s
     os.environ.setdefault("DSVT_GEMM_SM_FRACTION", "50")
     if args.impl == "reference":
         ref = importlib.import_module("bench_reference")
-        return ref.main(args)
+        return ref.main(args)          # a dict on rank 0, None elsewhere
     import numpy as np
     import torch
     world, rank, local = dist_setup(args)
@@ -503,7 +520,7 @@ def main():
         torch.cuda.empty_cache()
 
     if rank != 0:
-        return 0
+        return None
     frames = F * world * args.steps
     value = frames / (dev_ms * 1e-3)
     e2e = frames / (e2e_ms * 1e-3)
@@ -600,8 +617,7 @@ def main():
             line["cpu_baseline"] = cpu_baseline(cfg, pkg.synth.ring_lidar(args.points, seed=0), stats)
         except Exception as e:   # the checker must never take the bench down
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"failed: {e}"}
-    print(json.dumps(line))
-    return 0
+    return line
 
 
 if __name__ == "__main__":

@@ -160,22 +160,12 @@ def cpu_port_arm(args, cfg, pkg):
 
 
 def main(args):
+    """Returns the JSON line (a dict) on rank 0, None on the other ranks; bench.main() prints it.  The reference's
+    creators print their fields to stdout (e.g. getSet.cu:829): bench.main() points fd 1 at stderr while this runs."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return 0          # rank 0 alone runs and prints the reference arm
-    # the reference's creators print their fields to stdout (e.g. getSet.cu:829); keep stdout clean for the one
-    # JSON line by pointing fd 1 at stderr while the reference code runs
-    sys.stdout.flush()
-    saved_fd = os.dup(1)
-    os.dup2(2, 1)
-    try:
-        line = _run(args)
-    finally:
-        sys.stdout.flush()
-        os.dup2(saved_fd, 1)
-        os.close(saved_fd)
-    print(json.dumps(line))
-    return 0
+        return None       # rank 0 alone runs the reference arm
+    return _run(args)
 
 
 def _run(args):
