@@ -600,8 +600,9 @@ def _main():
                    "gemm_sm_fraction_pct": int(os.environ.get("DSVT_GEMM_SM_FRACTION", "100")),
                    "frame_stats": stats,
                    "l2": "no explicit flush: each step touches F frames x ~0.5 GB of distinct buffers >> 126 MB L2"},
-        "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": F * (args.points * 16 + 4),
-                "d2h_bytes_per_step": F * (cfg.max_top_k * 9 * 4 + 4), "ms_per_step": round(e2e_ms / args.steps, 4)},
+        "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": world * F * (args.points * 16 + 4),
+                "d2h_bytes_per_step": world * F * (cfg.max_top_k * 9 * 4 + 4), "ms_per_step": round(e2e_ms / args.steps, 4),
+                "bytes_note": "whole job: all ranks' pinned-host clouds in, boxes + counts out, per step"},
         "gpu_launches": int(launches_per_frame * F * args.steps * 2),
         "launches_per_frame": int(launches_per_frame),
         "clocks": clocks,
