@@ -221,6 +221,12 @@ def plugin_breakdown(slot, cfg, peaks, reps=3):
 
     w = f.w
     res = {}
+    # empty-kernel floor of this timing protocol (the latency-bound plugins are quoted against it): a GELU
+    # launch over zero valid rows without tail fill -- a full-width grid whose CTAs exit at once, through the same C ABI
+    tiny, none_valid = torch.zeros(8, 384, device="cuda"), torch.zeros(1, dtype=torch.int32, device="cuda")
+    tiny_out = torch.empty_like(tiny)
+    res["_launch_floor"] = {"us": timed(lambda: capi.gelu(tiny, none_valid, out=tiny_out, zero_tails=0)), "bytes": 0,
+                            "calls_per_frame": 0, "note": "empty launch under the same events + L2-flush protocol"}
     us = timed(lambda: f.vox(f.points, f.points_size))
     res["points2features"] = {"us": us, "bytes": 16 * P + 44 * Pc + 20 * V + 8, "calls_per_frame": 1}
     for i in (0, 1):
