@@ -253,7 +253,7 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
                 for (int i = tid; i < kBM * (kBN / 4); i += kProducers) {
                     const int rloc = i / (kBN / 4), cc4 = i - rloc * (kBN / 4);
                     if (row0 + rloc < max_pillars)
-                        *reinterpret_cast<float4*>(out + (size_t) (row0 + rloc) * g.ld_out + cc4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                        stg_zero4(reinterpret_cast<float4*>(out + (size_t) (row0 + rloc) * g.ld_out + cc4 * 4));
                 }
             }
         }

@@ -67,6 +67,20 @@ __device__ __forceinline__ void stg_stream4(float4* p, const float4& v) {
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// Zero-fill of output tails (rows beyond the valid count: the reference memsets every output in full).  Nobody reads these
+// lines again, so they are written with an L2 evict-first policy and do not push the rows the next kernel needs out of L2.
+// DSVT_NO_EVICT_FIRST builds the plain streaming store (A/B runs).
+__device__ __forceinline__ void stg_zero4(float4* p) {
+#ifdef DSVT_NO_EVICT_FIRST
+    stg_stream4(p, make_float4(0.f, 0.f, 0.f, 0.f));
+#else
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%1,%1,%1}, %2;"
+                 :: "l"(p), "f"(0.f), "l"(pol) : "memory");
+#endif
+}
+
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {

@@ -42,12 +42,12 @@ gelu_kernel(const float4* __restrict__ in, const int* __restrict__ voxel_num, fl
         stg_stream4(dst + i + stride, make_float4(gelu_f(c.x), gelu_f(c.y), gelu_f(c.z), gelu_f(c.w)));
     }
     for (; i < end; i += stride) {
-        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < valid) {
             const float4 a = ldg_stream4(src + i);
-            r = make_float4(gelu_f(a.x), gelu_f(a.y), gelu_f(a.z), gelu_f(a.w));
+            stg_stream4(dst + i, make_float4(gelu_f(a.x), gelu_f(a.y), gelu_f(a.z), gelu_f(a.w)));
+        } else {
+            stg_zero4(dst + i);
         }
-        stg_stream4(dst + i, r);
     }
 }
 
@@ -126,7 +126,7 @@ layer_norm192_kernel(const float4* __restrict__ x, const float4* __restrict__ re
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) stg_stream4(out + off + k * 16 + sub, make_float4(0.f, 0.f, 0.f, 0.f));
+            for (int k = 0; k < 3; ++k) stg_zero4(out + off + k * 16 + sub);
         }
     }
 }
@@ -153,7 +153,7 @@ layer_norm192_chain_kernel(const float4* __restrict__ x, LnChain ch, const int* 
         const size_t off = ((size_t) b * max_pillars + row) * 48;
         if (row >= V) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) stg_stream4(out + off + k * 16 + sub, make_float4(0.f, 0.f, 0.f, 0.f));
+            for (int k = 0; k < 3; ++k) stg_zero4(out + off + k * 16 + sub);
             continue;
         }
         float4 v[3];
