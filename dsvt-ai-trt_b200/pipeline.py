@@ -66,11 +66,14 @@ class HotPathFrame:
     """Buffers + launch sequence for one frame slot (one CUDA stream owns one slot)."""
 
     def __init__(self, cfg, weights, precision=capi.DSVT_ATTN_FP32, seed=0, device="cuda", fuse_ln=True, share_plans=True,
-                 ffn="off", skip=()):
+                 ffn="off", skip=(), zero_tails=1):
         assert ffn in ("off", "graph", "fused")
         # diagnostic only (tools/ablate.py): plugin groups left out of the launch sequence to measure their marginal
         # cost with several frames in flight -- {"vox", "smax", "part", "plan", "attn", "ln", "gelu", "m2b", "fbox"}
         self.skip = frozenset(skip)
+        # 1 = the reference's contract (every output zero beyond its valid count, as its per-enqueue memsets leave it);
+        # 0 = rows beyond the counts are left untouched (no consumer in the graph reads them) -- bench "relaxed_tails" leg only
+        self.zero_tails = int(zero_tails)
         self.cfg, self.w, self.precision, self.fuse_ln, self.ffn = cfg, weights, precision, fuse_ln, ffn
         # GEMM-pipeline attention: one plan per (window partition, axis), shared by the two layers that use it
         self.share_plans = share_plans and precision in (capi.DSVT_ATTN_FP32_TC, capi.DSVT_ATTN_FP16_GEMM)
@@ -79,9 +82,9 @@ class HotPathFrame:
         mp, C, F = cfg.max_pillars_num, cfg.channel_num, cfg.ffn_channel_num
         self.points = torch.zeros(1, cfg.max_points_num, 4, dtype=torch.float32, device=device)
         self.points_size = torch.zeros(1, dtype=torch.int32, device=device)
-        self.vox = capi.Points2Features(cfg, device=device)
-        self.wp = [capi.WindowPartition(cfg, i, device=device) for i in (0, 1)]
-        self.gs = [capi.GetSet(cfg, i, device=device) for i in (0, 1)]
+        self.vox = capi.Points2Features(cfg, device=device, zero_tails=self.zero_tails)
+        self.wp = [capi.WindowPartition(cfg, i, device=device, zero_tails=self.zero_tails) for i in (0, 1)]
+        self.gs = [capi.GetSet(cfg, i, device=device, zero_tails=self.zero_tails) for i in (0, 1)]
         # stand-ins for the outputs of TensorRT-native glue layers
         self.x0 = torch.randn(mp, C, generator=g).to(device)                       # VFE / PFN output
         self.pos = [[torch.randn(mp, C, generator=g).mul_(0.5).to(device) for _ in range(2)]
@@ -120,12 +123,12 @@ class HotPathFrame:
         """Enqueue the frame's plugin invocations on the current stream."""
         cfg, w = self.cfg, self.w
         before = capi.launch_count()
-        skip = self.skip
+        skip, zt = self.skip, self.zero_tails
         vox = self.vox if "vox" in skip else self.vox(self.points, self.points_size)
         V = vox.pillar_num
         for k in range(0 if "smax" in skip else len(cfg.pfn_channels)):             # :580-590 (the voxeliser's row count lets it skip the full clear)
             capi.torch_scatter_max(self.w.pfn_out[k], vox.point_index_in_voxel[0], vox.point_num_in_voxel[0], V,
-                                   vox.point_num, max_point=self.max_point[k], max_voxel=self.max_voxel[k])
+                                   vox.point_num, max_point=self.max_point[k], max_voxel=self.max_voxel[k], zero_tails=zt)
         for i in (() if "part" in skip else (0, 1)):
             self.wp[i](vox.coords, V)
             self.gs[i](self.wp[i].global_index, self.wp[i].coors_in_win, self.wp[i].voxel_num_in_win,
@@ -146,35 +149,35 @@ class HotPathFrame:
                     capi.set_attention_fused(w.attn[blk * 2 + enc], x, self.pos[blk][enc], gs.global_index_in_set[0],
                                              gs.mask_expand_0[0], gs.set_num, V, axis=enc, out=self.attn_out,
                                              precision=self.precision, workspace=self.attn_ws,
-                                             plan=self.plans.get((blk % 2, enc)))
+                                             plan=self.plans.get((blk % 2, enc)), zero_tails=zt)
                 if "ln" in skip:
                     ln += 3 if enc == 0 else 4
                     if "gelu" not in skip:
-                        capi.gelu(self.ffn_hidden, V, out=self.gelu_out)
+                        capi.gelu(self.ffn_hidden, V, out=self.gelu_out, zero_tails=zt)
                     continue
                 capi.layer_norm(self.attn_out, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=x,
-                                out=self.src); ln += 1                                     # norm1(y + x)   :669-676
+                                out=self.src, zero_tails=zt); ln += 1                                     # norm1(y + x)   :669-676
                 ffn_out = self.ffn_out
                 if self.ffn == "off":
                     if "gelu" not in skip:
-                        capi.gelu(self.ffn_hidden, V, out=self.gelu_out)                   # :519 (inside the FFN)
+                        capi.gelu(self.ffn_hidden, V, out=self.gelu_out, zero_tails=zt)    # :519 (inside the FFN)
                 else:
                     fc1, fc2 = w.ffn[blk * 2 + enc]
                     if self.ffn == "graph":
-                        fc1.rows(self.src, V, out=self.ffn_h)                              # :513  FC 192->384
-                        capi.gelu(self.ffn_h, V, out=self.gelu_out)                        # :519  GeluPlugin
+                        fc1.rows(self.src, V, out=self.ffn_h, zero_tails=zt)               # :513  FC 192->384
+                        capi.gelu(self.ffn_h, V, out=self.gelu_out, zero_tails=zt)         # :519  GeluPlugin
                     else:
-                        fc1.rows(self.src, V, activation=1, out=self.gelu_out)             # FC + GELU epilogue
-                    ffn_out = fc2.rows(self.gelu_out, V, out=self.ffn_o)                   # :524  FC 384->192
+                        fc1.rows(self.src, V, activation=1, out=self.gelu_out, zero_tails=zt)   # FC + GELU epilogue
+                    ffn_out = fc2.rows(self.gelu_out, V, out=self.ffn_o, zero_tails=zt)    # :524  FC 384->192
                 nxt = self.x_a if enc == 0 else self.x_b
                 if not self.fuse_ln:
                     capi.layer_norm(self.src, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=ffn_out,
-                                    out=self.src_b); ln += 1                               # norm2(src + src2) :685-690
+                                    out=self.src_b, zero_tails=zt); ln += 1                               # norm2(src + src2) :685-690
                     capi.layer_norm(self.src_b, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=x,
-                                    out=nxt); ln += 1                                      # norm(src + x)  :691-697
+                                    out=nxt, zero_tails=zt); ln += 1                                      # norm(src + x)  :691-697
                     if enc == 1:
                         capi.layer_norm(nxt, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=x_in,
-                                        out=self.blk_out[blk % 2]); ln += 1                # residual norm  :750-756
+                                        out=self.blk_out[blk % 2], zero_tails=zt); ln += 1                # residual norm  :750-756
                 else:
                     # the same LayerNorms as one chained launch (rows stay in registers between stages)
                     stages = [(ffn_out, w.gamma[ln], w.beta[ln]), (x, w.gamma[ln + 1], w.beta[ln + 1])]
@@ -182,13 +185,13 @@ class HotPathFrame:
                     if enc == 1:
                         stages.append((x_in, w.gamma[ln], w.beta[ln])); ln += 1
                     capi.layer_norm_chain(self.src, V, stages, cfg.layer_norm_eps,
-                                          out=nxt if enc == 0 else self.blk_out[blk % 2])
+                                          out=nxt if enc == 0 else self.blk_out[blk % 2], zero_tails=zt)
                 x = nxt
             x = self.blk_out[blk % 2]
         self.final = x
         if "m2b" not in skip:
             capi.map2bev(x, vox.coords[0], V, cfg.grid_x, cfg.grid_y, out=self.bev)      # :1128
         if "fbox" not in skip:
-            capi.filter_box(cfg, *self.cand, boxes=self.boxes, valid=self.valid)
+            capi.filter_box(cfg, *self.cand, boxes=self.boxes, valid=self.valid, zero_tails=zt)
         self.launches_per_frame = capi.launch_count() - before
         return self
