@@ -80,6 +80,9 @@ def _lib():
         lib.dsvt_linear_weights_create.restype = c_void_p
         lib.dsvt_linear_weights_create.argtypes = [c_int32, c_int32, c_void_p, c_void_p, c_int32]
         lib.dsvt_linear_weights_destroy.argtypes = [c_void_p]
+        lib.dsvt_small_linear_create.restype = c_void_p
+        lib.dsvt_small_linear_create.argtypes = [c_int32, c_int32, c_void_p, c_void_p, c_void_p]
+        lib.dsvt_small_linear_destroy.argtypes = [c_void_p]
         _sig_done = True
     return lib
 
@@ -415,9 +418,66 @@ class Linear:
                "dsvt_linear_rows_launch")
         return out
 
+    def rows_concat(self, x_lo, x_hi, rows, activation=0, out=None, zero_tails=1):
+        """Same as rows() for the input [x_lo | x_hi] (two dense tensors, e.g. the PFN's concatenation of the point
+        features and their per-pillar max), read in place.  activation: 0 none, 1 GELU, 2 ReLU."""
+        _need(x_lo, torch.float32, "x_lo")
+        _need(x_hi, torch.float32, "x_hi")
+        _need(rows, torch.int32, "rows")
+        max_rows, k_split = x_lo.shape[0], x_lo.shape[1]
+        assert x_hi.shape[0] == max_rows and k_split + x_hi.shape[1] == self.K
+        out = torch.empty(max_rows, self.N, dtype=torch.float32, device=x_lo.device) if out is None else out
+        _check(_lib().dsvt_linear_rows_concat_launch(c_void_p(self.handle), _ptr(x_lo), _ptr(x_hi), c_int32(k_split),
+                                                     _ptr(rows), c_int32(max_rows), c_int32(activation), _ptr(out),
+                                                     c_int32(zero_tails), _stream()),
+               "dsvt_linear_rows_concat_launch")
+        return out
+
     def close(self):
         if getattr(self, "handle", None):
             _lib().dsvt_linear_weights_destroy(c_void_p(self.handle))
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SmallLinear:
+    """y = act((x W^T) * scale + shift) for the narrow first layers of the PFN / position-embedding MLPs (K = 2, 4, 10);
+    scale / shift = the folded BatchNorm1d.  W [N,K] float32 host array."""
+
+    def __init__(self, W, scale=None, shift=None):
+        import numpy as np
+        W = np.ascontiguousarray(W, dtype=np.float32)
+        self.N, self.K = W.shape
+        sc = np.ascontiguousarray(scale, dtype=np.float32) if scale is not None else None
+        sh = np.ascontiguousarray(shift, dtype=np.float32) if shift is not None else None
+        self.handle = _lib().dsvt_small_linear_create(self.N, self.K, W.ctypes.data_as(c_void_p),
+                                                      sc.ctypes.data_as(c_void_p) if sc is not None else None,
+                                                      sh.ctypes.data_as(c_void_p) if sh is not None else None)
+        if not self.handle:
+            raise DsvtError("dsvt_small_linear_create: " + _lib().dsvt_last_error().decode())
+
+    def __call__(self, x, rows, activation=2, out=None, zero_tails=1):
+        """x [max_rows, K] (or [B, max_rows, K]) -> [.., max_rows, N]; rows [B] int32 on the device."""
+        _need(x, torch.float32, "x")
+        _need(rows, torch.int32, "rows")
+        B = x.shape[0] if x.dim() == 3 else 1
+        max_rows = x.shape[-2]
+        assert x.shape[-1] == self.K
+        shape = (B, max_rows, self.N) if x.dim() == 3 else (max_rows, self.N)
+        out = torch.empty(shape, dtype=torch.float32, device=x.device) if out is None else out
+        _check(_lib().dsvt_small_linear_launch(c_void_p(self.handle), _ptr(x), _ptr(rows), c_int32(B), c_int32(max_rows),
+                                               c_int32(activation), _ptr(out), c_int32(zero_tails), _stream()),
+               "dsvt_small_linear_launch")
+        return out
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib().dsvt_small_linear_destroy(c_void_p(self.handle))
             self.handle = None
 
     def __del__(self):

@@ -100,7 +100,10 @@ struct GemmRole {
     int pad_hi;             // floats inserted in front of columns 96..191 (K / V rows: bank-conflict-free head layout)
     int lda;                // floats per row of a0 / a1 (192 for the attention tensors; K for a wider linear layer)
     int accumulate;         // 1: add to the rows already in `out` (second 192-wide K block of a linear layer)
-    int act;                // 0: none, 1: GELU (tanh form, gelu.cu:201-211) on the finished value
+    int act;                // 0: none, 1: GELU (tanh form, gelu.cu:201-211), 2: ReLU on the finished value
+    const float* a0b;       // optional second source of the A operand: columns >= ksplit of the K block come from a0b
+    int ksplit, ldb;        //   (the PFN's concatenation [point features | per-pillar max], src/dsvt-ai-trt.cpp:583-587,
+                            //   read in place instead of being materialised); ksplit is a multiple of 32, a0b == nullptr: off
 };
 struct GemmRoles { GemmRole r[3]; };
 
@@ -164,6 +167,7 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
     float* out = g.out + (size_t) b * max_pillars * g.ld_out + g.col0;
     const float* a0 = g.a0 + (size_t) b * max_pillars * g.lda;
     const float* a1 = g.a1 ? g.a1 + (size_t) b * max_pillars * g.lda : nullptr;
+    const float* a0b = g.a0b ? g.a0b + (size_t) b * max_pillars * g.ldb : nullptr;
     if (tid == 0) SP(0);
 
     if (tid == 0) {
@@ -201,7 +205,9 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
 #else
             if (row < V) {
 #endif
-                ldg256(a0 + (size_t) row * g.lda + kc * kBK + c16 * 8, &d[0]);   // one 256-bit load: full 32-byte sectors
+                const int col = kc * kBK + c16 * 8;
+                if (a0b && col >= g.ksplit) ldg256(a0b + (size_t) row * g.ldb + (col - g.ksplit), &d[0]);
+                else ldg256(a0 + (size_t) row * g.lda + col, &d[0]);              // one 256-bit load: full 32-byte sectors
                 if (a1) ldg256(a1 + (size_t) row * g.lda + kc * kBK + c16 * 8, &d[8]);
                 else {
 #pragma unroll
@@ -334,6 +340,7 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
                             ov.x += pv4.x; ov.y += pv4.y; ov.z += pv4.z; ov.w += pv4.w;
                         }
                         if (g.act == 1) { ov.x = gelu_tanh(ov.x); ov.y = gelu_tanh(ov.y); ov.z = gelu_tanh(ov.z); ov.w = gelu_tanh(ov.w); }
+                        else if (g.act == 2) { ov.x = fmaxf(ov.x, 0.f); ov.y = fmaxf(ov.y, 0.f); ov.z = fmaxf(ov.z, 0.f); ov.w = fmaxf(ov.w, 0.f); }
                         if (grow >= V) ov = make_float4(0.f, 0.f, 0.f, 0.f);
 #ifdef DSVT_DBG_NO_STORE     // bottleneck probe (never in the product build): results are dropped (kept live by an impossible test)
                         if (orow[rr] >= 0 && ov.x == 1.2345e-30f) *reinterpret_cast<float4*>(outc + (size_t) orow[rr] * g.ld_out + j0) = ov;
@@ -772,8 +779,11 @@ void* linear_split_prepare(int N, int K, const float* W, const float* b, float* 
 }
 
 int linear_split_launch(const void* blob, int N, int K, float out_mul, bool split, int act, const float* x,
-                        const int* rows_dev, int rows_host, int max_rows, float* y, int zero_tails, cudaStream_t st)
+                        const float* x_hi, int k_split, const int* rows_dev, int rows_host, int max_rows, float* y,
+                        int zero_tails, cudaStream_t st)
 {
+    // x_hi != nullptr: the input row is the concatenation [x (k_split columns, dense) | x_hi (K - k_split columns, dense)];
+    // only single-K-block layers (K == 192) take it
     const int nb = N / kBN, kb = K / kC;
     const uint8_t* img = static_cast<const uint8_t*>(blob);
     const float* bias = reinterpret_cast<const float*>(img + (size_t) nb * kb * kWRoleBytes);
@@ -795,7 +805,8 @@ int linear_split_launch(const void* blob, int N, int K, float out_mul, bool spli
             for (int r = 0; r < 3; ++r) {
                 const int i = i0 + (r < n_roles ? r : 0);
                 GemmRole& g = roles.r[r];
-                g.a0 = x + (size_t) j * kC; g.a1 = nullptr; g.lda = K;
+                g.a0 = x + (size_t) j * kC; g.a1 = nullptr; g.lda = x_hi ? k_split : K;
+                g.a0b = x_hi; g.ksplit = x_hi ? k_split : 0; g.ldb = x_hi ? K - k_split : 0;
                 g.wimg = img + ((size_t) i * kb + j) * kWRoleBytes;
                 g.bias = j == 0 ? bias + i * kBN : zero_bias;
                 g.out = y; g.ld_out = N; g.col0 = i * kBN;
@@ -989,6 +1000,7 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
         g.plan_stride = plan_stride;
         g.pad_hi = r == 0 ? 0 : 4;
         g.lda = kC; g.accumulate = 0; g.act = 0;
+        g.a0b = nullptr; g.ksplit = 0; g.ldb = 0;
     }
     {
         GemmRole& g = out_roles.r[0];
@@ -1000,6 +1012,7 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
         g.post_mul = 1.0f;
         g.plan = nullptr; g.plan_stride = 0; g.pad_hi = 0;
         g.lda = kC; g.accumulate = 0; g.act = 0;
+        g.a0b = nullptr; g.ksplit = 0; g.ldb = 0;
         out_roles.r[1] = out_roles.r[2] = g;
     }
     if (g_skip_mask & 1) {

@@ -137,7 +137,8 @@ using namespace dsvt;
 namespace dsvt {   // attention_split.cu: the persistent split-precision GEMM as a plain linear layer
 void* linear_split_prepare(int N, int K, const float* W, const float* b, float* out_mul);
 int linear_split_launch(const void* blob, int N, int K, float out_mul, bool split, int act, const float* x,
-                        const int* rows_dev, int rows_host, int max_rows, float* y, int zero_tails, cudaStream_t st);
+                        const float* x_hi, int k_split, const int* rows_dev, int rows_host, int max_rows, float* y,
+                        int zero_tails, cudaStream_t st);
 }
 
 struct dsvt_linear_weights {
@@ -223,7 +224,7 @@ extern "C" int dsvt_linear_launch(const dsvt_linear_weights* w, const float* x, 
     if (w->split_blob) {
         DSVT_CHECK_ARG(!((uintptr_t) x & 31), "32-B alignment of x (256-bit loads)");
         return dsvt::linear_split_launch(w->split_blob, w->N, w->K, w->out_mul, w->precision == DSVT_ATTN_FP32_TC, 0, x,
-                                         nullptr, M, M, y, 0, reinterpret_cast<cudaStream_t>(stream));
+                                         nullptr, 0, nullptr, M, M, y, 0, reinterpret_cast<cudaStream_t>(stream));
     }
     const int esize = w->precision == DSVT_ATTN_FP16 ? 2 : 4;
     const size_t smem = (size_t) w->K * esize * (kTileM + kTileN);
@@ -246,8 +247,22 @@ extern "C" int dsvt_linear_rows_launch(const dsvt_linear_weights* w, const float
 {
     DSVT_CHECK_ARG(w && x && y && rows && max_rows >= 1, "NULL argument");
     DSVT_CHECK_ARG(w->split_blob != nullptr, "built for precision DSVT_ATTN_FP32_TC / DSVT_ATTN_FP16_GEMM weights only");
-    DSVT_CHECK_ARG(activation == 0 || activation == 1, "activation: 0 none, 1 GELU");
+    DSVT_CHECK_ARG(activation >= 0 && activation <= 2, "activation: 0 none, 1 GELU, 2 ReLU");
     DSVT_CHECK_ARG(!(((uintptr_t) x & 31) | ((uintptr_t) y & 15)), "alignment (x 32 B, y 16 B)");
     return dsvt::linear_split_launch(w->split_blob, w->N, w->K, w->out_mul, w->precision == DSVT_ATTN_FP32_TC, activation, x,
-                                     rows, 0, max_rows, y, zero_tails, reinterpret_cast<cudaStream_t>(stream));
+                                     nullptr, 0, rows, 0, max_rows, y, zero_tails, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dsvt_linear_rows_concat_launch(const dsvt_linear_weights* w, const float* x_lo, const float* x_hi,
+                                              int32_t k_split, const int32_t* rows, int32_t max_rows, int32_t activation,
+                                              float* y, int32_t zero_tails, dsvt_stream_t stream)
+{
+    DSVT_CHECK_ARG(w && x_lo && x_hi && y && rows && max_rows >= 1, "NULL argument");
+    DSVT_CHECK_ARG(w->split_blob != nullptr, "built for precision DSVT_ATTN_FP32_TC / DSVT_ATTN_FP16_GEMM weights only");
+    DSVT_CHECK_ARG(w->K == 192, "the in-place concatenation is built for K == 192 layers");
+    DSVT_CHECK_ARG(k_split > 0 && k_split < w->K && k_split % 32 == 0, "k_split must be a multiple of 32 inside (0, K)");
+    DSVT_CHECK_ARG(activation >= 0 && activation <= 2, "activation: 0 none, 1 GELU, 2 ReLU");
+    DSVT_CHECK_ARG(!((((uintptr_t) x_lo | (uintptr_t) x_hi) & 31) | ((uintptr_t) y & 15)), "alignment (x 32 B, y 16 B)");
+    return dsvt::linear_split_launch(w->split_blob, w->N, w->K, w->out_mul, w->precision == DSVT_ATTN_FP32_TC, activation, x_lo,
+                                     x_hi, k_split, rows, 0, max_rows, y, zero_tails, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -20,6 +20,12 @@ come from the real voxeliser / partition of the frame's cloud).
 kernel (dsvt_linear_rows_launch), so a DSVT block becomes a real data flow from its input rows to its output rows:
     "graph": FC 192->384 -> GeluPlugin -> FC 384->192        (the reference graph's three nodes)
     "fused": FC 192->384 with the GELU in its epilogue -> FC 384->192   (one pass less over the 384-wide rows)
+
+``backbone=True`` (with ``ffn`` on) runs the remaining TensorRT-native layers of the 3-D backbone as well, so that the frame
+is ONE data flow from the raw points to the BEV map (random-init weights, BatchNorm folded):
+    PFN layer 0  Linear(10->96)+BN+ReLU on the decorated points           (src/dsvt-ai-trt.cpp:577, dsvt_small_linear_launch)
+    PFN layer 1  Linear(192->192)+BN+ReLU on [points | per-pillar max]    (:583-587, dsvt_linear_rows_concat_launch)
+    8 position-embedding MLPs  Linear(2->192)+BN+ReLU -> Linear(192->192) (:603-637) on the in-window coordinates
 """
 import numpy as np
 import torch
@@ -52,6 +58,34 @@ class FrameWeights:
                            (rng.standard_normal((C, cfg.ffn_channel_num)) * 0.05).astype(np.float32),
                            (rng.standard_normal(C) * 0.02).astype(np.float32)) for _ in range(cfg.num_blocks * 2)]
         self._ffn = None
+        # VFE (PFN layers) and position-embedding MLPs (src/dsvt-ai-trt.cpp:577-637): BatchNorm1d folded to (scale, shift)
+        def bn(n):
+            gamma, var = 1.0 + 0.1 * rng.standard_normal(n), rng.uniform(0.5, 1.5, n)
+            mean, beta = 0.1 * rng.standard_normal(n), 0.1 * rng.standard_normal(n)
+            scale = 0.5 * gamma / np.sqrt(var + 1e-5)
+            return scale.astype(np.float32), (beta - mean * scale).astype(np.float32)
+        F0, F1 = cfg.pfn_channels
+        self.vfe_host = {"pfn0": ((rng.standard_normal((F0, cfg.feature_num)) * 0.05).astype(np.float32),) + bn(F0),
+                         "pfn1": ((rng.standard_normal((F1, 2 * F0)) * 0.07).astype(np.float32),) + bn(F1)}
+        self.pos_host = [[((rng.standard_normal((C, 2)) * 0.3).astype(np.float32),) + bn(C) +
+                          ((rng.standard_normal((C, C)) * 0.07).astype(np.float32),
+                           (rng.standard_normal(C) * 0.02).astype(np.float32)) for _ in range(2)]
+                         for _ in range(cfg.num_blocks)]
+        self._glue = None
+
+    @property
+    def glue(self):
+        """Device weights of the VFE / position-embedding layers: pfn0, pfn1, pos[blk][enc] = (first, second)."""
+        if self._glue is None:
+            w0, s0, t0 = self.vfe_host["pfn0"]
+            w1, s1, t1 = self.vfe_host["pfn1"]
+            self._glue = {
+                "pfn0": capi.SmallLinear(w0, s0, t0),
+                # Linear (no bias) + BatchNorm folded into the GEMM's weights and bias, ReLU in its epilogue
+                "pfn1": capi.Linear(w1 * s1[:, None], t1, precision=capi.DSVT_ATTN_FP32_TC),
+                "pos": [[(capi.SmallLinear(a, sc, sh), capi.Linear(b2, bias2, precision=capi.DSVT_ATTN_FP32_TC))
+                         for a, sc, sh, b2, bias2 in row] for row in self.pos_host]}
+        return self._glue
 
     @property
     def ffn(self):
@@ -66,8 +100,10 @@ class HotPathFrame:
     """Buffers + launch sequence for one frame slot (one CUDA stream owns one slot)."""
 
     def __init__(self, cfg, weights, precision=capi.DSVT_ATTN_FP32, seed=0, device="cuda", fuse_ln=True, share_plans=True,
-                 ffn="off", skip=(), zero_tails=1):
+                 ffn="off", skip=(), zero_tails=1, backbone=False):
         assert ffn in ("off", "graph", "fused")
+        assert not backbone or ffn != "off", "backbone=True runs every layer: it needs the FFN linears on"
+        self.backbone = backbone
         # diagnostic only (tools/ablate.py): plugin groups left out of the launch sequence to measure their marginal
         # cost with several frames in flight -- {"vox", "smax", "part", "plan", "attn", "ln", "gelu", "m2b", "fbox"}
         self.skip = frozenset(skip)
@@ -103,6 +139,12 @@ class HotPathFrame:
         if ffn != "off":
             self.ffn_h = torch.empty(mp, F, device=device)      # FC 192->384 output (graph form only)
             self.ffn_o = torch.empty(mp, C, device=device)      # FC 384->192 output
+        if backbone:
+            Pm = cfg.max_points_num_voxel_filter
+            self.pfn0_out = torch.empty(Pm, cfg.pfn_channels[0], device=device)
+            self.pfn1_out = torch.empty(Pm, cfg.pfn_channels[1], device=device)
+            self.pos_hidden = torch.empty(mp, C, device=device)
+            self.pos_out = [[torch.empty(mp, C, device=device) for _ in range(2)] for _ in range(cfg.num_blocks)]
         self.x_a = torch.empty(mp, C, device=device)
         self.x_b = torch.empty(mp, C, device=device)
         self.blk_out = [torch.empty(mp, C, device=device) for _ in range(2)]
@@ -127,7 +169,15 @@ class HotPathFrame:
         vox = self.vox if "vox" in skip else self.vox(self.points, self.points_size)
         V = vox.pillar_num
         for k in range(0 if "smax" in skip else len(cfg.pfn_channels)):             # :580-590 (the voxeliser's row count lets it skip the full clear)
-            capi.torch_scatter_max(self.w.pfn_out[k], vox.point_index_in_voxel[0], vox.point_num_in_voxel[0], V,
+            pfn_out = self.w.pfn_out[k]
+            if self.backbone:                                                       # the PFN layer in front of the scatter-max
+                g = w.glue
+                if k == 0:
+                    pfn_out = g["pfn0"](vox.point_features[0], vox.point_num, activation=2, out=self.pfn0_out, zero_tails=zt)
+                else:
+                    pfn_out = g["pfn1"].rows_concat(self.pfn0_out, self.max_point[0], vox.point_num, activation=2,
+                                                    out=self.pfn1_out, zero_tails=zt)
+            capi.torch_scatter_max(pfn_out, vox.point_index_in_voxel[0], vox.point_num_in_voxel[0], V,
                                    vox.point_num, max_point=self.max_point[k], max_voxel=self.max_voxel[k], zero_tails=zt)
         for i in (() if "part" in skip else (0, 1)):
             self.wp[i](vox.coords, V)
@@ -140,13 +190,21 @@ class HotPathFrame:
                     self.plans[(part, axis)] = capi.set_attention_plan(
                         gs.global_index_in_set[0], gs.mask_expand_0[0], gs.set_num, axis, cfg.max_pillars_num,
                         cfg.num_heads, cfg.channel_num, out=self.plans.get((part, axis)))
-        x, ln = self.x0, 0
+        x, ln, pos = self.x0, 0, self.pos
+        if self.backbone:
+            x = self.max_voxel[-1]                         # VFE output: per-pillar max of PFN layer 1 (:589, output 1)
+            pos = self.pos_out
+            for blk in range(cfg.num_blocks):              # pos_embed[blk][i] from the shift-i window coordinates (:603-637)
+                for enc in (0, 1):
+                    first, second = w.glue["pos"][blk][enc]
+                    first(self.wp[enc].coors_in_win_x_y[0], V, activation=2, out=self.pos_hidden, zero_tails=zt)
+                    second.rows(self.pos_hidden, V, out=self.pos_out[blk][enc], zero_tails=zt)
         for blk in range(cfg.num_blocks):
             gs = self.gs[blk % 2]                      # blocks 0,2: 12x12 windows; 1,3: 24x24 shifted (:654-:1018)
             x_in = x
             for enc in (0, 1):
                 if "attn" not in skip:
-                    capi.set_attention_fused(w.attn[blk * 2 + enc], x, self.pos[blk][enc], gs.global_index_in_set[0],
+                    capi.set_attention_fused(w.attn[blk * 2 + enc], x, pos[blk][enc], gs.global_index_in_set[0],
                                              gs.mask_expand_0[0], gs.set_num, V, axis=enc, out=self.attn_out,
                                              precision=self.precision, workspace=self.attn_ws,
                                              plan=self.plans.get((blk % 2, enc)), zero_tails=zt)

@@ -311,6 +311,27 @@ int dsvt_linear_launch(const dsvt_linear_weights* w, const float* x, int32_t M, 
  */
 int dsvt_linear_rows_launch(const dsvt_linear_weights* w, const float* x, const int32_t* rows, int32_t max_rows,
                             int32_t activation, float* y, int32_t zero_tails, dsvt_stream_t stream);
+/*
+ * Same layer with the input row given as the concatenation [x_lo (k_split columns) | x_hi (K - k_split columns)] of two
+ * dense tensors, read in place: the PFN's addConcatenation (src/dsvt-ai-trt.cpp:583-587) is not materialised.  K == 192,
+ * k_split a multiple of 32.  activation: 0 none, 1 GELU, 2 ReLU (a folded BatchNorm goes into W and b:
+ * fullyConnectedBnLELU, src/dsvt-ai-trt.cpp:268-286).
+ */
+int dsvt_linear_rows_concat_launch(const dsvt_linear_weights* w, const float* x_lo, const float* x_hi, int32_t k_split,
+                                   const int32_t* rows, int32_t max_rows, int32_t activation, float* y, int32_t zero_tails,
+                                   dsvt_stream_t stream);
+
+/*
+ * Narrow first layers of the VFE / position-embedding MLPs (TensorRT FullyConnected + Scale + ReLU in the reference:
+ * PFN layer 0 Linear(10 -> 96) src/dsvt-ai-trt.cpp:577, position embedding Linear(2 -> 192) :603-637 via :461-492):
+ *   y = act((x W^T) * scale + shift),  W [N,K] row-major, K in {2, 4, 10}, N / 4 dividing 192, scale / shift [N] = the folded
+ *   BatchNorm1d (NULL: 1 / 0).  x [B,max_rows,K] -> y [B,max_rows,N]; rows [B] on the device; rows beyond it zero-filled.
+ */
+typedef struct dsvt_small_linear dsvt_small_linear;
+dsvt_small_linear* dsvt_small_linear_create(int32_t N, int32_t K, const float* W, const float* scale, const float* shift);
+void dsvt_small_linear_destroy(dsvt_small_linear* w);
+int dsvt_small_linear_launch(const dsvt_small_linear* w, const float* x, const int32_t* rows, int32_t batch,
+                             int32_t max_rows, int32_t activation, float* y, int32_t zero_tails, dsvt_stream_t stream);
 
 /* ------------------------------------------------------------------------ *
  * (next #3) TorchScatterMaxPlugin::enqueue     plugins/src/torchScatterMax.cu:282-309 (kernel :201-262)

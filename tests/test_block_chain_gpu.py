@@ -65,3 +65,87 @@ def test_dsvt_block_chain(frame0, cfgs, ffn, fuse_ln):
     assert err <= 2e-4, err
     # the frame really went through the C ABI (voxeliser, partition, plans, attention, LayerNorms, FFN linears)
     assert fr.launches_per_frame > 20
+
+
+def _lin64(x, W, scale=None, shift=None, bias=None, relu=False):
+    """float64 restatement of a TensorRT FullyConnected (+ Scale of the folded BatchNorm) (+ ReLU) layer."""
+    y = x.astype(np.float64) @ W.T.astype(np.float64)
+    if scale is not None:
+        y = y * scale + shift
+    if bias is not None:
+        y = y + bias
+    if relu:
+        y = np.maximum(y, 0.0)
+    return y.astype(np.float32)
+
+
+def oracle_backbone(w, cfg, frame0):
+    """The whole 3-D backbone of HotPathFrame(backbone=True) with the oracle's functions (src/dsvt-ai-trt.cpp:571-1128)."""
+    o = cpu.points2features(pad_points(frame0, cfg.max_points_num), len(frame0), cfg)
+    V, Pc, mp, Pm = o["pillar_num"], o["point_num"], cfg.max_pillars_num, cfg.max_points_num_voxel_filter
+    piv, pnv = o["point_index_in_voxel"], o["point_num_in_voxel"]
+    w0, s0, t0 = w.vfe_host["pfn0"]
+    w1, s1, t1 = w.vfe_host["pfn1"]
+    h0 = np.zeros((Pm, cfg.pfn_channels[0]), np.float32)
+    h0[:Pc] = _lin64(o["point_features"][:Pc], w0, s0, t0, relu=True)                      # :577
+    mp0, _ = cpu.torch_scatter_max(h0, piv, pnv, V)                                        # :579
+    h1 = np.zeros((Pm, cfg.pfn_channels[1]), np.float32)
+    h1[:Pc] = _lin64(np.concatenate([h0[:Pc], mp0[:Pc]], axis=1), w1, s1, t1, relu=True)   # :583-587
+    _, x = cpu.torch_scatter_max(h1, piv, pnv, V)                                          # :589, output 1
+    parts = []
+    for which in (0, 1):
+        owp = cpu.window_partition(o["coords"], V, cfg, which)
+        ogs = cpu.get_set(owp["global_index"], owp["coors_in_win"], owp["voxel_num_in_win"], owp["win_num"], cfg, which)
+        parts.append((owp, ogs))
+    gamma, beta = w.gamma.cpu().numpy(), w.beta.cpu().numpy()
+    ln = 0
+    for blk in range(cfg.num_blocks):
+        ogs = parts[blk % 2][1]
+        ns, idx, mask = ogs["set_num"], ogs["global_index_in_set"], ogs["mask_expand_0"]
+        x_in = x
+        for enc in (0, 1):
+            a, sc, sh, b2, bias2 = w.pos_host[blk][enc]
+            pos = np.zeros((mp, cfg.channel_num), np.float32)
+            xy = parts[enc][0]["coors_in_win_x_y"][:V]                                     # shift-`enc` window coordinates
+            pos[:V] = _lin64(_lin64(xy, a, sc, sh, relu=True), b2, bias=bias2)             # :603-637
+            q, k, v = cpu.get_value_by_index(x, pos, idx, ns, enc)
+            att = cpu.set_attention(q, k, v, mask, ns, *w.attn_host[blk * 2 + enc])
+            y = cpu.map_set_feature2voxel(att, idx, ns, enc, mp)
+            src = cpu.layer_norm(y, V, gamma[ln], beta[ln], residual=x); ln += 1
+            f1, fb1, f2, fb2 = w._ffn_host[blk * 2 + enc]
+            h = np.zeros((mp, cfg.ffn_channel_num), np.float32)
+            h[:V] = _lin64(src[:V], f1, bias=fb1)
+            g = cpu.gelu(h, V)
+            src2 = np.zeros((mp, cfg.channel_num), np.float32)
+            src2[:V] = _lin64(g[:V], f2, bias=fb2)
+            src = cpu.layer_norm(src, V, gamma[ln], beta[ln], residual=src2); ln += 1
+            x = cpu.layer_norm(src, V, gamma[ln], beta[ln], residual=x); ln += 1
+        x = cpu.layer_norm(x, V, gamma[ln], beta[ln], residual=x_in); ln += 1
+    bev = cpu.map2bev(x, o["coords"], V, cfg.grid_x, cfg.grid_y)
+    return x, bev, V, Pc
+
+
+@pytest.mark.parametrize("ffn", ["graph", "fused"])
+def test_whole_3d_backbone_chain(frame0, cfgs, ffn):
+    """Raw points -> PFN -> scatter-max -> partition / sets -> 2 DSVT blocks (12x12 and shifted 24x24 windows) -> BEV map:
+    every layer of the reference's 3-D backbone executed on the GPU through the C ABI, against the oracle chain."""
+    capi = importlib.import_module("dsvt-ai-trt_b200.capi")
+    pipeline = importlib.import_module("dsvt-ai-trt_b200.pipeline")
+    cfg = cfgs.REFERENCE.with_(num_blocks=2)
+    w = pipeline.FrameWeights(cfg, seed=4)
+    fr = pipeline.HotPathFrame(cfg, w, precision=capi.DSVT_ATTN_FP32_TC, seed=6, ffn=ffn, backbone=True)
+    fr.load_points(frame0)
+    fr.run()
+    torch.cuda.synchronize()
+    ref, bev, V, Pc = oracle_backbone(w, cfg, frame0)
+    assert int(fr.vox.pillar_num[0]) == V and int(fr.vox.point_num[0]) == Pc
+    # VFE output (pillar features before the blocks)
+    vfe = fr.max_voxel[-1].cpu().numpy()
+    assert np.all(vfe[V:] == 0)
+    got = fr.final.cpu().numpy()
+    assert np.isfinite(got).all() and np.all(got[V:] == 0)
+    err = np.abs(got - ref).max()
+    assert err <= 5e-4, err                     # north-star FP32 bound: 1e-3
+    gbev = fr.bev.cpu().numpy()
+    assert np.array_equal(gbev != 0, bev != 0)  # the same cells are occupied
+    assert np.abs(gbev - bev).max() <= 5e-4
