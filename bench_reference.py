@@ -23,7 +23,8 @@ REF_DIR = os.path.join(ROOT, "oracle", "_ref", "waymo")
 
 
 class ReferenceFrame:
-    def __init__(self, plg, cfg, cloud, seed):
+    def __init__(self, plg, cfg, cloud, seed, backbone=False):
+        self.backbone = backbone
         import numpy as np
         import torch
         import torch.nn.functional as Fn
@@ -82,6 +83,15 @@ class ReferenceFrame:
         self.cand = [carve(sc, 1).view(1, K), carve(cl, 1).view(1, K), carve(xs, 1).view(1, K), carve(ys, 1).view(1, K),
                      carve(ce, 2).view(1, 1, K, 2), carve(cz, 1).view(1, 1, K, 1), carve(an, 1).view(1, 1, K, 1),
                      carve(dm, 3).view(1, 1, K, 3)]
+        if backbone:
+            # the TensorRT-native layers of the 3-D backbone (FullyConnected + Scale + ReLU, src/dsvt-ai-trt.cpp:268-286,
+            # :461-529), stood in by PyTorch eager (cuBLAS) over the full static shapes like the engine's layers
+            F0, F1 = cfg.pfn_channels
+            r = lambda *sh, k=1.0: (torch.randn(*sh, generator=g) * k).to(dev)
+            self.pfn = [(r(F0, 10, k=0.05), r(F0, k=0.1) + 0.5, r(F0, k=0.1)), (r(F1, 2 * F0, k=0.07), r(F1, k=0.1) + 0.5, r(F1, k=0.1))]
+            self.pos_w = [[(r(C, 2, k=0.3), r(C, k=0.1) + 0.5, r(C, k=0.1), r(C, C, k=0.07), r(C, k=0.02)) for _ in range(2)]
+                          for _ in range(cfg.num_blocks)]
+            self.ffn_w = [(r(F, C, k=0.07), r(F, k=0.02), r(C, F, k=0.05), r(C, k=0.02)) for _ in range(cfg.num_blocks * 2)]
         self.out = {}          # persistent output tensors per plugin call site (static addresses for graph capture)
         self.graph = None
         self.boxes = None
@@ -103,25 +113,45 @@ class ReferenceFrame:
 
     def run(self):
         cfg, torch = self.cfg, self.torch
+        Fn = self.Fn
         vo = self.call("vox", self.vox, [self.points, self.points_size])
         V = vo[4]
-        for k in range(len(self.smax)):
-            self.call(f"sm{k}", self.smax[k], [self.pfn_out[k], vo[1], vo[3], V])
-        parts = []
+        x0 = self.x0
+        if self.backbone:
+            (w0, s0, t0), (w1, s1, t1) = self.pfn
+            h0 = torch.relu(Fn.linear(vo[0], w0) * s0 + t0)                                 # PFN layer 0  (:577)
+            sm0 = self.call("sm0", self.smax[0], [h0, vo[1], vo[3], V])
+            h1 = torch.relu(Fn.linear(torch.cat([h0, sm0[0]], dim=2), w1) * s1 + t1)      # concat + PFN layer 1 (:583-587)
+            x0 = self.call("sm1", self.smax[1], [h1, vo[1], vo[3], V])[1]
+        else:
+            for k in range(len(self.smax)):
+                self.call(f"sm{k}", self.smax[k], [self.pfn_out[k], vo[1], vo[3], V])
+        parts, wps = [], []
         for i in (0, 1):
             w = self.call(f"wp{i}", self.wp[i], [vo[2], V])
+            wps.append(w)
             parts.append(self.call(f"gs{i}", self.gs[i], w[:4]))
-        x, ln = self.x0, 0
+        pos = self.pos
+        if self.backbone:                                                                   # 8 position-embedding MLPs (:603-637)
+            pos = [[Fn.linear(torch.relu(Fn.linear(wps[enc][5], a) * sc + sh), b2, bias2)
+                    for enc, (a, sc, sh, b2, bias2) in enumerate(row)] for row in self.pos_w]
+        x, ln = x0, 0
         for blk in range(cfg.num_blocks):
             gs = parts[blk % 2]
             x_in = x
             for enc in (0, 1):
-                q, k, v = self.call(f"gv{enc}", self.gather[enc], [x, self.pos[blk][enc], gs[0], gs[2]])
+                q, k, v = self.call(f"gv{enc}", self.gather[enc], [x, pos[blk][enc], gs[0], gs[2]])
                 a = self.mha(q, k, v, gs[3], self.attn_w[blk * 2 + enc])
                 y = self.call(f"ms{enc}", self.scatter[enc], [a, gs[0], gs[2]])[0]
                 src = self.call(f"ln{ln}", self.ln[ln], [y + x, V])[0]; ln += 1
-                self.call("ge", self.gelu, [self.ffn_hidden, V])
-                src = self.call(f"ln{ln}", self.ln[ln], [src + self.ffn_out, V])[0]; ln += 1
+                if self.backbone:                                                           # FFN (:494-529)
+                    f1, fb1, f2, fb2 = self.ffn_w[blk * 2 + enc]
+                    hid = self.call("ge", self.gelu, [Fn.linear(src, f1, fb1), V])[0]
+                    ffn_out = Fn.linear(hid, f2, fb2)
+                else:
+                    self.call("ge", self.gelu, [self.ffn_hidden, V])
+                    ffn_out = self.ffn_out
+                src = self.call(f"ln{ln}", self.ln[ln], [src + ffn_out, V])[0]; ln += 1
                 x = self.call(f"ln{ln}", self.ln[ln], [src + x, V])[0]; ln += 1
             x = self.call(f"ln{ln}", self.ln[ln], [x + x_in, V])[0]; ln += 1
         self.call("m2b", self.m2b, [x, vo[2], V])
@@ -210,6 +240,27 @@ def _run(args):
             "e2e": {"value": round(e2e, 3), "unit": bench.UNIT, "h2d_bytes_per_step": F * args.points * 16,
                     "d2h_bytes_per_step": F * (cfg.max_top_k * 36 + 4)},
         })
+        if not getattr(args, "no_ffn_leg", False):
+            # the complete 3-D backbone (our arm's ffn_in_frame.backbone3d): + PFN, position-embedding and FFN linears as
+            # PyTorch eager / cuBLAS with TF32 allowed (TensorRT's default on this class of GPU), full static shapes
+            try:
+                del slots
+                torch.cuda.empty_cache()
+                torch.backends.cuda.matmul.allow_tf32 = True
+                slots_b = []
+                for i in range(F):
+                    fr = ReferenceFrame(plg, cfg, pkg.synth.ring_lidar(args.points, seed=i), i, backbone=True)
+                    fr.capture(streams[i % S])
+                    slots_b.append(fr)
+                torch.cuda.synchronize()
+                bench.run_steps(slots_b, streams, args.warmup, host=False)
+                ms_b = bench.run_steps(slots_b, streams, args.steps, host=False)
+                line["backbone3d"] = {"value": round(frames / (ms_b * 1e-3), 3), "unit": bench.UNIT,
+                                      "note": "reference plugins + PyTorch-eager (cuBLAS, TF32 allowed) stand-ins for every "
+                                              "TensorRT-native layer of the 3-D backbone, over the engine's full static shapes; TF32 also "
+                                              "speeds up the MHA stand-in, which is why this leg can beat the FP32 plugin-only frame"}
+            except Exception as exc2:
+                line["backbone3d"] = {"value": None, "note": f"failed: {str(exc2)[:200]}"}
     except Exception as exc:     # reference kernels unavailable / faulted -> CPU oracle port
         cb = cpu_port_arm(args, cfg, pkg)
         line.update({
