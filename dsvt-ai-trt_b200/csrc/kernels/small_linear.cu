@@ -116,11 +116,12 @@ extern "C" int dsvt_small_linear_launch(const dsvt_small_linear* w, const float*
     DSVT_CHECK_ARG(!((uintptr_t) y & 15), "y must be 16-byte aligned");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     switch (w->K) {
-        case 2: return launch_k<2>(w, x, rows, batch, max_rows, activation, y, zero_tails, st);
-        case 4: return launch_k<4>(w, x, rows, batch, max_rows, activation, y, zero_tails, st);
-        case 10: return launch_k<10>(w, x, rows, batch, max_rows, activation, y, zero_tails, st);
+#define DSVT_SL_CASE(KK) case KK: return launch_k<KK>(w, x, rows, batch, max_rows, activation, y, zero_tails, st);
+        DSVT_SL_CASE(1) DSVT_SL_CASE(2) DSVT_SL_CASE(3) DSVT_SL_CASE(4) DSVT_SL_CASE(5) DSVT_SL_CASE(6) DSVT_SL_CASE(7) DSVT_SL_CASE(8)
+        DSVT_SL_CASE(9) DSVT_SL_CASE(10) DSVT_SL_CASE(11) DSVT_SL_CASE(12) DSVT_SL_CASE(13) DSVT_SL_CASE(14) DSVT_SL_CASE(15) DSVT_SL_CASE(16)
+#undef DSVT_SL_CASE
         default:
-            set_last_error("dsvt_small_linear_launch: K = %d is not built (2, 4, 10)", w->K);
+            set_last_error("dsvt_small_linear_launch: K = %d out of range [1, 16]", w->K);
             return DSVT_ERR_UNSUPPORTED;
     }
 }

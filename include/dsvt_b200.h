@@ -324,7 +324,7 @@ int dsvt_linear_rows_concat_launch(const dsvt_linear_weights* w, const float* x_
 /*
  * Narrow first layers of the VFE / position-embedding MLPs (TensorRT FullyConnected + Scale + ReLU in the reference:
  * PFN layer 0 Linear(10 -> 96) src/dsvt-ai-trt.cpp:577, position embedding Linear(2 -> 192) :603-637 via :461-492):
- *   y = act((x W^T) * scale + shift),  W [N,K] row-major, K in {2, 4, 10}, N / 4 dividing 192, scale / shift [N] = the folded
+ *   y = act((x W^T) * scale + shift),  W [N,K] row-major, K in [1, 16], N / 4 dividing 192, scale / shift [N] = the folded
  *   BatchNorm1d (NULL: 1 / 0).  x [B,max_rows,K] -> y [B,max_rows,N]; rows [B] on the device; rows beyond it zero-filled.
  */
 typedef struct dsvt_small_linear dsvt_small_linear;

@@ -57,3 +57,58 @@ def test_linear_fp32_accurate_tensor_cores(N, K):
     # single FP16 operands: the USE_FP16 tolerance
     y16 = capi.Linear(W, b, precision=capi.DSVT_ATTN_FP16_GEMM)(torch.from_numpy(x[:M]).cuda())
     assert np.abs(y16.cpu().numpy() - ref).max() <= 1e-2
+
+
+@pytest.mark.parametrize("N,K", [(96, 10), (192, 2), (96, 7), (192, 16)])
+@pytest.mark.parametrize("rows", [0, 1, 1000, 1537])
+def test_small_linear(N, K, rows):
+    """Narrow first layers of the PFN / position-embedding MLPs (FullyConnected + Scale + ReLU, reference
+    src/dsvt-ai-trt.cpp:268-286): y = relu((x W^T) * scale + shift) against float64; batch 2 with different row counts."""
+    capi = importlib.import_module("dsvt-ai-trt_b200.capi")
+    rng = np.random.default_rng(N + K + rows)
+    cap = 1537
+    W = (rng.standard_normal((N, K)) * 0.3).astype(np.float32)
+    scale = (0.5 + 0.1 * rng.standard_normal(N)).astype(np.float32)
+    shift = (0.1 * rng.standard_normal(N)).astype(np.float32)
+    x = (rng.standard_normal((2, cap, K)) * 3).astype(np.float32)
+    counts = np.array([rows, min(cap, rows + 5)], np.int32)
+    lin = capi.SmallLinear(W, scale, shift)
+    out = torch.full((2, cap, N), float("nan"), device="cuda")
+    lin(torch.from_numpy(x).cuda(), torch.from_numpy(counts).cuda(), activation=2, out=out)
+    got = out.cpu().numpy()
+    for b in range(2):
+        ref = np.maximum((x[b, :counts[b]].astype(np.float64) @ W.T.astype(np.float64)) * scale + shift, 0.0)
+        assert np.abs(got[b, :counts[b]] - ref).max(initial=0.0) <= 1e-5
+        assert np.all(got[b, counts[b]:] == 0)
+    # no activation, no BatchNorm
+    lin2 = capi.SmallLinear(W)
+    y2 = lin2(torch.from_numpy(x[0]).cuda(), torch.from_numpy(counts[:1]).cuda(), activation=0).cpu().numpy()
+    assert np.abs(y2[:rows] - x[0, :rows].astype(np.float64) @ W.T.astype(np.float64)).max(initial=0.0) <= 1e-5
+
+
+@pytest.mark.parametrize("rows", [0, 777, 2048])
+@pytest.mark.parametrize("act", [0, 2])
+def test_linear_rows_concat(rows, act):
+    """PFN layer 1: Linear(192 -> 192) on the concatenation [x_lo (96) | x_hi (96)] read in place (reference
+    src/dsvt-ai-trt.cpp:583-587), BatchNorm folded into W / b, ReLU epilogue; FP32 tolerance 2e-5 relative to the row scale."""
+    capi = importlib.import_module("dsvt-ai-trt_b200.capi")
+    rng = np.random.default_rng(rows + act)
+    cap = 2048
+    W = (rng.standard_normal((192, 192)) * 0.07).astype(np.float32)
+    b = (rng.standard_normal(192) * 0.1).astype(np.float32)
+    lo = rng.standard_normal((cap, 96)).astype(np.float32)
+    hi = rng.standard_normal((cap, 96)).astype(np.float32)
+    lin = capi.Linear(W, b, precision=capi.DSVT_ATTN_FP32_TC)
+    out = torch.full((cap, 192), float("nan"), device="cuda")
+    lin.rows_concat(torch.from_numpy(lo).cuda(), torch.from_numpy(hi).cuda(),
+                    torch.tensor([rows], dtype=torch.int32, device="cuda"), activation=act, out=out)
+    got = out.cpu().numpy()
+    ref = np.concatenate([lo, hi], axis=1)[:rows].astype(np.float64) @ W.T.astype(np.float64) + b
+    if act == 2:
+        ref = np.maximum(ref, 0.0)
+    assert np.abs(got[:rows] - ref).max(initial=0.0) <= 2e-5
+    assert np.all(got[rows:] == 0)
+    # identical to the same layer on the materialised concatenation
+    cat = torch.from_numpy(np.concatenate([lo, hi], axis=1)).cuda()
+    same = lin.rows(cat, torch.tensor([rows], dtype=torch.int32, device="cuda"), activation=act)
+    assert torch.equal(same, out)
