@@ -499,11 +499,12 @@ def _main():
                    "workload": "same frames and plugins + the 16 FFN linears (192->384, 384->192 per encoder layer, "
                                "src/dsvt-ai-trt.cpp:494-529) on the FP32-accurate tcgen05 linear kernel; PFN / pos-embed MLPs, "
                                "BEV backbone and head still not executed"}
-        for name in ("graph", "fused", "backbone3d"):
+        for name in ("graph", "fused", "backbone3d", "backbone3d_fused"):
             slots_f = []
             for i, s in enumerate(slots):
                 fr = pipeline.HotPathFrame(cfg, weights, precision=precision, seed=sharding.global_frame_id(rank, world, i),
-                                           ffn="graph" if name == "backbone3d" else name, backbone=name == "backbone3d")
+                                           ffn={"backbone3d": "graph", "backbone3d_fused": "fused"}.get(name, name),
+                                           backbone=name.startswith("backbone3d"))
                 sf = Slot.__new__(Slot)
                 sf.frame, sf.n = fr, s.n
                 sf.host_points, sf.host_n, sf.host_boxes, sf.host_valid = s.host_points, s.host_n, s.host_boxes, s.host_valid
@@ -523,7 +524,9 @@ def _main():
                              "e2e": round(F * world * args.steps / (e2e_f * 1e-3), 2),
                              "launches_per_frame": int(slots_f[0].frame.launches_per_frame),
                              "form": {"graph": "FC -> GeluPlugin -> FC (the reference graph's nodes)",
-                                      "fused": "FC with GELU epilogue -> FC (GeluPlugin folded into the linear)",
+                                      "fused": "FC with GELU epilogue -> split-K FC with the residual add in its epilogue (GeluPlugin and "
+                                               "the kSUM behind the FFN folded into the linears)",
+                                      "backbone3d_fused": "backbone3d with the 'fused' FFN form",
                                       "backbone3d": "EVERY layer of the reference's 3-D backbone, raw points -> BEV map, as one data "
                                                     "flow: 'graph' + PFN layers 0 / 1 (Linear+BN+ReLU) and the 8 position-embedding "
                                                     "MLPs (src/dsvt-ai-trt.cpp:571-1128); only the 2-D BEV backbone + head and the "

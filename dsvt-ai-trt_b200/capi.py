@@ -418,6 +418,18 @@ class Linear:
                "dsvt_linear_rows_launch")
         return out
 
+    def rows_splitk(self, x, rows, add=None, out=None):
+        """Split-K form (N == 192, K = 192 * kb): one launch, out[j] = partial product of K block j (bias and the optional
+        residual rows `add` in part 0); the result is out.sum(0).  x [max_rows, K] -> out [kb, max_rows, 192]."""
+        _need(x, torch.float32, "x")
+        _need(rows, torch.int32, "rows")
+        max_rows, kb = x.shape[0], self.K // 192
+        out = torch.empty(kb, max_rows, self.N, dtype=torch.float32, device=x.device) if out is None else out
+        _check(_lib().dsvt_linear_rows_splitk_launch(c_void_p(self.handle), _ptr(x), _ptr(add), _ptr(rows),
+                                                     c_int32(max_rows), _ptr(out), _stream()),
+               "dsvt_linear_rows_splitk_launch")
+        return out
+
     def rows_concat(self, x_lo, x_hi, rows, activation=0, out=None, zero_tails=1):
         """Same as rows() for the input [x_lo | x_hi] (two dense tensors, e.g. the PFN's concatenation of the point
         features and their per-pillar max), read in place.  activation: 0 none, 1 GELU, 2 ReLU."""

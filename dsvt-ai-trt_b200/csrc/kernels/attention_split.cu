@@ -101,6 +101,8 @@ struct GemmRole {
     int lda;                // floats per row of a0 / a1 (192 for the attention tensors; K for a wider linear layer)
     int accumulate;         // 1: add to the rows already in `out` (second 192-wide K block of a linear layer)
     int act;                // 0: none, 1: GELU (tanh form, gelu.cu:201-211), 2: ReLU on the finished value
+    const float* add_src;   // optional rows [rows, ld_out-compatible N] added to the finished value (a residual folded into the
+    int ld_add;             //   epilogue: the addElementWise(kSUM) behind the FFN, src/dsvt-ai-trt.cpp:685); nullptr: off
     const float* a0b;       // optional second source of the A operand: columns >= ksplit of the K block come from a0b
     int ksplit, ldb;        //   (the PFN's concatenation [point features | per-pillar max], src/dsvt-ai-trt.cpp:583-587,
                             //   read in place instead of being materialised); ksplit is a multiple of 32, a0b == nullptr: off
@@ -338,6 +340,11 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
                         if (g.accumulate && orow[rr] >= 0 && grow < V) {   // second K block: add to the first block's rows
                             const float4 pv4 = *reinterpret_cast<const float4*>(outc + (size_t) orow[rr] * g.ld_out + j0);
                             ov.x += pv4.x; ov.y += pv4.y; ov.z += pv4.z; ov.w += pv4.w;
+                        }
+                        if (g.add_src && orow[rr] >= 0 && grow < V) {      // residual rows, same coalesced 128-byte segments
+                            const float4 ad = __ldg(reinterpret_cast<const float4*>(
+                                g.add_src + ((size_t) b * max_pillars + grow) * g.ld_add + g.col0 + hf * 96 + c4 * 4 + j0));
+                            ov.x += ad.x; ov.y += ad.y; ov.z += ad.z; ov.w += ad.w;
                         }
                         if (g.act == 1) { ov.x = gelu_tanh(ov.x); ov.y = gelu_tanh(ov.y); ov.z = gelu_tanh(ov.z); ov.w = gelu_tanh(ov.w); }
                         else if (g.act == 2) { ov.x = fmaxf(ov.x, 0.f); ov.y = fmaxf(ov.y, 0.f); ov.z = fmaxf(ov.z, 0.f); ov.w = fmaxf(ov.w, 0.f); }
@@ -807,6 +814,7 @@ int linear_split_launch(const void* blob, int N, int K, float out_mul, bool spli
                 GemmRole& g = roles.r[r];
                 g.a0 = x + (size_t) j * kC; g.a1 = nullptr; g.lda = x_hi ? k_split : K;
                 g.a0b = x_hi; g.ksplit = x_hi ? k_split : 0; g.ldb = x_hi ? K - k_split : 0;
+                g.add_src = nullptr; g.ld_add = 0;
                 g.wimg = img + ((size_t) i * kb + j) * kWRoleBytes;
                 g.bias = j == 0 ? bias + i * kBN : zero_bias;
                 g.out = y; g.ld_out = N; g.col0 = i * kBN;
@@ -824,6 +832,51 @@ int linear_split_launch(const void* blob, int N, int K, float out_mul, bool spli
                 proj_gemm_kernel<false><<<dim3(grid, 1), kThreadsG, Lay<false>::total, st>>>(roles, n_roles, rows_dev, rows_host, max_rows, 1, zt);
             DSVT_LAUNCH_CHECK();
         }
+    return DSVT_OK;
+}
+
+// Split-K form of a [*, K] -> [*, 192] layer (K = 192 * kb, kb <= 3): ONE launch whose roles are the K blocks; role j writes
+// the partial product of K block j to y_parts[j] ([max_rows, 192] each; bias and the optional residual rows `add` go into
+// part 0).  The consumer sums the parts (the LayerNorm behind the FFN takes part 1 as its residual input), so the
+// read-modify-write of the accumulating two-launch form and one pipeline fill / drain disappear.
+int linear_split_k_launch(const void* blob, int N, int K, float out_mul, bool split, const float* x, const float* add,
+                          const int* rows_dev, int max_rows, float* y_parts, cudaStream_t st)
+{
+    const int kb = K / kC;
+    const uint8_t* img = static_cast<const uint8_t*>(blob);
+    const float* bias = reinterpret_cast<const float*>(img + (size_t) kb * kWRoleBytes);
+    static float* zero_bias = nullptr;
+    if (!zero_bias) {
+        DSVT_CUDA(cudaMalloc(&zero_bias, kBN * sizeof(float)));
+        DSVT_CUDA(cudaMemset(zero_bias, 0, kBN * sizeof(float)));
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        DSVT_CUDA(cudaFuncSetAttribute(proj_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<true>::total));
+        DSVT_CUDA(cudaFuncSetAttribute(proj_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<false>::total));
+        attr_set = true;
+    }
+    GemmRoles roles;
+    for (int r = 0; r < 3; ++r) {
+        const int j = r < kb ? r : 0;
+        GemmRole& g = roles.r[r];
+        g.a0 = x + (size_t) j * kC; g.a1 = nullptr; g.lda = K;
+        g.a0b = nullptr; g.ksplit = 0; g.ldb = 0;
+        g.wimg = img + (size_t) j * kWRoleBytes;
+        g.bias = j == 0 ? bias : zero_bias;
+        g.out = y_parts + (size_t) j * max_rows * N; g.ld_out = N; g.col0 = 0;
+        g.out_mul = out_mul; g.post_mul = 1.0f;
+        g.plan = nullptr; g.plan_stride = 0; g.pad_hi = 0;
+        g.accumulate = 0; g.act = 0;
+        g.add_src = j == 0 ? add : nullptr; g.ld_add = N;
+    }
+    const int per = sm_count() * gemm_sm_fraction() / 100;
+    const int grid = per >= kb ? per / kb * kb : kb;
+    if (split)
+        proj_gemm_kernel<true><<<dim3(grid, 1), kThreadsG, Lay<true>::total, st>>>(roles, kb, rows_dev, 0, max_rows, 1, 0);
+    else
+        proj_gemm_kernel<false><<<dim3(grid, 1), kThreadsG, Lay<false>::total, st>>>(roles, kb, rows_dev, 0, max_rows, 1, 0);
+    DSVT_LAUNCH_CHECK();
     return DSVT_OK;
 }
 
@@ -1000,7 +1053,7 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
         g.plan_stride = plan_stride;
         g.pad_hi = r == 0 ? 0 : 4;
         g.lda = kC; g.accumulate = 0; g.act = 0;
-        g.a0b = nullptr; g.ksplit = 0; g.ldb = 0;
+        g.a0b = nullptr; g.ksplit = 0; g.ldb = 0; g.add_src = nullptr; g.ld_add = 0;
     }
     {
         GemmRole& g = out_roles.r[0];
@@ -1012,7 +1065,7 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
         g.post_mul = 1.0f;
         g.plan = nullptr; g.plan_stride = 0; g.pad_hi = 0;
         g.lda = kC; g.accumulate = 0; g.act = 0;
-        g.a0b = nullptr; g.ksplit = 0; g.ldb = 0;
+        g.a0b = nullptr; g.ksplit = 0; g.ldb = 0; g.add_src = nullptr; g.ld_add = 0;
         out_roles.r[1] = out_roles.r[2] = g;
     }
     if (g_skip_mask & 1) {

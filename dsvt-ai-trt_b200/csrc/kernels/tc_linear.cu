@@ -139,6 +139,8 @@ void* linear_split_prepare(int N, int K, const float* W, const float* b, float* 
 int linear_split_launch(const void* blob, int N, int K, float out_mul, bool split, int act, const float* x,
                         const float* x_hi, int k_split, const int* rows_dev, int rows_host, int max_rows, float* y,
                         int zero_tails, cudaStream_t st);
+int linear_split_k_launch(const void* blob, int N, int K, float out_mul, bool split, const float* x, const float* add,
+                          const int* rows_dev, int max_rows, float* y_parts, cudaStream_t st);
 }
 
 struct dsvt_linear_weights {
@@ -265,4 +267,15 @@ extern "C" int dsvt_linear_rows_concat_launch(const dsvt_linear_weights* w, cons
     DSVT_CHECK_ARG(!((((uintptr_t) x_lo | (uintptr_t) x_hi) & 31) | ((uintptr_t) y & 15)), "alignment (x 32 B, y 16 B)");
     return dsvt::linear_split_launch(w->split_blob, w->N, w->K, w->out_mul, w->precision == DSVT_ATTN_FP32_TC, activation, x_lo,
                                      x_hi, k_split, rows, 0, max_rows, y, zero_tails, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dsvt_linear_rows_splitk_launch(const dsvt_linear_weights* w, const float* x, const float* add,
+                                              const int32_t* rows, int32_t max_rows, float* y_parts, dsvt_stream_t stream)
+{
+    DSVT_CHECK_ARG(w && x && y_parts && rows && max_rows >= 1, "NULL argument");
+    DSVT_CHECK_ARG(w->split_blob != nullptr, "built for precision DSVT_ATTN_FP32_TC / DSVT_ATTN_FP16_GEMM weights only");
+    DSVT_CHECK_ARG(w->N == 192 && w->K >= 192 && w->K <= 576, "split-K form: N == 192, K in {192, 384, 576}");
+    DSVT_CHECK_ARG(!(((uintptr_t) x & 31) | ((uintptr_t) y_parts & 15) | ((uintptr_t) add & 15)), "alignment (x 32 B, y / add 16 B)");
+    return dsvt::linear_split_k_launch(w->split_blob, w->N, w->K, w->out_mul, w->precision == DSVT_ATTN_FP32_TC, x, add, rows,
+                                       max_rows, y_parts, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -19,7 +19,8 @@ come from the real voxeliser / partition of the frame's cloud).
 (fullyConnected_gelu_fullyConnected, src/dsvt-ai-trt.cpp:494-529) run on the FP32-accurate tensor-core linear
 kernel (dsvt_linear_rows_launch), so a DSVT block becomes a real data flow from its input rows to its output rows:
     "graph": FC 192->384 -> GeluPlugin -> FC 384->192        (the reference graph's three nodes)
-    "fused": FC 192->384 with the GELU in its epilogue -> FC 384->192   (one pass less over the 384-wide rows)
+    "fused": FC 192->384 with the GELU in its epilogue -> FC 384->192 in split-K form with the residual add behind the FFN
+             in its epilogue (one pass less over the 384-wide rows, one launch instead of two accumulating ones)
 
 ``backbone=True`` (with ``ffn`` on) runs the remaining TensorRT-native layers of the 3-D backbone as well, so that the frame
 is ONE data flow from the raw points to the BEV map (random-init weights, BatchNorm folded):
@@ -139,6 +140,7 @@ class HotPathFrame:
         if ffn != "off":
             self.ffn_h = torch.empty(mp, F, device=device)      # FC 192->384 output (graph form only)
             self.ffn_o = torch.empty(mp, C, device=device)      # FC 384->192 output
+            self.ffn_parts = torch.empty(F // C, mp, C, device=device)    # ... as split-K partial sums (fused form)
         if backbone:
             Pm = cfg.max_points_num_voxel_filter
             self.pfn0_out = torch.empty(Pm, cfg.pfn_channels[0], device=device)
@@ -214,7 +216,7 @@ class HotPathFrame:
                         capi.gelu(self.ffn_hidden, V, out=self.gelu_out, zero_tails=zt)
                     continue
                 capi.layer_norm(self.attn_out, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=x,
-                                out=self.src, zero_tails=zt); ln += 1                                     # norm1(y + x)   :669-676
+                                out=self.src, zero_tails=zt); ln += 1                      # norm1(y + x)   :669-676
                 ffn_out = self.ffn_out
                 if self.ffn == "off":
                     if "gelu" not in skip:
@@ -226,23 +228,30 @@ class HotPathFrame:
                         capi.gelu(self.ffn_h, V, out=self.gelu_out, zero_tails=zt)         # :519  GeluPlugin
                     else:
                         fc1.rows(self.src, V, activation=1, out=self.gelu_out, zero_tails=zt)   # FC + GELU epilogue
-                    ffn_out = fc2.rows(self.gelu_out, V, out=self.ffn_o, zero_tails=zt)    # :524  FC 384->192
+                    if self.ffn == "graph":
+                        ffn_out = fc2.rows(self.gelu_out, V, out=self.ffn_o, zero_tails=zt)   # :524  FC 384->192
                 nxt = self.x_a if enc == 0 else self.x_b
+                ln_in = self.src
+                if self.ffn == "fused" and "ln" not in skip:
+                    # FC 384->192 in split-K form: ONE launch, part 0 = first K block + bias + src (the residual add behind
+                    # the FFN folded into the epilogue), part 1 = second K block; norm2 sums them
+                    parts = fc2.rows_splitk(self.gelu_out, V, add=self.src, out=self.ffn_parts)
+                    ln_in, ffn_out = parts[0], parts[1]
                 if not self.fuse_ln:
-                    capi.layer_norm(self.src, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=ffn_out,
-                                    out=self.src_b, zero_tails=zt); ln += 1                               # norm2(src + src2) :685-690
+                    capi.layer_norm(ln_in, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=ffn_out,
+                                    out=self.src_b, zero_tails=zt); ln += 1                # norm2(src + src2) :685-690
                     capi.layer_norm(self.src_b, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=x,
-                                    out=nxt, zero_tails=zt); ln += 1                                      # norm(src + x)  :691-697
+                                    out=nxt, zero_tails=zt); ln += 1                       # norm(src + x)  :691-697
                     if enc == 1:
                         capi.layer_norm(nxt, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=x_in,
-                                        out=self.blk_out[blk % 2], zero_tails=zt); ln += 1                # residual norm  :750-756
+                                        out=self.blk_out[blk % 2], zero_tails=zt); ln += 1  # residual norm  :750-756
                 else:
                     # the same LayerNorms as one chained launch (rows stay in registers between stages)
                     stages = [(ffn_out, w.gamma[ln], w.beta[ln]), (x, w.gamma[ln + 1], w.beta[ln + 1])]
                     ln += 2
                     if enc == 1:
                         stages.append((x_in, w.gamma[ln], w.beta[ln])); ln += 1
-                    capi.layer_norm_chain(self.src, V, stages, cfg.layer_norm_eps,
+                    capi.layer_norm_chain(ln_in, V, stages, cfg.layer_norm_eps,
                                           out=nxt if enc == 0 else self.blk_out[blk % 2], zero_tails=zt)
                 x = nxt
             x = self.blk_out[blk % 2]

@@ -322,6 +322,15 @@ int dsvt_linear_rows_concat_launch(const dsvt_linear_weights* w, const float* x_
                                    dsvt_stream_t stream);
 
 /*
+ * Split-K form for N == 192, K = 192 * kb (kb <= 3; the FFN's second linear 384 -> 192): ONE launch, K block j writes its
+ * partial product to y_parts[j] ([max_rows,192] each, rows beyond `rows` untouched); bias and the optional residual rows
+ * `add` [max_rows,192] (the addElementWise(kSUM) behind the FFN, src/dsvt-ai-trt.cpp:685) go into part 0.  The result is
+ * the sum of the parts: pass part 0 as x and part 1 as the residual of the LayerNorm that follows.
+ */
+int dsvt_linear_rows_splitk_launch(const dsvt_linear_weights* w, const float* x, const float* add, const int32_t* rows,
+                                   int32_t max_rows, float* y_parts, dsvt_stream_t stream);
+
+/*
  * Narrow first layers of the VFE / position-embedding MLPs (TensorRT FullyConnected + Scale + ReLU in the reference:
  * PFN layer 0 Linear(10 -> 96) src/dsvt-ai-trt.cpp:577, position embedding Linear(2 -> 192) :603-637 via :461-492):
  *   y = act((x W^T) * scale + shift),  W [N,K] row-major, K in [1, 16], N / 4 dividing 192, scale / shift [N] = the folded

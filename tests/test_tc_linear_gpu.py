@@ -112,3 +112,23 @@ def test_linear_rows_concat(rows, act):
     cat = torch.from_numpy(np.concatenate([lo, hi], axis=1)).cuda()
     same = lin.rows(cat, torch.tensor([rows], dtype=torch.int32, device="cuda"), activation=act)
     assert torch.equal(same, out)
+
+
+@pytest.mark.parametrize("rows", [0, 333, 1024])
+@pytest.mark.parametrize("with_add", [False, True])
+def test_linear_rows_splitk(rows, with_add):
+    """FFN second linear 384 -> 192 in split-K form: one launch, the parts sum to x W^T + b (+ residual rows)."""
+    capi = importlib.import_module("dsvt-ai-trt_b200.capi")
+    rng = np.random.default_rng(rows + with_add)
+    cap = 1024
+    W = (rng.standard_normal((192, 384)) * 0.05).astype(np.float32)
+    b = (rng.standard_normal(192) * 0.1).astype(np.float32)
+    x = rng.standard_normal((cap, 384)).astype(np.float32)
+    add = rng.standard_normal((cap, 192)).astype(np.float32)
+    lin = capi.Linear(W, b, precision=capi.DSVT_ATTN_FP32_TC)
+    parts = lin.rows_splitk(torch.from_numpy(x).cuda(), torch.tensor([rows], dtype=torch.int32, device="cuda"),
+                            add=torch.from_numpy(add).cuda() if with_add else None)
+    assert parts.shape == (2, cap, 192)
+    got = (parts[0, :rows] + parts[1, :rows]).cpu().numpy()
+    ref = x[:rows].astype(np.float64) @ W.T.astype(np.float64) + b + (add[:rows] if with_add else 0.0)
+    assert np.abs(got - ref).max(initial=0.0) <= 2e-5
