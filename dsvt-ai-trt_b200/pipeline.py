@@ -22,6 +22,10 @@ kernel (dsvt_linear_rows_launch), so a DSVT block becomes a real data flow from 
     "fused": FC 192->384 with the GELU in its epilogue -> FC 384->192 in split-K form with the residual add behind the FFN
              in its epilogue (one pass less over the 384-wide rows, one launch instead of two accumulating ones)
 
+The linear layers stand for TensorRT FullyConnected layers, which have no zero-tail contract (the engine computes all
+max_pillars rows; rows beyond the valid count hold bias-only values there and are never read by a plugin): they are launched
+with zero_tails = 0 and leave those rows untouched.  Every plugin output keeps the reference's zero tails.
+
 ``backbone=True`` (with ``ffn`` on) runs the remaining TensorRT-native layers of the 3-D backbone as well, so that the frame
 is ONE data flow from the raw points to the BEV map (random-init weights, BatchNorm folded):
     PFN layer 0  Linear(10->96)+BN+ReLU on the decorated points           (src/dsvt-ai-trt.cpp:577, dsvt_small_linear_launch)
@@ -175,10 +179,10 @@ class HotPathFrame:
             if self.backbone:                                                       # the PFN layer in front of the scatter-max
                 g = w.glue
                 if k == 0:
-                    pfn_out = g["pfn0"](vox.point_features[0], vox.point_num, activation=2, out=self.pfn0_out, zero_tails=zt)
+                    pfn_out = g["pfn0"](vox.point_features[0], vox.point_num, activation=2, out=self.pfn0_out, zero_tails=0)
                 else:
                     pfn_out = g["pfn1"].rows_concat(self.pfn0_out, self.max_point[0], vox.point_num, activation=2,
-                                                    out=self.pfn1_out, zero_tails=zt)
+                                                    out=self.pfn1_out, zero_tails=0)
             capi.torch_scatter_max(pfn_out, vox.point_index_in_voxel[0], vox.point_num_in_voxel[0], V,
                                    vox.point_num, max_point=self.max_point[k], max_voxel=self.max_voxel[k], zero_tails=zt)
         for i in (() if "part" in skip else (0, 1)):
@@ -199,8 +203,8 @@ class HotPathFrame:
             for blk in range(cfg.num_blocks):              # pos_embed[blk][i] from the shift-i window coordinates (:603-637)
                 for enc in (0, 1):
                     first, second = w.glue["pos"][blk][enc]
-                    first(self.wp[enc].coors_in_win_x_y[0], V, activation=2, out=self.pos_hidden, zero_tails=zt)
-                    second.rows(self.pos_hidden, V, out=self.pos_out[blk][enc], zero_tails=zt)
+                    first(self.wp[enc].coors_in_win_x_y[0], V, activation=2, out=self.pos_hidden, zero_tails=0)
+                    second.rows(self.pos_hidden, V, out=self.pos_out[blk][enc], zero_tails=0)
         for blk in range(cfg.num_blocks):
             gs = self.gs[blk % 2]                      # blocks 0,2: 12x12 windows; 1,3: 24x24 shifted (:654-:1018)
             x_in = x
@@ -224,12 +228,12 @@ class HotPathFrame:
                 else:
                     fc1, fc2 = w.ffn[blk * 2 + enc]
                     if self.ffn == "graph":
-                        fc1.rows(self.src, V, out=self.ffn_h, zero_tails=zt)               # :513  FC 192->384
+                        fc1.rows(self.src, V, out=self.ffn_h, zero_tails=0)               # :513  FC 192->384
                         capi.gelu(self.ffn_h, V, out=self.gelu_out, zero_tails=zt)         # :519  GeluPlugin
                     else:
-                        fc1.rows(self.src, V, activation=1, out=self.gelu_out, zero_tails=zt)   # FC + GELU epilogue
+                        fc1.rows(self.src, V, activation=1, out=self.gelu_out, zero_tails=0)   # FC + GELU epilogue
                     if self.ffn == "graph":
-                        ffn_out = fc2.rows(self.gelu_out, V, out=self.ffn_o, zero_tails=zt)   # :524  FC 384->192
+                        ffn_out = fc2.rows(self.gelu_out, V, out=self.ffn_o, zero_tails=0)   # :524  FC 384->192
                 nxt = self.x_a if enc == 0 else self.x_b
                 ln_in = self.src
                 if self.ffn == "fused" and "ln" not in skip:
