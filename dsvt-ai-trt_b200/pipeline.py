@@ -39,44 +39,102 @@ from . import capi
 
 
 class FrameWeights:
-    """Random-init weights of the 8 attention layers and 28 LayerNorms (no checkpoint is reachable offline)."""
+    """Weights of the 3-D backbone: 8 attention layers, 28 LayerNorms, FFN / PFN / position-embedding linears.
+    ``FrameWeights(cfg, seed)`` draws random-init values (the bench: no checkpoint is reachable offline);
+    ``FrameWeights.from_wts(cfg, tensors)`` takes the reference's trained tensors (dsvt.wts names, oracle/wts.py)."""
 
-    def __init__(self, cfg, seed=0, device="cuda"):
+    def __init__(self, cfg, seed=0, device="cuda", _host=None):
         rng = np.random.default_rng(seed)
         C = cfg.channel_num
-        self.attn, self.attn_host = [], []          # device images / the host arrays they were made from (for the tests)
-        for _ in range(cfg.num_blocks * 2):
-            self.attn_host.append(((rng.standard_normal((3 * C, C)) * 0.06).astype(np.float32),
-                                   (rng.standard_normal(3 * C) * 0.02).astype(np.float32),
-                                   (rng.standard_normal((C, C)) * 0.06).astype(np.float32),
-                                   (rng.standard_normal(C) * 0.02).astype(np.float32)))
-            self.attn.append(capi.AttentionWeights(*self.attn_host[-1], C, cfg.num_heads))
+        host = _host if _host is not None else self._random_host(cfg, rng)
+        self.attn_host = host["attn"]               # the host arrays the device images are made from (for the tests)
+        self.attn = [capi.AttentionWeights(*a, C, cfg.num_heads) for a in self.attn_host]
         # stand-ins for the two PFN layer outputs (src/dsvt-ai-trt.cpp:577-590), shared by all frame slots (read-only)
         g = torch.Generator(device="cpu").manual_seed(seed + 1)
         self.pfn_out = [torch.randn(cfg.max_points_num_voxel_filter, f, generator=g).to(device) for f in cfg.pfn_channels]
-        n_ln = cfg.num_blocks * 7
-        self.gamma = torch.from_numpy((1.0 + 0.1 * rng.standard_normal((n_ln, C))).astype(np.float32)).to(device)
-        self.beta = torch.from_numpy((0.1 * rng.standard_normal((n_ln, C))).astype(np.float32)).to(device)
+        self.gamma = torch.from_numpy(host["gamma"]).to(device)
+        self.beta = torch.from_numpy(host["beta"]).to(device)
         # FFN linears (fullyConnected_gelu_fullyConnected, src/dsvt-ai-trt.cpp:494-529): created on first use
-        self._ffn_host = [((rng.standard_normal((cfg.ffn_channel_num, C)) * 0.07).astype(np.float32),
-                           (rng.standard_normal(cfg.ffn_channel_num) * 0.02).astype(np.float32),
-                           (rng.standard_normal((C, cfg.ffn_channel_num)) * 0.05).astype(np.float32),
-                           (rng.standard_normal(C) * 0.02).astype(np.float32)) for _ in range(cfg.num_blocks * 2)]
+        self._ffn_host = host["ffn"]
         self._ffn = None
         # VFE (PFN layers) and position-embedding MLPs (src/dsvt-ai-trt.cpp:577-637): BatchNorm1d folded to (scale, shift)
-        def bn(n):
-            gamma, var = 1.0 + 0.1 * rng.standard_normal(n), rng.uniform(0.5, 1.5, n)
-            mean, beta = 0.1 * rng.standard_normal(n), 0.1 * rng.standard_normal(n)
-            scale = 0.5 * gamma / np.sqrt(var + 1e-5)
-            return scale.astype(np.float32), (beta - mean * scale).astype(np.float32)
-        F0, F1 = cfg.pfn_channels
-        self.vfe_host = {"pfn0": ((rng.standard_normal((F0, cfg.feature_num)) * 0.05).astype(np.float32),) + bn(F0),
-                         "pfn1": ((rng.standard_normal((F1, 2 * F0)) * 0.07).astype(np.float32),) + bn(F1)}
-        self.pos_host = [[((rng.standard_normal((C, 2)) * 0.3).astype(np.float32),) + bn(C) +
-                          ((rng.standard_normal((C, C)) * 0.07).astype(np.float32),
-                           (rng.standard_normal(C) * 0.02).astype(np.float32)) for _ in range(2)]
-                         for _ in range(cfg.num_blocks)]
+        self.vfe_host = host["vfe"]
+        self.pos_host = host["pos"]
         self._glue = None
+
+    @staticmethod
+    def _random_host(cfg, rng):
+        C = cfg.channel_num
+        attn = [((rng.standard_normal((3 * C, C)) * 0.06).astype(np.float32),
+                 (rng.standard_normal(3 * C) * 0.02).astype(np.float32),
+                 (rng.standard_normal((C, C)) * 0.06).astype(np.float32),
+                 (rng.standard_normal(C) * 0.02).astype(np.float32)) for _ in range(cfg.num_blocks * 2)]
+        n_ln = cfg.num_blocks * 7
+        gamma = (1.0 + 0.1 * rng.standard_normal((n_ln, C))).astype(np.float32)
+        beta = (0.1 * rng.standard_normal((n_ln, C))).astype(np.float32)
+        ffn = [((rng.standard_normal((cfg.ffn_channel_num, C)) * 0.07).astype(np.float32),
+                (rng.standard_normal(cfg.ffn_channel_num) * 0.02).astype(np.float32),
+                (rng.standard_normal((C, cfg.ffn_channel_num)) * 0.05).astype(np.float32),
+                (rng.standard_normal(C) * 0.02).astype(np.float32)) for _ in range(cfg.num_blocks * 2)]
+
+        def bn(n):
+            g_, var = 1.0 + 0.1 * rng.standard_normal(n), rng.uniform(0.5, 1.5, n)
+            mean, b_ = 0.1 * rng.standard_normal(n), 0.1 * rng.standard_normal(n)
+            scale = 0.5 * g_ / np.sqrt(var + 1e-5)
+            return scale.astype(np.float32), (b_ - mean * scale).astype(np.float32)
+        F0, F1 = cfg.pfn_channels
+        vfe = {"pfn0": ((rng.standard_normal((F0, cfg.feature_num)) * 0.05).astype(np.float32),) + bn(F0),
+               "pfn1": ((rng.standard_normal((F1, 2 * F0)) * 0.07).astype(np.float32),) + bn(F1)}
+        pos = [[((rng.standard_normal((C, 2)) * 0.3).astype(np.float32),) + bn(C) +
+                ((rng.standard_normal((C, C)) * 0.07).astype(np.float32),
+                 (rng.standard_normal(C) * 0.02).astype(np.float32)) for _ in range(2)]
+               for _ in range(cfg.num_blocks)]
+        return {"attn": attn, "gamma": gamma, "beta": beta, "ffn": ffn, "vfe": vfe, "pos": pos}
+
+    @classmethod
+    def from_wts(cls, cfg, t, seed=0, device="cuda"):
+        """``t``: {name: float32 array} as oracle/wts.read_wts returns it (in_proj split into .query/.key/.value like the
+        reference's loadWeights_new, include/helper.h:367-433).  The wiring follows src/dsvt-ai-trt.cpp:577-1128:
+        BatchNorm1d folded with eps 1e-5 (:284, :477; add_batchNorm1d_relu :99-147), the first position-embedding linear's
+        bias folded into the BatchNorm shift, LayerNorms in graph order norm1, norm2, norm per encoder + residual_norm."""
+        C, F = cfg.channel_num, cfg.ffn_channel_num
+
+        def bn(prefix, bias=None, eps=1e-5):
+            g_, b_ = t[prefix + ".weight"].astype(np.float64), t[prefix + ".bias"].astype(np.float64)
+            mean, var = t[prefix + ".running_mean"].astype(np.float64), t[prefix + ".running_var"].astype(np.float64)
+            scale = g_ / np.sqrt(var + eps)
+            shift = b_ - mean * scale
+            if bias is not None:                     # y = (W x + bias) * scale + shift
+                shift = shift + bias.astype(np.float64) * scale
+            return scale.astype(np.float32), shift.astype(np.float32)
+
+        attn, ffn, gamma, beta, pos = [], [], [], [], []
+        for blk in range(cfg.num_blocks):
+            row = []
+            for enc in (0, 1):
+                p = f"module.backbone_3d.stage_0.{blk}.encoder_list.{enc}"
+                a = p + ".win_attn.self_attn"
+                w_in = np.concatenate([t[f"{a}.in_proj_weight.{k}"] for k in ("query", "key", "value")]).reshape(3 * C, C)
+                b_in = np.concatenate([t[f"{a}.in_proj_bias.{k}"] for k in ("query", "key", "value")])
+                attn.append((w_in, b_in, t[a + ".out_proj.weight"].reshape(C, C), t[a + ".out_proj.bias"]))
+                ffn.append((t[p + ".win_attn.linear1.weight"].reshape(F, C), t[p + ".win_attn.linear1.bias"],
+                            t[p + ".win_attn.linear2.weight"].reshape(C, F), t[p + ".win_attn.linear2.bias"]))
+                for n in (".win_attn.norm1", ".win_attn.norm2", ".norm"):
+                    gamma.append(t[p + n + ".weight"]); beta.append(t[p + n + ".bias"])
+                e = f"module.backbone_3d.input_layer.posembed_layers.0.{blk}.{enc}.position_embedding_head"
+                row.append((t[e + ".0.weight"].reshape(C, 2),) + bn(e + ".1", bias=t[e + ".0.bias"]) +
+                           (t[e + ".3.weight"].reshape(C, C), t[e + ".3.bias"]))
+            pos.append(row)
+            r = f"module.backbone_3d.residual_norm_stage_0.{blk}"
+            gamma.append(t[r + ".weight"]); beta.append(t[r + ".bias"])
+        F0, F1 = cfg.pfn_channels
+        vfe = {"pfn0": (t["module.vfe.pfn_layers.0.linear.weight"].reshape(F0, cfg.feature_num),) + bn("module.vfe.pfn_layers.0.norm"),
+               "pfn1": (t["module.vfe.pfn_layers.1.linear.weight"].reshape(F1, 2 * F0),) + bn("module.vfe.pfn_layers.1.norm")}
+        host = {"attn": [tuple(np.ascontiguousarray(x, dtype=np.float32) for x in a) for a in attn],
+                "ffn": [tuple(np.ascontiguousarray(x, dtype=np.float32) for x in a) for a in ffn],
+                "gamma": np.stack(gamma).astype(np.float32), "beta": np.stack(beta).astype(np.float32),
+                "vfe": vfe, "pos": pos}
+        return cls(cfg, seed=seed, device=device, _host=host)
 
     @property
     def glue(self):

@@ -3,24 +3,29 @@
 ``ring_lidar`` is the generator fixed by SURVEY.md 8(d) config 2: 64 beams, elevation
 linspace(-17.6 deg, +2.4 deg), sensor height 1.8 m, P/64 azimuth steps per beam with random phase,
 ground hit at r = h / tan(-elev) unless a per-sector obstacle range U(5,75) m (180 sectors) is
-closer, 0.2 % range noise, z noise sigma 0.02, intensity U(0,1).  ``uniform_disc`` is the density
-stress of config 5.
+closer, 0.2 % range noise, z noise sigma 0.02, intensity U(0,1).  The obstacle ranges are drawn per
+(beam, sector): that is the reading of the survey's text which reproduces the statistics it quotes for
+P = 200 000 (about 30.6 k pillars, 189 k kept points, 1130 windows / 1450 sets at 12x12 and 323 / 1016
+at 24x24 shift 6; this generator: 30 781 / 189 692 / 1127 / 1464 / 325 / 1016 for seed 0).  With
+``per_beam_obstacles=False`` every beam sees the same 180 ranges (vertical walls: all 64 beams of a sector
+fall into the same few pillars) -- round 1's reading, about 16.6 k pillars and 897 / 596 sets; kept for the
+sparse end of the density sweep.  ``uniform_disc`` is the density stress of config 5.
 """
 import numpy as np
 
 
-def ring_lidar(n_points: int, seed: int = 0) -> np.ndarray:
+def ring_lidar(n_points: int, seed: int = 0, per_beam_obstacles: bool = True) -> np.ndarray:
     rng = np.random.default_rng(seed)
     beams = 64
     per = n_points // beams
     elev = np.deg2rad(np.linspace(-17.6, 2.4, beams))
     h = 1.8
-    sectors = rng.uniform(5.0, 75.0, size=180)
+    all_sectors = rng.uniform(5.0, 75.0, size=(beams if per_beam_obstacles else 1, 180))
     pts = np.empty((beams * per, 4), dtype=np.float32)
     for b in range(beams):
         az = (np.arange(per) + rng.uniform()) * (2 * np.pi / per)
         sec = np.minimum((az / (2 * np.pi) * 180).astype(np.int64), 179)
-        obstacle = sectors[sec]
+        obstacle = all_sectors[b if per_beam_obstacles else 0][sec]
         if elev[b] < 0:
             ground = h / np.tan(-elev[b])
             r = np.minimum(ground, obstacle)

@@ -142,14 +142,29 @@ def map_set_feature2voxel(feat, idx, set_num, axis, max_pillars):
     return out
 
 
-def set_attention(q, k, v, mask, n_sets, w_in, b_in, w_out, b_out, heads=8):
+def set_attention(q, k, v, mask, n_sets, w_in, b_in, w_out, b_out, heads=8, threads=None):
+    """`threads`: the sets are independent, so the serial C routine is called on slices of them from a thread pool
+    (ctypes releases the GIL) -- only to keep the large parity cases short; the arithmetic per set is unchanged."""
     q, k, v, mask = _f32(q), _f32(k), _f32(v), _f32(mask)
     _, S, C = q.shape
     out = np.zeros_like(q)
-    rc = lib().oracle_set_attention(_p(q), _p(k), _p(v), _p(mask), c_int(int(n_sets)), c_int(S), c_int(C),
-                                    c_int(heads), _p(_f32(w_in)), _p(_f32(b_in)), _p(_f32(w_out)),
-                                    _p(_f32(b_out)), _p(out))
-    assert rc == 0
+    w_in, b_in, w_out, b_out = _f32(w_in), _f32(b_in), _f32(w_out), _f32(b_out)
+    fn = lib().oracle_set_attention
+    n_sets = int(n_sets)
+
+    def run(a, b):
+        rc = fn(_p(q[a:b]), _p(k[a:b]), _p(v[a:b]), _p(mask[a:b]), c_int(b - a), c_int(S), c_int(C),
+                c_int(heads), _p(w_in), _p(b_in), _p(w_out), _p(b_out), _p(out[a:b]))
+        assert rc == 0
+    if threads is None:
+        threads = min(os.cpu_count() or 1, 16) if n_sets >= 256 else 1
+    if threads <= 1 or n_sets < 2 * threads:
+        run(0, n_sets)
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        cuts = [n_sets * i // threads for i in range(threads + 1)]
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(lambda ab: run(*ab), zip(cuts[:-1], cuts[1:])))
     return out
 
 

@@ -149,3 +149,59 @@ def test_whole_3d_backbone_chain(frame0, cfgs, ffn):
     gbev = fr.bev.cpu().numpy()
     assert np.array_equal(gbev != 0, bev != 0)  # the same cells are occupied
     assert np.abs(gbev - bev).max() <= 5e-4
+
+
+# ---- the bench workload and the trained weights -----------------------------------------
+def _run_backbone(cfg, w, cloud, seed=6, ffn="graph", precision=None):
+    capi = importlib.import_module("dsvt-ai-trt_b200.capi")
+    pipeline = importlib.import_module("dsvt-ai-trt_b200.pipeline")
+    fr = pipeline.HotPathFrame(cfg, w, precision=capi.DSVT_ATTN_FP32_TC if precision is None else precision, seed=seed,
+                               ffn=ffn, backbone=True)
+    fr.load_points(cloud)
+    fr.run()
+    torch.cuda.synchronize()
+    return fr
+
+
+def _check_backbone(fr, w, cfg, cloud, tol):
+    ref, bev, V, Pc = oracle_backbone(w, cfg, cloud)
+    assert int(fr.vox.pillar_num[0]) == V and int(fr.vox.point_num[0]) == Pc
+    got = fr.final.cpu().numpy()
+    assert np.isfinite(got).all() and np.all(got[V:] == 0)
+    err = np.abs(got - ref).max()
+    assert err <= tol, err
+    gbev = fr.bev.cpu().numpy()
+    assert np.array_equal(gbev != 0, bev != 0)
+    assert np.abs(gbev - bev).max() <= tol
+    return V, err
+
+
+@pytest.mark.parametrize("geometry", ["WAYMO", "WAYMO_030"])
+def test_bench_workload_chain(pkg, cfgs, geometry):
+    """The bench's own frame (BASELINE.json configs[1]): one 200k-point ring cloud, Waymo capacities (320k / 40k / 4096),
+    ALL 4 blocks, every layer of the 3-D backbone, pillar 0.32 (grid 468) and 0.30 (grid 500), against the oracle chain."""
+    pipeline = importlib.import_module("dsvt-ai-trt_b200.pipeline")
+    cfg = getattr(cfgs, geometry)
+    cloud = pkg.synth.ring_lidar(200000, seed=0)
+    w = pipeline.FrameWeights(cfg, seed=0)
+    fr = _run_backbone(cfg, w, cloud, ffn="fused")
+    V, err = _check_backbone(fr, w, cfg, cloud, 5e-4)
+    assert V > 25000                    # the survey's density (~30.6 k pillars), not round 1's 16.6 k
+    assert int(fr.gs[0].set_num[0]) > 1300 and int(fr.gs[1].set_num[0]) > 900
+
+
+def test_trained_weights_chain(frame0, cfgs):
+    """BASELINE.json configs[0]: the reference's sample frame through all 4 blocks with the TRAINED tensors of dsvt.wts
+    (tests/golden/dsvt_backbone3d_wts.npz, written by tools/make_wts_fixture.py through oracle/wts.py; in_proj split as
+    helper.h:367-433; in_proj_bias is all zeros in the real file)."""
+    import os
+    from conftest import GOLDEN
+    pipeline = importlib.import_module("dsvt-ai-trt_b200.pipeline")
+    t = dict(np.load(os.path.join(GOLDEN, "dsvt_backbone3d_wts.npz")))
+    cfg = cfgs.REFERENCE
+    w = pipeline.FrameWeights.from_wts(cfg, t)
+    assert all(float(np.abs(a[1]).max()) == 0.0 for a in w.attn_host)      # the edge case is really exercised
+    for ffn in ("graph", "fused"):
+        fr = _run_backbone(cfg, w, frame0, ffn=ffn)
+        V, err = _check_backbone(fr, w, cfg, frame0, 5e-4)
+        assert V == 5504
