@@ -3,9 +3,16 @@
 
 A "step" is one pass of the hot path over one batch of F synthetic 200k-point clouds per GPU
 (BASELINE.json configs[1]; frames are independent, one frame per CUDA stream, frame f -> rank f mod N).
+The frame is SURVEY.md 8(d)'s "3-D backbone frame": raw points -> voxeliser -> PFN -> scatter-max -> window partition
+-> getSet -> 4 DSVT blocks (8 set attentions, 8 FFNs, 28 LayerNorms, 8 position-embedding MLPs) -> BEV map, +
+filterBoxByScore on synthetic head candidates -- every layer of the reference's 3-D backbone as ONE data flow.
   value : whole-job frames/s, clouds already resident in HBM, each frame one captured CUDA graph replay.
   e2e   : the same frames through HOST buffers: pinned host cloud -> H2D -> graph -> D2H of the [500,9]
           boxes + count, inside the timed region.
+  legs  : the same clouds as (a) the plugin-only frame (round 1's headline: TensorRT-native layers stood in by fixed
+          tensors), (b) the reference graph's node structure (FC -> GeluPlugin -> FC), (c) the FP16 configuration
+          (BASELINE.json configs[2]), (d) without the contract's zero tails, (e) BASELINE.json configs[3] run literally:
+          64 frames x 180k points, frame f -> rank f mod N, one frame per stream, NCCL gather inside the timed region.
   roofline / plugins : per-plugin device time measured with CUDA events in an instrumented pass over the
           same frames, against MEASURED_PEAKS.json.
   cpu_baseline : the CPU oracle port (oracle/dsvt_oracle.c, 1 core) on a bounded sample of one frame.
@@ -42,12 +49,9 @@ def parse():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32_cuda", "fp32_tc", "tf32", "fp16", "fp16_gemm"])
     ap.add_argument("--points", type=int, default=N_POINTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-relaxed-leg", action="store_true",
-                    help="skip the extra leg that measures the frame without the contract's zero-filled tails")
-    ap.add_argument("--no-ffn-leg", action="store_true",
-                    help="skip the extra leg that runs the FFN linears (SURVEY 8(f) #4) inside the frame")
-    ap.add_argument("--no-fp16-config", action="store_true",
-                    help="skip the extra BASELINE.json configs[2] (FP16 tensor-core attention) measurement")
+    ap.add_argument("--no-legs", action="store_true", help="headline frame only (skip every extra leg)")
+    ap.add_argument("--no-config4", action="store_true", help="skip the BASELINE.json configs[3] leg (64 x 180k frames)")
+    ap.add_argument("--no-breakdown", action="store_true", help="skip the per-plugin breakdown of the reference arm")
     return ap.parse_args()
 
 
@@ -137,29 +141,45 @@ def max_over_ranks(x, world):
 
 
 # ---------------------------------------------------------------------------------------------
+# frame kinds (HotPathFrame keyword arguments); "backbone3d" is the headline
+FRAME_KINDS = {
+    "backbone3d": dict(ffn="fused", backbone=True),          # every layer of the 3-D backbone, FFN in its fused form
+    "backbone3d_graph": dict(ffn="graph", backbone=True),    # ... in the reference graph's node structure
+    "plugin_only": dict(ffn="off", backbone=False),          # plugins only; TensorRT-native layers stood in by fixed tensors
+    "relaxed_tails": dict(ffn="fused", backbone=True, zero_tails=0),
+}
+
+
 class Slot:
     """One frame slot: buffers, captured graph, pinned host staging."""
 
-    def __init__(self, pipeline_mod, cfg, weights, precision, cloud, seed):
+    def __init__(self, pipeline_mod, cfg, weights, precision, cloud, seed, kind="backbone3d", share=None):
         import torch
-        self.frame = pipeline_mod.HotPathFrame(cfg, weights, precision=precision, seed=seed)
+        self.frame = pipeline_mod.HotPathFrame(cfg, weights, precision=precision, seed=seed, **FRAME_KINDS[kind])
         self.n = len(cloud)
-        self.host_points = torch.from_numpy(cloud).pin_memory()
-        self.host_n = torch.tensor([self.n], dtype=torch.int32).pin_memory()
-        self.host_boxes = torch.empty(cfg.max_top_k, 9, dtype=torch.float32).pin_memory()
-        self.host_valid = torch.empty(1, dtype=torch.int32).pin_memory()
-        self.frame.load_points(cloud)
+        if share is not None:          # another leg over the same cloud: reuse the pinned staging buffers
+            self.host_points, self.host_n = share.host_points, share.host_n
+            self.host_boxes, self.host_valid = share.host_boxes, share.host_valid
+            self.frame.points.copy_(share.frame.points)
+            self.frame.points_size.copy_(share.frame.points_size)
+        else:
+            self.host_points = torch.from_numpy(cloud).pin_memory()
+            self.host_n = torch.tensor([self.n], dtype=torch.int32).pin_memory()
+            self.host_boxes = torch.empty(cfg.max_top_k, 9, dtype=torch.float32).pin_memory()
+            self.host_valid = torch.empty(1, dtype=torch.int32).pin_memory()
+            self.frame.load_points(cloud)
         self.graph = None
 
     def capture(self, stream):
         import torch
         with torch.cuda.stream(stream):
-            self.frame.run()                      # warm-up (cudaFuncSetAttribute etc. happen outside capture)
+            self.frame.run()                      # warm-up launch outside the capture
             stream.synchronize()
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph, stream=stream):
                 self.frame.run()
         stream.synchronize()
+        return self
 
     def enqueue_device(self):
         self.graph.replay()
@@ -194,18 +214,21 @@ def run_steps(slots, streams, n_steps, host):
     return total
 
 
-def plugin_breakdown(slot, cfg, peaks, reps=3):
-    """Per-plugin device time (CUDA events, eager launches on the slot's buffers) + roofline numbers."""
-    import numpy as np
+def plugin_breakdown(slot, cfg, peaks, reps=5):
+    """Per-launch device time of every kernel group of the HEADLINE frame (CUDA events around single eager launches on the
+    slot's own buffers after one full run, L2 flushed before each repetition, median) + roofline numbers.
+    calls_per_frame is the launch count in the backbone3d frame (FFN in its fused form)."""
     import torch
     capi = importlib.import_module("dsvt-ai-trt_b200.capi")
     f = slot.frame
+    assert f.backbone and f.ffn == "fused", "the breakdown describes the headline frame kind"
     f.run()
     torch.cuda.synchronize()
     V, Pc, P = int(f.vox.pillar_num[0]), int(f.vox.point_num[0]), slot.n
     W = [int(f.wp[i].win_num[0]) for i in (0, 1)]
     NS = [int(f.gs[i].set_num[0]) for i in (0, 1)]
     C, Fc, S = cfg.channel_num, cfg.ffn_channel_num, cfg.voxel_num_set
+    F0, F1 = cfg.pfn_channels
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
     def timed(fn):
@@ -221,7 +244,9 @@ def plugin_breakdown(slot, cfg, peaks, reps=3):
         ts.sort()
         return ts[len(ts) // 2]
 
-    w = f.w
+    w, g, vox = f.w, f.w.glue, f.vox
+    Vt = vox.pillar_num
+    x = f.max_voxel[-1]                          # the VFE output: real pillar features
     res = {}
     # empty-kernel floor of this timing protocol (the latency-bound plugins are quoted against it): a GELU
     # launch over zero valid rows without tail fill -- a full-width grid whose CTAs exit at once, through the same C ABI
@@ -229,43 +254,59 @@ def plugin_breakdown(slot, cfg, peaks, reps=3):
     tiny_out = torch.empty_like(tiny)
     res["_launch_floor"] = {"us": timed(lambda: capi.gelu(tiny, none_valid, out=tiny_out, zero_tails=0)), "bytes": 0,
                             "calls_per_frame": 0, "note": "empty launch under the same events + L2-flush protocol"}
-    us = timed(lambda: f.vox(f.points, f.points_size))
+    us = timed(lambda: vox(f.points, f.points_size))
     res["points2features"] = {"us": us, "bytes": 16 * P + 44 * Pc + 20 * V + 8, "calls_per_frame": 1}
     for i in (0, 1):
         us = timed(lambda: f.gs[i](f.wp[i].global_index, f.wp[i].coors_in_win, f.wp[i].voxel_num_in_win, f.wp[i].win_num))
         res[f"get_set_{i}"] = {"us": us, "bytes": 16 * V + 4 * W[i] + 2880 * NS[i] + 4, "calls_per_frame": 1}
-        us = timed(lambda: f.wp[i](f.vox.coords, f.vox.pillar_num))
+        us = timed(lambda: f.wp[i](vox.coords, Vt))
         res[f"window_partition_{i}"] = {"us": us, "bytes": 16 * V + 16 * V + 20 * V + 4 * W[i], "calls_per_frame": 1,
                                         "scope": "next"}
+    # VFE: PFN layer 0 (streaming 10 -> 96), scatter-max, PFN layer 1 on [points | max] (tcgen05 linear), scatter-max
+    us = timed(lambda: g["pfn0"](vox.point_features[0], vox.point_num, activation=2, out=f.pfn0_out, zero_tails=0))
+    res["pfn0_linear_bn_relu"] = {"us": us, "bytes": 4 * Pc * (10 + F0), "calls_per_frame": 1, "scope": "next#4"}
+    us = timed(lambda: g["pfn1"].rows_concat(f.pfn0_out, f.max_point[0], vox.point_num, activation=2, out=f.pfn1_out, zero_tails=0))
+    res["pfn1_linear_bn_relu"] = {"us": us, "bytes": 4 * Pc * (2 * F0 + F1), "flops": 2 * Pc * 2 * F0 * F1,
+                                  "calls_per_frame": 1, "scope": "next#4"}
     Pf = cfg.max_points_num_voxel_filter
-    for k, fch in enumerate(cfg.pfn_channels):
-        us = timed(lambda: capi.torch_scatter_max(w.pfn_out[k], f.vox.point_index_in_voxel[0], f.vox.point_num_in_voxel[0],
-                                                  f.vox.pillar_num, f.vox.point_num, max_point=f.max_point[k],
-                                                  max_voxel=f.max_voxel[k]))
+    for k, (fch, src) in enumerate(((F0, f.pfn0_out), (F1, f.pfn1_out))):
+        us = timed(lambda: capi.torch_scatter_max(src, vox.point_index_in_voxel[0], vox.point_num_in_voxel[0], Vt,
+                                                  vox.point_num, max_point=f.max_point[k], max_voxel=f.max_voxel[k]))
         res[f"torch_scatter_max_{fch}"] = {"us": us, "bytes": 4 * fch * (2 * Pc + V) + 4 * (Pc + V), "calls_per_frame": 1,
                                            "scope": "next", "contract_bytes": 4 * fch * (Pc + Pf + cfg.max_pillars_num)}
-    us = timed(lambda: capi.map2bev(f.final, f.vox.coords[0], f.vox.pillar_num, cfg.grid_x, cfg.grid_y, out=f.bev))
+    first, second = g["pos"][0][0]
+    us = timed(lambda: first(f.wp[0].coors_in_win_x_y[0], Vt, activation=2, out=f.pos_hidden, zero_tails=0))
+    res["pos_embed_linear1_bn_relu"] = {"us": us, "bytes": 4 * V * (2 + C), "calls_per_frame": 8, "scope": "next#4"}
+    us = timed(lambda: second.rows(f.pos_hidden, Vt, out=f.pos_out[0][0], zero_tails=0))
+    res["pos_embed_linear2"] = {"us": us, "bytes": 4 * V * 2 * C, "flops": 2 * V * C * C, "calls_per_frame": 8, "scope": "next#4"}
+    us = timed(lambda: capi.map2bev(f.final, vox.coords[0], Vt, cfg.grid_x, cfg.grid_y, out=f.bev))
     res["map2bev"] = {"us": us, "bytes": 2 * 4 * C * V + 16 * V, "calls_per_frame": 1, "scope": "next",
                       "contract_bytes": 4 * C * (cfg.grid_x * cfg.grid_y + V)}
-    us = timed(lambda: capi.gelu(f.ffn_hidden, f.vox.pillar_num, out=f.gelu_out))
-    res["gelu"] = {"us": us, "bytes": 2 * 4 * Fc * V, "calls_per_frame": 8}
-    us = timed(lambda: capi.layer_norm(f.attn_out, f.vox.pillar_num, w.gamma[0], w.beta[0], cfg.layer_norm_eps, out=f.src))
+    us = timed(lambda: capi.gelu(f.gelu_out, Vt, out=f.ffn_h))
+    res["gelu"] = {"us": us, "bytes": 2 * 4 * Fc * V, "calls_per_frame": 0,
+                   "note": "GeluPlugin alone (the headline frame folds it into the first FFN linear's epilogue)"}
+    us = timed(lambda: capi.layer_norm(f.attn_out, Vt, w.gamma[0], w.beta[0], cfg.layer_norm_eps, out=f.src))
     res["layer_norm"] = {"us": us, "bytes": 2 * 4 * C * V + 2 * 4 * C, "calls_per_frame": 0}
-    us = timed(lambda: capi.layer_norm(f.attn_out, f.vox.pillar_num, w.gamma[0], w.beta[0], cfg.layer_norm_eps,
-                                       residual=f.x0, out=f.src))
-    fused = getattr(f, "fuse_ln", False)
-    res["layer_norm_residual"] = {"us": us, "bytes": 3 * 4 * C * V + 2 * 4 * C, "calls_per_frame": 8 if fused else 28}
-    if fused:      # 20 of the 28 LayerNorm plugins run as 4 two-stage + 4 three-stage chained launches per frame
-        st2 = [(f.ffn_out, w.gamma[1], w.beta[1]), (f.x0, w.gamma[2], w.beta[2])]
-        st3 = st2 + [(f.x0, w.gamma[3], w.beta[3])]
-        us = timed(lambda: capi.layer_norm_chain(f.src, f.vox.pillar_num, st2, cfg.layer_norm_eps, out=f.src_b))
-        res["layer_norm_chain2"] = {"us": us, "bytes": 2 * (2 * 4 * C * V + 2 * 4 * C), "calls_per_frame": 4,
-                                    "note": "bytes = 2 LayerNorm plugins' algorithmic bytes; the chain moves 4 row passes"}
-        us = timed(lambda: capi.layer_norm_chain(f.src, f.vox.pillar_num, st3, cfg.layer_norm_eps, out=f.src_b))
-        res["layer_norm_chain3"] = {"us": us, "bytes": 3 * (2 * 4 * C * V + 2 * 4 * C), "calls_per_frame": 4,
-                                    "note": "bytes = 3 LayerNorm plugins' algorithmic bytes; the chain moves 5 row passes"}
+    us = timed(lambda: capi.layer_norm(f.attn_out, Vt, w.gamma[0], w.beta[0], cfg.layer_norm_eps, residual=x, out=f.src))
+    res["layer_norm_residual"] = {"us": us, "bytes": 3 * 4 * C * V + 2 * 4 * C, "calls_per_frame": 8}
+    # 20 of the 28 LayerNorm plugins run as 4 two-stage + 4 three-stage chained launches per frame
+    st2 = [(f.ffn_parts[1], w.gamma[1], w.beta[1]), (x, w.gamma[2], w.beta[2])]
+    st3 = st2 + [(x, w.gamma[3], w.beta[3])]
+    us = timed(lambda: capi.layer_norm_chain(f.ffn_parts[0], Vt, st2, cfg.layer_norm_eps, out=f.src_b))
+    res["layer_norm_chain2"] = {"us": us, "bytes": 2 * (2 * 4 * C * V + 2 * 4 * C), "calls_per_frame": 4,
+                                "note": "bytes = 2 LayerNorm plugins' algorithmic bytes; the chain moves 4 row passes"}
+    us = timed(lambda: capi.layer_norm_chain(f.ffn_parts[0], Vt, st3, cfg.layer_norm_eps, out=f.src_b))
+    res["layer_norm_chain3"] = {"us": us, "bytes": 3 * (2 * 4 * C * V + 2 * 4 * C), "calls_per_frame": 4,
+                                "note": "bytes = 3 LayerNorm plugins' algorithmic bytes; the chain moves 5 row passes"}
     us = timed(lambda: capi.filter_box(cfg, *f.cand, boxes=f.boxes, valid=f.valid))
     res["filter_box"] = {"us": us, "bytes": 22000 + 18004, "calls_per_frame": 1}
+    # FFN (src/dsvt-ai-trt.cpp:494-529) on the FP32-accurate tcgen05 linear kernel
+    fc1, fc2 = w.ffn[0]
+    us = timed(lambda: fc1.rows(f.src, Vt, activation=1, out=f.gelu_out, zero_tails=0))
+    res["ffn_linear1_gelu"] = {"us": us, "flops": 2 * C * Fc * V, "bytes": 4 * V * (C + Fc), "calls_per_frame": 8, "scope": "next#4"}
+    us = timed(lambda: fc2.rows_splitk(f.gelu_out, Vt, add=f.src, out=f.ffn_parts))
+    res["ffn_linear2_splitk"] = {"us": us, "flops": 2 * C * Fc * V, "bytes": 4 * V * (Fc + C + 2 * C), "calls_per_frame": 8,
+                                 "scope": "next#4"}
     pipeline_prec = f.precision in (capi.DSVT_ATTN_FP32_TC, capi.DSVT_ATTN_FP16_GEMM)
     lib = capi._lib()
     # kernels are timed ALONE here: the attention GEMMs get every SM (the throughput runs above use half per launch)
@@ -273,8 +314,8 @@ def plugin_breakdown(slot, cfg, peaks, reps=3):
     for i in (0, 1):
         gs = f.gs[i]
         plan = f.plans.get((i, 0)) if getattr(f, "plans", None) else None
-        call = lambda: capi.set_attention_fused(w.attn[i], f.x0, f.pos[i][0], gs.global_index_in_set[0],
-                                                gs.mask_expand_0[0], gs.set_num, f.vox.pillar_num, axis=0,
+        call = lambda: capi.set_attention_fused(w.attn[i], x, f.pos_out[i][0], gs.global_index_in_set[0],
+                                                gs.mask_expand_0[0], gs.set_num, Vt, axis=0,
                                                 out=f.attn_out, precision=f.precision, workspace=f.attn_ws, plan=plan)
         us = timed(call)
         if plan is not None:      # one plan per (partition, axis) serves two layers: 4 plan builds per frame
@@ -307,22 +348,6 @@ def plugin_breakdown(slot, cfg, peaks, reps=3):
                                   "flops": None},
                     "out_proj_gemm": {"us": round(c, 2), "flops": 2 * C * C * V, "mma_flops_issued": split * 2 * C * C * V,
                                       "bytes": 4 * V * 2 * C + 2 * split * 2 * C * C}}
-    # next #4 (not part of the frame): the FFN's two linear layers (src/dsvt-ai-trt.cpp:494-529) on the FP32-accurate
-    # tensor-core GEMM, with the GeluPlugin fused into the first one's epilogue
-    if pipeline_prec:
-        rng = np.random.default_rng(5)
-        l1 = capi.Linear((rng.standard_normal((Fc, C)) * 0.06).astype(np.float32), (rng.standard_normal(Fc) * 0.02).astype(np.float32),
-                         precision=f.precision)
-        l2 = capi.Linear((rng.standard_normal((C, Fc)) * 0.06).astype(np.float32), (rng.standard_normal(C) * 0.02).astype(np.float32),
-                         precision=f.precision)
-        hid = torch.empty(cfg.max_pillars_num, Fc, device="cuda")
-        us1 = timed(lambda: l1.rows(f.src, f.vox.pillar_num, activation=1, out=hid))
-        us2 = timed(lambda: l2.rows(hid, f.vox.pillar_num, out=f.src_b))
-        res["ffn_linear1_gelu"] = {"us": us1, "flops": 2 * C * Fc * V, "bytes": 4 * V * (C + Fc), "calls_per_frame": 0,
-                                   "scope": "next#4: TensorRT FullyConnected 192->384 + GeluPlugin in one kernel; not in the frame"}
-        res["ffn_linear2"] = {"us": us2, "flops": 2 * C * Fc * V, "bytes": 4 * V * (C + Fc) + 4 * V * C, "calls_per_frame": 0,
-                              "scope": "next#4: TensorRT FullyConnected 384->192 (two 192-wide K blocks); not in the frame"}
-        del l1, l2, hid
     lib.dsvt_debug_set_gemm_sm_fraction(prev_frac)
     for k, r in res.items():
         if r.get("bytes"):
@@ -399,6 +424,103 @@ def main():
     return 0
 
 
+def workload_config(args, cfg, world, F, S):
+    """The `config` object -- byte-identical in both arms (`--impl ours` / `--impl reference`)."""
+    return {"workload": f"BASELINE.json configs[1]: {args.points}-pt synthetic ring-lidar clouds (SURVEY 8(d) generator, seed = "
+                        f"global frame id), pillar {cfg.voxel_x:g}x{cfg.voxel_y:g} (grid {cfg.grid_x}), 4 DSVT blocks, set="
+                        f"{cfg.voxel_num_set}, FP32; '3-D backbone frame' of SURVEY 8(d): voxeliser -> PFN -> scatter-max -> window "
+                        "partition -> getSet -> 8 x (set attention, FFN, LayerNorms, position embedding) -> BEV map, + filterBoxByScore "
+                        "on synthetic head candidates; the 2-D BEV backbone + CenterHead are NOT executed",
+            "points_per_frame": args.points, "frames_per_step_per_gpu": F, "streams_per_gpu": S,
+            "capacities": {"max_points": cfg.max_points_num, "max_pillars": cfg.max_pillars_num, "max_sets": cfg.max_win_num},
+            "parallelism": f"frame-parallel x{world} (frame f -> rank f mod N)",
+            "l2": "no explicit flush: each step touches F frames x ~0.6 GB of distinct buffers >> 126 MB L2"}
+
+
+def timed_leg(slots, streams, args, world, host_too=True):
+    """warm-up + K timed steps, device-resident and (optionally) through host buffers; max over ranks -> (dev_ms, e2e_ms)."""
+    run_steps(slots, streams, args.warmup, host=False)
+    barrier(world)
+    dev_ms = run_steps(slots, streams, args.steps, host=False)
+    barrier(world)
+    dev_ms = max_over_ranks(dev_ms, world)
+    e2e_ms = None
+    if host_too:
+        run_steps(slots, streams, max(1, args.warmup), host=True)
+        barrier(world)
+        e2e_ms = run_steps(slots, streams, args.steps, host=True)
+        barrier(world)
+        e2e_ms = max_over_ranks(e2e_ms, world)
+    return dev_ms, e2e_ms
+
+
+def config4_leg(args, cfg, world, rank, make_frame_slot, n_frames=64, points=180000):
+    """BASELINE.json configs[3] as written: 64 frames x 180k points, frame f -> rank f mod N, ONE FRAME PER STREAM, the
+    results gathered with NCCL -- all inside the timed region (H2D of every cloud, the frames, D2D packing of the
+    [500,9] boxes + counts = 18 004 B per frame, one batched gather to rank 0).  Strong scaling: 64 frames in total."""
+    import torch
+    pkg = importlib.import_module("dsvt-ai-trt_b200")
+    sharding = importlib.import_module("dsvt-ai-trt_b200.sharding")
+    ids = sharding.frames_for_rank(n_frames, rank, world)
+    streams = [torch.cuda.Stream() for _ in ids]
+    slots = [make_frame_slot(pkg.synth.ring_lidar(points, seed=f), f).capture(st) for f, st in zip(ids, streams)]
+    K = cfg.max_top_k
+    packed = torch.empty(len(slots), K * 9 + 1, device="cuda")          # per frame: 500 x 9 f32 boxes + the count (as bits)
+    main = torch.cuda.current_stream()
+
+    def one_pass():
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record(main)
+        for i, (s, st) in enumerate(zip(slots, streams)):
+            st.wait_event(start)
+            with torch.cuda.stream(st):
+                s.frame.points[0, : s.n].copy_(s.host_points, non_blocking=True)
+                s.frame.points_size.copy_(s.host_n, non_blocking=True)
+                s.graph.replay()
+                packed[i, : K * 9].copy_(s.frame.boxes[0].reshape(-1), non_blocking=True)
+                packed[i, K * 9:].copy_(s.frame.valid.view(torch.float32), non_blocking=True)
+            main.wait_stream(st)
+        gathered = sharding.gather_packed(packed, dst=0)                 # NCCL gather (identity at N = 1)
+        end.record(main)
+        end.synchronize()
+        return start.elapsed_time(end), gathered
+
+    for _ in range(max(1, args.warmup)):
+        one_pass()
+    barrier(world)
+    total, gathered = 0.0, None
+    for _ in range(args.steps):
+        ms, gathered = one_pass()
+        total += ms
+    barrier(world)
+    total = max_over_ranks(total, world)
+    boxes_kept = None
+    if gathered is not None:
+        boxes_kept = int(gathered[:, K * 9].contiguous().view(torch.int32).sum())
+    del slots
+    torch.cuda.empty_cache()
+    return {"value": round(n_frames * args.steps / (total * 1e-3), 2), "unit": UNIT, "scaling": "strong",
+            "ms_per_pass": round(total / args.steps, 3), "frames": n_frames, "points_per_frame": points,
+            "frames_this_rank": len(ids), "streams_this_rank": len(ids),
+            "gather": {"backend": "nccl" if world > 1 else "none (1 rank)", "bytes_per_frame": (K * 9 + 1) * 4,
+                       "inside_timed_region": True},
+            "h2d_bytes_per_pass": n_frames * (points * 16 + 4), "boxes_gathered": boxes_kept,
+            "workload": "BASELINE.json configs[3]: 64 synthetic Waymo-shape frames (180k points each, seeds 0-63), one frame per "
+                        "stream, frame f -> rank f mod N, NCCL gather of the boxes; same frame kind as the headline"}
+
+
+def load_ncu_traffic():
+    """DRAM bytes per launch of the profiled kernels: profiles/ncu_traffic.json, written by tools/ncu_traffic.py from a
+    committed `ncu --set full` capture of this bench's frame."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return {}
+    try:
+        return json.load(open(path))
+    except Exception:
+        return {}
+
+
 def _main():
     args = parse()
     # throughput setting of the attention GEMMs: half the SMs per launch (each CTA amortises its resident weight image
@@ -413,154 +535,71 @@ def _main():
     pkg = importlib.import_module("dsvt-ai-trt_b200")
     capi = importlib.import_module("dsvt-ai-trt_b200.capi")
     pipeline = importlib.import_module("dsvt-ai-trt_b200.pipeline")
+    sharding = importlib.import_module("dsvt-ai-trt_b200.sharding")
     cfg = pkg.config.WAYMO
     peaks = load_peaks()
-    # "fp32" = the FP32 configuration (attention tolerance 2e-5 vs the oracle): FP32-accurate split-FP16 tcgen05 GEMM
-    # pipeline; "fp32_cuda" = the same tolerance on the CUDA-core kernel (the exact-arithmetic yard-stick)
+    # "fp32" = the FP32 configuration (attention tolerance 2e-5 vs the oracle) on the tensor-core path;
+    # "fp32_cuda" = the same tolerance on the CUDA-core kernel (the exact-arithmetic yard-stick)
     precision = {"fp32": capi.DSVT_ATTN_FP32_TC, "fp32_cuda": capi.DSVT_ATTN_FP32, "fp32_tc": capi.DSVT_ATTN_FP32_TC,
-                 "tf32": capi.DSVT_ATTN_TF32, "fp16": capi.DSVT_ATTN_FP16, "fp16_gemm": capi.DSVT_ATTN_FP16_GEMM}[args.precision]
+                 "fp16": capi.DSVT_ATTN_FP16, "fp16_gemm": capi.DSVT_ATTN_FP16_GEMM}[args.precision]
 
     F, S = args.frames_per_step, max(1, min(args.streams, args.frames_per_step))
     weights = pipeline.FrameWeights(cfg, seed=0)
     streams = [torch.cuda.Stream() for _ in range(S)]
-    slots = []
-    sharding = importlib.import_module("dsvt-ai-trt_b200.sharding")
-    for i in range(F):
-        seed = sharding.global_frame_id(rank, world, i)   # frame f -> rank f mod N (weak scaling: F frames per rank)
-        cloud = pkg.synth.ring_lidar(args.points, seed=seed)
-        slot = Slot(pipeline, cfg, weights, precision, cloud, seed)
-        slot.capture(streams[i % S])
-        slots.append(slot)
+    clouds = [pkg.synth.ring_lidar(args.points, seed=sharding.global_frame_id(rank, world, i)) for i in range(F)]
+
+    def make_slots(kind, prec, base=None):
+        out = []
+        for i in range(F):
+            s = Slot(pipeline, cfg, weights, prec, clouds[i], sharding.global_frame_id(rank, world, i), kind=kind,
+                     share=base[i] if base else None)
+            out.append(s.capture(streams[i % S]))
+        torch.cuda.synchronize()
+        return out
+
+    slots = make_slots("backbone3d", precision)
     launches_per_frame = slots[0].frame.launches_per_frame
-    torch.cuda.synchronize()
 
     sampler = ClockSampler(local) if rank == 0 else None
-    # ---- device-resident leg -----------------------------------------------------------------
-    run_steps(slots, streams, args.warmup, host=False)
-    barrier(world)
     if sampler:
         sampler.start()
-    dev_ms = run_steps(slots, streams, args.steps, host=False)
-    barrier(world)
-    dev_ms = max_over_ranks(dev_ms, world)
-    # ---- end-to-end leg (host buffers) ---------------------------------------------------------
-    run_steps(slots, streams, max(1, args.warmup), host=True)
-    barrier(world)
-    e2e_ms = run_steps(slots, streams, args.steps, host=True)
-    barrier(world)
-    e2e_ms = max_over_ranks(e2e_ms, world)
+    dev_ms, e2e_ms = timed_leg(slots, streams, args, world)
     clocks = sampler.finish() if sampler else None
 
-    # gather the results of the last step on rank 0 (the "trivial NCCL result gather")
+    # the "trivial NCCL result gather" of SURVEY 8(e) for the last step (the timed form is the config4 leg)
     boxes = torch.stack([s.frame.boxes[0] for s in slots])
     valid = torch.cat([s.frame.valid for s in slots])
     gathered = sharding.gather_results(boxes, valid, dst=0)
 
-    # ---- BASELINE.json configs[2]: same frames, FP16 tensor-core set attention (tolerance 1e-2) ----------------
-    # two implementations are timed: the single fused kernel (projections, QK^T and PV all on tcgen05) and the GEMM
-    # pipeline with single FP16 operands (projections on tcgen05, QK^T / PV in FP32 on CUDA cores)
-    fp16_cfg = None
-    if args.precision == "fp32" and not args.no_fp16_config:
-        fp16_cfg = {"unit": UNIT, "dtype": "f16 operands / f32 accumulate",
-                    "workload": "BASELINE.json configs[2]: same frames, set attention with FP16 tensor-core operands, tolerance 1e-2"}
-        for name, prec in (("fused_tcgen05_kernel", capi.DSVT_ATTN_FP16), ("gemm_pipeline", capi.DSVT_ATTN_FP16_GEMM)):
-            slots16 = []
-            for i, s in enumerate(slots):
-                fr = pipeline.HotPathFrame(cfg, weights, precision=prec, seed=sharding.global_frame_id(rank, world, i))
-                s16 = Slot.__new__(Slot)
-                s16.frame, s16.n = fr, s.n
-                s16.host_points, s16.host_n, s16.host_boxes, s16.host_valid = s.host_points, s.host_n, s.host_boxes, s.host_valid
-                fr.points.copy_(s.frame.points)
-                fr.points_size.copy_(s.frame.points_size)
-                s16.graph = None
-                s16.capture(streams[i % S])
-                slots16.append(s16)
-            run_steps(slots16, streams, args.warmup, host=False)
-            barrier(world)
-            ms16 = max_over_ranks(run_steps(slots16, streams, args.steps, host=False), world)
-            run_steps(slots16, streams, 1, host=True)
-            barrier(world)
-            e2e16 = max_over_ranks(run_steps(slots16, streams, args.steps, host=True), world)
-            barrier(world)
-            leg = {"value": round(F * world * args.steps / (ms16 * 1e-3), 2), "e2e": round(F * world * args.steps / (e2e16 * 1e-3), 2)}
-            if rank == 0:
-                pl16, us16, _ = plugin_breakdown(slots16[0], cfg, peaks)
-                leg["set_attention"] = {k: v for k, v in pl16.items() if k.startswith("set_attention")}
-                leg["frame_us_sum_of_plugins"] = round(us16, 1)
-            fp16_cfg[name] = leg
-            del slots16
-        best = max(("fused_tcgen05_kernel", "gemm_pipeline"), key=lambda k: fp16_cfg[k]["value"])
-        fp16_cfg["value"], fp16_cfg["e2e"], fp16_cfg["best"] = fp16_cfg[best]["value"], fp16_cfg[best]["e2e"], best
-
-    # ---- the same frames with the FFN linears executed (every DSVT block a real data flow) ----------
-    ffn_cfg = None
-    if args.precision == "fp32" and not args.no_ffn_leg:
-        ffn_cfg = {"unit": UNIT,
-                   "workload": "same frames and plugins + the 16 FFN linears (192->384, 384->192 per encoder layer, "
-                               "src/dsvt-ai-trt.cpp:494-529) on the FP32-accurate tcgen05 linear kernel; PFN / pos-embed MLPs, "
-                               "BEV backbone and head still not executed"}
-        for name in ("graph", "fused", "backbone3d", "backbone3d_fused"):
-            slots_f = []
-            for i, s in enumerate(slots):
-                fr = pipeline.HotPathFrame(cfg, weights, precision=precision, seed=sharding.global_frame_id(rank, world, i),
-                                           ffn={"backbone3d": "graph", "backbone3d_fused": "fused"}.get(name, name),
-                                           backbone=name.startswith("backbone3d"))
-                sf = Slot.__new__(Slot)
-                sf.frame, sf.n = fr, s.n
-                sf.host_points, sf.host_n, sf.host_boxes, sf.host_valid = s.host_points, s.host_n, s.host_boxes, s.host_valid
-                fr.points.copy_(s.frame.points)
-                fr.points_size.copy_(s.frame.points_size)
-                sf.graph = None
-                sf.capture(streams[i % S])
-                slots_f.append(sf)
-            run_steps(slots_f, streams, args.warmup, host=False)
-            barrier(world)
-            ms_f = max_over_ranks(run_steps(slots_f, streams, args.steps, host=False), world)
-            run_steps(slots_f, streams, 1, host=True)
-            barrier(world)
-            e2e_f = max_over_ranks(run_steps(slots_f, streams, args.steps, host=True), world)
-            barrier(world)
-            ffn_cfg[name] = {"value": round(F * world * args.steps / (ms_f * 1e-3), 2),
-                             "e2e": round(F * world * args.steps / (e2e_f * 1e-3), 2),
-                             "launches_per_frame": int(slots_f[0].frame.launches_per_frame),
-                             "form": {"graph": "FC -> GeluPlugin -> FC (the reference graph's nodes)",
-                                      "fused": "FC with GELU epilogue -> split-K FC with the residual add in its epilogue (GeluPlugin and "
-                                               "the kSUM behind the FFN folded into the linears)",
-                                      "backbone3d_fused": "backbone3d with the 'fused' FFN form",
-                                      "backbone3d": "EVERY layer of the reference's 3-D backbone, raw points -> BEV map, as one data "
-                                                    "flow: 'graph' + PFN layers 0 / 1 (Linear+BN+ReLU) and the 8 position-embedding "
-                                                    "MLPs (src/dsvt-ai-trt.cpp:571-1128); only the 2-D BEV backbone + head and the "
-                                                    "post-process graph in front of filterBoxByScore are not executed"}[name]}
-            del slots_f
+    def leg(kind, prec, note):
+        ls = make_slots(kind, prec, base=slots)
+        d, e = timed_leg(ls, streams, args, world)
+        out = {"value": round(F * world * args.steps / (d * 1e-3), 2), "e2e": round(F * world * args.steps / (e * 1e-3), 2),
+               "unit": UNIT, "launches_per_frame": int(ls[0].frame.launches_per_frame), "note": note}
+        del ls
         torch.cuda.empty_cache()
+        return out
 
-    # ---- what the zero-filled tails cost: the same frames with zero_tails = 0 (NOT the reference's contract) ----------
-    relaxed = None
-    if args.precision == "fp32" and not args.no_relaxed_leg:
-        slots_r = []
-        for i, s in enumerate(slots):
-            fr = pipeline.HotPathFrame(cfg, weights, precision=precision, seed=sharding.global_frame_id(rank, world, i),
-                                       zero_tails=0)
-            sr = Slot.__new__(Slot)
-            sr.frame, sr.n = fr, s.n
-            sr.host_points, sr.host_n, sr.host_boxes, sr.host_valid = s.host_points, s.host_n, s.host_boxes, s.host_valid
-            fr.points.copy_(s.frame.points)
-            fr.points_size.copy_(s.frame.points_size)
-            sr.graph = None
-            sr.capture(streams[i % S])
-            slots_r.append(sr)
-        run_steps(slots_r, streams, args.warmup, host=False)
-        barrier(world)
-        ms_r = max_over_ranks(run_steps(slots_r, streams, args.steps, host=False), world)
-        barrier(world)
-        relaxed = {"value": round(F * world * args.steps / (ms_r * 1e-3), 2), "unit": UNIT,
-                   "note": "NOT the headline and NOT the reference's contract: every plugin launched with zero_tails = 0, i.e. "
-                           "rows beyond the valid counts are left untouched instead of zero-filled (the reference memsets every "
-                           "output per enqueue; no consumer in the graph reads those rows). The difference to `value` is "
-                           "what the contract's zero tails cost at capacities 320000 / 40000 / 4096 (16.5 k of 40 k pillar "
-                           "rows valid); the dense BEV map is still cleared"}
-        del slots_r
+    legs = {}
+    if not args.no_legs and args.precision == "fp32":
+        legs["plugin_only"] = leg("plugin_only", precision,
+                                  "round 1's headline frame: the reference's ten plugins + the fused set attention; the TensorRT-"
+                                  "native layers (PFN, position embedding, FFN linears) are NOT executed, fixed tensors stand in")
+        legs["backbone3d_graph"] = leg("backbone3d_graph", precision,
+                                       "the headline's data flow in the reference graph's node structure: FC -> GeluPlugin -> FC "
+                                       "(the headline folds the GELU and the residual add into the linears' epilogues)")
+        legs["fp16_config"] = leg("backbone3d", capi.DSVT_ATTN_FP16,
+                                  "BASELINE.json configs[2]: same frames, set attention on the single fused FP16 tcgen05 kernel "
+                                  "(QK^T / PV on tensor cores, FP32 accumulate), tolerance 1e-2")
+        legs["relaxed_tails"] = leg("relaxed_tails", precision,
+                                    "NOT the reference's contract: every plugin launched with zero_tails = 0 (rows beyond the "
+                                    "valid counts left untouched; no consumer reads them) -- what the contract's zero tails cost")
+    cfg4 = None
+    if not args.no_legs and not args.no_config4 and args.precision == "fp32":
+        del slots[1:]                    # frame 0's slot stays for the breakdown; the leg needs the memory of 64 slots at N = 1
         torch.cuda.empty_cache()
+        cfg4 = config4_leg(args, cfg, world, rank,
+                           lambda cloud, f: Slot(pipeline, cfg, weights, precision, cloud, f, kind="backbone3d"))
 
     if rank != 0:
         return None
@@ -568,17 +607,54 @@ def _main():
     value = frames / (dev_ms * 1e-3)
     e2e = frames / (e2e_ms * 1e-3)
     plugins, frame_us, stats = plugin_breakdown(slots[0], cfg, peaks)
-    # per-KERNEL view: a plugin that is one kernel counts as such; the GEMM-pipeline attention contributes its three kernels
+    roof = roofline_block(plugins, frame_us, peaks)
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision.startswith("fp32") else args.precision,
+        "dtype_note": {"fp32": "plugin I/O and all non-GEMM arithmetic FP32; projections / linears on tcgen05 with FP16 hi+lo split "
+                               "operands (3 MMAs per product, FP32 accumulate in TMEM) held to the FP32 tolerance (2e-5 vs the oracle)",
+                       "fp32_cuda": "all arithmetic on the FP32 CUDA cores"}.get(args.precision),
+        "data": "synthetic",
+        "config": workload_config(args, cfg, world, F, S),
+        "frame_kind": "backbone3d (every layer of the reference's 3-D backbone as one data flow, src/dsvt-ai-trt.cpp:571-1128)",
+        "frame_stats": stats,
+        "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": world * F * (args.points * 16 + 4),
+                "d2h_bytes_per_step": world * F * (cfg.max_top_k * 9 * 4 + 4), "ms_per_step": round(e2e_ms / args.steps, 4),
+                "bytes_note": "whole job: all ranks' pinned-host clouds in, boxes + counts out, per step"},
+        "gpu_launches": int(launches_per_frame * F * args.steps * 2),
+        "launches_per_frame": int(launches_per_frame),
+        "gemm_sm_fraction_pct": int(os.environ.get("DSVT_GEMM_SM_FRACTION", "100")),
+        "clocks": clocks,
+        "roofline": roof,
+        "plugins": plugins,
+        "frame_us_sum_of_plugins": round(frame_us, 1),
+        "legs": legs,
+        "config4_64x180k": cfg4,
+        "gathered_boxes": None if gathered is None else int(gathered[1].sum()),
+    }
+    if not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline(cfg, clouds[0], stats)
+        except Exception as e:   # the checker must never take the bench down
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"failed: {e}"}
+    return line
+
+
+def roofline_block(plugins, frame_us, peaks):
+    """The dominant KERNEL by share of the frame: algorithmic bytes / flops (SURVEY 8(d) figures x units per launch) over
+    its live CUDA-event duration, against MEASURED_PEAKS.json."""
+    # per-KERNEL view: a plugin that is one kernel counts as such; the GEMM-pipeline attention contributes its kernels
     kernels = {}
     for k, r in plugins.items():
         if not r["calls_per_frame"]:
             continue
-        if "kernels" in r:      # the attention pipeline's kernels: the two window partitions run the SAME kernels
+        if "kernels" in r:      # the two window partitions run the SAME kernels: call-weighted mean
             for kn, kr in r["kernels"].items():
                 a = kernels.setdefault(f"set_attention.{kn}", {"us": 0.0, "calls_per_frame": 0, "bytes": 0, "flops": 0,
                                                                "mma_flops_issued": 0})
                 c = r["calls_per_frame"]
-                a["us"] = (a["us"] * a["calls_per_frame"] + kr["us"] * c) / (a["calls_per_frame"] + c)   # call-weighted mean
+                a["us"] = (a["us"] * a["calls_per_frame"] + kr["us"] * c) / (a["calls_per_frame"] + c)
                 for f_ in ("bytes", "flops", "mma_flops_issued"):
                     a[f_] = (a[f_] * a["calls_per_frame"] + (kr.get(f_) or 0) * c) / (a["calls_per_frame"] + c)
                 a["calls_per_frame"] += c
@@ -592,77 +668,39 @@ def _main():
     issued = dom.get("mma_flops_issued") or dom.get("flops") or 0
     intensity = issued / dom["bytes"] if dom.get("bytes") else float("inf")
     if dom.get("flops") and intensity >= ridge:
-        tf = dom["flops"] / dom["us"] * 1e-6
+        tf = (dom.get("mma_flops_issued") or dom["flops"]) / dom["us"] * 1e-6
         roof = {"kernel": dom_key, "bound": "tensor", "achieved": round(tf, 3), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": round(tf / peaks["bf16_tflops"], 5), "traffic": None}
+                "frac": round(tf / peaks["bf16_tflops"], 5)}
     else:
         gbs = dom["bytes"] / dom["us"] * 1e-3
         roof = {"kernel": dom_key, "bound": "hbm", "achieved": round(gbs, 2), "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": round(gbs / peaks["hbm_gbs"], 5), "traffic": None}
+                "unit": "GB/s", "frac": round(gbs / peaks["hbm_gbs"], 5)}
     if dom.get("flops"):
         roof["flop_per_byte"] = round(intensity, 1)
         roof["ridge_flop_per_byte"] = round(ridge, 1)
         roof["algorithmic_tflops"] = round(dom["flops"] / dom["us"] * 1e-6, 2)
         if dom.get("mma_flops_issued"):
             roof["mma_tflops_issued"] = round(dom["mma_flops_issued"] / dom["us"] * 1e-6, 2)
-            roof["note"] = ("a [rows,192]x[192,192] projection GEMM sits left of the ridge even with the three FP16 MMAs per "
-                            "product of the FP32-accurate mode (hi*hi + hi*lo + lo*hi): it is bound by its row / weight / "
-                            "output traffic, so the fraction is quoted against the HBM roof")
-    roof["peak_source"] = peaks["source"] + (" burst cuBLAS bf16 / copy bandwidth (MEASURED_PEAKS.json)")
-    # DRAM traffic per launch of the attention kernels from the committed ncu --set full capture (cold caches: ncu
-    # flushes between kernels, so the intermediates that live in L2 in a real step are counted as DRAM reads there)
-    ncu_traffic = {"qkv_proj_gemm": 26.6e6, "attn_core": 40.0e6, "out_proj_gemm": 12.9e6}
-    roof["traffic"] = ncu_traffic.get(dom_key.split(".")[-1])
-    roof["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_attention_split_v3.txt"
-                              if roof["traffic"] else None)
+    roof["peak_source"] = peaks["source"] + " (burst cuBLAS bf16 / copy bandwidth, MEASURED_PEAKS.json)"
+    t = load_ncu_traffic().get(dom_key)
+    roof["traffic"] = t.get("dram_bytes_per_launch") if t else None
+    roof["traffic_source"] = t.get("source") if t else None
     roof["algorithmic_bytes"] = dom.get("bytes")
-    roof["us"] = dom["us"]
+    roof["us"] = round(dom["us"], 2)
     roof["share_of_frame"] = round(dom["us"] * dom["calls_per_frame"] / frame_us, 3)
-    roof["timing"] = ("CUDA events (recorded inside the library between the pipeline's kernels), L2 flushed before the call, "
-                      "instrumented pass on the bench's frame 0")
-    attn_us = sum(plugins[k]["us"] * plugins[k]["calls_per_frame"] for k in plugins if k.startswith("set_attention"))
-    attn_flops = sum((plugins[k].get("flops") or 0) * plugins[k]["calls_per_frame"] for k in plugins if k.startswith("set_attention"))
-    roof["set_attention_plugin"] = {"us_per_frame": round(attn_us, 1), "share_of_frame": round(attn_us / frame_us, 3),
-                                    "algorithmic_tflops": round(attn_flops / attn_us * 1e-6, 2) if attn_us else None,
-                                    "frac_of_bf16_peak": round(attn_flops / attn_us * 1e-6 / peaks["bf16_tflops"], 5) if attn_us else None,
-                                    "note": "flops = 11 612 160 x sets (SURVEY 8d: all 36 slots of every set)"}
-    line = {
-        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision.startswith("fp32") else args.precision,
-        "dtype_note": {"fp32": "plugin I/O and all non-GEMM arithmetic FP32; attention projections on tcgen05 with FP16 hi+lo split "
-                               "operands (3 MMAs per product, FP32 accumulate in TMEM) held to the FP32 tolerance (2e-5 vs the oracle)",
-                       "fp32_cuda": "all arithmetic on the FP32 CUDA cores"}.get(args.precision),
-        "data": "synthetic",
-        "config": {"workload": f"BASELINE.json configs[1]: {args.points}-pt synthetic ring-lidar clouds, pillar "
-                               f"{cfg.voxel_x:g}x{cfg.voxel_y:g} (grid {cfg.grid_x}), 4 DSVT blocks, set={cfg.voxel_num_set}, "
-                               f"{args.precision.upper()}; all ten reference plugins (a1..a6 + windowPartition, scatter-max x2, map2bev; gather / scatter "
-                               "fused into the set attention), TensorRT-native glue (PFN / pos-embed / FFN linears, BEV backbone, "
-                               "head) NOT executed",
-                   "frames_per_step_per_gpu": F, "streams_per_gpu": S, "parallelism": f"frame-parallel x{world}",
-                   "gemm_sm_fraction_pct": int(os.environ.get("DSVT_GEMM_SM_FRACTION", "100")),
-                   "frame_stats": stats,
-                   "l2": "no explicit flush: each step touches F frames x ~0.5 GB of distinct buffers >> 126 MB L2"},
-        "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": world * F * (args.points * 16 + 4),
-                "d2h_bytes_per_step": world * F * (cfg.max_top_k * 9 * 4 + 4), "ms_per_step": round(e2e_ms / args.steps, 4),
-                "bytes_note": "whole job: all ranks' pinned-host clouds in, boxes + counts out, per step"},
-        "gpu_launches": int(launches_per_frame * F * args.steps * 2),
-        "launches_per_frame": int(launches_per_frame),
-        "clocks": clocks,
-        "roofline": roof,
-        "plugins": plugins,
-        "frame_us_sum_of_plugins": round(frame_us, 1),
-        "fp16_config": fp16_cfg,
-        "ffn_in_frame": ffn_cfg,
-        "relaxed_tails": relaxed,
-        "gathered_boxes": None if gathered is None else int(gathered[1].sum()),
-    }
-    if not args.no_cpu_baseline:
-        try:
-            line["cpu_baseline"] = cpu_baseline(cfg, pkg.synth.ring_lidar(args.points, seed=0), stats)
-        except Exception as e:   # the checker must never take the bench down
-            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"failed: {e}"}
-    return line
+    roof["timing"] = "CUDA events around the kernel on its launch stream, L2 flushed before each repetition, bench frame 0"
+    attn_us = sum(plugins[k]["us"] * plugins[k]["calls_per_frame"] for k in plugins if k.startswith("set_attention_") and "plan" not in k)
+    attn_flops = sum((plugins[k].get("flops") or 0) * plugins[k]["calls_per_frame"] for k in plugins if k.startswith("set_attention_"))
+    if attn_us:
+        roof["set_attention_plugin"] = {"us_per_frame": round(attn_us, 1), "share_of_frame": round(attn_us / frame_us, 3),
+                                        "algorithmic_tflops": round(attn_flops / attn_us * 1e-6, 2),
+                                        "frac_of_bf16_peak": round(attn_flops / attn_us * 1e-6 / peaks["bf16_tflops"], 5),
+                                        "note": "flops = 11 612 160 x sets (SURVEY 8d: all 36 slots of every set)"}
+    roof["kernels"] = {k: {"us": round(v["us"], 2), "calls_per_frame": v["calls_per_frame"],
+                           "share_of_frame": round(v["us"] * v["calls_per_frame"] / frame_us, 3),
+                           "hbm_frac": round(v["bytes"] / v["us"] * 1e-3 / peaks["hbm_gbs"], 4) if v.get("bytes") else None}
+                       for k, v in kernels.items()}
+    return roof
 
 
 if __name__ == "__main__":

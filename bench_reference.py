@@ -5,11 +5,14 @@ layers.  This arm therefore runs the reference's plugin source
 sm_100a into oracle/_ref/waymo/ (capacities raised through oracle/ref_config_waymo/params.h, the reference's
 own configuration mechanism), through the same TensorRT-style C harness, in the reference's graph order and
 with the reference's tensor plumbing: GetValueByIndex -> MHA -> MapSetFeature2Voxel, separate elementwise
-residual adds, every plugin's own full-capacity memsets.  multHeadAttention() executes inside closed-source
-TensorRT in the reference; it is stood in by torch.nn.functional.multi_head_attention_forward (PyTorch eager,
-FP32, over all max_win_num padded sets exactly like the reference graph).  None of this repo's kernels run on
-this path.  If oracle/_ref is missing or the reference kernels fault, the arm falls back to timing the CPU
-oracle port (kind "port").
+residual adds, every plugin's own full-capacity memsets.  multHeadAttention() and the FullyConnected layers execute
+inside closed-source TensorRT in the reference; they are stood in by PyTorch eager (cuBLAS, TF32 allowed like
+TensorRT's default builder flags; the MHA over all max_win_num padded sets exactly like the reference graph).
+The headline is the same "3-D backbone frame" as the 'ours' arm, on the same clouds, with the same `config` object;
+under torchrun every rank runs its shard (frame f -> rank f mod N).  `plugins` attributes the frame time to the
+reference's own CUDA vs the stand-ins (BASELINE.md B1 protocol: 10 warm-up + 100 timed calls, median).
+None of this repo's kernels run on this path and libdsvt_b200.so is never loaded by it.  If oracle/_ref is missing
+or the reference kernels fault, the arm falls back to timing the CPU oracle port (kind "port").
 """
 import importlib
 import json
@@ -61,6 +64,7 @@ class ReferenceFrame:
         self.points[0, : self.n] = torch.from_numpy(cloud).to(dev)
         self.points_size = torch.tensor([self.n], dtype=torch.int32, device=dev)
         self.host_points = torch.from_numpy(cloud).pin_memory()
+        self.host_n = torch.tensor([self.n], dtype=torch.int32).pin_memory()
         self.host_boxes = torch.empty(cfg.max_top_k, 9).pin_memory()
         self.host_valid = torch.empty(1, dtype=torch.int32).pin_memory()
         g2 = torch.Generator().manual_seed(1)
@@ -69,6 +73,8 @@ class ReferenceFrame:
         self.pos = [[torch.randn(1, mp, C, generator=g).mul_(0.5).to(dev) for _ in range(2)] for _ in range(cfg.num_blocks)]
         self.ffn_hidden = torch.randn(1, mp, F, generator=g).to(dev)
         self.ffn_out = torch.randn(1, mp, C, generator=g).mul_(0.5).to(dev)
+        if backbone:      # computed by the frame itself: keep one tensor of each kind for the per-plugin breakdown only
+            self.pos = [[self.pos[0][0]] * 2] * cfg.num_blocks
         self.attn_w = [((torch.randn(3 * C, C, generator=g) * 0.06).to(dev), (torch.randn(3 * C, generator=g) * 0.02).to(dev),
                         (torch.randn(C, C, generator=g) * 0.06).to(dev), (torch.randn(C, generator=g) * 0.02).to(dev))
                        for _ in range(cfg.num_blocks * 2)]
@@ -173,6 +179,7 @@ class ReferenceFrame:
 
     def enqueue_host(self):
         self.points[0, : self.n].copy_(self.host_points, non_blocking=True)
+        self.points_size.copy_(self.host_n, non_blocking=True)
         self.graph.replay()
         self.host_boxes.copy_(self.boxes[0], non_blocking=True)
         self.host_valid.copy_(self.valid, non_blocking=True)
@@ -189,12 +196,84 @@ def cpu_port_arm(args, cfg, pkg):
     return best
 
 
+def plugin_breakdown(fr, warm=10, reps=100):
+    """every reference plugin (and every stand-in) of ONE frame timed alone on the frame's own tensors --
+    10 warm-up + 100 timed enqueue calls, CUDA events, median; the reference's per-enqueue memsets are part of its enqueue.
+    Attributes the frame time to the reference's own CUDA vs the PyTorch stand-ins (MHA, residual adds, linears)."""
+    torch, Fn, cfg = fr.torch, fr.Fn, fr.cfg
+    fr.run()
+    torch.cuda.synchronize()
+    o = fr.out
+    vo, V = o["vox"], o["vox"][4]
+
+    def timed(fn):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); b.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3)
+        ts.sort()
+        return round(ts[len(ts) // 2], 2)
+
+    res = {}
+    add = lambda name, us, calls, kind: res.__setitem__(name, {"us": us, "calls_per_frame": calls, "kind": kind})
+    add("points2Features", timed(lambda: fr.vox.enqueue([fr.points, fr.points_size], outputs=o["vox"])), 1, "reference CUDA")
+    src = [fr.pfn_out[0] if not fr.backbone else None, None]
+    if fr.backbone:
+        (w0, s0, t0), (w1, s1, t1) = fr.pfn
+        h0 = torch.relu(Fn.linear(vo[0], w0) * s0 + t0)
+        h1 = torch.relu(Fn.linear(torch.cat([h0, o["sm0"][0]], dim=2), w1) * s1 + t1)
+        add("pfn_layers(torch)", timed(lambda: (torch.relu(Fn.linear(vo[0], w0) * s0 + t0),
+                                               torch.relu(Fn.linear(torch.cat([h0, o["sm0"][0]], dim=2), w1) * s1 + t1))), 1,
+            "PyTorch stand-in for TensorRT layers")
+        src = [h0, h1]
+    else:
+        src = fr.pfn_out
+    for k in (0, 1):
+        add(f"torchScatterMax_{cfg.pfn_channels[k]}", timed(lambda: fr.smax[k].enqueue([src[k], vo[1], vo[3], V], outputs=o[f"sm{k}"])),
+            1, "reference CUDA")
+    for i in (0, 1):
+        add(f"windowPartition_{i}", timed(lambda: fr.wp[i].enqueue([vo[2], V], outputs=o[f"wp{i}"])), 1, "reference CUDA")
+        add(f"getSet_{i}", timed(lambda: fr.gs[i].enqueue(o[f"wp{i}"][:4], outputs=o[f"gs{i}"])), 1, "reference CUDA")
+    x = o["sm1"][1] if fr.backbone else fr.x0
+    pos = fr.pos[0][0]
+    for i in (0, 1):
+        gs = o[f"gs{i}"]
+        add(f"getValueByIndex_part{i}", timed(lambda: fr.gather[0].enqueue([x, pos, gs[0], gs[2]], outputs=o["gv0"])), 4, "reference CUDA")
+        q, k, v = o["gv0"]
+        add(f"multHeadAttention_part{i}(torch)", timed(lambda: fr.mha(q, k, v, gs[3], fr.attn_w[0])), 4,
+            "PyTorch stand-in for TensorRT layers")
+        a = fr.mha(q, k, v, gs[3], fr.attn_w[0])
+        add(f"mapSetFeature2voxel_part{i}", timed(lambda: fr.scatter[0].enqueue([a, gs[0], gs[2]], outputs=o["ms0"])), 4, "reference CUDA")
+    y = o["ms0"][0]
+    add("elementwise_sum(torch)", timed(lambda: y + x), 28, "PyTorch stand-in for TensorRT layers")
+    add("layerNorm", timed(lambda: fr.ln[0].enqueue([y, V], outputs=o["ln0"])), 28, "reference CUDA")
+    hid = fr.ffn_hidden
+    if fr.backbone:
+        f1, fb1, f2, fb2 = fr.ffn_w[0]
+        hid = Fn.linear(o["ln0"][0], f1, fb1)
+        add("ffn_linears(torch)", timed(lambda: Fn.linear(Fn.linear(o["ln0"][0], f1, fb1), f2, fb2)), 8, "PyTorch stand-in for TensorRT layers")
+        a_, sc, sh, b2, bias2 = fr.pos_w[0][0]
+        add("pos_embed_mlp(torch)", timed(lambda: Fn.linear(torch.relu(Fn.linear(o["wp0"][5], a_) * sc + sh), b2, bias2)), 8,
+            "PyTorch stand-in for TensorRT layers")
+    add("gelu", timed(lambda: fr.gelu.enqueue([hid, V], outputs=o["ge"])), 8, "reference CUDA")
+    add("map2bev", timed(lambda: fr.m2b.enqueue([y, vo[2], V], outputs=o["m2b"])), 1, "reference CUDA")
+    add("filterBoxByScore", timed(lambda: fr.fb.enqueue(fr.cand, outputs=o["fb"])), 1, "reference CUDA")
+    total = sum(r["us"] * r["calls_per_frame"] for r in res.values())
+    ref_cuda = sum(r["us"] * r["calls_per_frame"] for r in res.values() if r["kind"] == "reference CUDA")
+    return {"protocol": f"{warm} warm-up + {reps} timed calls per plugin, CUDA events, median; one frame's own tensors, no L2 flush",
+            "per_plugin": res, "sum_us_per_frame": round(total, 1),
+            "reference_cuda_us_per_frame": round(ref_cuda, 1), "torch_standins_us_per_frame": round(total - ref_cuda, 1),
+            "reference_cuda_share": round(ref_cuda / total, 3)}
+
+
 def main(args):
-    """Returns the JSON line (a dict) on rank 0, None on the other ranks; bench.main() prints it.  The reference's
-    creators print their fields to stdout (e.g. getSet.cu:829): bench.main() points fd 1 at stderr while this runs."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return None       # rank 0 alone runs the reference arm
+    """Returns the JSON line (a dict) on rank 0, None on the other ranks; bench.main() prints it.  Under torchrun EVERY
+    rank runs its shard of the frames (frame f -> rank f mod N, exactly like the 'ours' arm), so the ratio between the two
+    arms is like-for-like at every N.  The reference's creators print their fields to stdout (e.g. getSet.cu:829):
+    bench.main() points fd 1 at stderr while this runs."""
     return _run(args)
 
 
@@ -202,71 +281,77 @@ def _run(args):
     import torch
     bench = importlib.import_module("bench")
     pkg = importlib.import_module("dsvt-ai-trt_b200")
+    sharding = importlib.import_module("dsvt-ai-trt_b200.sharding")
     cfg = pkg.config.WAYMO
-    line = {"impl": "reference", "metric": bench.METRIC, "unit": bench.UNIT, "n_gpus": 1, "steps": args.steps,
-            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic"}
+    world, rank, local = bench.dist_setup(args)
     F, S = args.frames_per_step, max(1, min(args.streams, args.frames_per_step))
+    line = {"impl": "reference", "metric": bench.METRIC, "unit": bench.UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": bench.workload_config(args, cfg, world, F, S)}
     try:
         if not (torch.cuda.is_available() and os.path.exists(os.path.join(REF_DIR, "libref_getSet.so"))):
             raise RuntimeError("oracle/_ref/waymo not available")
-        torch.cuda.set_device(0)
         plg = importlib.import_module("dsvt-ai-trt_b200.plugins")
+        # TensorRT-native layers (FullyConnected, MatrixMultiply) are stood in by cuBLAS through PyTorch eager with TF32
+        # allowed -- TensorRT's own default (BuilderFlag::kTF32) on this class of GPU -- over the engine's full static shapes
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
         streams = [torch.cuda.Stream() for _ in range(S)]
-        slots = []
-        for i in range(F):
-            fr = ReferenceFrame(plg, cfg, pkg.synth.ring_lidar(args.points, seed=i), i)
-            fr.capture(streams[i % S])
-            slots.append(fr)
-        torch.cuda.synchronize()
-        bench.run_steps(slots, streams, args.warmup, host=False)
-        torch.cuda.synchronize()
-        dev_ms = bench.run_steps(slots, streams, args.steps, host=False)
-        bench.run_steps(slots, streams, max(1, args.warmup), host=True)
-        e2e_ms = bench.run_steps(slots, streams, args.steps, host=True)
-        torch.cuda.synchronize()
-        frames = F * args.steps
+        clouds = [pkg.synth.ring_lidar(args.points, seed=sharding.global_frame_id(rank, world, i)) for i in range(F)]
+
+        def make(backbone):
+            out = []
+            for i in range(F):
+                fr = ReferenceFrame(plg, cfg, clouds[i], sharding.global_frame_id(rank, world, i), backbone=backbone)
+                fr.capture(streams[i % S])
+                out.append(fr)
+            torch.cuda.synchronize()
+            return out
+
+        slots = make(True)
+        dev_ms, e2e_ms = bench.timed_leg(slots, streams, args, world)
+        frames = F * world * args.steps
         value, e2e = frames / (dev_ms * 1e-3), frames / (e2e_ms * 1e-3)
+        breakdown = None
+        if rank == 0 and not getattr(args, "no_breakdown", False):
+            try:
+                breakdown = plugin_breakdown(slots[0])
+            except Exception as exc3:
+                breakdown = {"failed": str(exc3)[:300]}
+        bench.barrier(world)
+        legs = {}
+        if not getattr(args, "no_legs", False):
+            del slots
+            torch.cuda.empty_cache()
+            slots_p = make(False)
+            d, e = bench.timed_leg(slots_p, streams, args, world)
+            legs["plugin_only"] = {"value": round(frames / (d * 1e-3), 3), "e2e": round(frames / (e * 1e-3), 3), "unit": bench.UNIT,
+                                   "note": "round 1's headline frame: reference plugins + the MHA stand-in; PFN / position-embedding "
+                                           "/ FFN linears NOT executed (fixed tensors stand in)"}
+        if rank != 0:
+            return None
         line.update({
             "value": round(value, 3), "ms_per_step": round(dev_ms / args.steps, 3),
-            "config": {"workload": f"same plugin sequence and clouds as the 'ours' arm ({args.points}-pt ring-lidar, "
-                                   f"capacities {cfg.max_points_num}/{cfg.max_pillars_num}/{cfg.max_win_num}); reference "
-                                   "plugin sources compiled unmodified for sm_100a (oracle/_ref/waymo), MHA stood in by "
-                                   "PyTorch eager over all padded sets, residual adds by torch, CUDA-graph replay",
-                       "frames_per_step_per_gpu": F, "streams_per_gpu": S},
+            "frame_kind": "backbone3d (every layer of the reference's 3-D backbone as one data flow, src/dsvt-ai-trt.cpp:571-1128)",
+            "impl_note": "the reference's plugin sources compiled UNMODIFIED for sm_100a (oracle/_ref/waymo, capacities raised "
+                         "through the reference's own params.h), in the reference's graph order with its tensor plumbing "
+                         "(GetValueByIndex -> MHA -> MapSetFeature2Voxel, separate residual adds, every plugin's full-capacity "
+                         "memsets); TensorRT-native layers (multHeadAttention over all padded sets, PFN / position-embedding / "
+                         "FFN FullyConnected layers) stood in by PyTorch eager / cuBLAS with TF32 allowed; CUDA-graph replay",
             "cpu_baseline": {"value": round(value, 3), "unit": bench.UNIT, "cores": 0, "kind": "reference",
                              "sample": "the reference's own CUDA kernels on the B200 (it has no CPU compute path); "
                                        "host cores only launch"},
-            "e2e": {"value": round(e2e, 3), "unit": bench.UNIT, "h2d_bytes_per_step": F * args.points * 16,
-                    "d2h_bytes_per_step": F * (cfg.max_top_k * 36 + 4)},
+            "e2e": {"value": round(e2e, 3), "unit": bench.UNIT, "h2d_bytes_per_step": world * F * (args.points * 16 + 4),
+                    "d2h_bytes_per_step": world * F * (cfg.max_top_k * 36 + 4), "ms_per_step": round(e2e_ms / args.steps, 3)},
+            "plugins": breakdown, "legs": legs,
         })
-        if not getattr(args, "no_ffn_leg", False):
-            # the complete 3-D backbone (our arm's ffn_in_frame.backbone3d): + PFN, position-embedding and FFN linears as
-            # PyTorch eager / cuBLAS with TF32 allowed (TensorRT's default on this class of GPU), full static shapes
-            try:
-                del slots
-                torch.cuda.empty_cache()
-                torch.backends.cuda.matmul.allow_tf32 = True
-                slots_b = []
-                for i in range(F):
-                    fr = ReferenceFrame(plg, cfg, pkg.synth.ring_lidar(args.points, seed=i), i, backbone=True)
-                    fr.capture(streams[i % S])
-                    slots_b.append(fr)
-                torch.cuda.synchronize()
-                bench.run_steps(slots_b, streams, args.warmup, host=False)
-                ms_b = bench.run_steps(slots_b, streams, args.steps, host=False)
-                line["backbone3d"] = {"value": round(frames / (ms_b * 1e-3), 3), "unit": bench.UNIT,
-                                      "note": "reference plugins + PyTorch-eager (cuBLAS, TF32 allowed) stand-ins for every "
-                                              "TensorRT-native layer of the 3-D backbone, over the engine's full static shapes; TF32 also "
-                                              "speeds up the MHA stand-in, which is why this leg can beat the FP32 plugin-only frame"}
-            except Exception as exc2:
-                line["backbone3d"] = {"value": None, "note": f"failed: {str(exc2)[:200]}"}
     except Exception as exc:     # reference kernels unavailable / faulted -> CPU oracle port
+        if rank != 0:
+            return None
         cb = cpu_port_arm(args, cfg, pkg)
         line.update({
             "value": round(cb["value"], 5), "ms_per_step": round(1e3 / cb["value"], 1),
-            "config": {"workload": f"CPU oracle port, 1 frame of {args.points} pts per step (bounded sample, see cpu_baseline)",
-                       "fallback_reason": str(exc)[:200]},
+            "impl_note": "FALLBACK: CPU oracle port, 1 frame per step (bounded sample, see cpu_baseline): " + str(exc)[:200],
             "cpu_baseline": cb,
             "e2e": {"value": round(cb["value"], 5), "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         })

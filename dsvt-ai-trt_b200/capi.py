@@ -10,7 +10,8 @@ import torch
 
 from ._lib import load_library
 
-DSVT_ATTN_FP32, DSVT_ATTN_TF32, DSVT_ATTN_FP16, DSVT_ATTN_FP32_TC, DSVT_ATTN_FP16_GEMM = 0, 1, 2, 3, 4
+DSVT_ATTN_FP32, DSVT_ATTN_FP16, DSVT_ATTN_FP32_TC, DSVT_ATTN_FP16_GEMM = 0, 2, 3, 4
+DSVT_LINEAR_TF32 = 1          # dense linear layers only (tc_linear.cu)
 
 
 class P2FParams(Structure):
@@ -387,7 +388,7 @@ def map_set_feature2voxel(feat, global_index_in_set, set_num, axis, max_pillars,
 class Linear:
     """y = x W^T + b on the tensor cores (tcgen05); W [N,K] float32 host array."""
 
-    def __init__(self, W, b=None, precision=DSVT_ATTN_TF32):
+    def __init__(self, W, b=None, precision=DSVT_LINEAR_TF32):
         import numpy as np
         W = np.ascontiguousarray(W, dtype=np.float32)
         self.N, self.K = W.shape

@@ -114,12 +114,7 @@ static int attn_dispatch(const dsvt_set_attention_params* p, const dsvt_attentio
                                "(dsvt_set_attention_fused_launch) only");
                 return DSVT_ERR_UNSUPPORTED;
             }
-            {
-                // DSVT_TC_SERIAL=1 selects the first-generation (phase-serial) kernel, kept for A/B measurements
-                static const bool serial = [] { const char* e = getenv("DSVT_TC_SERIAL"); return e && e[0] == '1'; }();
-                if (serial) return set_attention_tc_fused(p, w->tc_blob, q, pos, idx, mask, set_num, voxel_num, out, st);
-                return set_attention_tc2_fused(p, w->tc_blob, q, pos, idx, mask, set_num, voxel_num, out, st);
-            }
+            return set_attention_tc2_fused(p, w->tc_blob, q, pos, idx, mask, set_num, voxel_num, out, st);
         default:
             set_last_error("set attention: precision %d is not available in this build", p->precision);
             return DSVT_ERR_UNSUPPORTED;

@@ -10,19 +10,15 @@ struct AttnWeightsDev {
     const float* b_in;      // [3C]
     const float* w_out_t;   // [C][C]
     const float* b_out;     // [C]
-    const void* tc_blob;    // operand images for the tcgen05 path (attention_tc.cu), or nullptr
+    const void* tc_blob;    // operand images for the tcgen05 path (attention_tc2.cu), or nullptr
 };
 
 int set_attention_fp32(const dsvt_set_attention_params* p, const AttnWeightsDev& w, bool fused,
                        const float* q, const float* k, const float* v, const float* pos, const int* idx,
                        const float* mask, const int* set_num, const int* voxel_num, float* out, cudaStream_t st);
 
-// FP16 tensor-core path (attention_tc.cu)
+// FP16 tensor-core path (attention_tc2.cu)
 void* attention_tc_prepare(int C, int H, const float* w_in, const float* b_in, const float* w_out, const float* b_out);
-int set_attention_tc_fused(const dsvt_set_attention_params* p, const void* tc_blob,
-                           const float* x, const float* pos, const int* idx, const float* mask,
-                           const int* set_num, const int* voxel_num, float* out, cudaStream_t st);
-
 int set_attention_tc2_fused(const dsvt_set_attention_params* p, const void* tc_blob,
                             const float* x, const float* pos, const int* idx, const float* mask,
                             const int* set_num, const int* voxel_num, float* out, cudaStream_t st);

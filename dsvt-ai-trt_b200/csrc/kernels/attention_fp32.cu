@@ -373,12 +373,7 @@ int launch_fp32(const dsvt_set_attention_params* p, const AttnWeightsDev& w,
 {
     // (one CTA per SM with half of the SM left to L1 for the weight stream was measured 40 % slower)
     const size_t smem = (size_t) AttnSmem<S>::total * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        DSVT_CUDA(cudaFuncSetAttribute(set_attention_fp32_kernel<S, FUSED>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        attr_set = true;
-    }
+    DSVT_RAISE_SMEM((set_attention_fp32_kernel<S, FUSED>), smem);
     constexpr int NS = AttnSmem<S>::NS;
     set_attention_fp32_kernel<S, FUSED><<<dim3((p->max_set_num + NS - 1) / NS, p->batch), kThreadsA, smem, st>>>(
         q, k, v, pos, idx, mask, set_num, voxel_num, out, w, p->max_set_num, p->max_pillars_num, p->axis_id,

@@ -106,6 +106,10 @@ struct GemmRole {
     const float* a0b;       // optional second source of the A operand: columns >= ksplit of the K block come from a0b
     int ksplit, ldb;        //   (the PFN's concatenation [point features | per-pillar max], src/dsvt-ai-trt.cpp:583-587,
                             //   read in place instead of being materialised); ksplit is a multiple of 32, a0b == nullptr: off
+    const int* cover;       // optional voxel -> (set, token) map of the attention plan (per-batch stride cover_stride ints):
+    size_t cover_stride;    //   rows whose entry is negative belong to no set and are written as exact zeros -- the
+                            //   reference scatters the set features into a zero-filled tensor (mapSetFeature2voxel.cu:312),
+                            //   so a voxel dropped by a capacity guard must not receive bias + W * (stale workspace row)
 };
 struct GemmRoles { GemmRole r[3]; };
 
@@ -135,8 +139,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// phase stamps of one CTA (tools/split_profile.py): compiled in with -DDSVT_PROFILE only, never in the product build
+#ifdef DSVT_PROFILE
 __device__ long long g_split_prof[64];
 #define SP(i) do { if (blockIdx.x == 3 && blockIdx.y == 0) g_split_prof[(n_roles == 1 ? 40 : 0) + (i)] = clock64(); } while (0)
+#define CP(i) do { if (blockIdx.x == 5 && blockIdx.y == 0 && threadIdx.x == 0) g_split_prof[32 + i] = clock64(); } while (0)
+#else
+#define SP(i) do { } while (0)
+#define CP(i) do { } while (0)
+#endif
 
 // Persistent: grid = (n_roles * ctas_per_role, batch).  A CTA owns ONE role: its 147 KB weight image (hi + lo) is copied
 // into shared memory once and stays there while the CTA walks over row tiles t0, t0 + ctas_per_role, ...  Three engines
@@ -284,9 +295,11 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
                 const int acc = n & 1;
                 // (the row map does not depend on the accumulators: its two dependent loads overlap the MMA wait)
                 int orow[8];                                       // output row of this lane's 8 rows, -1: not written
+                unsigned dead = 0;                                 // bit rr: a valid row that belongs to no set -> zeros
 #pragma unroll
                 for (int rr = 0; rr < 8; ++rr) {
                     const int grow = row0 + rr * 4 + rg;
+                    if (g.cover && grow < V && __ldg(g.cover + (size_t) b * g.cover_stride + grow) < 0) dead |= 1u << rr;
                     if (g.plan) {                                  // voxel row -> token position (set-major order)
                         orow[rr] = -1;
                         if (grow < V) {
@@ -348,7 +361,7 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
                         }
                         if (g.act == 1) { ov.x = gelu_tanh(ov.x); ov.y = gelu_tanh(ov.y); ov.z = gelu_tanh(ov.z); ov.w = gelu_tanh(ov.w); }
                         else if (g.act == 2) { ov.x = fmaxf(ov.x, 0.f); ov.y = fmaxf(ov.y, 0.f); ov.z = fmaxf(ov.z, 0.f); ov.w = fmaxf(ov.w, 0.f); }
-                        if (grow >= V) ov = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (grow >= V || (dead >> rr & 1u)) ov = make_float4(0.f, 0.f, 0.f, 0.f);
 #ifdef DSVT_DBG_NO_STORE     // bottleneck probe (never in the product build): results are dropped (kept live by an impossible test)
                         if (orow[rr] >= 0 && ov.x == 1.2345e-30f) *reinterpret_cast<float4*>(outc + (size_t) orow[rr] * g.ld_out + j0) = ov;
 #else
@@ -550,7 +563,6 @@ attn_core_kernel(const float* __restrict__ qbuf, const float* __restrict__ kvbuf
     __shared__ float s_cmask[kH][S];    // ... compacted, log2 domain: [head][token]
 
     const int b = blockIdx.y, tid = threadIdx.x;
-#define CP(i) do { if (blockIdx.x == 5 && blockIdx.y == 0 && threadIdx.x == 0) g_split_prof[32 + i] = clock64(); } while (0)
     CP(0);
     const PlanView pv = plan_view(const_cast<int*>(plan) + (size_t) b * plan_stride, max_sets, max_pillars);
     qbuf += (size_t) b * max_pillars * kC;
@@ -710,12 +722,10 @@ int launch_core(const dsvt_set_attention_params* p, const float* qbuf, const flo
                 const float* mask, const int* set_num, float* o, cudaStream_t st)
 {
     const size_t smem = (size_t) S * kKvTok * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        DSVT_CUDA(cudaFuncSetAttribute(attn_core_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        DSVT_CUDA(cudaFuncSetAttribute(attn_core_kernel<S>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                       (int) cudaSharedmemCarveoutMaxShared));
-        attr_set = true;
+    {
+        static PerDeviceOnce once;
+        const int rc = once.raise_smem(attn_core_kernel<S>, (int) smem, true);
+        if (rc != DSVT_OK) return rc;
     }
     const int cap = 12 * sm_count();        // idle CTAs (sets >= set_num) cost a launch slot each: do not start thousands
     const int grid = p->max_set_num < cap ? p->max_set_num : cap;
@@ -734,6 +744,11 @@ struct SplitBlobHeader {
 }  // namespace
 
 static int gemm_sm_fraction();
+static int gemm_raise_smem() {
+    DSVT_RAISE_SMEM(proj_gemm_kernel<true>, Lay<true>::total);
+    DSVT_RAISE_SMEM(proj_gemm_kernel<false>, Lay<false>::total);
+    return DSVT_OK;
+}
 
 // One 192 x 192 weight block W[n0 .. n0+192][k0 .. k0+192] (row stride ldw) as the kernel's image: six K chunks of
 // [hi 192x32 | lo 192x32] FP16, pre-scaled by 2^sh.
@@ -766,12 +781,12 @@ static int scale_shift(const float* W, size_t n) {
 }
 
 // ---- dense linear layer on the same kernel: y[M,N] = act(x[M,K] W[N,K]^T + b), K and N multiples of 192 -------------
-// Device blob: [N/192][K/192] block images (147456 B each), then bias [N] f32.  One launch per 192-wide K block (the
+// Device blob: [N/192][K/192] block images (147456 B each), then bias [N] f32, then 192 zero floats (the bias of K blocks > 0).  One launch per 192-wide K block (the
 // CTA's resident weight image is one block); the second and later K blocks add to the rows written by the first.
 void* linear_split_prepare(int N, int K, const float* W, const float* b, float* out_mul) {
     const int nb = N / kBN, kb = K / kC;
     const size_t img_bytes = (size_t) nb * kb * kWRoleBytes;
-    std::vector<uint8_t> host(img_bytes + (size_t) N * sizeof(float));
+    std::vector<uint8_t> host(img_bytes + ((size_t) N + kBN) * sizeof(float), 0);     // images | bias [N] | 192 zeros
     const int sh = scale_shift(W, (size_t) N * K);
     *out_mul = ldexpf(1.0f, -sh);
     for (int i = 0; i < nb; ++i)
@@ -794,17 +809,8 @@ int linear_split_launch(const void* blob, int N, int K, float out_mul, bool spli
     const int nb = N / kBN, kb = K / kC;
     const uint8_t* img = static_cast<const uint8_t*>(blob);
     const float* bias = reinterpret_cast<const float*>(img + (size_t) nb * kb * kWRoleBytes);
-    static float* zero_bias = nullptr;          // K blocks after the first add no bias
-    if (!zero_bias) {
-        DSVT_CUDA(cudaMalloc(&zero_bias, kBN * sizeof(float)));
-        DSVT_CUDA(cudaMemset(zero_bias, 0, kBN * sizeof(float)));
-    }
-    static bool attr_set = false;
-    if (!attr_set) {
-        DSVT_CUDA(cudaFuncSetAttribute(proj_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<true>::total));
-        DSVT_CUDA(cudaFuncSetAttribute(proj_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<false>::total));
-        attr_set = true;
-    }
+    const float* zero_bias = bias + N;           // K blocks after the first add no bias: 192 zeros kept behind the bias
+    { const int rc_attr = gemm_raise_smem(); if (rc_attr != DSVT_OK) return rc_attr; }
     for (int j = 0; j < kb; ++j)
         for (int i0 = 0; i0 < nb; i0 += 3) {            // up to three 192-column output blocks (roles) per launch
             const int n_roles = nb - i0 < 3 ? nb - i0 : 3;
@@ -814,7 +820,7 @@ int linear_split_launch(const void* blob, int N, int K, float out_mul, bool spli
                 GemmRole& g = roles.r[r];
                 g.a0 = x + (size_t) j * kC; g.a1 = nullptr; g.lda = x_hi ? k_split : K;
                 g.a0b = x_hi; g.ksplit = x_hi ? k_split : 0; g.ldb = x_hi ? K - k_split : 0;
-                g.add_src = nullptr; g.ld_add = 0;
+                g.add_src = nullptr; g.ld_add = 0; g.cover = nullptr; g.cover_stride = 0;
                 g.wimg = img + ((size_t) i * kb + j) * kWRoleBytes;
                 g.bias = j == 0 ? bias + i * kBN : zero_bias;
                 g.out = y; g.ld_out = N; g.col0 = i * kBN;
@@ -845,23 +851,14 @@ int linear_split_k_launch(const void* blob, int N, int K, float out_mul, bool sp
     const int kb = K / kC;
     const uint8_t* img = static_cast<const uint8_t*>(blob);
     const float* bias = reinterpret_cast<const float*>(img + (size_t) kb * kWRoleBytes);
-    static float* zero_bias = nullptr;
-    if (!zero_bias) {
-        DSVT_CUDA(cudaMalloc(&zero_bias, kBN * sizeof(float)));
-        DSVT_CUDA(cudaMemset(zero_bias, 0, kBN * sizeof(float)));
-    }
-    static bool attr_set = false;
-    if (!attr_set) {
-        DSVT_CUDA(cudaFuncSetAttribute(proj_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<true>::total));
-        DSVT_CUDA(cudaFuncSetAttribute(proj_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<false>::total));
-        attr_set = true;
-    }
+    const float* zero_bias = bias + N;           // 192 zeros kept behind the bias in the weight blob
+    { const int rc_attr = gemm_raise_smem(); if (rc_attr != DSVT_OK) return rc_attr; }
     GemmRoles roles;
     for (int r = 0; r < 3; ++r) {
         const int j = r < kb ? r : 0;
         GemmRole& g = roles.r[r];
         g.a0 = x + (size_t) j * kC; g.a1 = nullptr; g.lda = K;
-        g.a0b = nullptr; g.ksplit = 0; g.ldb = 0;
+        g.a0b = nullptr; g.ksplit = 0; g.ldb = 0; g.cover = nullptr; g.cover_stride = 0;
         g.wimg = img + (size_t) j * kWRoleBytes;
         g.bias = j == 0 ? bias : zero_bias;
         g.out = y_parts + (size_t) j * max_rows * N; g.ld_out = N; g.col0 = 0;
@@ -1019,12 +1016,7 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
     const uint8_t* img = static_cast<const uint8_t*>(split_blob);
     const float* bias = reinterpret_cast<const float*>(img + (size_t) kRoles * kWRoleBytes);
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        DSVT_CUDA(cudaFuncSetAttribute(proj_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<true>::total));
-        DSVT_CUDA(cudaFuncSetAttribute(proj_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<false>::total));
-        attr_set = true;
-    }
+    { const int rc_attr = gemm_raise_smem(); if (rc_attr != DSVT_OK) return rc_attr; }
     if ((rc = stage_mark(0, st)) != DSVT_OK) return rc;
     const int* plan = static_cast<const int*>(plan_in);
     if (!plan) {                                   // stateless call: build the partition's plan first
@@ -1053,7 +1045,7 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
         g.plan_stride = plan_stride;
         g.pad_hi = r == 0 ? 0 : 4;
         g.lda = kC; g.accumulate = 0; g.act = 0;
-        g.a0b = nullptr; g.ksplit = 0; g.ldb = 0; g.add_src = nullptr; g.ld_add = 0;
+        g.a0b = nullptr; g.ksplit = 0; g.ldb = 0; g.add_src = nullptr; g.ld_add = 0; g.cover = nullptr; g.cover_stride = 0;
     }
     {
         GemmRole& g = out_roles.r[0];
@@ -1066,6 +1058,8 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
         g.plan = nullptr; g.plan_stride = 0; g.pad_hi = 0;
         g.lda = kC; g.accumulate = 0; g.act = 0;
         g.a0b = nullptr; g.ksplit = 0; g.ldb = 0; g.add_src = nullptr; g.ld_add = 0;
+        g.cover = plan_view(const_cast<int*>(plan), p->max_set_num, p->max_pillars_num).vox_su;   // voxels in no set -> 0
+        g.cover_stride = plan_stride;
         out_roles.r[1] = out_roles.r[2] = g;
     }
     if (g_skip_mask & 1) {
@@ -1120,6 +1114,8 @@ extern "C" int dsvt_debug_attention_stage_us(float* out3) {
     }
     return 0;
 }
+#ifdef DSVT_PROFILE
 extern "C" int dsvt_debug_split_profile(long long* out64) {
     return cudaMemcpyFromSymbol(out64, dsvt::g_split_prof, sizeof(long long) * 64) == cudaSuccess ? 0 : 1;
 }
+#endif

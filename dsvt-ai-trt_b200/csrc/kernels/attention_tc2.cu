@@ -13,6 +13,8 @@
 // the out-projection accumulator reuses [0,192).
 #include "attention_common.cuh"
 #include "tc_common.cuh"
+#include <cstring>
+#include <vector>
 #include <cuda_fp16.h>
 
 namespace dsvt {
@@ -468,6 +470,44 @@ set_attention_tc2_kernel(const float* __restrict__ x, const float* __restrict__ 
 
 }  // namespace
 
+// ---- host: FP16 operand images of one attention layer ----------------------------------------------------------
+void* attention_tc_prepare(int C, int H, const float* w_in, const float* b_in, const float* w_out, const float* b_out)
+{
+    if (C != kC || H != kH) return nullptr;
+    const float inv_scale = 1.0f / sqrtf((float) kD);
+    std::vector<uint8_t> blob(kWImgBytes + 4 * kC * sizeof(float), 0);
+    auto put = [&](uint8_t* tile, int rows, int n, int k, float v) {   // [chunk][row][8 halves]
+        const __half hv = __float2half_rn(v);
+        memcpy(tile + ((size_t) (k / 8) * rows + n) * 16 + (k % 8) * 2, &hv, 2);
+    };
+    for (int h = 0; h < kH; ++h) {
+        uint8_t* qk = blob.data() + (size_t) h * kWHeadBytes;
+        uint8_t* vv = qk + kWqkBytes;
+        for (int d = 0; d < kD; ++d)
+            for (int k = 0; k < kC; ++k) {
+                put(qk, 48, d, k, w_in[(size_t) (0 * kC + h * kD + d) * kC + k] * inv_scale);      // query rows, pre-scaled
+                put(qk, 48, 24 + d, k, w_in[(size_t) (1 * kC + h * kD + d) * kC + k]);             // key rows
+                put(vv, 32, d, k, w_in[(size_t) (2 * kC + h * kD + d) * kC + k]);                  // value rows (+8 zero rows)
+            }
+    }
+    for (int half = 0; half < 2; ++half) {
+        uint8_t* t = blob.data() + (size_t) kH * kWHeadBytes + (size_t) half * kWoutHalfBytes;
+        for (int n = 0; n < 96; ++n)
+            for (int k = 0; k < kC; ++k) put(t, 96, n, k, w_out[(size_t) (half * 96 + n) * kC + k]);
+    }
+    float* fb = reinterpret_cast<float*>(blob.data() + kWImgBytes);
+    for (int i = 0; i < kC; ++i) {
+        fb[i] = b_in[i] * inv_scale;
+        fb[kC + i] = b_in[kC + i];
+        fb[2 * kC + i] = b_in[2 * kC + i];
+        fb[3 * kC + i] = b_out[i];
+    }
+    void* dev = nullptr;
+    if (cudaMalloc(&dev, blob.size()) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(dev, blob.data(), blob.size(), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(dev); return nullptr; }
+    return dev;
+}
+
 int set_attention_tc2_fused(const dsvt_set_attention_params* p, const void* tc_blob,
                             const float* x, const float* pos, const int* idx, const float* mask,
                             const int* set_num, const int* voxel_num, float* out, cudaStream_t st)
@@ -483,11 +523,7 @@ int set_attention_tc2_fused(const dsvt_set_attention_params* p, const void* tc_b
     TcBlobView2 wb;
     wb.w_img = static_cast<const uint8_t*>(tc_blob);
     wb.bias = reinterpret_cast<const float*>(wb.w_img + kWImgBytes);
-    static bool attr_set = false;
-    if (!attr_set) {
-        DSVT_CUDA(cudaFuncSetAttribute(set_attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-        attr_set = true;
-    }
+    DSVT_RAISE_SMEM(set_attention_tc2_kernel, SM_TOTAL);
     const int max_tiles = (p->max_set_num + kSetsPerTile - 1) / kSetsPerTile;
     const int grid = max_tiles < sm_count() ? max_tiles : sm_count();
     set_attention_tc2_kernel<<<dim3(grid, p->batch), kThreads, SM_TOTAL, st>>>(

@@ -55,6 +55,31 @@ struct WsCarver {
 
 int sm_count();
 
+// One-time, PER-DEVICE raise of a kernel's dynamic shared-memory limit: cudaFuncSetAttribute acts on the current device's
+// context, so the "done" state is a bit per device ordinal, not a process-wide flag.  Thread-safe without a lock: the
+// attribute call is idempotent, two racing first calls on a device merely both make it.  Never allocates or synchronises,
+// so it is legal inside a stream capture.
+struct PerDeviceOnce {
+    std::atomic<uint64_t> done{0};
+    template <typename K> int raise_smem(K kernel, int bytes, bool max_carveout = false) {
+        int dev = 0;
+        DSVT_CUDA(cudaGetDevice(&dev));
+        const uint64_t bit = 1ull << (dev & 63);
+        if (done.load(std::memory_order_acquire) & bit) return DSVT_OK;
+        DSVT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        if (max_carveout)
+            DSVT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared));
+        done.fetch_or(bit, std::memory_order_release);
+        return DSVT_OK;
+    }
+};
+#define DSVT_RAISE_SMEM(kernel, bytes)                                             \
+    do {                                                                           \
+        static ::dsvt::PerDeviceOnce once__;                                       \
+        const int rc__ = once__.raise_smem(kernel, (int) (bytes));                 \
+        if (rc__ != DSVT_OK) return rc__;                                          \
+    } while (0)
+
 // --- device helpers ---------------------------------------------------------
 __device__ __forceinline__ float4 ldg_stream4(const float4* p) {
     float4 r;

@@ -258,10 +258,10 @@ wp_scan_kernel(const int* __restrict__ dense_count, int* __restrict__ dense_slot
     if (zero_tails) for (int i = W + threadIdx.x; i < max_win; i += blockDim.x) vnw[i] = 0;
 }
 
-// every voxel claims a (race-ordered) slot inside its window's staging list
+// every voxel claims a (race-ordered) slot inside its window's staging list; the finalize kernel sorts the list
 __global__ void __launch_bounds__(kWpThreads)
 wp_scatter_kernel(const int* __restrict__ voxel_num, int max_pillars, const int* __restrict__ vox_win,
-                  const int* __restrict__ dense_slot, int* __restrict__ dense_cursor,
+                  const int* __restrict__ dense_count, const int* __restrict__ dense_slot, int* __restrict__ dense_cursor,
                   int* __restrict__ global_index, size_t ws_stride, int max_win, int max_vpw)
 {
     const int b = blockIdx.y;
@@ -273,10 +273,18 @@ wp_scatter_kernel(const int* __restrict__ voxel_num, int max_pillars, const int*
     if (dense < 0) return;
     const int slot = dense_slot[(size_t) b * ws_stride + dense];
     if (slot < 0) return;
-    const int pos = atomicAdd(dense_cursor + (size_t) b * ws_stride + dense, 1);
-    // stage unsorted; windows with more than max_vpw voxels keep an arbitrary subset here and are
-    // canonicalised below only among the kept ones (the reference drops by race as well, :303)
-    if (pos < max_vpw) global_index[((size_t) b * max_win + slot) * max_vpw + pos] = v;
+    if (dense_count[(size_t) b * ws_stride + dense] > max_vpw) {
+        // capacity overflow (only possible when max_voxel_num_per_win < cells per window): the serial-execution outcome
+        // keeps the max_vpw LOWEST voxel ids (the reference drops by race, :303).  Rank by counting -- a correctness
+        // path, O(V) per voxel of an overfull window.
+        const int* vw = vox_win + (size_t) b * ws_stride;
+        int rank = 0;
+        for (int u = 0; u < v && rank < max_vpw; ++u) rank += vw[u] == dense;
+        if (rank < max_vpw) global_index[((size_t) b * max_win + slot) * max_vpw + rank] = v;
+        return;
+    }
+    const int pos = atomicAdd(dense_cursor + (size_t) b * ws_stride + dense, 1);   // staged unsorted
+    global_index[((size_t) b * max_win + slot) * max_vpw + pos] = v;
 }
 
 // one CTA per window slot: sort the staged voxel ids ascending, emit in-window coordinates
@@ -404,11 +412,7 @@ extern "C" int dsvt_get_set_launch(const dsvt_get_set_params* p,
     const size_t cell_words = ((size_t) p->win_shape_x * p->win_shape_y * p->win_shape_z + 31) / 32;
     const size_t smem = ((size_t) p->max_voxel_num_per_win * 4 + 4 * cell_words) * sizeof(int);
     DSVT_CHECK_ARG(smem <= 200 * 1024, "window too large for shared memory");
-    static bool attr_set = false;
-    if (smem > 48 * 1024 && !attr_set) {
-        DSVT_CUDA(cudaFuncSetAttribute(get_set_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    if (smem > 48 * 1024) DSVT_RAISE_SMEM(get_set_kernel, 200 * 1024);
     get_set_kernel<<<dim3(p->max_win_num, p->batch), kGsThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
         global_index, coors_in_win, voxel_num_in_win, win_num, global_index_in_set, set_voxel_mask, set_num,
         mask_expand_0, mask_expand_1, p->voxel_num_set, p->max_win_num, p->max_voxel_num_per_win,
@@ -493,18 +497,14 @@ extern "C" int dsvt_window_partition_launch(const dsvt_window_partition_params* 
     wp_scan_kernel<<<B, 1024, 0, st>>>(dense_count, dense_slot, dense_cursor, voxel_num_in_win, win_num, stride,
                                        dn, p->max_win_num, p->max_voxel_num_per_win, p->zero_tails);
     DSVT_LAUNCH_CHECK();
-    wp_scatter_kernel<<<grid_v, kWpThreads, 0, st>>>(voxel_num, p->max_pillars_num, vox_win, dense_slot,
+    wp_scatter_kernel<<<grid_v, kWpThreads, 0, st>>>(voxel_num, p->max_pillars_num, vox_win, dense_count, dense_slot,
                                                      dense_cursor, global_index, stride, p->max_win_num,
                                                      p->max_voxel_num_per_win);
     DSVT_LAUNCH_CHECK();
     // ids + sorted + keys (3 x max_vpw ints) + the occupancy bitmap and its popcount prefix over the window's cells
     const size_t wp_cell_words = ((size_t) p->win_shape_x * p->win_shape_y * p->win_shape_z + 31) / 32;
     const size_t smem = ((size_t) p->max_voxel_num_per_win * 3 + 2 * wp_cell_words) * sizeof(int);
-    static bool attr_set = false;
-    if (smem > 48 * 1024 && !attr_set) {
-        DSVT_CUDA(cudaFuncSetAttribute(wp_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    if (smem > 48 * 1024) DSVT_RAISE_SMEM(wp_finalize_kernel, 200 * 1024);
     wp_finalize_kernel<<<dim3(p->max_win_num, B), kGsThreads, smem, st>>>(
         coords, p->max_pillars_num, voxel_num_in_win, win_num, global_index, coors_in_win, p->max_win_num,
         p->max_voxel_num_per_win, p->shift_x, p->shift_y, p->shift_z, p->win_shape_x, p->win_shape_y,

@@ -79,6 +79,9 @@ layer_norm192_kernel(const float4* __restrict__ x, const float4* __restrict__ re
     int V = voxel_num[b];
     V = V < max_pillars ? V : max_pillars;
     const int sub = threadIdx.x & 15;                 // lane within the half-warp
+    // the two half-warps of a warp own different rows and diverge at the valid-count / end-row boundary: the reductions
+    // name only the 16 lanes of the own half
+    const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);
     const int rows_per_block = blockDim.x >> 4;
     const int end_row = zero_tails ? max_pillars : V;
     float4 g[3], be[3];
@@ -103,7 +106,7 @@ layer_norm192_kernel(const float4* __restrict__ x, const float4* __restrict__ re
 #pragma unroll
             for (int k = 0; k < 3; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(hmask, s, o);
             const float mean = s / 192.f;
             float q = 0.f;
 #pragma unroll
@@ -112,7 +115,7 @@ layer_norm192_kernel(const float4* __restrict__ x, const float4* __restrict__ re
                 q += (a * a + c * c) + (d * d + e * e);
             }
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+            for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(hmask, q, o);
             const float var = q / 192.f;
             const float sd = sqrtf(var + eps);
 #pragma unroll
@@ -146,6 +149,7 @@ layer_norm192_chain_kernel(const float4* __restrict__ x, LnChain ch, const int* 
     int V = voxel_num[b];
     V = V < max_pillars ? V : max_pillars;
     const int sub = threadIdx.x & 15;
+    const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);     // reductions stay inside the own half-warp (see above)
     const int rows_per_block = blockDim.x >> 4;
     const int end_row = zero_tails ? max_pillars : V;
     for (int row = blockIdx.x * rows_per_block + (threadIdx.x >> 4); row < end_row;
@@ -172,7 +176,7 @@ layer_norm192_chain_kernel(const float4* __restrict__ x, LnChain ch, const int* 
 #pragma unroll
             for (int k = 0; k < 3; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(hmask, s, o);
             const float mean = s / 192.f;
             float q = 0.f;
 #pragma unroll
@@ -181,7 +185,7 @@ layer_norm192_chain_kernel(const float4* __restrict__ x, LnChain ch, const int* 
                 q += (a * a + c * c) + (d * d + e * e);
             }
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+            for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(hmask, q, o);
             const float sd = sqrtf(q / 192.f + eps);
 #pragma unroll
             for (int k = 0; k < 3; ++k) {

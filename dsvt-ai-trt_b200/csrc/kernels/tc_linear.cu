@@ -179,7 +179,7 @@ extern "C" dsvt_linear_weights* dsvt_linear_weights_create(int32_t N, int32_t K,
     }
     const int esize = precision == DSVT_ATTN_FP16 ? 2 : 4;
     const int epc = 16 / esize;
-    if (N <= 0 || K <= 0 || N % kTileN || K % (2 * epc) || !W || (precision != DSVT_ATTN_FP16 && precision != DSVT_ATTN_TF32)) {
+    if (N <= 0 || K <= 0 || N % kTileN || K % (2 * epc) || !W || (precision != DSVT_ATTN_FP16 && precision != DSVT_LINEAR_TF32)) {
         set_last_error("dsvt_linear_weights_create: need N %% 64 == 0, K %% %d == 0, precision TF32 or FP16", 2 * epc);
         return nullptr;
     }

@@ -353,6 +353,9 @@ public:
         const PluginField* g = find_field(fc, "weights");
         const PluginField* b = find_field(fc, "bias");
         if (wsize <= 0 || !g || !b || !g->data || !b->data) return nullptr;
+        // the kernels index gamma / beta by channel: a weights_size or field length that disagrees with channel_num would
+        // be read out of bounds on the host (the reference copies weights_size floats unchecked, layerNorm.cu:126-158)
+        if (wsize != field_int(fc, "channel_num") || g->length != wsize || b->length != wsize) return nullptr;
         // the creator parses "eps" (layerNorm.cu:558) although it advertises "pes": the reference helper
         // therefore never sends it and eps stays 0.0.  Same behaviour here.
         return new (std::nothrow) LayerNormPlugin(field_int(fc, "max_pillars_num"), field_int(fc, "channel_num"), wsize,
@@ -641,7 +644,8 @@ public:
         const PluginField* wo = find_field(fc, "out_proj_weight");
         const PluginField* bo = find_field(fc, "out_proj_bias");
         const int C = field_int(fc, "channel_num");
-        if (C <= 0 || !wi || !bi || !wo || !bo || !wi->data || !bi->data || !wo->data || !bo->data) return nullptr;
+        if (C <= 0 || C > 4096 || !wi || !bi || !wo || !bo || !wi->data || !bi->data || !wo->data || !bo->data) return nullptr;
+        if (wi->length != 3 * C * C || bi->length != 3 * C || wo->length != C * C || bo->length != C) return nullptr;
         return new (std::nothrow) SetAttentionPlugin(
             field_int(fc, "max_win_num"), field_int(fc, "voxel_num_set"), C, field_int(fc, "num_heads", 0, 8),
             field_int(fc, "precision", 0, DSVT_ATTN_FP32), static_cast<const float*>(wi->data),
@@ -650,25 +654,28 @@ public:
     static IPluginV2* from_bytes(const void* data, size_t len) {
         Reader r(data, len);
         const int ms = r.get<int>(), S = r.get<int>(), C = r.get<int>(), H = r.get<int>(), prec = r.get<int>();
+        const int nb_in = r.get<int>();          // 4 or 5: whether the optional set_num input is connected
         if (!r.ok() || C <= 0 || C > 4096 || r.left() < ((size_t) 4 * C * C + 4 * C) * sizeof(float)) return nullptr;
         std::vector<float> wi((size_t) 3 * C * C), bi(3 * C), wo((size_t) C * C), bo(C);
         r.get_array(wi.data(), wi.size()); r.get_array(bi.data(), bi.size());
         r.get_array(wo.data(), wo.size()); r.get_array(bo.data(), bo.size());
-        return new (std::nothrow) SetAttentionPlugin(ms, S, C, H, prec, wi.data(), bi.data(), wo.data(), bo.data());
+        auto* pl = new (std::nothrow) SetAttentionPlugin(ms, S, C, H, prec, wi.data(), bi.data(), wo.data(), bo.data());
+        if (pl) pl->nb_inputs_seen_ = nb_in == 5 ? 5 : 4;
+        return pl;
     }
     size_t getSerializationSize() const noexcept override {
-        return 5 * sizeof(int) + ((size_t) 4 * C_ * C_ + 4 * C_) * sizeof(float);
+        return 6 * sizeof(int) + ((size_t) 4 * C_ * C_ + 4 * C_) * sizeof(float);
     }
     void serialize(void* buf) const noexcept override {
         Writer w(buf);
-        w.put(max_sets_); w.put(S_); w.put(C_); w.put(heads_); w.put(precision_);
+        w.put(max_sets_); w.put(S_); w.put(C_); w.put(heads_); w.put(precision_); w.put(nb_inputs_seen_);
         w.put_array(w_in_.data(), w_in_.size()); w.put_array(b_in_.data(), b_in_.size());
         w.put_array(w_out_.data(), w_out_.size()); w.put_array(b_out_.data(), b_out_.size());
     }
     IPluginV2DynamicExt* clone() const noexcept override {
         auto* c = new (std::nothrow) SetAttentionPlugin(max_sets_, S_, C_, heads_, precision_, w_in_.data(),
                                                         b_in_.data(), w_out_.data(), b_out_.data());
-        if (c) c->setPluginNamespace(ns_.c_str());
+        if (c) { c->setPluginNamespace(ns_.c_str()); c->nb_inputs_seen_ = nb_inputs_seen_; }
         return c;
     }
     int32_t initialize() noexcept override { return upload(); }
@@ -753,7 +760,8 @@ public:
         const PluginField* wo = find_field(fc, "out_proj_weight");
         const PluginField* bo = find_field(fc, "out_proj_bias");
         const int C = field_int(fc, "channel_num");
-        if (C <= 0 || !wi || !bi || !wo || !bo || !wi->data || !bi->data || !wo->data || !bo->data) return nullptr;
+        if (C <= 0 || C > 4096 || !wi || !bi || !wo || !bo || !wi->data || !bi->data || !wo->data || !bo->data) return nullptr;
+        if (wi->length != 3 * C * C || bi->length != 3 * C || wo->length != C * C || bo->length != C) return nullptr;
         return new (std::nothrow) SetAttentionFusedPlugin(
             field_int(fc, "max_win_num"), field_int(fc, "voxel_num_set"), C, field_int(fc, "num_heads", 0, 8),
             field_int(fc, "precision", 0, DSVT_ATTN_FP32_TC), field_int(fc, "max_pillars_num"), field_int(fc, "axis_id"),

@@ -184,12 +184,14 @@ class HotPathFrame:
         self.vox = capi.Points2Features(cfg, device=device, zero_tails=self.zero_tails)
         self.wp = [capi.WindowPartition(cfg, i, device=device, zero_tails=self.zero_tails) for i in (0, 1)]
         self.gs = [capi.GetSet(cfg, i, device=device, zero_tails=self.zero_tails) for i in (0, 1)]
-        # stand-ins for the outputs of TensorRT-native glue layers
-        self.x0 = torch.randn(mp, C, generator=g).to(device)                       # VFE / PFN output
-        self.pos = [[torch.randn(mp, C, generator=g).mul_(0.5).to(device) for _ in range(2)]
-                    for _ in range(cfg.num_blocks)]                                 # 8 pos-embed MLP outputs
-        self.ffn_hidden = torch.randn(mp, F, generator=g).to(device)               # FFN linear 192->384 output
-        self.ffn_out = torch.randn(mp, C, generator=g).mul_(0.5).to(device)        # FFN linear 384->192 output
+        # stand-ins for the outputs of TensorRT-native glue layers (only the ones this frame kind does not compute)
+        if not backbone:
+            self.x0 = torch.randn(mp, C, generator=g).to(device)                       # VFE / PFN output
+            self.pos = [[torch.randn(mp, C, generator=g).mul_(0.5).to(device) for _ in range(2)]
+                        for _ in range(cfg.num_blocks)]                                 # 8 pos-embed MLP outputs
+        if ffn == "off":
+            self.ffn_hidden = torch.randn(mp, F, generator=g).to(device)               # FFN linear 192->384 output
+            self.ffn_out = torch.randn(mp, C, generator=g).mul_(0.5).to(device)        # FFN linear 384->192 output
         cand = __import__("importlib").import_module(__package__ + ".synth").head_candidates(cfg.max_top_k, seed)
         self.cand = [torch.from_numpy(c).to(device)[None] for c in cand]           # CenterHead top-K outputs
         # activations
@@ -254,8 +256,10 @@ class HotPathFrame:
                     self.plans[(part, axis)] = capi.set_attention_plan(
                         gs.global_index_in_set[0], gs.mask_expand_0[0], gs.set_num, axis, cfg.max_pillars_num,
                         cfg.num_heads, cfg.channel_num, out=self.plans.get((part, axis)))
-        x, ln, pos = self.x0, 0, self.pos
-        if self.backbone:
+        x, ln = None, 0
+        if not self.backbone:
+            x, pos = self.x0, self.pos
+        else:
             x = self.max_voxel[-1]                         # VFE output: per-pillar max of PFN layer 1 (:589, output 1)
             pos = self.pos_out
             for blk in range(cfg.num_blocks):              # pos_embed[blk][i] from the shift-i window coordinates (:603-637)
@@ -279,8 +283,9 @@ class HotPathFrame:
                     continue
                 capi.layer_norm(self.attn_out, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=x,
                                 out=self.src, zero_tails=zt); ln += 1                      # norm1(y + x)   :669-676
-                ffn_out = self.ffn_out
+                ffn_out = None
                 if self.ffn == "off":
+                    ffn_out = self.ffn_out
                     if "gelu" not in skip:
                         capi.gelu(self.ffn_hidden, V, out=self.gelu_out, zero_tails=zt)    # :519 (inside the FFN)
                 else:

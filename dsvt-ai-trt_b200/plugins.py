@@ -17,7 +17,7 @@ from ctypes import POINTER, Structure, c_char_p, c_int32, c_size_t, c_void_p
 import numpy as np
 import torch
 
-from ._lib import load_plugin_library, load_library
+from ._lib import load_plugin_library
 
 FIELD_FLOAT32, FIELD_INT32 = 1, 5
 DTYPE_FLOAT, DTYPE_INT32 = 0, 3
@@ -47,7 +47,8 @@ class PluginLibrary:
         if path is None:
             self.lib = load_plugin_library()
         else:
-            load_library()
+            # a foreign harness library (oracle/_ref/libref_*.so: the reference's own plugin sources): opened on its own --
+            # it must not pull this repo's kernels into the process (the reference bench arm runs none of them)
             self.lib = ctypes.CDLL(path, mode=ctypes.RTLD_LOCAL)
         L = self.lib
         L.dsvt_plugin_registry_name.restype = c_char_p

@@ -38,3 +38,16 @@ def gather_results(boxes: torch.Tensor, valid: torch.Tensor, dst: int = 0):
     all_b = torch.stack(bl, dim=1).reshape(world * F, *boxes.shape[1:])     # [F, N, ...] -> frame-major interleave
     all_v = torch.stack(vl, dim=1).reshape(world * F)
     return all_b, all_v
+
+
+def gather_packed(packed: torch.Tensor, dst: int = 0):
+    """packed [F_local, W] (one row per frame: boxes + count) -> on `dst` [N * F_local, W] in GLOBAL frame order; None on
+    the other ranks.  ONE batched collective (64 x 18 004 B = 1.15 MB); enqueued on the current stream."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return packed
+    world, rank = dist.get_world_size(), dist.get_rank()
+    parts = [torch.empty_like(packed) for _ in range(world)] if rank == dst else None
+    dist.gather(packed, parts, dst=dst)
+    if rank != dst:
+        return None
+    return torch.stack(parts, dim=1).reshape(world * packed.shape[0], packed.shape[1])   # frame f = local f // N on rank f % N

@@ -220,7 +220,7 @@ int dsvt_filter_box_launch(const dsvt_filter_box_params* p,
  * ------------------------------------------------------------------------ */
 enum {
     DSVT_ATTN_FP32 = 0,      /* CUDA-core FP32 contractions: the FP32 configuration (tolerance 1e-3)                */
-    DSVT_ATTN_TF32 = 1,      /* tcgen05 kind::tf32 operands, FP32 accumulate in TMEM (dense linear layers only)      */
+    /* 1 is not a set-attention precision: see DSVT_LINEAR_TF32 below */
     DSVT_ATTN_FP16 = 2,      /* tcgen05 kind::f16, FP16 operands, FP32 accumulate: the reference's USE_FP16
                                 configuration (params.h:332; tolerance 1e-2); one fused kernel, QK^T / PV on tcgen05 */
     DSVT_ATTN_FP32_TC = 3,   /* FP32-accurate on tcgen05 (fused entry point, needs a workspace): per-voxel projection
@@ -294,8 +294,10 @@ int dsvt_set_attention_fused_planned_launch(const dsvt_set_attention_params* p, 
 /* ------------------------------------------------------------------------ *
  * (next #4) dense linear layer  y = x * W^T + b on tcgen05 -- replaces the TensorRT FullyConnected
  * layers next to the plugins (fullyConnected_gelu_fullyConnected, src/dsvt-ai-trt.cpp:494-529).
- * W [N,K] row-major (PyTorch [out,in]), N % 64 == 0, K % 16 == 0; precision DSVT_ATTN_TF32 or _FP16.
+ * W [N,K] row-major (PyTorch [out,in]), N % 64 == 0, K % 16 == 0; precision DSVT_LINEAR_TF32 (single-tile
+ * tcgen05 kind::tf32) or DSVT_ATTN_FP16 (kind::f16); DSVT_ATTN_FP32_TC / DSVT_ATTN_FP16_GEMM: see below.
  * ------------------------------------------------------------------------ */
+enum { DSVT_LINEAR_TF32 = 1 };   /* tcgen05 kind::tf32 operands, FP32 accumulate in TMEM -- dense linear layers only */
 typedef struct dsvt_linear_weights dsvt_linear_weights;
 dsvt_linear_weights* dsvt_linear_weights_create(int32_t N, int32_t K, const float* W, const float* b,
                                                 int32_t precision);

@@ -164,6 +164,16 @@ def test_partition_reference_frame(frame0, cfgs, kat):
         assert owp["win_num"] == kat["000000"][tag]["windows"] and ogs["set_num"] == kat["000000"][tag]["sets"]
 
 
+def test_partition_window_capacity_overflow(frame0, cfgs):
+    """max_voxel_num_per_win below the cells of a window: overfull windows keep their LOWEST voxel ids (the outcome of the
+    reference's loop executed serially, windowPartition.cu:303) -- deterministic and bit-exact against the oracle."""
+    cfg = cfgs.REFERENCE.with_(max_voxel_num_per_win=20)
+    o = cpu.points2features(pad_points(frame0, cfg.max_points_num), len(frame0), cfg)
+    for which in (0, 1):
+        owp, _ = check_partition(o, cfg, which)
+        assert (owp["voxel_num_in_win"] == 20).sum() > 10          # the overflow path really ran
+
+
 @pytest.mark.parametrize("S", [24, 36, 48])
 def test_partition_waymo_shape(pkg, cfgs, S):
     cfg = cfgs.WAYMO.with_(voxel_num_set=S, max_pillars_num=110000, max_win_num=8192)
@@ -379,6 +389,44 @@ def test_set_attention_fused_frame(frame0, cfgs, precision):
                                             torch.tensor([ns], dtype=torch.int32, device="cuda"), axis,
                                             cfg.max_pillars_num)
             assert np.array_equal(sc.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("precision", [0, 2, 3, 4])
+def test_set_attention_fused_set_capacity_overflow(frame0, cfgs, precision):
+    """max_win_num below the frame's set count: GetSet drops the sets beyond the capacity, their voxels belong to no set and
+    the reference's scatter into a zero-filled tensor (mapSetFeature2voxel.cu:312) leaves those rows exactly 0 -- also
+    when the workspace still holds rows of an earlier call."""
+    cfg = cfgs.REFERENCE.with_(max_win_num=300)            # frame 0 has 454 sets at 12x12
+    o = cpu.points2features(pad_points(frame0, cfg.max_points_num), len(frame0), cfg)
+    V = o["pillar_num"]
+    rng = np.random.default_rng(12)
+    x = np.zeros((cfg.max_pillars_num, 192), np.float32)
+    pos = np.zeros_like(x)
+    x[:V] = rng.standard_normal((V, 192))
+    pos[:V] = rng.standard_normal((V, 192)) * 0.5
+    _, _, _, _, w = _attn_inputs(1, 1, seed=6)
+    W = capi.AttentionWeights(w["w_in"], w["b_in"], w["w_out"], w["b_out"])
+    owp = cpu.window_partition(o["coords"], V, cfg, 0)
+    ogs = cpu.get_set(owp["global_index"], owp["coors_in_win"], owp["voxel_num_in_win"], owp["win_num"], cfg, 0)
+    ns = ogs["set_num"]
+    assert ns == 300
+    ws_bytes = capi.set_attention_workspace_bytes(1, cfg.max_win_num, 36, 192, 8, cfg.max_pillars_num, precision)
+    ws = torch.full((max(ws_bytes, 256),), 0x7F, dtype=torch.uint8, device="cuda")      # stale workspace: large finite floats
+    for axis in (0, 1):
+        q, k, v = cpu.get_value_by_index(x, pos, ogs["global_index_in_set"], ns, axis)
+        a = cpu.set_attention(q, k, v, ogs["mask_expand_0"], ns, **w)
+        ref = cpu.map_set_feature2voxel(a, ogs["global_index_in_set"], ns, axis, cfg.max_pillars_num)
+        covered = np.zeros(cfg.max_pillars_num, bool)
+        covered[np.unique(ogs["global_index_in_set"][axis, :ns])] = True
+        assert (~covered[:V]).sum() > 500
+        out = torch.full((cfg.max_pillars_num, 192), float("nan"), device="cuda")
+        capi.set_attention_fused(W, dev(x), dev(pos), dev(ogs["global_index_in_set"]), dev(ogs["mask_expand_0"]),
+                                 torch.tensor([ns], dtype=torch.int32, device="cuda"),
+                                 torch.tensor([V], dtype=torch.int32, device="cuda"), axis, out=out, precision=precision,
+                                 workspace=ws if ws_bytes else None)
+        got = out.cpu().numpy()
+        assert np.all(got[~covered] == 0), "voxels in no set must be exactly zero"
+        assert np.abs(got - ref).max() <= ATTN_TOL[precision]
 
 
 @pytest.mark.parametrize("precision", [3, 4])

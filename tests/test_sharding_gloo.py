@@ -32,10 +32,17 @@ def _worker(rank, world, port, n_frames, q):
         assert sh.global_frame_id(rank, world, i) == f
     res = sh.gather_results(boxes, valid, dst=0)
     t = sh.reduce_max(10.0 + rank)
+    # BASELINE.json configs[3]'s batched gather: one packed row per frame (boxes + count)
+    packed = torch.stack([torch.cat([torch.full((K * 9,), float(f)), torch.tensor([f], dtype=torch.int32).view(torch.float32)])
+                          for f in mine])
+    gp = sh.gather_packed(packed, dst=0)
     if rank == 0:
+        assert gp.shape == (n_frames, K * 9 + 1)
+        assert gp[:, 0].tolist() == [float(f) for f in range(n_frames)]
+        assert gp[:, K * 9].contiguous().view(torch.int32).tolist() == list(range(n_frames))
         q.put((res[0][:, 0, 0].tolist(), res[1].tolist(), t))
     else:
-        assert res is None
+        assert res is None and gp is None
         q.put(("t", t))
     dist.barrier()
     dist.destroy_process_group()
