@@ -107,6 +107,9 @@ static int attn_dispatch(const dsvt_set_attention_params* p, const dsvt_attentio
             return set_attention_split_fused(p, w->split_blob, w->split_out_mul, p->precision == DSVT_ATTN_FP32_TC,
                                              q, pos, idx, mask, set_num, voxel_num, out, plan, workspace, workspace_bytes, st);
         case DSVT_ATTN_FP32:
+            // fused form: these two kernels scatter set rows into `out`; a voxel that belongs to no set (a set dropped by a
+            // capacity guard upstream) must read exactly 0 like the reference's zero-filled tensor (mapSetFeature2voxel.cu:312)
+            if (fused) DSVT_CUDA(cudaMemsetAsync(out, 0, (size_t) p->batch * p->max_pillars_num * p->channel_num * sizeof(float), st));
             return set_attention_fp32(p, w->dev, fused, q, k, v, pos, idx, mask, set_num, voxel_num, out, st);
         case DSVT_ATTN_FP16:
             if (!fused) {
@@ -114,6 +117,7 @@ static int attn_dispatch(const dsvt_set_attention_params* p, const dsvt_attentio
                                "(dsvt_set_attention_fused_launch) only");
                 return DSVT_ERR_UNSUPPORTED;
             }
+            DSVT_CUDA(cudaMemsetAsync(out, 0, (size_t) p->batch * p->max_pillars_num * p->channel_num * sizeof(float), st));
             return set_attention_tc2_fused(p, w->tc_blob, q, pos, idx, mask, set_num, voxel_num, out, st);
         default:
             set_last_error("set attention: precision %d is not available in this build", p->precision);

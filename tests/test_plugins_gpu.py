@@ -143,7 +143,8 @@ def test_set_attention_plugin(lib, plg, attention_case):
     n, S, C = c["q"].shape
     p = plg.add_set_attention_op(lib, n, S, C, 8, c["w_in"], c["b_in"], c["w_out"], c["b_out"], precision=0)
     p2, blob = roundtrip(lib, p)
-    assert len(blob) == 5 * 4 + (4 * C * C + 4 * C) * 4
+    assert len(blob) == 6 * 4 + (4 * C * C + 4 * C) * 4       # 5 x i32 config + the connected input count (4 / 5) + weights
+    assert struct.unpack("<6i", blob[:24]) == (n, S, C, 8, 0, 4)
     for plugin in (p, p2):
         (out,) = plugin.enqueue([dev(c["q"])[None], dev(c["k"])[None], dev(c["v"])[None], dev(c["mask"])[None]],
                                 poison=float("nan"))
@@ -153,6 +154,10 @@ def test_set_attention_plugin(lib, plg, attention_case):
                        poison=float("nan"))
     got = out[0].cpu().numpy()
     assert np.abs(got[:2] - c["out"][:2]).max() <= 2e-5 and np.all(got[2:] == 0)
+    # the optional input survives clone() and serialize -> deserialize (TensorRT clones after configurePlugin and
+    # deserialises at run time): the clone must not fall back to "all max_set_num sets"
+    for again in (p.clone(), lib.deserialize(p.type, p.serialize())):
+        assert struct.unpack("<6i", again.serialize()[:24])[5] == 5
 
 
 @pytest.mark.parametrize("precision", [0, 2, 3, 4])
