@@ -330,10 +330,12 @@ def set_attention_plan(global_index_in_set, mask, set_num, axis, max_pillars, he
 
 
 def set_attention_fused(weights, x, pos, global_index_in_set, mask, set_num, voxel_num, axis, out=None,
-                        precision=DSVT_ATTN_FP32, zero_tails=1, workspace=None, plan=None):
+                        precision=DSVT_ATTN_FP32, zero_tails=1, workspace=None, plan=None, norm=None):
     """Fused gather + attention + scatter: x,pos [B,max_pillars,C], global_index_in_set [B,2,max_sets,S].
     `workspace`: uint8 device tensor of dsvt_set_attention_workspace_size bytes (allocated here when None and the
-    precision needs one; pass a persistent buffer when capturing CUDA graphs)."""
+    precision needs one; pass a persistent buffer when capturing CUDA graphs).
+    `norm` = (residual, gamma, beta, eps): out = LayerNorm(attention + residual) in the out-projection's epilogue
+    (dsvt_set_attention_fused_norm_launch; GEMM-pipeline precisions)."""
     _need(x, torch.float32, "x")
     _need(pos, torch.float32, "pos")
     _need(global_index_in_set, torch.int32, "global_index_in_set")
@@ -346,6 +348,16 @@ def set_attention_fused(weights, x, pos, global_index_in_set, mask, set_num, vox
     ws_bytes = int(_lib().dsvt_set_attention_workspace_size(ctypes.byref(p)))
     if ws_bytes and workspace is None:
         workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    if norm is not None:
+        res, gamma, beta, eps = norm
+        for t, n in ((res, "residual"), (gamma, "gamma"), (beta, "beta")):
+            _need(t, torch.float32, n)
+        rc = _lib().dsvt_set_attention_fused_norm_launch(
+            ctypes.byref(p), c_void_p(weights.handle), _ptr(x), _ptr(pos), _ptr(global_index_in_set), _ptr(mask),
+            _ptr(set_num), _ptr(voxel_num), _ptr(res), _ptr(gamma), _ptr(beta), c_float(eps), _ptr(out), _ptr(plan),
+            _ptr(workspace), c_size_t(workspace.numel() if workspace is not None else 0), _stream())
+        _check(rc, "dsvt_set_attention_fused_norm_launch")
+        return out
     if plan is not None and ws_bytes:
         rc = _lib().dsvt_set_attention_fused_planned_launch(
             ctypes.byref(p), c_void_p(weights.handle), _ptr(x), _ptr(pos), _ptr(global_index_in_set), _ptr(mask),
@@ -429,6 +441,21 @@ class Linear:
         _check(_lib().dsvt_linear_rows_splitk_launch(c_void_p(self.handle), _ptr(x), _ptr(add), _ptr(rows),
                                                      c_int32(max_rows), _ptr(out), _stream()),
                "dsvt_linear_rows_splitk_launch")
+        return out
+
+    def rows_norm(self, x, rows, stages, eps=0.0, out=None, zero_tails=1):
+        """Linear (N == 192, K in {192, 384}) + a chain of (residual add + LayerNorm) stages in one kernel:
+        stages = [(residual_or_None, gamma, beta), ...] (<= 3).  x [max_rows, K] -> [max_rows, 192]."""
+        _need(x, torch.float32, "x")
+        _need(rows, torch.int32, "rows")
+        max_rows = x.shape[0]
+        out = torch.empty(max_rows, self.N, dtype=torch.float32, device=x.device) if out is None else out
+        arr = (LnStage * len(stages))()
+        for i, (r, g, b) in enumerate(stages):
+            arr[i] = LnStage(r.data_ptr() if r is not None else None, g.data_ptr(), b.data_ptr())
+        _check(_lib().dsvt_linear_rows_norm_launch(c_void_p(self.handle), _ptr(x), _ptr(rows), c_int32(max_rows), arr,
+                                                   c_int32(len(stages)), c_float(eps), _ptr(out), c_int32(zero_tails),
+                                                   _stream()), "dsvt_linear_rows_norm_launch")
         return out
 
     def rows_concat(self, x_lo, x_hi, rows, activation=0, out=None, zero_tails=1):

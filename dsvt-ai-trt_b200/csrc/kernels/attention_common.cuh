@@ -30,10 +30,12 @@ size_t attention_split_workspace(const dsvt_set_attention_params* p);
 size_t attention_split_plan_bytes(const dsvt_set_attention_params* p);
 int attention_split_plan(const dsvt_set_attention_params* p, const int* idx, const float* mask, const int* set_num,
                          void* plan, size_t plan_bytes, cudaStream_t st);
+// optional epilogue of the out-projection: out = LayerNorm(attention + residual) (norm1 of the encoder layer)
+struct AttnNorm { const float* residual; const float* gamma; const float* beta; float eps; };
 int set_attention_split_fused(const dsvt_set_attention_params* p, const void* split_blob, const float* out_mul,
                               bool split, const float* x, const float* pos, const int* idx, const float* mask,
                               const int* set_num, const int* voxel_num, float* out, const void* plan,
-                              void* workspace, size_t workspace_bytes, cudaStream_t st);
+                              void* workspace, size_t workspace_bytes, cudaStream_t st, const AttnNorm* norm = nullptr);
 
 }  // namespace dsvt
 

@@ -106,6 +106,16 @@ struct GemmRole {
     const float* a0b;       // optional second source of the A operand: columns >= ksplit of the K block come from a0b
     int ksplit, ldb;        //   (the PFN's concatenation [point features | per-pillar max], src/dsvt-ai-trt.cpp:583-587,
                             //   read in place instead of being materialised); ksplit is a multiple of 32, a0b == nullptr: off
+    int kchunks;            // K / 32 (tile kernel only): 6, or 12 for a K = 384 layer whose two weight blocks are consecutive
+    // LayerNorm-chain epilogue (tile kernel only, N == 192, no plan): the finished row y0 = acc * out_mul + bias goes through
+    //   y = LN_s(y + ln_res[s]) for s < n_ln  (the addElementWise(kSUM) + LayerNormPlugin pairs that follow the attention's
+    //   out-projection and the FFN's second linear in the reference graph, src/dsvt-ai-trt.cpp:669-697, :750-756) before it
+    //   is stored -- the intermediate tensors never reach memory.  Arithmetic per stage = layer_norm192_kernel (rowwise.cu).
+    int n_ln;
+    const float* ln_res[3];     // [rows, 192] each, or nullptr
+    const float* ln_gamma[3];
+    const float* ln_beta[3];
+    float ln_eps;
     const int* cover;       // optional voxel -> (set, token) map of the attention plan (per-batch stride cover_stride ints):
     size_t cover_stride;    //   rows whose entry is negative belong to no set and are written as exact zeros -- the
                             //   reference scatters the set features into a zero-filled tensor (mapSetFeature2voxel.cu:312),
@@ -144,9 +154,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ long long g_split_prof[64];
 #define SP(i) do { if (blockIdx.x == 3 && blockIdx.y == 0) g_split_prof[(n_roles == 1 ? 40 : 0) + (i)] = clock64(); } while (0)
 #define CP(i) do { if (blockIdx.x == 5 && blockIdx.y == 0 && threadIdx.x == 0) g_split_prof[32 + i] = clock64(); } while (0)
+#define TP(i) do { if (blockIdx.x == 20 && blockIdx.y == 0) g_split_prof[(i)] = clock64(); } while (0)
 #else
 #define SP(i) do { } while (0)
 #define CP(i) do { } while (0)
+#define TP(i) do { } while (0)
 #endif
 
 // Persistent: grid = (n_roles * ctas_per_role, batch).  A CTA owns ONE role: its 147 KB weight image (hi + lo) is copied
@@ -438,6 +450,361 @@ proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num
     __syncthreads();
     if (tid == 0) SP(21);
     if (warp == kIssuerWarp) tmem_dealloc<512>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Single-pass form of the same GEMM: one CTA = one 128-row tile of one role, NOT persistent, two CTAs per SM.
+//
+// Why: at these sizes (30 k rows = 241 tiles, 148 SMs) the persistent kernel above never reaches a steady state -- a CTA
+// computes 1-5 tiles, so its 147 KB resident weight image (4-5 us to arrive when every SM pulls the same lines), the first
+// row loads and the final drain are most of its life, and with one 229 KB CTA per SM nothing overlaps them: the ncu source
+// view shows 46 % of the warp samples waiting on global loads and 23 % parked at the final barrier
+// (profiles/r2_gemm_persistent_stalls.txt).  Here the weights are NOT resident: each K chunk's [hi | lo] image (24 KB, an
+// L2 hit for every CTA but the first) streams through the same 2-stage ring as the converted A chunk, the CTA needs 80 KB
+// of shared memory and 192 TMEM columns, and TWO CTAs share an SM so that one's loads overlap the other's epilogue.  L2->SM
+// traffic per tile rises from 96-192 KB (rows) to 243-339 KB (rows + weights), still under the L2 fabric's ~42 B/clk/SM.
+// Roles, operand images, the MMA sequence and the epilogue arithmetic are those of proj_gemm_kernel: results are bit-identical.
+constexpr int kLnStride = 196;                        // floats per row of the LayerNorm tile: 49 x 16 B, conflict-free row writes
+constexpr int kTStages = 2;                           // converted A chunks
+constexpr int kTWStages = 2;                          // weight chunks (a third stage and per-row L2 prefetches of every operand
+                                                      // were measured: slower -- the memory system, not latency, is the limit)
+constexpr int kTWorkers = 256;                        // warps 0-7: A producers, then the epilogue
+constexpr int kTIssuerWarp = 8;                       // warp 8: MMA issue;  warp 9: weight-chunk copies + L2 prefetches
+constexpr int kTThreads = 10 * 32;
+template <bool SPLIT> struct TLay {
+    static constexpr int terms = SPLIT ? 2 : 1;
+    static constexpr int a_stage = terms * kATerm;            // 16384 / 8192
+    static constexpr int w_stage = terms * kBTerm;            // 24576 / 12288
+    static constexpr int w = kTStages * a_stage;              // weight ring behind the A ring
+    static constexpr int ring = w + kTWStages * w_stage;      // 106496 / 53248
+    static constexpr int ln_tile = kBM * kLnStride * 4;       // 100352: the finished FP32 tile of the LayerNorm epilogue
+    static constexpr int plain = ring > kEpiWarps * kEpiScratch ? ring : kEpiWarps * kEpiScratch;   // epilogue scratch aliases the ring
+    static constexpr int total = plain > ln_tile ? plain : ln_tile;                                  // ... and so does the LayerNorm tile
+};
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(kTThreads, 2)
+proj_tile_kernel(const __grid_constant__ GemmRoles roles, const int* __restrict__ voxel_num, int rows_host, int max_pillars,
+                 int max_sets, int zero_tails)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t w_full[kTWStages], w_empty[kTWStages], a_full[kTStages], s_empty[kTStages], acc_full;
+    __shared__ uint32_t tmem_slot;
+    using L = TLay<SPLIT>;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x, b = blockIdx.z;
+    const GemmRole& g = roles.r[blockIdx.y];       // read in place from the parameter space (no local copy of the struct)
+    int V = voxel_num ? voxel_num[b] : rows_host;
+    V = V < max_pillars ? V : max_pillars;
+    const int row_base = tile * kBM;
+    float* out = g.out + (size_t) b * max_pillars * g.ld_out + g.col0;
+    if (row_base >= V) {                                  // a tile of tail rows: zero-filled (plugin outputs), or nothing to do
+        if (zero_tails)
+            for (int i = tid; i < kBM * (kBN / 4); i += kTThreads) {
+                const int rloc = i / (kBN / 4), cc4 = i - rloc * (kBN / 4);
+                if (row_base + rloc < max_pillars)
+                    stg_zero4(reinterpret_cast<float4*>(out + (size_t) (row_base + rloc) * g.ld_out + cc4 * 4));
+            }
+        return;
+    }
+    const float* a0 = g.a0 + (size_t) b * max_pillars * g.lda;
+    const float* a1 = g.a1 ? g.a1 + (size_t) b * max_pillars * g.lda : nullptr;
+    const float* a0b = g.a0b ? g.a0b + (size_t) b * max_pillars * g.ldb : nullptr;
+    if (tid == 0) TP(0);
+
+    if (tid == 0) {
+        for (int s = 0; s < kTStages; ++s) { mbar_init(&a_full[s], kTWorkers); mbar_init(&s_empty[s], 1); }
+        for (int s = 0; s < kTWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        mbar_init(&acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == kTIssuerWarp) tmem_alloc<256>(&tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    if (tid == 0) TP(1);
+
+    if (warp < 8) {
+        // =========================== A PRODUCERS =========================================================
+        // step s = (K chunk kc = s >> 1, half = s & 1): rows half*64 + warp*8 + (lane & 7), 16-byte K piece c16 = lane >> 3
+        constexpr int kDepth = 3, kUnroll = 6;                  // lcm(2 halves, kDepth): static buffer / half indices
+        const int n_steps = g.kchunks * 2;                      // a multiple of 12
+        const int rl = warp * 8 + (lane & 7), c16 = lane >> 3;
+        float buf[kDepth][16];                                  // [0..7] = a0 row piece, [8..15] = a1 (pos) row piece
+        auto issue = [&](int s, float (&d)[16]) {
+            const int kc = s >> 1, row = row_base + (s & 1) * 64 + rl;
+            if (row < V) {
+                const int col = kc * kBK + c16 * 8;
+                if (a0b && col >= g.ksplit) ldg256(a0b + (size_t) row * g.ldb + (col - g.ksplit), &d[0]);
+                else ldg256(a0 + (size_t) row * g.lda + col, &d[0]);
+                if (a1) ldg256(a1 + (size_t) row * g.lda + col, &d[8]);
+                else {
+#pragma unroll
+                    for (int e = 8; e < 16; ++e) d[e] = 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) d[e] = 0.f;
+            }
+        };
+#pragma unroll
+        for (int s = 0; s < kDepth - 1; ++s) issue(s, buf[s]);
+#pragma unroll 1
+        for (int s0 = 0; s0 < n_steps; s0 += kUnroll) {
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int s = s0 + u;
+                if (s + kDepth - 1 < n_steps) issue(s + kDepth - 1, buf[(u + kDepth - 1) % kDepth]);
+                const int cc = s >> 1, st = cc % kTStages, r = (u & 1) * 64 + rl;
+                if ((u & 1) == 0 && cc >= kTStages) mbar_wait(&s_empty[st], ((cc / kTStages) - 1) & 1);
+                float (&d)[16] = buf[u % kDepth];
+                const float v[8] = {d[0] + d[8], d[1] + d[9], d[2] + d[10], d[3] + d[11],
+                                    d[4] + d[12], d[5] + d[13], d[6] + d[14], d[7] + d[15]};
+                const uint4 hi = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+                uint8_t* stage = smem + st * L::a_stage;
+                *reinterpret_cast<uint4*>(stage + c16 * (kBM * 16) + r * 16) = hi;
+                if (SPLIT) {
+                    const float2 h0 = unpack_h2(hi.x), h1 = unpack_h2(hi.y), h2 = unpack_h2(hi.z), h3 = unpack_h2(hi.w);
+                    const uint4 lo = make_uint4(pack_h2(v[0] - h0.x, v[1] - h0.y), pack_h2(v[2] - h1.x, v[3] - h1.y),
+                                                pack_h2(v[4] - h2.x, v[5] - h2.y), pack_h2(v[6] - h3.x, v[7] - h3.y));
+                    *reinterpret_cast<uint4*>(stage + kATerm + c16 * (kBM * 16) + r * 16) = lo;
+                }
+                if (u & 1) {
+                    fence_proxy_async_smem();
+                    mbar_arrive(&a_full[st]);
+                    if (tid == 0 && cc < 6) TP(2 + cc);
+                }
+            }
+        }
+
+        // =========================== EPILOGUE (same warps) ===============================================
+        // warp = (TMEM lane quarter q4, column half hf): 3 slabs of 32 columns.  Slab: TMEM -> registers (lane = row)
+        // -> swizzled scratch -> (lane = 4 columns of 8 rows) scale + bias -> full 128-byte row segments to global.
+        const int q4 = warp & 3, hf = warp >> 2;
+        const uint32_t tlane = tmem + ((uint32_t) (q4 * 32) << 16) + hf * 96;
+        const int rg = lane >> 3, c4 = lane & 7;
+        const float* bias = g.bias + hf * 96 + c4 * 4;
+        float* outc = out + hf * (96 + g.pad_hi) + c4 * 4;
+        const PlanView pv = plan_view(const_cast<int*>(g.plan) + (size_t) b * g.plan_stride, max_sets, max_pillars);
+        const int row0 = row_base + q4 * 32;
+        int orow[8];                                       // output row of this lane's 8 rows, -1: not written
+        unsigned dead = 0;                                 // bit rr: a valid row that belongs to no set -> zeros
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+            const int grow = row0 + rr * 4 + rg;
+            if (g.cover && grow < V && __ldg(g.cover + (size_t) b * g.cover_stride + grow) < 0) dead |= 1u << rr;
+            if (g.plan) {                                  // voxel row -> token position (set-major order)
+                orow[rr] = -1;
+                if (grow < V) {
+                    const int su = __ldg(pv.vox_su + grow);
+                    if (su >= 0) {
+                        const int t = __ldg(pv.set_off + (su >> 6)) + (su & 63);
+                        if (t < max_pillars) orow[rr] = t;
+                    }
+                }
+            } else {
+                orow[rr] = (grow < V || (zero_tails && grow < max_pillars)) ? grow : -1;
+            }
+        }
+        float4 bias3[3];                                   // loaded BEFORE the accumulators are waited for: a load issued per slab
+#pragma unroll                                             // would put one L2 round trip on every slab's critical path
+        for (int j = 0; j < 3; ++j) bias3[j] = __ldg(reinterpret_cast<const float4*>(bias + j * 32));
+        if (tid == 0) TP(8);
+        mbar_wait(&acc_full, 0);                           // every MMA has completed: the ring is dead, the scratch may alias it
+        tc_fence_after_sync();
+        if (tid == 0) TP(9);
+        if (g.n_ln > 0) {
+            // ---- LayerNorm-chain epilogue: pass A, TMEM -> finished FP32 rows in shared memory (lane = row) ----------
+            float* tile = reinterpret_cast<float*>(smem);
+            {
+                float* trow = tile + (size_t) (q4 * 32 + lane) * kLnStride + hf * 96;
+                const int grow = row0 + lane;
+                const bool is_dead = g.cover && grow < V && __ldg(g.cover + (size_t) b * g.cover_stride + grow) < 0;
+#pragma unroll 1
+                for (int j0 = 0; j0 < 96; j0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(tlane + j0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + hf * 96 + j0 + 4 * j));
+                        float4 y = make_float4(__uint_as_float(r[4 * j]) * g.out_mul + bb.x, __uint_as_float(r[4 * j + 1]) * g.out_mul + bb.y,
+                                               __uint_as_float(r[4 * j + 2]) * g.out_mul + bb.z, __uint_as_float(r[4 * j + 3]) * g.out_mul + bb.w);
+                        if (is_dead) y = make_float4(0.f, 0.f, 0.f, 0.f);
+                        *reinterpret_cast<float4*>(trow + j0 + 4 * j) = y;
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight epilogue warps
+            // ---- pass B: half a warp per row, the chain of layer_norm192_chain_kernel (rowwise.cu) on the staged rows ---
+            const int sub = lane & 15;
+            const unsigned hmask = 0xFFFFu << (lane & 16);
+#pragma unroll 1
+            for (int it = 0; it < 8; ++it) {
+                const int rloc = warp * 16 + it * 2 + (lane >> 4), grow = row_base + rloc;
+                if (grow >= max_pillars) continue;
+                float4* orow4 = reinterpret_cast<float4*>(out + (size_t) grow * g.ld_out);
+                if (grow >= V) {
+                    if (zero_tails)
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) stg_zero4(orow4 + k * 16 + sub);
+                    continue;
+                }
+                float4 v[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) v[k] = *reinterpret_cast<const float4*>(tile + (size_t) rloc * kLnStride + (k * 16 + sub) * 4);
+#pragma unroll
+                for (int st = 0; st < 3; ++st) {
+                    if (st >= g.n_ln) break;
+                    if (g.ln_res[st] != nullptr) {
+                        const float4* rp = reinterpret_cast<const float4*>(g.ln_res[st] + ((size_t) b * max_pillars + grow) * kC);
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const float4 r = ldg_stream4(rp + k * 16 + sub);
+                            v[k].x += r.x; v[k].y += r.y; v[k].z += r.z; v[k].w += r.w;
+                        }
+                    }
+                    float sum = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(hmask, sum, o);
+                    const float mean = sum / 192.f;
+                    float q = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float a = v[k].x - mean, c = v[k].y - mean, d = v[k].z - mean, e = v[k].w - mean;
+                        q += (a * a + c * c) + (d * d + e * e);
+                    }
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(hmask, q, o);
+                    const float sd = sqrtf(q / 192.f + g.ln_eps);
+                    const float4* gp = reinterpret_cast<const float4*>(g.ln_gamma[st]);
+                    const float4* bp = reinterpret_cast<const float4*>(g.ln_beta[st]);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float4 ga = __ldg(gp + k * 16 + sub), be = __ldg(bp + k * 16 + sub);
+                        v[k].x = (v[k].x - mean) / sd * ga.x + be.x;
+                        v[k].y = (v[k].y - mean) / sd * ga.y + be.y;
+                        v[k].z = (v[k].z - mean) / sd * ga.z + be.z;
+                        v[k].w = (v[k].w - mean) / sd * ga.w + be.w;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) stg_stream4(orow4 + k * 16 + sub, v[k]);
+            }
+        } else {
+        float4* scr = reinterpret_cast<float4*>(smem + warp * kEpiScratch);
+#pragma unroll 1
+        for (int j0 = 0; j0 < 96; j0 += 32) {
+            // rows added in the epilogue (second K block / residual): all eight loads of the slab are in flight before the
+            // accumulators are touched (they were the longest stall of the persistent kernel's epilogue)
+            float4 extra[8];
+            const bool has_acc = g.accumulate != 0, has_add = g.add_src != nullptr;
+            if (has_acc || has_add) {
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) {
+                    const int grow = row0 + rr * 4 + rg;
+                    extra[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (orow[rr] >= 0 && grow < V) {
+                        if (has_acc) extra[rr] = *reinterpret_cast<const float4*>(outc + (size_t) orow[rr] * g.ld_out + j0);
+                        if (has_add) {
+                            const float4 ad = __ldg(reinterpret_cast<const float4*>(
+                                g.add_src + ((size_t) b * max_pillars + grow) * g.ld_add + g.col0 + hf * 96 + c4 * 4 + j0));
+                            extra[rr].x += ad.x; extra[rr].y += ad.y; extra[rr].z += ad.z; extra[rr].w += ad.w;
+                        }
+                    }
+                }
+            }
+            const float4 bb = j0 == 0 ? bias3[0] : (j0 == 32 ? bias3[1] : bias3[2]);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {               // two 16-column loads: keeps the live registers under the cap
+                uint32_t r[16];
+                tmem_ld16(tlane + j0 + hh * 16, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 4; ++j)                // float4 j of row `lane` lands in slot j ^ (lane & 7)
+                    scr[lane * 8 + ((hh * 4 + j) ^ (lane & 7))] =
+                        make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                    __uint_as_float(r[4 * j + 3]));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {               // 4 rows x 128 contiguous bytes per store instruction
+                const int grow = row0 + rr * 4 + rg, rloc = rr * 4 + rg;
+                const float4 v = scr[rloc * 8 + (c4 ^ (rloc & 7))];
+                // out_mul is a power of two: the product is exact, so this is one rounding of (acc + bias)
+                float4 ov = make_float4((v.x * g.out_mul + bb.x) * g.post_mul, (v.y * g.out_mul + bb.y) * g.post_mul,
+                                        (v.z * g.out_mul + bb.z) * g.post_mul, (v.w * g.out_mul + bb.w) * g.post_mul);
+                if (has_acc || has_add) { ov.x += extra[rr].x; ov.y += extra[rr].y; ov.z += extra[rr].z; ov.w += extra[rr].w; }
+                if (g.act == 1) { ov.x = gelu_tanh(ov.x); ov.y = gelu_tanh(ov.y); ov.z = gelu_tanh(ov.z); ov.w = gelu_tanh(ov.w); }
+                else if (g.act == 2) { ov.x = fmaxf(ov.x, 0.f); ov.y = fmaxf(ov.y, 0.f); ov.z = fmaxf(ov.z, 0.f); ov.w = fmaxf(ov.w, 0.f); }
+                if (grow >= V || (dead >> rr & 1u)) ov = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (orow[rr] >= 0) *reinterpret_cast<float4*>(outc + (size_t) orow[rr] * g.ld_out + j0) = ov;
+            }
+            __syncwarp();
+            if (tid == 0) TP(10 + (j0 >> 5));
+        }
+        }
+    } else if (warp == kTIssuerWarp) {
+        // =========================== MMA ISSUE ===========================================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(kFmtF16, kBM, kBN);
+            const uint32_t sbase = smem_u32(smem);
+#pragma unroll 1
+            for (int kc = 0; kc < g.kchunks; ++kc) {
+                const int st = kc % kTStages, ws = kc % kTWStages;
+                mbar_wait(&w_full[ws], (kc / kTWStages) & 1);
+                if (kc < 6) TP(14 + kc);
+                mbar_wait(&a_full[st], (kc / kTStages) & 1);
+                tc_fence_after_sync();
+                if (kc < 6) TP(20 + kc);
+                const uint32_t sa = sbase + st * L::a_stage, sw = sbase + L::w + ws * L::w_stage;
+#pragma unroll
+                for (int ks = 0; ks < kBK / 16; ++ks) {
+                    const uint64_t a_hi = make_smem_desc(sa + ks * 2 * (kBM * 16), kBM * 16, 128);
+                    const uint64_t b_hi = make_smem_desc(sw + ks * 2 * (kBN * 16), kBN * 16, 128);
+                    if (SPLIT) {
+                        const uint64_t a_lo = make_smem_desc(sa + kATerm + ks * 2 * (kBM * 16), kBM * 16, 128);
+                        const uint64_t b_lo = make_smem_desc(sw + kBTerm + ks * 2 * (kBN * 16), kBN * 16, 128);
+                        umma_f16(tmem, a_lo, b_hi, idesc, (kc | ks) != 0);
+                        umma_f16(tmem, a_hi, b_lo, idesc, 1);
+                        umma_f16(tmem, a_hi, b_hi, idesc, 1);
+                    } else {
+                        umma_f16(tmem, a_hi, b_hi, idesc, (kc | ks) != 0);
+                    }
+                }
+                umma_commit(&s_empty[st]);
+                umma_commit(&w_empty[ws]);
+            }
+            umma_commit(&acc_full);
+        }
+        __syncwarp();
+    } else {
+        // =========================== WEIGHT-CHUNK COPIES =================================================
+        const int nrows = V - row_base < kBM ? V - row_base : kBM;
+        if (lane == 0) {
+            if (g.lda == kC) {       // the tile's rows are one contiguous block: pull them into L2 as large sequential requests
+                const uint32_t bytes = (uint32_t) (nrows * kC * sizeof(float));
+                l2_prefetch(a0 + (size_t) row_base * kC, bytes);
+                if (a1) l2_prefetch(a1 + (size_t) row_base * kC, bytes);
+            }
+#pragma unroll 1
+            for (int kc = 0; kc < g.kchunks; ++kc) {
+                const int ws = kc % kTWStages;
+                if (kc >= kTWStages) mbar_wait(&w_empty[ws], ((kc / kTWStages) - 1) & 1);
+                mbar_arrive_expect_tx(&w_full[ws], L::w_stage);
+                bulk_g2s(smem + L::w + ws * L::w_stage, g.wimg + (size_t) kc * kWChunkBytes, L::w_stage, &w_full[ws]);
+            }
+        }
+        __syncwarp();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (tid == 0) TP(13);
+    if (warp == kTIssuerWarp) tmem_dealloc<256>(tmem);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -747,6 +1114,35 @@ static int gemm_sm_fraction();
 static int gemm_raise_smem() {
     DSVT_RAISE_SMEM(proj_gemm_kernel<true>, Lay<true>::total);
     DSVT_RAISE_SMEM(proj_gemm_kernel<false>, Lay<false>::total);
+    DSVT_RAISE_SMEM(proj_tile_kernel<true>, TLay<true>::total);
+    DSVT_RAISE_SMEM(proj_tile_kernel<false>, TLay<false>::total);
+    return DSVT_OK;
+}
+// DSVT_GEMM_IMPL=persistent selects the resident-weight persistent kernel (A/B runs); default: the single-pass tile kernel
+static bool gemm_persistent() {
+    static const bool v = [] { const char* e = getenv("DSVT_GEMM_IMPL"); return e && e[0] == 'p'; }();
+    return v;
+}
+// One GEMM launch over `n_roles` roles (<= 3): every role is [rows, 192] x [192, 192]^T with its own operands / epilogue.
+static int launch_gemm(const GemmRoles& roles, int n_roles, const int* rows_dev, int rows_host, int max_rows, int max_sets,
+                       int zero_tails, int batch, bool split, cudaStream_t st)
+{
+    { const int rc_attr = gemm_raise_smem(); if (rc_attr != DSVT_OK) return rc_attr; }
+    if (!gemm_persistent()) {
+        const dim3 grid((max_rows + kBM - 1) / kBM, n_roles, batch);
+        const bool ln = roles.r[0].n_ln > 0;       // the LayerNorm epilogue stages the finished tile: 98 KB instead of 80 KB
+        if (split) proj_tile_kernel<true><<<grid, kTThreads, ln ? TLay<true>::total : TLay<true>::plain, st>>>(roles, rows_dev, rows_host, max_rows, max_sets, zero_tails);
+        else proj_tile_kernel<false><<<grid, kTThreads, ln ? TLay<false>::total : TLay<false>::plain, st>>>(roles, rows_dev, rows_host, max_rows, max_sets, zero_tails);
+        DSVT_LAUNCH_CHECK();
+        return DSVT_OK;
+    }
+    // persistent grid: one CTA per SM (divided among the batch), a multiple of the number of roles.
+    // DSVT_GEMM_SM_FRACTION=<percent>: CTAs per launch as a share of the SMs
+    const int per = sm_count() * gemm_sm_fraction() / 100 / batch;
+    const int grid = per >= n_roles ? per / n_roles * n_roles : n_roles;
+    if (split) proj_gemm_kernel<true><<<dim3(grid, batch), kThreadsG, Lay<true>::total, st>>>(roles, n_roles, rows_dev, rows_host, max_rows, max_sets, zero_tails);
+    else proj_gemm_kernel<false><<<dim3(grid, batch), kThreadsG, Lay<false>::total, st>>>(roles, n_roles, rows_dev, rows_host, max_rows, max_sets, zero_tails);
+    DSVT_LAUNCH_CHECK();
     return DSVT_OK;
 }
 
@@ -818,6 +1214,8 @@ int linear_split_launch(const void* blob, int N, int K, float out_mul, bool spli
             for (int r = 0; r < 3; ++r) {
                 const int i = i0 + (r < n_roles ? r : 0);
                 GemmRole& g = roles.r[r];
+        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f;
+                g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f;
                 g.a0 = x + (size_t) j * kC; g.a1 = nullptr; g.lda = x_hi ? k_split : K;
                 g.a0b = x_hi; g.ksplit = x_hi ? k_split : 0; g.ldb = x_hi ? K - k_split : 0;
                 g.add_src = nullptr; g.ld_add = 0; g.cover = nullptr; g.cover_stride = 0;
@@ -829,14 +1227,9 @@ int linear_split_launch(const void* blob, int N, int K, float out_mul, bool spli
                 g.accumulate = j > 0;
                 g.act = j == kb - 1 ? act : 0;
             }
-            const int per = sm_count() * gemm_sm_fraction() / 100;
-            const int grid = per >= n_roles ? per / n_roles * n_roles : n_roles;
             const int zt = (zero_tails && j == 0) ? 1 : 0;
-            if (split)
-                proj_gemm_kernel<true><<<dim3(grid, 1), kThreadsG, Lay<true>::total, st>>>(roles, n_roles, rows_dev, rows_host, max_rows, 1, zt);
-            else
-                proj_gemm_kernel<false><<<dim3(grid, 1), kThreadsG, Lay<false>::total, st>>>(roles, n_roles, rows_dev, rows_host, max_rows, 1, zt);
-            DSVT_LAUNCH_CHECK();
+            const int rc = launch_gemm(roles, n_roles, rows_dev, rows_host, max_rows, 1, zt, 1, split, st);
+            if (rc != DSVT_OK) return rc;
         }
     return DSVT_OK;
 }
@@ -857,6 +1250,7 @@ int linear_split_k_launch(const void* blob, int N, int K, float out_mul, bool sp
     for (int r = 0; r < 3; ++r) {
         const int j = r < kb ? r : 0;
         GemmRole& g = roles.r[r];
+        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f;
         g.a0 = x + (size_t) j * kC; g.a1 = nullptr; g.lda = K;
         g.a0b = nullptr; g.ksplit = 0; g.ldb = 0; g.cover = nullptr; g.cover_stride = 0;
         g.wimg = img + (size_t) j * kWRoleBytes;
@@ -867,14 +1261,39 @@ int linear_split_k_launch(const void* blob, int N, int K, float out_mul, bool sp
         g.accumulate = 0; g.act = 0;
         g.add_src = j == 0 ? add : nullptr; g.ld_add = N;
     }
-    const int per = sm_count() * gemm_sm_fraction() / 100;
-    const int grid = per >= kb ? per / kb * kb : kb;
-    if (split)
-        proj_gemm_kernel<true><<<dim3(grid, 1), kThreadsG, Lay<true>::total, st>>>(roles, kb, rows_dev, 0, max_rows, 1, 0);
-    else
-        proj_gemm_kernel<false><<<dim3(grid, 1), kThreadsG, Lay<false>::total, st>>>(roles, kb, rows_dev, 0, max_rows, 1, 0);
-    DSVT_LAUNCH_CHECK();
-    return DSVT_OK;
+    return launch_gemm(roles, kb, rows_dev, 0, max_rows, 1, 0, 1, split, st);
+}
+
+// [*, K] -> [*, 192] layer (K = 192 or 384) followed by a chain of up to three (residual add + LayerNorm) stages, in ONE
+// kernel: the linear's rows go through the LayerNorms in the epilogue and are stored once (tile kernel only).
+int linear_ln_launch(const void* blob, int K, float out_mul, bool split, const float* x, const int* rows_dev, int max_rows,
+                     int n_ln, const float* const* res, const float* const* gamma, const float* const* beta, float eps,
+                     float* y, int zero_tails, cudaStream_t st)
+{
+    if (gemm_persistent()) {
+        set_last_error("linear + LayerNorm epilogue: not available with DSVT_GEMM_IMPL=persistent");
+        return DSVT_ERR_UNSUPPORTED;
+    }
+    const int kb = K / kC;
+    const uint8_t* img = static_cast<const uint8_t*>(blob);
+    GemmRoles roles;
+    GemmRole& g = roles.r[0];
+    g.a0 = x; g.a1 = nullptr; g.lda = K;
+    g.a0b = nullptr; g.ksplit = 0; g.ldb = 0; g.cover = nullptr; g.cover_stride = 0;
+    g.wimg = img;                                    // K block j's image follows block j-1's: chunks 0 .. 6 kb - 1 are consecutive
+    g.bias = reinterpret_cast<const float*>(img + (size_t) kb * kWRoleBytes);
+    g.out = y; g.ld_out = kC; g.col0 = 0;
+    g.out_mul = out_mul; g.post_mul = 1.0f;
+    g.plan = nullptr; g.plan_stride = 0; g.pad_hi = 0;
+    g.accumulate = 0; g.act = 0; g.add_src = nullptr; g.ld_add = 0;
+    g.kchunks = kb * kNumK; g.n_ln = n_ln; g.ln_eps = eps;
+    for (int s = 0; s < 3; ++s) {
+        g.ln_res[s] = s < n_ln ? res[s] : nullptr;
+        g.ln_gamma[s] = s < n_ln ? gamma[s] : nullptr;
+        g.ln_beta[s] = s < n_ln ? beta[s] : nullptr;
+    }
+    roles.r[1] = roles.r[2] = g;
+    return launch_gemm(roles, 1, rows_dev, 0, max_rows, 1, zero_tails, 1, split, st);
 }
 
 // Device blob: [kRoles][kNumK][hi 12288 | lo 12288] weight images, then bias [kRoles][192] f32.
@@ -990,7 +1409,7 @@ int attention_split_plan(const dsvt_set_attention_params* p, const int* idx, con
 int set_attention_split_fused(const dsvt_set_attention_params* p, const void* split_blob, const float* out_mul,
                               bool split, const float* x, const float* pos, const int* idx, const float* mask,
                               const int* set_num, const int* voxel_num, float* out, const void* plan_in,
-                              void* workspace, size_t workspace_bytes, cudaStream_t st)
+                              void* workspace, size_t workspace_bytes, cudaStream_t st, const AttnNorm* norm)
 {
     int rc = split_check(p);
     if (rc != DSVT_OK) return rc;
@@ -1024,14 +1443,10 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
         plan = own_plan;
     }
     const size_t plan_stride = plan_words(p->max_set_num, p->voxel_num_set, p->max_pillars_num);
-    // persistent grids: one CTA per SM (divided among the batch), a multiple of the number of roles
-    // DSVT_GEMM_SM_FRACTION=<percent> (tuning knob): CTAs per launch as a share of the SMs.  Fewer CTAs amortise the
-    // resident weight image over more row tiles and leave SMs to the kernels of concurrently running frames.
-    const int per_b = sm_count() * gemm_sm_fraction() / 100 / p->batch;
-    const int grid_in = per_b >= 3 ? per_b / 3 * 3 : 3, grid_out = per_b >= 1 ? per_b : 1;
     GemmRoles in_roles, out_roles;
     for (int r = 0; r < 3; ++r) {
         GemmRole& g = in_roles.r[r];
+        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f;
         g.a0 = x;
         g.a1 = r < 2 ? pos : nullptr;
         g.wimg = img + (size_t) r * kWRoleBytes;
@@ -1049,6 +1464,7 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
     }
     {
         GemmRole& g = out_roles.r[0];
+        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f;
         g.a0 = o; g.a1 = nullptr;
         g.wimg = img + (size_t) 3 * kWRoleBytes;
         g.bias = bias + 3 * kC;
@@ -1060,17 +1476,20 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
         g.a0b = nullptr; g.ksplit = 0; g.ldb = 0; g.add_src = nullptr; g.ld_add = 0;
         g.cover = plan_view(const_cast<int*>(plan), p->max_set_num, p->max_pillars_num).vox_su;   // voxels in no set -> 0
         g.cover_stride = plan_stride;
+        if (norm) {                                // out = LayerNorm(attention + residual): norm1(y + x), src/dsvt-ai-trt.cpp:669-676
+            if (gemm_persistent()) {
+                set_last_error("set attention + norm epilogue: not available with DSVT_GEMM_IMPL=persistent");
+                return DSVT_ERR_UNSUPPORTED;
+            }
+            g.n_ln = 1; g.ln_eps = norm->eps;
+            g.ln_res[0] = norm->residual; g.ln_gamma[0] = norm->gamma; g.ln_beta[0] = norm->beta;
+            g.ln_res[1] = g.ln_res[2] = nullptr; g.ln_gamma[1] = g.ln_gamma[2] = nullptr; g.ln_beta[1] = g.ln_beta[2] = nullptr;
+        }
         out_roles.r[1] = out_roles.r[2] = g;
     }
-    if (g_skip_mask & 1) {
-    } else if (split) {
-        proj_gemm_kernel<true><<<dim3(grid_in, p->batch), kThreadsG, Lay<true>::total, st>>>(
-            in_roles, 3, voxel_num, 0, p->max_pillars_num, p->max_set_num, 0);
-    } else {
-        proj_gemm_kernel<false><<<dim3(grid_in, p->batch), kThreadsG, Lay<false>::total, st>>>(
-            in_roles, 3, voxel_num, 0, p->max_pillars_num, p->max_set_num, 0);
-    }
-    DSVT_LAUNCH_CHECK();
+    if (!(g_skip_mask & 1) &&
+        (rc = launch_gemm(in_roles, 3, voxel_num, 0, p->max_pillars_num, p->max_set_num, 0, p->batch, split, st)) != DSVT_OK)
+        return rc;
     if ((rc = stage_mark(1, st)) != DSVT_OK) return rc;
     if (!(g_skip_mask & 2)) switch (p->voxel_num_set) {
         case 24: rc = launch_core<24>(p, qbuf, kvbuf, plan, mask, set_num, o, st); break;
@@ -1079,15 +1498,9 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
     }
     if (rc != DSVT_OK) return rc;
     if ((rc = stage_mark(2, st)) != DSVT_OK) return rc;
-    if (g_skip_mask & 4) {
-    } else if (split) {
-        proj_gemm_kernel<true><<<dim3(grid_out, p->batch), kThreadsG, Lay<true>::total, st>>>(
-            out_roles, 1, voxel_num, 0, p->max_pillars_num, p->max_set_num, p->zero_tails);
-    } else {
-        proj_gemm_kernel<false><<<dim3(grid_out, p->batch), kThreadsG, Lay<false>::total, st>>>(
-            out_roles, 1, voxel_num, 0, p->max_pillars_num, p->max_set_num, p->zero_tails);
-    }
-    DSVT_LAUNCH_CHECK();
+    if (!(g_skip_mask & 4) &&
+        (rc = launch_gemm(out_roles, 1, voxel_num, 0, p->max_pillars_num, p->max_set_num, p->zero_tails, p->batch, split, st)) != DSVT_OK)
+        return rc;
     return stage_mark(3, st);
 }
 

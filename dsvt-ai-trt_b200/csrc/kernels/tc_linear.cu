@@ -141,6 +141,9 @@ int linear_split_launch(const void* blob, int N, int K, float out_mul, bool spli
                         int zero_tails, cudaStream_t st);
 int linear_split_k_launch(const void* blob, int N, int K, float out_mul, bool split, const float* x, const float* add,
                           const int* rows_dev, int max_rows, float* y_parts, cudaStream_t st);
+int linear_ln_launch(const void* blob, int K, float out_mul, bool split, const float* x, const int* rows_dev, int max_rows,
+                     int n_ln, const float* const* res, const float* const* gamma, const float* const* beta, float eps,
+                     float* y, int zero_tails, cudaStream_t st);
 }
 
 struct dsvt_linear_weights {
@@ -278,4 +281,25 @@ extern "C" int dsvt_linear_rows_splitk_launch(const dsvt_linear_weights* w, cons
     DSVT_CHECK_ARG(!(((uintptr_t) x & 31) | ((uintptr_t) y_parts & 15) | ((uintptr_t) add & 15)), "alignment (x 32 B, y / add 16 B)");
     return dsvt::linear_split_k_launch(w->split_blob, w->N, w->K, w->out_mul, w->precision == DSVT_ATTN_FP32_TC, x, add, rows,
                                        max_rows, y_parts, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dsvt_linear_rows_norm_launch(const dsvt_linear_weights* w, const float* x, const int32_t* rows, int32_t max_rows,
+                                            const dsvt_ln_stage* stages, int32_t n_stages, float eps, float* y,
+                                            int32_t zero_tails, dsvt_stream_t stream)
+{
+    DSVT_CHECK_ARG(w && x && y && rows && stages && max_rows >= 1, "NULL argument");
+    DSVT_CHECK_ARG(w->split_blob != nullptr, "built for precision DSVT_ATTN_FP32_TC / DSVT_ATTN_FP16_GEMM weights only");
+    DSVT_CHECK_ARG(w->N == 192 && (w->K == 192 || w->K == 384), "linear + LayerNorm chain: N == 192, K in {192, 384}");
+    DSVT_CHECK_ARG(n_stages >= 1 && n_stages <= 3, "1..3 LayerNorm stages");
+    DSVT_CHECK_ARG(!(((uintptr_t) x & 31) | ((uintptr_t) y & 15)), "alignment (x 32 B, y 16 B)");
+    const float* res[3] = {nullptr, nullptr, nullptr};
+    const float* gamma[3] = {nullptr, nullptr, nullptr};
+    const float* beta[3] = {nullptr, nullptr, nullptr};
+    for (int s = 0; s < n_stages; ++s) {
+        DSVT_CHECK_ARG(stages[s].gamma && stages[s].beta, "NULL gamma / beta");
+        DSVT_CHECK_ARG(!(((uintptr_t) stages[s].residual | (uintptr_t) stages[s].gamma | (uintptr_t) stages[s].beta) & 15), "16-B alignment");
+        res[s] = stages[s].residual; gamma[s] = stages[s].gamma; beta[s] = stages[s].beta;
+    }
+    return dsvt::linear_ln_launch(w->split_blob, w->K, w->out_mul, w->precision == DSVT_ATTN_FP32_TC, x, rows, max_rows,
+                                  n_stages, res, gamma, beta, eps, y, zero_tails, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -21,6 +21,10 @@ kernel (dsvt_linear_rows_launch), so a DSVT block becomes a real data flow from 
     "graph": FC 192->384 -> GeluPlugin -> FC 384->192        (the reference graph's three nodes)
     "fused": FC 192->384 with the GELU in its epilogue -> FC 384->192 in split-K form with the residual add behind the FFN
              in its epilogue (one pass less over the 384-wide rows, one launch instead of two accumulating ones)
+    "epilogue": the LayerNorms move into the GEMM epilogues as well -- norm1(attention + x) into the attention's
+             out-projection (dsvt_set_attention_fused_norm_launch), the two / three LayerNorms behind the FFN into the
+             second FFN linear (dsvt_linear_rows_norm_launch, K = 384 in one pass): 5 kernels per encoder layer, the
+             attention output and the FFN output never reach memory
 
 The linear layers stand for TensorRT FullyConnected layers, which have no zero-tail contract (the engine computes all
 max_pillars rows; rows beyond the valid count hold bias-only values there and are never read by a plugin): they are launched
@@ -164,11 +168,12 @@ class HotPathFrame:
 
     def __init__(self, cfg, weights, precision=capi.DSVT_ATTN_FP32, seed=0, device="cuda", fuse_ln=True, share_plans=True,
                  ffn="off", skip=(), zero_tails=1, backbone=False):
-        assert ffn in ("off", "graph", "fused")
+        assert ffn in ("off", "graph", "fused", "epilogue")
         assert not backbone or ffn != "off", "backbone=True runs every layer: it needs the FFN linears on"
         self.backbone = backbone
         # diagnostic only (tools/ablate.py): plugin groups left out of the launch sequence to measure their marginal
-        # cost with several frames in flight -- {"vox", "smax", "part", "plan", "attn", "ln", "gelu", "m2b", "fbox"}
+        # cost with several frames in flight -- {"vox", "smax", "part", "plan", "attn", "ln", "gelu", "m2b", "fbox"} and, for the
+        # backbone3d frame, {"pfn", "pos", "ln1", "ffn1", "ffn2", "lnc"}
         self.skip = frozenset(skip)
         # 1 = the reference's contract (every output zero beyond its valid count, as its per-enqueue memsets leave it);
         # 0 = rows beyond the counts are left untouched (no consumer in the graph reads them) -- bench "relaxed_tails" leg only
@@ -238,7 +243,9 @@ class HotPathFrame:
             pfn_out = self.w.pfn_out[k]
             if self.backbone:                                                       # the PFN layer in front of the scatter-max
                 g = w.glue
-                if k == 0:
+                if "pfn" in skip:
+                    pfn_out = self.pfn0_out if k == 0 else self.pfn1_out
+                elif k == 0:
                     pfn_out = g["pfn0"](vox.point_features[0], vox.point_num, activation=2, out=self.pfn0_out, zero_tails=0)
                 else:
                     pfn_out = g["pfn1"].rows_concat(self.pfn0_out, self.max_point[0], vox.point_num, activation=2,
@@ -262,7 +269,7 @@ class HotPathFrame:
         else:
             x = self.max_voxel[-1]                         # VFE output: per-pillar max of PFN layer 1 (:589, output 1)
             pos = self.pos_out
-            for blk in range(cfg.num_blocks):              # pos_embed[blk][i] from the shift-i window coordinates (:603-637)
+            for blk in range(0 if "pos" in skip else cfg.num_blocks):   # pos_embed[blk][i] from the shift-i window coordinates (:603-637)
                 for enc in (0, 1):
                     first, second = w.glue["pos"][blk][enc]
                     first(self.wp[enc].coors_in_win_x_y[0], V, activation=2, out=self.pos_hidden, zero_tails=0)
@@ -271,18 +278,23 @@ class HotPathFrame:
             gs = self.gs[blk % 2]                      # blocks 0,2: 12x12 windows; 1,3: 24x24 shifted (:654-:1018)
             x_in = x
             for enc in (0, 1):
+                epi = self.ffn == "epilogue"
                 if "attn" not in skip:
                     capi.set_attention_fused(w.attn[blk * 2 + enc], x, pos[blk][enc], gs.global_index_in_set[0],
-                                             gs.mask_expand_0[0], gs.set_num, V, axis=enc, out=self.attn_out,
+                                             gs.mask_expand_0[0], gs.set_num, V, axis=enc,
+                                             out=self.src if epi else self.attn_out,
                                              precision=self.precision, workspace=self.attn_ws,
-                                             plan=self.plans.get((blk % 2, enc)), zero_tails=zt)
+                                             plan=self.plans.get((blk % 2, enc)), zero_tails=zt,
+                                             norm=(x, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps) if epi else None)
                 if "ln" in skip:
                     ln += 3 if enc == 0 else 4
                     if "gelu" not in skip:
                         capi.gelu(self.ffn_hidden, V, out=self.gelu_out, zero_tails=zt)
                     continue
-                capi.layer_norm(self.attn_out, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=x,
-                                out=self.src, zero_tails=zt); ln += 1                      # norm1(y + x)   :669-676
+                if "ln1" not in skip and not epi:
+                    capi.layer_norm(self.attn_out, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=x,
+                                    out=self.src, zero_tails=zt)                           # norm1(y + x)   :669-676
+                ln += 1
                 ffn_out = None
                 if self.ffn == "off":
                     ffn_out = self.ffn_out
@@ -293,8 +305,19 @@ class HotPathFrame:
                     if self.ffn == "graph":
                         fc1.rows(self.src, V, out=self.ffn_h, zero_tails=0)               # :513  FC 192->384
                         capi.gelu(self.ffn_h, V, out=self.gelu_out, zero_tails=zt)         # :519  GeluPlugin
-                    else:
+                    elif "ffn1" not in skip:
                         fc1.rows(self.src, V, activation=1, out=self.gelu_out, zero_tails=0)   # FC + GELU epilogue
+                    if epi:
+                        # FC 384->192 (one pass over K) + norm2(src + src2) + norm(src + x) [+ the block's residual norm]
+                        stages = [(self.src, w.gamma[ln], w.beta[ln]), (x, w.gamma[ln + 1], w.beta[ln + 1])]
+                        ln += 2
+                        if enc == 1:
+                            stages.append((x_in, w.gamma[ln], w.beta[ln])); ln += 1
+                        nxt = self.x_a if enc == 0 else self.blk_out[blk % 2]
+                        if "ffn2" not in skip:
+                            fc2.rows_norm(self.gelu_out, V, stages, cfg.layer_norm_eps, out=nxt, zero_tails=zt)
+                        x = nxt
+                        continue
                     if self.ffn == "graph":
                         ffn_out = fc2.rows(self.gelu_out, V, out=self.ffn_o, zero_tails=0)   # :524  FC 384->192
                 nxt = self.x_a if enc == 0 else self.x_b
@@ -302,7 +325,7 @@ class HotPathFrame:
                 if self.ffn == "fused" and "ln" not in skip:
                     # FC 384->192 in split-K form: ONE launch, part 0 = first K block + bias + src (the residual add behind
                     # the FFN folded into the epilogue), part 1 = second K block; norm2 sums them
-                    parts = fc2.rows_splitk(self.gelu_out, V, add=self.src, out=self.ffn_parts)
+                    parts = self.ffn_parts if "ffn2" in skip else fc2.rows_splitk(self.gelu_out, V, add=self.src, out=self.ffn_parts)
                     ln_in, ffn_out = parts[0], parts[1]
                 if not self.fuse_ln:
                     capi.layer_norm(ln_in, V, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps, residual=ffn_out,
@@ -318,8 +341,9 @@ class HotPathFrame:
                     ln += 2
                     if enc == 1:
                         stages.append((x_in, w.gamma[ln], w.beta[ln])); ln += 1
-                    capi.layer_norm_chain(ln_in, V, stages, cfg.layer_norm_eps,
-                                          out=nxt if enc == 0 else self.blk_out[blk % 2], zero_tails=zt)
+                    if "lnc" not in skip:
+                        capi.layer_norm_chain(ln_in, V, stages, cfg.layer_norm_eps,
+                                              out=nxt if enc == 0 else self.blk_out[blk % 2], zero_tails=zt)
                 x = nxt
             x = self.blk_out[blk % 2]
         self.final = x

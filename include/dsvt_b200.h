@@ -291,6 +291,20 @@ int dsvt_set_attention_fused_planned_launch(const dsvt_set_attention_params* p, 
                                             float* out, const void* plan, void* workspace, size_t workspace_bytes,
                                             dsvt_stream_t stream);
 
+/*
+ * The fused form followed by the encoder layer's first residual add + LayerNorm in the same launch sequence:
+ *   out = LayerNorm(attention(x, pos) + residual) * gamma + beta      (norm1(src2 + src), src/dsvt-ai-trt.cpp:669-676;
+ * addElementWise(kSUM) + LayerNormPlugin) -- the LayerNorm runs in the out-projection's epilogue, the attention output
+ * itself never reaches memory.  GEMM-pipeline precisions only; plan may be NULL (rebuilt per call).  residual
+ * [B,max_pillars_num,C], gamma / beta [C] on the device.  Arithmetic of the LayerNorm = dsvt_layer_norm_launch.
+ */
+int dsvt_set_attention_fused_norm_launch(const dsvt_set_attention_params* p, const dsvt_attention_weights* w,
+                                         const float* x, const float* pos, const int32_t* global_index_in_set,
+                                         const float* mask, const int32_t* set_num, const int32_t* voxel_num,
+                                         const float* residual, const float* gamma, const float* beta, float eps,
+                                         float* out, const void* plan, void* workspace, size_t workspace_bytes,
+                                         dsvt_stream_t stream);
+
 /* ------------------------------------------------------------------------ *
  * (next #4) dense linear layer  y = x * W^T + b on tcgen05 -- replaces the TensorRT FullyConnected
  * layers next to the plugins (fullyConnected_gelu_fullyConnected, src/dsvt-ai-trt.cpp:494-529).
@@ -331,6 +345,16 @@ int dsvt_linear_rows_concat_launch(const dsvt_linear_weights* w, const float* x_
  */
 int dsvt_linear_rows_splitk_launch(const dsvt_linear_weights* w, const float* x, const float* add, const int32_t* rows,
                                    int32_t max_rows, float* y_parts, dsvt_stream_t stream);
+
+/*
+ * A [*, K] -> [*, 192] layer (K = 192 or 384: the FFN's second linear) followed by up to three (residual add + LayerNorm)
+ * stages in ONE kernel:  y0 = x W^T + b;  y = LN_s(y + stages[s].residual) for s < n_stages  -- the kSUM + LayerNormPlugin
+ * pairs behind the FFN (norm2(src + src2), norm(src + x), the block's residual norm; src/dsvt-ai-trt.cpp:685-697, :750-756).
+ * Rows beyond `rows` are zero-filled when zero_tails.  Same arithmetic per stage as dsvt_layer_norm_chain_launch.
+ */
+int dsvt_linear_rows_norm_launch(const dsvt_linear_weights* w, const float* x, const int32_t* rows, int32_t max_rows,
+                                 const dsvt_ln_stage* stages, int32_t n_stages, float eps, float* y, int32_t zero_tails,
+                                 dsvt_stream_t stream);
 
 /*
  * Narrow first layers of the VFE / position-embedding MLPs (TensorRT FullyConnected + Scale + ReLU in the reference:

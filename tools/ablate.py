@@ -19,7 +19,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--frames", type=int, default=16)
     ap.add_argument("--streams", type=int, default=8)
-    ap.add_argument("--groups", default="vox,smax,part,plan,attn,attn_qkv,attn_core,attn_out,ln,gelu,m2b,fbox")
+    ap.add_argument("--groups", default="vox,pfn,smax,part,plan,pos,attn,attn_qkv,attn_core,attn_out,ln1,ffn1,ffn2,lnc,m2b,fbox")
+    ap.add_argument("--kind", default="backbone3d", help="bench.FRAME_KINDS key")
     args = ap.parse_args()
     os.environ.setdefault("DSVT_GEMM_SM_FRACTION", "50")
     import torch
@@ -32,7 +33,7 @@ def main():
     streams = [torch.cuda.Stream() for _ in range(args.streams)]
     slots = []
     for i in range(args.frames):
-        s = bench.Slot(pipeline, cfg, weights, capi.DSVT_ATTN_FP32_TC, pkg.synth.ring_lidar(bench.N_POINTS, seed=i), i)
+        s = bench.Slot(pipeline, cfg, weights, capi.DSVT_ATTN_FP32_TC, pkg.synth.ring_lidar(bench.N_POINTS, seed=i), i, kind=args.kind)
         s.frame.run()              # every buffer holds a valid frame before groups are left out
         slots.append(s)
     torch.cuda.synchronize()

@@ -1,0 +1,35 @@
+"""Phase timestamps (SM cycles) of ONE CTA (tile 20, role 0) of the single-pass tile GEMM on the bench's frame 0, for each
+of its uses.  Needs the profile build:
+    make -C dsvt-ai-trt_b200/csrc OUT=$PWD/dsvt-ai-trt_b200/lib_prof EXTRA_DEFS=-DDSVT_PROFILE
+    DSVT_B200_LIBDIR=$PWD/dsvt-ai-trt_b200/lib_prof python tools/tile_profile.py
+"""
+import ctypes, importlib, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+pkg = importlib.import_module("dsvt-ai-trt_b200"); capi = importlib.import_module("dsvt-ai-trt_b200.capi")
+pipeline = importlib.import_module("dsvt-ai-trt_b200.pipeline")
+cfg = pkg.config.WAYMO
+w = pipeline.FrameWeights(cfg, seed=0)
+f = pipeline.HotPathFrame(cfg, w, precision=capi.DSVT_ATTN_FP32_TC, ffn="fused", backbone=True)
+f.load_points(pkg.synth.ring_lidar(200000, seed=0))
+f.run(); f.run(); torch.cuda.synchronize()
+V = f.vox.pillar_num
+fc1, fc2 = w.ffn[0]
+first, second = w.glue["pos"][0][0]
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+lab = {0: "start", 1: "setup done (barriers, TMEM)", 8: "producer: all chunks staged", 9: "accumulators complete", 10: "slab 0 stored",
+       11: "slab 1 stored", 12: "slab 2 stored", 13: "CTA end"}
+for kc in range(6):
+    lab[2 + kc] = f"producer: chunk {kc} staged"; lab[14 + kc] = f"issuer: W chunk {kc} landed"; lab[20 + kc] = f"issuer: A chunk {kc} full"
+def show(title, fn):
+    flush.zero_(); torch.cuda.synchronize()
+    fn(); torch.cuda.synchronize()
+    buf = (ctypes.c_longlong * 64)()
+    capi._lib().dsvt_debug_split_profile(buf)
+    t = np.array(buf[:], dtype=np.int64)
+    print(title)
+    for i in sorted(lab, key=lambda i: t[i]):
+        print(f"  {lab[i]:34s} t={t[i]-t[0]:7d}")
+show("pos-embed linear 2 (192->192, cold L2):", lambda: second.rows(f.pos_hidden, V, out=f.pos_out[0][0], zero_tails=0))
+show("FFN linear 1 + GELU (192->384):", lambda: fc1.rows(f.src, V, activation=1, out=f.gelu_out, zero_tails=0))
+show("FFN linear 2 split-K (+ residual):", lambda: fc2.rows_splitk(f.gelu_out, V, add=f.src, out=f.ffn_parts))
