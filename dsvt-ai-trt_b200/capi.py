@@ -527,6 +527,19 @@ class SmallLinear:
             pass
 
 
+def pos_embed_mlp(first, second, x2, rows, out=None, zero_tails=1):
+    """Position-embedding MLP Linear(2->192)+BN+ReLU -> Linear(192->192) in one kernel (dsvt_pos_embed_mlp_launch):
+    first = SmallLinear(2 -> 192), second = Linear(192 -> 192, FP32_TC / FP16_GEMM); x2 [max_rows, 2]."""
+    _need(x2, torch.float32, "x2")
+    _need(rows, torch.int32, "rows")
+    max_rows = x2.shape[-2]
+    out = torch.empty(max_rows, 192, dtype=torch.float32, device=x2.device) if out is None else out
+    _check(_lib().dsvt_pos_embed_mlp_launch(c_void_p(first.handle), c_void_p(second.handle), _ptr(x2), _ptr(rows),
+                                            c_int32(max_rows), _ptr(out), c_int32(zero_tails), _stream()),
+           "dsvt_pos_embed_mlp_launch")
+    return out
+
+
 class ScatterMaxParams(Structure):
     _fields_ = [("batch", c_int32), ("max_points_num", c_int32), ("max_pillars_num", c_int32), ("feature_num", c_int32),
                 ("max_num_points_per_voxel", c_int32), ("zero_tails", c_int32)]

@@ -68,14 +68,11 @@ template <bool SPLIT> struct Lay {
 // Per batch item, in ints (each array padded to 64): hdr[64] (hdr[0] = T, number of distinct tokens) |
 // set_off[max_sets + 1] (exclusive prefix of tokens per set) | nu[max_sets] | order[max_sets] (sets by descending token
 // count: the core kernel starts the longest sets first) | vox_su[max_pillars] (voxel -> set * 64 + u,
-// -1 if the voxel is in no set) | tile_set[max_sets + 1]: first set of every TOKEN TILE of the fused kernel -- consecutive
-// whole sets packed greedily into tiles of at most 128 tokens (hdr[1] = number of tiles; tile t = sets
-// [tile_set[t], tile_set[t + 1])) | tok[max_sets * S] as int2 (voxel row, slot) of the u-th distinct token of each set.
+// -1 if the voxel is in no set) | tok[max_sets * S] as int2 (voxel row, slot) of the u-th distinct token of each set.
 __host__ __device__ inline size_t pad64(size_t n) { return (n + 63) & ~(size_t) 63; }
-struct PlanView { int* hdr; int* set_off; int* nu; int* order; int* vox_su; int2* tok; int* tile_set; };
+struct PlanView { int* hdr; int* set_off; int* nu; int* order; int* vox_su; int2* tok; };
 __host__ __device__ inline size_t plan_words(int max_sets, int S, int max_pillars) {
-    return 64 + pad64((size_t) max_sets + 1) + 2 * pad64(max_sets) + pad64(max_pillars) + pad64((size_t) 2 * max_sets * S) +
-           pad64((size_t) max_sets + 1);
+    return 64 + pad64((size_t) max_sets + 1) + 2 * pad64(max_sets) + pad64(max_pillars) + pad64((size_t) 2 * max_sets * S);
 }
 __host__ __device__ inline PlanView plan_view(int* base, int max_sets, int max_pillars) {
     PlanView v;
@@ -84,8 +81,7 @@ __host__ __device__ inline PlanView plan_view(int* base, int max_sets, int max_p
     v.nu = v.set_off + pad64((size_t) max_sets + 1);
     v.order = v.nu + pad64(max_sets);
     v.vox_su = v.order + pad64(max_sets);
-    v.tile_set = v.vox_su + pad64(max_pillars);
-    v.tok = reinterpret_cast<int2*>(v.tile_set + pad64((size_t) max_sets + 1));
+    v.tok = reinterpret_cast<int2*>(v.vox_su + pad64(max_pillars));
     return v;
 }
 
@@ -110,6 +106,11 @@ struct GemmRole {
     const float* a0b;       // optional second source of the A operand: columns >= ksplit of the K block come from a0b
     int ksplit, ldb;        //   (the PFN's concatenation [point features | per-pillar max], src/dsvt-ai-trt.cpp:583-587,
                             //   read in place instead of being materialised); ksplit is a multiple of 32, a0b == nullptr: off
+    // generated A operand (tile kernel only): row = relu((x2 W1^T) * scale + shift), the narrow first layer of a position-
+    // embedding MLP (Linear(2 -> 192) + BatchNorm1d + ReLU, src/dsvt-ai-trt.cpp:461-492) evaluated by the producers instead of
+    // being read back from memory.  gen_x [rows, 2]; gen_blob = W1 [192][2] | scale [192] | shift [192] (dsvt_small_linear)
+    const float* gen_x;
+    const float* gen_blob;
     int kchunks;            // K / 32 (tile kernel only): 6, or 12 for a K = 384 layer whose two weight blocks are consecutive
     // LayerNorm-chain epilogue (tile kernel only, N == 192, no plan): the finished row y0 = acc * out_mul + bias goes through
     //   y = LN_s(y + ln_res[s]) for s < n_ln  (the addElementWise(kSUM) + LayerNormPlugin pairs that follow the attention's
@@ -159,15 +160,10 @@ __device__ long long g_split_prof[64];
 #define SP(i) do { if (blockIdx.x == 3 && blockIdx.y == 0) g_split_prof[(n_roles == 1 ? 40 : 0) + (i)] = clock64(); } while (0)
 #define CP(i) do { if (blockIdx.x == 5 && blockIdx.y == 0 && threadIdx.x == 0) g_split_prof[32 + i] = clock64(); } while (0)
 #define TP(i) do { if (blockIdx.x == 20 && blockIdx.y == 0) g_split_prof[(i)] = clock64(); } while (0)
-// fused kernel: thread-0-of-role interval sums over all units of CTA 7: FA(slot, t_prev) adds clock64() - t_prev and restarts t_prev
-#define FA(i, tp) do { if (blockIdx.x == 7 && blockIdx.y == 0) { const long long now__ = clock64(); g_split_prof[(i)] += now__ - (tp); (tp) = now__; } } while (0)
-#define FP(i) do { } while (0)
 #else
 #define SP(i) do { } while (0)
 #define CP(i) do { } while (0)
 #define TP(i) do { } while (0)
-#define FP(i) do { } while (0)
-#define FA(i, tp) do { } while (0)
 #endif
 
 // Persistent: grid = (n_roles * ctas_per_role, batch).  A CTA owns ONE role: its 147 KB weight image (hi + lo) is copied
@@ -499,6 +495,7 @@ proj_tile_kernel(const __grid_constant__ GemmRoles roles, const int* __restrict_
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t w_full[kTWStages], w_empty[kTWStages], a_full[kTStages], s_empty[kTStages], acc_full;
     __shared__ uint32_t tmem_slot;
+    __shared__ float4 s_gen[kC];                     // per column (w0, w1, scale, shift) of a generated A operand
     using L = TLay<SPLIT>;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -529,6 +526,10 @@ proj_tile_kernel(const __grid_constant__ GemmRoles roles, const int* __restrict_
         fence_barrier_init();
     }
     if (warp == kTIssuerWarp) tmem_alloc<256>(&tmem_slot);
+    if (g.gen_x)
+        for (int t = tid; t < kC; t += kTThreads)
+            s_gen[t] = make_float4(__ldg(g.gen_blob + 2 * t), __ldg(g.gen_blob + 2 * t + 1), __ldg(g.gen_blob + 2 * kC + t),
+                                   __ldg(g.gen_blob + 3 * kC + t));
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -542,9 +543,28 @@ proj_tile_kernel(const __grid_constant__ GemmRoles roles, const int* __restrict_
         const int n_steps = g.kchunks * 2;                      // a multiple of 12
         const int rl = warp * 8 + (lane & 7), c16 = lane >> 3;
         float buf[kDepth][16];                                  // [0..7] = a0 row piece, [8..15] = a1 (pos) row piece
+        const float* gen_x = g.gen_x ? g.gen_x + (size_t) b * max_pillars * 2 : nullptr;
+        float2 gxy[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};      // the two rows of this thread (half 0 / 1)
+        if (gen_x) {
+#pragma unroll
+            for (int hf2 = 0; hf2 < 2; ++hf2)
+                if (row_base + hf2 * 64 + rl < V) gxy[hf2] = __ldg(reinterpret_cast<const float2*>(gen_x) + row_base + hf2 * 64 + rl);
+        }
         auto issue = [&](int s, float (&d)[16]) {
             const int kc = s >> 1, row = row_base + (s & 1) * 64 + rl;
-            if (row < V) {
+            if (row < V && gen_x) {               // same arithmetic as small_linear_kernel<2>: FC, Scale (folded BatchNorm), ReLU
+                const int col = kc * kBK + c16 * 8;
+                const float2 xy = gxy[s & 1];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float4 wv = s_gen[col + e];
+                    float acc = fmaf(xy.x, wv.x, 0.f);
+                    acc = fmaf(xy.y, wv.y, acc);
+                    acc = fmaf(acc, wv.z, wv.w);
+                    d[e] = fmaxf(acc, 0.f);
+                    d[8 + e] = 0.f;
+                }
+            } else if (row < V) {
                 const int col = kc * kBK + c16 * 8;
                 if (a0b && col >= g.ksplit) ldg256(a0b + (size_t) row * g.ldb + (col - g.ksplit), &d[0]);
                 else ldg256(a0 + (size_t) row * g.lda + col, &d[0]);
@@ -795,7 +815,7 @@ proj_tile_kernel(const __grid_constant__ GemmRoles roles, const int* __restrict_
         // =========================== WEIGHT-CHUNK COPIES =================================================
         const int nrows = V - row_base < kBM ? V - row_base : kBM;
         if (lane == 0) {
-            if (g.lda == kC) {       // the tile's rows are one contiguous block: pull them into L2 as large sequential requests
+            if (g.lda == kC && !g.gen_x) {   // the tile's rows are one contiguous block: pull them into L2 as large sequential requests
                 const uint32_t bytes = (uint32_t) (nrows * kC * sizeof(float));
                 l2_prefetch(a0 + (size_t) row_base * kC, bytes);
                 if (a1) l2_prefetch(a1 + (size_t) row_base * kC, bytes);
@@ -895,28 +915,6 @@ attn_plan_scan_kernel(const int* __restrict__ set_num, int* __restrict__ plan, s
     }
     __syncthreads();
     for (int i = threadIdx.x; i < ns; i += 1024) pv.order[atomicAdd(&bucket[min(pv.nu[i], 64)], 1)] = i;
-
-    // Token tiles of the fused kernel: greedy next-fit of whole sets into tiles of <= 128 tokens.  nxt[s] = first set that
-    // no longer fits into a tile starting at set s (found in parallel by bisection over the prefix sums); thread 0 then
-    // walks the chain -- one step per TILE, not per set.
-    extern __shared__ int nxt[];                       // [ns]
-    __syncthreads();                                   // set_off[] of this CTA's earlier global stores
-    for (int i = threadIdx.x; i < ns; i += 1024) {
-        const int lim = pv.set_off[i] + 128;           // a tile holds tokens [set_off[i], lim)
-        int lo = i + 1, hi = ns;                        // largest e in (i, ns] with set_off[e] <= lim (e = i + 1 always fits: S <= 64)
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (pv.set_off[mid] <= lim) lo = mid; else hi = mid - 1;
-        }
-        nxt[i] = lo;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-        for (int sidx = 0; sidx < ns; sidx = nxt[sidx]) pv.tile_set[t++] = sidx;
-        pv.tile_set[t] = ns;
-        pv.hdr[1] = t;
-    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1098,405 +1096,6 @@ attn_core_kernel(const float* __restrict__ qbuf, const float* __restrict__ kvbuf
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// FUSED QKV projection + per-set attention core (DSVT_ATTN_FP32_TC / DSVT_ATTN_FP16_GEMM, the product path).
-//
-// Replaces  proj GEMM (roles Q, K, V) -> q / kv workspace -> attn_core_kernel  by one kernel; what it removes is the
-// 284 MB per call (30.8 k voxels) that the three projections write and the core reads back.
-//
-// Work unit = (token tile, head group): a tile is up to 128 TOKENS of consecutive whole sets in the plan's token order
-// (plan tile table), a head group is 4 of the 8 heads.  Per unit, warp-specialised and pipelined ACROSS units:
-//   warps 8-15   producers : gather the tile's rows x[vox], pos[vox] (768-byte rows, the plan's token -> voxel map), form
-//                            A_qk = x + pos and A_v = x as FP16 hi/lo UMMA chunks, one K16 step per ring stage; one of them
-//                            also issues the step's weight copy ([Wq_hg | Wk_hg | Wv_hg] x 16 k, hi | lo, 18 KB)
-//                issuer    : the first producer thread, after staging its piece of a step:  D_qk[128 x 192] += A_qk W_qk^T  and
-//                            D_v[128 x 96] += A_v W_v^T  (3 MMAs each in the split mode) into tensor memory (288 columns).
-//                            (A 17th warp for it would cap the kernel at 96 registers per thread -- 5 warps on one scheduler --
-//                            and the two-query core then spills into an L1 that the 218 KB of shared memory leave 10 KB of.)
-//   warps 0-7    core      : thread = (token row pair, head): the Q rows go to registers, the K / V rows (+ bias) to a
-//                            shared-memory tile, the accumulators are handed back, then scores + key mask -> online softmax
-//                            (log2 domain, chunks of 4 keys) -> PV over the keys of the rows' set in FP32 (FFMA2, every K / V
-//                            piece feeds two queries), all operands on chip; 24 output channels of o[voxel] per query.
-// While the core warps work on unit n the producers / issuer run unit n + 1.  Shared memory: ring 3 x 34 KB | K/V tile 102 KB
-// | 3 metadata slots; 1 CTA per SM, persistent over units (unit u -> CTA u mod grid).
-constexpr int kFStages = 3;
-constexpr int kFSteps = kC / 16;                       // 12 K16 steps
-constexpr int kFWRows = 3 * 96;                        // [Wq_hg | Wk_hg | Wv_hg]
-constexpr int kFATerm = kBM * 16 * 2;                  // 4096: one precision term of one A operand, one step
-constexpr int kFWTerm = kFWRows * 16 * 2;              // 9216
-constexpr int kFWChunk = 2 * kFWTerm;                  // weight image per (head group, step): hi | lo
-constexpr int kFWImgBytes = 2 * kFSteps * kFWChunk;    // 442368 per layer
-constexpr int kFKvTok = 816;                           // bytes per token of the K/V tile: K 384 | 16 | V 384 | 32 (51 x 16 B: odd)
-constexpr int kFKvV = 400;
-constexpr int kFCoreThreads = 256, kFProdThreads = 256;
-constexpr int kFIssuerWarp = 8;                        // the first producer warp: TMEM allocation; its lane 0 also issues the MMAs
-constexpr int kFThreads = 16 * 32;                     // 4 warps per scheduler: 128 registers per thread, no spills into the 10 KB L1
-constexpr int kFMetaSlot = kBM * 4 + kBM * 4 + 4 * kBM * 4;    // vrow | (lo, hi) | cmask[4][128]
-template <bool SPLIT> struct FLay {
-    static constexpr int terms = SPLIT ? 2 : 1;
-    static constexpr int a_bytes = 2 * terms * kFATerm;        // A_qk terms | A_v terms
-    static constexpr int w_bytes = terms * kFWTerm;
-    static constexpr int stage = a_bytes + w_bytes;            // 34816 / 17408
-    static constexpr int kv = kFStages * stage;
-    static constexpr int meta = kv + kBM * kFKvTok;
-    static constexpr int total = meta + 3 * kFMetaSlot;        // 218112 / 165888
-};
-struct FusedArgs {
-    const float* x; const float* pos;          // [B, max_pillars, 192]
-    const uint8_t* wimg;                       // [2 head groups][12 steps][hi | lo]
-    const float* bias;                         // [3][192]: b_q | b_k | b_v
-    float out_mul[3];                          // undoes the weight pre-scaling per role
-    float q_scale;                             // 1 / sqrt(24), applied after the biased projection
-    const int* plan; size_t plan_stride;
-    const float* mask;                         // [B, max_sets, 8, S]
-    const int* set_num;
-    float* o;                                  // [B, max_pillars, 192] attention output, voxel order
-    int max_sets, max_pillars, S;
-};
-
-template <bool SPLIT>
-__global__ void __launch_bounds__(kFThreads, 1)
-qkv_core_kernel(const __grid_constant__ FusedArgs A)
-{
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t w_full[kFStages], a_full[kFStages], s_empty[kFStages], acc_full, acc_empty, meta_full[3];
-    __shared__ uint32_t tmem_slot;
-    using L = FLay<SPLIT>;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.y;
-    const PlanView pv = plan_view(const_cast<int*>(A.plan) + (size_t) b * A.plan_stride, A.max_sets, A.max_pillars);
-    const int n_units = 2 * pv.hdr[1];
-    const int cnt = n_units > (int) blockIdx.x ? (n_units - (int) blockIdx.x + (int) gridDim.x - 1) / (int) gridDim.x : 0;
-    if (cnt == 0) return;
-#ifdef DSVT_PROFILE
-    if (blockIdx.x == 7 && blockIdx.y == 0 && threadIdx.x == 0) { g_split_prof[30] = cnt; g_split_prof[31] = clock64(); }
-#endif
-
-    if (tid == 0) {
-        for (int s = 0; s < kFStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&a_full[s], kFProdThreads); mbar_init(&s_empty[s], 1); }
-        for (int s = 0; s < 3; ++s) mbar_init(&meta_full[s], kFProdThreads);
-        mbar_init(&acc_full, 1);
-        mbar_init(&acc_empty, 8);
-        fence_barrier_init();
-    }
-    if (warp == kFIssuerWarp) tmem_alloc<512>(&tmem_slot);
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem = tmem_slot;
-
-    if (warp < 8) {
-        // =========================== CORE: thread = (two consecutive token rows, one head of the group) ====
-        // warp = (TMEM lane quarter q4, head pair hp); even lanes own head 2 hp, odd lanes head 2 hp + 1, both for the row pair
-        // (lane & ~1, lane | 1) of the quarter: every K / V piece read from shared memory feeds TWO queries (the per-set core
-        // is bound by shared-memory bandwidth: one query per read moves 2.4 MB per unit through the 128 B/clk pipe).
-        const int q4 = warp & 3, hp = warp >> 2, hsel = lane & 1, hh = 2 * hp + hsel;
-        const int my_row = q4 * 32 + lane, r0 = q4 * 32 + (lane & ~1), r1 = r0 + 1;
-        const uint32_t tl = tmem + ((uint32_t) (q4 * 32) << 16);
-        float* o = A.o + (size_t) b * A.max_pillars * kC;
-        uint8_t* kv = smem + L::kv;
-        long long tp = clock64();
-        (void) tp;
-#pragma unroll 1
-        for (int n = 0; n < cnt; ++n) {
-            const int unit = blockIdx.x + n * gridDim.x, hg = unit & 1, slot = n % 3;
-            mbar_wait(&meta_full[slot], (n / 3) & 1);
-            const int* m_vrow = reinterpret_cast<const int*>(smem + L::meta + slot * kFMetaSlot);
-            const uint32_t* m_rng = reinterpret_cast<const uint32_t*>(m_vrow + kBM);
-            const float* m_cmask = reinterpret_cast<const float*>(m_rng + kBM) + hh * kBM;
-            const uint32_t rng0 = m_rng[r0], rng1 = m_rng[r1];
-            const int vrow0 = m_vrow[r0], vrow1 = m_vrow[r1];
-            if (tid == 0) FA(0, tp);      // metadata wait
-            mbar_wait(&acc_full, n & 1);
-            tc_fence_after_sync();
-            if (tid == 0) FA(1, tp);      // accumulator wait
-            float2 q0[kD / 2], q1[kD / 2];
-            {   // Q rows: each lane drains ITS row for both heads of the pair, keeps the head it owns and swaps the other
-                // with its neighbour: q = (acc * 2^-s + b_q) / sqrt(24)
-                const float om = A.out_mul[0], qs = A.q_scale;
-                float2 keep[kD / 2], send[kD / 2];
-#pragma unroll
-                for (int hd = 0; hd < 2; ++hd) {
-                    uint32_t a[16], c[8];
-                    tmem_ld16(tl + (2 * hp + hd) * kD, a);
-                    tmem_ld8(tl + (2 * hp + hd) * kD + 16, c);
-                    const float4* bq = reinterpret_cast<const float4*>(A.bias + hg * 96 + (2 * hp + hd) * kD);
-                    float4 bb[6];
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) bb[i] = __ldg(bq + i);
-                    tmem_ld_wait();
-                    float2 v[kD / 2];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        v[2 * i] = f2((__uint_as_float(a[4 * i]) * om + bb[i].x) * qs, (__uint_as_float(a[4 * i + 1]) * om + bb[i].y) * qs);
-                        v[2 * i + 1] = f2((__uint_as_float(a[4 * i + 2]) * om + bb[i].z) * qs, (__uint_as_float(a[4 * i + 3]) * om + bb[i].w) * qs);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        v[8 + 2 * i] = f2((__uint_as_float(c[4 * i]) * om + bb[4 + i].x) * qs, (__uint_as_float(c[4 * i + 1]) * om + bb[4 + i].y) * qs);
-                        v[8 + 2 * i + 1] = f2((__uint_as_float(c[4 * i + 2]) * om + bb[4 + i].z) * qs, (__uint_as_float(c[4 * i + 3]) * om + bb[4 + i].w) * qs);
-                    }
-#pragma unroll
-                    for (int i = 0; i < kD / 2; ++i) {
-                        if (hd == hsel) keep[i] = v[i]; else send[i] = v[i];
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < kD / 2; ++i) {
-                    const float rx = __shfl_xor_sync(0xffffffffu, send[i].x, 1), ry = __shfl_xor_sync(0xffffffffu, send[i].y, 1);
-                    // even lane: own row is r0 -> q0 = keep, q1 = neighbour's;  odd lane: own row is r1 -> q1 = keep, q0 = neighbour's
-                    q0[i] = hsel ? f2(rx, ry) : keep[i];
-                    q1[i] = hsel ? keep[i] : f2(rx, ry);
-                }
-            }
-#pragma unroll
-            for (int part = 0; part < 2; ++part) {      // K then V rows (both heads of the pair) of this lane's row -> shared tile
-                const float om = A.out_mul[1 + part];
-#pragma unroll
-                for (int hd = 0; hd < 2; ++hd) {
-                    uint32_t a[16], c[8];
-                    tmem_ld16(tl + (part ? 192 : 96) + (2 * hp + hd) * kD, a);
-                    tmem_ld8(tl + (part ? 192 : 96) + (2 * hp + hd) * kD + 16, c);
-                    const float4* bp = reinterpret_cast<const float4*>(A.bias + (1 + part) * kC + hg * 96 + (2 * hp + hd) * kD);
-                    float4 bb[6];
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) bb[i] = __ldg(bp + i);
-                    tmem_ld_wait();
-                    float4* dst = reinterpret_cast<float4*>(kv + (size_t) my_row * kFKvTok + (part ? kFKvV : 0) + (2 * hp + hd) * 96);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        dst[i] = make_float4(__uint_as_float(a[4 * i]) * om + bb[i].x, __uint_as_float(a[4 * i + 1]) * om + bb[i].y,
-                                             __uint_as_float(a[4 * i + 2]) * om + bb[i].z, __uint_as_float(a[4 * i + 3]) * om + bb[i].w);
-#pragma unroll
-                    for (int i = 0; i < 2; ++i)
-                        dst[4 + i] = make_float4(__uint_as_float(c[4 * i]) * om + bb[4 + i].x, __uint_as_float(c[4 * i + 1]) * om + bb[4 + i].y,
-                                                 __uint_as_float(c[4 * i + 2]) * om + bb[4 + i].z, __uint_as_float(c[4 * i + 3]) * om + bb[4 + i].w);
-                }
-            }
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty);                 // the accumulators may be overwritten by the next unit
-            if (tid == 0) FA(2, tp);      // drain
-            asm volatile("bar.sync 1, 256;" ::: "memory");          // every K / V row of the tile is in shared memory
-            if (tid == 0) FA(3, tp);      // tile barrier
-
-            const bool valid0 = (rng0 & 0xFFFFu) < (rng0 >> 16), valid1 = (rng1 & 0xFFFFu) < (rng1 >> 16);
-            const bool same = valid1 && rng0 == rng1;
-            // pass 0: the keys of row r0's set for (q0, q1) -- q1's result counts when r1 is in the same set (the usual case);
-            // pass 1 (rows on two sides of a set boundary): the keys of r1's set for q1
-#pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                if (pass == 0 ? !valid0 : !(valid1 && !same)) continue;
-                const uint32_t rng = pass == 0 ? rng0 : rng1;
-                const int lo = (int) (rng & 0xFFFFu), hi = (int) (rng >> 16);
-                if (pass == 1) {
-#pragma unroll
-                    for (int i = 0; i < kD / 2; ++i) q0[i] = q1[i];
-                }
-                float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-                float2 acc0[kD / 2], acc1[kD / 2];
-#pragma unroll
-                for (int d2 = 0; d2 < kD / 2; ++d2) { acc0[d2] = f2(0.f, 0.f); acc1[d2] = f2(0.f, 0.f); }
-#pragma unroll 1
-                for (int j0 = lo; j0 < hi; j0 += 4) {
-                    float sc0[4], sc1[4];
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int j = j0 + jj, jc = j < hi ? j : hi - 1;          // tail keys: re-read the last one, masked out
-                        const float4* kp = reinterpret_cast<const float4*>(kv + (size_t) jc * kFKvTok + hh * 96);
-                        float2 a0 = f2(0.f, 0.f), a1 = f2(0.f, 0.f), b0 = f2(0.f, 0.f), b1 = f2(0.f, 0.f);
-#pragma unroll
-                        for (int d4 = 0; d4 < kD / 4; ++d4) {
-                            const float4 kk = kp[d4];
-                            const float2 klo = f2(kk.x, kk.y), khi = f2(kk.z, kk.w);
-                            a0 = __ffma2_rn(q0[2 * d4], klo, a0); a1 = __ffma2_rn(q0[2 * d4 + 1], khi, a1);
-                            b0 = __ffma2_rn(q1[2 * d4], klo, b0); b1 = __ffma2_rn(q1[2 * d4 + 1], khi, b1);
-                        }
-                        const float mk = j < hi ? m_cmask[jc] : -INFINITY;
-                        sc0[jj] = fmaf((a0.x + a0.y) + (a1.x + a1.y), kLog2e, mk);
-                        sc1[jj] = fmaf((b0.x + b0.y) + (b1.x + b1.y), kLog2e, mk);
-                    }
-                    const float m0n = fmaxf(fmaxf(m0, fmaxf(sc0[0], sc0[1])), fmaxf(sc0[2], sc0[3]));
-                    const float m1n = fmaxf(fmaxf(m1, fmaxf(sc1[0], sc1[1])), fmaxf(sc1[2], sc1[3]));
-                    const float al0 = ex2(m0 - m0n), al1 = ex2(m1 - m1n);         // first chunk: 2^-inf = 0
-                    l0 *= al0; l1 *= al1;
-                    const float2 al02 = f2(al0, al0), al12 = f2(al1, al1);
-#pragma unroll
-                    for (int d2 = 0; d2 < kD / 2; ++d2) { acc0[d2] = __fmul2_rn(acc0[d2], al02); acc1[d2] = __fmul2_rn(acc1[d2], al12); }
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int j = j0 + jj, jc = j < hi ? j : hi - 1;
-                        const float p0 = ex2(sc0[jj] - m0n), p1 = ex2(sc1[jj] - m1n);
-                        l0 += p0; l1 += p1;
-                        const float2 p02 = f2(p0, p0), p12 = f2(p1, p1);
-                        const float4* vp = reinterpret_cast<const float4*>(kv + (size_t) jc * kFKvTok + kFKvV + hh * 96);
-#pragma unroll
-                        for (int d4 = 0; d4 < kD / 4; ++d4) {
-                            const float4 vv = vp[d4];
-                            const float2 vlo = f2(vv.x, vv.y), vhi = f2(vv.z, vv.w);
-                            acc0[2 * d4] = __ffma2_rn(p02, vlo, acc0[2 * d4]); acc0[2 * d4 + 1] = __ffma2_rn(p02, vhi, acc0[2 * d4 + 1]);
-                            acc1[2 * d4] = __ffma2_rn(p12, vlo, acc1[2 * d4]); acc1[2 * d4 + 1] = __ffma2_rn(p12, vhi, acc1[2 * d4 + 1]);
-                        }
-                    }
-                    m0 = m0n; m1 = m1n;
-                }
-                const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
-                const int va = pass == 0 ? vrow0 : vrow1;                       // the row q0 stands for in this pass
-                if (va >= 0) {
-                    float4* op = reinterpret_cast<float4*>(o + (size_t) va * kC + hg * 96 + hh * kD);
-#pragma unroll
-                    for (int d4 = 0; d4 < kD / 4; ++d4)
-                        op[d4] = make_float4(acc0[2 * d4].x * inv0, acc0[2 * d4].y * inv0, acc0[2 * d4 + 1].x * inv0, acc0[2 * d4 + 1].y * inv0);
-                }
-                if (pass == 0 && same && vrow1 >= 0) {
-                    float4* op = reinterpret_cast<float4*>(o + (size_t) vrow1 * kC + hg * 96 + hh * kD);
-#pragma unroll
-                    for (int d4 = 0; d4 < kD / 4; ++d4)
-                        op[d4] = make_float4(acc1[2 * d4].x * inv1, acc1[2 * d4].y * inv1, acc1[2 * d4 + 1].x * inv1, acc1[2 * d4 + 1].y * inv1);
-                }
-            }
-            if (tid == 0) FA(4, tp);      // attention
-            asm volatile("bar.sync 1, 256;" ::: "memory");          // the K/V tile is recycled by the next unit
-            if (tid == 0) FA(5, tp);      // end barrier
-        }
-    } else {
-        // =========================== PRODUCERS (+ MMA issue by their first thread): thread = (token row r, 16-byte K piece c16 of the step) ====
-        const int pt = tid - kFCoreThreads, r = pt & 127, c16 = pt >> 7;
-        const float* x = A.x + (size_t) b * A.max_pillars * kC;
-        const float* pos = A.pos + (size_t) b * A.max_pillars * kC;
-        const float* mask = A.mask + (size_t) b * A.max_sets * kH * A.S;
-        int ns = A.set_num[b];
-        ns = ns < A.max_sets ? ns : A.max_sets;
-        int gstep = 0;
-        long long tp = clock64();
-        (void) tp;
-        const uint32_t idesc_qk = make_idesc(kFmtF16, kBM, 192), idesc_v = make_idesc(kFmtF16, kBM, 96);
-        const uint32_t sbase = smem_u32(smem);
-#pragma unroll 1
-        for (int n = 0; n < cnt; ++n) {
-            const int unit = blockIdx.x + n * gridDim.x, tile = unit >> 1, hg = unit & 1, slot = n % 3;
-            int* m_vrow = reinterpret_cast<int*>(smem + L::meta + slot * kFMetaSlot);
-            uint32_t* m_rng = reinterpret_cast<uint32_t*>(m_vrow + kBM);
-            float* m_cmask = reinterpret_cast<float*>(m_rng + kBM);
-            if (pt < kBM) {
-                // metadata of the tile's token r: voxel row, key range of its set inside the tile, key mask (log2 domain)
-                const int s0 = __ldg(pv.tile_set + tile), s1 = __ldg(pv.tile_set + tile + 1);
-                const int T0 = __ldg(pv.set_off + s0), ntok = __ldg(pv.set_off + s1) - T0;
-                int vrow = -1;
-                uint32_t rng = 0;
-                float cm[4] = {0.f, 0.f, 0.f, 0.f};
-                if (r < ntok) {
-                    const int t = T0 + r;
-                    int sidx = s0;
-                    while (sidx + 1 < s1 && __ldg(pv.set_off + sidx + 1) <= t) ++sidx;
-                    const int off = __ldg(pv.set_off + sidx), end = __ldg(pv.set_off + sidx + 1);
-                    const int2 tk = __ldg(pv.tok + (size_t) sidx * A.S + (t - off));
-                    vrow = (tk.x >= 0 && tk.x < A.max_pillars) ? tk.x : -1;
-                    rng = (uint32_t) (off - T0) | ((uint32_t) (end - T0) << 16);
-#pragma unroll
-                    for (int h = 0; h < 4; ++h) cm[h] = __ldg(mask + ((size_t) sidx * kH + hg * 4 + h) * A.S + tk.y) * kLog2e;
-                }
-                m_vrow[r] = vrow;
-                m_rng[r] = rng;
-#pragma unroll
-                for (int h = 0; h < 4; ++h) m_cmask[h * kBM + r] = cm[h];
-            }
-            if (pt == 0) FA(8, tp);       // metadata
-            asm volatile("bar.sync 2, 256;" ::: "memory");
-            mbar_arrive(&meta_full[slot]);
-            if (pt == 0) FA(9, tp);       // metadata barrier
-            const int vr = m_vrow[r];
-            const float* xr = x + (size_t) (vr < 0 ? 0 : vr) * kC + c16 * 8;
-            const float* pr = pos + (size_t) (vr < 0 ? 0 : vr) * kC + c16 * 8;
-            const uint8_t* wsrc = A.wimg + (size_t) hg * kFSteps * kFWChunk;
-            constexpr int kDepth = 4;
-            float buf[kDepth][16];
-            auto issue = [&](int ks, float (&d)[16]) {
-                if (vr >= 0) { ldg256(xr + ks * 16, &d[0]); ldg256(pr + ks * 16, &d[8]); }
-                else {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) d[e] = 0.f;
-                }
-            };
-#pragma unroll
-            for (int ks = 0; ks < kDepth - 1; ++ks) issue(ks, buf[ks]);
-#pragma unroll
-            for (int ks = 0; ks < kFSteps; ++ks, ++gstep) {
-                if (ks + kDepth - 1 < kFSteps) issue(ks + kDepth - 1, buf[(ks + kDepth - 1) % kDepth]);
-                const int st = gstep % kFStages;
-                if (pt == 0) FA(10, tp);  // loads issue etc
-                if (gstep >= kFStages) mbar_wait(&s_empty[st], ((gstep / kFStages) - 1) & 1);
-                if (pt == 0) FA(11, tp);  // wait for a free stage
-                uint8_t* stage = smem + st * L::stage;
-                if (pt == 0) {
-                    mbar_arrive_expect_tx(&w_full[st], L::w_bytes);
-                    bulk_g2s(stage + L::a_bytes, wsrc + (size_t) ks * kFWChunk, L::w_bytes, &w_full[st]);
-                }
-                float (&d)[16] = buf[ks % kDepth];
-                const float vq[8] = {d[0] + d[8], d[1] + d[9], d[2] + d[10], d[3] + d[11], d[4] + d[12], d[5] + d[13], d[6] + d[14], d[7] + d[15]};
-                const uint4 qh = make_uint4(pack_h2(vq[0], vq[1]), pack_h2(vq[2], vq[3]), pack_h2(vq[4], vq[5]), pack_h2(vq[6], vq[7]));
-                const uint4 vh = make_uint4(pack_h2(d[0], d[1]), pack_h2(d[2], d[3]), pack_h2(d[4], d[5]), pack_h2(d[6], d[7]));
-                uint8_t* dst = stage + c16 * (kBM * 16) + r * 16;
-                *reinterpret_cast<uint4*>(dst) = qh;
-                *reinterpret_cast<uint4*>(dst + L::terms * kFATerm) = vh;
-                if (SPLIT) {
-                    const float2 a0 = unpack_h2(qh.x), a1 = unpack_h2(qh.y), a2 = unpack_h2(qh.z), a3 = unpack_h2(qh.w);
-                    *reinterpret_cast<uint4*>(dst + kFATerm) =
-                        make_uint4(pack_h2(vq[0] - a0.x, vq[1] - a0.y), pack_h2(vq[2] - a1.x, vq[3] - a1.y),
-                                   pack_h2(vq[4] - a2.x, vq[5] - a2.y), pack_h2(vq[6] - a3.x, vq[7] - a3.y));
-                    const float2 e0 = unpack_h2(vh.x), e1 = unpack_h2(vh.y), e2 = unpack_h2(vh.z), e3 = unpack_h2(vh.w);
-                    *reinterpret_cast<uint4*>(dst + 3 * kFATerm) =
-                        make_uint4(pack_h2(d[0] - e0.x, d[1] - e0.y), pack_h2(d[2] - e1.x, d[3] - e1.y),
-                                   pack_h2(d[4] - e2.x, d[5] - e2.y), pack_h2(d[6] - e3.x, d[7] - e3.y));
-                }
-                fence_proxy_async_smem();
-                mbar_arrive(&a_full[st]);
-                if (pt == 0) {
-                    FA(12, tp);           // convert + store (incl. waiting for the row loads)
-                    // ---- MMA issue for this step (one thread): D_qk[128 x 192] += A_qk W_qk^T, D_v[128 x 96] += A_v W_v^T ----
-                    if (ks == 0 && n >= 1) { mbar_wait(&acc_empty, (n - 1) & 1); }
-                    FA(16, tp);           // waiting for the core to drain the accumulators
-                    mbar_wait(&w_full[st], (gstep / kFStages) & 1);
-                    FA(17, tp);           // waiting for the weight chunk
-                    mbar_wait(&a_full[st], (gstep / kFStages) & 1);
-                    tc_fence_after_sync();
-                    FA(18, tp);           // waiting for the other producers
-                    const uint32_t sa = sbase + st * L::stage, sw = sa + L::a_bytes;
-                    const uint64_t aq_hi = make_smem_desc(sa, kBM * 16, 128);
-                    const uint64_t av_hi = make_smem_desc(sa + L::terms * kFATerm, kBM * 16, 128);
-                    const uint64_t bq_hi = make_smem_desc(sw, kFWRows * 16, 128);
-                    const uint64_t bv_hi = make_smem_desc(sw + 192 * 16, kFWRows * 16, 128);
-                    if (SPLIT) {
-                        const uint64_t aq_lo = make_smem_desc(sa + kFATerm, kBM * 16, 128);
-                        const uint64_t av_lo = make_smem_desc(sa + 3 * kFATerm, kBM * 16, 128);
-                        const uint64_t bq_lo = make_smem_desc(sw + kFWTerm, kFWRows * 16, 128);
-                        const uint64_t bv_lo = make_smem_desc(sw + kFWTerm + 192 * 16, kFWRows * 16, 128);
-                        umma_f16(tmem, aq_lo, bq_hi, idesc_qk, ks != 0);
-                        umma_f16(tmem, aq_hi, bq_lo, idesc_qk, 1);
-                        umma_f16(tmem, aq_hi, bq_hi, idesc_qk, 1);
-                        umma_f16(tmem + 192, av_lo, bv_hi, idesc_v, ks != 0);
-                        umma_f16(tmem + 192, av_hi, bv_lo, idesc_v, 1);
-                        umma_f16(tmem + 192, av_hi, bv_hi, idesc_v, 1);
-                    } else {
-                        umma_f16(tmem, aq_hi, bq_hi, idesc_qk, ks != 0);
-                        umma_f16(tmem + 192, av_hi, bv_hi, idesc_v, ks != 0);
-                    }
-                    umma_commit(&s_empty[st]);
-                    if (ks == kFSteps - 1) umma_commit(&acc_full);
-                    FA(19, tp);           // issue
-                }
-            }
-        }
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-#ifdef DSVT_PROFILE
-    if (blockIdx.x == 7 && blockIdx.y == 0 && threadIdx.x == 0) g_split_prof[32] = clock64() - g_split_prof[31];
-#endif
-    if (warp == kFIssuerWarp) tmem_dealloc<512>(tmem);
-}
-
 template <int S>
 int launch_plan(const dsvt_set_attention_params* p, const int* idx, const float* mask, const int* set_num, int* plan,
                 cudaStream_t st)
@@ -1509,13 +1108,7 @@ int launch_plan(const dsvt_set_attention_params* p, const int* idx, const float*
     attn_plan_sets_kernel<S><<<dim3((p->max_set_num + 7) / 8, p->batch), 256, 0, st>>>(
         idx, mask, set_num, plan, stride, p->max_set_num, p->max_pillars_num, p->axis_id);
     DSVT_LAUNCH_CHECK();
-    const size_t scan_smem = (size_t) p->max_set_num * sizeof(int);
-    if (scan_smem > 200 * 1024) {
-        set_last_error("set attention plan: max_set_num %d exceeds the tile builder's shared memory", p->max_set_num);
-        return DSVT_ERR_UNSUPPORTED;
-    }
-    if (scan_smem > 40 * 1024) DSVT_RAISE_SMEM(attn_plan_scan_kernel, 200 * 1024);
-    attn_plan_scan_kernel<<<p->batch, 1024, scan_smem, st>>>(set_num, plan, stride, p->max_set_num, p->max_pillars_num);
+    attn_plan_scan_kernel<<<p->batch, 1024, 0, st>>>(set_num, plan, stride, p->max_set_num, p->max_pillars_num);
     DSVT_LAUNCH_CHECK();
     return DSVT_OK;
 }
@@ -1650,8 +1243,8 @@ int linear_split_launch(const void* blob, int N, int K, float out_mul, bool spli
             for (int r = 0; r < 3; ++r) {
                 const int i = i0 + (r < n_roles ? r : 0);
                 GemmRole& g = roles.r[r];
-        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f;
-                g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f;
+        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f; g.gen_x = nullptr; g.gen_blob = nullptr;
+                g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f; g.gen_x = nullptr; g.gen_blob = nullptr;
                 g.a0 = x + (size_t) j * kC; g.a1 = nullptr; g.lda = x_hi ? k_split : K;
                 g.a0b = x_hi; g.ksplit = x_hi ? k_split : 0; g.ldb = x_hi ? K - k_split : 0;
                 g.add_src = nullptr; g.ld_add = 0; g.cover = nullptr; g.cover_stride = 0;
@@ -1686,7 +1279,7 @@ int linear_split_k_launch(const void* blob, int N, int K, float out_mul, bool sp
     for (int r = 0; r < 3; ++r) {
         const int j = r < kb ? r : 0;
         GemmRole& g = roles.r[r];
-        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f;
+        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f; g.gen_x = nullptr; g.gen_blob = nullptr;
         g.a0 = x + (size_t) j * kC; g.a1 = nullptr; g.lda = K;
         g.a0b = nullptr; g.ksplit = 0; g.ldb = 0; g.cover = nullptr; g.cover_stride = 0;
         g.wimg = img + (size_t) j * kWRoleBytes;
@@ -1698,6 +1291,33 @@ int linear_split_k_launch(const void* blob, int N, int K, float out_mul, bool sp
         g.add_src = j == 0 ? add : nullptr; g.ld_add = N;
     }
     return launch_gemm(roles, kb, rows_dev, 0, max_rows, 1, 0, 1, split, st);
+}
+
+// Position-embedding MLP in one kernel: y = relu((x2 W1^T) * scale + shift) W2^T + b2 with x2 [rows, 2]; the first layer is
+// evaluated by the GEMM's producers (GemmRole::gen_x), its [rows, 192] output never reaches memory (tile kernel only).
+int linear_gen_launch(const void* blob, float out_mul, bool split, const float* x2, const float* small_blob, const int* rows_dev,
+                      int max_rows, float* y, int zero_tails, cudaStream_t st)
+{
+    if (gemm_persistent()) {
+        set_last_error("position-embedding MLP: not available with DSVT_GEMM_IMPL=persistent");
+        return DSVT_ERR_UNSUPPORTED;
+    }
+    const uint8_t* img = static_cast<const uint8_t*>(blob);
+    GemmRoles roles;
+    GemmRole& g = roles.r[0];
+    g.a0 = x2; g.a1 = nullptr; g.lda = kC;          // a0 is not read in this mode
+    g.a0b = nullptr; g.ksplit = 0; g.ldb = 0; g.cover = nullptr; g.cover_stride = 0;
+    g.wimg = img;
+    g.bias = reinterpret_cast<const float*>(img + (size_t) kWRoleBytes);
+    g.out = y; g.ld_out = kC; g.col0 = 0;
+    g.out_mul = out_mul; g.post_mul = 1.0f;
+    g.plan = nullptr; g.plan_stride = 0; g.pad_hi = 0;
+    g.accumulate = 0; g.act = 0; g.add_src = nullptr; g.ld_add = 0;
+    g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f;
+    for (int s = 0; s < 3; ++s) { g.ln_res[s] = nullptr; g.ln_gamma[s] = nullptr; g.ln_beta[s] = nullptr; }
+    g.gen_x = x2; g.gen_blob = small_blob;
+    roles.r[1] = roles.r[2] = g;
+    return launch_gemm(roles, 1, rows_dev, 0, max_rows, 1, zero_tails, 1, split, st);
 }
 
 // [*, K] -> [*, 192] layer (K = 192 or 384) followed by a chain of up to three (residual add + LayerNorm) stages, in ONE
@@ -1722,7 +1342,7 @@ int linear_ln_launch(const void* blob, int K, float out_mul, bool split, const f
     g.out_mul = out_mul; g.post_mul = 1.0f;
     g.plan = nullptr; g.plan_stride = 0; g.pad_hi = 0;
     g.accumulate = 0; g.act = 0; g.add_src = nullptr; g.ld_add = 0;
-    g.kchunks = kb * kNumK; g.n_ln = n_ln; g.ln_eps = eps;
+    g.kchunks = kb * kNumK; g.n_ln = n_ln; g.ln_eps = eps; g.gen_x = nullptr; g.gen_blob = nullptr;
     for (int s = 0; s < 3; ++s) {
         g.ln_res[s] = s < n_ln ? res[s] : nullptr;
         g.ln_gamma[s] = s < n_ln ? gamma[s] : nullptr;
@@ -1738,9 +1358,7 @@ void* attention_split_prepare(const float* w_in, const float* b_in, const float*
                               float* out_mul)
 {
     const size_t img_bytes = (size_t) kRoles * kWRoleBytes;
-    const size_t fused_off = img_bytes + (size_t) kRoles * kC * sizeof(float);
-    std::vector<uint8_t> host(fused_off + kFWImgBytes);
-    int role_shift[kRoles];
+    std::vector<uint8_t> host(img_bytes + (size_t) kRoles * kC * sizeof(float));
     for (int role = 0; role < kRoles; ++role) {
         const float* W = role < 3 ? w_in + (size_t) role * kC * kC : w_out;       // [192 out][192 in]
         float maxabs = 0.f;
@@ -1755,7 +1373,6 @@ void* attention_split_prepare(const float* w_in, const float* b_in, const float*
         }
         const float ws = ldexpf(1.0f, sh);
         out_mul[role] = ldexpf(1.0f, -sh);
-        role_shift[role] = sh;
         for (int kc = 0; kc < kNumK; ++kc) {
             uint8_t* hi_img = host.data() + (size_t) role * kWRoleBytes + (size_t) kc * kWChunkBytes;
             uint8_t* lo_img = hi_img + kBTerm;
@@ -1775,28 +1392,6 @@ void* attention_split_prepare(const float* w_in, const float* b_in, const float*
         const float* bsrc = role < 3 ? b_in + role * kC : b_out;
         for (int n = 0; n < kC; ++n) bias[n] = bsrc[n];
     }
-    // images of the fused QKV + core kernel: per (head group, K16 step) the rows [Wq_hg | Wk_hg | Wv_hg] (288 x 16) as
-    // [hi | lo] in the UMMA K-major layout, every role pre-scaled by its own power of two (the same as above)
-    for (int hg = 0; hg < 2; ++hg)
-        for (int ks = 0; ks < kFSteps; ++ks) {
-            uint8_t* hi_img = host.data() + fused_off + ((size_t) hg * kFSteps + ks) * kFWChunk;
-            uint8_t* lo_img = hi_img + kFWTerm;
-            for (int n = 0; n < kFWRows; ++n) {
-                const int role = n / 96, j = n % 96;
-                const float ws = ldexpf(1.0f, role_shift[role]);
-                const float* wrow = w_in + (size_t) (role * kC + hg * 96 + j) * kC;
-                for (int c16 = 0; c16 < 2; ++c16)
-                    for (int e = 0; e < 8; ++e) {
-                        const float w = wrow[ks * 16 + c16 * 8 + e] * ws;
-                        const __half h = __float2half_rn(w);
-                        const __half l = __float2half_rn(w - __half2float(h));
-                        const uint16_t hb = __half_as_ushort(h), lb = __half_as_ushort(l);
-                        const size_t off = (size_t) c16 * (kFWRows * 16) + (size_t) n * 16 + e * 2;
-                        memcpy(hi_img + off, &hb, 2);
-                        memcpy(lo_img + off, &lb, 2);
-                    }
-            }
-        }
     void* dev = nullptr;
     if (cudaMalloc(&dev, host.size()) != cudaSuccess) return nullptr;
     if (cudaMemcpy(dev, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -1907,7 +1502,7 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
     GemmRoles in_roles, out_roles;
     for (int r = 0; r < 3; ++r) {
         GemmRole& g = in_roles.r[r];
-        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f;
+        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f; g.gen_x = nullptr; g.gen_blob = nullptr;
         g.a0 = x;
         g.a1 = r < 2 ? pos : nullptr;
         g.wimg = img + (size_t) r * kWRoleBytes;
@@ -1925,7 +1520,7 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
     }
     {
         GemmRole& g = out_roles.r[0];
-        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f;
+        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f; g.gen_x = nullptr; g.gen_blob = nullptr;
         g.a0 = o; g.a1 = nullptr;
         g.wimg = img + (size_t) 3 * kWRoleBytes;
         g.bias = bias + 3 * kC;
@@ -1948,29 +1543,6 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
         }
         out_roles.r[1] = out_roles.r[2] = g;
     }
-    // DSVT_ATTN_IMPL=pipeline selects the separate QKV GEMM + core kernels (A/B runs); default: the fused kernel
-    static const bool use_pipeline = [] { const char* e = getenv("DSVT_ATTN_IMPL"); return e && e[0] == 'p'; }();
-    if (!use_pipeline) {
-        FusedArgs fa;
-        fa.x = x; fa.pos = pos;
-        fa.wimg = img + (size_t) kRoles * kWRoleBytes + (size_t) kRoles * kC * sizeof(float);
-        fa.bias = bias;
-        fa.out_mul[0] = out_mul[0]; fa.out_mul[1] = out_mul[1]; fa.out_mul[2] = out_mul[2];
-        fa.q_scale = 1.0f / sqrtf((float) (kC / kH));
-        fa.plan = plan; fa.plan_stride = plan_stride;
-        fa.mask = mask; fa.set_num = set_num; fa.o = o;
-        fa.max_sets = p->max_set_num; fa.max_pillars = p->max_pillars_num; fa.S = p->voxel_num_set;
-        if (!(g_skip_mask & 3)) {
-            DSVT_RAISE_SMEM(qkv_core_kernel<true>, FLay<true>::total);
-            DSVT_RAISE_SMEM(qkv_core_kernel<false>, FLay<false>::total);
-            const dim3 grid(sm_count(), p->batch);
-            if (split) qkv_core_kernel<true><<<grid, kFThreads, FLay<true>::total, st>>>(fa);
-            else qkv_core_kernel<false><<<grid, kFThreads, FLay<false>::total, st>>>(fa);
-            DSVT_LAUNCH_CHECK();
-        }
-        if ((rc = stage_mark(1, st)) != DSVT_OK) return rc;
-        if ((rc = stage_mark(2, st)) != DSVT_OK) return rc;
-    } else {
     if (!(g_skip_mask & 1) &&
         (rc = launch_gemm(in_roles, 3, voxel_num, 0, p->max_pillars_num, p->max_set_num, 0, p->batch, split, st)) != DSVT_OK)
         return rc;
@@ -1982,7 +1554,6 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
     }
     if (rc != DSVT_OK) return rc;
     if ((rc = stage_mark(2, st)) != DSVT_OK) return rc;
-    }
     if (!(g_skip_mask & 4) &&
         (rc = launch_gemm(out_roles, 1, voxel_num, 0, p->max_pillars_num, p->max_set_num, p->zero_tails, p->batch, split, st)) != DSVT_OK)
         return rc;
@@ -2013,10 +1584,6 @@ extern "C" int dsvt_debug_attention_stage_us(float* out3) {
     return 0;
 }
 #ifdef DSVT_PROFILE
-extern "C" int dsvt_debug_split_profile_reset(void) {
-    static const long long zeros[64] = {0};
-    return cudaMemcpyToSymbol(dsvt::g_split_prof, zeros, sizeof(zeros)) == cudaSuccess ? 0 : 1;
-}
 extern "C" int dsvt_debug_split_profile(long long* out64) {
     return cudaMemcpyFromSymbol(out64, dsvt::g_split_prof, sizeof(long long) * 64) == cudaSuccess ? 0 : 1;
 }

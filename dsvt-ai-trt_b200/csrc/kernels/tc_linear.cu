@@ -141,6 +141,8 @@ int linear_split_launch(const void* blob, int N, int K, float out_mul, bool spli
                         int zero_tails, cudaStream_t st);
 int linear_split_k_launch(const void* blob, int N, int K, float out_mul, bool split, const float* x, const float* add,
                           const int* rows_dev, int max_rows, float* y_parts, cudaStream_t st);
+int linear_gen_launch(const void* blob, float out_mul, bool split, const float* x2, const float* small_blob, const int* rows_dev,
+                      int max_rows, float* y, int zero_tails, cudaStream_t st);
 int linear_ln_launch(const void* blob, int K, float out_mul, bool split, const float* x, const int* rows_dev, int max_rows,
                      int n_ln, const float* const* res, const float* const* gamma, const float* const* beta, float eps,
                      float* y, int zero_tails, cudaStream_t st);
@@ -302,4 +304,20 @@ extern "C" int dsvt_linear_rows_norm_launch(const dsvt_linear_weights* w, const 
     }
     return dsvt::linear_ln_launch(w->split_blob, w->K, w->out_mul, w->precision == DSVT_ATTN_FP32_TC, x, rows, max_rows,
                                   n_stages, res, gamma, beta, eps, y, zero_tails, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// small_linear.cu
+struct dsvt_small_linear { int N, K; float* blob; };
+
+extern "C" int dsvt_pos_embed_mlp_launch(const dsvt_small_linear* first, const dsvt_linear_weights* second, const float* x2,
+                                         const int32_t* rows, int32_t max_rows, float* y, int32_t zero_tails,
+                                         dsvt_stream_t stream)
+{
+    DSVT_CHECK_ARG(first && second && x2 && rows && y && max_rows >= 1, "NULL argument");
+    DSVT_CHECK_ARG(first->K == 2 && first->N == 192, "first layer: Linear(2 -> 192) (+ folded BatchNorm, ReLU)");
+    DSVT_CHECK_ARG(second->split_blob != nullptr && second->N == 192 && second->K == 192,
+                   "second layer: Linear(192 -> 192) created with DSVT_ATTN_FP32_TC / DSVT_ATTN_FP16_GEMM");
+    DSVT_CHECK_ARG(!(((uintptr_t) x2 & 7) | ((uintptr_t) y & 15)), "alignment (x2 8 B, y 16 B)");
+    return dsvt::linear_gen_launch(second->split_blob, second->out_mul, second->precision == DSVT_ATTN_FP32_TC, x2, first->blob,
+                                   rows, max_rows, y, zero_tails, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -272,6 +272,10 @@ class HotPathFrame:
             for blk in range(0 if "pos" in skip else cfg.num_blocks):   # pos_embed[blk][i] from the shift-i window coordinates (:603-637)
                 for enc in (0, 1):
                     first, second = w.glue["pos"][blk][enc]
+                    if self.ffn == "epilogue":             # both layers in one kernel: the hidden rows never reach memory
+                        capi.pos_embed_mlp(first, second, self.wp[enc].coors_in_win_x_y[0], V, out=self.pos_out[blk][enc],
+                                           zero_tails=0)
+                        continue
                     first(self.wp[enc].coors_in_win_x_y[0], V, activation=2, out=self.pos_hidden, zero_tails=0)
                     second.rows(self.pos_hidden, V, out=self.pos_out[blk][enc], zero_tails=0)
         for blk in range(cfg.num_blocks):

@@ -368,6 +368,16 @@ void dsvt_small_linear_destroy(dsvt_small_linear* w);
 int dsvt_small_linear_launch(const dsvt_small_linear* w, const float* x, const int32_t* rows, int32_t batch,
                              int32_t max_rows, int32_t activation, float* y, int32_t zero_tails, dsvt_stream_t stream);
 
+/*
+ * One position-embedding MLP (fullyConnectedBnLELU_fullyConnected, src/dsvt-ai-trt.cpp:461-492; 8 call sites :603-637) in one
+ * kernel:  y = relu((x2 W1^T) * scale + shift) W2^T + b2,  x2 [max_rows,2] = the in-window coordinates (WindowPartitionPlugin
+ * output 5), `first` = Linear(2 -> 192) + folded BatchNorm1d, `second` = Linear(192 -> 192) created with DSVT_ATTN_FP32_TC or
+ * DSVT_ATTN_FP16_GEMM.  The 192-wide hidden rows are generated inside the second layer's GEMM and never reach memory; results
+ * are bit-identical to dsvt_small_linear_launch (ReLU) followed by dsvt_linear_rows_launch.
+ */
+int dsvt_pos_embed_mlp_launch(const dsvt_small_linear* first, const dsvt_linear_weights* second, const float* x2,
+                              const int32_t* rows, int32_t max_rows, float* y, int32_t zero_tails, dsvt_stream_t stream);
+
 /* ------------------------------------------------------------------------ *
  * (next #3) TorchScatterMaxPlugin::enqueue     plugins/src/torchScatterMax.cu:282-309 (kernel :201-262)
  *           Map2BevPlugin::enqueue             plugins/src/map2bev.cu:283-312 (kernel :250-265)

@@ -132,3 +132,65 @@ def test_linear_rows_splitk(rows, with_add):
     got = (parts[0, :rows] + parts[1, :rows]).cpu().numpy()
     ref = x[:rows].astype(np.float64) @ W.T.astype(np.float64) + b + (add[:rows] if with_add else 0.0)
     assert np.abs(got - ref).max(initial=0.0) <= 2e-5
+
+
+@pytest.mark.parametrize("rows", [1, 127, 128, 1000, 1300])
+def test_pos_embed_mlp_one_kernel(rows):
+    """dsvt_pos_embed_mlp_launch (Linear(2->192)+BN+ReLU generated inside the Linear(192->192) GEMM) is bit-identical to
+    the two launches it replaces, and within the FP32 tolerance of a float64 evaluation (src/dsvt-ai-trt.cpp:461-492)."""
+    capi = importlib.import_module("dsvt-ai-trt_b200.capi")
+    rng = np.random.default_rng(rows)
+    cap, C = 1300, 192
+    x2 = np.zeros((cap, 2), np.float32)
+    x2[:rows] = rng.integers(-12, 12, (rows, 2)).astype(np.float32) + 0.5        # in-window coordinates: x - W/2
+    w1 = (rng.standard_normal((C, 2)) * 0.3).astype(np.float32)
+    sc = (0.5 + 0.1 * rng.standard_normal(C)).astype(np.float32)
+    sh = (0.1 * rng.standard_normal(C)).astype(np.float32)
+    w2 = (rng.standard_normal((C, C)) * 0.07).astype(np.float32)
+    b2 = (rng.standard_normal(C) * 0.02).astype(np.float32)
+    first, second = capi.SmallLinear(w1, sc, sh), capi.Linear(w2, b2, precision=capi.DSVT_ATTN_FP32_TC)
+    dx, n = torch.from_numpy(x2).cuda(), torch.tensor([rows], dtype=torch.int32, device="cuda")
+    hidden = first(dx, n, activation=2)
+    two = second.rows(hidden, n)
+    one = torch.full((cap, C), float("nan"), device="cuda")
+    capi.pos_embed_mlp(first, second, dx, n, out=one)
+    torch.cuda.synchronize()
+    assert torch.equal(one, two)
+    assert float(one[rows:].abs().max()) == 0.0 if rows < cap else True
+    h64 = np.maximum((x2[:rows].astype(np.float64) @ w1.T.astype(np.float64)) * sc + sh, 0.0)
+    ref = h64 @ w2.T.astype(np.float64) + b2
+    assert np.abs(one[:rows].cpu().numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("K,n_ln", [(192, 1), (384, 2), (384, 3)])
+@pytest.mark.parametrize("rows", [1, 200, 1000])
+def test_linear_rows_norm(K, n_ln, rows):
+    """dsvt_linear_rows_norm_launch: linear + a chain of (residual add + LayerNorm) stages in the GEMM epilogue against the
+    separate launches (same arithmetic per stage) and a float64 evaluation."""
+    capi = importlib.import_module("dsvt-ai-trt_b200.capi")
+    rng = np.random.default_rng(K + n_ln + rows)
+    cap, C = 1300, 192
+    x = np.zeros((cap, K), np.float32)
+    x[:rows] = rng.standard_normal((rows, K))
+    W = (rng.standard_normal((C, K)) * 0.06).astype(np.float32)
+    b = (rng.standard_normal(C) * 0.05).astype(np.float32)
+    lin = capi.Linear(W, b, precision=capi.DSVT_ATTN_FP32_TC)
+    res = [torch.from_numpy(rng.standard_normal((cap, C)).astype(np.float32)).cuda() for _ in range(n_ln)]
+    gam = [torch.from_numpy((1 + 0.1 * rng.standard_normal(C)).astype(np.float32)).cuda() for _ in range(n_ln)]
+    bet = [torch.from_numpy((0.1 * rng.standard_normal(C)).astype(np.float32)).cuda() for _ in range(n_ln)]
+    dx, n = torch.from_numpy(x).cuda(), torch.tensor([rows], dtype=torch.int32, device="cuda")
+    stages = list(zip(res, gam, bet))
+    out = torch.full((cap, C), float("nan"), device="cuda")
+    lin.rows_norm(dx, n, stages, 0.0, out=out)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert np.all(got[rows:] == 0)
+    y = x[:rows].astype(np.float64) @ W.T.astype(np.float64) + b
+    for r, g_, b_ in stages:
+        y = y + r[:rows].cpu().numpy().astype(np.float64)
+        mu = y.mean(1, keepdims=True)
+        y = (y - mu) / np.sqrt(((y - mu) ** 2).mean(1, keepdims=True)) * g_.cpu().numpy() + b_.cpu().numpy()
+    assert np.abs(got[:rows] - y).max() <= 5e-5
+    if K == 192:      # against the separate launches: linear, then the LayerNorm chain kernel (identical arithmetic per stage)
+        two = capi.layer_norm_chain(lin.rows(dx, n), n, stages, 0.0)
+        assert torch.equal(out, two)
