@@ -292,7 +292,7 @@ class AttentionWeights:
             pass
 
 
-def set_attention(weights, q, k, v, mask, set_num=None, out=None, precision=DSVT_ATTN_FP32, zero_tails=1):
+def set_attention(weights, q, k, v, mask, set_num=None, out=None, precision=DSVT_ATTN_FP32, zero_tails=1, workspace=None):
     """Plugin-shaped form: q,k,v [B,max_sets,S,C] (or without B), mask [B,max_sets,H,S]."""
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (mask, "mask")):
         _need(t, torch.float32, n)
@@ -300,8 +300,11 @@ def set_attention(weights, q, k, v, mask, set_num=None, out=None, precision=DSVT
     max_sets, S, C = q.shape[-3], q.shape[-2], q.shape[-1]
     out = torch.empty_like(q) if out is None else out
     p = AttnParams(B, max_sets, S, C, weights.heads, 0, 0, precision, zero_tails)
+    ws_bytes = int(_lib().dsvt_set_attention_workspace_size(ctypes.byref(p)))
+    if ws_bytes and workspace is None:
+        workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
     rc = _lib().dsvt_set_attention_launch(ctypes.byref(p), c_void_p(weights.handle), _ptr(q), _ptr(k), _ptr(v),
-                                          _ptr(mask), _ptr(set_num), _ptr(out), c_void_p(0), c_size_t(0), _stream())
+                                          _ptr(mask), _ptr(set_num), _ptr(out), _ptr(workspace), c_size_t(ws_bytes), _stream())
     _check(rc, "dsvt_set_attention_launch")
     return out
 

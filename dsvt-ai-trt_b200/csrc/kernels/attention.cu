@@ -87,7 +87,8 @@ static int attn_check(const dsvt_set_attention_params* p, const dsvt_attention_w
 
 extern "C" size_t dsvt_set_attention_workspace_size(const dsvt_set_attention_params* p) {
     if (p && (p->precision == DSVT_ATTN_FP32_TC || p->precision == DSVT_ATTN_FP16_GEMM))
-        return attention_split_workspace(p);   // qkv [B,max_pillars,3C] + o [B,max_pillars,C], f32
+        // max_pillars_num == 0: the plugin-shaped (q, k, v) form, one row per set slot
+        return p->max_pillars_num > 0 ? attention_split_workspace(p) : attention_split_plugin_workspace(p);
     return 0;   // single-kernel paths: everything between the token tile and the output row stays on chip
 }
 
@@ -103,11 +104,9 @@ static int attn_dispatch(const dsvt_set_attention_params* p, const dsvt_attentio
     switch (p->precision) {
         case DSVT_ATTN_FP32_TC:
         case DSVT_ATTN_FP16_GEMM:
-            if (!fused) {
-                set_last_error("set attention: the GEMM pipeline is built for the fused entry point "
-                               "(dsvt_set_attention_fused_launch) only");
-                return DSVT_ERR_UNSUPPORTED;
-            }
+            if (!fused)
+                return set_attention_split_plugin(p, w->split_blob, w->split_out_mul, p->precision == DSVT_ATTN_FP32_TC,
+                                                  q, k, v, mask, set_num, out, workspace, workspace_bytes, st);
             return set_attention_split_fused(p, w->split_blob, w->split_out_mul, p->precision == DSVT_ATTN_FP32_TC,
                                              q, pos, idx, mask, set_num, voxel_num, out, plan, workspace, workspace_bytes, st, norm);
         case DSVT_ATTN_FP32:

@@ -37,6 +37,12 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
                               const int* set_num, const int* voxel_num, float* out, const void* plan,
                               void* workspace, size_t workspace_bytes, cudaStream_t st, const AttnNorm* norm = nullptr);
 
+// the same pipeline for pre-gathered q / k / v [B, max_sets, S, 192] (the drop-in for multHeadAttention() itself)
+size_t attention_split_plugin_workspace(const dsvt_set_attention_params* p);
+int set_attention_split_plugin(const dsvt_set_attention_params* p, const void* split_blob, const float* out_mul, bool split,
+                               const float* q, const float* k, const float* v, const float* mask, const int* set_num,
+                               float* out, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 }  // namespace dsvt
 
 struct dsvt_attention_weights {

@@ -1560,6 +1560,117 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
     return stage_mark(3, st);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Plugin-shaped form (the drop-in for multHeadAttention() itself, src/dsvt-ai-trt.cpp:288-458: q, k, v arrive pre-gathered as
+// [B, max_sets, S, 192]) on the same tensor-core pipeline.  Every slot of a valid set is a token here (the gather has already
+// duplicated the padding slots; the key mask removes them), so the "plan" is the identity: token = row = set * S + slot.
+namespace {
+__global__ void __launch_bounds__(256)
+attn_identity_plan_kernel(const int* __restrict__ set_num, int* __restrict__ plan, size_t plan_stride, int* __restrict__ rows_out,
+                          int max_sets, int S)
+{
+    const int b = blockIdx.y, rows_cap = max_sets * S;
+    const PlanView pv = plan_view(plan + (size_t) b * plan_stride, max_sets, rows_cap);
+    int ns = set_num ? set_num[b] : max_sets;
+    ns = ns < max_sets ? (ns < 0 ? 0 : ns) : max_sets;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { pv.hdr[0] = ns * S; rows_out[b] = ns * S; rows_out[gridDim.y + b] = ns; }     // rows | sets, per batch item
+    if (i <= max_sets) pv.set_off[i] = (i < ns ? i : ns) * S;
+    if (i < max_sets) { pv.nu[i] = i < ns ? S : 0; pv.order[i] = i; }
+    for (int t = i; t < rows_cap; t += gridDim.x * blockDim.x) {
+        const int set = t / S, u = t - set * S;
+        pv.vox_su[t] = set < ns ? set * 64 + u : -1;
+        pv.tok[t] = make_int2(t, u);
+    }
+}
+}  // namespace
+
+size_t attention_split_plugin_workspace(const dsvt_set_attention_params* p) {
+    dsvt_set_attention_params q = *p;
+    q.max_pillars_num = p->max_set_num * p->voxel_num_set;        // one row per set slot
+    return attention_split_workspace(&q) + align_up(2 * (size_t) p->batch * sizeof(int), kWsAlign);   // + the device-side counts
+}
+
+int set_attention_split_plugin(const dsvt_set_attention_params* p, const void* split_blob, const float* out_mul, bool split,
+                               const float* q, const float* k, const float* v, const float* mask, const int* set_num,
+                               float* out, void* workspace, size_t workspace_bytes, cudaStream_t st)
+{
+    int rc = split_check(p);
+    if (rc != DSVT_OK) return rc;
+    if (!split_blob) { set_last_error("set attention (GEMM pipeline): weights were not prepared"); return DSVT_ERR_INVALID_ARGUMENT; }
+    if (((uintptr_t) q | (uintptr_t) k | (uintptr_t) v | (uintptr_t) workspace) & 31) {
+        set_last_error("set attention (GEMM pipeline): q, k, v and workspace must be 32-byte aligned (256-bit loads)");
+        return DSVT_ERR_INVALID_ARGUMENT;
+    }
+    if (!workspace || workspace_bytes < attention_split_plugin_workspace(p)) {
+        set_last_error("set attention (GEMM pipeline): workspace of %zu bytes required (dsvt_set_attention_workspace_size)",
+                       attention_split_plugin_workspace(p));
+        return DSVT_ERR_INVALID_ARGUMENT;
+    }
+    dsvt_set_attention_params pp = *p;
+    const int rows_cap = p->max_set_num * p->voxel_num_set;
+    pp.max_pillars_num = rows_cap;
+    const size_t rows = (size_t) p->batch * rows_cap;
+    WsCarver ws(workspace);
+    float* qbuf = ws.take<float>(rows * kC);
+    float* kvbuf = ws.take<float>(rows * kKvTok);
+    float* o = ws.take<float>(rows * kC);
+    int* plan = ws.take<int>(plan_bytes_of(&pp) / sizeof(int));
+    int* rows_dev = ws.take<int>(2 * (size_t) p->batch);     // [B] valid rows (= sets * S) | [B] valid sets
+    const size_t plan_stride = plan_words(p->max_set_num, p->voxel_num_set, rows_cap);
+    const uint8_t* img = static_cast<const uint8_t*>(split_blob);
+    const float* bias = reinterpret_cast<const float*>(img + (size_t) kRoles * kWRoleBytes);
+
+    const int pgrid = (rows_cap + 255) / 256 < 1024 ? (rows_cap + 255) / 256 : 1024;
+    attn_identity_plan_kernel<<<dim3(pgrid > (p->max_set_num + 256) / 256 ? pgrid : (p->max_set_num + 256) / 256, p->batch), 256, 0, st>>>(
+        set_num, plan, plan_stride, rows_dev, p->max_set_num, p->voxel_num_set);
+    DSVT_LAUNCH_CHECK();
+
+    GemmRoles in_roles, out_roles;
+    const float* srcs[3] = {q, k, v};
+    for (int r = 0; r < 3; ++r) {
+        GemmRole& g = in_roles.r[r];
+        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f; g.gen_x = nullptr; g.gen_blob = nullptr;
+        for (int s2 = 0; s2 < 3; ++s2) { g.ln_res[s2] = nullptr; g.ln_gamma[s2] = nullptr; g.ln_beta[s2] = nullptr; }
+        g.a0 = srcs[r]; g.a1 = nullptr;                      // the gather plugin has already formed q = k = x + pos, v = x
+        g.wimg = img + (size_t) r * kWRoleBytes;
+        g.bias = bias + r * kC;
+        g.out = r == 0 ? qbuf : kvbuf;
+        g.ld_out = r == 0 ? kC : kKvTok;
+        g.col0 = r == 2 ? kKvRow : 0;
+        g.out_mul = out_mul[r];
+        g.post_mul = r == 0 ? 1.0f / sqrtf((float) (kC / kH)) : 1.0f;
+        g.plan = plan; g.plan_stride = plan_stride;
+        g.pad_hi = r == 0 ? 0 : 4;
+        g.lda = kC; g.accumulate = 0; g.act = 0;
+        g.a0b = nullptr; g.ksplit = 0; g.ldb = 0; g.add_src = nullptr; g.ld_add = 0; g.cover = nullptr; g.cover_stride = 0;
+    }
+    {
+        GemmRole& g = out_roles.r[0];
+        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f; g.gen_x = nullptr; g.gen_blob = nullptr;
+        for (int s2 = 0; s2 < 3; ++s2) { g.ln_res[s2] = nullptr; g.ln_gamma[s2] = nullptr; g.ln_beta[s2] = nullptr; }
+        g.a0 = o; g.a1 = nullptr;
+        g.wimg = img + (size_t) 3 * kWRoleBytes;
+        g.bias = bias + 3 * kC;
+        g.out = out; g.ld_out = kC; g.col0 = 0;
+        g.out_mul = out_mul[3]; g.post_mul = 1.0f;
+        g.plan = nullptr; g.plan_stride = 0; g.pad_hi = 0;
+        g.lda = kC; g.accumulate = 0; g.act = 0;
+        g.a0b = nullptr; g.ksplit = 0; g.ldb = 0; g.add_src = nullptr; g.ld_add = 0; g.cover = nullptr; g.cover_stride = 0;
+        out_roles.r[1] = out_roles.r[2] = g;
+    }
+    const int* ns_dev = rows_dev + p->batch;                 // set_num == NULL: all max_set_num sets, as the reference graph does
+    if ((rc = launch_gemm(in_roles, 3, rows_dev, 0, rows_cap, p->max_set_num, 0, p->batch, split, st)) != DSVT_OK) return rc;
+    switch (p->voxel_num_set) {
+        case 24: rc = launch_core<24>(&pp, qbuf, kvbuf, plan, mask, ns_dev, o, st); break;
+        case 36: rc = launch_core<36>(&pp, qbuf, kvbuf, plan, mask, ns_dev, o, st); break;
+        default: rc = launch_core<48>(&pp, qbuf, kvbuf, plan, mask, ns_dev, o, st); break;
+    }
+    if (rc != DSVT_OK) return rc;
+    return launch_gemm(out_roles, 1, rows_dev, 0, rows_cap, p->max_set_num, p->zero_tails, p->batch, split, st);
+}
+
 }  // namespace dsvt
 
 extern "C" void dsvt_debug_attention_stage_timing(int enable) { dsvt::g_stage_timing = enable != 0; }

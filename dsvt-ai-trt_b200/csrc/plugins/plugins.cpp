@@ -703,7 +703,16 @@ public:
         return report(dsvt_set_attention_launch(&p, dev_, static_cast<const float*>(inputs[0]),
                                                 static_cast<const float*>(inputs[1]), static_cast<const float*>(inputs[2]),
                                                 static_cast<const float*>(inputs[3]), set_num,
-                                                static_cast<float*>(outputs[0]), ws, 0, stream), kName);
+                                                static_cast<float*>(outputs[0]), ws, dsvt_set_attention_workspace_size(&p),
+                                                stream), kName);
+    }
+    // tensor-core precisions (DSVT_ATTN_FP32_TC / DSVT_ATTN_FP16_GEMM): projections of the set slots + per-set core need
+    // FP32 intermediates; 0 bytes for the CUDA-core precision
+    size_t getWorkspaceSize(const PluginTensorDesc* in, int32_t, const PluginTensorDesc*, int32_t) const noexcept override {
+        dsvt_set_attention_params p{};
+        p.batch = batch_of(in); p.max_set_num = max_sets_; p.voxel_num_set = S_; p.channel_num = C_;
+        p.num_heads = heads_; p.precision = precision_; p.zero_tails = 1;
+        return dsvt_set_attention_workspace_size(&p);
     }
     void configurePlugin(const DynamicPluginTensorDesc*, int32_t nbInputs, const DynamicPluginTensorDesc*,
                          int32_t) noexcept override { nb_inputs_seen_ = nbInputs; }
@@ -746,13 +755,19 @@ public:
                 {"precision", PluginFieldType::kINT32}, {"max_pillars_num", PluginFieldType::kINT32},
                 {"axis_id", PluginFieldType::kINT32},
                 {"in_proj_weight", PluginFieldType::kFLOAT32}, {"in_proj_bias", PluginFieldType::kFLOAT32},
-                {"out_proj_weight", PluginFieldType::kFLOAT32}, {"out_proj_bias", PluginFieldType::kFLOAT32}};
+                {"out_proj_weight", PluginFieldType::kFLOAT32}, {"out_proj_bias", PluginFieldType::kFLOAT32},
+                // optional: the encoder layer's norm1 -- output = LayerNorm(attention + x) (src/dsvt-ai-trt.cpp:669-676)
+                {"norm_weight", PluginFieldType::kFLOAT32}, {"norm_bias", PluginFieldType::kFLOAT32},
+                {"norm_eps", PluginFieldType::kFLOAT32}};
     }
     SetAttentionFusedPlugin(int max_sets, int S, int C, int heads, int precision, int max_pillars, int axis,
-                            const float* w_in, const float* b_in, const float* w_out, const float* b_out)
+                            const float* w_in, const float* b_in, const float* w_out, const float* b_out,
+                            const float* norm_w = nullptr, const float* norm_b = nullptr, float norm_eps = 0.f)
         : max_sets_(max_sets), S_(S), C_(C), heads_(heads), precision_(precision), max_pillars_(max_pillars), axis_(axis),
           w_in_(w_in, w_in + (size_t) 3 * C * C), b_in_(b_in, b_in + 3 * C),
-          w_out_(w_out, w_out + (size_t) C * C), b_out_(b_out, b_out + C) {}
+          w_out_(w_out, w_out + (size_t) C * C), b_out_(b_out, b_out + C), norm_eps_(norm_eps) {
+        if (norm_w && norm_b) { norm_w_.assign(norm_w, norm_w + C); norm_b_.assign(norm_b, norm_b + C); }
+    }
     ~SetAttentionFusedPlugin() override { release(); }
     static IPluginV2* from_fields(const PluginFieldCollection* fc) {
         const PluginField* wi = find_field(fc, "in_proj_weight");
@@ -762,11 +777,17 @@ public:
         const int C = field_int(fc, "channel_num");
         if (C <= 0 || C > 4096 || !wi || !bi || !wo || !bo || !wi->data || !bi->data || !wo->data || !bo->data) return nullptr;
         if (wi->length != 3 * C * C || bi->length != 3 * C || wo->length != C * C || bo->length != C) return nullptr;
+        const PluginField* nw = find_field(fc, "norm_weight");
+        const PluginField* nb = find_field(fc, "norm_bias");
+        const bool norm = nw && nb && nw->data && nb->data;
+        if (norm && (nw->length != C || nb->length != C)) return nullptr;
         return new (std::nothrow) SetAttentionFusedPlugin(
             field_int(fc, "max_win_num"), field_int(fc, "voxel_num_set"), C, field_int(fc, "num_heads", 0, 8),
             field_int(fc, "precision", 0, DSVT_ATTN_FP32_TC), field_int(fc, "max_pillars_num"), field_int(fc, "axis_id"),
             static_cast<const float*>(wi->data), static_cast<const float*>(bi->data),
-            static_cast<const float*>(wo->data), static_cast<const float*>(bo->data));
+            static_cast<const float*>(wo->data), static_cast<const float*>(bo->data),
+            norm ? static_cast<const float*>(nw->data) : nullptr, norm ? static_cast<const float*>(nb->data) : nullptr,
+            field_float(fc, "norm_eps", 0, 0.0f));
     }
     static IPluginV2* from_bytes(const void* data, size_t len) {
         Reader r(data, len);
@@ -776,20 +797,39 @@ public:
         std::vector<float> wi((size_t) 3 * C * C), bi(3 * C), wo((size_t) C * C), bo(C);
         r.get_array(wi.data(), wi.size()); r.get_array(bi.data(), bi.size());
         r.get_array(wo.data(), wo.size()); r.get_array(bo.data(), bo.size());
-        return new (std::nothrow) SetAttentionFusedPlugin(ms, S, C, H, prec, mp, axis, wi.data(), bi.data(), wo.data(), bo.data());
+        // trailer (absent in blobs written before the norm epilogue existed): has_norm, eps, gamma[C], beta[C]
+        std::vector<float> nw, nb;
+        float eps = 0.f;
+        if (r.left() >= sizeof(int) + sizeof(float)) {
+            const int has = r.get<int>();
+            eps = r.get<float>();
+            if (has) {
+                if (r.left() < (size_t) 2 * C * sizeof(float)) return nullptr;
+                nw.resize(C); nb.resize(C);
+                r.get_array(nw.data(), C); r.get_array(nb.data(), C);
+            }
+        }
+        return new (std::nothrow) SetAttentionFusedPlugin(ms, S, C, H, prec, mp, axis, wi.data(), bi.data(), wo.data(), bo.data(),
+                                                          nw.empty() ? nullptr : nw.data(), nb.empty() ? nullptr : nb.data(), eps);
     }
     size_t getSerializationSize() const noexcept override {
-        return 7 * sizeof(int) + ((size_t) 4 * C_ * C_ + 4 * C_) * sizeof(float);
+        return 7 * sizeof(int) + ((size_t) 4 * C_ * C_ + 4 * C_) * sizeof(float) + sizeof(int) + sizeof(float) +
+               (norm_w_.size() + norm_b_.size()) * sizeof(float);
     }
     void serialize(void* buf) const noexcept override {
         Writer w(buf);
         w.put(max_sets_); w.put(S_); w.put(C_); w.put(heads_); w.put(precision_); w.put(max_pillars_); w.put(axis_);
         w.put_array(w_in_.data(), w_in_.size()); w.put_array(b_in_.data(), b_in_.size());
         w.put_array(w_out_.data(), w_out_.size()); w.put_array(b_out_.data(), b_out_.size());
+        const int has = norm_w_.empty() ? 0 : 1;
+        w.put(has); w.put(norm_eps_);
+        if (has) { w.put_array(norm_w_.data(), norm_w_.size()); w.put_array(norm_b_.data(), norm_b_.size()); }
     }
     IPluginV2DynamicExt* clone() const noexcept override {
         auto* c = new (std::nothrow) SetAttentionFusedPlugin(max_sets_, S_, C_, heads_, precision_, max_pillars_, axis_,
-                                                             w_in_.data(), b_in_.data(), w_out_.data(), b_out_.data());
+                                                             w_in_.data(), b_in_.data(), w_out_.data(), b_out_.data(),
+                                                             norm_w_.empty() ? nullptr : norm_w_.data(),
+                                                             norm_b_.empty() ? nullptr : norm_b_.data(), norm_eps_);
         if (c) { c->setPluginNamespace(ns_.c_str()); c->nb_inputs_seen_ = nb_inputs_seen_; }
         return c;
     }
@@ -817,6 +857,13 @@ public:
         if (upload() != 0) return DSVT_ERR_CUDA;
         const dsvt_set_attention_params p = params(batch_of(in));
         const void* plan = nb_inputs_seen_ == 7 ? inputs[6] : nullptr;
+        if (norm_dev_)          // norm1 folded into the out-projection's epilogue: residual = x (input 0)
+            return report(dsvt_set_attention_fused_norm_launch(
+                              &p, dev_, static_cast<const float*>(inputs[0]), static_cast<const float*>(inputs[1]),
+                              static_cast<const int32_t*>(inputs[2]), static_cast<const float*>(inputs[3]),
+                              static_cast<const int32_t*>(inputs[4]), static_cast<const int32_t*>(inputs[5]),
+                              static_cast<const float*>(inputs[0]), norm_dev_, norm_dev_ + C_, norm_eps_,
+                              static_cast<float*>(outputs[0]), plan, ws, dsvt_set_attention_workspace_size(&p), stream), kName);
         return report(dsvt_set_attention_fused_planned_launch(
                           &p, dev_, static_cast<const float*>(inputs[0]), static_cast<const float*>(inputs[1]),
                           static_cast<const int32_t*>(inputs[2]), static_cast<const float*>(inputs[3]),
@@ -837,16 +884,24 @@ private:
         return p;
     }
     int upload() {
-        if (dev_) return 0;
-        dev_ = dsvt_attention_weights_create(C_, heads_, w_in_.data(), b_in_.data(), w_out_.data(), b_out_.data());
-        return dev_ ? 0 : 1;
+        if (!dev_) dev_ = dsvt_attention_weights_create(C_, heads_, w_in_.data(), b_in_.data(), w_out_.data(), b_out_.data());
+        if (!dev_) return 1;
+        if (!norm_w_.empty() && !norm_dev_) {
+            if (cudaMalloc(reinterpret_cast<void**>(&norm_dev_), (size_t) 2 * C_ * sizeof(float)) != cudaSuccess) return 1;
+            if (cudaMemcpy(norm_dev_, norm_w_.data(), C_ * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+                cudaMemcpy(norm_dev_ + C_, norm_b_.data(), C_ * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return 1;
+        }
+        return 0;
     }
     void release() {
         if (dev_) { dsvt_attention_weights_destroy(dev_); dev_ = nullptr; }
+        if (norm_dev_) { cudaFree(norm_dev_); norm_dev_ = nullptr; }
     }
     int max_sets_, S_, C_, heads_, precision_, max_pillars_, axis_;
-    std::vector<float> w_in_, b_in_, w_out_, b_out_;
+    std::vector<float> w_in_, b_in_, w_out_, b_out_, norm_w_, norm_b_;
+    float norm_eps_ = 0.f;
     dsvt_attention_weights* dev_ = nullptr;
+    float* norm_dev_ = nullptr;
     int nb_inputs_seen_ = 6;
 };
 
@@ -1039,6 +1094,226 @@ private:
     dsvt_map2bev_params p_;
 };
 
+// =================================================================================================
+// LayerNormChainPlugin (new) -- n = 1..3 consecutive (addElementWise(kSUM) + LayerNormPlugin) pairs of the reference graph
+// (src/dsvt-ai-trt.cpp:685-697, :750-756) as ONE node: y = LN_n(... LN_1(x + r_1) ... + r_n).
+// Inputs : x [B,max_pillars,C] f32, voxel_num [B] i32, r_1 .. r_n [B,max_pillars,C] f32.  Output [B,max_pillars,C] f32.
+// Fields : max_pillars_num, channel_num, n_stages (i32), eps (f32), weights f32[n*C], bias f32[n*C] (stage-major).
+// Serialised: 3 x i32, f32, then gamma[n*C], beta[n*C].  Same arithmetic as n LayerNormPlugin nodes (bit-identical).
+// =================================================================================================
+class LayerNormChainPlugin final : public PluginBase {
+public:
+    static constexpr const char* kName = "LayerNormChainPlugin";
+    static FieldList field_list() {
+        return {{"max_pillars_num", PluginFieldType::kINT32}, {"channel_num", PluginFieldType::kINT32},
+                {"n_stages", PluginFieldType::kINT32}, {"eps", PluginFieldType::kFLOAT32},
+                {"weights", PluginFieldType::kFLOAT32}, {"bias", PluginFieldType::kFLOAT32}};
+    }
+    LayerNormChainPlugin(int max_pillars, int channels, int n, float eps, const float* gamma, const float* beta)
+        : max_pillars_(max_pillars), channels_(channels), n_(n), eps_(eps),
+          gamma_(gamma, gamma + (size_t) n * channels), beta_(beta, beta + (size_t) n * channels) {}
+    ~LayerNormChainPlugin() override { release(); }
+    static IPluginV2* from_fields(const PluginFieldCollection* fc) {
+        const int C = field_int(fc, "channel_num"), n = field_int(fc, "n_stages");
+        const PluginField* g = find_field(fc, "weights");
+        const PluginField* b = find_field(fc, "bias");
+        if (C <= 0 || C > 65536 || n < 1 || n > 3 || !g || !b || !g->data || !b->data) return nullptr;
+        if (g->length != n * C || b->length != n * C) return nullptr;
+        return new (std::nothrow) LayerNormChainPlugin(field_int(fc, "max_pillars_num"), C, n, field_float(fc, "eps", 0, 0.0f),
+                                                       static_cast<const float*>(g->data), static_cast<const float*>(b->data));
+    }
+    static IPluginV2* from_bytes(const void* data, size_t len) {
+        Reader r(data, len);
+        const int mp = r.get<int>(), C = r.get<int>(), n = r.get<int>();
+        const float eps = r.get<float>();
+        if (!r.ok() || C <= 0 || C > 65536 || n < 1 || n > 3 || r.left() < (size_t) 2 * n * C * sizeof(float)) return nullptr;
+        std::vector<float> g((size_t) n * C), b((size_t) n * C);
+        r.get_array(g.data(), g.size());
+        r.get_array(b.data(), b.size());
+        return new (std::nothrow) LayerNormChainPlugin(mp, C, n, eps, g.data(), b.data());
+    }
+    size_t getSerializationSize() const noexcept override { return 3 * sizeof(int) + sizeof(float) + (gamma_.size() + beta_.size()) * sizeof(float); }
+    void serialize(void* buf) const noexcept override {
+        Writer w(buf);
+        w.put(max_pillars_); w.put(channels_); w.put(n_); w.put(eps_);
+        w.put_array(gamma_.data(), gamma_.size());
+        w.put_array(beta_.data(), beta_.size());
+    }
+    IPluginV2DynamicExt* clone() const noexcept override {
+        auto* c = new (std::nothrow) LayerNormChainPlugin(max_pillars_, channels_, n_, eps_, gamma_.data(), beta_.data());
+        if (c) c->setPluginNamespace(ns_.c_str());
+        return c;
+    }
+    int32_t initialize() noexcept override { return upload(); }
+    void terminate() noexcept override { release(); }
+    const char* getPluginType() const noexcept override { return kName; }
+    int32_t getNbOutputs() const noexcept override { return 1; }
+    DimsExprs getOutputDimensions(int32_t, const DimsExprs* in, int32_t, IExprBuilder& b) noexcept override {
+        return dims(b, in[0].d[0], {max_pillars_, channels_});
+    }
+    bool supportsFormatCombination(int32_t pos, const PluginTensorDesc* io, int32_t nbIn, int32_t nbOut) noexcept override {
+        if (pos < 0 || pos >= nbIn + nbOut || nbIn != 2 + n_ || io[pos].format != TensorFormat::kLINEAR) return false;
+        return io[pos].type == (pos == 1 ? I : F);
+    }
+    DataType getOutputDataType(int32_t, const DataType*, int32_t) const noexcept override { return F; }
+    int32_t enqueue(const PluginTensorDesc* in, const PluginTensorDesc*, const void* const* inputs,
+                    void* const* outputs, void*, cudaStream_t stream) noexcept override {
+        if (upload() != 0) return DSVT_ERR_CUDA;
+        dsvt_layer_norm_params p{batch_of(in), max_pillars_, channels_, eps_, 1};
+        dsvt_ln_stage st[3];
+        for (int s = 0; s < n_; ++s)
+            st[s] = dsvt_ln_stage{static_cast<const float*>(inputs[2 + s]), dev_ + (size_t) s * channels_,
+                                  dev_ + (size_t) (n_ + s) * channels_};
+        return report(dsvt_layer_norm_chain_launch(&p, static_cast<const float*>(inputs[0]), static_cast<const int32_t*>(inputs[1]),
+                                                   st, n_, static_cast<float*>(outputs[0]), stream), kName);
+    }
+protected:
+    const std::vector<DataType>& io_types() const override {
+        static const std::vector<DataType> t{F, I, F, F, F, F};
+        return t;
+    }
+    size_t nb_inputs() const override { return 2 + (size_t) n_; }
+private:
+    int upload() {
+        if (dev_) return 0;
+        const size_t n = gamma_.size();
+        if (cudaMalloc(reinterpret_cast<void**>(&dev_), 2 * n * sizeof(float)) != cudaSuccess) return 1;
+        if (cudaMemcpy(dev_, gamma_.data(), n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(dev_ + n, beta_.data(), n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) { release(); return 1; }
+        return 0;
+    }
+    void release() { if (dev_) { cudaFree(dev_); dev_ = nullptr; } }
+    int max_pillars_, channels_, n_;
+    float eps_;
+    std::vector<float> gamma_, beta_;
+    float* dev_ = nullptr;
+};
+
+// =================================================================================================
+// LinearPlugin (new) -- one TensorRT FullyConnected layer of the 3-D backbone with what follows it in the reference graph
+// folded into the same node (fullyConnected_gelu_fullyConnected src/dsvt-ai-trt.cpp:494-529, the kSUM + LayerNormPlugin
+// pairs :685-697 / :750-756):  y = act(x W^T + b), then optionally n_stages x (add residual_s, LayerNorm_s).
+// Inputs : x [B,max_rows,K] f32, rows [B] i32 (valid row count, e.g. Points2Features output 4), residual_1..n [B,max_rows,N].
+// Output : [B,max_rows,N] f32, rows beyond the count zero.
+// Fields : max_rows, in_features (K), out_features (N), activation (0 none, 1 GELU, 2 ReLU), precision (DSVT_ATTN_FP32_TC or
+//          DSVT_ATTN_FP16_GEMM), weight f32[N*K], bias f32[N], n_stages (0..3; needs N == 192, activation 0), ln_eps,
+//          ln_weights f32[n*N], ln_bias f32[n*N].
+// =================================================================================================
+class LinearPlugin final : public PluginBase {
+public:
+    static constexpr const char* kName = "LinearPlugin";
+    static FieldList field_list() {
+        return {{"max_rows", PluginFieldType::kINT32}, {"in_features", PluginFieldType::kINT32},
+                {"out_features", PluginFieldType::kINT32}, {"activation", PluginFieldType::kINT32},
+                {"precision", PluginFieldType::kINT32}, {"weight", PluginFieldType::kFLOAT32},
+                {"bias", PluginFieldType::kFLOAT32}, {"n_stages", PluginFieldType::kINT32},
+                {"ln_eps", PluginFieldType::kFLOAT32}, {"ln_weights", PluginFieldType::kFLOAT32},
+                {"ln_bias", PluginFieldType::kFLOAT32}};
+    }
+    LinearPlugin(int max_rows, int K, int N, int act, int precision, const float* W, const float* b, int n_ln, float eps,
+                 const float* gamma, const float* beta)
+        : max_rows_(max_rows), K_(K), N_(N), act_(act), precision_(precision), n_ln_(n_ln), eps_(eps),
+          w_(W, W + (size_t) N * K), b_(b, b + N) {
+        if (n_ln > 0) { gamma_.assign(gamma, gamma + (size_t) n_ln * N); beta_.assign(beta, beta + (size_t) n_ln * N); }
+    }
+    ~LinearPlugin() override { release(); }
+    static bool valid(int K, int N, int act, int n_ln) {
+        return K > 0 && N > 0 && K % 192 == 0 && N % 192 == 0 && K <= 768 && N <= 768 && act >= 0 && act <= 2 && n_ln >= 0 &&
+               n_ln <= 3 && (n_ln == 0 || (N == 192 && act == 0 && K <= 384));
+    }
+    static IPluginV2* from_fields(const PluginFieldCollection* fc) {
+        const int K = field_int(fc, "in_features"), N = field_int(fc, "out_features"), act = field_int(fc, "activation");
+        const int n_ln = field_int(fc, "n_stages");
+        const PluginField* w = find_field(fc, "weight");
+        const PluginField* b = find_field(fc, "bias");
+        const PluginField* g = find_field(fc, "ln_weights");
+        const PluginField* be = find_field(fc, "ln_bias");
+        if (!valid(K, N, act, n_ln) || !w || !b || !w->data || !b->data || w->length != N * K || b->length != N) return nullptr;
+        if (n_ln > 0 && (!g || !be || !g->data || !be->data || g->length != n_ln * N || be->length != n_ln * N)) return nullptr;
+        return new (std::nothrow) LinearPlugin(field_int(fc, "max_rows"), K, N, act, field_int(fc, "precision", 0, DSVT_ATTN_FP32_TC),
+                                               static_cast<const float*>(w->data), static_cast<const float*>(b->data), n_ln,
+                                               field_float(fc, "ln_eps", 0, 0.0f), n_ln ? static_cast<const float*>(g->data) : nullptr,
+                                               n_ln ? static_cast<const float*>(be->data) : nullptr);
+    }
+    static IPluginV2* from_bytes(const void* data, size_t len) {
+        Reader r(data, len);
+        const int mr = r.get<int>(), K = r.get<int>(), N = r.get<int>(), act = r.get<int>(), prec = r.get<int>(), n_ln = r.get<int>();
+        const float eps = r.get<float>();
+        if (!r.ok() || !valid(K, N, act, n_ln) || r.left() < ((size_t) N * K + N + (size_t) 2 * n_ln * N) * sizeof(float)) return nullptr;
+        std::vector<float> w((size_t) N * K), b(N), g((size_t) n_ln * N), be((size_t) n_ln * N);
+        r.get_array(w.data(), w.size()); r.get_array(b.data(), b.size());
+        r.get_array(g.data(), g.size()); r.get_array(be.data(), be.size());
+        return new (std::nothrow) LinearPlugin(mr, K, N, act, prec, w.data(), b.data(), n_ln, eps, g.data(), be.data());
+    }
+    size_t getSerializationSize() const noexcept override {
+        return 6 * sizeof(int) + sizeof(float) + (w_.size() + b_.size() + gamma_.size() + beta_.size()) * sizeof(float);
+    }
+    void serialize(void* buf) const noexcept override {
+        Writer w(buf);
+        w.put(max_rows_); w.put(K_); w.put(N_); w.put(act_); w.put(precision_); w.put(n_ln_); w.put(eps_);
+        w.put_array(w_.data(), w_.size()); w.put_array(b_.data(), b_.size());
+        w.put_array(gamma_.data(), gamma_.size()); w.put_array(beta_.data(), beta_.size());
+    }
+    IPluginV2DynamicExt* clone() const noexcept override {
+        auto* c = new (std::nothrow) LinearPlugin(max_rows_, K_, N_, act_, precision_, w_.data(), b_.data(), n_ln_, eps_,
+                                                  gamma_.data(), beta_.data());
+        if (c) c->setPluginNamespace(ns_.c_str());
+        return c;
+    }
+    int32_t initialize() noexcept override { return upload(); }
+    void terminate() noexcept override { release(); }
+    const char* getPluginType() const noexcept override { return kName; }
+    int32_t getNbOutputs() const noexcept override { return 1; }
+    DimsExprs getOutputDimensions(int32_t, const DimsExprs* in, int32_t, IExprBuilder& b) noexcept override {
+        return dims(b, in[0].d[0], {max_rows_, N_});
+    }
+    bool supportsFormatCombination(int32_t pos, const PluginTensorDesc* io, int32_t nbIn, int32_t nbOut) noexcept override {
+        if (pos < 0 || pos >= nbIn + nbOut || nbIn != 2 + n_ln_ || io[pos].format != TensorFormat::kLINEAR) return false;
+        return io[pos].type == (pos == 1 ? I : F);
+    }
+    DataType getOutputDataType(int32_t, const DataType*, int32_t) const noexcept override { return F; }
+    int32_t enqueue(const PluginTensorDesc* in, const PluginTensorDesc*, const void* const* inputs,
+                    void* const* outputs, void*, cudaStream_t stream) noexcept override {
+        if (upload() != 0) return DSVT_ERR_CUDA;
+        if (batch_of(in) != 1) { std::fprintf(stderr, "[dsvt_b200] LinearPlugin: batch 1 only\n"); return DSVT_ERR_UNSUPPORTED; }
+        const float* x = static_cast<const float*>(inputs[0]);
+        const int32_t* rows = static_cast<const int32_t*>(inputs[1]);
+        float* y = static_cast<float*>(outputs[0]);
+        if (n_ln_ == 0) return report(dsvt_linear_rows_launch(dev_, x, rows, max_rows_, act_, y, 1, stream), kName);
+        dsvt_ln_stage st[3];
+        for (int s = 0; s < n_ln_; ++s)
+            st[s] = dsvt_ln_stage{static_cast<const float*>(inputs[2 + s]), ln_dev_ + (size_t) s * N_, ln_dev_ + (size_t) (n_ln_ + s) * N_};
+        return report(dsvt_linear_rows_norm_launch(dev_, x, rows, max_rows_, st, n_ln_, eps_, y, 1, stream), kName);
+    }
+protected:
+    const std::vector<DataType>& io_types() const override {
+        static const std::vector<DataType> t{F, I, F, F, F, F};
+        return t;
+    }
+    size_t nb_inputs() const override { return 2 + (size_t) n_ln_; }
+private:
+    int upload() {
+        if (!dev_) dev_ = dsvt_linear_weights_create(N_, K_, w_.data(), b_.data(), precision_);
+        if (!dev_) return 1;
+        if (n_ln_ > 0 && !ln_dev_) {
+            const size_t n = gamma_.size();
+            if (cudaMalloc(reinterpret_cast<void**>(&ln_dev_), 2 * n * sizeof(float)) != cudaSuccess) return 1;
+            if (cudaMemcpy(ln_dev_, gamma_.data(), n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+                cudaMemcpy(ln_dev_ + n, beta_.data(), n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return 1;
+        }
+        return 0;
+    }
+    void release() {
+        if (dev_) { dsvt_linear_weights_destroy(dev_); dev_ = nullptr; }
+        if (ln_dev_) { cudaFree(ln_dev_); ln_dev_ = nullptr; }
+    }
+    int max_rows_, K_, N_, act_, precision_, n_ln_;
+    float eps_;
+    std::vector<float> w_, b_, gamma_, beta_;
+    dsvt_linear_weights* dev_ = nullptr;
+    float* ln_dev_ = nullptr;
+};
+
 // registration: from the library only (the reference registers from two images)
 using Points2FeaturesPluginCreator = CreatorBase<Points2FeaturesPlugin>;
 using WindowPartitionPluginCreator = CreatorBase<WindowPartitionPlugin>;
@@ -1053,6 +1328,8 @@ using SetAttentionFusedPluginCreator = CreatorBase<SetAttentionFusedPlugin>;
 using TorchScatterMaxPluginCreator = CreatorBase<TorchScatterMaxPlugin>;
 using Map2BevPluginCreator = CreatorBase<Map2BevPlugin>;
 using SetAttentionPlanPluginCreator = CreatorBase<SetAttentionPlanPlugin>;
+using LayerNormChainPluginCreator = CreatorBase<LayerNormChainPlugin>;
+using LinearPluginCreator = CreatorBase<LinearPlugin>;
 
 REGISTER_TENSORRT_PLUGIN(Points2FeaturesPluginCreator);
 REGISTER_TENSORRT_PLUGIN(WindowPartitionPluginCreator);
@@ -1067,5 +1344,7 @@ REGISTER_TENSORRT_PLUGIN(SetAttentionFusedPluginCreator);
 REGISTER_TENSORRT_PLUGIN(TorchScatterMaxPluginCreator);
 REGISTER_TENSORRT_PLUGIN(Map2BevPluginCreator);
 REGISTER_TENSORRT_PLUGIN(SetAttentionPlanPluginCreator);
+REGISTER_TENSORRT_PLUGIN(LayerNormChainPluginCreator);
+REGISTER_TENSORRT_PLUGIN(LinearPluginCreator);
 
 }  // namespace dsvt_plugins

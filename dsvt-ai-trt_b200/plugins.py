@@ -259,15 +259,42 @@ def add_set_attention_op(lib, max_win_num, voxel_num_set, channel_num, num_heads
 
 
 def add_set_attention_fused_op(lib, max_win_num, voxel_num_set, channel_num, num_heads, max_pillars_num, axis_id,
-                               in_proj_weight, in_proj_bias, out_proj_weight, out_proj_bias, precision=3):
+                               in_proj_weight, in_proj_bias, out_proj_weight, out_proj_bias, precision=3,
+                               norm_weight=None, norm_bias=None, norm_eps=0.0):
     """One node for GetValueByIndexPlugin -> multHeadAttention() -> MapSetFeature2VoxelPlugin
-    (src/dsvt-ai-trt.cpp:653-668).  precision: DSVT_ATTN_* (3 = FP32-accurate tcgen05 GEMM pipeline)."""
-    return lib.create("SetAttentionFusedPlugin", {
+    (src/dsvt-ai-trt.cpp:653-668).  precision: DSVT_ATTN_* (3 = FP32-accurate tcgen05 GEMM pipeline).
+    norm_weight / norm_bias: also folds the kSUM + LayerNormPlugin behind it (norm1(y + x), :669-676) into the node."""
+    fields = {
         "max_win_num": max_win_num, "voxel_num_set": voxel_num_set, "channel_num": channel_num,
         "num_heads": num_heads, "precision": precision, "max_pillars_num": max_pillars_num, "axis_id": axis_id,
         "in_proj_weight": np.asarray(in_proj_weight, np.float32), "in_proj_bias": np.asarray(in_proj_bias, np.float32),
         "out_proj_weight": np.asarray(out_proj_weight, np.float32),
-        "out_proj_bias": np.asarray(out_proj_bias, np.float32)})
+        "out_proj_bias": np.asarray(out_proj_bias, np.float32)}
+    if norm_weight is not None:
+        fields.update({"norm_weight": np.asarray(norm_weight, np.float32), "norm_bias": np.asarray(norm_bias, np.float32),
+                       "norm_eps": float(norm_eps)})
+    return lib.create("SetAttentionFusedPlugin", fields)
+
+
+def add_layer_norm_chain_op(lib, max_pillars_num, channel_num, weights, bias, eps=0.0):
+    """n = len(weights) consecutive (kSUM + LayerNormPlugin) pairs as one node; weights / bias [n, C].
+    Inputs: x, voxel_num, residual_1 .. residual_n."""
+    w, b = np.asarray(weights, np.float32), np.asarray(bias, np.float32)
+    return lib.create("LayerNormChainPlugin", {
+        "max_pillars_num": max_pillars_num, "channel_num": channel_num, "n_stages": int(w.shape[0]), "eps": float(eps),
+        "weights": w, "bias": b})
+
+
+def add_linear_op(lib, max_rows, in_features, out_features, weight, bias, activation=0, precision=3, ln_weights=None,
+                  ln_bias=None, ln_eps=0.0):
+    """A TensorRT FullyConnected layer of the 3-D backbone (+ GELU / ReLU, or + the LayerNorm chain that follows the FFN) as
+    one node.  Inputs: x [B,max_rows,K], rows [B], residual_1 .. residual_n (n = len(ln_weights))."""
+    fields = {"max_rows": max_rows, "in_features": in_features, "out_features": out_features, "activation": activation,
+              "precision": precision, "weight": np.asarray(weight, np.float32), "bias": np.asarray(bias, np.float32),
+              "n_stages": 0 if ln_weights is None else int(np.asarray(ln_weights).shape[0]), "ln_eps": float(ln_eps)}
+    if ln_weights is not None:
+        fields.update({"ln_weights": np.asarray(ln_weights, np.float32), "ln_bias": np.asarray(ln_bias, np.float32)})
+    return lib.create("LinearPlugin", fields)
 
 
 def add_torch_scatter_max(lib, max_points_num, max_pillars_num, feature_num):

@@ -251,12 +251,16 @@ dsvt_attention_weights* dsvt_attention_weights_create(int32_t channel_num, int32
                                                       const float* out_proj_weight, const float* out_proj_bias);
 void dsvt_attention_weights_destroy(dsvt_attention_weights* w);
 
+/* bytes of workspace the launch entry points need for p->precision; max_pillars_num == 0 selects the plugin-shaped form */
 size_t dsvt_set_attention_workspace_size(const dsvt_set_attention_params* p);
 /*
  * Plugin-shaped form (drop-in for the multHeadAttention() sub-graph):
  * in : q, k, v [B,max_set_num,S,C] f32 ; mask [B,max_set_num,num_heads,S] f32 (additive key mask)
  *      set_num [B] i32 or NULL (NULL = all max_set_num sets, as the reference graph does)
  * out: [B,max_set_num,S,C] f32
+ * Precisions: DSVT_ATTN_FP32 (CUDA cores, no workspace) and the tensor-core pipeline DSVT_ATTN_FP32_TC / DSVT_ATTN_FP16_GEMM
+ * (projections of the set slots on tcgen05, per-set core in FP32; workspace of dsvt_set_attention_workspace_size bytes with
+ * max_pillars_num = 0; q, k, v 32-byte aligned).
  */
 int dsvt_set_attention_launch(const dsvt_set_attention_params* p, const dsvt_attention_weights* w,
                               const float* q, const float* k, const float* v, const float* mask,

@@ -188,7 +188,7 @@ def test_set_attention_fused_plugin(lib, plg, precision):
                                            precision=precision)
         p2, blob = roundtrip(lib, p)
         assert blob[:28] == struct.pack("<7i", max_sets, S, C, H, precision, max_pillars, axis)
-        assert len(blob) == 7 * 4 + (4 * C * C + 4 * C) * 4
+        assert len(blob) == 7 * 4 + (4 * C * C + 4 * C) * 4 + 8            # + (has_norm = 0, eps) trailer
         q, k, v = cpu.get_value_by_index(x, pos, idx, n_sets, axis)
         a = cpu.set_attention(q, k, v, mask, n_sets, w_in, b_in, w_out, b_out)
         ref = cpu.map_set_feature2voxel(a, idx, n_sets, axis, max_pillars)
@@ -208,8 +208,123 @@ def test_set_attention_fused_plugin(lib, plg, precision):
             assert torch.equal(out7, out)
 
 
+@pytest.mark.parametrize("precision", [3, 4])
+def test_set_attention_plugin_tensor_cores(lib, plg, attention_case, precision):
+    """The true drop-in for multHeadAttention() (q, k, v pre-gathered by GetValueByIndexPlugin) on the tensor-core pipeline:
+    SetAttentionPlugin with precision DSVT_ATTN_FP32_TC / DSVT_ATTN_FP16_GEMM against the torch-MHA golden case and, with
+    the optional set count, against the oracle on a padded frame-shaped input."""
+    c = attention_case
+    n, S, C = c["q"].shape
+    tol = 2e-5 if precision == 3 else 1e-2
+    p = plg.add_set_attention_op(lib, n, S, C, 8, c["w_in"], c["b_in"], c["w_out"], c["b_out"], precision=precision)
+    p2, _ = roundtrip(lib, p)
+    for plugin in (p, p2):
+        (out,) = plugin.enqueue([dev(c["q"])[None], dev(c["k"])[None], dev(c["v"])[None], dev(c["mask"])[None]],
+                                poison=float("nan"))
+        assert np.abs(out[0].cpu().numpy() - c["out"]).max() <= tol
+    rng = np.random.default_rng(8)
+    n_sets, max_sets = 150, 200
+    q = rng.standard_normal((max_sets, S, C)).astype(np.float32)
+    k = (q + 0.25 * rng.standard_normal(q.shape)).astype(np.float32)
+    v = rng.standard_normal((max_sets, S, C)).astype(np.float32)
+    mask = np.zeros((max_sets, 8, S), np.float32)
+    for s_ in range(max_sets):
+        mask[s_, :, rng.permutation(S - 1)[: rng.integers(0, S - 1)] + 1] = -np.finfo(np.float32).max
+    p = plg.add_set_attention_op(lib, max_sets, S, C, 8, c["w_in"], c["b_in"], c["w_out"], c["b_out"], precision=precision)
+    (out,) = p.enqueue([dev(q)[None], dev(k)[None], dev(v)[None], dev(mask)[None], i32(n_sets)], poison=float("nan"))
+    ref = cpu.set_attention(q, k, v, mask, n_sets, c["w_in"], c["b_in"], c["w_out"], c["b_out"])
+    got = out[0].cpu().numpy()
+    assert np.all(got[n_sets:] == 0)
+    assert np.abs(got[:n_sets] - ref[:n_sets]).max() <= tol
+
+
+def test_set_attention_fused_plugin_with_norm(lib, plg, frame0, cfgs):
+    """SetAttentionFusedPlugin with the optional norm fields = GetValueByIndex -> multHeadAttention -> MapSetFeature2Voxel ->
+    kSUM -> LayerNormPlugin (src/dsvt-ai-trt.cpp:653-676) as ONE node, on the reference frame, against the oracle chain."""
+    cfg = cfgs.REFERENCE
+    o = cpu.points2features(pad_points(frame0, cfg.max_points_num), len(frame0), cfg)
+    V, C = o["pillar_num"], 192
+    owp = cpu.window_partition(o["coords"], V, cfg, 0)
+    ogs = cpu.get_set(owp["global_index"], owp["coors_in_win"], owp["voxel_num_in_win"], owp["win_num"], cfg, 0)
+    ns, idx, mask = ogs["set_num"], ogs["global_index_in_set"], ogs["mask_expand_0"]
+    rng = np.random.default_rng(21)
+    x = np.zeros((cfg.max_pillars_num, C), np.float32); pos = np.zeros_like(x)
+    x[:V] = rng.standard_normal((V, C)); pos[:V] = rng.standard_normal((V, C)) * 0.5
+    w_in = (rng.standard_normal((3 * C, C)) * 0.06).astype(np.float32); b_in = (rng.standard_normal(3 * C) * 0.1).astype(np.float32)
+    w_out = (rng.standard_normal((C, C)) * 0.06).astype(np.float32); b_out = (rng.standard_normal(C) * 0.1).astype(np.float32)
+    gamma = (1 + 0.1 * rng.standard_normal(C)).astype(np.float32); beta = (0.1 * rng.standard_normal(C)).astype(np.float32)
+    for axis in (0, 1):
+        p = plg.add_set_attention_fused_op(lib, cfg.max_win_num, 36, C, 8, cfg.max_pillars_num, axis, w_in, b_in, w_out, b_out,
+                                           precision=3, norm_weight=gamma, norm_bias=beta)
+        p2, blob = roundtrip(lib, p)
+        assert len(blob) == 7 * 4 + (4 * C * C + 4 * C) * 4 + 8 + 2 * C * 4
+        q, k, v = cpu.get_value_by_index(x, pos, idx, ns, axis)
+        a = cpu.set_attention(q, k, v, mask, ns, w_in, b_in, w_out, b_out)
+        y = cpu.map_set_feature2voxel(a, idx, ns, axis, cfg.max_pillars_num)
+        ref = cpu.layer_norm(y, V, gamma, beta, 0.0, residual=x)
+        for plugin in (p, p2):
+            (out,) = plugin.enqueue([dev(x)[None], dev(pos)[None], dev(idx)[None], dev(mask)[None], i32(ns), i32(V)],
+                                    poison=float("nan"))
+            got = out[0].cpu().numpy()
+            assert np.all(got[V:] == 0)
+            assert np.abs(got - ref).max() <= 1e-4
+
+
+@pytest.mark.parametrize("n_stages", [1, 2, 3])
+def test_layer_norm_chain_plugin(lib, plg, n_stages):
+    """LayerNormChainPlugin == n_stages x (addElementWise(kSUM) + LayerNormPlugin), bit-identical to the single plugins."""
+    rng = np.random.default_rng(n_stages)
+    mp, C, V = 700, 192, 555
+    x = np.zeros((mp, C), np.float32); x[:V] = rng.standard_normal((V, C))
+    res = [rng.standard_normal((mp, C)).astype(np.float32) for _ in range(n_stages)]
+    gam = (1 + 0.1 * rng.standard_normal((n_stages, C))).astype(np.float32)
+    bet = (0.1 * rng.standard_normal((n_stages, C))).astype(np.float32)
+    p = plg.add_layer_norm_chain_op(lib, mp, C, gam, bet)
+    p, blob = roundtrip(lib, p)
+    assert blob[:16] == struct.pack("<3if", mp, C, n_stages, 0.0)
+    (out,) = p.enqueue([dev(x)[None], i32(V)] + [dev(r)[None] for r in res], poison=float("nan"))
+    ref, single = x, dev(x)[None]
+    for s_ in range(n_stages):
+        ref = cpu.layer_norm(ref, V, gam[s_], bet[s_], 0.0, residual=res[s_])
+        ln = plg.add_layer_norm_op(lib, mp, C, gam[s_], bet[s_])
+        (single,) = ln.enqueue([single + dev(res[s_])[None], i32(V)])
+    got = out[0].cpu().numpy()
+    assert np.all(got[V:] == 0) and np.abs(got - ref).max() <= 2e-5
+    assert torch.equal(out, single)
+
+
+@pytest.mark.parametrize("K,N,act,n_ln", [(192, 384, 1, 0), (384, 192, 0, 0), (384, 192, 0, 2), (384, 192, 0, 3), (192, 192, 2, 0)])
+def test_linear_plugin(lib, plg, K, N, act, n_ln):
+    """LinearPlugin: a TensorRT FullyConnected layer of the 3-D backbone (+ GELU / ReLU, or + the LayerNorm chain behind the
+    FFN) as one node, against float64."""
+    rng = np.random.default_rng(K + N + act + n_ln)
+    mr, rows = 1300, 1000
+    x = np.zeros((mr, K), np.float32); x[:rows] = rng.standard_normal((rows, K))
+    W = (rng.standard_normal((N, K)) * 0.06).astype(np.float32); b = (rng.standard_normal(N) * 0.05).astype(np.float32)
+    res = [rng.standard_normal((mr, N)).astype(np.float32) for _ in range(n_ln)]
+    gam = (1 + 0.1 * rng.standard_normal((n_ln, N))).astype(np.float32)
+    bet = (0.1 * rng.standard_normal((n_ln, N))).astype(np.float32)
+    p = plg.add_linear_op(lib, mr, K, N, W, b, activation=act, ln_weights=gam if n_ln else None, ln_bias=bet if n_ln else None)
+    p, blob = roundtrip(lib, p)
+    assert blob[:24] == struct.pack("<6i", mr, K, N, act, 3, n_ln)
+    (out,) = p.enqueue([dev(x)[None], i32(rows)] + [dev(r)[None] for r in res], poison=float("nan"))
+    y = x[:rows].astype(np.float64) @ W.T.astype(np.float64) + b
+    if act == 1:
+        y = (0.5 + 0.5 * np.tanh(y * (0.035677408136300125 * y * y + 0.7978845608028654))) * y
+    elif act == 2:
+        y = np.maximum(y, 0.0)
+    for s_ in range(n_ln):
+        y = y + res[s_][:rows]
+        mu = y.mean(1, keepdims=True)
+        y = (y - mu) / np.sqrt(((y - mu) ** 2).mean(1, keepdims=True)) * gam[s_] + bet[s_]
+    got = out[0].cpu().numpy()
+    assert np.all(got[rows:] == 0)
+    assert np.abs(got[:rows] - y).max() <= 5e-5
+
+
 def test_registry_and_formats(lib):
     names = set(lib.registered())
     assert {"Points2FeaturesPlugin", "GetSetPlugin", "GeluPlugin", "LayerNormPlugin", "FilterBoxByScorePlugin",
             "WindowPartitionPlugin", "GetValueByIndexPlugin", "MapSetFeature2VoxelPlugin", "SetAttentionPlugin",
-            "SetAttentionFusedPlugin", "SetAttentionPlanPlugin", "TorchScatterMaxPlugin", "Map2BevPlugin"} <= names
+            "SetAttentionFusedPlugin", "SetAttentionPlanPlugin", "TorchScatterMaxPlugin", "Map2BevPlugin",
+            "LayerNormChainPlugin", "LinearPlugin"} <= names
