@@ -305,16 +305,13 @@ def plugin_breakdown(slot, cfg, peaks, reps=5):
     res["ffn_linear2_norm3"] = {"us": us, "flops": 2 * C * Fc * V, "bytes": 4 * V * (Fc + 3 * C + C), "calls_per_frame": 4,
                                 "scope": "next#4 + 3 LayerNormPlugins"}
     pipeline_prec = f.precision in (capi.DSVT_ATTN_FP32_TC, capi.DSVT_ATTN_FP16_GEMM)
-    lib = capi._lib()
-    # kernels are timed ALONE here: the attention GEMMs get every SM (the throughput runs above use half per launch)
-    prev_frac = lib.dsvt_debug_set_gemm_sm_fraction(100)
     for i in (0, 1):
         gs = f.gs[i]
         plan = f.plans.get((i, 0)) if getattr(f, "plans", None) else None
-        call = lambda: capi.set_attention_fused(w.attn[i], x, f.pos_out[i][0], gs.global_index_in_set[0],
-                                                gs.mask_expand_0[0], gs.set_num, Vt, axis=0,
-                                                out=f.src_b, precision=f.precision, workspace=f.attn_ws, plan=plan,
-                                                norm=(x, w.gamma[0], w.beta[0], cfg.layer_norm_eps))
+        call = lambda stages=7: capi.set_attention_fused(
+            w.attn[i], x, f.pos_out[i][0], gs.global_index_in_set[0], gs.mask_expand_0[0], gs.set_num, Vt, axis=0,
+            out=f.src_b, precision=f.precision, workspace=f.attn_ws, plan=plan,
+            norm=(x, w.gamma[0], w.beta[0], cfg.layer_norm_eps), stages=stages)
         us = timed(call)
         if plan is not None:      # one plan per (partition, axis) serves two layers: 4 plan builds per frame
             pus = timed(lambda: capi.set_attention_plan(gs.global_index_in_set[0], gs.mask_expand_0[0], gs.set_num, 0,
@@ -323,30 +320,17 @@ def plugin_breakdown(slot, cfg, peaks, reps=5):
                                               "calls_per_frame": 2}
         flops = 11612160 * NS[i] if S == 36 else None
         res[f"set_attention_{i}"] = {"us": us, "flops": flops, "bytes": 83088 * NS[i] + 590000, "calls_per_frame": 4}
-        if pipeline_prec:
-            # the three kernels of the GEMM pipeline, CUDA events recorded between them inside the library
-            lib.dsvt_debug_attention_stage_timing(1)
-            st = []
-            for _ in range(reps):
-                flush.zero_()
-                call()
-                torch.cuda.synchronize()
-                buf = (ctypes.c_float * 3)()
-                if lib.dsvt_debug_attention_stage_us(buf) == 0:
-                    st.append(list(buf))
-            lib.dsvt_debug_attention_stage_timing(0)
-            if st:
-                st.sort(key=sum)
-                a, b, c = st[len(st) // 2]
-                split = 3 if f.precision == capi.DSVT_ATTN_FP32_TC else 1
-                res[f"set_attention_{i}"]["kernels"] = {
-                    "qkv_proj_gemm": {"us": round(a, 2), "flops": 2 * 3 * C * C * V, "mma_flops_issued": split * 2 * 3 * C * C * V,
-                                      "bytes": 4 * V * (2 * C + 3 * C) + 3 * 2 * split * 2 * C * C},
-                    "attn_core": {"us": round(b, 2), "bytes": 4 * V * (3 * C + C) + NS[i] * (S * 4 + 8 * S * 4),
-                                  "flops": None},
-                    "out_proj_gemm_norm1": {"us": round(c, 2), "flops": 2 * C * C * V, "mma_flops_issued": split * 2 * C * C * V,
-                                            "bytes": 4 * V * 3 * C + 2 * split * 2 * C * C}}
-    lib.dsvt_debug_set_gemm_sm_fraction(prev_frac)
+        if pipeline_prec and plan is not None:
+            # the three kernels of the pipeline, one launch each (dsvt_set_attention_fused_stages_launch), CUDA events around
+            a, b, c = timed(lambda: call(1)), timed(lambda: call(2)), timed(lambda: call(4))
+            split = 3 if f.precision == capi.DSVT_ATTN_FP32_TC else 1
+            res[f"set_attention_{i}"]["kernels"] = {
+                "qkv_proj_gemm": {"us": round(a, 2), "flops": 2 * 3 * C * C * V, "mma_flops_issued": split * 2 * 3 * C * C * V,
+                                  "bytes": 4 * V * (2 * C + 3 * C) + 3 * 2 * split * 2 * C * C},
+                "attn_core": {"us": round(b, 2), "bytes": 4 * V * (3 * C + C) + NS[i] * (S * 4 + 8 * S * 4),
+                              "flops": None},
+                "out_proj_gemm_norm1": {"us": round(c, 2), "flops": 2 * C * C * V, "mma_flops_issued": split * 2 * C * C * V,
+                                        "bytes": 4 * V * 3 * C + 2 * split * 2 * C * C}}
     for k, r in res.items():
         if r.get("bytes"):
             r["gbs"] = r["bytes"] / r["us"] * 1e-3
@@ -521,9 +505,6 @@ def load_ncu_traffic():
 
 def _main():
     args = parse()
-    # throughput setting of the attention GEMMs: half the SMs per launch (each CTA amortises its resident weight image
-    # over twice the row tiles and the other half serves the frames of the other streams); measured +3 % frames/s
-    os.environ.setdefault("DSVT_GEMM_SM_FRACTION", "50")
     if args.impl == "reference":
         ref = importlib.import_module("bench_reference")
         return ref.main(args)          # a dict on rank 0, None elsewhere
@@ -622,7 +603,6 @@ def _main():
                 "bytes_note": "whole job: all ranks' pinned-host clouds in, boxes + counts out, per step"},
         "gpu_launches": int(launches_per_frame * F * args.steps * 2),
         "launches_per_frame": int(launches_per_frame),
-        "gemm_sm_fraction_pct": int(os.environ.get("DSVT_GEMM_SM_FRACTION", "100")),
         "clocks": clocks,
         "roofline": roof,
         "plugins": plugins,

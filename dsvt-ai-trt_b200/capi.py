@@ -333,12 +333,13 @@ def set_attention_plan(global_index_in_set, mask, set_num, axis, max_pillars, he
 
 
 def set_attention_fused(weights, x, pos, global_index_in_set, mask, set_num, voxel_num, axis, out=None,
-                        precision=DSVT_ATTN_FP32, zero_tails=1, workspace=None, plan=None, norm=None):
+                        precision=DSVT_ATTN_FP32, zero_tails=1, workspace=None, plan=None, norm=None, stages=7):
     """Fused gather + attention + scatter: x,pos [B,max_pillars,C], global_index_in_set [B,2,max_sets,S].
     `workspace`: uint8 device tensor of dsvt_set_attention_workspace_size bytes (allocated here when None and the
     precision needs one; pass a persistent buffer when capturing CUDA graphs).
     `norm` = (residual, gamma, beta, eps): out = LayerNorm(attention + residual) in the out-projection's epilogue
-    (dsvt_set_attention_fused_norm_launch; GEMM-pipeline precisions)."""
+    (dsvt_set_attention_fused_norm_launch; GEMM-pipeline precisions).
+    `stages` != 7: dsvt_set_attention_fused_stages_launch -- only the named kernels (1 QKV GEMM, 2 core, 4 out-projection)."""
     _need(x, torch.float32, "x")
     _need(pos, torch.float32, "pos")
     _need(global_index_in_set, torch.int32, "global_index_in_set")
@@ -351,6 +352,14 @@ def set_attention_fused(weights, x, pos, global_index_in_set, mask, set_num, vox
     ws_bytes = int(_lib().dsvt_set_attention_workspace_size(ctypes.byref(p)))
     if ws_bytes and workspace is None:
         workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    if stages != 7:
+        res, gamma, beta, eps = norm if norm is not None else (None, None, None, 0.0)
+        rc = _lib().dsvt_set_attention_fused_stages_launch(
+            ctypes.byref(p), c_void_p(weights.handle), _ptr(x), _ptr(pos), _ptr(global_index_in_set), _ptr(mask),
+            _ptr(set_num), _ptr(voxel_num), _ptr(res), _ptr(gamma), _ptr(beta), c_float(eps), _ptr(out), _ptr(plan),
+            _ptr(workspace), c_size_t(workspace.numel() if workspace is not None else 0), c_int32(stages), _stream())
+        _check(rc, "dsvt_set_attention_fused_stages_launch")
+        return out
     if norm is not None:
         res, gamma, beta, eps = norm
         for t, n in ((res, "residual"), (gamma, "gamma"), (beta, "beta")):

@@ -35,7 +35,8 @@ struct AttnNorm { const float* residual; const float* gamma; const float* beta; 
 int set_attention_split_fused(const dsvt_set_attention_params* p, const void* split_blob, const float* out_mul,
                               bool split, const float* x, const float* pos, const int* idx, const float* mask,
                               const int* set_num, const int* voxel_num, float* out, const void* plan,
-                              void* workspace, size_t workspace_bytes, cudaStream_t st, const AttnNorm* norm = nullptr);
+                              void* workspace, size_t workspace_bytes, cudaStream_t st, const AttnNorm* norm = nullptr,
+                              int stages = 7);
 
 // the same pipeline for pre-gathered q / k / v [B, max_sets, S, 192] (the drop-in for multHeadAttention() itself)
 size_t attention_split_plugin_workspace(const dsvt_set_attention_params* p);

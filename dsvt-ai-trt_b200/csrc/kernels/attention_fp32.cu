@@ -137,8 +137,12 @@ __device__ __forceinline__ void project(const float* __restrict__ Xs, const floa
     }
 }
 
+#ifdef DSVT_PROFILE      // phase stamps of one CTA (tools/fp32_profile.py): never in the product build
 __device__ long long g_fp32_prof[32];
 #define F32_PROF(i) do { if (blockIdx.x == 5 && blockIdx.y == 0 && threadIdx.x == 0) g_fp32_prof[i] = clock64(); } while (0)
+#else
+#define F32_PROF(i) do { } while (0)
+#endif
 
 template <int S, bool FUSED>
 __global__ void __launch_bounds__(kThreadsA, (S <= 36) ? 2 : 1)
@@ -242,7 +246,9 @@ set_attention_fp32_kernel(const float* __restrict__ qin, const float* __restrict
     __syncthreads();
     const int nu = s_nu;
     F32_PROF(1);
+#ifdef DSVT_PROFILE
     if (blockIdx.x == 5 && blockIdx.y == 0 && threadIdx.x == 0) g_fp32_prof[20] = nu;
+#endif
 
     auto load_tile = [&](const float* src_plain, bool add_pos) {
         for (int t = tid; t < nu * (kC / 4); t += kThreadsA) {
@@ -405,6 +411,8 @@ int set_attention_fp32(const dsvt_set_attention_params* p, const AttnWeightsDev&
 
 }  // namespace dsvt
 
+#ifdef DSVT_PROFILE
 extern "C" int dsvt_debug_fp32_profile(long long* out32) {
     return cudaMemcpyFromSymbol(out32, dsvt::g_fp32_prof, sizeof(long long) * 32) == cudaSuccess ? 0 : 1;
 }
+#endif

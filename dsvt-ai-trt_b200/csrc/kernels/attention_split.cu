@@ -1,6 +1,6 @@
 // a3 -- set attention as a three-kernel pipeline (DSVT_ATTN_FP32_TC and DSVT_ATTN_FP16_GEMM):
 //
-//   1. proj_gemm_kernel (roles Q, K, V): per VOXEL (not per set slot) projections on tcgen05,
+//   1. proj_tile_kernel (roles Q, K, V): per VOXEL (not per set slot) projections on tcgen05,
 //        Q = ((x+pos) Wq^T + bq) / sqrt(24),  K = (x+pos) Wk^T + bk,  V = x Wv^T + bv        -> qkv [V, 576] f32
 //      Every voxel belongs to exactly one set per axis (getSet's rank formula never lets two sets share a voxel),
 //      so projecting voxels instead of the 36 slots of every set removes the padding repeats (2/3 of the slots on the
@@ -8,7 +8,7 @@
 //   2. attn_core_kernel: one CTA per set gathers the K/V rows of the set's distinct tokens into shared memory and
 //      evaluates scores + key mask -> softmax -> PV in FP32 on the CUDA cores (8.6 % of the FLOPs, 36x36x24 per head:
 //      too small for a 128-row UMMA tile)                                                            -> o [V, 192] f32
-//   3. proj_gemm_kernel (role O): out = o Wout^T + bout, tail rows zero-filled                   -> out [V, 192] f32
+//   3. proj_tile_kernel (role O): out = o Wout^T + bout, tail rows zero-filled                   -> out [V, 192] f32
 //
 // Restates multHeadAttention() (reference src/dsvt-ai-trt.cpp:288-458) with GetValueByIndex
 // (getValueByIndex.cu:282-303) and MapSetFeature2Voxel (mapSetFeature2voxel.cu:258-275) folded in.
@@ -19,11 +19,11 @@
 // are pre-scaled by a power of two per role so hi/lo stay in FP16's normal range (undone exactly in the epilogue);
 // activations must satisfy |x + pos| < 65504 (they are LayerNorm outputs).  DSVT_ATTN_FP16_GEMM uses the hi terms only.
 //
-// GEMM kernel: CTA tile 128 rows x 192 columns, K = 192 streamed in 6 chunks of 32 through a 2-stage ring
-// (A: 8 producer warps read FP32 rows with coalesced 128-bit loads, add pos, split, and write the UMMA K-major
-// interleaved layout of tc_common.cuh conflict-free; B: one cp.async.bulk per chunk of the pre-arranged weight
-// image); one thread issues the MMAs; the 8 producer warps then drain the 192 accumulator columns from TMEM.
-// 100 KB shared memory and 256 TMEM columns per CTA -> two CTAs per SM overlap each other's phases.
+// GEMM kernel (proj_tile_kernel): one CTA = one 128-row x 192-column tile of one role, K streamed in chunks of 32 through a
+// 2-stage ring (A: 8 producer warps read FP32 rows with 256-bit loads, add pos, split, and write the UMMA K-major
+// interleaved layout of tc_common.cuh conflict-free; B: one cp.async.bulk per chunk of the pre-arranged weight image); one
+// thread issues the MMAs; the producer warps then drain the 192 accumulator columns from TMEM (optionally through a chain
+// of LayerNorms).  80 KB shared memory and 256 TMEM columns per CTA -> two CTAs per SM overlap each other's phases.
 #include "attention_common.cuh"
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
@@ -40,28 +40,13 @@ using namespace tc;
 constexpr int kC = 192, kH = 8, kD = 24;
 constexpr int kBM = 128, kBN = 192, kBK = 32;
 constexpr int kNumK = kC / kBK;                      // 6 K chunks
-constexpr int kAStages = 3;                          // ring of A chunks
-constexpr int kProducers = 256;                      // warps 0-7 : A producers
-constexpr int kEpiWarps = 8;                         // warps 8-15: epilogue (TMEM lane quarter = warp % 4, column half = (warp-8)/4)
-constexpr int kIssuerWarp = 8 + kEpiWarps;           // warp 16  : weight copies + MMA issue
-constexpr int kThreadsG = (8 + kEpiWarps + 1) * 32;  // 544
+constexpr int kEpiWarps = 8;                         // epilogue warps (TMEM lane quarter = warp % 4, column half = warp / 4)
 constexpr int kATerm = kBM * kBK * 2;                // 8192 B: one precision term of an A chunk
 constexpr int kBTerm = kBN * kBK * 2;                // 12288 B
 constexpr int kWChunkBytes = 2 * kBTerm;             // weight image per (role, K chunk): hi | lo
 constexpr int kWRoleBytes = kNumK * kWChunkBytes;    // 147456
 constexpr int kRoles = 4;                            // Q, K, V, O
 constexpr int kEpiScratch = 32 * 32 * 4;             // 4096 B per epilogue warp: 32 rows x 32 columns, XOR-swizzled float4s
-constexpr int kAccCols = 256;                        // TMEM column stride between the two accumulators
-
-template <bool SPLIT> struct Lay {
-    static constexpr int terms = SPLIT ? 2 : 1;
-    static constexpr int w_chunk = terms * kBTerm;                 // resident weight bytes per K chunk
-    static constexpr int w = 0;                                    // [6][hi | lo]
-    static constexpr int a = w + kNumK * w_chunk;                  // [kAStages][hi | lo]
-    static constexpr int a_stage = terms * kATerm;
-    static constexpr int epi = a + kAStages * a_stage;             // [4 warps][32][36] f32
-    static constexpr int total = epi + kEpiWarps * kEpiScratch;    // 229376 / 131072
-};
 
 // ---- attention plan: the set partition of one (frame, window partition, axis) in token order ----------------------
 // Built once by dsvt_set_attention_plan_launch and shared by every attention layer that uses the partition.
@@ -157,318 +142,25 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // phase stamps of one CTA (tools/split_profile.py): compiled in with -DDSVT_PROFILE only, never in the product build
 #ifdef DSVT_PROFILE
 __device__ long long g_split_prof[64];
-#define SP(i) do { if (blockIdx.x == 3 && blockIdx.y == 0) g_split_prof[(n_roles == 1 ? 40 : 0) + (i)] = clock64(); } while (0)
 #define CP(i) do { if (blockIdx.x == 5 && blockIdx.y == 0 && threadIdx.x == 0) g_split_prof[32 + i] = clock64(); } while (0)
 #define TP(i) do { if (blockIdx.x == 20 && blockIdx.y == 0) g_split_prof[(i)] = clock64(); } while (0)
 #else
-#define SP(i) do { } while (0)
 #define CP(i) do { } while (0)
 #define TP(i) do { } while (0)
 #endif
 
-// Persistent: grid = (n_roles * ctas_per_role, batch).  A CTA owns ONE role: its 147 KB weight image (hi + lo) is copied
-// into shared memory once and stays there while the CTA walks over row tiles t0, t0 + ctas_per_role, ...  Three engines
-// overlap through mbarriers: 8 producer warps fill a 3-stage ring of A chunks (FP32 rows -> (+pos) -> FP16 hi/lo,
-// loads for step g+2 in flight while step g is converted, across tile boundaries), one thread issues the MMAs into one
-// of two TMEM accumulators, 4 epilogue warps drain the other one (TMEM -> registers -> per-warp transposition scratch
-// -> full 128-byte row segments to global memory).
-template <bool SPLIT>
-__global__ void __launch_bounds__(kThreadsG, 1)
-proj_gemm_kernel(GemmRoles roles, int n_roles, const int* __restrict__ voxel_num, int rows_host, int max_pillars,
-                 int max_sets, int zero_tails)
-{
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t w_full[kNumK], a_full[kAStages], a_empty[kAStages], acc_full[2], acc_empty[2];
-    __shared__ uint32_t tmem_slot;
-    using L = Lay<SPLIT>;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.y;
-    const int role_id = blockIdx.x % n_roles, t0 = blockIdx.x / n_roles, stride = gridDim.x / n_roles;
-    const GemmRole g = roles.r[role_id];
-    int V = voxel_num ? voxel_num[b] : rows_host;       // valid rows: device-side count, or the host's (plain linear layer)
-    V = V < max_pillars ? V : max_pillars;
-    const int n_tiles = (max_pillars + kBM - 1) / kBM, valid_tiles = (V + kBM - 1) / kBM;
-    const int cnt = valid_tiles > t0 ? (valid_tiles - t0 + stride - 1) / stride : 0;    // row tiles this CTA computes
-    // (walking the K chunks from a per-CTA starting chunk, so that the CTAs of a role do not all want the same weight
-    //  lines at kernel start, was measured: no change -- the weight copies are bandwidth-, not hot-line-bound)
-    constexpr int rot = 0;
-    if (cnt == 0 && !zero_tails) return;
-    float* out = g.out + (size_t) b * max_pillars * g.ld_out + g.col0;
-    const float* a0 = g.a0 + (size_t) b * max_pillars * g.lda;
-    const float* a1 = g.a1 ? g.a1 + (size_t) b * max_pillars * g.lda : nullptr;
-    const float* a0b = g.a0b ? g.a0b + (size_t) b * max_pillars * g.ldb : nullptr;
-    if (tid == 0) SP(0);
-
-    if (tid == 0) {
-        for (int s = 0; s < kNumK; ++s) mbar_init(&w_full[s], 1);
-        for (int s = 0; s < kAStages; ++s) { mbar_init(&a_full[s], kProducers); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
-        fence_barrier_init();
-    }
-    if (warp == kIssuerWarp) tmem_alloc<512>(&tmem_slot);
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem = tmem_slot;
-    if (tid == 0) SP(1);
-
-    if (warp < 8) {
-        // =========================== A PRODUCERS =========================================================
-        // step g = (tile n, K chunk kc, half): rows half*64 + warp*8 + (lane & 7), 16-byte K piece c16 = lane >> 3.
-        // A quarter-warp (8 lanes) writes 8 consecutive rows of one piece (128 contiguous bytes: conflict-free);
-        // the four lanes that share a row read one full 128-byte line of it.
-#ifndef DSVT_GEMM_DEPTH
-#define DSVT_GEMM_DEPTH 3          // row-piece loads in flight per producer thread (3, 4 or 6: the unroll must divide 12)
-#endif
-        constexpr int kStepsPerTile = kNumK * 2, kDepth = DSVT_GEMM_DEPTH;
-        constexpr int kUnroll = kDepth % 2 == 0 ? kDepth : 2 * kDepth;      // lcm(2 halves, kDepth): static buffer / half indices
-        static_assert(kStepsPerTile % kUnroll == 0, "producer unroll must divide the steps of a tile");
-        const int total = cnt * kStepsPerTile;
-        const int rl = warp * 8 + (lane & 7), c16 = lane >> 3;
-        float buf[kDepth][16];                                  // [0..7] = a0 row piece, [8..15] = a1 (pos) row piece
-        auto issue = [&](int gs, float (&d)[16]) {
-            const int n = gs / kStepsPerTile, s = gs - n * kStepsPerTile;
-            const int kc = ((s >> 1) + rot) % kNumK, row = (t0 + n * stride) * kBM + (s & 1) * 64 + rl;
-#ifdef DSVT_DBG_NO_LOAD      // bottleneck probe (never in the product build): the producers convert zeros
-            if (false) {
-#else
-            if (row < V) {
-#endif
-                const int col = kc * kBK + c16 * 8;
-                if (a0b && col >= g.ksplit) ldg256(a0b + (size_t) row * g.ldb + (col - g.ksplit), &d[0]);
-                else ldg256(a0 + (size_t) row * g.lda + col, &d[0]);              // one 256-bit load: full 32-byte sectors
-                if (a1) ldg256(a1 + (size_t) row * g.lda + kc * kBK + c16 * 8, &d[8]);
-                else {
-#pragma unroll
-                    for (int e = 8; e < 16; ++e) d[e] = 0.f;
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 16; ++e) d[e] = 0.f;
-            }
-        };
-#pragma unroll
-        for (int s = 0; s < kDepth - 1; ++s)
-            if (s < total) issue(s, buf[s]);
-#pragma unroll 1
-        for (int g0 = 0; g0 < total; g0 += kUnroll) {
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const int gs = g0 + u;
-                if (gs + kDepth - 1 < total) issue(gs + kDepth - 1, buf[(u + kDepth - 1) % kDepth]);
-                const int cc = gs >> 1, st = cc % kAStages, r = (u & 1) * 64 + rl;
-                if ((u & 1) == 0 && cc >= kAStages) mbar_wait(&a_empty[st], ((cc / kAStages) - 1) & 1);
-                float (&d)[16] = buf[u % kDepth];
-                const float v[8] = {d[0] + d[8], d[1] + d[9], d[2] + d[10], d[3] + d[11],
-                                    d[4] + d[12], d[5] + d[13], d[6] + d[14], d[7] + d[15]};
-                const uint4 hi = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-                uint8_t* stage = smem + L::a + st * L::a_stage;
-                *reinterpret_cast<uint4*>(stage + c16 * (kBM * 16) + r * 16) = hi;
-                if (SPLIT) {
-                    const float2 h0 = unpack_h2(hi.x), h1 = unpack_h2(hi.y), h2 = unpack_h2(hi.z), h3 = unpack_h2(hi.w);
-                    const uint4 lo = make_uint4(pack_h2(v[0] - h0.x, v[1] - h0.y), pack_h2(v[2] - h1.x, v[3] - h1.y),
-                                                pack_h2(v[4] - h2.x, v[5] - h2.y), pack_h2(v[6] - h3.x, v[7] - h3.y));
-                    *reinterpret_cast<uint4*>(stage + kATerm + c16 * (kBM * 16) + r * 16) = lo;
-                }
-                if (u & 1) {
-                    fence_proxy_async_smem();
-                    mbar_arrive(&a_full[st]);
-                    if (tid == 0 && cc < 6) SP(2 + cc);
-                }
-            }
-        }
-        if (tid == 0) SP(14);
-        // tiles of tail rows (>= voxel_num) assigned to this CTA are zero-filled by the producers, which are idle from
-        // here on -- the epilogue warps only zero the invalid rows of the last partial tile
-        if (zero_tails) {
-            for (int n = cnt;; ++n) {
-                const int t = t0 + n * stride;
-                if (t >= n_tiles) break;
-                const int row0 = t * kBM;
-                for (int i = tid; i < kBM * (kBN / 4); i += kProducers) {
-                    const int rloc = i / (kBN / 4), cc4 = i - rloc * (kBN / 4);
-                    if (row0 + rloc < max_pillars)
-                        stg_zero4(reinterpret_cast<float4*>(out + (size_t) (row0 + rloc) * g.ld_out + cc4 * 4));
-                }
-            }
-        }
-    } else if (warp < 8 + kEpiWarps) {
-        // =========================== EPILOGUE ============================================================
-        // warp = (TMEM lane quarter q4, column half hf): 3 slabs of 32 columns.  Slab: TMEM -> registers (lane = row)
-        // -> swizzled scratch -> (lane = 4 columns of 8 rows) scale + bias -> full 128-byte row segments to global.
-        const int q4 = warp & 3, hf = (warp - 8) >> 2;
-        float4* scr = reinterpret_cast<float4*>(smem + L::epi + (warp - 8) * kEpiScratch);
-        const uint32_t tlane = tmem + ((uint32_t) (q4 * 32) << 16) + hf * 96;
-        const int rg = lane >> 3, c4 = lane & 7;
-        const float* bias = g.bias + hf * 96 + c4 * 4;
-        float* outc = out + hf * (96 + g.pad_hi) + c4 * 4;
-        const PlanView pv = plan_view(const_cast<int*>(g.plan) + (size_t) b * g.plan_stride, max_sets, max_pillars);
-        for (int n = 0;; ++n) {
-            const int t = t0 + n * stride;
-            if (t >= n_tiles) break;
-            const int row0 = t * kBM + q4 * 32;                    // first row of this warp's lane quarter
-            if (n < cnt) {
-                const int acc = n & 1;
-                // (the row map does not depend on the accumulators: its two dependent loads overlap the MMA wait)
-                int orow[8];                                       // output row of this lane's 8 rows, -1: not written
-                unsigned dead = 0;                                 // bit rr: a valid row that belongs to no set -> zeros
-#pragma unroll
-                for (int rr = 0; rr < 8; ++rr) {
-                    const int grow = row0 + rr * 4 + rg;
-                    if (g.cover && grow < V && __ldg(g.cover + (size_t) b * g.cover_stride + grow) < 0) dead |= 1u << rr;
-                    if (g.plan) {                                  // voxel row -> token position (set-major order)
-                        orow[rr] = -1;
-                        if (grow < V) {
-                            const int su = __ldg(pv.vox_su + grow);
-                            if (su >= 0) {
-                                const int t = __ldg(pv.set_off + (su >> 6)) + (su & 63);
-                                if (t < max_pillars) orow[rr] = t;
-                            }
-                        }
-                    } else {
-                        orow[rr] = (grow < V || (zero_tails && grow < max_pillars)) ? grow : -1;
-                    }
-                }
-                mbar_wait(&acc_full[acc], (n >> 1) & 1);
-                tc_fence_after_sync();
-                if (lane == 0 && warp == 8 && n == 0) SP(20);
-#pragma unroll 1
-                for (int j0 = 0; j0 < 96; j0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(tlane + acc * kAccCols + j0, r);
-                    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + j0));
-                    tmem_ld_wait();
-#ifdef DSVT_EPI_PROBE        // phase stamps of the first tile's three slabs (tools/split_profile.py)
-                    if (lane == 0 && warp == 8 && n == 0 && n_roles != 1) SP(22 + (j0 >> 5) * 3);
-#endif
-                    if (j0 == 64) {                                // accumulator drained: hand it back to the issuer
-                        tc_fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&acc_empty[acc]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)                    // float4 j of row `lane` lands in slot j ^ (lane & 7)
-                        scr[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                                                       __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-                    __syncwarp();
-                    float4 v[8];
-#pragma unroll
-                    for (int rr = 0; rr < 8; ++rr) {
-                        const int rloc = rr * 4 + rg;
-                        v[rr] = scr[rloc * 8 + (c4 ^ (rloc & 7))];
-                    }
-#ifdef DSVT_EPI_PROBE
-                    if (lane == 0 && warp == 8 && n == 0 && n_roles != 1) SP(23 + (j0 >> 5) * 3);
-#endif
-#pragma unroll
-                    for (int rr = 0; rr < 8; ++rr) {               // 4 rows x 128 contiguous bytes per store instruction
-                        const int grow = row0 + rr * 4 + rg;
-                        // out_mul is a power of two: the product is exact, so this is one rounding of (acc + bias)
-                        float4 ov = make_float4((v[rr].x * g.out_mul + bb.x) * g.post_mul, (v[rr].y * g.out_mul + bb.y) * g.post_mul,
-                                                (v[rr].z * g.out_mul + bb.z) * g.post_mul, (v[rr].w * g.out_mul + bb.w) * g.post_mul);
-                        if (g.accumulate && orow[rr] >= 0 && grow < V) {   // second K block: add to the first block's rows
-                            const float4 pv4 = *reinterpret_cast<const float4*>(outc + (size_t) orow[rr] * g.ld_out + j0);
-                            ov.x += pv4.x; ov.y += pv4.y; ov.z += pv4.z; ov.w += pv4.w;
-                        }
-                        if (g.add_src && orow[rr] >= 0 && grow < V) {      // residual rows, same coalesced 128-byte segments
-                            const float4 ad = __ldg(reinterpret_cast<const float4*>(
-                                g.add_src + ((size_t) b * max_pillars + grow) * g.ld_add + g.col0 + hf * 96 + c4 * 4 + j0));
-                            ov.x += ad.x; ov.y += ad.y; ov.z += ad.z; ov.w += ad.w;
-                        }
-                        if (g.act == 1) { ov.x = gelu_tanh(ov.x); ov.y = gelu_tanh(ov.y); ov.z = gelu_tanh(ov.z); ov.w = gelu_tanh(ov.w); }
-                        else if (g.act == 2) { ov.x = fmaxf(ov.x, 0.f); ov.y = fmaxf(ov.y, 0.f); ov.z = fmaxf(ov.z, 0.f); ov.w = fmaxf(ov.w, 0.f); }
-                        if (grow >= V || (dead >> rr & 1u)) ov = make_float4(0.f, 0.f, 0.f, 0.f);
-#ifdef DSVT_DBG_NO_STORE     // bottleneck probe (never in the product build): results are dropped (kept live by an impossible test)
-                        if (orow[rr] >= 0 && ov.x == 1.2345e-30f) *reinterpret_cast<float4*>(outc + (size_t) orow[rr] * g.ld_out + j0) = ov;
-#else
-                        if (orow[rr] >= 0) *reinterpret_cast<float4*>(outc + (size_t) orow[rr] * g.ld_out + j0) = ov;
-#endif
-                    }
-                    __syncwarp();
-#ifdef DSVT_EPI_PROBE
-                    if (lane == 0 && warp == 8 && n == 0 && n_roles != 1) SP(24 + (j0 >> 5) * 3);
-#endif
-                }
-                if (lane == 0 && warp == 8 && n == 0) SP(16);
-                if (lane == 0 && warp == 8 && n == cnt - 1) SP(17);
-            } else {
-                break;                                             // tail tiles: zero-filled by the producer warps
-            }
-        }
-    } else {
-        // =========================== WEIGHT COPIES + MMA ISSUE ===========================================
-        if (lane == 0 && cnt > 0) {
-            // pull this CTA's row tiles into L2 as large sequential requests (a tile is 96 KB contiguous per source); the
-            // producers then read them in 128-byte-per-row K chunks, a pattern that wastes DRAM pages when it misses L2
-            for (int n = 0; n < cnt && g.lda == kC; ++n) {           // (a tile is contiguous only when rows are 192 wide)
-                const int row0 = (t0 + n * stride) * kBM;
-                const uint32_t bytes = (uint32_t) ((V - row0 < kBM ? V - row0 : kBM) * kC * sizeof(float));
-                l2_prefetch(a0 + (size_t) row0 * kC, bytes);
-                if (a1) l2_prefetch(a1 + (size_t) row0 * kC, bytes);
-            }
-            for (int i = 0; i < kNumK; ++i) {
-                const int kc = (i + rot) % kNumK;
-                mbar_arrive_expect_tx(&w_full[kc], L::w_chunk);
-                bulk_g2s(smem + L::w + kc * L::w_chunk, g.wimg + (size_t) kc * kWChunkBytes, L::w_chunk, &w_full[kc]);
-            }
-            const uint32_t idesc = make_idesc(kFmtF16, kBM, kBN);
-            const uint32_t sbase = smem_u32(smem);
-            int cc = 0;
-#pragma unroll 1
-            for (int n = 0; n < cnt; ++n) {
-                const int acc = n & 1;
-                if (n >= 2) { mbar_wait(&acc_empty[acc], ((n >> 1) - 1) & 1); tc_fence_after_sync(); }
-                const uint32_t d_tmem = tmem + acc * kAccCols;
-#pragma unroll 1
-                for (int kc = 0; kc < kNumK; ++kc, ++cc) {
-                    const int kcw = (kc + rot) % kNumK;            // the chunk the producers staged at ring position cc
-                    if (n == 0) mbar_wait(&w_full[kcw], 0);
-                    const int st = cc % kAStages;
-                    mbar_wait(&a_full[st], (cc / kAStages) & 1);
-                    tc_fence_after_sync();
-                    if (n == 0) SP(8 + kc);
-                    const uint32_t sa = sbase + L::a + st * L::a_stage, sw = sbase + L::w + kcw * L::w_chunk;
-#pragma unroll
-                    for (int ks = 0; ks < kBK / 16; ++ks) {
-                        const uint64_t a_hi = make_smem_desc(sa + ks * 2 * (kBM * 16), kBM * 16, 128);
-                        const uint64_t b_hi = make_smem_desc(sw + ks * 2 * (kBN * 16), kBN * 16, 128);
-                        if (SPLIT) {
-                            const uint64_t a_lo = make_smem_desc(sa + kATerm + ks * 2 * (kBM * 16), kBM * 16, 128);
-                            const uint64_t b_lo = make_smem_desc(sw + kBTerm + ks * 2 * (kBN * 16), kBN * 16, 128);
-                            umma_f16(d_tmem, a_lo, b_hi, idesc, (kc | ks) != 0);
-                            umma_f16(d_tmem, a_hi, b_lo, idesc, 1);
-                            umma_f16(d_tmem, a_hi, b_hi, idesc, 1);
-                        } else {
-                            umma_f16(d_tmem, a_hi, b_hi, idesc, (kc | ks) != 0);
-                        }
-                    }
-                    umma_commit(&a_empty[st]);
-                }
-                umma_commit(&acc_full[acc]);
-            }
-            SP(15);
-        }
-        __syncwarp();
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    if (tid == 0) SP(21);
-    if (warp == kIssuerWarp) tmem_dealloc<512>(tmem);
-}
-
 // ---------------------------------------------------------------------------------------------------------------
-// Single-pass form of the same GEMM: one CTA = one 128-row tile of one role, NOT persistent, two CTAs per SM.
+// The projection / linear-layer GEMM: one CTA = one 128-row tile of one role, NOT persistent, two CTAs per SM.
 //
-// Why: at these sizes (30 k rows = 241 tiles, 148 SMs) the persistent kernel above never reaches a steady state -- a CTA
-// computes 1-5 tiles, so its 147 KB resident weight image (4-5 us to arrive when every SM pulls the same lines), the first
-// row loads and the final drain are most of its life, and with one 229 KB CTA per SM nothing overlaps them: the ncu source
-// view shows 46 % of the warp samples waiting on global loads and 23 % parked at the final barrier
-// (profiles/r2_gemm_persistent_stalls.txt).  Here the weights are NOT resident: each K chunk's [hi | lo] image (24 KB, an
-// L2 hit for every CTA but the first) streams through the same 2-stage ring as the converted A chunk, the CTA needs 80 KB
-// of shared memory and 192 TMEM columns, and TWO CTAs share an SM so that one's loads overlap the other's epilogue.  L2->SM
-// traffic per tile rises from 96-192 KB (rows) to 243-339 KB (rows + weights), still under the L2 fabric's ~42 B/clk/SM.
-// Roles, operand images, the MMA sequence and the epilogue arithmetic are those of proj_gemm_kernel: results are bit-identical.
+// Round 1 ran this GEMM as a persistent kernel with a 147 KB resident weight image per CTA (one 229 KB CTA per SM).  At
+// these sizes (30 k rows = 241 tiles, 148 SMs) that kernel never reached a steady state -- a CTA computed 1-5 tiles, so the
+// arrival of its weight image (4-5 us when every SM pulls the same lines), the first row loads and the final drain were most
+// of its life and nothing overlapped them: its ncu source view showed 46 % of the warp samples waiting on global loads and
+// 23 % parked at the final barrier (profiles/r2_gemm_persistent_stalls.txt).  Here the weights are NOT resident: each K
+// chunk's [hi | lo] image (24 KB, an L2 hit for every CTA but the first) streams through a 2-stage ring next to the
+// converted A chunk, the CTA needs 80 KB of shared memory and 192 TMEM columns, and TWO CTAs share an SM so that one's loads
+// overlap the other's epilogue.  L2->SM traffic per tile rises from 96-192 KB (rows) to 243-339 KB (rows + weights).
+// Operand images, MMA sequence and epilogue arithmetic are unchanged from round 1: results are bit-identical.
 constexpr int kLnStride = 196;                        // floats per row of the LayerNorm tile: 49 x 16 B, conflict-free row writes
 constexpr int kTStages = 2;                           // converted A chunks
 constexpr int kTWStages = 2;                          // weight chunks (a third stage and per-row L2 prefetches of every operand
@@ -1139,38 +831,16 @@ struct SplitBlobHeader {
 
 }  // namespace
 
-static int gemm_sm_fraction();
-static int gemm_raise_smem() {
-    DSVT_RAISE_SMEM(proj_gemm_kernel<true>, Lay<true>::total);
-    DSVT_RAISE_SMEM(proj_gemm_kernel<false>, Lay<false>::total);
-    DSVT_RAISE_SMEM(proj_tile_kernel<true>, TLay<true>::total);
-    DSVT_RAISE_SMEM(proj_tile_kernel<false>, TLay<false>::total);
-    return DSVT_OK;
-}
-// DSVT_GEMM_IMPL=persistent selects the resident-weight persistent kernel (A/B runs); default: the single-pass tile kernel
-static bool gemm_persistent() {
-    static const bool v = [] { const char* e = getenv("DSVT_GEMM_IMPL"); return e && e[0] == 'p'; }();
-    return v;
-}
-// One GEMM launch over `n_roles` roles (<= 3): every role is [rows, 192] x [192, 192]^T with its own operands / epilogue.
+// One GEMM launch over `n_roles` roles (<= 3): every role is [rows, 192 k] x [192 k, 192]^T with its own operands / epilogue.
 static int launch_gemm(const GemmRoles& roles, int n_roles, const int* rows_dev, int rows_host, int max_rows, int max_sets,
                        int zero_tails, int batch, bool split, cudaStream_t st)
 {
-    { const int rc_attr = gemm_raise_smem(); if (rc_attr != DSVT_OK) return rc_attr; }
-    if (!gemm_persistent()) {
-        const dim3 grid((max_rows + kBM - 1) / kBM, n_roles, batch);
-        const bool ln = roles.r[0].n_ln > 0;       // the LayerNorm epilogue stages the finished tile: 98 KB instead of 80 KB
-        if (split) proj_tile_kernel<true><<<grid, kTThreads, ln ? TLay<true>::total : TLay<true>::plain, st>>>(roles, rows_dev, rows_host, max_rows, max_sets, zero_tails);
-        else proj_tile_kernel<false><<<grid, kTThreads, ln ? TLay<false>::total : TLay<false>::plain, st>>>(roles, rows_dev, rows_host, max_rows, max_sets, zero_tails);
-        DSVT_LAUNCH_CHECK();
-        return DSVT_OK;
-    }
-    // persistent grid: one CTA per SM (divided among the batch), a multiple of the number of roles.
-    // DSVT_GEMM_SM_FRACTION=<percent>: CTAs per launch as a share of the SMs
-    const int per = sm_count() * gemm_sm_fraction() / 100 / batch;
-    const int grid = per >= n_roles ? per / n_roles * n_roles : n_roles;
-    if (split) proj_gemm_kernel<true><<<dim3(grid, batch), kThreadsG, Lay<true>::total, st>>>(roles, n_roles, rows_dev, rows_host, max_rows, max_sets, zero_tails);
-    else proj_gemm_kernel<false><<<dim3(grid, batch), kThreadsG, Lay<false>::total, st>>>(roles, n_roles, rows_dev, rows_host, max_rows, max_sets, zero_tails);
+    DSVT_RAISE_SMEM(proj_tile_kernel<true>, TLay<true>::total);
+    DSVT_RAISE_SMEM(proj_tile_kernel<false>, TLay<false>::total);
+    const dim3 grid((max_rows + kBM - 1) / kBM, n_roles, batch);
+    const bool ln = roles.r[0].n_ln > 0;       // the LayerNorm epilogue stages the finished tile: 98 KB instead of 80 KB
+    if (split) proj_tile_kernel<true><<<grid, kTThreads, ln ? TLay<true>::total : TLay<true>::plain, st>>>(roles, rows_dev, rows_host, max_rows, max_sets, zero_tails);
+    else proj_tile_kernel<false><<<grid, kTThreads, ln ? TLay<false>::total : TLay<false>::plain, st>>>(roles, rows_dev, rows_host, max_rows, max_sets, zero_tails);
     DSVT_LAUNCH_CHECK();
     return DSVT_OK;
 }
@@ -1235,7 +905,6 @@ int linear_split_launch(const void* blob, int N, int K, float out_mul, bool spli
     const uint8_t* img = static_cast<const uint8_t*>(blob);
     const float* bias = reinterpret_cast<const float*>(img + (size_t) nb * kb * kWRoleBytes);
     const float* zero_bias = bias + N;           // K blocks after the first add no bias: 192 zeros kept behind the bias
-    { const int rc_attr = gemm_raise_smem(); if (rc_attr != DSVT_OK) return rc_attr; }
     for (int j = 0; j < kb; ++j)
         for (int i0 = 0; i0 < nb; i0 += 3) {            // up to three 192-column output blocks (roles) per launch
             const int n_roles = nb - i0 < 3 ? nb - i0 : 3;
@@ -1274,7 +943,6 @@ int linear_split_k_launch(const void* blob, int N, int K, float out_mul, bool sp
     const uint8_t* img = static_cast<const uint8_t*>(blob);
     const float* bias = reinterpret_cast<const float*>(img + (size_t) kb * kWRoleBytes);
     const float* zero_bias = bias + N;           // 192 zeros kept behind the bias in the weight blob
-    { const int rc_attr = gemm_raise_smem(); if (rc_attr != DSVT_OK) return rc_attr; }
     GemmRoles roles;
     for (int r = 0; r < 3; ++r) {
         const int j = r < kb ? r : 0;
@@ -1298,10 +966,6 @@ int linear_split_k_launch(const void* blob, int N, int K, float out_mul, bool sp
 int linear_gen_launch(const void* blob, float out_mul, bool split, const float* x2, const float* small_blob, const int* rows_dev,
                       int max_rows, float* y, int zero_tails, cudaStream_t st)
 {
-    if (gemm_persistent()) {
-        set_last_error("position-embedding MLP: not available with DSVT_GEMM_IMPL=persistent");
-        return DSVT_ERR_UNSUPPORTED;
-    }
     const uint8_t* img = static_cast<const uint8_t*>(blob);
     GemmRoles roles;
     GemmRole& g = roles.r[0];
@@ -1326,10 +990,6 @@ int linear_ln_launch(const void* blob, int K, float out_mul, bool split, const f
                      int n_ln, const float* const* res, const float* const* gamma, const float* const* beta, float eps,
                      float* y, int zero_tails, cudaStream_t st)
 {
-    if (gemm_persistent()) {
-        set_last_error("linear + LayerNorm epilogue: not available with DSVT_GEMM_IMPL=persistent");
-        return DSVT_ERR_UNSUPPORTED;
-    }
     const int kb = K / kC;
     const uint8_t* img = static_cast<const uint8_t*>(blob);
     GemmRoles roles;
@@ -1401,28 +1061,6 @@ void* attention_split_prepare(const float* w_in, const float* b_in, const float*
     return dev;
 }
 
-// Optional per-kernel timing of the pipeline (bench.py's roofline block): when enabled, CUDA events are recorded on the
-// launch stream between the three kernels.  Not for use under stream capture.
-static bool g_stage_timing = false;
-static cudaEvent_t g_stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};
-static int stage_mark(int i, cudaStream_t st) {
-    if (!g_stage_timing) return DSVT_OK;
-    if (!g_stage_ev[i]) DSVT_CUDA(cudaEventCreate(&g_stage_ev[i]));
-    DSVT_CUDA(cudaEventRecord(g_stage_ev[i], st));
-    return DSVT_OK;
-}
-
-static int g_skip_mask = 0;   // diagnostic (tools/ablate.py): bit 0 / 1 / 2 = do not launch the QKV GEMM / core / out-projection
-static int g_gemm_sm_fraction = -1;
-static int gemm_sm_fraction() {
-    if (g_gemm_sm_fraction < 0) {
-        const char* e = getenv("DSVT_GEMM_SM_FRACTION");
-        const int v = e ? atoi(e) : 100;
-        g_gemm_sm_fraction = v < 5 ? 5 : (v > 100 ? 100 : v);
-    }
-    return g_gemm_sm_fraction;
-}
-
 static size_t plan_bytes_of(const dsvt_set_attention_params* p) {
     return align_up((size_t) p->batch * plan_words(p->max_set_num, p->voxel_num_set, p->max_pillars_num) * sizeof(int), kWsAlign);
 }
@@ -1465,7 +1103,7 @@ int attention_split_plan(const dsvt_set_attention_params* p, const int* idx, con
 int set_attention_split_fused(const dsvt_set_attention_params* p, const void* split_blob, const float* out_mul,
                               bool split, const float* x, const float* pos, const int* idx, const float* mask,
                               const int* set_num, const int* voxel_num, float* out, const void* plan_in,
-                              void* workspace, size_t workspace_bytes, cudaStream_t st, const AttnNorm* norm)
+                              void* workspace, size_t workspace_bytes, cudaStream_t st, const AttnNorm* norm, int stages)
 {
     int rc = split_check(p);
     if (rc != DSVT_OK) return rc;
@@ -1491,8 +1129,6 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
     const uint8_t* img = static_cast<const uint8_t*>(split_blob);
     const float* bias = reinterpret_cast<const float*>(img + (size_t) kRoles * kWRoleBytes);
 
-    { const int rc_attr = gemm_raise_smem(); if (rc_attr != DSVT_OK) return rc_attr; }
-    if ((rc = stage_mark(0, st)) != DSVT_OK) return rc;
     const int* plan = static_cast<const int*>(plan_in);
     if (!plan) {                                   // stateless call: build the partition's plan first
         if ((rc = attention_split_plan(p, idx, mask, set_num, own_plan, plan_bytes_of(p), st)) != DSVT_OK) return rc;
@@ -1533,31 +1169,27 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
         g.cover = plan_view(const_cast<int*>(plan), p->max_set_num, p->max_pillars_num).vox_su;   // voxels in no set -> 0
         g.cover_stride = plan_stride;
         if (norm) {                                // out = LayerNorm(attention + residual): norm1(y + x), src/dsvt-ai-trt.cpp:669-676
-            if (gemm_persistent()) {
-                set_last_error("set attention + norm epilogue: not available with DSVT_GEMM_IMPL=persistent");
-                return DSVT_ERR_UNSUPPORTED;
-            }
             g.n_ln = 1; g.ln_eps = norm->eps;
             g.ln_res[0] = norm->residual; g.ln_gamma[0] = norm->gamma; g.ln_beta[0] = norm->beta;
             g.ln_res[1] = g.ln_res[2] = nullptr; g.ln_gamma[1] = g.ln_gamma[2] = nullptr; g.ln_beta[1] = g.ln_beta[2] = nullptr;
         }
         out_roles.r[1] = out_roles.r[2] = g;
     }
-    if (!(g_skip_mask & 1) &&
+    // `stages`: bit 0 QKV projection GEMM, bit 1 per-set core, bit 2 out-projection GEMM (all three in normal operation; the
+    // instrumented entry point launches them one at a time so that each can be bracketed by CUDA events)
+    if ((stages & 1) &&
         (rc = launch_gemm(in_roles, 3, voxel_num, 0, p->max_pillars_num, p->max_set_num, 0, p->batch, split, st)) != DSVT_OK)
         return rc;
-    if ((rc = stage_mark(1, st)) != DSVT_OK) return rc;
-    if (!(g_skip_mask & 2)) switch (p->voxel_num_set) {
+    if (stages & 2) switch (p->voxel_num_set) {
         case 24: rc = launch_core<24>(p, qbuf, kvbuf, plan, mask, set_num, o, st); break;
         case 36: rc = launch_core<36>(p, qbuf, kvbuf, plan, mask, set_num, o, st); break;
         default: rc = launch_core<48>(p, qbuf, kvbuf, plan, mask, set_num, o, st); break;
     }
     if (rc != DSVT_OK) return rc;
-    if ((rc = stage_mark(2, st)) != DSVT_OK) return rc;
-    if (!(g_skip_mask & 4) &&
+    if ((stages & 4) &&
         (rc = launch_gemm(out_roles, 1, voxel_num, 0, p->max_pillars_num, p->max_set_num, p->zero_tails, p->batch, split, st)) != DSVT_OK)
         return rc;
-    return stage_mark(3, st);
+    return DSVT_OK;
 }
 
 
@@ -1673,27 +1305,6 @@ int set_attention_split_plugin(const dsvt_set_attention_params* p, const void* s
 
 }  // namespace dsvt
 
-extern "C" void dsvt_debug_attention_stage_timing(int enable) { dsvt::g_stage_timing = enable != 0; }
-// diagnostic: kernels of the GEMM-pipeline attention that are NOT launched (bit 0 QKV GEMM, 1 core, 2 out-projection);
-// used by tools/ablate.py to measure each kernel's marginal cost with several frames in flight.  0 = normal operation.
-extern "C" void dsvt_debug_set_attention_skip_mask(int mask) { dsvt::g_skip_mask = mask & 7; }
-// share of the SMs (percent, 5..100) the attention GEMMs launch CTAs on; initial value: DSVT_GEMM_SM_FRACTION or 100.
-// Returns the previous value.  100 = lowest latency of a single call, ~50 = best throughput with several frames in flight.
-extern "C" int dsvt_debug_set_gemm_sm_fraction(int percent) {
-    const int prev = dsvt::gemm_sm_fraction();
-    dsvt::g_gemm_sm_fraction = percent < 5 ? 5 : (percent > 100 ? 100 : percent);
-    return prev;
-}
-// microseconds of {QKV projection GEMM, per-set core, out-projection GEMM} of the last timed call (after a stream sync)
-extern "C" int dsvt_debug_attention_stage_us(float* out3) {
-    for (int i = 0; i < 3; ++i) {
-        float ms = 0.f;
-        if (!dsvt::g_stage_ev[i] || !dsvt::g_stage_ev[i + 1] ||
-            cudaEventElapsedTime(&ms, dsvt::g_stage_ev[i], dsvt::g_stage_ev[i + 1]) != cudaSuccess) return 1;
-        out3[i] = ms * 1000.f;
-    }
-    return 0;
-}
 #ifdef DSVT_PROFILE
 extern "C" int dsvt_debug_split_profile(long long* out64) {
     return cudaMemcpyFromSymbol(out64, dsvt::g_split_prof, sizeof(long long) * 64) == cudaSuccess ? 0 : 1;

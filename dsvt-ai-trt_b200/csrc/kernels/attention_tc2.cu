@@ -85,8 +85,12 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                  :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 
+#ifdef DSVT_PROFILE      // phase stamps of one CTA (tools/tc_profile.py): never in the product build
 __device__ long long g_tc2_prof[64];
 #define P2(i) do { if (blockIdx.x == 0 && tile == (int) blockIdx.x) g_tc2_prof[i] = clock64(); } while (0)
+#else
+#define P2(i) do { } while (0)
+#endif
 
 struct Barriers {
     uint64_t w_full, wout_full, a_full, so_full, out_full;
@@ -534,6 +538,8 @@ int set_attention_tc2_fused(const dsvt_set_attention_params* p, const void* tc_b
 
 }  // namespace dsvt
 
+#ifdef DSVT_PROFILE
 extern "C" int dsvt_debug_tc2_profile(long long* out64) {
     return cudaMemcpyFromSymbol(out64, dsvt::g_tc2_prof, sizeof(long long) * 64) == cudaSuccess ? 0 : 1;
 }
+#endif

@@ -284,12 +284,14 @@ class HotPathFrame:
             for enc in (0, 1):
                 epi = self.ffn == "epilogue"
                 if "attn" not in skip:
+                    stages = 7 - sum(bit for g_, bit in (("attn_qkv", 1), ("attn_core", 2), ("attn_out", 4)) if g_ in skip)
                     capi.set_attention_fused(w.attn[blk * 2 + enc], x, pos[blk][enc], gs.global_index_in_set[0],
                                              gs.mask_expand_0[0], gs.set_num, V, axis=enc,
                                              out=self.src if epi else self.attn_out,
                                              precision=self.precision, workspace=self.attn_ws,
                                              plan=self.plans.get((blk % 2, enc)), zero_tails=zt,
-                                             norm=(x, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps) if epi else None)
+                                             norm=(x, w.gamma[ln], w.beta[ln], cfg.layer_norm_eps) if epi else None,
+                                             stages=stages)
                 if "ln" in skip:
                     ln += 3 if enc == 0 else 4
                     if "gelu" not in skip:

@@ -309,6 +309,19 @@ int dsvt_set_attention_fused_norm_launch(const dsvt_set_attention_params* p, con
                                          float* out, const void* plan, void* workspace, size_t workspace_bytes,
                                          dsvt_stream_t stream);
 
+/*
+ * Instrumentation form of the two entry points above (GEMM-pipeline precisions, prebuilt plan): launches only the kernels
+ * named in `stages` -- bit 0 the QKV projection GEMM, bit 1 the per-set core, bit 2 the out-projection GEMM (with the norm
+ * epilogue when residual != NULL) -- on the workspace the earlier stages left behind, so that a caller can bracket each
+ * kernel with its own CUDA events (bench.py's per-kernel roofline).  stages = 7 is the normal call.  No global state.
+ */
+int dsvt_set_attention_fused_stages_launch(const dsvt_set_attention_params* p, const dsvt_attention_weights* w,
+                                           const float* x, const float* pos, const int32_t* global_index_in_set,
+                                           const float* mask, const int32_t* set_num, const int32_t* voxel_num,
+                                           const float* residual, const float* gamma, const float* beta, float eps,
+                                           float* out, const void* plan, void* workspace, size_t workspace_bytes,
+                                           int32_t stages, dsvt_stream_t stream);
+
 /* ------------------------------------------------------------------------ *
  * (next #4) dense linear layer  y = x * W^T + b on tcgen05 -- replaces the TensorRT FullyConnected
  * layers next to the plugins (fullyConnected_gelu_fullyConnected, src/dsvt-ai-trt.cpp:494-529).

@@ -5,8 +5,8 @@
 * ``build_reference()`` -- when ``/root/reference`` is present (authoring container only),
   nvcc-compiles the reference's OWN plugin sources, unmodified and in place, against the in-repo
   TensorRT scaffold header, one shared object per plugin (they define clashing global helpers,
-  SURVEY.md 2.1), each linked with ``oracle/ref_harness.cpp`` (a C harness that drives the plugin
-  through its IPluginCreator / IPluginV2DynamicExt interface).  Outputs go only to ``oracle/_ref/``
+  SURVEY.md 2.1), each linked with ``dsvt-ai-trt_b200/csrc/plugins/plugin_c_api.cpp`` (the C harness of
+  ``include/dsvt_b200_plugin_c.h``, which drives a plugin through its IPluginCreator / IPluginV2DynamicExt interface).  Outputs go only to ``oracle/_ref/``
   (git-ignored, shipped to the GPU box by gpurun).  No reference source is copied into the repo.
   The reference's own CMake build is NOT used (it needs TensorRT + Boost, both absent).
 """

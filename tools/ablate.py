@@ -22,7 +22,6 @@ def main():
     ap.add_argument("--groups", default="vox,pfn,smax,part,plan,pos,attn,attn_qkv,attn_core,attn_out,ln1,ffn1,ffn2,lnc,m2b,fbox")
     ap.add_argument("--kind", default="backbone3d", help="bench.FRAME_KINDS key")
     args = ap.parse_args()
-    os.environ.setdefault("DSVT_GEMM_SM_FRACTION", "50")
     import torch
     bench = importlib.import_module("bench")
     pkg = importlib.import_module("dsvt-ai-trt_b200")
@@ -38,11 +37,7 @@ def main():
         slots.append(s)
     torch.cuda.synchronize()
 
-    lib = pkg.load_library()
-
     def measure(skip):
-        mask = sum({"attn_qkv": 1, "attn_core": 2, "attn_out": 4}.get(g, 0) for g in skip)
-        lib.dsvt_debug_set_attention_skip_mask(mask)
         for i, s in enumerate(slots):
             s.frame.skip = frozenset(skip)
             s.capture(streams[i % len(streams)])

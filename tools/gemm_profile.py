@@ -1,7 +1,7 @@
 """One eager pass over the GEMM-class launches of the headline frame (bench frame 0) between cudaProfilerStart/Stop,
 for `ncu --profile-from-start off` captures:
 
-    ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'proj_gemm|attn_core' \
+    ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'proj_tile|attn_core' \
         -o gpurun_out/r2_gemm python tools/gemm_profile.py
 """
 import importlib
@@ -14,10 +14,9 @@ import torch  # noqa: E402
 pkg = importlib.import_module("dsvt-ai-trt_b200")
 capi = importlib.import_module("dsvt-ai-trt_b200.capi")
 pipeline = importlib.import_module("dsvt-ai-trt_b200.pipeline")
-os.environ.setdefault("DSVT_GEMM_SM_FRACTION", sys.argv[1] if len(sys.argv) > 1 else "100")
 cfg = pkg.config.WAYMO
 w = pipeline.FrameWeights(cfg, seed=0)
-f = pipeline.HotPathFrame(cfg, w, precision=capi.DSVT_ATTN_FP32_TC, ffn="fused", backbone=True)
+f = pipeline.HotPathFrame(cfg, w, precision=capi.DSVT_ATTN_FP32_TC, ffn="epilogue", backbone=True)
 f.load_points(pkg.synth.ring_lidar(200000, seed=0))
 for _ in range(2):
     f.run()
@@ -32,10 +31,11 @@ flush.zero_()
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
 capi.set_attention_fused(w.attn[0], x, f.pos_out[0][0], gs.global_index_in_set[0], gs.mask_expand_0[0], gs.set_num, V, axis=0,
-                         out=f.attn_out, precision=f.precision, workspace=f.attn_ws, plan=f.plans[(0, 0)])
+                         out=f.src, precision=f.precision, workspace=f.attn_ws, plan=f.plans[(0, 0)],
+                         norm=(x, w.gamma[0], w.beta[0], cfg.layer_norm_eps))
 fc1.rows(f.src, V, activation=1, out=f.gelu_out, zero_tails=0)
-fc2.rows_splitk(f.gelu_out, V, add=f.src, out=f.ffn_parts)
-second.rows(f.pos_hidden, V, out=f.pos_out[0][0], zero_tails=0)
+fc2.rows_norm(f.gelu_out, V, [(f.src, w.gamma[1], w.beta[1]), (x, w.gamma[2], w.beta[2])], cfg.layer_norm_eps, out=f.x_a)
+capi.pos_embed_mlp(first, second, f.wp[0].coors_in_win_x_y[0], V, out=f.pos_out[0][0], zero_tails=0)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
-print("profiled: QKV GEMM, core, out-projection, FFN linear 1 (+GELU), FFN linear 2 (split-K), pos-embed linear 2")
+print("profiled: QKV GEMM, core, out-projection + norm1, FFN linear 1 (+GELU), FFN linear 2 + LayerNorm chain, pos-embed MLP")
