@@ -148,6 +148,7 @@ FRAME_KINDS = {
     "backbone3d_graph": dict(ffn="graph", backbone=True),    # ... in the reference graph's node structure
     "plugin_only": dict(ffn="off", backbone=False),          # plugins only; TensorRT-native layers stood in by fixed tensors
     "relaxed_tails": dict(ffn="epilogue", backbone=True, zero_tails=0),
+    "backbone3d_postprocess": dict(ffn="epilogue", backbone=True, head=True),   # + CenterHead post-process graph + GPU NMS
 }
 
 
@@ -291,6 +292,18 @@ def plugin_breakdown(slot, cfg, peaks, reps=5):
                                           "in GEMM epilogues"}
     us = timed(lambda: capi.filter_box(cfg, *f.cand, boxes=f.boxes, valid=f.valid))
     res["filter_box"] = {"us": us, "bytes": 22000 + 18004, "calls_per_frame": 1}
+    # post-process graph + rotated NMS (legs.backbone3d_postprocess; not part of the headline frame)
+    pipeline_mod = importlib.import_module("dsvt-ai-trt_b200.pipeline")
+    hf = pipeline_mod.HotPathFrame(cfg, w, precision=f.precision, seed=0, ffn="off", backbone=False, head=True)
+    HWc = cfg.grid_x * cfg.grid_y
+    us = timed(lambda: hf.topk(*hf.head_maps))
+    res["center_head_topk"] = {"us": us, "bytes": 4 * 10 * HWc + cfg.max_top_k * 13 * 4, "calls_per_frame": 0, "scope": "next#4",
+                               "note": "sigmoid + two-stage TopK(500) + gathers + exp / atan of src/dsvt-ai-trt.cpp:1471-1691; 4 kernels"}
+    capi.filter_box(cfg, *hf.topk.outputs, boxes=hf.boxes, valid=hf.valid)
+    us = timed(lambda: hf.nms(hf.boxes, hf.valid))
+    res["rotated_nms"] = {"us": us, "bytes": 2 * cfg.max_top_k * 36, "calls_per_frame": 0, "scope": "next#4",
+                          "note": f"nms_cpu (include/helper.h:257-283) on the GPU: {int(hf.valid[0])} boxes in, {int(hf.nms.num[0])} out; 3 kernels"}
+    del hf
     # FFN (src/dsvt-ai-trt.cpp:494-529) on the FP32-accurate tcgen05 linear kernel; the second linear carries the LayerNorms
     # behind the FFN (norm2, norm, and the block's residual norm on every second layer) in its epilogue
     fc1, fc2 = w.ffn[0]
@@ -570,6 +583,10 @@ def _main():
         legs["fp16_config"] = leg("backbone3d", capi.DSVT_ATTN_FP16,
                                   "BASELINE.json configs[2]: same frames, set attention on the single fused FP16 tcgen05 kernel "
                                   "(QK^T / PV on tensor cores, FP32 accumulate), tolerance 1e-2")
+        legs["backbone3d_postprocess"] = leg("backbone3d_postprocess", precision,
+                                             "the headline frame + the CenterHead post-process graph (sigmoid / TopK / gathers / atan, "
+                                             "src/dsvt-ai-trt.cpp:1471-1691) on synthetic head maps feeding FilterBoxByScorePlugin, + the "
+                                             "rotated NMS the reference runs on the HOST (include/helper.h:257-283) as CUDA kernels")
         legs["relaxed_tails"] = leg("relaxed_tails", precision,
                                     "NOT the reference's contract: every plugin launched with zero_tails = 0 (rows beyond the "
                                     "valid counts left untouched; no consumer reads them) -- what the contract's zero tails cost")

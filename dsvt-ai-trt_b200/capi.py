@@ -593,3 +593,70 @@ def map2bev(voxel_features, coords, voxel_num, grid_x, grid_y, out=None):
     rc = _lib().dsvt_map2bev_launch(ctypes.byref(p), _ptr(voxel_features), _ptr(coords), _ptr(voxel_num), _ptr(out), _stream())
     _check(rc, "dsvt_map2bev_launch")
     return out
+
+
+class CenterHeadParams(Structure):
+    _fields_ = [("batch", c_int32), ("num_classes", c_int32), ("height", c_int32), ("width", c_int32), ("max_top_k", c_int32)]
+
+
+class NmsParams(Structure):
+    _fields_ = [("batch", c_int32), ("max_boxes", c_int32), ("nms_thresh", c_float), ("zero_tails", c_int32)]
+
+
+class CenterHeadTopK:
+    """The CenterHead post-process graph in front of FilterBoxByScorePlugin (dsvt_center_head_topk_launch): pre-allocated
+    outputs in the plugin's input order -- scores, classes, xs, ys, center, center_z, angle, dim."""
+
+    def __init__(self, num_classes, height, width, max_top_k=500, batch=1, device="cuda"):
+        self.p = CenterHeadParams(batch, num_classes, height, width, max_top_k)
+        lib = _lib()
+        lib.dsvt_center_head_topk_workspace_size.restype = c_size_t
+        n = int(lib.dsvt_center_head_topk_workspace_size(ctypes.byref(self.p)))
+        if n == 0:
+            raise DsvtError("center_head_topk: " + lib.dsvt_last_error().decode())
+        B, K = batch, max_top_k
+        self.ws = torch.empty(n, dtype=torch.uint8, device=device)
+        self.scores = torch.empty(B, K, dtype=torch.float32, device=device)
+        self.classes, self.xs, self.ys = (torch.empty(B, K, dtype=torch.int32, device=device) for _ in range(3))
+        self.center = torch.empty(B, 1, K, 2, dtype=torch.float32, device=device)
+        self.center_z = torch.empty(B, 1, K, 1, dtype=torch.float32, device=device)
+        self.angle = torch.empty(B, 1, K, 1, dtype=torch.float32, device=device)
+        self.dim = torch.empty(B, 1, K, 3, dtype=torch.float32, device=device)
+
+    @property
+    def outputs(self):
+        return [self.scores, self.classes, self.xs, self.ys, self.center, self.center_z, self.angle, self.dim]
+
+    def __call__(self, heatmap, center, center_z, dim, rot):
+        for t, n in ((heatmap, "heatmap"), (center, "center"), (center_z, "center_z"), (dim, "dim"), (rot, "rot")):
+            _need(t, torch.float32, n)
+        rc = _lib().dsvt_center_head_topk_launch(
+            ctypes.byref(self.p), _ptr(heatmap), _ptr(center), _ptr(center_z), _ptr(dim), _ptr(rot), _ptr(self.scores),
+            _ptr(self.classes), _ptr(self.xs), _ptr(self.ys), _ptr(self.center), _ptr(self.center_z), _ptr(self.angle),
+            _ptr(self.dim), _ptr(self.ws), c_size_t(self.ws.numel()), _stream())
+        _check(rc, "dsvt_center_head_topk_launch")
+        return self
+
+
+class RotatedNms:
+    """nms_cpu of the reference (include/helper.h:257-283) on the GPU: dsvt_rotated_nms_launch."""
+
+    def __init__(self, max_boxes=500, nms_thresh=0.01, batch=1, device="cuda", zero_tails=1):
+        self.p = NmsParams(batch, max_boxes, nms_thresh, zero_tails)
+        lib = _lib()
+        lib.dsvt_rotated_nms_workspace_size.restype = c_size_t
+        n = int(lib.dsvt_rotated_nms_workspace_size(ctypes.byref(self.p)))
+        if n == 0:
+            raise DsvtError("rotated_nms: " + lib.dsvt_last_error().decode())
+        self.ws = torch.empty(n, dtype=torch.uint8, device=device)
+        self.boxes = torch.empty(batch, max_boxes, 9, dtype=torch.float32, device=device)
+        self.num = torch.empty(batch, dtype=torch.int32, device=device)
+        self.keep = torch.empty(batch, max_boxes, dtype=torch.int32, device=device)
+
+    def __call__(self, boxes, valid):
+        _need(boxes, torch.float32, "boxes")
+        _need(valid, torch.int32, "valid")
+        rc = _lib().dsvt_rotated_nms_launch(ctypes.byref(self.p), _ptr(boxes), _ptr(valid), _ptr(self.boxes), _ptr(self.num),
+                                            _ptr(self.keep), _ptr(self.ws), c_size_t(self.ws.numel()), _stream())
+        _check(rc, "dsvt_rotated_nms_launch")
+        return self

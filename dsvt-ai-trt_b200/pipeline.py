@@ -167,7 +167,7 @@ class HotPathFrame:
     """Buffers + launch sequence for one frame slot (one CUDA stream owns one slot)."""
 
     def __init__(self, cfg, weights, precision=capi.DSVT_ATTN_FP32, seed=0, device="cuda", fuse_ln=True, share_plans=True,
-                 ffn="off", skip=(), zero_tails=1, backbone=False):
+                 ffn="off", skip=(), zero_tails=1, backbone=False, head=False):
         assert ffn in ("off", "graph", "fused", "epilogue")
         assert not backbone or ffn != "off", "backbone=True runs every layer: it needs the FFN linears on"
         self.backbone = backbone
@@ -225,6 +225,19 @@ class HotPathFrame:
         self.bev = torch.empty(cfg.grid_y, cfg.grid_x, C, device=device)
         self.boxes = torch.empty(1, cfg.max_top_k, 9, device=device)
         self.valid = torch.empty(1, dtype=torch.int32, device=device)
+        # head=True: the post-process graph behind the CenterHead (sigmoid / TopK / gathers, src/dsvt-ai-trt.cpp:1471-1691) on
+        # synthetic head maps (the 2-D backbone + CenterHead convolutions are not executed), FilterBoxByScorePlugin on ITS
+        # outputs instead of on synthetic candidates, and the rotated NMS the reference runs on the host (helper.h:257-283)
+        self.head = head
+        if head:
+            nc = 10
+            gh = torch.Generator(device="cpu").manual_seed(seed + 77)
+            r = lambda c, mul=1.0, add=0.0: torch.randn(1, c, cfg.grid_y, cfg.grid_x, generator=gh).mul_(mul).add_(add).to(device)
+            # heat-map logits with ~250 cells above the 0.3 score threshold, centre offsets in [0,1), log sizes, (cos, sin)
+            self.head_maps = (r(nc, 1.0, -4.6), torch.rand(1, 2, cfg.grid_y, cfg.grid_x, generator=gh).to(device),
+                              r(1, 0.8, -1.0), r(3, 0.4, 0.5), r(2))
+            self.topk = capi.CenterHeadTopK(nc, cfg.grid_y, cfg.grid_x, cfg.max_top_k, device=device)
+            self.nms = capi.RotatedNms(cfg.max_top_k, 0.01, device=device, zero_tails=self.zero_tails)      # NMS_THRESH, params.h:334
         self.launches_per_frame = None
 
     def load_points(self, pts_np):
@@ -355,7 +368,11 @@ class HotPathFrame:
         self.final = x
         if "m2b" not in skip:
             capi.map2bev(x, vox.coords[0], V, cfg.grid_x, cfg.grid_y, out=self.bev)      # :1128
-        if "fbox" not in skip:
+        if self.head:
+            self.topk(*self.head_maps)
+            capi.filter_box(cfg, *self.topk.outputs, boxes=self.boxes, valid=self.valid, zero_tails=zt)
+            self.nms(self.boxes, self.valid)
+        elif "fbox" not in skip:
             capi.filter_box(cfg, *self.cand, boxes=self.boxes, valid=self.valid, zero_tails=zt)
         self.launches_per_frame = capi.launch_count() - before
         return self

@@ -432,6 +432,51 @@ typedef struct dsvt_map2bev_params {
 int dsvt_map2bev_launch(const dsvt_map2bev_params* p, const float* voxel_features, const int32_t* coords,
                         const int32_t* voxel_num, float* map_features, dsvt_stream_t stream);
 
+/* ------------------------------------------------------------------------ *
+ * (next #4, tail) CenterHead post-process graph         src/dsvt-ai-trt.cpp:1471-1691 (TensorRT layers: sigmoid, exp,
+ *                                                       TopK x2, index arithmetic, gathers, atan) -- produces the eight
+ *                                                       inputs of FilterBoxByScorePlugin
+ * ------------------------------------------------------------------------ */
+typedef struct dsvt_center_head_params {
+    int32_t batch;
+    int32_t num_classes;            /* 10 */
+    int32_t height, width;          /* 468 x 468 (feature-map stride 1) */
+    int32_t max_top_k;              /* HM_TOP_K 500 (<= 1024) */
+} dsvt_center_head_params;
+size_t dsvt_center_head_topk_workspace_size(const dsvt_center_head_params* p);
+/*
+ * in : heatmap [B,num_classes,H,W] f32 LOGITS (hm head output before the sigmoid) ; center [B,2,H,W] ; center_z [B,1,H,W] ;
+ *      dim [B,3,H,W] (log sizes) ; rot [B,2,H,W] (channel 0 = cos, 1 = sin)
+ * out: scores [B,K] f32 = sigmoid of the K largest logits over all classes and cells, descending (ties: ascending flat
+ *      index class*H*W + y*W + x) ; classes, xs, ys [B,K] i32 ; center [B,1,K,2] ; center_z [B,1,K,1] ; angle [B,1,K,1] =
+ *      atan(sin / cos) ; dim [B,1,K,3] = exp(dim)          -- the input tensors of dsvt_filter_box_launch, in its order.
+ */
+int dsvt_center_head_topk_launch(const dsvt_center_head_params* p, const float* heatmap, const float* center,
+                                 const float* center_z, const float* dim, const float* rot, float* scores,
+                                 int32_t* classes, int32_t* xs, int32_t* ys, float* center_g, float* center_z_g,
+                                 float* angle, float* dim_g, void* workspace, size_t workspace_bytes, dsvt_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * (next #4, tail) rotated NMS                            include/helper.h:257-283 (nms_cpu; box_overlap :166-255), run by
+ *                                                       the reference on the HOST after the engine (src/dsvt-ai-trt.cpp:1954)
+ * ------------------------------------------------------------------------ */
+typedef struct dsvt_nms_params {
+    int32_t batch;
+    int32_t max_boxes;              /* rows of `boxes` per frame: max_top_k 500 (<= 1024) */
+    float nms_thresh;               /* NMS_THRESH 0.01 (params.h:334) */
+    int32_t zero_tails;
+} dsvt_nms_params;
+size_t dsvt_rotated_nms_workspace_size(const dsvt_nms_params* p);
+/*
+ * in : boxes [B,max_boxes,9] f32 (x,y,z,dx,dy,dz,angle,class,score) and valid [B] i32 = FilterBoxByScorePlugin's outputs
+ * out: out_boxes [B,max_boxes,9] = the surviving boxes in descending score order (ties: ascending input index -- the
+ *      reference's std::sort leaves ties unspecified), out_num [B], keep_index [B,max_boxes] i32 (input row of every
+ *      survivor; may be NULL).  A box suppresses every lower-scored box with rotated IoU >= nms_thresh.
+ */
+int dsvt_rotated_nms_launch(const dsvt_nms_params* p, const float* boxes, const int32_t* valid, float* out_boxes,
+                            int32_t* out_num, int32_t* keep_index, void* workspace, size_t workspace_bytes,
+                            dsvt_stream_t stream);
+
 /* standalone forms of the two gather/scatter plugins (next #2), kept for graph compatibility */
 int dsvt_get_value_by_index_launch(const dsvt_set_attention_params* p, const float* x, const float* pos,
                                    const int32_t* global_index_in_set, const int32_t* set_num,

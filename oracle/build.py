@@ -105,8 +105,31 @@ def build_reference(verbose=False, variant=None):
     return built
 
 
+def build_reference_nms(verbose=False):
+    """The reference's host-side rotated NMS (include/helper.h:92-283), compiled unmodified behind a 12-line C entry point
+    (oracle/ref_nms_harness.cpp) -> oracle/_ref/libref_nms.so.  Returns the path or None."""
+    so = os.path.join(HERE, "_ref", "libref_nms.so")
+    if not reference_available():
+        return so if os.path.exists(so) else None
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    harness = os.path.join(HERE, "ref_nms_harness.cpp")
+    hdr = os.path.join(REF, "include", "helper.h")
+    if _newer(so, [harness, hdr]):
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+        cmd = ["g++", "-std=c++14", "-O2", "-w", "-fPIC", "-shared", "-ffp-contract=off", "-I" + STUB, "-I" + os.path.join(REF, "include"),
+               "-I" + cuda_inc, harness, "-o", so]
+        if verbose:
+            print(" ".join(cmd))
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(f"[oracle/_ref] nms: build failed\n{r.stderr[-2000:]}\n")
+            return None
+    return so
+
+
 if __name__ == "__main__":
     print(build_oracle(verbose=True))
     for variant in (None, "waymo"):
         for k, v in build_reference(verbose=True, variant=variant).items():
             print(variant, k, v)
+    print(build_reference_nms(verbose=True))

@@ -185,3 +185,44 @@ def map2bev(voxel_features, coords, voxel_num, gx, gy):
     out = np.zeros((gy, gx, C), np.float32)
     lib().oracle_map2bev(_p(f), _p(co), c_int(int(voxel_num)), c_int(max_pillars), c_int(C), c_int(gx), c_int(gy), _p(out))
     return out
+
+
+def center_head_topk(heatmap, center, center_z, dim, rot, K=500):
+    """The post-process graph of src/dsvt-ai-trt.cpp:1471-1691, literally: sigmoid, TopK(K) per class over H*W, TopK(K) over
+    the nc*K survivors, index arithmetic, gathers, exp / atan.  Both TopKs are stable (score descending, earlier element
+    first on ties: for the flattened second stage that is class-major, i.e. ascending flat index).  float32 throughout.
+    heatmap [nc,H,W] logits, center [2,H,W], center_z [1,H,W], dim [3,H,W], rot [2,H,W] (cos, sin)."""
+    hm = _f32(heatmap)
+    nc, H, W = hm.shape
+    HW = H * W
+    s = (np.float32(1.0) / (np.float32(1.0) + np.exp(-hm, dtype=np.float32))).reshape(nc, HW)       # :1479
+    # stage 1 orders by the LOGIT so that sigmoid ties (saturation) do not reorder what the GPU selects on; where the
+    # sigmoids are distinct this is the same order
+    inds = np.stack([np.argsort(-hm.reshape(nc, HW)[c], kind="stable")[:K] for c in range(nc)])      # :1513  [nc,K]
+    sc1 = np.take_along_axis(s, inds, axis=1)
+    lg1 = np.take_along_axis(hm.reshape(nc, HW), inds, axis=1)
+    ind2 = np.argsort(-lg1.reshape(-1), kind="stable")[:K]                                            # :1563
+    scores = sc1.reshape(-1)[ind2]
+    classes = (ind2 // K).astype(np.int32)                                                            # :1570
+    cell = inds.reshape(-1)[ind2]                                                                     # :1592
+    ys, xs = (cell // W).astype(np.int32), (cell % W).astype(np.int32)                                # :1543-1547
+    c = _f32(center).reshape(2, HW)
+    d = np.exp(_f32(dim).reshape(3, HW), dtype=np.float32)                                            # :1489
+    r = _f32(rot).reshape(2, HW)
+    return dict(scores=scores.astype(np.float32), classes=classes, xs=xs, ys=ys,
+                center=np.stack([c[0, cell], c[1, cell]], axis=1), center_z=_f32(center_z).reshape(HW)[cell],
+                angle=np.arctan(r[1, cell] / r[0, cell]).astype(np.float32), dim=np.stack([d[0, cell], d[1, cell], d[2, cell]], axis=1))
+
+
+def nms(boxes, n, nms_thresh):
+    """nms_cpu (include/helper.h:257-283) restated in C: input rows of the surviving boxes, in output order."""
+    boxes = _f32(boxes)
+    keep = np.zeros(max(int(n), 1), np.int32)
+    k = lib().oracle_nms(_p(boxes), c_int(int(n)), c_float(nms_thresh), _p(keep))
+    return keep[:k].copy()
+
+
+def nms_iou(boxes, i, j):
+    fn = lib().oracle_nms_iou
+    fn.restype = ctypes.c_float
+    return float(fn(_p(_f32(boxes)), c_int(int(i)), c_int(int(j))))

@@ -472,3 +472,112 @@ ORACLE_API void oracle_map2bev(const float* voxel_features, const int* coords, i
             map[((size_t) y * gx + x) * C + c] = voxel_features[(size_t) v * C + c];   /* :263 */
     }
 }
+
+/* ------------------------------------------------------------------------- *
+ * next #4 tail  rotated NMS on the host: include/helper.h:92-283 (nms_cpu, box_overlap, intersection, check_box2d,
+ * rotate_around_center; the code the reference took from CUDA-PointPillars' postprocess.cpp).  float arithmetic and
+ * the order of operations are kept; std::sort is restated as a STABLE descending sort (ties keep input order).
+ * boxes [n,9] = (x, y, z, dx, dy, dz, angle, class, score) as FilterBoxByScorePlugin emits them (:1954).
+ * keep[] receives the input indices of the surviving boxes in output order; returns their number.
+ * ------------------------------------------------------------------------- */
+typedef struct { float x, y; } nms_f2;
+typedef struct { float x, y, z, w, l, h, rt; int id; float score; } nms_box;
+static const float kNmsEps = 1e-8f;                                                /* helper.h:26 ThresHold */
+
+static float nms_cross(nms_f2 p1, nms_f2 p2, nms_f2 p0) {                         /* :107-109 */
+    return (p1.x - p0.x) * (p2.y - p0.y) - (p2.x - p0.x) * (p1.y - p0.y);
+}
+static int nms_check_box2d(const nms_box* box, nms_f2 p) {                         /* :111-121 */
+    const float MARGIN = 1e-2f;
+    const float angle_cos = cosf(-box->rt), angle_sin = sinf(-box->rt);            /* cos/sin(float) -> float overloads */
+    const float rot_x = (p.x - box->x) * angle_cos + (p.y - box->y) * (-angle_sin);
+    const float rot_y = (p.x - box->x) * angle_sin + (p.y - box->y) * angle_cos;
+    return (fabsf(rot_x) < box->w / 2 + MARGIN && fabsf(rot_y) < box->l / 2 + MARGIN);
+}
+static int nms_intersection(nms_f2 p1, nms_f2 p0, nms_f2 q1, nms_f2 q0, nms_f2* ans) {   /* :123-157 */
+    if ((fminf(p0.x, p1.x) <= fmaxf(q0.x, q1.x) && fminf(q0.x, q1.x) <= fmaxf(p0.x, p1.x) &&
+         fminf(p0.y, p1.y) <= fmaxf(q0.y, q1.y) && fminf(q0.y, q1.y) <= fmaxf(p0.y, p1.y)) == 0)
+        return 0;
+    const float s1 = nms_cross(q0, p1, p0), s2 = nms_cross(p1, q1, p0);
+    const float s3 = nms_cross(p0, q1, q0), s4 = nms_cross(q1, p1, q0);
+    if (!(s1 * s2 > 0 && s3 * s4 > 0)) return 0;
+    const float s5 = nms_cross(q1, p1, p0);
+    if (fabsf(s5 - s1) > kNmsEps) {
+        ans->x = (s5 * q0.x - s1 * q1.x) / (s5 - s1);
+        ans->y = (s5 * q0.y - s1 * q1.y) / (s5 - s1);
+    } else {
+        const float a0 = p0.y - p1.y, b0 = p1.x - p0.x, c0 = p0.x * p1.y - p1.x * p0.y;
+        const float a1 = q0.y - q1.y, b1 = q1.x - q0.x, c1 = q0.x * q1.y - q1.x * q0.y;
+        const float D = a0 * b1 - a1 * b0;
+        ans->x = (b0 * c1 - b1 * c0) / D;
+        ans->y = (a1 * c0 - a0 * c1) / D;
+    }
+    return 1;
+}
+static void nms_rotate(nms_f2 c, float ac, float as, nms_f2* p) {                  /* :159-164 */
+    const float nx = (p->x - c.x) * ac + (p->y - c.y) * (-as) + c.x;
+    const float ny = (p->x - c.x) * as + (p->y - c.y) * ac + c.y;
+    p->x = nx; p->y = ny;
+}
+static float nms_box_overlap(const nms_box* a, const nms_box* b) {                 /* :166-255 */
+    const float a_dx = a->w / 2, b_dx = b->w / 2, a_dy = a->l / 2, b_dy = b->l / 2;
+    nms_f2 ca[5] = {{a->x - a_dx, a->y - a_dy}, {a->x + a_dx, a->y - a_dy}, {a->x + a_dx, a->y + a_dy}, {a->x - a_dx, a->y + a_dy}, {0, 0}};
+    nms_f2 cb[5] = {{b->x - b_dx, b->y - b_dy}, {b->x + b_dx, b->y - b_dy}, {b->x + b_dx, b->y + b_dy}, {b->x - b_dx, b->y + b_dy}, {0, 0}};
+    const nms_f2 center_a = {a->x, a->y}, center_b = {b->x, b->y};
+    nms_f2 pts[16], pc = {0, 0};
+    int cnt = 0;
+    const float a_cos = cosf(a->rt), a_sin = sinf(a->rt), b_cos = cosf(b->rt), b_sin = sinf(b->rt);
+    for (int k = 0; k < 4; ++k) { nms_rotate(center_a, a_cos, a_sin, &ca[k]); nms_rotate(center_b, b_cos, b_sin, &cb[k]); }
+    ca[4] = ca[0]; cb[4] = cb[0];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            if (nms_intersection(ca[i + 1], ca[i], cb[j + 1], cb[j], &pts[cnt])) { pc.x += pts[cnt].x; pc.y += pts[cnt].y; ++cnt; }
+    for (int k = 0; k < 4; ++k) {
+        if (nms_check_box2d(a, cb[k])) { pc.x += cb[k].x; pc.y += cb[k].y; pts[cnt++] = cb[k]; }
+        if (nms_check_box2d(b, ca[k])) { pc.x += ca[k].x; pc.y += ca[k].y; pts[cnt++] = ca[k]; }
+    }
+    pc.x /= cnt; pc.y /= cnt;
+    for (int j = 0; j < cnt - 1; ++j)
+        for (int i = 0; i < cnt - j - 1; ++i)
+            if (atan2f(pts[i].y - pc.y, pts[i].x - pc.x) > atan2f(pts[i + 1].y - pc.y, pts[i + 1].x - pc.x)) {
+                const nms_f2 t = pts[i]; pts[i] = pts[i + 1]; pts[i + 1] = t;
+            }
+    float area = 0;
+    for (int k = 0; k < cnt - 1; ++k) {
+        const nms_f2 u = {pts[k].x - pts[0].x, pts[k].y - pts[0].y}, v = {pts[k + 1].x - pts[0].x, pts[k + 1].y - pts[0].y};
+        area += (u.x * v.y - u.y * v.x);
+    }
+    return (float) (fabs((double) area) / 2.0);                                    /* fabs(area) / 2.0 in double, returned as float */
+}
+/* pairwise IoU of boxes i, j (for the tests: distance of every decision from the threshold) */
+ORACLE_API float oracle_nms_iou(const float* boxes, int i, int j)
+{
+    nms_box a = {boxes[i * 9], boxes[i * 9 + 1], boxes[i * 9 + 2], boxes[i * 9 + 3], boxes[i * 9 + 4], boxes[i * 9 + 5], boxes[i * 9 + 6], i, boxes[i * 9 + 8]};
+    nms_box b = {boxes[j * 9], boxes[j * 9 + 1], boxes[j * 9 + 2], boxes[j * 9 + 3], boxes[j * 9 + 4], boxes[j * 9 + 5], boxes[j * 9 + 6], j, boxes[j * 9 + 8]};
+    const float sa = a.w * a.l, sb = b.w * b.l, so = nms_box_overlap(&a, &b);
+    return so / fmaxf(sa + sb - so, kNmsEps);
+}
+ORACLE_API int oracle_nms(const float* boxes, int n, float nms_thresh, int* keep)  /* :257-283 */
+{
+    if (n <= 0) return 0;
+    int* order = (int*) malloc((size_t) n * sizeof(int));
+    char* suppressed = (char*) calloc((size_t) n, 1);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    for (int i = 1; i < n; ++i) {                       /* stable insertion sort, descending score */
+        const int v = order[i];
+        int j = i - 1;
+        while (j >= 0 && boxes[order[j] * 9 + 8] < boxes[v * 9 + 8]) { order[j + 1] = order[j]; --j; }
+        order[j + 1] = v;
+    }
+    int kept = 0;
+    for (int i = 0; i < n; ++i) {
+        if (suppressed[i]) continue;
+        keep[kept++] = order[i];
+        for (int j = i + 1; j < n; ++j) {
+            if (suppressed[j]) continue;
+            if (oracle_nms_iou(boxes, order[i], order[j]) >= nms_thresh) suppressed[j] = 1;
+        }
+    }
+    free(order); free(suppressed);
+    return kept;
+}
