@@ -103,8 +103,15 @@ static int attn_dispatch(const dsvt_set_attention_params* p, const dsvt_attentio
         return DSVT_ERR_UNSUPPORTED;
     }
     if (norm && p->precision != DSVT_ATTN_FP32_TC && p->precision != DSVT_ATTN_FP16_GEMM) {
-        set_last_error("set attention + norm: built for the GEMM-pipeline precisions (DSVT_ATTN_FP32_TC / DSVT_ATTN_FP16_GEMM)");
-        return DSVT_ERR_UNSUPPORTED;
+        // single-kernel precisions have no GEMM epilogue to carry the norm: attention into `out`, then the row-wise
+        // LayerNorm kernel over out + residual in place (same arithmetic, one more launch)
+        if (!fused) { set_last_error("set attention + norm: fused entry points only"); return DSVT_ERR_UNSUPPORTED; }
+        int rc = attn_dispatch(p, w, fused, q, k, v, pos, idx, mask, set_num, voxel_num, out, plan, workspace, workspace_bytes, st,
+                               nullptr, 7);
+        if (rc != DSVT_OK) return rc;
+        const dsvt_layer_norm_params lp{p->batch, p->max_pillars_num, p->channel_num, norm->eps, 1};
+        return dsvt_layer_norm_launch(&lp, out, norm->residual, voxel_num, norm->gamma, norm->beta, out,
+                                      reinterpret_cast<dsvt_stream_t>(st));
     }
     switch (p->precision) {
         case DSVT_ATTN_FP32_TC:

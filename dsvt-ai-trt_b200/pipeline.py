@@ -236,9 +236,25 @@ class HotPathFrame:
             # heat-map logits with ~250 cells above the 0.3 score threshold, centre offsets in [0,1), log sizes, (cos, sin)
             self.head_maps = (r(nc, 1.0, -4.6), torch.rand(1, 2, cfg.grid_y, cfg.grid_x, generator=gh).to(device),
                               r(1, 0.8, -1.0), r(3, 0.4, 0.5), r(2))
+            # head="conv": the head maps come from the cuDNN stand-in of the 2-D backbone + CenterHead convolutions run on the
+            # frame's own BEV map (conv_standin.py: library code with random weights, labelled; bench "whole_pipeline" leg)
+            self.conv = None
+            if head == "conv":
+                cs = __import__("importlib").import_module(__package__ + ".conv_standin")
+                self.conv = cs.BevHeadStandIn(cfg.grid_y, cfg.grid_x, seed=seed + 78, device=device)
             self.topk = capi.CenterHeadTopK(nc, cfg.grid_y, cfg.grid_x, cfg.max_top_k, device=device)
             self.nms = capi.RotatedNms(cfg.max_top_k, 0.01, device=device, zero_tails=self.zero_tails)      # NMS_THRESH, params.h:334
         self.launches_per_frame = None
+
+    def calibrate_head(self, n_above=250):
+        """head="conv" only, random weights: shift the heat-map bias so that n_above cells of THIS frame's map score above
+        SCORE_THRESH (a trained head's map is that sparse); one frame run + sync, outside any timed region."""
+        self.run()
+        torch.cuda.synchronize()
+        m = self.conv(self.bev)["hm"].flatten()
+        kth = torch.topk(m, n_above).values[-1].item()
+        logit = float(np.log(self.cfg.score_threshold / (1.0 - self.cfg.score_threshold)))
+        self.conv.heads["hm"][1][1].add_(logit - kth)
 
     def load_points(self, pts_np):
         n = min(len(pts_np), self.cfg.max_points_num)
@@ -369,7 +385,11 @@ class HotPathFrame:
         if "m2b" not in skip:
             capi.map2bev(x, vox.coords[0], V, cfg.grid_x, cfg.grid_y, out=self.bev)      # :1128
         if self.head:
-            self.topk(*self.head_maps)
+            if self.conv is not None:
+                m = self.conv(self.bev)
+                self.topk(m["hm"], m["center"], m["center_z"], m["dim"], m["rot"])
+            else:
+                self.topk(*self.head_maps)
             capi.filter_box(cfg, *self.topk.outputs, boxes=self.boxes, valid=self.valid, zero_tails=zt)
             self.nms(self.boxes, self.valid)
         elif "fbox" not in skip:

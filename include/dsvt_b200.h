@@ -299,7 +299,8 @@ int dsvt_set_attention_fused_planned_launch(const dsvt_set_attention_params* p, 
  * The fused form followed by the encoder layer's first residual add + LayerNorm in the same launch sequence:
  *   out = LayerNorm(attention(x, pos) + residual) * gamma + beta      (norm1(src2 + src), src/dsvt-ai-trt.cpp:669-676;
  * addElementWise(kSUM) + LayerNormPlugin) -- the LayerNorm runs in the out-projection's epilogue, the attention output
- * itself never reaches memory.  GEMM-pipeline precisions only; plan may be NULL (rebuilt per call).  residual
+ * itself never reaches memory (GEMM-pipeline precisions; the single-kernel precisions run attention + the row-wise LayerNorm
+ * kernel in place, same results, one more launch).  plan may be NULL (rebuilt per call).  residual
  * [B,max_pillars_num,C], gamma / beta [C] on the device.  Arithmetic of the LayerNorm = dsvt_layer_norm_launch.
  */
 int dsvt_set_attention_fused_norm_launch(const dsvt_set_attention_params* p, const dsvt_attention_weights* w,

@@ -151,6 +151,19 @@ def test_whole_3d_backbone_chain(frame0, cfgs, ffn):
     assert np.abs(gbev - bev).max() <= 5e-4
 
 
+@pytest.mark.parametrize("precision,tol", [("DSVT_ATTN_FP32", 5e-4), ("DSVT_ATTN_FP16", 1e-2)])
+def test_backbone_chain_single_kernel_precisions(frame0, cfgs, precision, tol):
+    """The headline frame kind (norms in the epilogues) with the single-kernel set attention precisions -- the bench's
+    fp16_config leg (BASELINE.json configs[2], tolerance 1e-2) and the CUDA-core FP32 path: dsvt_set_attention_fused_norm_launch
+    falls back to attention + row-wise LayerNorm there."""
+    capi = importlib.import_module("dsvt-ai-trt_b200.capi")
+    pipeline = importlib.import_module("dsvt-ai-trt_b200.pipeline")
+    cfg = cfgs.REFERENCE.with_(num_blocks=2)
+    w = pipeline.FrameWeights(cfg, seed=4)
+    fr = _run_backbone(cfg, w, frame0, ffn="epilogue", precision=getattr(capi, precision))
+    _check_backbone(fr, w, cfg, frame0, tol)
+
+
 # ---- the bench workload and the trained weights (VERDICT r1 items 1b-1d) -----------------------------------------
 def _run_backbone(cfg, w, cloud, seed=6, ffn="graph", precision=None):
     capi = importlib.import_module("dsvt-ai-trt_b200.capi")

@@ -103,3 +103,40 @@ def test_rotated_nms_gpu(n, seed, spread, thresh):
     else:
         out = op.boxes[0].cpu().numpy()
         assert np.array_equal(out[:got_n], boxes[keep]) and np.all(out[got_n:] == 0)
+
+
+@pytest.mark.gpu
+def test_whole_pipeline_postprocess_parity():
+    """The whole_pipeline frame kind (points -> 3-D backbone -> BEV map -> cuDNN stand-in convolutions -> post-process graph ->
+    FilterBoxByScore -> rotated NMS): the post-process half is checked against the oracle on the head maps the frame really
+    produced.  Those maps come out of BF16 convolutions, so the heat map is full of exact ties -- the tie order (ascending
+    flat index) has to hold for the candidate lists to match."""
+    import torch
+    capi = importlib.import_module("dsvt-ai-trt_b200.capi")
+    pipeline = importlib.import_module("dsvt-ai-trt_b200.pipeline")
+    synth = importlib.import_module("dsvt-ai-trt_b200.synth")
+    config = importlib.import_module("dsvt-ai-trt_b200.config")
+    cfg = config.WAYMO
+    w = pipeline.FrameWeights(cfg, seed=3)
+    f = pipeline.HotPathFrame(cfg, w, precision=capi.DSVT_ATTN_FP32_TC, seed=3, ffn="epilogue", backbone=True, head="conv")
+    f.load_points(synth.ring_lidar(60_000, seed=5))
+    f.calibrate_head(n_above=180)
+    f.run()
+    torch.cuda.synchronize()
+    m = {k: v[0].cpu().numpy() for k, v in f.conv(f.bev).items()}
+    n_ties = m["hm"].size - np.unique(m["hm"]).size
+    assert n_ties > 1000                                            # the premise of the test
+    o = cpu.center_head_topk(m["hm"], m["center"], m["center_z"], m["dim"], m["rot"], cfg.max_top_k)
+    t = f.topk
+    assert np.array_equal(t.classes[0].cpu().numpy(), o["classes"])
+    assert np.array_equal(t.xs[0].cpu().numpy(), o["xs"]) and np.array_equal(t.ys[0].cpu().numpy(), o["ys"])
+    # FilterBoxByScore + NMS on the GPU's own candidates (last-bit differences of exp / atan must not be blamed on them)
+    g = lambda a: a.cpu().numpy()
+    boxes, valid, _ = cpu.filter_box(g(t.scores[0]), g(t.classes[0]), g(t.xs[0]), g(t.ys[0]), g(t.center[0, 0]), g(t.center_z[0, 0, :, 0]),
+                                     g(t.angle[0, 0, :, 0]), g(t.dim[0, 0]), cfg)
+    assert int(f.valid[0]) == valid and 50 <= valid <= cfg.max_top_k
+    assert np.array_equal(g(f.boxes[0]), boxes)
+    keep = cpu.nms(boxes, valid, 0.01)
+    n = int(f.nms.num[0])
+    assert n == len(keep) and np.array_equal(g(f.nms.keep[0, :n]), keep)
+    assert np.array_equal(g(f.nms.boxes[0, :n]), boxes[keep])
