@@ -130,10 +130,13 @@ __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 // GELU, tanh form with the reference's constants (gelu.cu:201-211, params.h:75-77) as the logistic identity
-// 0.5 + 0.5 tanh(u) = 1 / (1 + e^(-2u)) -- the same f32 formulation as rowwise.cu's GeluPlugin kernel
+// 0.5 + 0.5 tanh(u) = 1 / (1 + e^(-2u)) -- the f32 formulation of rowwise.cu's GeluPlugin kernel, with the quotient as
+// reciprocal-multiply (MUFU.RCP, <= 2 ulp; e^(-2u) = inf gives x * 0 = -0 like the exact division): the IEEE division's
+// Newton step + slow-path call per element made the FFN epilogue 2.3x as long as the plain one (21 k vs 9 k cycles per CTA,
+// profiles/r2_tile_profile.txt; half of its stall samples were instruction-fetch misses in the unrolled division code)
 __device__ __forceinline__ float gelu_tanh(float x) {
     const float u = x * (0.035677408136300125f * x * x + 0.7978845608028654f);
-    return x / (1.0f + __expf(-2.0f * u));
+    return __fdividef(x, 1.0f + __expf(-2.0f * u));
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -359,49 +362,65 @@ proj_tile_kernel(const __grid_constant__ GemmRoles roles, const int* __restrict_
                 }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight epilogue warps
+            if (tid == 0) TP(10);
             // ---- pass B: half a warp per row, the chain of layer_norm192_chain_kernel (rowwise.cu) on the staged rows ---
+            // The residual rows of iteration it + 1 (every stage) are loaded while iteration it is computed: issued in program
+            // order behind each stage, they put 8 x n_ln dependent memory round trips on the epilogue (27 k of a CTA's 47 k cycles,
+            // profiles/r2_tile_profile.txt).
             const int sub = lane & 15;
             const unsigned hmask = 0xFFFFu << (lane & 16);
-#pragma unroll 1
-            for (int it = 0; it < 8; ++it) {
-                const int rloc = warp * 16 + it * 2 + (lane >> 4), grow = row_base + rloc;
-                if (grow >= max_pillars) continue;
-                float4* orow4 = reinterpret_cast<float4*>(out + (size_t) grow * g.ld_out);
-                if (grow >= V) {
-                    if (zero_tails)
+            // The work of a half-warp is the list of entries n = (row it, stage st), st fastest.  The residual pieces of entries
+            // n + 1 .. n + 3 are in flight while entry n is computed (a rotating queue of three register slots, refilled as soon
+            // as a slot is consumed): one row of lead for a 3-stage chain, three rows for norm1 alone.  Issued at their place in
+            // program order, the loads put 8 x n_ln dependent memory round trips on the epilogue (27 k of a CTA's 47 k cycles).
+            float4 rq[3][3];
+            const int n_ln = g.n_ln, total = 8 * n_ln;
+            auto res_load = [&](int n, float4 (&d)[3]) {
+                const int it = n / n_ln, st = n - it * n_ln;
+                const int grow = row_base + warp * 16 + it * 2 + (lane >> 4);
+                const float* base = n < total ? g.ln_res[st] : nullptr;
+                if (base != nullptr && grow < V) {
+                    const float4* rp = reinterpret_cast<const float4*>(base + ((size_t) b * max_pillars + grow) * kC);
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) stg_zero4(orow4 + k * 16 + sub);
-                    continue;
+                    for (int k = 0; k < 3; ++k) d[k] = ldg_stream4(rp + k * 16 + sub);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) d[k] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                float4 v[3];
+            };
 #pragma unroll
-                for (int k = 0; k < 3; ++k) v[k] = *reinterpret_cast<const float4*>(tile + (size_t) rloc * kLnStride + (k * 16 + sub) * 4);
+            for (int q = 0; q < 3; ++q) res_load(q, rq[q]);
+            float4 v[3];
+#pragma unroll 1
+            for (int n0 = 0; n0 < total; n0 += 3) {
 #pragma unroll
-                for (int st = 0; st < 3; ++st) {
-                    if (st >= g.n_ln) break;
-                    if (g.ln_res[st] != nullptr) {
-                        const float4* rp = reinterpret_cast<const float4*>(g.ln_res[st] + ((size_t) b * max_pillars + grow) * kC);
+                for (int q = 0; q < 3; ++q) {
+                    const int n = n0 + q;
+                    if (n >= total) break;
+                    const int it = n / n_ln, st = n - it * n_ln;
+                    const int rloc = warp * 16 + it * 2 + (lane >> 4), grow = row_base + rloc;
+                    if (st == 0) {
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            const float4 r = ldg_stream4(rp + k * 16 + sub);
-                            v[k].x += r.x; v[k].y += r.y; v[k].z += r.z; v[k].w += r.w;
-                        }
+                        for (int k = 0; k < 3; ++k) v[k] = *reinterpret_cast<const float4*>(tile + (size_t) rloc * kLnStride + (k * 16 + sub) * 4);
                     }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { v[k].x += rq[q][k].x; v[k].y += rq[q][k].y; v[k].z += rq[q][k].z; v[k].w += rq[q][k].w; }
+                    res_load(n + 3, rq[q]);
                     float sum = 0.f;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
 #pragma unroll
                     for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(hmask, sum, o);
                     const float mean = sum / 192.f;
-                    float q = 0.f;
+                    float qs = 0.f;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
                         const float a = v[k].x - mean, c = v[k].y - mean, d = v[k].z - mean, e = v[k].w - mean;
-                        q += (a * a + c * c) + (d * d + e * e);
+                        qs += (a * a + c * c) + (d * d + e * e);
                     }
 #pragma unroll
-                    for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(hmask, q, o);
-                    const float sd = sqrtf(q / 192.f + g.ln_eps);
+                    for (int o = 8; o > 0; o >>= 1) qs += __shfl_xor_sync(hmask, qs, o);
+                    const float sd = sqrtf(qs / 192.f + g.ln_eps);
                     const float4* gp = reinterpret_cast<const float4*>(g.ln_gamma[st]);
                     const float4* bp = reinterpret_cast<const float4*>(g.ln_beta[st]);
 #pragma unroll
@@ -412,9 +431,18 @@ proj_tile_kernel(const __grid_constant__ GemmRoles roles, const int* __restrict_
                         v[k].z = (v[k].z - mean) / sd * ga.z + be.z;
                         v[k].w = (v[k].w - mean) / sd * ga.w + be.w;
                     }
-                }
+                    if (st == n_ln - 1) {
+                        float4* orow4 = reinterpret_cast<float4*>(out + (size_t) grow * g.ld_out);
+                        if (grow < V) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) stg_stream4(orow4 + k * 16 + sub, v[k]);
+                            for (int k = 0; k < 3; ++k) stg_stream4(orow4 + k * 16 + sub, v[k]);
+                        } else if (zero_tails && grow < max_pillars) {
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) stg_zero4(orow4 + k * 16 + sub);
+                        }
+                        if (tid == 0 && it == 3) TP(11);
+                    }
+                }
             }
         } else {
         float4* scr = reinterpret_cast<float4*>(smem + warp * kEpiScratch);
@@ -512,6 +540,10 @@ proj_tile_kernel(const __grid_constant__ GemmRoles roles, const int* __restrict_
                 l2_prefetch(a0 + (size_t) row_base * kC, bytes);
                 if (a1) l2_prefetch(a1 + (size_t) row_base * kC, bytes);
             }
+            // residual rows of the LayerNorm-chain epilogue: in L2 by the time the accumulators are complete
+            for (int st = 0; st < g.n_ln; ++st)
+                if (g.ln_res[st] != nullptr)
+                    l2_prefetch(g.ln_res[st] + ((size_t) b * max_pillars + row_base) * kC, (uint32_t) (nrows * kC * sizeof(float)));
 #pragma unroll 1
             for (int kc = 0; kc < g.kchunks; ++kc) {
                 const int ws = kc % kTWStages;

@@ -10,7 +10,7 @@ pkg = importlib.import_module("dsvt-ai-trt_b200"); capi = importlib.import_modul
 pipeline = importlib.import_module("dsvt-ai-trt_b200.pipeline")
 cfg = pkg.config.WAYMO
 w = pipeline.FrameWeights(cfg, seed=0)
-f = pipeline.HotPathFrame(cfg, w, precision=capi.DSVT_ATTN_FP32_TC, ffn="fused", backbone=True)
+f = pipeline.HotPathFrame(cfg, w, precision=capi.DSVT_ATTN_FP32_TC, ffn="epilogue", backbone=True)
 f.load_points(pkg.synth.ring_lidar(200000, seed=0))
 f.run(); f.run(); torch.cuda.synchronize()
 V = f.vox.pillar_num
@@ -30,6 +30,16 @@ def show(title, fn):
     print(title)
     for i in sorted(lab, key=lambda i: t[i]):
         print(f"  {lab[i]:34s} t={t[i]-t[0]:7d}")
-show("pos-embed linear 2 (192->192, cold L2):", lambda: second.rows(f.pos_hidden, V, out=f.pos_out[0][0], zero_tails=0))
+x = f.blk_out[0]
+gs = f.gs[0]
+plan = f.plans[(0, 0)]
+ln = [(x, w.gamma[1], w.beta[1])]
+attn = lambda stages: capi.set_attention_fused(
+    w.attn[0], x, f.pos_out[0][0], gs.global_index_in_set[0], gs.mask_expand_0[0], gs.set_num, V, axis=0, out=f.src_b,
+    precision=f.precision, workspace=f.attn_ws, plan=plan, norm=(x, w.gamma[0], w.beta[0], cfg.layer_norm_eps), stages=stages)
+show("plain linear 192->192 (the pos-embed MLP's second layer, A read from memory; cold L2):", lambda: second.rows(f.pos_hidden, V, out=f.pos_out[0][0], zero_tails=0))
+show("QKV projection GEMM, role q (A = x + pos):", lambda: attn(1))
+attn(2); torch.cuda.synchronize()
+show("out-projection + norm1 (LayerNorm epilogue):", lambda: attn(4))
 show("FFN linear 1 + GELU (192->384):", lambda: fc1.rows(f.src, V, activation=1, out=f.gelu_out, zero_tails=0))
-show("FFN linear 2 split-K (+ residual):", lambda: fc2.rows_splitk(f.gelu_out, V, add=f.src, out=f.ffn_parts))
+show("FFN linear 2 (K = 384) + norm2 (LayerNorm epilogue):", lambda: fc2.rows_norm(f.gelu_out, V, ln, cfg.layer_norm_eps, out=f.src_b))
