@@ -100,7 +100,8 @@ struct GemmRole {
     // LayerNorm-chain epilogue (tile kernel only, N == 192, no plan): the finished row y0 = acc * out_mul + bias goes through
     //   y = LN_s(y + ln_res[s]) for s < n_ln  (the addElementWise(kSUM) + LayerNormPlugin pairs that follow the attention's
     //   out-projection and the FFN's second linear in the reference graph, src/dsvt-ai-trt.cpp:669-697, :750-756) before it
-    //   is stored -- the intermediate tensors never reach memory.  Arithmetic per stage = layer_norm192_kernel (rowwise.cu).
+    //   is stored -- the intermediate tensors never reach memory.  Arithmetic per stage = layer_norm192_kernel (rowwise.cu)
+    //   except that the quotient by the standard deviation is a reciprocal-multiply (<= 1 ulp per element).
     int n_ln;
     const float* ln_res[3];     // [rows, 192] each, or nullptr
     const float* ln_gamma[3];
@@ -165,7 +166,10 @@ __device__ long long g_split_prof[64];
 // overlap the other's epilogue.  L2->SM traffic per tile rises from 96-192 KB (rows) to 243-339 KB (rows + weights).
 // Operand images, MMA sequence and epilogue arithmetic are unchanged from round 1: results are bit-identical.
 constexpr int kLnStride = 196;                        // floats per row of the LayerNorm tile: 49 x 16 B, conflict-free row writes
-constexpr int kTStages = 2;                           // converted A chunks
+#ifndef DSVT_TSTAGES
+#define DSVT_TSTAGES 2
+#endif
+constexpr int kTStages = DSVT_TSTAGES;                // converted A chunks
 constexpr int kTWStages = 2;                          // weight chunks (a third stage and per-row L2 prefetches of every operand
                                                       // were measured: slower -- the memory system, not latency, is the limit)
 constexpr int kTWorkers = 256;                        // warps 0-7: A producers, then the epilogue
@@ -213,9 +217,14 @@ proj_tile_kernel(const __grid_constant__ GemmRoles roles, const int* __restrict_
     const float* a1 = g.a1 ? g.a1 + (size_t) b * max_pillars * g.lda : nullptr;
     const float* a0b = g.a0b ? g.a0b + (size_t) b * max_pillars * g.ldb : nullptr;
     if (tid == 0) TP(0);
+#ifdef DSVT_EXP_IMG        // experiment: the A operand arrives as ready-made 16 KB chunk images (bulk copies of the same bytes)
+    const bool a_img = !g.gen_x && !g.a0b;
+#else
+    const bool a_img = false;
+#endif
 
     if (tid == 0) {
-        for (int s = 0; s < kTStages; ++s) { mbar_init(&a_full[s], kTWorkers); mbar_init(&s_empty[s], 1); }
+        for (int s = 0; s < kTStages; ++s) { mbar_init(&a_full[s], a_img ? 1 : kTWorkers); mbar_init(&s_empty[s], 1); }
         for (int s = 0; s < kTWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
         mbar_init(&acc_full, 1);
         fence_barrier_init();
@@ -259,7 +268,14 @@ proj_tile_kernel(const __grid_constant__ GemmRoles roles, const int* __restrict_
                     d[e] = fmaxf(acc, 0.f);
                     d[8 + e] = 0.f;
                 }
-            } else if (row < V) {
+            }
+#ifdef DSVT_EXP_NOA       // experiment: the A operand is not read (wrong results; what the row loads cost)
+            else if (row < V) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) d[e] = 1.f;
+            }
+#endif
+            else if (row < V) {
                 const int col = kc * kBK + c16 * 8;
                 if (a0b && col >= g.ksplit) ldg256(a0b + (size_t) row * g.ldb + (col - g.ksplit), &d[0]);
                 else ldg256(a0 + (size_t) row * g.lda + col, &d[0]);
@@ -273,10 +289,12 @@ proj_tile_kernel(const __grid_constant__ GemmRoles roles, const int* __restrict_
                 for (int e = 0; e < 16; ++e) d[e] = 0.f;
             }
         };
+        if (!a_img) {
 #pragma unroll
         for (int s = 0; s < kDepth - 1; ++s) issue(s, buf[s]);
+        }
 #pragma unroll 1
-        for (int s0 = 0; s0 < n_steps; s0 += kUnroll) {
+        for (int s0 = 0; s0 < (a_img ? 0 : n_steps); s0 += kUnroll) {
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
                 const int s = s0 + u;
@@ -420,16 +438,18 @@ proj_tile_kernel(const __grid_constant__ GemmRoles roles, const int* __restrict_
                     }
 #pragma unroll
                     for (int o = 8; o > 0; o >>= 1) qs += __shfl_xor_sync(hmask, qs, o);
-                    const float sd = sqrtf(qs / 192.f + g.ln_eps);
+                    // (v - mean) / sd as (v - mean) * (1 / sd): <= 1 ulp per element from layer_norm192_kernel's quotient, 11 IEEE
+                    // divisions per lane and stage less (the pass is bound by instruction issue, not by memory)
+                    const float inv_sd = 1.0f / sqrtf(qs / 192.f + g.ln_eps);
                     const float4* gp = reinterpret_cast<const float4*>(g.ln_gamma[st]);
                     const float4* bp = reinterpret_cast<const float4*>(g.ln_beta[st]);
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
                         const float4 ga = __ldg(gp + k * 16 + sub), be = __ldg(bp + k * 16 + sub);
-                        v[k].x = (v[k].x - mean) / sd * ga.x + be.x;
-                        v[k].y = (v[k].y - mean) / sd * ga.y + be.y;
-                        v[k].z = (v[k].z - mean) / sd * ga.z + be.z;
-                        v[k].w = (v[k].w - mean) / sd * ga.w + be.w;
+                        v[k].x = (v[k].x - mean) * inv_sd * ga.x + be.x;
+                        v[k].y = (v[k].y - mean) * inv_sd * ga.y + be.y;
+                        v[k].z = (v[k].z - mean) * inv_sd * ga.z + be.z;
+                        v[k].w = (v[k].w - mean) * inv_sd * ga.w + be.w;
                     }
                     if (st == n_ln - 1) {
                         float4* orow4 = reinterpret_cast<float4*>(out + (size_t) grow * g.ld_out);
@@ -535,6 +555,7 @@ proj_tile_kernel(const __grid_constant__ GemmRoles roles, const int* __restrict_
         // =========================== WEIGHT-CHUNK COPIES =================================================
         const int nrows = V - row_base < kBM ? V - row_base : kBM;
         if (lane == 0) {
+            const uint64_t w_policy = l2_policy_evict_last();
             if (g.lda == kC && !g.gen_x) {   // the tile's rows are one contiguous block: pull them into L2 as large sequential requests
                 const uint32_t bytes = (uint32_t) (nrows * kC * sizeof(float));
                 l2_prefetch(a0 + (size_t) row_base * kC, bytes);
@@ -548,8 +569,28 @@ proj_tile_kernel(const __grid_constant__ GemmRoles roles, const int* __restrict_
             for (int kc = 0; kc < g.kchunks; ++kc) {
                 const int ws = kc % kTWStages;
                 if (kc >= kTWStages) mbar_wait(&w_empty[ws], ((kc / kTWStages) - 1) & 1);
+#ifdef DSVT_EXP_NOW       // experiment: weight chunks are not streamed (wrong results; what the W stream costs)
+                if (kc >= kTWStages) { mbar_arrive(&w_full[ws]); continue; }
+#endif
+#ifdef DSVT_EXP_NOW2      // experiment: no weight chunk is copied at all (what the FIRST chunk's arrival costs)
+                if (a_img) {
+                    const int st = kc % kTStages;
+                    if (kc >= kTStages) mbar_wait(&s_empty[st], ((kc / kTStages) - 1) & 1);
+                    mbar_arrive_expect_tx(&a_full[st], L::a_stage);
+                    bulk_g2s(smem + st * L::a_stage, reinterpret_cast<const uint8_t*>(a0) + ((size_t) tile * g.kchunks + kc) * L::a_stage,
+                             L::a_stage, &a_full[st]);
+                }
+                mbar_arrive(&w_full[ws]); continue;
+#endif
+                if (a_img) {
+                    const int st = kc % kTStages;
+                    if (kc >= kTStages) mbar_wait(&s_empty[st], ((kc / kTStages) - 1) & 1);
+                    mbar_arrive_expect_tx(&a_full[st], L::a_stage);
+                    bulk_g2s(smem + st * L::a_stage, reinterpret_cast<const uint8_t*>(a0) + ((size_t) tile * g.kchunks + kc) * L::a_stage,
+                             L::a_stage, &a_full[st]);
+                }
                 mbar_arrive_expect_tx(&w_full[ws], L::w_stage);
-                bulk_g2s(smem + L::w + ws * L::w_stage, g.wimg + (size_t) kc * kWChunkBytes, L::w_stage, &w_full[ws]);
+                bulk_g2s_hint(smem + L::w + ws * L::w_stage, g.wimg + (size_t) kc * kWChunkBytes, L::w_stage, &w_full[ws], w_policy);
             }
         }
         __syncwarp();

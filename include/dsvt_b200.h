@@ -301,7 +301,8 @@ int dsvt_set_attention_fused_planned_launch(const dsvt_set_attention_params* p, 
  * addElementWise(kSUM) + LayerNormPlugin) -- the LayerNorm runs in the out-projection's epilogue, the attention output
  * itself never reaches memory (GEMM-pipeline precisions; the single-kernel precisions run attention + the row-wise LayerNorm
  * kernel in place, same results, one more launch).  plan may be NULL (rebuilt per call).  residual
- * [B,max_pillars_num,C], gamma / beta [C] on the device.  Arithmetic of the LayerNorm = dsvt_layer_norm_launch.
+ * [B,max_pillars_num,C], gamma / beta [C] on the device.  Arithmetic of the LayerNorm = dsvt_layer_norm_launch up to
+ * the quotient by the standard deviation, which the epilogue evaluates as a reciprocal-multiply (<= 1 ulp per element).
  */
 int dsvt_set_attention_fused_norm_launch(const dsvt_set_attention_params* p, const dsvt_attention_weights* w,
                                          const float* x, const float* pos, const int32_t* global_index_in_set,

@@ -191,6 +191,6 @@ def test_linear_rows_norm(K, n_ln, rows):
         mu = y.mean(1, keepdims=True)
         y = (y - mu) / np.sqrt(((y - mu) ** 2).mean(1, keepdims=True)) * g_.cpu().numpy() + b_.cpu().numpy()
     assert np.abs(got[:rows] - y).max() <= 5e-5
-    if K == 192:      # against the separate launches: linear, then the LayerNorm chain kernel (identical arithmetic per stage)
-        two = capi.layer_norm_chain(lin.rows(dx, n), n, stages, 0.0)
-        assert torch.equal(out, two)
+    if K == 192:      # against the separate launches: linear, then the LayerNorm chain kernel (same arithmetic per stage up to
+        two = capi.layer_norm_chain(lin.rows(dx, n), n, stages, 0.0)       # the epilogue's reciprocal-multiply: a few ulp)
+        assert (out - two).abs().max().item() <= 2e-6

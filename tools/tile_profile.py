@@ -16,13 +16,13 @@ f.run(); f.run(); torch.cuda.synchronize()
 V = f.vox.pillar_num
 fc1, fc2 = w.ffn[0]
 first, second = w.glue["pos"][0][0]
-flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda"); flush_r = torch.zeros(64 << 20, dtype=torch.int32, device="cuda")
 lab = {0: "start", 1: "setup done (barriers, TMEM)", 8: "producer: all chunks staged", 9: "accumulators complete", 10: "slab 0 stored",
        11: "slab 1 stored", 12: "slab 2 stored", 13: "CTA end"}
 for kc in range(6):
     lab[2 + kc] = f"producer: chunk {kc} staged"; lab[14 + kc] = f"issuer: W chunk {kc} landed"; lab[20 + kc] = f"issuer: A chunk {kc} full"
 def show(title, fn):
-    flush.zero_(); torch.cuda.synchronize()
+    flush.zero_(); flush_r.max(); torch.cuda.synchronize()
     fn(); torch.cuda.synchronize()
     buf = (ctypes.c_longlong * 64)()
     capi._lib().dsvt_debug_split_profile(buf)
