@@ -186,6 +186,123 @@ template <bool SPLIT> struct TLay {
     static constexpr int total = plain > ln_tile ? plain : ln_tile;                                  // ... and so does the LayerNorm tile
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// LayerNorm-chain epilogue of a 128 x 192 accumulator tile (shared by the tile GEMM and the fused FFN kernel): the eight
+// epilogue warps (TMEM lane quarter = warp & 3, column half = warp >> 2) turn the accumulators at `tmem_acc` into
+//   y = LN_s(y + ln_res[s]) for s < n_ln,  y0 = acc * out_mul + bias
+// and store the rows once.  `tile` = 128 x kLnStride floats of shared memory that no asynchronous operation still touches.
+__device__ __forceinline__ void ln_chain_epilogue(const GemmRole& g, float* tile, uint32_t tmem_acc, int warp, int lane, int tid,
+                                                  int row_base, int V, int b, int max_pillars, float* out, int zero_tails)
+{
+    const int q4 = warp & 3, hf = warp >> 2;
+    const uint32_t tlane = tmem_acc + ((uint32_t) (q4 * 32) << 16) + hf * 96;
+    const int row0 = row_base + q4 * 32;
+    {
+        // ---- pass A, TMEM -> finished FP32 rows in shared memory (lane = row) ---------------------------------------
+        {
+            float* trow = tile + (size_t) (q4 * 32 + lane) * kLnStride + hf * 96;
+            const int grow = row0 + lane;
+            const bool is_dead = g.cover && grow < V && __ldg(g.cover + (size_t) b * g.cover_stride + grow) < 0;
+#pragma unroll 1
+            for (int j0 = 0; j0 < 96; j0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(tlane + j0, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + hf * 96 + j0 + 4 * j));
+                    float4 y = make_float4(__uint_as_float(r[4 * j]) * g.out_mul + bb.x, __uint_as_float(r[4 * j + 1]) * g.out_mul + bb.y,
+                                           __uint_as_float(r[4 * j + 2]) * g.out_mul + bb.z, __uint_as_float(r[4 * j + 3]) * g.out_mul + bb.w);
+                    if (is_dead) y = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(trow + j0 + 4 * j) = y;
+                }
+            }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight epilogue warps
+        if (tid == 0) TP(10);
+        // ---- pass B: half a warp per row, the chain of layer_norm192_chain_kernel (rowwise.cu) on the staged rows ---
+        const int sub = lane & 15;
+        const unsigned hmask = 0xFFFFu << (lane & 16);
+        // The work of a half-warp is the list of entries n = (row it, stage st), st fastest.  The residual pieces of entries
+        // n + 1 .. n + 3 are in flight while entry n is computed (a rotating queue of three register slots, refilled as soon
+        // as a slot is consumed): one row of lead for a 3-stage chain, three rows for norm1 alone.  Issued at their place in
+        // program order, the loads put 8 x n_ln dependent memory round trips on the epilogue (27 k of a CTA's 47 k cycles).
+        float4 rq[3][3];
+        const int n_ln = g.n_ln, total = 8 * n_ln;
+        auto res_load = [&](int n, float4 (&d)[3]) {
+            const int it = n / n_ln, st = n - it * n_ln;
+            const int grow = row_base + warp * 16 + it * 2 + (lane >> 4);
+            const float* base = n < total ? g.ln_res[st] : nullptr;
+            if (base != nullptr && grow < V) {
+                const float4* rp = reinterpret_cast<const float4*>(base + ((size_t) b * max_pillars + grow) * kC);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) d[k] = ldg_stream4(rp + k * 16 + sub);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) d[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+#pragma unroll
+        for (int q = 0; q < 3; ++q) res_load(q, rq[q]);
+        float4 v[3];
+#pragma unroll 1
+        for (int n0 = 0; n0 < total; n0 += 3) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int n = n0 + q;
+                if (n >= total) break;
+                const int it = n / n_ln, st = n - it * n_ln;
+                const int rloc = warp * 16 + it * 2 + (lane >> 4), grow = row_base + rloc;
+                if (st == 0) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) v[k] = *reinterpret_cast<const float4*>(tile + (size_t) rloc * kLnStride + (k * 16 + sub) * 4);
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { v[k].x += rq[q][k].x; v[k].y += rq[q][k].y; v[k].z += rq[q][k].z; v[k].w += rq[q][k].w; }
+                res_load(n + 3, rq[q]);
+                float sum = 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(hmask, sum, o);
+                const float mean = sum / 192.f;
+                float qs = 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float a = v[k].x - mean, c = v[k].y - mean, d = v[k].z - mean, e = v[k].w - mean;
+                    qs += (a * a + c * c) + (d * d + e * e);
+                }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) qs += __shfl_xor_sync(hmask, qs, o);
+                // (v - mean) / sd as (v - mean) * (1 / sd): <= 1 ulp per element from layer_norm192_kernel's quotient, 11 IEEE
+                // divisions per lane and stage less (the pass is bound by instruction issue, not by memory)
+                const float inv_sd = 1.0f / sqrtf(qs / 192.f + g.ln_eps);
+                const float4* gp = reinterpret_cast<const float4*>(g.ln_gamma[st]);
+                const float4* bp = reinterpret_cast<const float4*>(g.ln_beta[st]);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float4 ga = __ldg(gp + k * 16 + sub), be = __ldg(bp + k * 16 + sub);
+                    v[k].x = (v[k].x - mean) * inv_sd * ga.x + be.x;
+                    v[k].y = (v[k].y - mean) * inv_sd * ga.y + be.y;
+                    v[k].z = (v[k].z - mean) * inv_sd * ga.z + be.z;
+                    v[k].w = (v[k].w - mean) * inv_sd * ga.w + be.w;
+                }
+                if (st == n_ln - 1) {
+                    float4* orow4 = reinterpret_cast<float4*>(out + (size_t) grow * g.ld_out);
+                    if (grow < V) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) stg_stream4(orow4 + k * 16 + sub, v[k]);
+                    } else if (zero_tails && grow < max_pillars) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) stg_zero4(orow4 + k * 16 + sub);
+                    }
+                    if (tid == 0 && it == 3) TP(11);
+                }
+            }
+        }
+    }
+}
+
 template <bool SPLIT>
 __global__ void __launch_bounds__(kTThreads, 2)
 proj_tile_kernel(const __grid_constant__ GemmRoles roles, const int* __restrict__ voxel_num, int rows_host, int max_pillars,
@@ -358,112 +475,7 @@ proj_tile_kernel(const __grid_constant__ GemmRoles roles, const int* __restrict_
         tc_fence_after_sync();
         if (tid == 0) TP(9);
         if (g.n_ln > 0) {
-            // ---- LayerNorm-chain epilogue: pass A, TMEM -> finished FP32 rows in shared memory (lane = row) ----------
-            float* tile = reinterpret_cast<float*>(smem);
-            {
-                float* trow = tile + (size_t) (q4 * 32 + lane) * kLnStride + hf * 96;
-                const int grow = row0 + lane;
-                const bool is_dead = g.cover && grow < V && __ldg(g.cover + (size_t) b * g.cover_stride + grow) < 0;
-#pragma unroll 1
-                for (int j0 = 0; j0 < 96; j0 += 16) {
-                    uint32_t r[16];
-                    tmem_ld16(tlane + j0, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + hf * 96 + j0 + 4 * j));
-                        float4 y = make_float4(__uint_as_float(r[4 * j]) * g.out_mul + bb.x, __uint_as_float(r[4 * j + 1]) * g.out_mul + bb.y,
-                                               __uint_as_float(r[4 * j + 2]) * g.out_mul + bb.z, __uint_as_float(r[4 * j + 3]) * g.out_mul + bb.w);
-                        if (is_dead) y = make_float4(0.f, 0.f, 0.f, 0.f);
-                        *reinterpret_cast<float4*>(trow + j0 + 4 * j) = y;
-                    }
-                }
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight epilogue warps
-            if (tid == 0) TP(10);
-            // ---- pass B: half a warp per row, the chain of layer_norm192_chain_kernel (rowwise.cu) on the staged rows ---
-            // The residual rows of iteration it + 1 (every stage) are loaded while iteration it is computed: issued in program
-            // order behind each stage, they put 8 x n_ln dependent memory round trips on the epilogue (27 k of a CTA's 47 k cycles,
-            // profiles/r2_tile_profile.txt).
-            const int sub = lane & 15;
-            const unsigned hmask = 0xFFFFu << (lane & 16);
-            // The work of a half-warp is the list of entries n = (row it, stage st), st fastest.  The residual pieces of entries
-            // n + 1 .. n + 3 are in flight while entry n is computed (a rotating queue of three register slots, refilled as soon
-            // as a slot is consumed): one row of lead for a 3-stage chain, three rows for norm1 alone.  Issued at their place in
-            // program order, the loads put 8 x n_ln dependent memory round trips on the epilogue (27 k of a CTA's 47 k cycles).
-            float4 rq[3][3];
-            const int n_ln = g.n_ln, total = 8 * n_ln;
-            auto res_load = [&](int n, float4 (&d)[3]) {
-                const int it = n / n_ln, st = n - it * n_ln;
-                const int grow = row_base + warp * 16 + it * 2 + (lane >> 4);
-                const float* base = n < total ? g.ln_res[st] : nullptr;
-                if (base != nullptr && grow < V) {
-                    const float4* rp = reinterpret_cast<const float4*>(base + ((size_t) b * max_pillars + grow) * kC);
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) d[k] = ldg_stream4(rp + k * 16 + sub);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) d[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            };
-#pragma unroll
-            for (int q = 0; q < 3; ++q) res_load(q, rq[q]);
-            float4 v[3];
-#pragma unroll 1
-            for (int n0 = 0; n0 < total; n0 += 3) {
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    const int n = n0 + q;
-                    if (n >= total) break;
-                    const int it = n / n_ln, st = n - it * n_ln;
-                    const int rloc = warp * 16 + it * 2 + (lane >> 4), grow = row_base + rloc;
-                    if (st == 0) {
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) v[k] = *reinterpret_cast<const float4*>(tile + (size_t) rloc * kLnStride + (k * 16 + sub) * 4);
-                    }
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) { v[k].x += rq[q][k].x; v[k].y += rq[q][k].y; v[k].z += rq[q][k].z; v[k].w += rq[q][k].w; }
-                    res_load(n + 3, rq[q]);
-                    float sum = 0.f;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
-#pragma unroll
-                    for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(hmask, sum, o);
-                    const float mean = sum / 192.f;
-                    float qs = 0.f;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const float a = v[k].x - mean, c = v[k].y - mean, d = v[k].z - mean, e = v[k].w - mean;
-                        qs += (a * a + c * c) + (d * d + e * e);
-                    }
-#pragma unroll
-                    for (int o = 8; o > 0; o >>= 1) qs += __shfl_xor_sync(hmask, qs, o);
-                    // (v - mean) / sd as (v - mean) * (1 / sd): <= 1 ulp per element from layer_norm192_kernel's quotient, 11 IEEE
-                    // divisions per lane and stage less (the pass is bound by instruction issue, not by memory)
-                    const float inv_sd = 1.0f / sqrtf(qs / 192.f + g.ln_eps);
-                    const float4* gp = reinterpret_cast<const float4*>(g.ln_gamma[st]);
-                    const float4* bp = reinterpret_cast<const float4*>(g.ln_beta[st]);
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const float4 ga = __ldg(gp + k * 16 + sub), be = __ldg(bp + k * 16 + sub);
-                        v[k].x = (v[k].x - mean) * inv_sd * ga.x + be.x;
-                        v[k].y = (v[k].y - mean) * inv_sd * ga.y + be.y;
-                        v[k].z = (v[k].z - mean) * inv_sd * ga.z + be.z;
-                        v[k].w = (v[k].w - mean) * inv_sd * ga.w + be.w;
-                    }
-                    if (st == n_ln - 1) {
-                        float4* orow4 = reinterpret_cast<float4*>(out + (size_t) grow * g.ld_out);
-                        if (grow < V) {
-#pragma unroll
-                            for (int k = 0; k < 3; ++k) stg_stream4(orow4 + k * 16 + sub, v[k]);
-                        } else if (zero_tails && grow < max_pillars) {
-#pragma unroll
-                            for (int k = 0; k < 3; ++k) stg_zero4(orow4 + k * 16 + sub);
-                        }
-                        if (tid == 0 && it == 3) TP(11);
-                    }
-                }
-            }
+            ln_chain_epilogue(g, reinterpret_cast<float*>(smem), tmem, warp, lane, tid, row_base, V, b, max_pillars, out, zero_tails);
         } else {
         float4* scr = reinterpret_cast<float4*>(smem + warp * kEpiScratch);
 #pragma unroll 1
@@ -985,7 +997,6 @@ int linear_split_launch(const void* blob, int N, int K, float out_mul, bool spli
             for (int r = 0; r < 3; ++r) {
                 const int i = i0 + (r < n_roles ? r : 0);
                 GemmRole& g = roles.r[r];
-        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f; g.gen_x = nullptr; g.gen_blob = nullptr;
                 g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f; g.gen_x = nullptr; g.gen_blob = nullptr;
                 g.a0 = x + (size_t) j * kC; g.a1 = nullptr; g.lda = x_hi ? k_split : K;
                 g.a0b = x_hi; g.ksplit = x_hi ? k_split : 0; g.ldb = x_hi ? K - k_split : 0;
