@@ -455,6 +455,21 @@ class Linear:
                "dsvt_linear_rows_splitk_launch")
         return out
 
+    def ffn_norm(self, second, x, rows, stages, eps=0.0, out=None, zero_tails=1):
+        """self = Linear(192 -> 384), second = Linear(384 -> 192): gelu(x W1^T + b1) W2^T + b2 followed by the chain of
+        (residual add + LayerNorm) stages, in ONE kernel (dsvt_ffn_fused_launch); x [max_rows, 192] -> [max_rows, 192]."""
+        _need(x, torch.float32, "x")
+        _need(rows, torch.int32, "rows")
+        max_rows = x.shape[0]
+        out = torch.empty(max_rows, second.N, dtype=torch.float32, device=x.device) if out is None else out
+        arr = (LnStage * len(stages))()
+        for i, (r, g, b) in enumerate(stages):
+            arr[i] = LnStage(r.data_ptr() if r is not None else None, g.data_ptr(), b.data_ptr())
+        _check(_lib().dsvt_ffn_fused_launch(c_void_p(self.handle), c_void_p(second.handle), _ptr(x), _ptr(rows), c_int32(max_rows),
+                                            arr, c_int32(len(stages)), c_float(eps), _ptr(out), c_int32(zero_tails), _stream()),
+               "dsvt_ffn_fused_launch")
+        return out
+
     def rows_norm(self, x, rows, stages, eps=0.0, out=None, zero_tails=1):
         """Linear (N == 192, K in {192, 384}) + a chain of (residual add + LayerNorm) stages in one kernel:
         stages = [(residual_or_None, gamma, beta), ...] (<= 3).  x [max_rows, K] -> [max_rows, 192]."""

@@ -191,26 +191,31 @@ template <bool SPLIT> struct TLay {
 // epilogue warps (TMEM lane quarter = warp & 3, column half = warp >> 2) turn the accumulators at `tmem_acc` into
 //   y = LN_s(y + ln_res[s]) for s < n_ln,  y0 = acc * out_mul + bias
 // and store the rows once.  `tile` = 128 x kLnStride floats of shared memory that no asynchronous operation still touches.
+template <int NW>
 __device__ __forceinline__ void ln_chain_epilogue(const GemmRole& g, float* tile, uint32_t tmem_acc, int warp, int lane, int tid,
                                                   int row_base, int V, int b, int max_pillars, float* out, int zero_tails)
 {
+    static_assert(NW == 8 || NW == 16, "epilogue warps");
+    constexpr int kCols = kBN / (NW / 4);          // accumulator columns per warp in pass A: 96 / 48
+    constexpr int kRowsW = kBM / NW;               // rows per warp in pass B: 16 / 8
+    constexpr int kIters = kRowsW / 2;             // two rows (half-warps) per iteration
     const int q4 = warp & 3, hf = warp >> 2;
-    const uint32_t tlane = tmem_acc + ((uint32_t) (q4 * 32) << 16) + hf * 96;
+    const uint32_t tlane = tmem_acc + ((uint32_t) (q4 * 32) << 16) + hf * kCols;
     const int row0 = row_base + q4 * 32;
     {
         // ---- pass A, TMEM -> finished FP32 rows in shared memory (lane = row) ---------------------------------------
         {
-            float* trow = tile + (size_t) (q4 * 32 + lane) * kLnStride + hf * 96;
+            float* trow = tile + (size_t) (q4 * 32 + lane) * kLnStride + hf * kCols;
             const int grow = row0 + lane;
             const bool is_dead = g.cover && grow < V && __ldg(g.cover + (size_t) b * g.cover_stride + grow) < 0;
 #pragma unroll 1
-            for (int j0 = 0; j0 < 96; j0 += 16) {
+            for (int j0 = 0; j0 < kCols; j0 += 16) {
                 uint32_t r[16];
                 tmem_ld16(tlane + j0, r);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + hf * 96 + j0 + 4 * j));
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + hf * kCols + j0 + 4 * j));
                     float4 y = make_float4(__uint_as_float(r[4 * j]) * g.out_mul + bb.x, __uint_as_float(r[4 * j + 1]) * g.out_mul + bb.y,
                                            __uint_as_float(r[4 * j + 2]) * g.out_mul + bb.z, __uint_as_float(r[4 * j + 3]) * g.out_mul + bb.w);
                     if (is_dead) y = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -218,7 +223,7 @@ __device__ __forceinline__ void ln_chain_epilogue(const GemmRole& g, float* tile
                 }
             }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight epilogue warps
+        asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");          // the epilogue warps
         if (tid == 0) TP(10);
         // ---- pass B: half a warp per row, the chain of layer_norm192_chain_kernel (rowwise.cu) on the staged rows ---
         const int sub = lane & 15;
@@ -228,10 +233,10 @@ __device__ __forceinline__ void ln_chain_epilogue(const GemmRole& g, float* tile
         // as a slot is consumed): one row of lead for a 3-stage chain, three rows for norm1 alone.  Issued at their place in
         // program order, the loads put 8 x n_ln dependent memory round trips on the epilogue (27 k of a CTA's 47 k cycles).
         float4 rq[3][3];
-        const int n_ln = g.n_ln, total = 8 * n_ln;
+        const int n_ln = g.n_ln, total = kIters * n_ln;
         auto res_load = [&](int n, float4 (&d)[3]) {
             const int it = n / n_ln, st = n - it * n_ln;
-            const int grow = row_base + warp * 16 + it * 2 + (lane >> 4);
+            const int grow = row_base + warp * kRowsW + it * 2 + (lane >> 4);
             const float* base = n < total ? g.ln_res[st] : nullptr;
             if (base != nullptr && grow < V) {
                 const float4* rp = reinterpret_cast<const float4*>(base + ((size_t) b * max_pillars + grow) * kC);
@@ -252,7 +257,7 @@ __device__ __forceinline__ void ln_chain_epilogue(const GemmRole& g, float* tile
                 const int n = n0 + q;
                 if (n >= total) break;
                 const int it = n / n_ln, st = n - it * n_ln;
-                const int rloc = warp * 16 + it * 2 + (lane >> 4), grow = row_base + rloc;
+                const int rloc = warp * kRowsW + it * 2 + (lane >> 4), grow = row_base + rloc;
                 if (st == 0) {
 #pragma unroll
                     for (int k = 0; k < 3; ++k) v[k] = *reinterpret_cast<const float4*>(tile + (size_t) rloc * kLnStride + (k * 16 + sub) * 4);
@@ -296,7 +301,7 @@ __device__ __forceinline__ void ln_chain_epilogue(const GemmRole& g, float* tile
 #pragma unroll
                         for (int k = 0; k < 3; ++k) stg_zero4(orow4 + k * 16 + sub);
                     }
-                    if (tid == 0 && it == 3) TP(11);
+                    if (tid == 0 && it == kIters / 2 - 1) TP(11);
                 }
             }
         }
@@ -475,7 +480,7 @@ proj_tile_kernel(const __grid_constant__ GemmRoles roles, const int* __restrict_
         tc_fence_after_sync();
         if (tid == 0) TP(9);
         if (g.n_ln > 0) {
-            ln_chain_epilogue(g, reinterpret_cast<float*>(smem), tmem, warp, lane, tid, row_base, V, b, max_pillars, out, zero_tails);
+            ln_chain_epilogue<8>(g, reinterpret_cast<float*>(smem), tmem, warp, lane, tid, row_base, V, b, max_pillars, out, zero_tails);
         } else {
         float4* scr = reinterpret_cast<float4*>(smem + warp * kEpiScratch);
 #pragma unroll 1
@@ -531,7 +536,7 @@ proj_tile_kernel(const __grid_constant__ GemmRoles roles, const int* __restrict_
         }
     } else if (warp == kTIssuerWarp) {
         // =========================== MMA ISSUE ===========================================================
-        if (lane == 0) {
+        if (lane == 0) {       // (the converged-warp issue of ffn_fused.cuh was measured here: no gain, six MMAs per wait)
             const uint32_t idesc = make_idesc(kFmtF16, kBM, kBN);
             const uint32_t sbase = smem_u32(smem);
 #pragma unroll 1
@@ -613,7 +618,8 @@ proj_tile_kernel(const __grid_constant__ GemmRoles roles, const int* __restrict_
     if (warp == kTIssuerWarp) tmem_dealloc<256>(tmem);
 }
 
-// ---------------------------------------------------------------------------------------------------------------
+#include "ffn_fused.cuh"
+
 // ---------------------------------------------------------------------------------------------------------------
 // Plan kernel 1: one warp per set.  Token compaction, same rule as attention_fp32.cu: a slot that repeats the previous
 // voxel AND is masked as a key by every head (getSet.cu:546-563) is the same token as its twin.
@@ -1094,6 +1100,67 @@ int linear_ln_launch(const void* blob, int K, float out_mul, bool split, const f
     }
     roles.r[1] = roles.r[2] = g;
     return launch_gemm(roles, 1, rows_dev, 0, max_rows, 1, zero_tails, 1, split, st);
+}
+
+// ---- fused FFN (ffn_fused.cuh) ------------------------------------------------------------------------------------
+// W1 [384, 192] as six pieces of 64 output columns: piece p = six K chunks of [hi 64x32 | lo 64x32] FP16 (8 KB each),
+// pre-scaled like the block images of linear_split_prepare (same shift, so out_mul is the layer's).
+void* ffn_w1_pieces_prepare(const float* W) {
+    const int sh = scale_shift(W, (size_t) 2 * kC * kC);
+    const float ws = ldexpf(1.0f, sh);
+    std::vector<uint8_t> host((size_t) kFPieces * kFW1Piece, 0);
+    for (int p = 0; p < kFPieces; ++p)
+        for (int kc = 0; kc < kNumK; ++kc) {
+            uint8_t* hi_img = host.data() + (size_t) p * kFW1Piece + (size_t) kc * kFW1Chunk;
+            uint8_t* lo_img = hi_img + kFW1Chunk / 2;
+            for (int n = 0; n < kFP; ++n)
+                for (int c16 = 0; c16 < kBK / 8; ++c16)
+                    for (int e = 0; e < 8; ++e) {
+                        const float w = W[(size_t) (p * kFP + n) * kC + kc * kBK + c16 * 8 + e] * ws;
+                        const __half h = __float2half_rn(w);
+                        const __half l = __float2half_rn(w - __half2float(h));
+                        const uint16_t hb = __half_as_ushort(h), lb = __half_as_ushort(l);
+                        const size_t off = (size_t) c16 * (kFP * 16) + (size_t) n * 16 + e * 2;
+                        memcpy(hi_img + off, &hb, 2);
+                        memcpy(lo_img + off, &lb, 2);
+                    }
+        }
+    void* dev = nullptr;
+    if (cudaMalloc(&dev, host.size()) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(dev, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(dev); return nullptr; }
+    return dev;
+}
+
+// blob1 / pieces1: the 192 -> 384 layer (its bias sits behind the two block images), blob2: the 384 -> 192 layer
+int ffn_fused_launch(const void* blob1, const void* pieces1, float out_mul1, const void* blob2, float out_mul2, const float* x,
+                     const int* rows_dev, int max_rows, int n_ln, const float* const* res, const float* const* gamma,
+                     const float* const* beta, float eps, float* y, int zero_tails, cudaStream_t st)
+{
+    const uint8_t* img2 = static_cast<const uint8_t*>(blob2);
+    FfnArgs a;
+    GemmRole& g = a.g;
+    g.a0 = x; g.a1 = nullptr; g.lda = kC;
+    g.a0b = nullptr; g.ksplit = 0; g.ldb = 0; g.cover = nullptr; g.cover_stride = 0;
+    g.wimg = img2;
+    g.bias = reinterpret_cast<const float*>(img2 + (size_t) 2 * kWRoleBytes);
+    g.out = y; g.ld_out = kC; g.col0 = 0;
+    g.out_mul = out_mul2; g.post_mul = 1.0f;
+    g.plan = nullptr; g.plan_stride = 0; g.pad_hi = 0;
+    g.accumulate = 0; g.act = 0; g.add_src = nullptr; g.ld_add = 0;
+    g.kchunks = 2 * kNumK; g.n_ln = n_ln; g.ln_eps = eps; g.gen_x = nullptr; g.gen_blob = nullptr;
+    for (int s = 0; s < 3; ++s) {
+        g.ln_res[s] = s < n_ln ? res[s] : nullptr;
+        g.ln_gamma[s] = s < n_ln ? gamma[s] : nullptr;
+        g.ln_beta[s] = s < n_ln ? beta[s] : nullptr;
+    }
+    a.w1_img = static_cast<const uint8_t*>(pieces1);
+    a.bias1 = reinterpret_cast<const float*>(static_cast<const uint8_t*>(blob1) + (size_t) 2 * kWRoleBytes);
+    a.out_mul1 = out_mul1;
+    DSVT_RAISE_SMEM(ffn_fused_kernel, kFSmemTotal);
+    const dim3 grid((max_rows + kBM - 1) / kBM, 1, 1);
+    ffn_fused_kernel<<<grid, kFThreads, kFSmemTotal, st>>>(a, rows_dev, max_rows, zero_tails);
+    DSVT_LAUNCH_CHECK();
+    return DSVT_OK;
 }
 
 // Device blob: [kRoles][kNumK][hi 12288 | lo 12288] weight images, then bias [kRoles][192] f32.

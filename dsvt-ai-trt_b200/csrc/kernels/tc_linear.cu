@@ -146,6 +146,10 @@ int linear_gen_launch(const void* blob, float out_mul, bool split, const float* 
 int linear_ln_launch(const void* blob, int K, float out_mul, bool split, const float* x, const int* rows_dev, int max_rows,
                      int n_ln, const float* const* res, const float* const* gamma, const float* const* beta, float eps,
                      float* y, int zero_tails, cudaStream_t st);
+void* ffn_w1_pieces_prepare(const float* W);
+int ffn_fused_launch(const void* blob1, const void* pieces1, float out_mul1, const void* blob2, float out_mul2, const float* x,
+                     const int* rows_dev, int max_rows, int n_ln, const float* const* res, const float* const* gamma,
+                     const float* const* beta, float eps, float* y, int zero_tails, cudaStream_t st);
 }
 
 struct dsvt_linear_weights {
@@ -154,6 +158,7 @@ struct dsvt_linear_weights {
     float* bias;      // device [N]
     void* split_blob; // device: 192 x 192 block images + bias                   (FP32_TC / FP16_GEMM persistent kernel)
     float out_mul;
+    void* piece_blob; // device: a 192 -> 384 FP32_TC layer as 64-column pieces  (first layer of dsvt_ffn_fused_launch)
 };
 
 static uint16_t f32_to_f16_bits(float f) { return __half_as_ushort(__float2half_rn(f)); }
@@ -172,13 +177,22 @@ extern "C" dsvt_linear_weights* dsvt_linear_weights_create(int32_t N, int32_t K,
             set_last_error("dsvt_linear_weights_create: the FP32_TC / FP16_GEMM linear layer needs N %% 192 == 0 and K %% 192 == 0");
             return nullptr;
         }
-        auto* lw = new (std::nothrow) dsvt_linear_weights{N, K, precision, nullptr, nullptr, nullptr, 1.0f};
+        auto* lw = new (std::nothrow) dsvt_linear_weights{N, K, precision, nullptr, nullptr, nullptr, 1.0f, nullptr};
         if (!lw) return nullptr;
         lw->split_blob = dsvt::linear_split_prepare(N, K, W, b, &lw->out_mul);
         if (!lw->split_blob) {
             set_last_error("dsvt_linear_weights_create: CUDA allocation/copy failed");
             delete lw;
             return nullptr;
+        }
+        if (precision == DSVT_ATTN_FP32_TC && N == 384 && K == 192) {
+            lw->piece_blob = dsvt::ffn_w1_pieces_prepare(W);
+            if (!lw->piece_blob) {
+                set_last_error("dsvt_linear_weights_create: CUDA allocation/copy failed");
+                cudaFree(lw->split_blob);
+                delete lw;
+                return nullptr;
+            }
         }
         return lw;
     }
@@ -201,7 +215,7 @@ extern "C" dsvt_linear_weights* dsvt_linear_weights_create(int32_t N, int32_t K,
             }
         }
     }
-    auto* lw = new (std::nothrow) dsvt_linear_weights{N, K, precision, nullptr, nullptr, nullptr, 1.0f};
+    auto* lw = new (std::nothrow) dsvt_linear_weights{N, K, precision, nullptr, nullptr, nullptr, 1.0f, nullptr};
     if (!lw) return nullptr;
     std::vector<float> zero(N, 0.f);
     if (cudaMalloc(&lw->img, img.size()) != cudaSuccess || cudaMalloc(&lw->bias, N * sizeof(float)) != cudaSuccess ||
@@ -220,6 +234,7 @@ extern "C" void dsvt_linear_weights_destroy(dsvt_linear_weights* w) {
     cudaFree(w->img);
     cudaFree(w->bias);
     cudaFree(w->split_blob);
+    cudaFree(w->piece_blob);
     delete w;
 }
 
@@ -303,6 +318,29 @@ extern "C" int dsvt_linear_rows_norm_launch(const dsvt_linear_weights* w, const 
         res[s] = stages[s].residual; gamma[s] = stages[s].gamma; beta[s] = stages[s].beta;
     }
     return dsvt::linear_ln_launch(w->split_blob, w->K, w->out_mul, w->precision == DSVT_ATTN_FP32_TC, x, rows, max_rows,
+                                  n_stages, res, gamma, beta, eps, y, zero_tails, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dsvt_ffn_fused_launch(const dsvt_linear_weights* fc1, const dsvt_linear_weights* fc2, const float* x,
+                                     const int32_t* rows, int32_t max_rows, const dsvt_ln_stage* stages, int32_t n_stages,
+                                     float eps, float* y, int32_t zero_tails, dsvt_stream_t stream)
+{
+    DSVT_CHECK_ARG(fc1 && fc2 && x && y && rows && stages && max_rows >= 1, "NULL argument");
+    DSVT_CHECK_ARG(fc1->piece_blob != nullptr && fc1->N == 384 && fc1->K == 192,
+                   "first layer: Linear(192 -> 384) created with DSVT_ATTN_FP32_TC");
+    DSVT_CHECK_ARG(fc2->split_blob != nullptr && fc2->precision == DSVT_ATTN_FP32_TC && fc2->N == 192 && fc2->K == 384,
+                   "second layer: Linear(384 -> 192) created with DSVT_ATTN_FP32_TC");
+    DSVT_CHECK_ARG(n_stages >= 1 && n_stages <= 3, "1..3 LayerNorm stages");
+    DSVT_CHECK_ARG(!(((uintptr_t) x & 31) | ((uintptr_t) y & 15)), "alignment (x 32 B, y 16 B)");
+    const float* res[3] = {nullptr, nullptr, nullptr};
+    const float* gamma[3] = {nullptr, nullptr, nullptr};
+    const float* beta[3] = {nullptr, nullptr, nullptr};
+    for (int s = 0; s < n_stages; ++s) {
+        DSVT_CHECK_ARG(stages[s].gamma && stages[s].beta, "NULL gamma / beta");
+        DSVT_CHECK_ARG(!(((uintptr_t) stages[s].residual | (uintptr_t) stages[s].gamma | (uintptr_t) stages[s].beta) & 15), "16-B alignment");
+        res[s] = stages[s].residual; gamma[s] = stages[s].gamma; beta[s] = stages[s].beta;
+    }
+    return dsvt::ffn_fused_launch(fc1->split_blob, fc1->piece_blob, fc1->out_mul, fc2->split_blob, fc2->out_mul, x, rows, max_rows,
                                   n_stages, res, gamma, beta, eps, y, zero_tails, reinterpret_cast<cudaStream_t>(stream));
 }
 

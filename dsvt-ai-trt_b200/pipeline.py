@@ -25,6 +25,8 @@ kernel (dsvt_linear_rows_launch), so a DSVT block becomes a real data flow from 
              out-projection (dsvt_set_attention_fused_norm_launch), the two / three LayerNorms behind the FFN into the
              second FFN linear (dsvt_linear_rows_norm_launch, K = 384 in one pass): 5 kernels per encoder layer, the
              attention output and the FFN output never reach memory
+    "kernel": "epilogue" with the whole FFN (both linears, the GELU, the norms) as ONE kernel (dsvt_ffn_fused_launch): the
+             384-wide hidden rows stay in tensor memory; 4 kernels per encoder layer
 
 The linear layers stand for TensorRT FullyConnected layers, which have no zero-tail contract (the engine computes all
 max_pillars rows; rows beyond the valid count hold bias-only values there and are never read by a plugin): they are launched
@@ -168,7 +170,7 @@ class HotPathFrame:
 
     def __init__(self, cfg, weights, precision=capi.DSVT_ATTN_FP32, seed=0, device="cuda", fuse_ln=True, share_plans=True,
                  ffn="off", skip=(), zero_tails=1, backbone=False, head=False):
-        assert ffn in ("off", "graph", "fused", "epilogue")
+        assert ffn in ("off", "graph", "fused", "epilogue", "kernel")
         assert not backbone or ffn != "off", "backbone=True runs every layer: it needs the FFN linears on"
         self.backbone = backbone
         # diagnostic only (tools/ablate.py): plugin groups left out of the launch sequence to measure their marginal
@@ -301,7 +303,7 @@ class HotPathFrame:
             for blk in range(0 if "pos" in skip else cfg.num_blocks):   # pos_embed[blk][i] from the shift-i window coordinates (:603-637)
                 for enc in (0, 1):
                     first, second = w.glue["pos"][blk][enc]
-                    if self.ffn == "epilogue":             # both layers in one kernel: the hidden rows never reach memory
+                    if self.ffn in ("epilogue", "kernel"):  # both layers in one kernel: the hidden rows never reach memory
                         capi.pos_embed_mlp(first, second, self.wp[enc].coors_in_win_x_y[0], V, out=self.pos_out[blk][enc],
                                            zero_tails=0)
                         continue
@@ -311,7 +313,7 @@ class HotPathFrame:
             gs = self.gs[blk % 2]                      # blocks 0,2: 12x12 windows; 1,3: 24x24 shifted (:654-:1018)
             x_in = x
             for enc in (0, 1):
-                epi = self.ffn == "epilogue"
+                epi = self.ffn in ("epilogue", "kernel")
                 if "attn" not in skip:
                     stages = 7 - sum(bit for g_, bit in (("attn_qkv", 1), ("attn_core", 2), ("attn_out", 4)) if g_ in skip)
                     capi.set_attention_fused(w.attn[blk * 2 + enc], x, pos[blk][enc], gs.global_index_in_set[0],
@@ -340,7 +342,7 @@ class HotPathFrame:
                     if self.ffn == "graph":
                         fc1.rows(self.src, V, out=self.ffn_h, zero_tails=0)               # :513  FC 192->384
                         capi.gelu(self.ffn_h, V, out=self.gelu_out, zero_tails=zt)         # :519  GeluPlugin
-                    elif "ffn1" not in skip:
+                    elif "ffn1" not in skip and self.ffn != "kernel":
                         fc1.rows(self.src, V, activation=1, out=self.gelu_out, zero_tails=0)   # FC + GELU epilogue
                     if epi:
                         # FC 384->192 (one pass over K) + norm2(src + src2) + norm(src + x) [+ the block's residual norm]
@@ -349,7 +351,10 @@ class HotPathFrame:
                         if enc == 1:
                             stages.append((x_in, w.gamma[ln], w.beta[ln])); ln += 1
                         nxt = self.x_a if enc == 0 else self.blk_out[blk % 2]
-                        if "ffn2" not in skip:
+                        if self.ffn == "kernel":
+                            if "ffn2" not in skip:          # both linears, the GELU and the norms in one kernel
+                                fc1.ffn_norm(fc2, self.src, V, stages, cfg.layer_norm_eps, out=nxt, zero_tails=zt)
+                        elif "ffn2" not in skip:
                             fc2.rows_norm(self.gelu_out, V, stages, cfg.layer_norm_eps, out=nxt, zero_tails=zt)
                         x = nxt
                         continue

@@ -376,6 +376,18 @@ int dsvt_linear_rows_norm_launch(const dsvt_linear_weights* w, const float* x, c
                                  dsvt_stream_t stream);
 
 /*
+ * The FFN of one encoder layer as ONE kernel (fullyConnected_gelu_fullyConnected, src/dsvt-ai-trt.cpp:494-529, + the
+ * addElementWise / LayerNormPlugin pairs behind it, :685-697 and :750-756):
+ *   y = LN_n( ... LN_1( gelu(x W1^T + b1) W2^T + b2 + r_1 ) ... + r_n )
+ * fc1 = Linear(192 -> 384), fc2 = Linear(384 -> 192), both created with DSVT_ATTN_FP32_TC.  The 384-wide hidden rows stay on
+ * the SM (second GEMM's A operand in tensor memory); results = dsvt_linear_rows_launch(activation GELU) followed by
+ * dsvt_linear_rows_norm_launch.  x [max_rows,192] (32-B aligned), y [max_rows,192], rows [1] on the device.
+ */
+int dsvt_ffn_fused_launch(const dsvt_linear_weights* fc1, const dsvt_linear_weights* fc2, const float* x,
+                          const int32_t* rows, int32_t max_rows, const dsvt_ln_stage* stages, int32_t n_stages,
+                          float eps, float* y, int32_t zero_tails, dsvt_stream_t stream);
+
+/*
  * Narrow first layers of the VFE / position-embedding MLPs (TensorRT FullyConnected + Scale + ReLU in the reference:
  * PFN layer 0 Linear(10 -> 96) src/dsvt-ai-trt.cpp:577, position embedding Linear(2 -> 192) :603-637 via :461-492):
  *   y = act((x W^T) * scale + shift),  W [N,K] row-major, K in [1, 16], N / 4 dividing 192, scale / shift [N] = the folded

@@ -125,7 +125,7 @@ def oracle_backbone(w, cfg, frame0):
     return x, bev, V, Pc
 
 
-@pytest.mark.parametrize("ffn", ["graph", "fused", "epilogue"])
+@pytest.mark.parametrize("ffn", ["graph", "fused", "epilogue", "kernel"])
 def test_whole_3d_backbone_chain(frame0, cfgs, ffn):
     """Raw points -> PFN -> scatter-max -> partition / sets -> 2 DSVT blocks (12x12 and shifted 24x24 windows) -> BEV map:
     every layer of the reference's 3-D backbone executed on the GPU through the C ABI, against the oracle chain."""
@@ -197,7 +197,7 @@ def test_bench_workload_chain(pkg, cfgs, geometry):
     cfg = getattr(cfgs, geometry)
     cloud = pkg.synth.ring_lidar(200000, seed=0)
     w = pipeline.FrameWeights(cfg, seed=0)
-    fr = _run_backbone(cfg, w, cloud, ffn="epilogue")       # the bench's frame kind (bench.FRAME_KINDS["backbone3d"])
+    fr = _run_backbone(cfg, w, cloud, ffn="kernel")         # the bench's frame kind (bench.FRAME_KINDS["backbone3d"])
     V, err = _check_backbone(fr, w, cfg, cloud, 5e-4)
     assert V > 25000                    # the survey's density (~30.6 k pillars), not round 1's 16.6 k
     assert int(fr.gs[0].set_num[0]) > 1300 and int(fr.gs[1].set_num[0]) > 900

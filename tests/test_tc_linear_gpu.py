@@ -194,3 +194,43 @@ def test_linear_rows_norm(K, n_ln, rows):
     if K == 192:      # against the separate launches: linear, then the LayerNorm chain kernel (same arithmetic per stage up to
         two = capi.layer_norm_chain(lin.rows(dx, n), n, stages, 0.0)       # the epilogue's reciprocal-multiply: a few ulp)
         assert (out - two).abs().max().item() <= 2e-6
+
+
+@pytest.mark.parametrize("n_ln", [1, 2, 3])
+@pytest.mark.parametrize("rows", [1, 130, 1000, 2999])
+def test_ffn_fused(n_ln, rows):
+    """dsvt_ffn_fused_launch (FC 192->384, GELU, FC 384->192 and the LayerNorm chain in one kernel, hidden rows in tensor
+    memory) against the two-kernel form it replaces (same products in the same order) and a float64 evaluation."""
+    capi = importlib.import_module("dsvt-ai-trt_b200.capi")
+    rng = np.random.default_rng(17 * n_ln + rows)
+    cap, C, F = 3000, 192, 384
+    x = np.zeros((cap, C), np.float32)
+    x[:rows] = rng.standard_normal((rows, C))
+    W1 = (rng.standard_normal((F, C)) * 0.07).astype(np.float32)
+    b1 = (rng.standard_normal(F) * 0.05).astype(np.float32)
+    W2 = (rng.standard_normal((C, F)) * 0.05).astype(np.float32)
+    b2 = (rng.standard_normal(C) * 0.05).astype(np.float32)
+    fc1 = capi.Linear(W1, b1, precision=capi.DSVT_ATTN_FP32_TC)
+    fc2 = capi.Linear(W2, b2, precision=capi.DSVT_ATTN_FP32_TC)
+    res = [torch.from_numpy(rng.standard_normal((cap, C)).astype(np.float32)).cuda() for _ in range(n_ln)]
+    gam = [torch.from_numpy((1 + 0.1 * rng.standard_normal(C)).astype(np.float32)).cuda() for _ in range(n_ln)]
+    bet = [torch.from_numpy((0.1 * rng.standard_normal(C)).astype(np.float32)).cuda() for _ in range(n_ln)]
+    dx, n = torch.from_numpy(x).cuda(), torch.tensor([rows], dtype=torch.int32, device="cuda")
+    stages = list(zip(res, gam, bet))
+    out = torch.full((cap, C), float("nan"), device="cuda")
+    fc1.ffn_norm(fc2, dx, n, stages, 0.0, out=out)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert np.isfinite(got[:rows]).all() and np.all(got[rows:] == 0)
+    hidden = fc1.rows(dx, n, activation=1, zero_tails=0)
+    two = fc2.rows_norm(hidden, n, stages, 0.0)
+    torch.cuda.synchronize()
+    assert (out[:rows] - two[:rows]).abs().max().item() <= 2e-6
+    h = x[:rows].astype(np.float64) @ W1.T.astype(np.float64) + b1
+    h = 0.5 * h * (1.0 + np.tanh(0.7978845608028654 * (h + 0.044715 * h ** 3)))
+    y = h @ W2.T.astype(np.float64) + b2
+    for r, g_, b_ in stages:
+        y = y + r[:rows].cpu().numpy().astype(np.float64)
+        mu = y.mean(1, keepdims=True)
+        y = (y - mu) / np.sqrt(((y - mu) ** 2).mean(1, keepdims=True)) * g_.cpu().numpy() + b_.cpu().numpy()
+    assert np.abs(got[:rows] - y).max() <= 5e-5

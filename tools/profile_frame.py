@@ -1,5 +1,5 @@
 """One HEADLINE frame (bench.py's frame kind "backbone3d": Waymo capacities, 200 k-point ring cloud seed 0, every layer of the
-3-D backbone, norms / GELU in the GEMM epilogues) between cudaProfilerStart/Stop, after one warm frame:
+3-D backbone, norms / GELU in the GEMM epilogues, each FFN one kernel) between cudaProfilerStart/Stop, after one warm frame:
     ncu --profile-from-start off --set full --clock-control none --import-source on -o gpurun_out/r2_frame python tools/profile_frame.py
     ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file ... python tools/profile_frame.py
 [--head] adds the post-process graph + rotated NMS (frame kind "backbone3d_postprocess")."""
@@ -10,7 +10,7 @@ pkg = importlib.import_module("dsvt-ai-trt_b200"); capi = importlib.import_modul
 pipeline = importlib.import_module("dsvt-ai-trt_b200.pipeline")
 cfg = pkg.config.WAYMO
 w = pipeline.FrameWeights(cfg)
-f = pipeline.HotPathFrame(cfg, w, precision=capi.DSVT_ATTN_FP32_TC, ffn="epilogue", backbone=True, head="--head" in sys.argv)
+f = pipeline.HotPathFrame(cfg, w, precision=capi.DSVT_ATTN_FP32_TC, ffn="kernel", backbone=True, head="--head" in sys.argv)
 f.load_points(pkg.synth.ring_lidar(200000, 0))
 f.run(); torch.cuda.synchronize()
 torch.cuda.profiler.start()
