@@ -82,6 +82,7 @@ def _lib():
         lib.dsvt_linear_weights_create.argtypes = [c_int32, c_int32, c_void_p, c_void_p, c_int32]
         lib.dsvt_linear_weights_destroy.argtypes = [c_void_p]
         lib.dsvt_small_linear_create.restype = c_void_p
+        lib.dsvt_vfe_fused_workspace_size.restype = c_size_t
         lib.dsvt_small_linear_create.argtypes = [c_int32, c_int32, c_void_p, c_void_p, c_void_p]
         lib.dsvt_small_linear_destroy.argtypes = [c_void_p]
         _sig_done = True
@@ -564,6 +565,24 @@ def pos_embed_mlp(first, second, x2, rows, out=None, zero_tails=1):
     _check(_lib().dsvt_pos_embed_mlp_launch(c_void_p(first.handle), c_void_p(second.handle), _ptr(x2), _ptr(rows),
                                             c_int32(max_rows), _ptr(out), c_int32(zero_tails), _stream()),
            "dsvt_pos_embed_mlp_launch")
+    return out
+
+
+def vfe_fused(pfn0, pfn1, point_features, point_index_in_voxel, voxel_num, point_num, out=None, workspace=None, zero_tails=1):
+    """The pillar feature net in one kernel (dsvt_vfe_fused_launch): pfn0 = SmallLinear(10 -> 96), pfn1 = Linear(192 -> 192,
+    FP32_TC); point_features [max_points, 10], point_index_in_voxel [max_pillars, npv] -> voxel features [max_pillars, 192]."""
+    _need(point_features, torch.float32, "point_features")
+    _need(point_index_in_voxel, torch.int32, "point_index_in_voxel")
+    max_points = point_features.shape[-2]
+    max_pillars, npv = point_index_in_voxel.shape[-2], point_index_in_voxel.shape[-1]
+    out = torch.empty(max_pillars, 192, dtype=torch.float32, device=point_features.device) if out is None else out
+    ws = int(_lib().dsvt_vfe_fused_workspace_size(c_int32(max_points), c_int32(npv)))
+    if workspace is None:
+        workspace = torch.empty(ws, dtype=torch.uint8, device=point_features.device)
+    _check(_lib().dsvt_vfe_fused_launch(c_void_p(pfn0.handle), c_void_p(pfn1.handle), _ptr(point_features),
+                                        _ptr(point_index_in_voxel), _ptr(voxel_num), _ptr(point_num), c_int32(max_points),
+                                        c_int32(max_pillars), c_int32(npv), _ptr(out), _ptr(workspace),
+                                        c_size_t(workspace.numel()), c_int32(zero_tails), _stream()), "dsvt_vfe_fused_launch")
     return out
 
 

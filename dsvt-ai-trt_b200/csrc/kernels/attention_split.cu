@@ -619,6 +619,7 @@ proj_tile_kernel(const __grid_constant__ GemmRoles roles, const int* __restrict_
 }
 
 #include "ffn_fused.cuh"
+#include "vfe_fused.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------
 // Plan kernel 1: one warp per set.  Token compaction, same rule as attention_fp32.cu: a slot that repeats the previous
@@ -1159,6 +1160,32 @@ int ffn_fused_launch(const void* blob1, const void* pieces1, float out_mul1, con
     DSVT_RAISE_SMEM(ffn_fused_kernel, kFSmemTotal);
     const dim3 grid((max_rows + kBM - 1) / kBM, 1, 1);
     ffn_fused_kernel<<<grid, kFThreads, kFSmemTotal, st>>>(a, rows_dev, max_rows, zero_tails);
+    DSVT_LAUNCH_CHECK();
+    return DSVT_OK;
+}
+
+// ---- fused VFE (vfe_fused.cuh) ------------------------------------------------------------------------------------
+size_t vfe_fused_workspace(int max_points, int npv) {
+    const int win = ((kBM - (npv - 1)) / 16) * 16;
+    return ((size_t) (max_points + win - 1) / win + 4) * sizeof(int);
+}
+int vfe_fused_launch(const float* pfn0_blob, const void* blob1, float out_mul1, const float* point_features, const int* piv,
+                     const int* voxel_num, const int* point_num, int max_points, int max_pillars, int npv, float* max_voxel,
+                     void* workspace, int zero_tails, cudaStream_t st)
+{
+    int win = ((kBM - (npv - 1)) / 16) * 16;            // rows of a tile <= win + npv - 1 <= 128
+    win = win < kVfeMaxPillars ? win : kVfeMaxPillars;   // pillars of a tile <= win
+    const uint8_t* img1 = static_cast<const uint8_t*>(blob1);
+    VfeArgs a;
+    a.x = point_features; a.piv = piv; a.pfn0 = pfn0_blob;
+    a.w1_img = img1; a.bias1 = reinterpret_cast<const float*>(img1 + (size_t) kWRoleBytes); a.out_mul1 = out_mul1;
+    a.out = max_voxel; a.tiles = static_cast<const int*>(workspace); a.npv = npv; a.win = win;
+    const int pgrid = (max_pillars + 255) / 256 < 4 * sm_count() ? (max_pillars + 255) / 256 : 4 * sm_count();
+    vfe_plan_kernel<<<pgrid, 256, 0, st>>>(piv, voxel_num, static_cast<int*>(workspace), reinterpret_cast<float4*>(max_voxel),
+                                           max_pillars, npv, win, zero_tails);
+    DSVT_LAUNCH_CHECK();
+    DSVT_RAISE_SMEM(vfe_fused_kernel, kVfeSmem);
+    vfe_fused_kernel<<<(max_points + win - 1) / win, kVfeThreads, kVfeSmem, st>>>(a, voxel_num, point_num, max_points, max_pillars);
     DSVT_LAUNCH_CHECK();
     return DSVT_OK;
 }

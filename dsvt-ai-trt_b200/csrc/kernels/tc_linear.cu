@@ -147,6 +147,10 @@ int linear_ln_launch(const void* blob, int K, float out_mul, bool split, const f
                      int n_ln, const float* const* res, const float* const* gamma, const float* const* beta, float eps,
                      float* y, int zero_tails, cudaStream_t st);
 void* ffn_w1_pieces_prepare(const float* W);
+size_t vfe_fused_workspace(int max_points, int npv);
+int vfe_fused_launch(const float* pfn0_blob, const void* blob1, float out_mul1, const float* point_features, const int* piv,
+                     const int* voxel_num, const int* point_num, int max_points, int max_pillars, int npv, float* max_voxel,
+                     void* workspace, int zero_tails, cudaStream_t st);
 int ffn_fused_launch(const void* blob1, const void* pieces1, float out_mul1, const void* blob2, float out_mul2, const float* x,
                      const int* rows_dev, int max_rows, int n_ln, const float* const* res, const float* const* gamma,
                      const float* const* beta, float eps, float* y, int zero_tails, cudaStream_t st);
@@ -358,4 +362,29 @@ extern "C" int dsvt_pos_embed_mlp_launch(const dsvt_small_linear* first, const d
     DSVT_CHECK_ARG(!(((uintptr_t) x2 & 7) | ((uintptr_t) y & 15)), "alignment (x2 8 B, y 16 B)");
     return dsvt::linear_gen_launch(second->split_blob, second->out_mul, second->precision == DSVT_ATTN_FP32_TC, x2, first->blob,
                                    rows, max_rows, y, zero_tails, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t dsvt_vfe_fused_workspace_size(int32_t max_points_num, int32_t max_num_points_per_voxel) {
+    if (max_points_num < 1 || max_num_points_per_voxel < 1 || max_num_points_per_voxel > 64) return 0;
+    return dsvt::vfe_fused_workspace(max_points_num, max_num_points_per_voxel);
+}
+
+extern "C" int dsvt_vfe_fused_launch(const dsvt_small_linear* pfn0, const dsvt_linear_weights* pfn1, const float* point_features,
+                                     const int32_t* point_index_in_voxel, const int32_t* voxel_num, const int32_t* point_num,
+                                     int32_t max_points_num, int32_t max_pillars_num, int32_t max_num_points_per_voxel,
+                                     float* voxel_features, void* workspace, size_t workspace_bytes, int32_t zero_tails,
+                                     dsvt_stream_t stream)
+{
+    DSVT_CHECK_ARG(pfn0 && pfn1 && point_features && point_index_in_voxel && voxel_num && point_num && voxel_features && workspace,
+                   "NULL argument");
+    DSVT_CHECK_ARG(pfn0->K == 10 && pfn0->N == 96, "PFN layer 0: Linear(10 -> 96) (+ folded BatchNorm, ReLU)");
+    DSVT_CHECK_ARG(pfn1->split_blob != nullptr && pfn1->precision == DSVT_ATTN_FP32_TC && pfn1->N == 192 && pfn1->K == 192,
+                   "PFN layer 1: Linear(192 -> 192) created with DSVT_ATTN_FP32_TC (BatchNorm folded)");
+    DSVT_CHECK_ARG(max_points_num >= 1 && max_pillars_num >= 1 && max_num_points_per_voxel >= 1 && max_num_points_per_voxel <= 64,
+                   "capacities");
+    DSVT_CHECK_ARG(workspace_bytes >= dsvt::vfe_fused_workspace(max_points_num, max_num_points_per_voxel), "workspace too small");
+    DSVT_CHECK_ARG(!(((uintptr_t) point_features & 7) | ((uintptr_t) voxel_features & 15) | ((uintptr_t) workspace & 3)), "alignment");
+    return dsvt::vfe_fused_launch(pfn0->blob, pfn1->split_blob, pfn1->out_mul, point_features, point_index_in_voxel, voxel_num,
+                                  point_num, max_points_num, max_pillars_num, max_num_points_per_voxel, voxel_features, workspace,
+                                  zero_tails, reinterpret_cast<cudaStream_t>(stream));
 }

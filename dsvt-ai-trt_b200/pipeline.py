@@ -38,6 +38,8 @@ is ONE data flow from the raw points to the BEV map (random-init weights, BatchN
     PFN layer 1  Linear(192->192)+BN+ReLU on [points | per-pillar max]    (:583-587, dsvt_linear_rows_concat_launch)
     8 position-embedding MLPs  Linear(2->192)+BN+ReLU -> Linear(192->192) (:603-637) on the in-window coordinates
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -247,6 +249,7 @@ class HotPathFrame:
             self.topk = capi.CenterHeadTopK(nc, cfg.grid_y, cfg.grid_x, cfg.max_top_k, device=device)
             self.nms = capi.RotatedNms(cfg.max_top_k, 0.01, device=device, zero_tails=self.zero_tails)      # NMS_THRESH, params.h:334
         self.launches_per_frame = None
+        self.vfe_ws = None
 
     def calibrate_head(self, n_above=250):
         """head="conv" only, random weights: shift the heat-map bias so that n_above cells of THIS frame's map score above
@@ -270,7 +273,16 @@ class HotPathFrame:
         skip, zt = self.skip, self.zero_tails
         vox = self.vox if "vox" in skip else self.vox(self.points, self.points_size)
         V = vox.pillar_num
-        for k in range(0 if "smax" in skip else len(cfg.pfn_channels)):             # :580-590 (the voxeliser's row count lets it skip the full clear)
+        vfe_one = self.backbone and self.ffn == "kernel"      # PFN 0 + scatter-max + concat + PFN 1 + scatter-max in one kernel
+        if vfe_one and not ("smax" in skip and "pfn" in skip):
+            g = w.glue
+            if self.vfe_ws is None:
+                self.vfe_ws = torch.empty(int(capi._lib().dsvt_vfe_fused_workspace_size(
+                    ctypes.c_int32(vox.point_features.shape[-2]), ctypes.c_int32(vox.point_index_in_voxel.shape[-1]))) + 16,
+                    dtype=torch.uint8, device=self.points.device)
+            capi.vfe_fused(g["pfn0"], g["pfn1"], vox.point_features[0], vox.point_index_in_voxel[0], V, vox.point_num,
+                           out=self.max_voxel[-1], workspace=self.vfe_ws, zero_tails=zt)
+        for k in range(0 if ("smax" in skip or vfe_one) else len(cfg.pfn_channels)):             # :580-590 (the voxeliser's row count lets it skip the full clear)
             pfn_out = self.w.pfn_out[k]
             if self.backbone:                                                       # the PFN layer in front of the scatter-max
                 g = w.glue

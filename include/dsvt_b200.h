@@ -400,6 +400,25 @@ int dsvt_small_linear_launch(const dsvt_small_linear* w, const float* x, const i
                              int32_t max_rows, int32_t activation, float* y, int32_t zero_tails, dsvt_stream_t stream);
 
 /*
+ * The pillar feature net as ONE kernel (src/dsvt-ai-trt.cpp:571-590): PFN layer 0 (Linear(10 -> 96) + BatchNorm + ReLU),
+ * TorchScatterMaxPlugin, the concatenation [point features | per-pillar max], PFN layer 1 (Linear(192 -> 192) + BatchNorm +
+ * ReLU) and the second TorchScatterMaxPlugin, of which the graph reads output 1 only (:589):
+ *   voxel_features [max_pillars_num, 192] = per-pillar max of relu([h0 | max(h0)] W1^T + b1),  h0 = relu(bn0(x W0^T)).
+ * None of the four per-point tensors reaches memory.  pfn0 = dsvt_small_linear_create(96, 10, W0, scale, shift);
+ * pfn1 = dsvt_linear_weights_create(192, 192, W1 (BatchNorm folded), b1, DSVT_ATTN_FP32_TC).  Inputs are
+ * Points2FeaturesPlugin's outputs 0 (point rows [max_points_num, 10]), 1 (point_index_in_voxel; this library's voxeliser
+ * emits a pillar's rows consecutively, which the kernel relies on), 4 (pillar count) and 5 (row count).  Results = the four
+ * separate launches (dsvt_small_linear_launch, dsvt_torch_scatter_max_launch, dsvt_linear_rows_concat_launch,
+ * dsvt_torch_scatter_max_launch).  Rows beyond the pillar count are zero-filled when zero_tails != 0.
+ */
+size_t dsvt_vfe_fused_workspace_size(int32_t max_points_num, int32_t max_num_points_per_voxel);
+int dsvt_vfe_fused_launch(const dsvt_small_linear* pfn0, const dsvt_linear_weights* pfn1, const float* point_features,
+                          const int32_t* point_index_in_voxel, const int32_t* voxel_num, const int32_t* point_num,
+                          int32_t max_points_num, int32_t max_pillars_num, int32_t max_num_points_per_voxel,
+                          float* voxel_features, void* workspace, size_t workspace_bytes, int32_t zero_tails,
+                          dsvt_stream_t stream);
+
+/*
  * One position-embedding MLP (fullyConnectedBnLELU_fullyConnected, src/dsvt-ai-trt.cpp:461-492; 8 call sites :603-637) in one
  * kernel:  y = relu((x2 W1^T) * scale + shift) W2^T + b2,  x2 [max_rows,2] = the in-window coordinates (WindowPartitionPlugin
  * output 5), `first` = Linear(2 -> 192) + folded BatchNorm1d, `second` = Linear(192 -> 192) created with DSVT_ATTN_FP32_TC or
