@@ -274,18 +274,35 @@ def plugin_breakdown(slot, cfg, peaks, reps=5):
         us = timed(lambda: f.wp[i](vox.coords, Vt))
         res[f"window_partition_{i}"] = {"us": us, "bytes": 16 * V + 16 * V + 20 * V + 4 * W[i], "calls_per_frame": 1,
                                         "scope": "next"}
-    # VFE: PFN layer 0 (streaming 10 -> 96), scatter-max, PFN layer 1 on [points | max] (tcgen05 linear), scatter-max
-    us = timed(lambda: g["pfn0"](vox.point_features[0], vox.point_num, activation=2, out=f.pfn0_out, zero_tails=0))
-    res["pfn0_linear_bn_relu"] = {"us": us, "bytes": 4 * Pc * (10 + F0), "calls_per_frame": 1, "scope": "next#4"}
-    us = timed(lambda: g["pfn1"].rows_concat(f.pfn0_out, f.max_point[0], vox.point_num, activation=2, out=f.pfn1_out, zero_tails=0))
-    res["pfn1_linear_bn_relu"] = {"us": us, "bytes": 4 * Pc * (2 * F0 + F1), "flops": 2 * Pc * 2 * F0 * F1,
-                                  "calls_per_frame": 1, "scope": "next#4"}
+    # VFE.  Headline: ONE kernel (dsvt_vfe_fused_launch: PFN 0, per-pillar max, concat, PFN 1, per-pillar max; bytes = point rows
+    # in, one 768-byte row per pillar out).  Separate-launch form (legs.backbone3d_two_kernel_ffn / _graph): PFN layer 0
+    # (streaming 10 -> 96), scatter-max, PFN layer 1 on [points | max] (tcgen05 linear), scatter-max -- timed on scratch buffers
+    us = timed(lambda: capi.vfe_fused(g["pfn0"], g["pfn1"], vox.point_features[0], vox.point_index_in_voxel[0], Vt, vox.point_num,
+                                      out=f.max_voxel[-1], workspace=f.vfe_ws))
+    res["vfe_fused"] = {"us": us, "bytes": 40 * Pc + 4 * F1 * V + 8 * V, "flops": 2 * Pc * (10 * F0 + 2 * F0 * F1),
+                        "mma_flops_issued": 3 * 2 * Pc * 2 * F0 * F1, "calls_per_frame": 1,
+                        "scope": "next#3 (2 x TorchScatterMaxPlugin) + next#4 (PFN linears)", "launches": 2}
     Pf = cfg.max_points_num_voxel_filter
-    for k, (fch, src) in enumerate(((F0, f.pfn0_out), (F1, f.pfn1_out))):
+    sep = None if f.pfn0_out is not None else \
+        [torch.empty(Pf, F0, device="cuda"), torch.empty(Pf, F1, device="cuda"), torch.empty(Pf, F0, device="cuda"),
+         torch.empty(Pf, F1, device="cuda"), torch.empty(cfg.max_pillars_num, F0, device="cuda")]
+    pfn0_out, pfn1_out = (f.pfn0_out, f.pfn1_out) if sep is None else (sep[0], sep[1])
+    max_point = f.max_point if sep is None else [sep[2], sep[3]]
+    max_voxel = f.max_voxel if sep is None else [sep[4], f.max_voxel[-1]]
+    us = timed(lambda: g["pfn0"](vox.point_features[0], vox.point_num, activation=2, out=pfn0_out, zero_tails=0))
+    res["pfn0_linear_bn_relu"] = {"us": us, "bytes": 4 * Pc * (10 + F0), "calls_per_frame": 0, "scope": "next#4"}
+    capi.torch_scatter_max(pfn0_out, vox.point_index_in_voxel[0], vox.point_num_in_voxel[0], Vt, vox.point_num,
+                           max_point=max_point[0], max_voxel=max_voxel[0])
+    us = timed(lambda: g["pfn1"].rows_concat(pfn0_out, max_point[0], vox.point_num, activation=2, out=pfn1_out, zero_tails=0))
+    res["pfn1_linear_bn_relu"] = {"us": us, "bytes": 4 * Pc * (2 * F0 + F1), "flops": 2 * Pc * 2 * F0 * F1,
+                                  "calls_per_frame": 0, "scope": "next#4"}
+    for k, (fch, src) in enumerate(((F0, pfn0_out), (F1, pfn1_out))):
         us = timed(lambda: capi.torch_scatter_max(src, vox.point_index_in_voxel[0], vox.point_num_in_voxel[0], Vt,
-                                                  vox.point_num, max_point=f.max_point[k], max_voxel=f.max_voxel[k]))
-        res[f"torch_scatter_max_{fch}"] = {"us": us, "bytes": 4 * fch * (2 * Pc + V) + 4 * (Pc + V), "calls_per_frame": 1,
+                                                  vox.point_num, max_point=max_point[k], max_voxel=max_voxel[k]))
+        res[f"torch_scatter_max_{fch}"] = {"us": us, "bytes": 4 * fch * (2 * Pc + V) + 4 * (Pc + V), "calls_per_frame": 0,
                                            "scope": "next", "contract_bytes": 4 * fch * (Pc + Pf + cfg.max_pillars_num)}
+    del sep, pfn0_out, pfn1_out, max_point, max_voxel
+    torch.cuda.empty_cache()
     first, second = g["pos"][0][0]
     us = timed(lambda: capi.pos_embed_mlp(first, second, f.wp[0].coors_in_win_x_y[0], Vt, out=f.pos_out[0][0], zero_tails=0))
     res["pos_embed_mlp"] = {"us": us, "bytes": 4 * V * (2 + C), "flops": 2 * V * C * C, "calls_per_frame": 8, "scope": "next#4",

@@ -214,18 +214,21 @@ class HotPathFrame:
             self.ffn_h = torch.empty(mp, F, device=device)      # FC 192->384 output (graph form only)
             self.ffn_o = torch.empty(mp, C, device=device)      # FC 384->192 output
             self.ffn_parts = torch.empty(F // C, mp, C, device=device)    # ... as split-K partial sums (fused form)
+        vfe_one = backbone and ffn == "kernel"     # fused VFE kernel: the per-point tensors of the pillar feature net do not exist
+        self.pfn0_out = self.pfn1_out = None
         if backbone:
             Pm = cfg.max_points_num_voxel_filter
-            self.pfn0_out = torch.empty(Pm, cfg.pfn_channels[0], device=device)
-            self.pfn1_out = torch.empty(Pm, cfg.pfn_channels[1], device=device)
+            if not vfe_one:
+                self.pfn0_out = torch.empty(Pm, cfg.pfn_channels[0], device=device)
+                self.pfn1_out = torch.empty(Pm, cfg.pfn_channels[1], device=device)
             self.pos_hidden = torch.empty(mp, C, device=device)
             self.pos_out = [[torch.empty(mp, C, device=device) for _ in range(2)] for _ in range(cfg.num_blocks)]
         self.x_a = torch.empty(mp, C, device=device)
         self.x_b = torch.empty(mp, C, device=device)
         self.blk_out = [torch.empty(mp, C, device=device) for _ in range(2)]
         # VFE glue plugins (TorchScatterMaxPlugin x2) and the BEV map (Map2BevPlugin)
-        self.max_point = [torch.empty(cfg.max_points_num_voxel_filter, f, device=device) for f in cfg.pfn_channels]
-        self.max_voxel = [torch.empty(mp, f, device=device) for f in cfg.pfn_channels]
+        self.max_point = None if vfe_one else [torch.empty(cfg.max_points_num_voxel_filter, f, device=device) for f in cfg.pfn_channels]
+        self.max_voxel = [None if (vfe_one and i == 0) else torch.empty(mp, f, device=device) for i, f in enumerate(cfg.pfn_channels)]
         self.bev = torch.empty(cfg.grid_y, cfg.grid_x, C, device=device)
         self.boxes = torch.empty(1, cfg.max_top_k, 9, device=device)
         self.valid = torch.empty(1, dtype=torch.int32, device=device)
