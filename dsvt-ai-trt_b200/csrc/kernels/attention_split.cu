@@ -51,21 +51,21 @@ constexpr int kEpiScratch = 32 * 32 * 4;             // 4096 B per epilogue warp
 // ---- attention plan: the set partition of one (frame, window partition, axis) in token order ----------------------
 // Built once by dsvt_set_attention_plan_launch and shared by every attention layer that uses the partition.
 // Per batch item, in ints (each array padded to 64): hdr[64] (hdr[0] = T, number of distinct tokens) |
-// set_off[max_sets + 1] (exclusive prefix of tokens per set) | nu[max_sets] | order[max_sets] (sets by descending token
-// count: the core kernel starts the longest sets first) | vox_su[max_pillars] (voxel -> set * 64 + u,
+// set_off[max_sets + 1] (exclusive prefix of tokens per set) | nu[max_sets] | order[max_sets] as int4 (set, token offset,
+// token count, 0), sets by descending token count: the core kernel starts the longest sets first | vox_su[max_pillars] (voxel -> set * 64 + u,
 // -1 if the voxel is in no set) | tok[max_sets * S] as int2 (voxel row, slot) of the u-th distinct token of each set.
 __host__ __device__ inline size_t pad64(size_t n) { return (n + 63) & ~(size_t) 63; }
-struct PlanView { int* hdr; int* set_off; int* nu; int* order; int* vox_su; int2* tok; };
+struct PlanView { int* hdr; int* set_off; int* nu; int4* order; int* vox_su; int2* tok; };
 __host__ __device__ inline size_t plan_words(int max_sets, int S, int max_pillars) {
-    return 64 + pad64((size_t) max_sets + 1) + 2 * pad64(max_sets) + pad64(max_pillars) + pad64((size_t) 2 * max_sets * S);
+    return 64 + pad64((size_t) max_sets + 1) + 5 * pad64(max_sets) + pad64(max_pillars) + pad64((size_t) 2 * max_sets * S);
 }
 __host__ __device__ inline PlanView plan_view(int* base, int max_sets, int max_pillars) {
     PlanView v;
     v.hdr = base;
     v.set_off = base + 64;
     v.nu = v.set_off + pad64((size_t) max_sets + 1);
-    v.order = v.nu + pad64(max_sets);
-    v.vox_su = v.order + pad64(max_sets);
+    v.order = reinterpret_cast<int4*>(v.nu + pad64(max_sets));      // (set, token offset, token count, 0), longest sets first
+    v.vox_su = v.nu + 5 * pad64(max_sets);
     v.tok = reinterpret_cast<int2*>(v.vox_su + pad64(max_pillars));
     return v;
 }
@@ -698,7 +698,12 @@ attn_plan_scan_kernel(const int* __restrict__ set_num, int* __restrict__ plan, s
         for (int c = 64; c >= 0; --c) { const int n = bucket[c]; bucket[c] = run; run += n; }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < ns; i += 1024) pv.order[atomicAdd(&bucket[min(pv.nu[i], 64)], 1)] = i;
+    // one 16-byte record per set -- (set, token offset, token count): the core kernel's CTA finds everything it needs to issue
+    // its K / V copy with ONE load instead of a chain of three dependent ones (order -> set_off[set] -> set_off[set + 1])
+    for (int i = threadIdx.x; i < ns; i += 1024) {
+        const int off = pv.set_off[i];
+        pv.order[atomicAdd(&bucket[min(pv.nu[i], 64)], 1)] = make_int4(i, off, pv.set_off[i + 1] - off, 0);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -758,12 +763,13 @@ attn_core_kernel(const float* __restrict__ qbuf, const float* __restrict__ kvbuf
     uint32_t phase = 0;
 
     for (int si = blockIdx.x; si < ns; si += gridDim.x, phase ^= 1) {
-        const int set = __ldg(pv.order + si);                          // longest sets first
+        const int4 rec = __ldg(pv.order + si);                         // longest sets first: (set, token offset, token count)
+        const int set = rec.x;
 #ifdef DSVT_CORE_PHASE_PROFILE
         const long long t_begin = clock64();
 #endif
-        const int off = __ldg(pv.set_off + set);
-        const int nu = __ldg(pv.set_off + set + 1) - off;          // distinct tokens of the set (clamped to the row capacity)
+        const int off = rec.y;
+        const int nu = rec.z;                                       // distinct tokens of the set (clamped to the row capacity)
         if (nu <= 0) { phase ^= 1; continue; }
         const int nu4 = (nu + 3) & ~3;                              // keys are processed in chunks of 4
         if (tid == 0) {
@@ -1387,7 +1393,7 @@ attn_identity_plan_kernel(const int* __restrict__ set_num, int* __restrict__ pla
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) { pv.hdr[0] = ns * S; rows_out[b] = ns * S; rows_out[gridDim.y + b] = ns; }     // rows | sets, per batch item
     if (i <= max_sets) pv.set_off[i] = (i < ns ? i : ns) * S;
-    if (i < max_sets) { pv.nu[i] = i < ns ? S : 0; pv.order[i] = i; }
+    if (i < max_sets) { pv.nu[i] = i < ns ? S : 0; pv.order[i] = make_int4(i, (i < ns ? i : ns) * S, i < ns ? S : 0, 0); }
     for (int t = i; t < rows_cap; t += gridDim.x * blockDim.x) {
         const int set = t / S, u = t - set * S;
         pv.vox_su[t] = set < ns ? set * 64 + u : -1;

@@ -1,0 +1,25 @@
+"""Phase stamps (SM cycles) of one CTA (blockIdx.x = 5: one of the longest sets) of the per-set attention core on the bench's
+frame 0.  Needs the profile build (DSVT_B200_LIBDIR=.../lib_prof)."""
+import ctypes, importlib, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+pkg = importlib.import_module("dsvt-ai-trt_b200"); capi = importlib.import_module("dsvt-ai-trt_b200.capi")
+pipeline = importlib.import_module("dsvt-ai-trt_b200.pipeline")
+cfg = pkg.config.WAYMO
+w = pipeline.FrameWeights(cfg, seed=0)
+f = pipeline.HotPathFrame(cfg, w, precision=capi.DSVT_ATTN_FP32_TC, ffn="kernel", backbone=True)
+f.load_points(pkg.synth.ring_lidar(200000, seed=0))
+f.run(); torch.cuda.synchronize()
+V, gs, x = f.vox.pillar_num, f.gs[0], f.blk_out[0]
+attn = lambda stages: capi.set_attention_fused(
+    w.attn[0], x, f.pos_out[0][0], gs.global_index_in_set[0], gs.mask_expand_0[0], gs.set_num, V, axis=0, out=f.src_b,
+    precision=f.precision, workspace=f.attn_ws, plan=f.plans[(0, 0)], norm=(x, w.gamma[0], w.beta[0], cfg.layer_norm_eps), stages=stages)
+attn(1); torch.cuda.synchronize()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda"); flush_r = torch.zeros(64 << 20, dtype=torch.int32, device="cuda")
+for cold in (True, False):
+    if cold: flush.zero_(); flush_r.max()
+    torch.cuda.synchronize()
+    attn(2); torch.cuda.synchronize()
+    buf = (ctypes.c_longlong * 64)(); capi._lib().dsvt_debug_split_profile(buf)
+    t = np.array(buf[:], dtype=np.int64)
+    print(f"{'cold' if cold else 'warm'} L2: K/V tile + q rows + masks staged after {t[34] - t[32]} cycles, scores / softmax / PV + stores {t[35] - t[34]} cycles")
