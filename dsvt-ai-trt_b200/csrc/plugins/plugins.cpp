@@ -1314,6 +1314,221 @@ private:
     float* ln_dev_ = nullptr;
 };
 
+// =================================================================================================
+// FfnFusedPlugin (new) -- fullyConnected_gelu_fullyConnected (src/dsvt-ai-trt.cpp:494-529: FullyConnected 192 -> 384, GeluPlugin,
+// FullyConnected 384 -> 192) and the n_stages (kSUM + LayerNormPlugin) pairs behind it (:685-697, :750-756) as ONE node / ONE
+// kernel (dsvt_ffn_fused_launch): the 384-wide hidden rows stay in tensor memory.
+// Inputs : x [B,max_rows,192] f32, rows [B] i32, residual_1..n [B,max_rows,192].   Output: [B,max_rows,192], rows beyond the count zero.
+// Fields : max_rows, weight1 f32[384*192], bias1 f32[384], weight2 f32[192*384], bias2 f32[192], n_stages (1..3), ln_eps,
+//          ln_weights f32[n*192], ln_bias f32[n*192].
+// =================================================================================================
+class FfnFusedPlugin final : public PluginBase {
+public:
+    static constexpr const char* kName = "FfnFusedPlugin";
+    static constexpr int kCin = 192, kHid = 384;
+    static FieldList field_list() {
+        return {{"max_rows", PluginFieldType::kINT32}, {"weight1", PluginFieldType::kFLOAT32}, {"bias1", PluginFieldType::kFLOAT32},
+                {"weight2", PluginFieldType::kFLOAT32}, {"bias2", PluginFieldType::kFLOAT32}, {"n_stages", PluginFieldType::kINT32},
+                {"ln_eps", PluginFieldType::kFLOAT32}, {"ln_weights", PluginFieldType::kFLOAT32}, {"ln_bias", PluginFieldType::kFLOAT32}};
+    }
+    FfnFusedPlugin(int max_rows, const float* w1, const float* b1, const float* w2, const float* b2, int n_ln, float eps,
+                   const float* gamma, const float* beta)
+        : max_rows_(max_rows), n_ln_(n_ln), eps_(eps), w1_(w1, w1 + kHid * kCin), b1_(b1, b1 + kHid), w2_(w2, w2 + kCin * kHid),
+          b2_(b2, b2 + kCin), gamma_(gamma, gamma + (size_t) n_ln * kCin), beta_(beta, beta + (size_t) n_ln * kCin) {}
+    ~FfnFusedPlugin() override { release(); }
+    static IPluginV2* from_fields(const PluginFieldCollection* fc) {
+        const int n_ln = field_int(fc, "n_stages");
+        const PluginField *w1 = find_field(fc, "weight1"), *b1 = find_field(fc, "bias1"), *w2 = find_field(fc, "weight2"),
+                          *b2 = find_field(fc, "bias2"), *g = find_field(fc, "ln_weights"), *be = find_field(fc, "ln_bias");
+        if (n_ln < 1 || n_ln > 3 || !w1 || !b1 || !w2 || !b2 || !g || !be || !w1->data || !b1->data || !w2->data || !b2->data ||
+            !g->data || !be->data || w1->length != kHid * kCin || b1->length != kHid || w2->length != kCin * kHid ||
+            b2->length != kCin || g->length != n_ln * kCin || be->length != n_ln * kCin)
+            return nullptr;
+        return new (std::nothrow) FfnFusedPlugin(field_int(fc, "max_rows"), static_cast<const float*>(w1->data),
+                                                 static_cast<const float*>(b1->data), static_cast<const float*>(w2->data),
+                                                 static_cast<const float*>(b2->data), n_ln, field_float(fc, "ln_eps", 0, 0.0f),
+                                                 static_cast<const float*>(g->data), static_cast<const float*>(be->data));
+    }
+    static IPluginV2* from_bytes(const void* data, size_t len) {
+        Reader r(data, len);
+        const int mr = r.get<int>(), n_ln = r.get<int>();
+        const float eps = r.get<float>();
+        const size_t nw = (size_t) kHid * kCin;
+        if (!r.ok() || n_ln < 1 || n_ln > 3 || r.left() < (2 * nw + kHid + kCin + (size_t) 2 * n_ln * kCin) * sizeof(float)) return nullptr;
+        std::vector<float> w1(nw), b1(kHid), w2(nw), b2(kCin), g((size_t) n_ln * kCin), be((size_t) n_ln * kCin);
+        r.get_array(w1.data(), w1.size()); r.get_array(b1.data(), b1.size()); r.get_array(w2.data(), w2.size());
+        r.get_array(b2.data(), b2.size()); r.get_array(g.data(), g.size()); r.get_array(be.data(), be.size());
+        return new (std::nothrow) FfnFusedPlugin(mr, w1.data(), b1.data(), w2.data(), b2.data(), n_ln, eps, g.data(), be.data());
+    }
+    size_t getSerializationSize() const noexcept override {
+        return 2 * sizeof(int) + sizeof(float) +
+               (w1_.size() + b1_.size() + w2_.size() + b2_.size() + gamma_.size() + beta_.size()) * sizeof(float);
+    }
+    void serialize(void* buf) const noexcept override {
+        Writer w(buf);
+        w.put(max_rows_); w.put(n_ln_); w.put(eps_);
+        w.put_array(w1_.data(), w1_.size()); w.put_array(b1_.data(), b1_.size()); w.put_array(w2_.data(), w2_.size());
+        w.put_array(b2_.data(), b2_.size()); w.put_array(gamma_.data(), gamma_.size()); w.put_array(beta_.data(), beta_.size());
+    }
+    IPluginV2DynamicExt* clone() const noexcept override {
+        auto* c = new (std::nothrow) FfnFusedPlugin(max_rows_, w1_.data(), b1_.data(), w2_.data(), b2_.data(), n_ln_, eps_,
+                                                    gamma_.data(), beta_.data());
+        if (c) c->setPluginNamespace(ns_.c_str());
+        return c;
+    }
+    int32_t initialize() noexcept override { return upload(); }
+    void terminate() noexcept override { release(); }
+    const char* getPluginType() const noexcept override { return kName; }
+    int32_t getNbOutputs() const noexcept override { return 1; }
+    DimsExprs getOutputDimensions(int32_t, const DimsExprs* in, int32_t, IExprBuilder& b) noexcept override {
+        return dims(b, in[0].d[0], {max_rows_, kCin});
+    }
+    bool supportsFormatCombination(int32_t pos, const PluginTensorDesc* io, int32_t nbIn, int32_t nbOut) noexcept override {
+        if (pos < 0 || pos >= nbIn + nbOut || nbIn != 2 + n_ln_ || io[pos].format != TensorFormat::kLINEAR) return false;
+        return io[pos].type == (pos == 1 ? I : F);
+    }
+    DataType getOutputDataType(int32_t, const DataType*, int32_t) const noexcept override { return F; }
+    int32_t enqueue(const PluginTensorDesc* in, const PluginTensorDesc*, const void* const* inputs,
+                    void* const* outputs, void*, cudaStream_t stream) noexcept override {
+        if (upload() != 0) return DSVT_ERR_CUDA;
+        if (batch_of(in) != 1) { std::fprintf(stderr, "[dsvt_b200] FfnFusedPlugin: batch 1 only\n"); return DSVT_ERR_UNSUPPORTED; }
+        dsvt_ln_stage st[3];
+        for (int s = 0; s < n_ln_; ++s)
+            st[s] = dsvt_ln_stage{static_cast<const float*>(inputs[2 + s]), ln_dev_ + (size_t) s * kCin, ln_dev_ + (size_t) (n_ln_ + s) * kCin};
+        return report(dsvt_ffn_fused_launch(fc1_, fc2_, static_cast<const float*>(inputs[0]), static_cast<const int32_t*>(inputs[1]),
+                                            max_rows_, st, n_ln_, eps_, static_cast<float*>(outputs[0]), 1, stream), kName);
+    }
+protected:
+    const std::vector<DataType>& io_types() const override {
+        static const std::vector<DataType> t{F, I, F, F, F, F};
+        return t;
+    }
+    size_t nb_inputs() const override { return 2 + (size_t) n_ln_; }
+private:
+    int upload() {
+        if (!fc1_) fc1_ = dsvt_linear_weights_create(kHid, kCin, w1_.data(), b1_.data(), DSVT_ATTN_FP32_TC);
+        if (!fc2_) fc2_ = dsvt_linear_weights_create(kCin, kHid, w2_.data(), b2_.data(), DSVT_ATTN_FP32_TC);
+        if (!fc1_ || !fc2_) return 1;
+        if (!ln_dev_) {
+            const size_t n = gamma_.size();
+            if (cudaMalloc(reinterpret_cast<void**>(&ln_dev_), 2 * n * sizeof(float)) != cudaSuccess) return 1;
+            if (cudaMemcpy(ln_dev_, gamma_.data(), n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+                cudaMemcpy(ln_dev_ + n, beta_.data(), n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return 1;
+        }
+        return 0;
+    }
+    void release() {
+        if (fc1_) { dsvt_linear_weights_destroy(fc1_); fc1_ = nullptr; }
+        if (fc2_) { dsvt_linear_weights_destroy(fc2_); fc2_ = nullptr; }
+        if (ln_dev_) { cudaFree(ln_dev_); ln_dev_ = nullptr; }
+    }
+    int max_rows_, n_ln_;
+    float eps_;
+    std::vector<float> w1_, b1_, w2_, b2_, gamma_, beta_;
+    dsvt_linear_weights *fc1_ = nullptr, *fc2_ = nullptr;
+    float* ln_dev_ = nullptr;
+};
+
+// =================================================================================================
+// VfeFusedPlugin (new) -- the pillar feature net of src/dsvt-ai-trt.cpp:571-590 as ONE node (dsvt_vfe_fused_launch): PFN layer 0
+// (FullyConnected 10 -> 96 + Scale + ReLU), TorchScatterMaxPlugin, concatenation, PFN layer 1 (FullyConnected 192 -> 192 + Scale +
+// ReLU, BatchNorm folded into weight1 / bias1 by the builder) and the second TorchScatterMaxPlugin's output 1.
+// Inputs : Points2FeaturesPlugin outputs 0 (point rows [B,max_points,10]), 1 (point_index_in_voxel [B,max_pillars,npv] i32),
+//          4 (pillar count [B] i32), 5 (row count [B] i32).       Output: voxel features [B,max_pillars,192] f32.
+// Fields : max_points_num, max_pillars_num, max_num_points_per_voxel, weight0 f32[96*10], scale0 f32[96], shift0 f32[96],
+//          weight1 f32[192*192], bias1 f32[192].
+// =================================================================================================
+class VfeFusedPlugin final : public PluginBase {
+public:
+    static constexpr const char* kName = "VfeFusedPlugin";
+    static constexpr int kIn = 10, kMid = 96, kOut = 192;
+    static FieldList field_list() {
+        return {{"max_points_num", PluginFieldType::kINT32}, {"max_pillars_num", PluginFieldType::kINT32},
+                {"max_num_points_per_voxel", PluginFieldType::kINT32}, {"weight0", PluginFieldType::kFLOAT32},
+                {"scale0", PluginFieldType::kFLOAT32}, {"shift0", PluginFieldType::kFLOAT32}, {"weight1", PluginFieldType::kFLOAT32},
+                {"bias1", PluginFieldType::kFLOAT32}};
+    }
+    VfeFusedPlugin(int max_points, int max_pillars, int npv, const float* w0, const float* sc0, const float* sh0, const float* w1,
+                   const float* b1)
+        : max_points_(max_points), max_pillars_(max_pillars), npv_(npv), w0_(w0, w0 + kMid * kIn), sc0_(sc0, sc0 + kMid),
+          sh0_(sh0, sh0 + kMid), w1_(w1, w1 + kOut * kOut), b1_(b1, b1 + kOut) {}
+    ~VfeFusedPlugin() override { release(); }
+    static bool valid(int mp, int mv, int npv) { return mp >= 1 && mv >= 1 && npv >= 1 && npv <= 64; }
+    static IPluginV2* from_fields(const PluginFieldCollection* fc) {
+        const int mp = field_int(fc, "max_points_num"), mv = field_int(fc, "max_pillars_num"), npv = field_int(fc, "max_num_points_per_voxel");
+        const PluginField *w0 = find_field(fc, "weight0"), *sc = find_field(fc, "scale0"), *sh = find_field(fc, "shift0"),
+                          *w1 = find_field(fc, "weight1"), *b1 = find_field(fc, "bias1");
+        if (!valid(mp, mv, npv) || !w0 || !sc || !sh || !w1 || !b1 || !w0->data || !sc->data || !sh->data || !w1->data || !b1->data ||
+            w0->length != kMid * kIn || sc->length != kMid || sh->length != kMid || w1->length != kOut * kOut || b1->length != kOut)
+            return nullptr;
+        return new (std::nothrow) VfeFusedPlugin(mp, mv, npv, static_cast<const float*>(w0->data), static_cast<const float*>(sc->data),
+                                                 static_cast<const float*>(sh->data), static_cast<const float*>(w1->data),
+                                                 static_cast<const float*>(b1->data));
+    }
+    static IPluginV2* from_bytes(const void* data, size_t len) {
+        Reader r(data, len);
+        const int mp = r.get<int>(), mv = r.get<int>(), npv = r.get<int>();
+        if (!r.ok() || !valid(mp, mv, npv) || r.left() < ((size_t) kMid * kIn + 2 * kMid + (size_t) kOut * kOut + kOut) * sizeof(float)) return nullptr;
+        std::vector<float> w0((size_t) kMid * kIn), sc(kMid), sh(kMid), w1((size_t) kOut * kOut), b1(kOut);
+        r.get_array(w0.data(), w0.size()); r.get_array(sc.data(), sc.size()); r.get_array(sh.data(), sh.size());
+        r.get_array(w1.data(), w1.size()); r.get_array(b1.data(), b1.size());
+        return new (std::nothrow) VfeFusedPlugin(mp, mv, npv, w0.data(), sc.data(), sh.data(), w1.data(), b1.data());
+    }
+    size_t getSerializationSize() const noexcept override {
+        return 3 * sizeof(int) + (w0_.size() + sc0_.size() + sh0_.size() + w1_.size() + b1_.size()) * sizeof(float);
+    }
+    void serialize(void* buf) const noexcept override {
+        Writer w(buf);
+        w.put(max_points_); w.put(max_pillars_); w.put(npv_);
+        w.put_array(w0_.data(), w0_.size()); w.put_array(sc0_.data(), sc0_.size()); w.put_array(sh0_.data(), sh0_.size());
+        w.put_array(w1_.data(), w1_.size()); w.put_array(b1_.data(), b1_.size());
+    }
+    IPluginV2DynamicExt* clone() const noexcept override {
+        auto* c = new (std::nothrow) VfeFusedPlugin(max_points_, max_pillars_, npv_, w0_.data(), sc0_.data(), sh0_.data(), w1_.data(), b1_.data());
+        if (c) c->setPluginNamespace(ns_.c_str());
+        return c;
+    }
+    int32_t initialize() noexcept override { return upload(); }
+    void terminate() noexcept override { release(); }
+    const char* getPluginType() const noexcept override { return kName; }
+    int32_t getNbOutputs() const noexcept override { return 1; }
+    DimsExprs getOutputDimensions(int32_t, const DimsExprs* in, int32_t, IExprBuilder& b) noexcept override {
+        return dims(b, in[0].d[0], {max_pillars_, kOut});
+    }
+    size_t getWorkspaceSize(const PluginTensorDesc*, int32_t, const PluginTensorDesc*, int32_t) const noexcept override {
+        return dsvt_vfe_fused_workspace_size(max_points_, npv_);
+    }
+    int32_t enqueue(const PluginTensorDesc* in, const PluginTensorDesc*, const void* const* inputs,
+                    void* const* outputs, void* ws, cudaStream_t stream) noexcept override {
+        if (upload() != 0) return DSVT_ERR_CUDA;
+        if (batch_of(in) != 1) { std::fprintf(stderr, "[dsvt_b200] VfeFusedPlugin: batch 1 only\n"); return DSVT_ERR_UNSUPPORTED; }
+        return report(dsvt_vfe_fused_launch(pfn0_, pfn1_, static_cast<const float*>(inputs[0]), static_cast<const int32_t*>(inputs[1]),
+                                            static_cast<const int32_t*>(inputs[2]), static_cast<const int32_t*>(inputs[3]), max_points_,
+                                            max_pillars_, npv_, static_cast<float*>(outputs[0]), ws,
+                                            dsvt_vfe_fused_workspace_size(max_points_, npv_), 1, stream), kName);
+    }
+protected:
+    const std::vector<DataType>& io_types() const override {
+        static const std::vector<DataType> t{F, I, I, I, F};
+        return t;
+    }
+    size_t nb_inputs() const override { return 4; }
+private:
+    int upload() {
+        if (!pfn0_) pfn0_ = dsvt_small_linear_create(kMid, kIn, w0_.data(), sc0_.data(), sh0_.data());
+        if (!pfn1_) pfn1_ = dsvt_linear_weights_create(kOut, kOut, w1_.data(), b1_.data(), DSVT_ATTN_FP32_TC);
+        return pfn0_ && pfn1_ ? 0 : 1;
+    }
+    void release() {
+        if (pfn0_) { dsvt_small_linear_destroy(pfn0_); pfn0_ = nullptr; }
+        if (pfn1_) { dsvt_linear_weights_destroy(pfn1_); pfn1_ = nullptr; }
+    }
+    int max_points_, max_pillars_, npv_;
+    std::vector<float> w0_, sc0_, sh0_, w1_, b1_;
+    dsvt_small_linear* pfn0_ = nullptr;
+    dsvt_linear_weights* pfn1_ = nullptr;
+};
+
 // registration: from the library only (the reference registers from two images)
 using Points2FeaturesPluginCreator = CreatorBase<Points2FeaturesPlugin>;
 using WindowPartitionPluginCreator = CreatorBase<WindowPartitionPlugin>;
@@ -1330,6 +1545,8 @@ using Map2BevPluginCreator = CreatorBase<Map2BevPlugin>;
 using SetAttentionPlanPluginCreator = CreatorBase<SetAttentionPlanPlugin>;
 using LayerNormChainPluginCreator = CreatorBase<LayerNormChainPlugin>;
 using LinearPluginCreator = CreatorBase<LinearPlugin>;
+using FfnFusedPluginCreator = CreatorBase<FfnFusedPlugin>;
+using VfeFusedPluginCreator = CreatorBase<VfeFusedPlugin>;
 
 REGISTER_TENSORRT_PLUGIN(Points2FeaturesPluginCreator);
 REGISTER_TENSORRT_PLUGIN(WindowPartitionPluginCreator);
@@ -1346,5 +1563,7 @@ REGISTER_TENSORRT_PLUGIN(Map2BevPluginCreator);
 REGISTER_TENSORRT_PLUGIN(SetAttentionPlanPluginCreator);
 REGISTER_TENSORRT_PLUGIN(LayerNormChainPluginCreator);
 REGISTER_TENSORRT_PLUGIN(LinearPluginCreator);
+REGISTER_TENSORRT_PLUGIN(FfnFusedPluginCreator);
+REGISTER_TENSORRT_PLUGIN(VfeFusedPluginCreator);
 
 }  // namespace dsvt_plugins

@@ -297,6 +297,27 @@ def add_linear_op(lib, max_rows, in_features, out_features, weight, bias, activa
     return lib.create("LinearPlugin", fields)
 
 
+def add_ffn_fused_op(lib, max_rows, weight1, bias1, weight2, bias2, ln_weights, ln_bias, ln_eps=0.0):
+    """fullyConnected_gelu_fullyConnected (src/dsvt-ai-trt.cpp:494-529) + the n = len(ln_weights) (kSUM + LayerNormPlugin) pairs
+    behind it as one node / one kernel.  Inputs: x [B,max_rows,192], rows [B], residual_1 .. residual_n."""
+    g = np.asarray(ln_weights, np.float32)
+    return lib.create("FfnFusedPlugin", {
+        "max_rows": max_rows, "weight1": np.asarray(weight1, np.float32), "bias1": np.asarray(bias1, np.float32),
+        "weight2": np.asarray(weight2, np.float32), "bias2": np.asarray(bias2, np.float32), "n_stages": int(g.shape[0]),
+        "ln_eps": float(ln_eps), "ln_weights": g, "ln_bias": np.asarray(ln_bias, np.float32)})
+
+
+def add_vfe_fused_op(lib, max_points_num, max_pillars_num, max_num_points_per_voxel, weight0, scale0, shift0, weight1, bias1):
+    """The pillar feature net of src/dsvt-ai-trt.cpp:571-590 as one node: PFN 0 (Linear(10 -> 96), BatchNorm as scale0 / shift0,
+    ReLU), scatter-max, concat, PFN 1 (Linear(192 -> 192) with its BatchNorm folded into weight1 / bias1, ReLU), scatter-max.
+    Inputs: Points2FeaturesPlugin outputs 0, 1, 4, 5."""
+    return lib.create("VfeFusedPlugin", {
+        "max_points_num": max_points_num, "max_pillars_num": max_pillars_num,
+        "max_num_points_per_voxel": max_num_points_per_voxel, "weight0": np.asarray(weight0, np.float32),
+        "scale0": np.asarray(scale0, np.float32), "shift0": np.asarray(shift0, np.float32),
+        "weight1": np.asarray(weight1, np.float32), "bias1": np.asarray(bias1, np.float32)})
+
+
 def add_torch_scatter_max(lib, max_points_num, max_pillars_num, feature_num):
     """include/plugin_helper.h:125 (inputs: point_features, point_index_in_voxel, point_num_in_voxel, voxel_num)."""
     return lib.create("TorchScatterMaxPlugin", {

@@ -322,9 +322,67 @@ def test_linear_plugin(lib, plg, K, N, act, n_ln):
     assert np.abs(got[:rows] - y).max() <= 5e-5
 
 
+@pytest.mark.parametrize("n_ln", [2, 3])
+def test_ffn_fused_plugin(lib, plg, n_ln):
+    """FfnFusedPlugin: FC 192->384, GELU, FC 384->192 and the LayerNorm chain behind it as one node, against float64 and its own
+    serialised clone."""
+    rng = np.random.default_rng(40 + n_ln)
+    mr, rows, C, Fh = 1300, 1000, 192, 384
+    x = np.zeros((mr, C), np.float32); x[:rows] = rng.standard_normal((rows, C))
+    W1 = (rng.standard_normal((Fh, C)) * 0.07).astype(np.float32); b1 = (rng.standard_normal(Fh) * 0.05).astype(np.float32)
+    W2 = (rng.standard_normal((C, Fh)) * 0.05).astype(np.float32); b2 = (rng.standard_normal(C) * 0.05).astype(np.float32)
+    res = [rng.standard_normal((mr, C)).astype(np.float32) for _ in range(n_ln)]
+    gam = (1 + 0.1 * rng.standard_normal((n_ln, C))).astype(np.float32)
+    bet = (0.1 * rng.standard_normal((n_ln, C))).astype(np.float32)
+    p = plg.add_ffn_fused_op(lib, mr, W1, b1, W2, b2, gam, bet)
+    p, blob = roundtrip(lib, p)
+    assert blob[:8] == struct.pack("<2i", mr, n_ln)
+    (out,) = p.enqueue([dev(x)[None], i32(rows)] + [dev(r)[None] for r in res], poison=float("nan"))
+    h = x[:rows].astype(np.float64) @ W1.T.astype(np.float64) + b1
+    h = (0.5 + 0.5 * np.tanh(h * (0.035677408136300125 * h * h + 0.7978845608028654))) * h
+    y = h @ W2.T.astype(np.float64) + b2
+    for s_ in range(n_ln):
+        y = y + res[s_][:rows]
+        mu = y.mean(1, keepdims=True)
+        y = (y - mu) / np.sqrt(((y - mu) ** 2).mean(1, keepdims=True)) * gam[s_] + bet[s_]
+    got = out[0].cpu().numpy()
+    assert np.all(got[rows:] == 0)
+    assert np.abs(got[:rows] - y).max() <= 5e-5
+
+
+def test_vfe_fused_plugin(lib, plg, frame0):
+    """VfeFusedPlugin on Points2FeaturesPlugin's own outputs (the reference's sample frame) against the four nodes it replaces,
+    run through the C ABI: bit for bit."""
+    capi = importlib.import_module("dsvt-ai-trt_b200.capi")
+    config = importlib.import_module("dsvt-ai-trt_b200.config")
+    cfg = config.REFERENCE
+    rng = np.random.default_rng(11)
+    pts = np.zeros((cfg.max_points_num, 4), np.float32)
+    n = min(len(frame0), cfg.max_points_num)
+    pts[:n] = frame0[:n]
+    vox = capi.Points2Features(cfg)
+    vox(dev(pts)[None], i32(n))
+    W0 = (rng.standard_normal((96, 10)) * 0.3).astype(np.float32)
+    sc0, sh0 = (1 + 0.1 * rng.standard_normal(96)).astype(np.float32), (0.1 * rng.standard_normal(96)).astype(np.float32)
+    W1 = (rng.standard_normal((192, 192)) * 0.07).astype(np.float32); b1 = (rng.standard_normal(192) * 0.05).astype(np.float32)
+    p = plg.add_vfe_fused_op(lib, cfg.max_points_num_voxel_filter, cfg.max_pillars_num, cfg.max_num_points_per_voxel, W0, sc0, sh0, W1, b1)
+    p, blob = roundtrip(lib, p)
+    assert blob[:12] == struct.pack("<3i", cfg.max_points_num_voxel_filter, cfg.max_pillars_num, cfg.max_num_points_per_voxel)
+    (out,) = p.enqueue([vox.point_features, vox.point_index_in_voxel, vox.pillar_num, vox.point_num], poison=float("nan"))
+    pfn0 = capi.SmallLinear(W0, sc0, sh0)
+    pfn1 = capi.Linear(W1, b1, precision=capi.DSVT_ATTN_FP32_TC)
+    h0 = pfn0(vox.point_features[0], vox.point_num, activation=2, zero_tails=0)
+    mp0, _ = capi.torch_scatter_max(h0, vox.point_index_in_voxel[0], vox.point_num_in_voxel[0], vox.pillar_num, vox.point_num)
+    h1 = pfn1.rows_concat(h0, mp0, vox.point_num, activation=2, zero_tails=0)
+    _, mv1 = capi.torch_scatter_max(h1, vox.point_index_in_voxel[0], vox.point_num_in_voxel[0], vox.pillar_num, vox.point_num)
+    torch.cuda.synchronize()
+    V = int(vox.pillar_num[0])
+    assert V > 1000 and torch.equal(out[0][:V], mv1[:V]) and bool((out[0][V:] == 0).all())
+
+
 def test_registry_and_formats(lib):
     names = set(lib.registered())
     assert {"Points2FeaturesPlugin", "GetSetPlugin", "GeluPlugin", "LayerNormPlugin", "FilterBoxByScorePlugin",
             "WindowPartitionPlugin", "GetValueByIndexPlugin", "MapSetFeature2VoxelPlugin", "SetAttentionPlugin",
             "SetAttentionFusedPlugin", "SetAttentionPlanPlugin", "TorchScatterMaxPlugin", "Map2BevPlugin",
-            "LayerNormChainPlugin", "LinearPlugin"} <= names
+            "LayerNormChainPlugin", "LinearPlugin", "FfnFusedPlugin", "VfeFusedPlugin"} <= names
