@@ -242,3 +242,36 @@ def test_vfe_fused_equals_separate_launches(pkg, cfgs, n_points, seed):
     a, b = sep.max_voxel[-1], one.max_voxel[-1]
     assert torch.isfinite(b).all() and torch.all(b[V:] == 0)
     assert torch.equal(a[:V], b[:V])
+
+
+@pytest.mark.parametrize("n_points", [0, 1, 47])
+def test_headline_frame_degenerate_clouds(pkg, cfgs, n_points):
+    """The bench's frame kind on an empty cloud, a single point and a single pillar's worth of points: no fault, counts right,
+    every output row beyond the pillar count zero, and (for n > 0) finite features equal to the separate-launch form's."""
+    capi = importlib.import_module("dsvt-ai-trt_b200.capi")
+    pipeline = importlib.import_module("dsvt-ai-trt_b200.pipeline")
+    cfg = cfgs.REFERENCE
+    w = pipeline.FrameWeights(cfg, seed=9)
+    cloud = np.zeros((n_points, 4), np.float32)
+    if n_points:
+        rng = np.random.default_rng(n_points)
+        cloud[:, :2] = 10.0 + (rng.random((n_points, 2)) * (0.2 if n_points > 1 else 0.0)).astype(np.float32)   # one pillar
+        cloud[:, 2] = -1.0
+        cloud[:, 3] = 0.5
+    frames = {}
+    for ffn in ("kernel", "epilogue"):
+        fr = pipeline.HotPathFrame(cfg, w, precision=capi.DSVT_ATTN_FP32_TC, seed=2, ffn=ffn, backbone=True)
+        fr.load_points(cloud)
+        fr.run()
+        torch.cuda.synchronize()
+        frames[ffn] = fr
+    one, sep = frames["kernel"], frames["epilogue"]
+    V = int(one.vox.pillar_num[0])
+    assert V == int(sep.vox.pillar_num[0]) and V == (1 if n_points else 0)
+    assert int(one.vox.point_num[0]) == n_points
+    assert bool((one.max_voxel[-1][V:] == 0).all()) and bool((one.final[V:] == 0).all())
+    if V:
+        assert torch.isfinite(one.final[:V]).all()
+        assert torch.equal(one.max_voxel[-1][:V], sep.max_voxel[-1][:V])
+        assert (one.final[:V] - sep.final[:V]).abs().max().item() <= 1e-5
+    assert bool((one.bev.reshape(-1, cfg.channel_num).abs().sum(1) > 0).sum() == V) or V == 0
