@@ -305,8 +305,14 @@ def plugin_breakdown(slot, cfg, peaks, reps=5):
     torch.cuda.empty_cache()
     first, second = g["pos"][0][0]
     us = timed(lambda: capi.pos_embed_mlp(first, second, f.wp[0].coors_in_win_x_y[0], Vt, out=f.pos_out[0][0], zero_tails=0))
-    res["pos_embed_mlp"] = {"us": us, "bytes": 4 * V * (2 + C), "flops": 2 * V * C * C, "calls_per_frame": 8, "scope": "next#4",
-                            "note": "Linear(2->192)+BN+ReLU generated inside the Linear(192->192) GEMM's producers"}
+    res["pos_embed_mlp"] = {"us": us, "bytes": 4 * V * (2 + C), "flops": 2 * V * C * C, "calls_per_frame": 0, "scope": "next#4",
+                            "note": "Linear(2->192)+BN+ReLU generated inside the Linear(192->192) GEMM's producers; one MLP per launch"}
+    pairs = [(b_, e_) for b_ in range(cfg.num_blocks) for e_ in (0, 1)]
+    us = timed(lambda: capi.pos_embed_mlp_batch([g["pos"][b_][e_][0] for b_, e_ in pairs], [g["pos"][b_][e_][1] for b_, e_ in pairs],
+                                                [f.wp[e_].coors_in_win_x_y[0] for b_, e_ in pairs], Vt,
+                                                [f.pos_out[b_][e_] for b_, e_ in pairs], zero_tails=0))
+    res["pos_embed_mlp_x8"] = {"us": us, "bytes": 8 * 4 * V * (2 + C), "flops": 8 * 2 * V * C * C, "calls_per_frame": 1,
+                               "scope": "next#4", "note": "the frame's eight position-embedding MLPs as the roles of ONE launch"}
     us = timed(lambda: capi.map2bev(f.final, vox.coords[0], Vt, cfg.grid_x, cfg.grid_y, out=f.bev))
     res["map2bev"] = {"us": us, "bytes": 2 * 4 * C * V + 16 * V, "calls_per_frame": 1, "scope": "next",
                       "contract_bytes": 4 * C * (cfg.grid_x * cfg.grid_y + V)}

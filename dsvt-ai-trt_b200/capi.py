@@ -568,6 +568,22 @@ def pos_embed_mlp(first, second, x2, rows, out=None, zero_tails=1):
     return out
 
 
+def pos_embed_mlp_batch(firsts, seconds, x2s, rows, outs, zero_tails=1):
+    """n (<= 8) position-embedding MLPs in one launch (dsvt_pos_embed_mlp_batch_launch): lists of SmallLinear(2 -> 192),
+    Linear(192 -> 192), coordinate tensors [max_rows, 2] and output tensors [max_rows, 192]."""
+    n = len(firsts)
+    assert n == len(seconds) == len(x2s) == len(outs) and 1 <= n <= 8
+    for t in x2s:
+        _need(t, torch.float32, "x2")
+    _need(rows, torch.int32, "rows")
+    arr = lambda vals: (c_void_p * n)(*vals)
+    _check(_lib().dsvt_pos_embed_mlp_batch_launch(arr([f.handle for f in firsts]), arr([s_.handle for s_ in seconds]),
+                                                  arr([t.data_ptr() for t in x2s]), c_int32(n), _ptr(rows),
+                                                  c_int32(x2s[0].shape[-2]), arr([o.data_ptr() for o in outs]),
+                                                  c_int32(zero_tails), _stream()), "dsvt_pos_embed_mlp_batch_launch")
+    return outs
+
+
 def vfe_fused(pfn0, pfn1, point_features, point_index_in_voxel, voxel_num, point_num, out=None, workspace=None, zero_tails=1):
     """The pillar feature net in one kernel (dsvt_vfe_fused_launch): pfn0 = SmallLinear(10 -> 96), pfn1 = Linear(192 -> 192,
     FP32_TC); point_features [max_points, 10], point_index_in_voxel [max_pillars, npv] -> voxel features [max_pillars, 192]."""

@@ -112,7 +112,8 @@ struct GemmRole {
                             //   reference scatters the set features into a zero-filled tensor (mapSetFeature2voxel.cu:312),
                             //   so a voxel dropped by a capacity guard must not receive bias + W * (stale workspace row)
 };
-struct GemmRoles { GemmRole r[3]; };
+constexpr int kMaxRoles = 8;                         // roles (blockIdx.y) of one launch: Q / K / V, the column blocks of a wide layer,
+struct GemmRoles { GemmRole r[kMaxRoles]; };         // or the eight position-embedding MLPs of a frame
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
@@ -1079,6 +1080,31 @@ int linear_gen_launch(const void* blob, float out_mul, bool split, const float* 
     g.gen_x = x2; g.gen_blob = small_blob;
     roles.r[1] = roles.r[2] = g;
     return launch_gemm(roles, 1, rows_dev, 0, max_rows, 1, zero_tails, 1, split, st);
+}
+
+// n (<= 8) position-embedding MLPs in ONE launch (role = MLP): the eight MLPs of a frame depend on the window coordinates only,
+// and eight launches of 241 CTAs each leave a fifth of the 296 CTA slots of every wave empty.
+int linear_gen_batch_launch(int n, const void* const* blobs, const float* out_muls, bool split, const float* const* x2s,
+                            const float* const* small_blobs, const int* rows_dev, int max_rows, float* const* ys, int zero_tails,
+                            cudaStream_t st)
+{
+    GemmRoles roles;
+    for (int r = 0; r < n; ++r) {
+        const uint8_t* img = static_cast<const uint8_t*>(blobs[r]);
+        GemmRole& g = roles.r[r];
+        g.a0 = x2s[r]; g.a1 = nullptr; g.lda = kC;          // a0 is not read in this mode
+        g.a0b = nullptr; g.ksplit = 0; g.ldb = 0; g.cover = nullptr; g.cover_stride = 0;
+        g.wimg = img;
+        g.bias = reinterpret_cast<const float*>(img + (size_t) kWRoleBytes);
+        g.out = ys[r]; g.ld_out = kC; g.col0 = 0;
+        g.out_mul = out_muls[r]; g.post_mul = 1.0f;
+        g.plan = nullptr; g.plan_stride = 0; g.pad_hi = 0;
+        g.accumulate = 0; g.act = 0; g.add_src = nullptr; g.ld_add = 0;
+        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f;
+        for (int s = 0; s < 3; ++s) { g.ln_res[s] = nullptr; g.ln_gamma[s] = nullptr; g.ln_beta[s] = nullptr; }
+        g.gen_x = x2s[r]; g.gen_blob = small_blobs[r];
+    }
+    return launch_gemm(roles, n, rows_dev, 0, max_rows, 1, zero_tails, 1, split, st);
 }
 
 // [*, K] -> [*, 192] layer (K = 192 or 384) followed by a chain of up to three (residual add + LayerNorm) stages, in ONE

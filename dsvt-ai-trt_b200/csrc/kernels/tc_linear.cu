@@ -146,6 +146,9 @@ int linear_gen_launch(const void* blob, float out_mul, bool split, const float* 
 int linear_ln_launch(const void* blob, int K, float out_mul, bool split, const float* x, const int* rows_dev, int max_rows,
                      int n_ln, const float* const* res, const float* const* gamma, const float* const* beta, float eps,
                      float* y, int zero_tails, cudaStream_t st);
+int linear_gen_batch_launch(int n, const void* const* blobs, const float* out_muls, bool split, const float* const* x2s,
+                            const float* const* small_blobs, const int* rows_dev, int max_rows, float* const* ys, int zero_tails,
+                            cudaStream_t st);
 void* ffn_w1_pieces_prepare(const float* W);
 size_t vfe_fused_workspace(int max_points, int npv);
 int vfe_fused_launch(const float* pfn0_blob, const void* blob1, float out_mul1, const float* point_features, const int* piv,
@@ -362,6 +365,28 @@ extern "C" int dsvt_pos_embed_mlp_launch(const dsvt_small_linear* first, const d
     DSVT_CHECK_ARG(!(((uintptr_t) x2 & 7) | ((uintptr_t) y & 15)), "alignment (x2 8 B, y 16 B)");
     return dsvt::linear_gen_launch(second->split_blob, second->out_mul, second->precision == DSVT_ATTN_FP32_TC, x2, first->blob,
                                    rows, max_rows, y, zero_tails, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dsvt_pos_embed_mlp_batch_launch(const dsvt_small_linear* const* firsts, const dsvt_linear_weights* const* seconds,
+                                               const float* const* x2s, int32_t n, const int32_t* rows, int32_t max_rows,
+                                               float* const* ys, int32_t zero_tails, dsvt_stream_t stream)
+{
+    DSVT_CHECK_ARG(firsts && seconds && x2s && ys && rows && max_rows >= 1, "NULL argument");
+    DSVT_CHECK_ARG(n >= 1 && n <= 8, "1..8 MLPs per launch");
+    const void* blobs[8];
+    const float* small_blobs[8];
+    float out_muls[8];
+    for (int i = 0; i < n; ++i) {
+        DSVT_CHECK_ARG(firsts[i] && seconds[i] && x2s[i] && ys[i], "NULL entry");
+        DSVT_CHECK_ARG(firsts[i]->K == 2 && firsts[i]->N == 192, "first layer: Linear(2 -> 192) (+ folded BatchNorm, ReLU)");
+        DSVT_CHECK_ARG(seconds[i]->split_blob != nullptr && seconds[i]->N == 192 && seconds[i]->K == 192 &&
+                       seconds[i]->precision == seconds[0]->precision,
+                       "second layer: Linear(192 -> 192) created with DSVT_ATTN_FP32_TC / DSVT_ATTN_FP16_GEMM (one precision per launch)");
+        DSVT_CHECK_ARG(!(((uintptr_t) x2s[i] & 7) | ((uintptr_t) ys[i] & 15)), "alignment (x2 8 B, y 16 B)");
+        blobs[i] = seconds[i]->split_blob; small_blobs[i] = firsts[i]->blob; out_muls[i] = seconds[i]->out_mul;
+    }
+    return dsvt::linear_gen_batch_launch(n, blobs, out_muls, seconds[0]->precision == DSVT_ATTN_FP32_TC, x2s, small_blobs, rows,
+                                         max_rows, ys, zero_tails, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" size_t dsvt_vfe_fused_workspace_size(int32_t max_points_num, int32_t max_num_points_per_voxel) {

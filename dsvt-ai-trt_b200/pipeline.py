@@ -315,7 +315,14 @@ class HotPathFrame:
         else:
             x = self.max_voxel[-1]                         # VFE output: per-pillar max of PFN layer 1 (:589, output 1)
             pos = self.pos_out
-            for blk in range(0 if "pos" in skip else cfg.num_blocks):   # pos_embed[blk][i] from the shift-i window coordinates (:603-637)
+            if self.ffn == "kernel" and "pos" not in skip:   # all MLPs of the frame in one launch (they depend on the coordinates only)
+                pairs = [(blk, enc) for blk in range(cfg.num_blocks) for enc in (0, 1)]
+                for i0 in range(0, len(pairs), 8):
+                    grp = pairs[i0:i0 + 8]
+                    capi.pos_embed_mlp_batch([w.glue["pos"][b_][e_][0] for b_, e_ in grp], [w.glue["pos"][b_][e_][1] for b_, e_ in grp],
+                                             [self.wp[e_].coors_in_win_x_y[0] for b_, e_ in grp], V,
+                                             [self.pos_out[b_][e_] for b_, e_ in grp], zero_tails=0)
+            for blk in range(0 if ("pos" in skip or self.ffn == "kernel") else cfg.num_blocks):   # pos_embed[blk][i] from the shift-i window coordinates (:603-637)
                 for enc in (0, 1):
                     first, second = w.glue["pos"][blk][enc]
                     if self.ffn in ("epilogue", "kernel"):  # both layers in one kernel: the hidden rows never reach memory

@@ -427,6 +427,11 @@ int dsvt_vfe_fused_launch(const dsvt_small_linear* pfn0, const dsvt_linear_weigh
  */
 int dsvt_pos_embed_mlp_launch(const dsvt_small_linear* first, const dsvt_linear_weights* second, const float* x2,
                               const int32_t* rows, int32_t max_rows, float* y, int32_t zero_tails, dsvt_stream_t stream);
+/* n (<= 8) position-embedding MLPs in ONE launch -- the eight MLPs of a frame (src/dsvt-ai-trt.cpp:603-637) depend on the window
+ * coordinates only.  Arrays of n handles / device pointers (host arrays); results = n calls of dsvt_pos_embed_mlp_launch. */
+int dsvt_pos_embed_mlp_batch_launch(const dsvt_small_linear* const* firsts, const dsvt_linear_weights* const* seconds,
+                                    const float* const* x2s, int32_t n, const int32_t* rows, int32_t max_rows,
+                                    float* const* ys, int32_t zero_tails, dsvt_stream_t stream);
 
 /* ------------------------------------------------------------------------ *
  * (next #3) TorchScatterMaxPlugin::enqueue     plugins/src/torchScatterMax.cu:282-309 (kernel :201-262)

@@ -234,3 +234,24 @@ def test_ffn_fused(n_ln, rows):
         mu = y.mean(1, keepdims=True)
         y = (y - mu) / np.sqrt(((y - mu) ** 2).mean(1, keepdims=True)) * g_.cpu().numpy() + b_.cpu().numpy()
     assert np.abs(got[:rows] - y).max() <= 5e-5
+
+
+def test_pos_embed_mlp_batch_equals_single_launches():
+    """dsvt_pos_embed_mlp_batch_launch (up to eight MLPs as the roles of one launch) against one launch per MLP: bit for bit."""
+    capi = importlib.import_module("dsvt-ai-trt_b200.capi")
+    rng = np.random.default_rng(5)
+    cap, rows, n = 2000, 1500, 8
+    firsts, seconds, xs = [], [], []
+    for i in range(n):
+        firsts.append(capi.SmallLinear((rng.standard_normal((192, 2)) * 0.5).astype(np.float32),
+                                       (1 + 0.1 * rng.standard_normal(192)).astype(np.float32), (0.1 * rng.standard_normal(192)).astype(np.float32)))
+        seconds.append(capi.Linear((rng.standard_normal((192, 192)) * 0.06).astype(np.float32), (rng.standard_normal(192) * 0.05).astype(np.float32),
+                                   precision=capi.DSVT_ATTN_FP32_TC))
+        xs.append(torch.from_numpy(rng.integers(0, 24, size=(cap, 2)).astype(np.float32)).cuda())
+    nrows = torch.tensor([rows], dtype=torch.int32, device="cuda")
+    outs = [torch.full((cap, 192), float("nan"), device="cuda") for _ in range(n)]
+    capi.pos_embed_mlp_batch(firsts, seconds, xs, nrows, outs, zero_tails=1)
+    torch.cuda.synchronize()
+    for i in range(n):
+        one = capi.pos_embed_mlp(firsts[i], seconds[i], xs[i], nrows, zero_tails=1)
+        assert torch.equal(one, outs[i]) and bool((outs[i][rows:] == 0).all())

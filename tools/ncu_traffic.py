@@ -41,7 +41,8 @@ def main(rep, table, js):
         k = None
         if "proj_tile_kernel" in o["name"]:
             gy = int(re.findall(r"\d+", o["grid"])[1]) if o["grid"] else 0
-            if gy == 3: k = "set_attention.qkv_proj_gemm"
+            if gy == 8: k = "pos_embed_mlp_x8"
+            elif gy == 3: k = "set_attention.qkv_proj_gemm"
             elif gy == 2: k = "ffn_linear1_gelu"
             elif o["smem"] > 90e3:
                 k = "set_attention.out_proj_gemm_norm1"       # (the headline frame's only LayerNorm-epilogue tile GEMM)
