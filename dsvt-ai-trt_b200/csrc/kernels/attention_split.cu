@@ -887,6 +887,8 @@ attn_core_kernel(const float* __restrict__ qbuf, const float* __restrict__ kvbuf
     }
 }
 
+#include "qkv_fused.cuh"
+
 template <int S>
 int launch_plan(const dsvt_set_attention_params* p, const int* idx, const float* mask, const int* set_num, int* plan,
                 cudaStream_t st)
@@ -1387,9 +1389,23 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
     }
     // `stages`: bit 0 QKV projection GEMM, bit 1 per-set core, bit 2 out-projection GEMM (all three in normal operation; the
     // instrumented entry point launches them one at a time so that each can be bracketed by CUDA events)
-    if ((stages & 1) &&
-        (rc = launch_gemm(in_roles, 3, voxel_num, 0, p->max_pillars_num, p->max_set_num, 0, p->batch, split, st)) != DSVT_OK)
-        return rc;
+    if (stages & 1) {
+#ifndef DSVT_QKV_TILE_KERNEL
+        if (split) {                               // FP32 configuration: one tile-wide CTA for the three roles (qkv_fused.cuh)
+            QkvArgs qa;
+            qa.x = x; qa.pos = pos; qa.wimg = img; qa.bias = bias;
+            for (int r = 0; r < 3; ++r) qa.out_mul[r] = out_mul[r];
+            qa.q_post_mul = 1.0f / sqrtf((float) (kC / kH));
+            qa.qbuf = qbuf; qa.kvbuf = kvbuf; qa.plan = plan; qa.plan_stride = plan_stride;
+            DSVT_RAISE_SMEM(qkv_fused_kernel, kQSmem);
+            qkv_fused_kernel<<<dim3((p->max_pillars_num + kBM - 1) / kBM, 1, p->batch), kQThreads, kQSmem, st>>>(
+                qa, voxel_num, p->max_pillars_num, p->max_set_num);
+            DSVT_LAUNCH_CHECK();
+        } else
+#endif
+        if ((rc = launch_gemm(in_roles, 3, voxel_num, 0, p->max_pillars_num, p->max_set_num, 0, p->batch, split, st)) != DSVT_OK)
+            return rc;
+    }
     if (stages & 2) switch (p->voxel_num_set) {
         case 24: rc = launch_core<24>(p, qbuf, kvbuf, plan, mask, set_num, o, st); break;
         case 36: rc = launch_core<36>(p, qbuf, kvbuf, plan, mask, set_num, o, st); break;

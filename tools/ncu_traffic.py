@@ -49,6 +49,8 @@ def main(rep, table, js):
             else: k = "linear_single_role(pfn / pos_embed_mlp)"
         elif "attn_core_kernel" in o["name"]: k = "set_attention.attn_core"
         elif "ffn_fused_kernel" in o["name"]: k = "ffn_fused_norm"
+        elif "qkv_fused_kernel" in o["name"]: k = "set_attention.qkv_proj_gemm"
+        elif "vfe_fused_kernel" in o["name"]: k = "vfe_fused"
         o["key"] = k or o["name"]
         keys[o["key"]].append(o)
     with open(table, "w") as f:
