@@ -139,7 +139,11 @@ qkv_fused_kernel(const __grid_constant__ QkvArgs a, const int* __restrict__ voxe
                     const float4 v = scr[sr * 4 + (c4 ^ (sr & 3))];
                     // out_mul is a power of two: the product is exact, so this is one rounding of (acc + bias)
                     const float4 ov = make_float4((v.x * om + bb.x) * pm, (v.y * om + bb.y) * pm, (v.z * om + bb.z) * pm, (v.w * om + bb.w) * pm);
+#ifdef DSVT_EXP_NOSTORE    // experiment: the drain without its stores (ov.x can never be this value)
+                    if (srow_out[i] >= 0 && ov.x == 123456.789f) *reinterpret_cast<float4*>(base + (size_t) srow_out[i] * ld + col + shift) = ov;
+#else
                     if (srow_out[i] >= 0) *reinterpret_cast<float4*>(base + (size_t) srow_out[i] * ld + col + shift) = ov;
+#endif
                 }
                 __syncwarp();
             }
