@@ -888,6 +888,7 @@ attn_core_kernel(const float* __restrict__ qbuf, const float* __restrict__ kvbuf
 }
 
 #include "qkv_fused.cuh"
+#include "pos_fused.cuh"
 
 template <int S>
 int launch_plan(const dsvt_set_attention_params* p, const int* idx, const float* mask, const int* set_num, int* plan,
@@ -1090,6 +1091,20 @@ int linear_gen_batch_launch(int n, const void* const* blobs, const float* out_mu
                             const float* const* small_blobs, const int* rows_dev, int max_rows, float* const* ys, int zero_tails,
                             cudaStream_t st)
 {
+#ifndef DSVT_POS_TILE_KERNEL
+    if (split) {                                   // FP32 configuration: one tile-wide CTA, the MLPs as roles in sequence (pos_fused.cuh)
+        PosArgs a;
+        a.n = n;
+        for (int r = 0; r < n; ++r) {
+            const uint8_t* img = static_cast<const uint8_t*>(blobs[r]);
+            a.r[r] = PosRole{x2s[r], small_blobs[r], img, reinterpret_cast<const float*>(img + (size_t) kWRoleBytes), ys[r], out_muls[r]};
+        }
+        DSVT_RAISE_SMEM(pos_fused_kernel, kPSmem);
+        pos_fused_kernel<<<(max_rows + kBM - 1) / kBM, kQThreads, kPSmem, st>>>(a, rows_dev, max_rows, zero_tails);
+        DSVT_LAUNCH_CHECK();
+        return DSVT_OK;
+    }
+#endif
     GemmRoles roles;
     for (int r = 0; r < n; ++r) {
         const uint8_t* img = static_cast<const uint8_t*>(blobs[r]);
