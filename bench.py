@@ -143,17 +143,18 @@ def max_over_ranks(x, world):
 # ---------------------------------------------------------------------------------------------
 # frame kinds (HotPathFrame keyword arguments); "backbone3d" is the headline
 FRAME_KINDS = {
-    "backbone3d": dict(ffn="kernel", backbone=True),         # every layer of the 3-D backbone; GELU / residual adds / LayerNorms
-                                                             # in the GEMM epilogues, each FFN ONE kernel (hidden rows stay in
-                                                             # tensor memory): 4 kernels per encoder layer
+    "backbone3d": dict(ffn="layer", backbone=True),          # every layer of the 3-D backbone; 3 kernels per encoder layer: QKV
+                                                             # projection, per-set core, then out-projection + norm1 + FFN (hidden
+                                                             # rows in tensor memory) + the LayerNorm chain in ONE kernel
+    "backbone3d_four_kernel_layer": dict(ffn="kernel", backbone=True),   # ... out-projection + norm1 as a kernel of its own
     "backbone3d_two_kernel_ffn": dict(ffn="epilogue", backbone=True),   # ... FFN as FC + GELU, then FC + norms (round-2 mid form)
     "backbone3d_graph": dict(ffn="graph", backbone=True),    # ... in the reference graph's node structure
     "plugin_only": dict(ffn="off", backbone=False),          # plugins only; TensorRT-native layers stood in by fixed tensors
-    "relaxed_tails": dict(ffn="kernel", backbone=True, zero_tails=0),
-    "backbone3d_postprocess": dict(ffn="kernel", backbone=True, head=True),   # + CenterHead post-process graph + GPU NMS
+    "relaxed_tails": dict(ffn="layer", backbone=True, zero_tails=0),
+    "backbone3d_postprocess": dict(ffn="layer", backbone=True, head=True),   # + CenterHead post-process graph + GPU NMS
     # ... with the head maps computed from the frame's own BEV map by a cuDNN stand-in of the 2-D backbone + CenterHead
     # convolutions (library code, random weights): raw points -> boxes after NMS
-    "whole_pipeline": dict(ffn="kernel", backbone=True, head="conv"),
+    "whole_pipeline": dict(ffn="layer", backbone=True, head="conv"),
 }
 
 
@@ -230,7 +231,7 @@ def plugin_breakdown(slot, cfg, peaks, reps=5):
     import torch
     capi = importlib.import_module("dsvt-ai-trt_b200.capi")
     f = slot.frame
-    assert f.backbone and f.ffn == "kernel", "the breakdown describes the headline frame kind"
+    assert f.backbone and f.ffn == "layer", "the breakdown describes the headline frame kind"
     f.run()
     torch.cuda.synchronize()
     V, Pc, P = int(f.vox.pillar_num[0]), int(f.vox.point_num[0]), slot.n
@@ -351,13 +352,27 @@ def plugin_breakdown(slot, cfg, peaks, reps=5):
     us = timed(lambda: fc2.rows_norm(f.gelu_out, Vt, st3, cfg.layer_norm_eps, out=f.src_b))
     res["ffn_linear2_norm3"] = {"us": us, "flops": 2 * C * Fc * V, "bytes": 4 * V * (Fc + 3 * C + C), "calls_per_frame": 0,
                                 "scope": "next#4 + 3 LayerNormPlugins"}
-    # the headline's FFN: FC 192->384 + GELU + FC 384->192 + the LayerNorm chain in ONE kernel (dsvt_ffn_fused_launch); bytes =
-    # x in, residual rows in, y out -- the 384-wide hidden rows never reach memory
+    # the FFN alone: FC 192->384 + GELU + FC 384->192 + the LayerNorm chain in ONE kernel (dsvt_ffn_fused_launch; the
+    # backbone3d_four_kernel_layer leg); bytes = x in, residual rows in, y out -- the 384-wide hidden rows never reach memory
     for n_st, st in ((2, st2), (3, st3)):
         us = timed(lambda: fc1.ffn_norm(fc2, f.src, Vt, st, cfg.layer_norm_eps, out=f.src_b))
         res[f"ffn_fused_norm{n_st}"] = {"us": us, "flops": 4 * C * Fc * V, "mma_flops_issued": 3 * 4 * C * Fc * V,
-                                        "bytes": 4 * V * (C + n_st * C + C), "calls_per_frame": 4,
+                                        "bytes": 4 * V * (C + n_st * C + C), "calls_per_frame": 0,
                                         "scope": f"next#4 (both FFN linears + GeluPlugin) + {n_st} LayerNormPlugins"}
+    # the headline's layer tail: attention out-projection + norm1 + FFN + the LayerNorm chain in ONE kernel
+    # (dsvt_attention_tail_ffn_launch), timed on the workspace a QKV + core launch pair has just filled; bytes = core rows in,
+    # x in, src out, y out (+ the block input for the third norm)
+    gs0, plan0 = f.gs[0], f.plans[(0, 0)]
+    capi.set_attention_fused(w.attn[0], x, f.pos_out[0][0], gs0.global_index_in_set[0], gs0.mask_expand_0[0], gs0.set_num, Vt, axis=0,
+                             out=f.src_b, precision=f.precision, workspace=f.attn_ws, plan=plan0, stages=3)
+    for n_st, st in ((2, st2), (3, st3)):
+        us = timed(lambda: capi.attention_tail_ffn(w.attn[0], fc1, fc2, x, gs0.global_index_in_set[0], Vt, 0, plan0, f.attn_ws,
+                                                   (w.gamma[0], w.beta[0], cfg.layer_norm_eps), st, cfg.layer_norm_eps,
+                                                   src=f.src, out=f.src_b))
+        res[f"attention_tail_ffn_norm{n_st}"] = {
+            "us": us, "flops": 2 * C * C * V + 4 * C * Fc * V, "mma_flops_issued": 3 * (2 * C * C * V + 4 * C * Fc * V),
+            "bytes": 4 * V * C * (4 + (n_st - 2)), "calls_per_frame": 4,
+            "scope": f"a3 out-projection + LayerNormPlugin (norm1) + next#4 (FFN) + {n_st} LayerNormPlugins"}
     pipeline_prec = f.precision in (capi.DSVT_ATTN_FP32_TC, capi.DSVT_ATTN_FP16_GEMM)
     for i in (0, 1):
         gs = f.gs[i]
@@ -366,25 +381,30 @@ def plugin_breakdown(slot, cfg, peaks, reps=5):
             w.attn[i], x, f.pos_out[i][0], gs.global_index_in_set[0], gs.mask_expand_0[0], gs.set_num, Vt, axis=0,
             out=f.src_b, precision=f.precision, workspace=f.attn_ws, plan=plan,
             norm=(x, w.gamma[0], w.beta[0], cfg.layer_norm_eps), stages=stages)
-        us = timed(call)
         if plan is not None:      # one plan per (partition, axis) serves two layers: 4 plan builds per frame
             pus = timed(lambda: capi.set_attention_plan(gs.global_index_in_set[0], gs.mask_expand_0[0], gs.set_num, 0,
                                                         cfg.max_pillars_num, cfg.num_heads, cfg.channel_num, out=plan))
             res[f"set_attention_plan_{i}"] = {"us": pus, "bytes": NS[i] * (S * 4 + 8 * S * 4) + 4 * V + NS[i] * S * 8,
                                               "calls_per_frame": 2}
         flops = 11612160 * NS[i] if S == 36 else None
-        res[f"set_attention_{i}"] = {"us": us, "flops": flops, "bytes": 83088 * NS[i] + 590000, "calls_per_frame": 4}
         if pipeline_prec and plan is not None:
-            # the three kernels of the pipeline, one launch each (dsvt_set_attention_fused_stages_launch), CUDA events around
+            # the headline frame launches the QKV projection and the per-set core here; the out-projection (+ norm1) runs inside
+            # attention_tail_ffn_norm*.  One launch each (dsvt_set_attention_fused_stages_launch), CUDA events around
             a, b, c = timed(lambda: call(1)), timed(lambda: call(2)), timed(lambda: call(4))
             split = 3 if f.precision == capi.DSVT_ATTN_FP32_TC else 1
+            res[f"set_attention_{i}"] = {"us": a + b, "flops": None if flops is None else flops - 2 * C * C * V,
+                                         "bytes": 83088 * NS[i] + 590000, "calls_per_frame": 4,
+                                         "note": "QKV projection + per-set core (the out-projection is part of attention_tail_ffn_norm*)"}
             res[f"set_attention_{i}"]["kernels"] = {
                 "qkv_proj_gemm": {"us": round(a, 2), "flops": 2 * 3 * C * C * V, "mma_flops_issued": split * 2 * 3 * C * C * V,
                                   "bytes": 4 * V * (2 * C + 3 * C) + 3 * 2 * split * 2 * C * C},
                 "attn_core": {"us": round(b, 2), "bytes": 4 * V * (3 * C + C) + NS[i] * (S * 4 + 8 * S * 4),
-                              "flops": None},
-                "out_proj_gemm_norm1": {"us": round(c, 2), "flops": 2 * C * C * V, "mma_flops_issued": split * 2 * C * C * V,
-                                        "bytes": 4 * V * 3 * C + 2 * split * 2 * C * C}}
+                              "flops": None}}
+            res[f"set_attention_out_proj_norm1_{i}"] = {
+                "us": c, "flops": 2 * C * C * V, "mma_flops_issued": split * 2 * C * C * V, "bytes": 4 * V * 3 * C + 2 * split * 2 * C * C,
+                "calls_per_frame": 0, "note": "out-projection + norm1 as a launch of its own (backbone3d_four_kernel_layer leg)"}
+        else:
+            res[f"set_attention_{i}"] = {"us": timed(call), "flops": flops, "bytes": 83088 * NS[i] + 590000, "calls_per_frame": 4}
     for k, r in res.items():
         if r.get("bytes"):
             r["gbs"] = r["bytes"] / r["us"] * 1e-3
@@ -637,6 +657,9 @@ def _main():
         legs["plugin_only"] = leg("plugin_only", precision,
                                   "round 1's headline frame: the reference's ten plugins + the fused set attention; the TensorRT-"
                                   "native layers (PFN, position embedding, FFN linears) are NOT executed, fixed tensors stand in")
+        legs["backbone3d_four_kernel_layer"] = leg("backbone3d_four_kernel_layer", precision,
+                                                   "the headline's data flow with the attention's out-projection + norm1 as a kernel "
+                                                   "of its own in front of the fused FFN kernel (4 kernels per encoder layer)")
         legs["backbone3d_two_kernel_ffn"] = leg("backbone3d_two_kernel_ffn", precision,
                                                 "the headline's data flow with every FFN as two kernels (FC + GELU epilogue, then FC + "
                                                 "LayerNorm-chain epilogue): the 384-wide hidden rows go through memory")
@@ -726,6 +749,14 @@ def roofline_block(plugins, frame_us, peaks):
                 a["calls_per_frame"] += c
         else:
             kernels[k] = r
+    # the layer-tail kernel runs with two or three LayerNorm stages behind the FFN: ONE kernel, call-weighted mean of the two
+    for base in ("attention_tail_ffn", "ffn_fused"):
+        parts = [kernels.pop(f"{base}_norm{n}") for n in (2, 3) if f"{base}_norm{n}" in kernels]
+        if parts:
+            c = sum(p_["calls_per_frame"] for p_ in parts)
+            kernels[base] = {"calls_per_frame": c,
+                             **{f_: sum((p_.get(f_) or 0) * p_["calls_per_frame"] for p_ in parts) / c
+                                for f_ in ("us", "bytes", "flops", "mma_flops_issued")}}
     dom_key = max(kernels, key=lambda k: kernels[k]["us"] * kernels[k]["calls_per_frame"])
     dom = kernels[dom_key]
     # which roof bounds it: arithmetic intensity of the work the kernel actually issues (flops / algorithmic byte) against

@@ -584,6 +584,30 @@ def pos_embed_mlp_batch(firsts, seconds, x2s, rows, outs, zero_tails=1):
     return outs
 
 
+def attention_tail_ffn(weights, fc1, fc2, x, global_index_in_set, voxel_num, axis, plan, workspace, norm1, stages, eps=0.0,
+                       src=None, out=None, zero_tails=1):
+    """The tail of an encoder layer in one kernel (dsvt_attention_tail_ffn_launch): out-projection of the attention whose QKV
+    projection + core have just run (set_attention_fused(..., stages=3) with the same weights / plan / workspace),
+    norm1 = (gamma, beta, eps) of LayerNorm(attention + x), the FFN fc1 -> GELU -> fc2 and the LayerNorm chain `stages`
+    (the first stage's residual is the `src` this call writes)."""
+    _need(x, torch.float32, "x")
+    max_pillars, C = x.shape[-2], x.shape[-1]
+    max_sets, S = global_index_in_set.shape[-2], global_index_in_set.shape[-1]
+    p = AttnParams(1, max_sets, S, C, weights.heads, max_pillars, axis, DSVT_ATTN_FP32_TC, zero_tails)
+    src = torch.empty_like(x) if src is None else src
+    out = torch.empty_like(x) if out is None else out
+    arr = (LnStage * len(stages))()
+    for i, (r, g, b) in enumerate(stages):
+        arr[i] = LnStage(r.data_ptr() if r is not None else None, g.data_ptr(), b.data_ptr())
+    g1, b1, e1 = norm1
+    _check(_lib().dsvt_attention_tail_ffn_launch(ctypes.byref(p), c_void_p(weights.handle), _ptr(plan), _ptr(workspace),
+                                                 c_size_t(workspace.numel()), _ptr(voxel_num), _ptr(x), _ptr(g1), _ptr(b1),
+                                                 c_float(e1), c_void_p(fc1.handle), c_void_p(fc2.handle), arr,
+                                                 c_int32(len(stages)), c_float(eps), _ptr(src), _ptr(out), _stream()),
+           "dsvt_attention_tail_ffn_launch")
+    return out
+
+
 def vfe_fused(pfn0, pfn1, point_features, point_index_in_voxel, voxel_num, point_num, out=None, workspace=None, zero_tails=1):
     """The pillar feature net in one kernel (dsvt_vfe_fused_launch): pfn0 = SmallLinear(10 -> 96), pfn1 = Linear(192 -> 192,
     FP32_TC); point_features [max_points, 10], point_index_in_voxel [max_pillars, npv] -> voxel features [max_pillars, 192]."""

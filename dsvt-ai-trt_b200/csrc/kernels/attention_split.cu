@@ -107,6 +107,8 @@ struct GemmRole {
     const float* ln_gamma[3];
     const float* ln_beta[3];
     float ln_eps;
+    int ln_res0_written_here;   // 1: ln_res[0] was written by THIS kernel (the fused out-projection + FFN form): read it through L2
+                                //    (ld.global.cg), not through the non-coherent read-only path
     const int* cover;       // optional voxel -> (set, token) map of the attention plan (per-batch stride cover_stride ints):
     size_t cover_stride;    //   rows whose entry is negative belong to no set and are written as exact zeros -- the
                             //   reference scatters the set features into a zero-filled tensor (mapSetFeature2voxel.cu:312),
@@ -241,8 +243,14 @@ __device__ __forceinline__ void ln_chain_epilogue(const GemmRole& g, float* tile
             const float* base = n < total ? g.ln_res[st] : nullptr;
             if (base != nullptr && grow < V) {
                 const float4* rp = reinterpret_cast<const float4*>(base + ((size_t) b * max_pillars + grow) * kC);
+                if (st == 0 && g.ln_res0_written_here) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) d[k] = ldg_stream4(rp + k * 16 + sub);
+                    for (int k = 0; k < 3; ++k)
+                        asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(d[k].x), "=f"(d[k].y), "=f"(d[k].z), "=f"(d[k].w) : "l"(rp + k * 16 + sub));
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) d[k] = ldg_stream4(rp + k * 16 + sub);
+                }
             } else {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) d[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1014,7 +1022,7 @@ int linear_split_launch(const void* blob, int N, int K, float out_mul, bool spli
             for (int r = 0; r < 3; ++r) {
                 const int i = i0 + (r < n_roles ? r : 0);
                 GemmRole& g = roles.r[r];
-                g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f; g.gen_x = nullptr; g.gen_blob = nullptr;
+                g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f; g.ln_res0_written_here = 0; g.gen_x = nullptr; g.gen_blob = nullptr;
                 g.a0 = x + (size_t) j * kC; g.a1 = nullptr; g.lda = x_hi ? k_split : K;
                 g.a0b = x_hi; g.ksplit = x_hi ? k_split : 0; g.ldb = x_hi ? K - k_split : 0;
                 g.add_src = nullptr; g.ld_add = 0; g.cover = nullptr; g.cover_stride = 0;
@@ -1048,7 +1056,7 @@ int linear_split_k_launch(const void* blob, int N, int K, float out_mul, bool sp
     for (int r = 0; r < 3; ++r) {
         const int j = r < kb ? r : 0;
         GemmRole& g = roles.r[r];
-        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f; g.gen_x = nullptr; g.gen_blob = nullptr;
+        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f; g.ln_res0_written_here = 0; g.gen_x = nullptr; g.gen_blob = nullptr;
         g.a0 = x + (size_t) j * kC; g.a1 = nullptr; g.lda = K;
         g.a0b = nullptr; g.ksplit = 0; g.ldb = 0; g.cover = nullptr; g.cover_stride = 0;
         g.wimg = img + (size_t) j * kWRoleBytes;
@@ -1078,7 +1086,7 @@ int linear_gen_launch(const void* blob, float out_mul, bool split, const float* 
     g.out_mul = out_mul; g.post_mul = 1.0f;
     g.plan = nullptr; g.plan_stride = 0; g.pad_hi = 0;
     g.accumulate = 0; g.act = 0; g.add_src = nullptr; g.ld_add = 0;
-    g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f;
+    g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f; g.ln_res0_written_here = 0;
     for (int s = 0; s < 3; ++s) { g.ln_res[s] = nullptr; g.ln_gamma[s] = nullptr; g.ln_beta[s] = nullptr; }
     g.gen_x = x2; g.gen_blob = small_blob;
     roles.r[1] = roles.r[2] = g;
@@ -1117,7 +1125,7 @@ int linear_gen_batch_launch(int n, const void* const* blobs, const float* out_mu
         g.out_mul = out_muls[r]; g.post_mul = 1.0f;
         g.plan = nullptr; g.plan_stride = 0; g.pad_hi = 0;
         g.accumulate = 0; g.act = 0; g.add_src = nullptr; g.ld_add = 0;
-        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f;
+        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f; g.ln_res0_written_here = 0;
         for (int s = 0; s < 3; ++s) { g.ln_res[s] = nullptr; g.ln_gamma[s] = nullptr; g.ln_beta[s] = nullptr; }
         g.gen_x = x2s[r]; g.gen_blob = small_blobs[r];
     }
@@ -1142,7 +1150,7 @@ int linear_ln_launch(const void* blob, int K, float out_mul, bool split, const f
     g.out_mul = out_mul; g.post_mul = 1.0f;
     g.plan = nullptr; g.plan_stride = 0; g.pad_hi = 0;
     g.accumulate = 0; g.act = 0; g.add_src = nullptr; g.ld_add = 0;
-    g.kchunks = kb * kNumK; g.n_ln = n_ln; g.ln_eps = eps; g.gen_x = nullptr; g.gen_blob = nullptr;
+    g.kchunks = kb * kNumK; g.n_ln = n_ln; g.ln_eps = eps; g.ln_res0_written_here = 0; g.gen_x = nullptr; g.gen_blob = nullptr;
     for (int s = 0; s < 3; ++s) {
         g.ln_res[s] = s < n_ln ? res[s] : nullptr;
         g.ln_gamma[s] = s < n_ln ? gamma[s] : nullptr;
@@ -1182,9 +1190,14 @@ void* ffn_w1_pieces_prepare(const float* W) {
 }
 
 // blob1 / pieces1: the 192 -> 384 layer (its bias sits behind the two block images), blob2: the 384 -> 192 layer
-int ffn_fused_launch(const void* blob1, const void* pieces1, float out_mul1, const void* blob2, float out_mul2, const float* x,
-                     const int* rows_dev, int max_rows, int n_ln, const float* const* res, const float* const* gamma,
-                     const float* const* beta, float eps, float* y, int zero_tails, cudaStream_t st)
+struct FfnOutProj {            // the attention tail folded in front of the FFN (attn_ffn_fused_launch); all null / 0: plain FFN
+    const float* o; const uint8_t* wo_img; const float* bias_o; float out_mul_o; const int* cover;
+    const float* res1; const float* gamma1; const float* beta1; float eps1; float* src_out;
+};
+static int ffn_fused_launch_impl(const void* blob1, const void* pieces1, float out_mul1, const void* blob2, float out_mul2,
+                                 const float* x, const FfnOutProj* op, const int* rows_dev, int max_rows, int n_ln,
+                                 const float* const* res, const float* const* gamma, const float* const* beta, float eps, float* y,
+                                 int zero_tails, cudaStream_t st)
 {
     const uint8_t* img2 = static_cast<const uint8_t*>(blob2);
     FfnArgs a;
@@ -1197,7 +1210,7 @@ int ffn_fused_launch(const void* blob1, const void* pieces1, float out_mul1, con
     g.out_mul = out_mul2; g.post_mul = 1.0f;
     g.plan = nullptr; g.plan_stride = 0; g.pad_hi = 0;
     g.accumulate = 0; g.act = 0; g.add_src = nullptr; g.ld_add = 0;
-    g.kchunks = 2 * kNumK; g.n_ln = n_ln; g.ln_eps = eps; g.gen_x = nullptr; g.gen_blob = nullptr;
+    g.kchunks = 2 * kNumK; g.n_ln = n_ln; g.ln_eps = eps; g.ln_res0_written_here = op ? 1 : 0; g.gen_x = nullptr; g.gen_blob = nullptr;
     for (int s = 0; s < 3; ++s) {
         g.ln_res[s] = s < n_ln ? res[s] : nullptr;
         g.ln_gamma[s] = s < n_ln ? gamma[s] : nullptr;
@@ -1206,12 +1219,30 @@ int ffn_fused_launch(const void* blob1, const void* pieces1, float out_mul1, con
     a.w1_img = static_cast<const uint8_t*>(pieces1);
     a.bias1 = reinterpret_cast<const float*>(static_cast<const uint8_t*>(blob1) + (size_t) 2 * kWRoleBytes);
     a.out_mul1 = out_mul1;
-    DSVT_RAISE_SMEM(ffn_fused_kernel, kFSmemTotal);
+    a.o = nullptr; a.wo_img = nullptr; a.bias_o = nullptr; a.out_mul_o = 1.0f; a.cover = nullptr;
+    a.res1 = nullptr; a.gamma1 = nullptr; a.beta1 = nullptr; a.eps1 = 0.f; a.src_out = nullptr;
     const dim3 grid((max_rows + kBM - 1) / kBM, 1, 1);
-    ffn_fused_kernel<<<grid, kFThreads, kFSmemTotal, st>>>(a, rows_dev, max_rows, zero_tails);
+    if (op) {
+        a.o = op->o; a.wo_img = op->wo_img; a.bias_o = op->bias_o; a.out_mul_o = op->out_mul_o; a.cover = op->cover;
+        a.res1 = op->res1; a.gamma1 = op->gamma1; a.beta1 = op->beta1; a.eps1 = op->eps1; a.src_out = op->src_out;
+        g.ln_res[0] = op->src_out;                  // norm2's residual = the src rows this kernel writes
+        DSVT_RAISE_SMEM(ffn_fused_kernel<true>, kFSmemTotal);
+        ffn_fused_kernel<true><<<grid, kFThreads, kFSmemTotal, st>>>(a, rows_dev, max_rows, zero_tails);
+    } else {
+        DSVT_RAISE_SMEM(ffn_fused_kernel<false>, kFSmemTotal);
+        ffn_fused_kernel<false><<<grid, kFThreads, kFSmemTotal, st>>>(a, rows_dev, max_rows, zero_tails);
+    }
     DSVT_LAUNCH_CHECK();
     return DSVT_OK;
 }
+int ffn_fused_launch(const void* blob1, const void* pieces1, float out_mul1, const void* blob2, float out_mul2, const float* x,
+                     const int* rows_dev, int max_rows, int n_ln, const float* const* res, const float* const* gamma,
+                     const float* const* beta, float eps, float* y, int zero_tails, cudaStream_t st)
+{
+    return ffn_fused_launch_impl(blob1, pieces1, out_mul1, blob2, out_mul2, x, nullptr, rows_dev, max_rows, n_ln, res, gamma, beta,
+                                 eps, y, zero_tails, st);
+}
+
 
 // ---- fused VFE (vfe_fused.cuh) ------------------------------------------------------------------------------------
 size_t vfe_fused_workspace(int max_points, int npv) {
@@ -1365,7 +1396,7 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
     GemmRoles in_roles, out_roles;
     for (int r = 0; r < 3; ++r) {
         GemmRole& g = in_roles.r[r];
-        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f; g.gen_x = nullptr; g.gen_blob = nullptr;
+        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f; g.ln_res0_written_here = 0; g.gen_x = nullptr; g.gen_blob = nullptr;
         g.a0 = x;
         g.a1 = r < 2 ? pos : nullptr;
         g.wimg = img + (size_t) r * kWRoleBytes;
@@ -1383,7 +1414,7 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
     }
     {
         GemmRole& g = out_roles.r[0];
-        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f; g.gen_x = nullptr; g.gen_blob = nullptr;
+        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f; g.ln_res0_written_here = 0; g.gen_x = nullptr; g.gen_blob = nullptr;
         g.a0 = o; g.a1 = nullptr;
         g.wimg = img + (size_t) 3 * kWRoleBytes;
         g.bias = bias + 3 * kC;
@@ -1396,7 +1427,7 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
         g.cover = plan_view(const_cast<int*>(plan), p->max_set_num, p->max_pillars_num).vox_su;   // voxels in no set -> 0
         g.cover_stride = plan_stride;
         if (norm) {                                // out = LayerNorm(attention + residual): norm1(y + x), src/dsvt-ai-trt.cpp:669-676
-            g.n_ln = 1; g.ln_eps = norm->eps;
+            g.n_ln = 1; g.ln_eps = norm->eps; g.ln_res0_written_here = 0;
             g.ln_res[0] = norm->residual; g.ln_gamma[0] = norm->gamma; g.ln_beta[0] = norm->beta;
             g.ln_res[1] = g.ln_res[2] = nullptr; g.ln_gamma[1] = g.ln_gamma[2] = nullptr; g.ln_beta[1] = g.ln_beta[2] = nullptr;
         }
@@ -1431,6 +1462,35 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
         (rc = launch_gemm(out_roles, 1, voxel_num, 0, p->max_pillars_num, p->max_set_num, p->zero_tails, p->batch, split, st)) != DSVT_OK)
         return rc;
     return DSVT_OK;
+}
+
+// The tail of an encoder layer in ONE kernel: out-projection of the attention (rows `o` of the per-set core, in the caller's
+// set-attention workspace) + norm1(. + x) + the FFN + the LayerNorm chain behind it.  Batch 1.
+int attn_ffn_fused_launch(const dsvt_set_attention_params* p, const void* attn_blob, const float* attn_out_mul, const void* plan,
+                          void* workspace, size_t workspace_bytes, const float* x_res, const float* gamma1, const float* beta1,
+                          float eps1, const void* blob1, const void* pieces1, float out_mul1, const void* blob2, float out_mul2,
+                          const int* rows_dev, int n_ln, const float* const* res, const float* const* gamma, const float* const* beta,
+                          float eps, float* src_out, float* y, int zero_tails, cudaStream_t st)
+{
+    int rc = split_check(p);
+    if (rc != DSVT_OK) return rc;
+    if (p->batch != 1 || !plan || !workspace || workspace_bytes < attention_split_workspace(p)) {
+        set_last_error("attention tail + FFN: batch 1, a prebuilt plan and the set-attention workspace are required");
+        return DSVT_ERR_INVALID_ARGUMENT;
+    }
+    const size_t rows = (size_t) p->max_pillars_num;
+    WsCarver ws(workspace);
+    ws.take<float>(rows * kC);                      // q
+    ws.take<float>(rows * kKvTok);                  // k | v
+    const float* o = ws.take<float>(rows * kC);
+    const uint8_t* img = static_cast<const uint8_t*>(attn_blob);
+    const float* bias = reinterpret_cast<const float*>(img + (size_t) kRoles * kWRoleBytes);
+    FfnOutProj op;
+    op.o = o; op.wo_img = img + (size_t) 3 * kWRoleBytes; op.bias_o = bias + 3 * kC; op.out_mul_o = attn_out_mul[3];
+    op.cover = plan_view(const_cast<int*>(static_cast<const int*>(plan)), p->max_set_num, p->max_pillars_num).vox_su;
+    op.res1 = x_res; op.gamma1 = gamma1; op.beta1 = beta1; op.eps1 = eps1; op.src_out = src_out;
+    return ffn_fused_launch_impl(blob1, pieces1, out_mul1, blob2, out_mul2, nullptr, &op, rows_dev, p->max_pillars_num, n_ln, res,
+                                 gamma, beta, eps, y, zero_tails, st);
 }
 
 
@@ -1504,7 +1564,7 @@ int set_attention_split_plugin(const dsvt_set_attention_params* p, const void* s
     const float* srcs[3] = {q, k, v};
     for (int r = 0; r < 3; ++r) {
         GemmRole& g = in_roles.r[r];
-        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f; g.gen_x = nullptr; g.gen_blob = nullptr;
+        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f; g.ln_res0_written_here = 0; g.gen_x = nullptr; g.gen_blob = nullptr;
         for (int s2 = 0; s2 < 3; ++s2) { g.ln_res[s2] = nullptr; g.ln_gamma[s2] = nullptr; g.ln_beta[s2] = nullptr; }
         g.a0 = srcs[r]; g.a1 = nullptr;                      // the gather plugin has already formed q = k = x + pos, v = x
         g.wimg = img + (size_t) r * kWRoleBytes;
@@ -1521,7 +1581,7 @@ int set_attention_split_plugin(const dsvt_set_attention_params* p, const void* s
     }
     {
         GemmRole& g = out_roles.r[0];
-        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f; g.gen_x = nullptr; g.gen_blob = nullptr;
+        g.kchunks = kNumK; g.n_ln = 0; g.ln_eps = 0.f; g.ln_res0_written_here = 0; g.gen_x = nullptr; g.gen_blob = nullptr;
         for (int s2 = 0; s2 < 3; ++s2) { g.ln_res[s2] = nullptr; g.ln_gamma[s2] = nullptr; g.ln_beta[s2] = nullptr; }
         g.a0 = o; g.a1 = nullptr;
         g.wimg = img + (size_t) 3 * kWRoleBytes;

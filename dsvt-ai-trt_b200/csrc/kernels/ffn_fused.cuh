@@ -33,14 +33,118 @@ struct FfnArgs {
     const uint8_t* w1_img;    // 6 pieces x 48 KB
     const float* bias1;       // [384]
     float out_mul1;
+    // OUT_PROJ form (the tile starts with the attention's out-projection + norm1; g.a0 is not read, g.ln_res[0] = src_out):
+    const float* o;           // [max_pillars, 192] rows of the per-set core (voxel order)
+    const uint8_t* wo_img;    // out-projection: 6 chunk images of 24 KB
+    const float* bias_o;      // [192]
+    float out_mul_o;
+    const int* cover;         // voxel -> (set, token) map of the attention plan: negative = the voxel is in no set (row = 0)
+    const float* res1;        // [max_pillars, 192] the layer input x: src = norm1(attention + x)
+    const float* gamma1;
+    const float* beta1;
+    float eps1;
+    float* src_out;           // [max_pillars, 192] src rows (read back as the residual of norm2)
 };
 
+// Out-projection epilogue of the OUT_PROJ form: src = LayerNorm(acc * out_mul + bias + x) (src/dsvt-ai-trt.cpp:669-676) for the
+// 128 x 192 accumulator tile at TMEM column 0, written (a) as FP32 rows to src_out and (b) as the FP16 hi / lo image that the
+// first FFN GEMM reads -- the FFN's input never comes back from memory.  Arithmetic = ln_chain_epilogue<16> with one stage and
+// the x-tile staging of the plain form.  `tile` = 128 x kLnStride floats in the (idle) weight ring.
+__device__ __forceinline__ void ln1_image_epilogue(const FfnArgs& args, uint8_t* smem, float* tile, uint32_t tmem, int warp, int lane,
+                                                   int row_base, int V, int max_pillars)
+{
+    const int q4 = warp & 3, cb = warp >> 2;
+    {
+        const uint32_t tlane = tmem + ((uint32_t) (q4 * 32) << 16) + cb * 48;
+        float* trow = tile + (size_t) (q4 * 32 + lane) * kLnStride + cb * 48;
+        const int grow = row_base + q4 * 32 + lane;
+        const bool is_dead = args.cover && grow < V && __ldg(args.cover + grow) < 0;
+#pragma unroll 1
+        for (int j0 = 0; j0 < 48; j0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(tlane + j0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(args.bias_o + cb * 48 + j0 + 4 * j));
+                float4 y = make_float4(__uint_as_float(r[4 * j]) * args.out_mul_o + bb.x, __uint_as_float(r[4 * j + 1]) * args.out_mul_o + bb.y,
+                                       __uint_as_float(r[4 * j + 2]) * args.out_mul_o + bb.z, __uint_as_float(r[4 * j + 3]) * args.out_mul_o + bb.w);
+                if (is_dead) y = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(trow + j0 + 4 * j) = y;
+            }
+        }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kFWorkers) : "memory");
+    const int sub = lane & 15;
+    const unsigned hmask = 0xFFFFu << (lane & 16);
+    float4 rq[4][3];                                        // the residual rows of this half-warp's four rows, all in flight at once
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int grow = row_base + warp * 8 + it * 2 + (lane >> 4);
+        if (grow < V) {
+            const float4* rp = reinterpret_cast<const float4*>(args.res1 + (size_t) grow * kC);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) rq[it][k] = ldg_stream4(rp + k * 16 + sub);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) rq[it][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int rloc = warp * 8 + it * 2 + (lane >> 4), grow = row_base + rloc;
+        float4 v[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            v[k] = *reinterpret_cast<const float4*>(tile + (size_t) rloc * kLnStride + (k * 16 + sub) * 4);
+            v[k].x += rq[it][k].x; v[k].y += rq[it][k].y; v[k].z += rq[it][k].z; v[k].w += rq[it][k].w;
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(hmask, sum, o);
+        const float mean = sum / 192.f;
+        float qs = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float a = v[k].x - mean, c = v[k].y - mean, d = v[k].z - mean, e = v[k].w - mean;
+            qs += (a * a + c * c) + (d * d + e * e);
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) qs += __shfl_xor_sync(hmask, qs, o);
+        const float inv_sd = 1.0f / sqrtf(qs / 192.f + args.eps1);
+        const float4* gp = reinterpret_cast<const float4*>(args.gamma1);
+        const float4* bp = reinterpret_cast<const float4*>(args.beta1);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float4 ga = __ldg(gp + k * 16 + sub), be = __ldg(bp + k * 16 + sub);
+            v[k].x = (v[k].x - mean) * inv_sd * ga.x + be.x;
+            v[k].y = (v[k].y - mean) * inv_sd * ga.y + be.y;
+            v[k].z = (v[k].z - mean) * inv_sd * ga.z + be.z;
+            v[k].w = (v[k].w - mean) * inv_sd * ga.w + be.w;
+            const bool live = grow < V;
+            if (live) reinterpret_cast<float4*>(args.src_out + (size_t) grow * kC)[k * 16 + sub] = v[k];
+            // the row's columns 4 (k*16 + sub) .. + 3 = half of one 16-byte K piece of the image (v + 0 like the row staging)
+            const float w0 = live ? v[k].x + 0.f : 0.f, w1 = live ? v[k].y + 0.f : 0.f, w2 = live ? v[k].z + 0.f : 0.f, w3 = live ? v[k].w + 0.f : 0.f;
+            const uint2 hi = make_uint2(pack_h2(w0, w1), pack_h2(w2, w3));
+            const float2 h0 = unpack_h2(hi.x), h1 = unpack_h2(hi.y);
+            const uint2 lo = make_uint2(pack_h2(w0 - h0.x, w1 - h0.y), pack_h2(w2 - h1.x, w3 - h1.y));
+            const int col = (k * 16 + sub) * 4, kc = col >> 5, c16 = (col & 31) >> 3, half = (col & 7) >> 2;
+            uint8_t* dst = smem + kc * (2 * kATerm) + c16 * (kBM * 16) + rloc * 16 + half * 8;
+            *reinterpret_cast<uint2*>(dst) = hi;
+            *reinterpret_cast<uint2*>(dst + kATerm) = lo;
+        }
+    }
+}
+
+template <bool OUT_PROJ>
 __global__ void __launch_bounds__(kFThreads, 1)
 ffn_fused_kernel(const __grid_constant__ FfnArgs args, const int* __restrict__ voxel_num, int max_pillars, int zero_tails)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t a1_full[kNumK], w_full[kFWSlots], w_empty[kFWSlots], acc1_full[2], acc1_empty[2], a2_full[2],
-        a2_empty[2], acc2_full;
+        a2_empty[2], acc2_full, acc_o_full, ring_free;
     __shared__ uint32_t tmem_slot;
     __shared__ float s_bias1[2 * kC];
 
@@ -60,7 +164,7 @@ ffn_fused_kernel(const __grid_constant__ FfnArgs args, const int* __restrict__ v
             }
         return;
     }
-    const float* x = g.a0 + (size_t) b * max_pillars * kC;
+    const float* x = (OUT_PROJ ? args.o : g.a0) + (size_t) b * max_pillars * kC;     // the rows staged first
     if (tid == 0) TP(0);
 
     if (tid == 0) {
@@ -70,7 +174,7 @@ ffn_fused_kernel(const __grid_constant__ FfnArgs args, const int* __restrict__ v
             mbar_init(&acc1_full[s], 1); mbar_init(&acc1_empty[s], kFWorkers);
             mbar_init(&a2_full[s], kFWorkers); mbar_init(&a2_empty[s], 1);
         }
-        mbar_init(&acc2_full, 1);
+        mbar_init(&acc2_full, 1); mbar_init(&acc_o_full, 1); mbar_init(&ring_free, kFWorkers);
         fence_barrier_init();
     }
     if (warp == kFWorkerWarps) tmem_alloc<512>(&tmem_slot);
@@ -115,6 +219,20 @@ ffn_fused_kernel(const __grid_constant__ FfnArgs args, const int* __restrict__ v
             }
         }
         if (tid == 0) TP(2);
+        if (OUT_PROJ) {
+            // =========================== out-projection drained through norm1 into src rows + the FFN's input image ====
+            mbar_wait(&acc_o_full, 0);                         // G_o complete: the o image and the weight ring are idle
+            tc_fence_after_sync();
+            if (tid == 0) TP(26);
+            ln1_image_epilogue(args, smem, reinterpret_cast<float*>(smem + kFA1), tmem, warp, lane, row_base, V, max_pillars);
+            tc_fence_before_sync();
+            fence_proxy_async_smem();
+#pragma unroll
+            for (int kc = 0; kc < kNumK; ++kc) mbar_arrive(&a1_full[kc]);      // second phase: the src image
+            mbar_arrive(&ring_free);
+            __threadfence_block();
+            if (tid == 0) TP(27);
+        }
         // =========================== per piece: ACC1 -> + b1, GELU, hi/lo split -> A2 (tensor memory) ========
         const int q4 = warp & 3, cq = warp >> 2;               // TMEM lane quarter, 16-column block of the piece
         const uint32_t lane_base = tmem + ((uint32_t) (q4 * 32) << 16);
@@ -162,6 +280,27 @@ ffn_fused_kernel(const __grid_constant__ FfnArgs args, const int* __restrict__ v
             const uint64_t a_base = make_smem_desc(sbase, kBM * 16, 128);
             const uint64_t w1_base = make_smem_desc(wbase, kFP * 16, 128), w2_base = make_smem_desc(wbase, kBN * 16, 128);
             int L = 0;                                         // weight-slot loads consumed so far
+            if (OUT_PROJ) {                                    // G_o: ACC2 = O Wo^T (drained by norm1 before G2(0) overwrites it)
+                const uint64_t wo_base = make_smem_desc(wbase, kBN * 16, 128);
+#pragma unroll 1
+                for (int kc = 0; kc < kNumK; ++kc, ++L) {
+                    const int slot = L % kFWSlots;
+                    mbar_wait(&a1_full[kc], 0); __syncwarp();
+                    mbar_wait(&w_full[slot], (L / kFWSlots) & 1); __syncwarp();
+                    tc_fence_after_sync();
+                    const uint64_t ad = a_base + (uint64_t) ((kc * 2 * kATerm) >> 4), wd = wo_base + (uint64_t) ((slot * kFSlot) >> 4);
+#pragma unroll
+                    for (int ks = 0; ks < kBK / 16; ++ks) {
+                        const uint64_t a_hi = ad + (uint64_t) ((ks * 2 * (kBM * 16)) >> 4), a_lo = a_hi + (uint64_t) (kATerm >> 4);
+                        const uint64_t b_hi = wd + (uint64_t) ((ks * 2 * (kBN * 16)) >> 4), b_lo = b_hi + (uint64_t) (kBTerm >> 4);
+                        umma_f16_w(tmem, a_lo, b_hi, idesc2, (kc | ks) != 0);
+                        umma_f16_w(tmem, a_hi, b_lo, idesc2, 1);
+                        umma_f16_w(tmem, a_hi, b_hi, idesc2, 1);
+                    }
+                    umma_commit_w(&w_empty[slot]);
+                }
+                umma_commit_w(&acc_o_full);
+            }
 #pragma unroll 1
             for (int i = 0; i < 2 * kFPieces; ++i) {
                 const bool g1 = i == 0 || (i != 2 * kFPieces - 1 && (i & 1));
@@ -181,7 +320,7 @@ ffn_fused_kernel(const __grid_constant__ FfnArgs args, const int* __restrict__ v
 #pragma unroll
                         for (int kcl = 0; kcl < 3; ++kcl) {
                             const int kc = half * 3 + kcl;
-                            if (p == 0) { mbar_wait(&a1_full[kc], 0); __syncwarp(); tc_fence_after_sync(); }
+                            if (p == 0) { mbar_wait(&a1_full[kc], OUT_PROJ ? 1 : 0); __syncwarp(); tc_fence_after_sync(); }
 #pragma unroll
                             for (int ks = 0; ks < kBK / 16; ++ks) {
                                 const uint64_t a_hi = a_base + (uint64_t) ((kc * 2 * kATerm + ks * 2 * (kBM * 16)) >> 4);
@@ -232,9 +371,23 @@ ffn_fused_kernel(const __grid_constant__ FfnArgs args, const int* __restrict__ v
             l2_prefetch(x + (size_t) row_base * kC, bytes);
             for (int st = 0; st < g.n_ln; ++st)
                 if (g.ln_res[st] != nullptr) l2_prefetch(g.ln_res[st] + ((size_t) b * max_pillars + row_base) * kC, bytes);
+            int L0 = 0;
+            if (OUT_PROJ) {
+                if (args.res1) l2_prefetch(args.res1 + (size_t) row_base * kC, bytes);
 #pragma unroll 1
-            for (int L = 0; L < 4 * kFPieces; ++L) {
-                const int i = L >> 1, half = L & 1, slot = L % kFWSlots;
+                for (; L0 < kNumK; ++L0) {                     // the out-projection's six chunks ...
+                    const int slot = L0 % kFWSlots;
+                    if (L0 >= kFWSlots) mbar_wait(&w_empty[slot], ((L0 / kFWSlots) - 1) & 1);
+                    mbar_arrive_expect_tx(&w_full[slot], kFSlot);
+                    bulk_g2s_hint(smem + kFA1 + slot * kFSlot, args.wo_img + (size_t) L0 * kWChunkBytes, kFSlot, &w_full[slot], w_policy);
+                }
+                mbar_wait(&ring_free, 0);                      // ... then the ring holds norm1's tile until the src image is written
+                fence_proxy_async_smem();
+            }
+#pragma unroll 1
+            for (int Lf = 0; Lf < 4 * kFPieces; ++Lf) {
+                const int L = L0 + Lf;
+                const int i = Lf >> 1, half = Lf & 1, slot = L % kFWSlots;
                 const bool g1 = i == 0 || (i != 2 * kFPieces - 1 && (i & 1));
                 const int p = i == 0 ? 0 : (i == 2 * kFPieces - 1 ? kFPieces - 1 : (g1 ? (i + 1) >> 1 : (i >> 1) - 1));
                 const uint8_t* src = g1 ? args.w1_img + (size_t) p * kFW1Piece + (size_t) half * kFSlot

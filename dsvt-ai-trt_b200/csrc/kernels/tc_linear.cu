@@ -9,6 +9,7 @@
 // store.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "attention_common.cuh"
 #include <cuda_fp16.h>
 #include <vector>
 #include <cmath>
@@ -150,6 +151,11 @@ int linear_gen_batch_launch(int n, const void* const* blobs, const float* out_mu
                             const float* const* small_blobs, const int* rows_dev, int max_rows, float* const* ys, int zero_tails,
                             cudaStream_t st);
 void* ffn_w1_pieces_prepare(const float* W);
+int attn_ffn_fused_launch(const dsvt_set_attention_params* p, const void* attn_blob, const float* attn_out_mul, const void* plan,
+                          void* workspace, size_t workspace_bytes, const float* x_res, const float* gamma1, const float* beta1,
+                          float eps1, const void* blob1, const void* pieces1, float out_mul1, const void* blob2, float out_mul2,
+                          const int* rows_dev, int n_ln, const float* const* res, const float* const* gamma, const float* const* beta,
+                          float eps, float* src_out, float* y, int zero_tails, cudaStream_t st);
 size_t vfe_fused_workspace(int max_points, int npv);
 int vfe_fused_launch(const float* pfn0_blob, const void* blob1, float out_mul1, const float* point_features, const int* piv,
                      const int* voxel_num, const int* point_num, int max_points, int max_pillars, int npv, float* max_voxel,
@@ -365,6 +371,37 @@ extern "C" int dsvt_pos_embed_mlp_launch(const dsvt_small_linear* first, const d
     DSVT_CHECK_ARG(!(((uintptr_t) x2 & 7) | ((uintptr_t) y & 15)), "alignment (x2 8 B, y 16 B)");
     return dsvt::linear_gen_launch(second->split_blob, second->out_mul, second->precision == DSVT_ATTN_FP32_TC, x2, first->blob,
                                    rows, max_rows, y, zero_tails, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dsvt_attention_tail_ffn_launch(const dsvt_set_attention_params* p, const dsvt_attention_weights* w, const void* plan,
+                                              void* workspace, size_t workspace_bytes, const int32_t* voxel_num, const float* x,
+                                              const float* norm1_gamma, const float* norm1_beta, float norm1_eps,
+                                              const dsvt_linear_weights* fc1, const dsvt_linear_weights* fc2,
+                                              const dsvt_ln_stage* stages, int32_t n_stages, float eps, float* src, float* y,
+                                              dsvt_stream_t stream)
+{
+    DSVT_CHECK_ARG(p && w && plan && workspace && voxel_num && x && norm1_gamma && norm1_beta && fc1 && fc2 && stages && src && y,
+                   "NULL argument");
+    DSVT_CHECK_ARG(p->precision == DSVT_ATTN_FP32_TC && w->split_blob != nullptr, "built for precision DSVT_ATTN_FP32_TC");
+    DSVT_CHECK_ARG(p->channel_num == 192 && w->channel_num == 192, "channel_num 192");
+    DSVT_CHECK_ARG(fc1->piece_blob != nullptr && fc1->N == 384 && fc1->K == 192,
+                   "first FFN layer: Linear(192 -> 384) created with DSVT_ATTN_FP32_TC");
+    DSVT_CHECK_ARG(fc2->split_blob != nullptr && fc2->precision == DSVT_ATTN_FP32_TC && fc2->N == 192 && fc2->K == 384,
+                   "second FFN layer: Linear(384 -> 192) created with DSVT_ATTN_FP32_TC");
+    DSVT_CHECK_ARG(n_stages >= 1 && n_stages <= 3, "1..3 LayerNorm stages (the first one's residual is `src`)");
+    DSVT_CHECK_ARG(!(((uintptr_t) x | (uintptr_t) src | (uintptr_t) y | (uintptr_t) norm1_gamma | (uintptr_t) norm1_beta) & 15), "16-B alignment");
+    const float* res[3] = {nullptr, nullptr, nullptr};
+    const float* gamma[3] = {nullptr, nullptr, nullptr};
+    const float* beta[3] = {nullptr, nullptr, nullptr};
+    for (int s = 0; s < n_stages; ++s) {
+        DSVT_CHECK_ARG(stages[s].gamma && stages[s].beta, "NULL gamma / beta");
+        DSVT_CHECK_ARG(!(((uintptr_t) stages[s].residual | (uintptr_t) stages[s].gamma | (uintptr_t) stages[s].beta) & 15), "16-B alignment");
+        res[s] = stages[s].residual; gamma[s] = stages[s].gamma; beta[s] = stages[s].beta;
+    }
+    return dsvt::attn_ffn_fused_launch(p, w->split_blob, w->split_out_mul, plan, workspace, workspace_bytes, x, norm1_gamma, norm1_beta,
+                                       norm1_eps, fc1->split_blob, fc1->piece_blob, fc1->out_mul, fc2->split_blob, fc2->out_mul,
+                                       voxel_num, n_stages, res, gamma, beta, eps, src, y, p->zero_tails,
+                                       reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int dsvt_pos_embed_mlp_batch_launch(const dsvt_small_linear* const* firsts, const dsvt_linear_weights* const* seconds,

@@ -25,6 +25,9 @@ kernel (dsvt_linear_rows_launch), so a DSVT block becomes a real data flow from 
              out-projection (dsvt_set_attention_fused_norm_launch), the two / three LayerNorms behind the FFN into the
              second FFN linear (dsvt_linear_rows_norm_launch, K = 384 in one pass): 5 kernels per encoder layer, the
              attention output and the FFN output never reach memory
+    "layer": "kernel" with the attention's out-projection and norm1 folded in front of the FFN kernel
+             (dsvt_attention_tail_ffn_launch): 3 kernels per encoder layer, neither the attention output nor src's FFN read
+             goes through memory
     "kernel": "epilogue" with the whole FFN (both linears, the GELU, the norms) as ONE kernel (dsvt_ffn_fused_launch): the
              384-wide hidden rows stay in tensor memory; 4 kernels per encoder layer
 
@@ -172,7 +175,9 @@ class HotPathFrame:
 
     def __init__(self, cfg, weights, precision=capi.DSVT_ATTN_FP32, seed=0, device="cuda", fuse_ln=True, share_plans=True,
                  ffn="off", skip=(), zero_tails=1, backbone=False, head=False):
-        assert ffn in ("off", "graph", "fused", "epilogue", "kernel")
+        assert ffn in ("off", "graph", "fused", "epilogue", "kernel", "layer")
+        if ffn == "layer" and precision != capi.DSVT_ATTN_FP32_TC:
+            ffn = "kernel"          # the layer-tail kernel continues the FP32_TC pipeline's workspace; other precisions keep 4 kernels
         assert not backbone or ffn != "off", "backbone=True runs every layer: it needs the FFN linears on"
         self.backbone = backbone
         # diagnostic only (tools/ablate.py): plugin groups left out of the launch sequence to measure their marginal
@@ -214,7 +219,7 @@ class HotPathFrame:
             self.ffn_h = torch.empty(mp, F, device=device)      # FC 192->384 output (graph form only)
             self.ffn_o = torch.empty(mp, C, device=device)      # FC 384->192 output
             self.ffn_parts = torch.empty(F // C, mp, C, device=device)    # ... as split-K partial sums (fused form)
-        vfe_one = backbone and ffn == "kernel"     # fused VFE kernel: the per-point tensors of the pillar feature net do not exist
+        vfe_one = backbone and ffn in ("kernel", "layer")     # fused VFE kernel: the per-point tensors of the pillar feature net do not exist
         self.pfn0_out = self.pfn1_out = None
         if backbone:
             Pm = cfg.max_points_num_voxel_filter
@@ -276,7 +281,7 @@ class HotPathFrame:
         skip, zt = self.skip, self.zero_tails
         vox = self.vox if "vox" in skip else self.vox(self.points, self.points_size)
         V = vox.pillar_num
-        vfe_one = self.backbone and self.ffn == "kernel"      # PFN 0 + scatter-max + concat + PFN 1 + scatter-max in one kernel
+        vfe_one = self.backbone and self.ffn in ("kernel", "layer")      # PFN 0 + scatter-max + concat + PFN 1 + scatter-max in one kernel
         if vfe_one and not ("smax" in skip and "pfn" in skip):
             g = w.glue
             if self.vfe_ws is None:
@@ -315,14 +320,14 @@ class HotPathFrame:
         else:
             x = self.max_voxel[-1]                         # VFE output: per-pillar max of PFN layer 1 (:589, output 1)
             pos = self.pos_out
-            if self.ffn == "kernel" and "pos" not in skip:   # all MLPs of the frame in one launch (they depend on the coordinates only)
+            if self.ffn in ("kernel", "layer") and "pos" not in skip:   # all MLPs of the frame in one launch (they depend on the coordinates only)
                 pairs = [(blk, enc) for blk in range(cfg.num_blocks) for enc in (0, 1)]
                 for i0 in range(0, len(pairs), 8):
                     grp = pairs[i0:i0 + 8]
                     capi.pos_embed_mlp_batch([w.glue["pos"][b_][e_][0] for b_, e_ in grp], [w.glue["pos"][b_][e_][1] for b_, e_ in grp],
                                              [self.wp[e_].coors_in_win_x_y[0] for b_, e_ in grp], V,
                                              [self.pos_out[b_][e_] for b_, e_ in grp], zero_tails=0)
-            for blk in range(0 if ("pos" in skip or self.ffn == "kernel") else cfg.num_blocks):   # pos_embed[blk][i] from the shift-i window coordinates (:603-637)
+            for blk in range(0 if ("pos" in skip or self.ffn in ("kernel", "layer")) else cfg.num_blocks):   # pos_embed[blk][i] from the shift-i window coordinates (:603-637)
                 for enc in (0, 1):
                     first, second = w.glue["pos"][blk][enc]
                     if self.ffn in ("epilogue", "kernel"):  # both layers in one kernel: the hidden rows never reach memory
@@ -335,6 +340,26 @@ class HotPathFrame:
             gs = self.gs[blk % 2]                      # blocks 0,2: 12x12 windows; 1,3: 24x24 shifted (:654-:1018)
             x_in = x
             for enc in (0, 1):
+                if self.ffn == "layer":
+                    # three kernels per encoder layer: QKV projection, per-set core, then out-projection + norm1 + FFN + norms
+                    aw, plan = w.attn[blk * 2 + enc], self.plans.get((blk % 2, enc))
+                    st3 = 3 - sum(bit for g_, bit in (("attn_qkv", 1), ("attn_core", 2)) if g_ in skip)
+                    if "attn" not in skip and st3:
+                        capi.set_attention_fused(aw, x, pos[blk][enc], gs.global_index_in_set[0], gs.mask_expand_0[0], gs.set_num, V,
+                                                 axis=enc, out=self.src, precision=self.precision, workspace=self.attn_ws,
+                                                 plan=plan, zero_tails=zt, stages=st3)
+                    fc1, fc2 = w.ffn[blk * 2 + enc]
+                    norm1 = (w.gamma[ln], w.beta[ln], cfg.layer_norm_eps)
+                    stages = [(self.src, w.gamma[ln + 1], w.beta[ln + 1]), (x, w.gamma[ln + 2], w.beta[ln + 2])]
+                    ln += 3
+                    if enc == 1:
+                        stages.append((x_in, w.gamma[ln], w.beta[ln])); ln += 1
+                    nxt = self.x_a if enc == 0 else self.blk_out[blk % 2]
+                    if not ({"attn", "attn_out", "ffn2"} & skip):
+                        capi.attention_tail_ffn(aw, fc1, fc2, x, gs.global_index_in_set[0], V, enc, plan, self.attn_ws, norm1, stages,
+                                                cfg.layer_norm_eps, src=self.src, out=nxt, zero_tails=zt)
+                    x = nxt
+                    continue
                 epi = self.ffn in ("epilogue", "kernel")
                 if "attn" not in skip:
                     stages = 7 - sum(bit for g_, bit in (("attn_qkv", 1), ("attn_core", 2), ("attn_out", 4)) if g_ in skip)

@@ -388,6 +388,21 @@ int dsvt_ffn_fused_launch(const dsvt_linear_weights* fc1, const dsvt_linear_weig
                           float eps, float* y, int32_t zero_tails, dsvt_stream_t stream);
 
 /*
+ * The tail of an encoder layer as ONE kernel: the attention's out-projection, norm1(attention + x) (src/dsvt-ai-trt.cpp:669-676),
+ * the FFN (:494-529) and the LayerNorm chain behind it (:685-697, :750-756).  Call after
+ * dsvt_set_attention_fused_stages_launch(..., stages = 3) (QKV projection + per-set core) with the SAME params, weights, plan and
+ * workspace: the kernel reads the core's rows from the workspace.  `src` [max_pillars_num,192] receives norm1's output; the FIRST
+ * LayerNorm stage's residual is `src` whatever stages[0].residual says (norm2(src + ffn)), the others are the caller's.
+ * Results = dsvt_set_attention_fused_norm_launch followed by dsvt_ffn_fused_launch.  DSVT_ATTN_FP32_TC, batch 1.
+ */
+int dsvt_attention_tail_ffn_launch(const dsvt_set_attention_params* p, const dsvt_attention_weights* w, const void* plan,
+                                   void* workspace, size_t workspace_bytes, const int32_t* voxel_num, const float* x,
+                                   const float* norm1_gamma, const float* norm1_beta, float norm1_eps,
+                                   const dsvt_linear_weights* fc1, const dsvt_linear_weights* fc2,
+                                   const dsvt_ln_stage* stages, int32_t n_stages, float eps, float* src, float* y,
+                                   dsvt_stream_t stream);
+
+/*
  * Narrow first layers of the VFE / position-embedding MLPs (TensorRT FullyConnected + Scale + ReLU in the reference:
  * PFN layer 0 Linear(10 -> 96) src/dsvt-ai-trt.cpp:577, position embedding Linear(2 -> 192) :603-637 via :461-492):
  *   y = act((x W^T) * scale + shift),  W [N,K] row-major, K in [1, 16], N / 4 dividing 192, scale / shift [N] = the folded

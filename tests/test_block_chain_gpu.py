@@ -125,7 +125,7 @@ def oracle_backbone(w, cfg, frame0):
     return x, bev, V, Pc
 
 
-@pytest.mark.parametrize("ffn", ["graph", "fused", "epilogue", "kernel"])
+@pytest.mark.parametrize("ffn", ["graph", "fused", "epilogue", "kernel", "layer"])
 def test_whole_3d_backbone_chain(frame0, cfgs, ffn):
     """Raw points -> PFN -> scatter-max -> partition / sets -> 2 DSVT blocks (12x12 and shifted 24x24 windows) -> BEV map:
     every layer of the reference's 3-D backbone executed on the GPU through the C ABI, against the oracle chain."""
@@ -197,7 +197,7 @@ def test_bench_workload_chain(pkg, cfgs, geometry):
     cfg = getattr(cfgs, geometry)
     cloud = pkg.synth.ring_lidar(200000, seed=0)
     w = pipeline.FrameWeights(cfg, seed=0)
-    fr = _run_backbone(cfg, w, cloud, ffn="kernel")         # the bench's frame kind (bench.FRAME_KINDS["backbone3d"])
+    fr = _run_backbone(cfg, w, cloud, ffn="layer")          # the bench's frame kind (bench.FRAME_KINDS["backbone3d"])
     V, err = _check_backbone(fr, w, cfg, cloud, 5e-4)
     assert V > 25000                    # the survey's density (~30.6 k pillars), not round 1's 16.6 k
     assert int(fr.gs[0].set_num[0]) > 1300 and int(fr.gs[1].set_num[0]) > 900
@@ -259,13 +259,13 @@ def test_headline_frame_degenerate_clouds(pkg, cfgs, n_points):
         cloud[:, 2] = -1.0
         cloud[:, 3] = 0.5
     frames = {}
-    for ffn in ("kernel", "epilogue"):
+    for ffn in ("layer", "epilogue"):
         fr = pipeline.HotPathFrame(cfg, w, precision=capi.DSVT_ATTN_FP32_TC, seed=2, ffn=ffn, backbone=True)
         fr.load_points(cloud)
         fr.run()
         torch.cuda.synchronize()
         frames[ffn] = fr
-    one, sep = frames["kernel"], frames["epilogue"]
+    one, sep = frames["layer"], frames["epilogue"]
     V = int(one.vox.pillar_num[0])
     assert V == int(sep.vox.pillar_num[0]) and V == (1 if n_points else 0)
     assert int(one.vox.point_num[0]) == n_points
@@ -275,3 +275,17 @@ def test_headline_frame_degenerate_clouds(pkg, cfgs, n_points):
         assert torch.equal(one.max_voxel[-1][:V], sep.max_voxel[-1][:V])
         assert (one.final[:V] - sep.final[:V]).abs().max().item() <= 1e-5
     assert bool((one.bev.reshape(-1, cfg.channel_num).abs().sum(1) > 0).sum() == V) or V == 0
+
+
+def test_layer_tail_kernel_equals_four_kernel_layer(frame0, cfgs):
+    """dsvt_attention_tail_ffn_launch (out-projection + norm1 + FFN + norms in one kernel) against the form it replaces
+    (dsvt_set_attention_fused_norm_launch + dsvt_ffn_fused_launch) over two whole blocks: same arithmetic, bit for bit."""
+    capi = importlib.import_module("dsvt-ai-trt_b200.capi")
+    pipeline = importlib.import_module("dsvt-ai-trt_b200.pipeline")
+    cfg = cfgs.REFERENCE.with_(num_blocks=2)
+    w = pipeline.FrameWeights(cfg, seed=4)
+    a = _run_backbone(cfg, w, frame0, ffn="kernel")
+    b = _run_backbone(cfg, w, frame0, ffn="layer")
+    V = int(a.vox.pillar_num[0])
+    assert V > 1000 and torch.equal(a.final[:V], b.final[:V]) and bool((b.final[V:] == 0).all())
+    assert b.launches_per_frame < a.launches_per_frame

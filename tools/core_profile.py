@@ -7,7 +7,7 @@ pkg = importlib.import_module("dsvt-ai-trt_b200"); capi = importlib.import_modul
 pipeline = importlib.import_module("dsvt-ai-trt_b200.pipeline")
 cfg = pkg.config.WAYMO
 w = pipeline.FrameWeights(cfg, seed=0)
-f = pipeline.HotPathFrame(cfg, w, precision=capi.DSVT_ATTN_FP32_TC, ffn="kernel", backbone=True)
+f = pipeline.HotPathFrame(cfg, w, precision=capi.DSVT_ATTN_FP32_TC, ffn="layer", backbone=True)
 f.load_points(pkg.synth.ring_lidar(200000, seed=0))
 f.run(); torch.cuda.synchronize()
 V, gs, x = f.vox.pillar_num, f.gs[0], f.blk_out[0]

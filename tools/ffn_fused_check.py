@@ -37,10 +37,19 @@ if os.environ.get("DSVT_B200_LIBDIR", "").endswith("lib_prof"):       # phase st
     st = [(f.src, w.gamma[1], w.beta[1]), (x, w.gamma[2], w.beta[2])]
     flush.zero_(); flush_r.max(); torch.cuda.synchronize()
     capi._lib().dsvt_debug_split_profile_reset() if hasattr(capi._lib(), "dsvt_debug_split_profile_reset") else None
-    fc1.ffn_norm(fc2, f.src, V, st, cfg.layer_norm_eps, out=o2); torch.cuda.synchronize()
+    if "--tail" in sys.argv:      # the attention-tail form: out-projection + norm1 in front (needs the core's rows in the workspace)
+        gs = f.gs[0]
+        capi.set_attention_fused(w.attn[0], x, f.pos_out[0][0], gs.global_index_in_set[0], gs.mask_expand_0[0], gs.set_num, V, axis=0,
+                                 out=f.src, precision=f.precision, workspace=f.attn_ws, plan=f.plans[(0, 0)], stages=3)
+        torch.cuda.synchronize(); flush.zero_(); flush_r.max(); torch.cuda.synchronize()
+        capi.attention_tail_ffn(w.attn[0], fc1, fc2, x, gs.global_index_in_set[0], V, 0, f.plans[(0, 0)], f.attn_ws,
+                                (w.gamma[0], w.beta[0], cfg.layer_norm_eps), st, cfg.layer_norm_eps, src=f.src, out=o2)
+    else:
+        fc1.ffn_norm(fc2, f.src, V, st, cfg.layer_norm_eps, out=o2)
+    torch.cuda.synchronize()
     buf = (ctypes.c_longlong * 64)(); capi._lib().dsvt_debug_split_profile(buf)
     t = np.array(buf[:], dtype=np.int64)
-    lab = {0: "start", 1: "setup done", 2: "x image staged", 9: "ACC2 complete", 10: "LN pass A done", 11: "LN pass B half", 13: "CTA end"}
+    lab = {0: "start", 1: "setup done", 2: "x (or o) image staged", 26: "[tail form] G_o complete", 27: "[tail form] norm1 done: src rows + image", 9: "ACC2 complete", 10: "LN pass A done", 11: "LN pass B half", 13: "CTA end"}
     for p in range(6): lab[3 + p] = f"workers: A2({p}) written"
     ops = ["G1(0)", "G1(1)", "G2(0)", "G1(2)", "G2(1)", "G1(3)", "G2(2)", "G1(4)", "G2(3)", "G1(5)", "G2(4)", "G2(5)"]
     for i, o in enumerate(ops): lab[14 + i] = f"issuer: begins {o}"

@@ -11,7 +11,7 @@ backbone = "--backbone" in sys.argv          # every layer of the 3-D backbone (
 prec = int(args[0]) if args else capi.DSVT_ATTN_FP32_TC
 cfg = pkg.config.WAYMO
 w = pipeline.FrameWeights(cfg)
-for ffn, zt in (("graph", 1), ("kernel", 1)):
+for ffn, zt in (("graph", 1), ("kernel", 1), ("layer", 1)):
     f = pipeline.HotPathFrame(cfg, w, precision=prec, ffn=ffn, zero_tails=zt, backbone=backbone)
     f.load_points(pkg.synth.ring_lidar(200000, 0))
     f.run(); torch.cuda.synchronize()

@@ -10,7 +10,7 @@ pkg = importlib.import_module("dsvt-ai-trt_b200"); capi = importlib.import_modul
 pipeline = importlib.import_module("dsvt-ai-trt_b200.pipeline")
 cfg = pkg.config.WAYMO
 w = pipeline.FrameWeights(cfg)
-f = pipeline.HotPathFrame(cfg, w, precision=capi.DSVT_ATTN_FP32_TC, ffn="kernel", backbone=True, head="--head" in sys.argv)
+f = pipeline.HotPathFrame(cfg, w, precision=capi.DSVT_ATTN_FP32_TC, ffn="layer", backbone=True, head="--head" in sys.argv)
 f.load_points(pkg.synth.ring_lidar(200000, 0))
 f.run(); torch.cuda.synchronize()
 torch.cuda.profiler.start()
