@@ -48,10 +48,11 @@ def main(rep, table, js):
                 k = "set_attention.out_proj_gemm_norm1"       # (the headline frame's only LayerNorm-epilogue tile GEMM)
             else: k = "linear_single_role(pfn / pos_embed_mlp)"
         elif "attn_core_kernel" in o["name"]: k = "set_attention.attn_core"
-        elif "ffn_fused_kernel<(bool)1>" in o["name"] or "ffn_fused_kernel<true>" in o["name"]: k = "attention_tail_ffn"
+        elif re.search(r"ffn_fused_kernel<(\(bool\))?(1|true)>", o["name"]): k = "attention_tail_ffn"
         elif "ffn_fused_kernel" in o["name"]: k = "ffn_fused"
         elif "qkv_fused_kernel" in o["name"]: k = "set_attention.qkv_proj_gemm"
         elif "vfe_fused_kernel" in o["name"]: k = "vfe_fused"
+        elif "pos_fused_kernel" in o["name"]: k = "pos_embed_mlp_x8"
         o["key"] = k or o["name"]
         keys[o["key"]].append(o)
     with open(table, "w") as f:
