@@ -21,8 +21,10 @@ constexpr int kFSlot = 2 * kBTerm;              // 24576 B
 constexpr int kFW1Chunk = 2 * kFP * kBK * 2;    // 8192 B: one K chunk of a W1 piece, [hi | lo][c16][n 64][16 B]
 constexpr int kFW1Piece = kNumK * kFW1Chunk;    // 49152 B
 constexpr int kFA1 = kNumK * 2 * kATerm;        // 98304 B: the resident x image
-constexpr int kFSmem = kFA1 + kFWSlots * kFSlot;                                     // 196608 B
-constexpr int kFSmemTotal = kFSmem > kBM * kLnStride * 4 ? kFSmem : kBM * kLnStride * 4;
+constexpr int kFRing = kBM * kLnStride * 4;     // 100352 B: the weight ring starts behind the LayerNorm tile that aliases the image
+                                                // (norm1 of the layer-tail form runs while the ring streams the FFN's first pieces)
+static_assert(kFRing >= kFA1 && kFRing % 128 == 0, "ring base");
+constexpr int kFSmemTotal = kFRing + kFWSlots * kFSlot;                              // 223232 B
 constexpr uint32_t kFAcc1 = 192, kFA2 = 320;
 constexpr int kFWorkerWarps = 16;               // one CTA per SM (196 KB of shared memory): twice the tile kernel's worker warps
 constexpr int kFWorkers = kFWorkerWarps * 32;
@@ -43,100 +45,8 @@ struct FfnArgs {
     const float* gamma1;
     const float* beta1;
     float eps1;
-    float* src_out;           // [max_pillars, 192] src rows (read back as the residual of norm2)
+    float* src_out;           // [max_pillars, 192] src rows (read back for the FFN's input image and as the residual of norm2)
 };
-
-// Out-projection epilogue of the OUT_PROJ form: src = LayerNorm(acc * out_mul + bias + x) (src/dsvt-ai-trt.cpp:669-676) for the
-// 128 x 192 accumulator tile at TMEM column 0, written (a) as FP32 rows to src_out and (b) as the FP16 hi / lo image that the
-// first FFN GEMM reads -- the FFN's input never comes back from memory.  Arithmetic = ln_chain_epilogue<16> with one stage and
-// the x-tile staging of the plain form.  `tile` = 128 x kLnStride floats in the (idle) weight ring.
-__device__ __forceinline__ void ln1_image_epilogue(const FfnArgs& args, uint8_t* smem, float* tile, uint32_t tmem, int warp, int lane,
-                                                   int row_base, int V, int max_pillars)
-{
-    const int q4 = warp & 3, cb = warp >> 2;
-    {
-        const uint32_t tlane = tmem + ((uint32_t) (q4 * 32) << 16) + cb * 48;
-        float* trow = tile + (size_t) (q4 * 32 + lane) * kLnStride + cb * 48;
-        const int grow = row_base + q4 * 32 + lane;
-        const bool is_dead = args.cover && grow < V && __ldg(args.cover + grow) < 0;
-#pragma unroll 1
-        for (int j0 = 0; j0 < 48; j0 += 16) {
-            uint32_t r[16];
-            tmem_ld16(tlane + j0, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(args.bias_o + cb * 48 + j0 + 4 * j));
-                float4 y = make_float4(__uint_as_float(r[4 * j]) * args.out_mul_o + bb.x, __uint_as_float(r[4 * j + 1]) * args.out_mul_o + bb.y,
-                                       __uint_as_float(r[4 * j + 2]) * args.out_mul_o + bb.z, __uint_as_float(r[4 * j + 3]) * args.out_mul_o + bb.w);
-                if (is_dead) y = make_float4(0.f, 0.f, 0.f, 0.f);
-                *reinterpret_cast<float4*>(trow + j0 + 4 * j) = y;
-            }
-        }
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(kFWorkers) : "memory");
-    const int sub = lane & 15;
-    const unsigned hmask = 0xFFFFu << (lane & 16);
-    float4 rq[4][3];                                        // the residual rows of this half-warp's four rows, all in flight at once
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        const int grow = row_base + warp * 8 + it * 2 + (lane >> 4);
-        if (grow < V) {
-            const float4* rp = reinterpret_cast<const float4*>(args.res1 + (size_t) grow * kC);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) rq[it][k] = ldg_stream4(rp + k * 16 + sub);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) rq[it][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    }
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        const int rloc = warp * 8 + it * 2 + (lane >> 4), grow = row_base + rloc;
-        float4 v[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            v[k] = *reinterpret_cast<const float4*>(tile + (size_t) rloc * kLnStride + (k * 16 + sub) * 4);
-            v[k].x += rq[it][k].x; v[k].y += rq[it][k].y; v[k].z += rq[it][k].z; v[k].w += rq[it][k].w;
-        }
-        float sum = 0.f;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(hmask, sum, o);
-        const float mean = sum / 192.f;
-        float qs = 0.f;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float a = v[k].x - mean, c = v[k].y - mean, d = v[k].z - mean, e = v[k].w - mean;
-            qs += (a * a + c * c) + (d * d + e * e);
-        }
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) qs += __shfl_xor_sync(hmask, qs, o);
-        const float inv_sd = 1.0f / sqrtf(qs / 192.f + args.eps1);
-        const float4* gp = reinterpret_cast<const float4*>(args.gamma1);
-        const float4* bp = reinterpret_cast<const float4*>(args.beta1);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float4 ga = __ldg(gp + k * 16 + sub), be = __ldg(bp + k * 16 + sub);
-            v[k].x = (v[k].x - mean) * inv_sd * ga.x + be.x;
-            v[k].y = (v[k].y - mean) * inv_sd * ga.y + be.y;
-            v[k].z = (v[k].z - mean) * inv_sd * ga.z + be.z;
-            v[k].w = (v[k].w - mean) * inv_sd * ga.w + be.w;
-            const bool live = grow < V;
-            if (live) reinterpret_cast<float4*>(args.src_out + (size_t) grow * kC)[k * 16 + sub] = v[k];
-            // the row's columns 4 (k*16 + sub) .. + 3 = half of one 16-byte K piece of the image (v + 0 like the row staging)
-            const float w0 = live ? v[k].x + 0.f : 0.f, w1 = live ? v[k].y + 0.f : 0.f, w2 = live ? v[k].z + 0.f : 0.f, w3 = live ? v[k].w + 0.f : 0.f;
-            const uint2 hi = make_uint2(pack_h2(w0, w1), pack_h2(w2, w3));
-            const float2 h0 = unpack_h2(hi.x), h1 = unpack_h2(hi.y);
-            const uint2 lo = make_uint2(pack_h2(w0 - h0.x, w1 - h0.y), pack_h2(w2 - h1.x, w3 - h1.y));
-            const int col = (k * 16 + sub) * 4, kc = col >> 5, c16 = (col & 31) >> 3, half = (col & 7) >> 2;
-            uint8_t* dst = smem + kc * (2 * kATerm) + c16 * (kBM * 16) + rloc * 16 + half * 8;
-            *reinterpret_cast<uint2*>(dst) = hi;
-            *reinterpret_cast<uint2*>(dst + kATerm) = lo;
-        }
-    }
-}
 
 template <bool OUT_PROJ>
 __global__ void __launch_bounds__(kFThreads, 1)
@@ -144,7 +54,7 @@ ffn_fused_kernel(const __grid_constant__ FfnArgs args, const int* __restrict__ v
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t a1_full[kNumK], w_full[kFWSlots], w_empty[kFWSlots], acc1_full[2], acc1_empty[2], a2_full[2],
-        a2_empty[2], acc2_full, acc_o_full, ring_free;
+        a2_empty[2], acc2_full, acc_o_full;
     __shared__ uint32_t tmem_slot;
     __shared__ float s_bias1[2 * kC];
 
@@ -174,7 +84,7 @@ ffn_fused_kernel(const __grid_constant__ FfnArgs args, const int* __restrict__ v
             mbar_init(&acc1_full[s], 1); mbar_init(&acc1_empty[s], kFWorkers);
             mbar_init(&a2_full[s], kFWorkers); mbar_init(&a2_empty[s], 1);
         }
-        mbar_init(&acc2_full, 1); mbar_init(&acc_o_full, 1); mbar_init(&ring_free, kFWorkers);
+        mbar_init(&acc2_full, 1); mbar_init(&acc_o_full, 1);
         fence_barrier_init();
     }
     if (warp == kFWorkerWarps) tmem_alloc<512>(&tmem_slot);
@@ -186,17 +96,23 @@ ffn_fused_kernel(const __grid_constant__ FfnArgs args, const int* __restrict__ v
     if (tid == 0) TP(1);
 
     if (warp < kFWorkerWarps) {
-        // =========================== x tile -> resident A image ============================================
-        // step = K chunk: row warp*8 + (lane & 7), 16-byte K piece c16 = lane >> 3
-        {
+        // =========================== rows -> resident A image ================================================
+        // step = K chunk: row warp*8 + (lane & 7), 16-byte K piece c16 = lane >> 3.  `coherent`: the rows were written by this
+        // kernel (src of the OUT_PROJ form) -- read through L2, not through the non-coherent read-only path
+        auto stage = [&](const float* rows, bool coherent) {
             constexpr int kDepth = 3;
             const int rl = warp * 8 + (lane & 7), c16 = lane >> 3, row = row_base + rl;
             float buf[kDepth][8];
             auto issue = [&](int kc, float (&d)[8]) {
-                if (row < V) ldg256(x + (size_t) row * kC + kc * kBK + c16 * 8, &d[0]);
-                else {
+                const float* p = rows + (size_t) row * kC + kc * kBK + c16 * 8;
+                if (row >= V) {
 #pragma unroll
                     for (int e = 0; e < 8; ++e) d[e] = 0.f;
+                } else if (coherent) {
+                    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]) : "l"(p));
+                    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(d[4]), "=f"(d[5]), "=f"(d[6]), "=f"(d[7]) : "l"(p + 4));
+                } else {
+                    ldg256(p, &d[0]);
                 }
             };
 #pragma unroll
@@ -217,20 +133,28 @@ ffn_fused_kernel(const __grid_constant__ FfnArgs args, const int* __restrict__ v
                 fence_proxy_async_smem();
                 mbar_arrive(&a1_full[kc]);
             }
-        }
+        };
+        stage(x, false);
         if (tid == 0) TP(2);
         if (OUT_PROJ) {
-            // =========================== out-projection drained through norm1 into src rows + the FFN's input image ====
-            mbar_wait(&acc_o_full, 0);                         // G_o complete: the o image and the weight ring are idle
+            // =========================== out-projection drained through norm1 into the src rows ==================
+            // src = LayerNorm(acc * out_mul + bias + x) (src/dsvt-ai-trt.cpp:669-676): the shared LayerNorm-chain epilogue with one
+            // stage, its FP32 tile in the (dead) o image -- the weight ring keeps streaming the FFN's first pieces meanwhile.  The
+            // FFN's input image is then staged from the src rows just written (L2 hits).
+            mbar_wait(&acc_o_full, 0);
             tc_fence_after_sync();
             if (tid == 0) TP(26);
-            ln1_image_epilogue(args, smem, reinterpret_cast<float*>(smem + kFA1), tmem, warp, lane, row_base, V, max_pillars);
+            GemmRole n1 = g;
+            n1.bias = args.bias_o; n1.out_mul = args.out_mul_o; n1.cover = args.cover; n1.cover_stride = 0;
+            n1.n_ln = 1; n1.ln_eps = args.eps1; n1.ln_res0_written_here = 0;
+            n1.ln_res[0] = args.res1; n1.ln_gamma[0] = args.gamma1; n1.ln_beta[0] = args.beta1;
+            n1.out = args.src_out;
+            ln_chain_epilogue<kFWorkerWarps>(n1, reinterpret_cast<float*>(smem), tmem, warp, lane, tid, row_base, V, b, max_pillars,
+                                             args.src_out + (size_t) b * max_pillars * kC, 0);
             tc_fence_before_sync();
-            fence_proxy_async_smem();
-#pragma unroll
-            for (int kc = 0; kc < kNumK; ++kc) mbar_arrive(&a1_full[kc]);      // second phase: the src image
-            mbar_arrive(&ring_free);
             __threadfence_block();
+            asm volatile("bar.sync 1, %0;" ::"n"(kFWorkers) : "memory");      // every src row of the tile is visible to the CTA
+            stage(args.src_out + (size_t) b * max_pillars * kC, true);        // second phase of a1_full: the src image
             if (tid == 0) TP(27);
         }
         // =========================== per piece: ACC1 -> + b1, GELU, hi/lo split -> A2 (tensor memory) ========
@@ -274,7 +198,7 @@ ffn_fused_kernel(const __grid_constant__ FfnArgs args, const int* __restrict__ v
         // =========================== MMA ISSUE ===========================================================
         {                                                      // the whole warp, converged: see umma_f16_w
             const uint32_t idesc1 = make_idesc(kFmtF16, kBM, kFP), idesc2 = make_idesc(kFmtF16, kBM, kBN);
-            const uint32_t sbase = smem_u32(smem), wbase = sbase + kFA1;
+            const uint32_t sbase = smem_u32(smem), wbase = sbase + kFRing;
             // descriptors = base + (byte offset >> 4): the issuing thread's own instruction stream is on the critical path
             // (36 + 12 MMAs per piece), so nothing but 64-bit adds of compile-time constants stays inside the loops
             const uint64_t a_base = make_smem_desc(sbase, kBM * 16, 128);
@@ -375,14 +299,12 @@ ffn_fused_kernel(const __grid_constant__ FfnArgs args, const int* __restrict__ v
             if (OUT_PROJ) {
                 if (args.res1) l2_prefetch(args.res1 + (size_t) row_base * kC, bytes);
 #pragma unroll 1
-                for (; L0 < kNumK; ++L0) {                     // the out-projection's six chunks ...
+                for (; L0 < kNumK; ++L0) {                     // the out-projection's six chunks, then the FFN's slots
                     const int slot = L0 % kFWSlots;
                     if (L0 >= kFWSlots) mbar_wait(&w_empty[slot], ((L0 / kFWSlots) - 1) & 1);
                     mbar_arrive_expect_tx(&w_full[slot], kFSlot);
-                    bulk_g2s_hint(smem + kFA1 + slot * kFSlot, args.wo_img + (size_t) L0 * kWChunkBytes, kFSlot, &w_full[slot], w_policy);
+                    bulk_g2s_hint(smem + kFRing + slot * kFSlot, args.wo_img + (size_t) L0 * kWChunkBytes, kFSlot, &w_full[slot], w_policy);
                 }
-                mbar_wait(&ring_free, 0);                      // ... then the ring holds norm1's tile until the src image is written
-                fence_proxy_async_smem();
             }
 #pragma unroll 1
             for (int Lf = 0; Lf < 4 * kFPieces; ++Lf) {
@@ -394,7 +316,7 @@ ffn_fused_kernel(const __grid_constant__ FfnArgs args, const int* __restrict__ v
                                         : g.wimg + (size_t) (2 * p + half) * kWChunkBytes;
                 if (L >= kFWSlots) mbar_wait(&w_empty[slot], ((L / kFWSlots) - 1) & 1);
                 mbar_arrive_expect_tx(&w_full[slot], kFSlot);
-                bulk_g2s_hint(smem + kFA1 + slot * kFSlot, src, kFSlot, &w_full[slot], w_policy);
+                bulk_g2s_hint(smem + kFRing + slot * kFSlot, src, kFSlot, &w_full[slot], w_policy);
             }
         }
         __syncwarp();

@@ -49,7 +49,7 @@ if os.environ.get("DSVT_B200_LIBDIR", "").endswith("lib_prof"):       # phase st
     torch.cuda.synchronize()
     buf = (ctypes.c_longlong * 64)(); capi._lib().dsvt_debug_split_profile(buf)
     t = np.array(buf[:], dtype=np.int64)
-    lab = {0: "start", 1: "setup done", 2: "x (or o) image staged", 26: "[tail form] G_o complete", 27: "[tail form] norm1 done: src rows + image", 9: "ACC2 complete", 10: "LN pass A done", 11: "LN pass B half", 13: "CTA end"}
+    lab = {0: "start", 1: "setup done", 2: "x (or o) image staged", 26: "[tail form] G_o complete", 27: "[tail form] norm1 done, src image staged", 9: "ACC2 complete", 10: "LN pass A done", 11: "LN pass B half", 13: "CTA end"}
     for p in range(6): lab[3 + p] = f"workers: A2({p}) written"
     ops = ["G1(0)", "G1(1)", "G2(0)", "G1(2)", "G2(1)", "G1(3)", "G2(2)", "G1(4)", "G2(3)", "G1(5)", "G2(4)", "G2(5)"]
     for i, o in enumerate(ops): lab[14 + i] = f"issuer: begins {o}"
