@@ -381,7 +381,7 @@ int dsvt_linear_rows_norm_launch(const dsvt_linear_weights* w, const float* x, c
  *   y = LN_n( ... LN_1( gelu(x W1^T + b1) W2^T + b2 + r_1 ) ... + r_n )
  * fc1 = Linear(192 -> 384), fc2 = Linear(384 -> 192), both created with DSVT_ATTN_FP32_TC.  The 384-wide hidden rows stay on
  * the SM (second GEMM's A operand in tensor memory); results = dsvt_linear_rows_launch(activation GELU) followed by
- * dsvt_linear_rows_norm_launch.  x [max_rows,192] (32-B aligned), y [max_rows,192], rows [1] on the device.
+ * dsvt_linear_rows_norm_launch.  x [max_rows,192] (32-B aligned), y [max_rows,192], rows [1] on the device (batch 1).
  */
 int dsvt_ffn_fused_launch(const dsvt_linear_weights* fc1, const dsvt_linear_weights* fc2, const float* x,
                           const int32_t* rows, int32_t max_rows, const dsvt_ln_stage* stages, int32_t n_stages,
@@ -424,7 +424,7 @@ int dsvt_small_linear_launch(const dsvt_small_linear* w, const float* x, const i
  * Points2FeaturesPlugin's outputs 0 (point rows [max_points_num, 10]), 1 (point_index_in_voxel; this library's voxeliser
  * emits a pillar's rows consecutively, which the kernel relies on), 4 (pillar count) and 5 (row count).  Results = the four
  * separate launches (dsvt_small_linear_launch, dsvt_torch_scatter_max_launch, dsvt_linear_rows_concat_launch,
- * dsvt_torch_scatter_max_launch).  Rows beyond the pillar count are zero-filled when zero_tails != 0.
+ * dsvt_torch_scatter_max_launch).  Rows beyond the pillar count are zero-filled when zero_tails != 0.  Batch 1.
  */
 size_t dsvt_vfe_fused_workspace_size(int32_t max_points_num, int32_t max_num_points_per_voxel);
 int dsvt_vfe_fused_launch(const dsvt_small_linear* pfn0, const dsvt_linear_weights* pfn1, const float* point_features,
