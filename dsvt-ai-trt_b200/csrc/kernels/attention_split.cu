@@ -24,6 +24,14 @@
 // interleaved layout of tc_common.cuh conflict-free; B: one cp.async.bulk per chunk of the pre-arranged weight image); one
 // thread issues the MMAs; the producer warps then drain the 192 accumulator columns from TMEM (optionally through a chain
 // of LayerNorms).  80 KB shared memory and 256 TMEM columns per CTA -> two CTAs per SM overlap each other's phases.
+//
+// Tile-wide successors (one CTA per 128-row tile and SM, 16 worker warps, a converged issuer warp, a copier; same operand
+// images, MMA order and epilogue arithmetic, bit-identical results) are included below and are what the fused frame launches:
+//   qkv_fused.cuh  step 1 for the fused FP32_TC entry (x + pos converted once for Q and K, roles in sequence)
+//   ffn_fused.cuh  the FFN + the LayerNorm chain behind it; with step 3 + norm1 in front it is the layer tail
+//   pos_fused.cuh  the position-embedding MLPs of a frame as roles in sequence
+//   vfe_fused.cuh  the pillar feature net (PFN 0, per-pillar max, concat, PFN 1, per-pillar max)
+// proj_tile_kernel stays the kernel of the plugin-shaped entry points (q/k/v form, LinearPlugin, dsvt_linear_rows_*).
 #include "attention_common.cuh"
 #include "tc_common.cuh"
 #include <cuda_fp16.h>

@@ -14,6 +14,11 @@
 // TMEM (512 columns): ACC2 0..191 | ACC1[b] 192+64b.. (FP32) | A2[b] 320+64b..: 32 packed hi columns, 32 packed lo columns.
 // The first GEMM runs one piece ahead of the second, so the tensor pipe works on G1(p+1) while the workers turn ACC1(p)
 // into A2(p).  Products, their order and the epilogue arithmetic are those of the two-kernel form.
+//
+// OUT_PROJ = true is the LAYER TAIL (dsvt_attention_tail_ffn_launch): the tile first stages the rows `o` of the attention's
+// per-set core, G_o puts the out-projection into ACC2, the shared LayerNorm epilogue drains it as src = norm1(. + x) (tile in
+// the dead o image; the weight ring sits behind that tile and keeps streaming), and the FFN's input image is staged from the
+// src rows just written -- out-projection, norm1, FFN and the norms behind it are one kernel.
 constexpr int kFP = 64;                         // hidden columns per piece
 constexpr int kFPieces = 2 * kC / kFP;          // 6
 constexpr int kFWSlots = 5;
