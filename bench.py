@@ -304,16 +304,25 @@ def plugin_breakdown(slot, cfg, peaks, reps=5):
                                            "scope": "next", "contract_bytes": 4 * fch * (Pc + Pf + cfg.max_pillars_num)}
     del sep, pfn0_out, pfn1_out, max_point, max_voxel
     torch.cuda.empty_cache()
-    first, second = g["pos"][0][0]
-    us = timed(lambda: capi.pos_embed_mlp(first, second, f.wp[0].coors_in_win_x_y[0], Vt, out=f.pos_out[0][0], zero_tails=0))
-    res["pos_embed_mlp"] = {"us": us, "bytes": 4 * V * (2 + C), "flops": 2 * V * C * C, "calls_per_frame": 0, "scope": "next#4",
-                            "note": "Linear(2->192)+BN+ReLU generated inside the Linear(192->192) GEMM's producers; one MLP per launch"}
+    # position embedding.  Headline: the eight MLPs evaluated on the CELLS of a window (tables of 24 x 24 rows, one launch), looked
+    # up by the QKV kernel; per-voxel forms (one launch per MLP / one launch for the eight) timed on scratch buffers
     pairs = [(b_, e_) for b_ in range(cfg.num_blocks) for e_ in (0, 1)]
     us = timed(lambda: capi.pos_embed_mlp_batch([g["pos"][b_][e_][0] for b_, e_ in pairs], [g["pos"][b_][e_][1] for b_, e_ in pairs],
-                                                [f.wp[e_].coors_in_win_x_y[0] for b_, e_ in pairs], Vt,
-                                                [f.pos_out[b_][e_] for b_, e_ in pairs], zero_tails=0))
-    res["pos_embed_mlp_x8"] = {"us": us, "bytes": 8 * 4 * V * (2 + C), "flops": 8 * 2 * V * C * C, "calls_per_frame": 1,
-                               "scope": "next#4", "note": "the frame's eight position-embedding MLPs as the roles of ONE launch"}
+                                                [f.pos_cells[e_] for b_, e_ in pairs], f.pos_rows,
+                                                [f.pos_tab[b_][e_] for b_, e_ in pairs], zero_tails=0))
+    ncell = int(f.pos_rows[0])
+    res["pos_embed_tables_x8"] = {"us": us, "bytes": 8 * 4 * ncell * (2 + C), "flops": 8 * 2 * ncell * C * C, "calls_per_frame": 1,
+                                  "scope": "next#4", "note": f"the eight position-embedding MLPs on the {ncell} cells of a window (one launch)"}
+    pos_scratch = [torch.empty(cfg.max_pillars_num, C, device="cuda") for _ in range(8)]
+    first, second = g["pos"][0][0]
+    us = timed(lambda: capi.pos_embed_mlp(first, second, f.wp[0].coors_in_win_x_y[0], Vt, out=pos_scratch[0], zero_tails=0))
+    res["pos_embed_mlp"] = {"us": us, "bytes": 4 * V * (2 + C), "flops": 2 * V * C * C, "calls_per_frame": 0, "scope": "next#4",
+                            "note": "per voxel: Linear(2->192)+BN+ReLU generated inside the Linear(192->192) GEMM's producers; one MLP per launch"}
+    us = timed(lambda: capi.pos_embed_mlp_batch([g["pos"][b_][e_][0] for b_, e_ in pairs], [g["pos"][b_][e_][1] for b_, e_ in pairs],
+                                                [f.wp[e_].coors_in_win_x_y[0] for b_, e_ in pairs], Vt, pos_scratch, zero_tails=0))
+    del pos_scratch
+    res["pos_embed_mlp_x8"] = {"us": us, "bytes": 8 * 4 * V * (2 + C), "flops": 8 * 2 * V * C * C, "calls_per_frame": 0,
+                               "scope": "next#4", "note": "per voxel: the frame's eight MLPs in one launch (backbone3d_four_kernel_layer leg)"}
     us = timed(lambda: capi.map2bev(f.final, vox.coords[0], Vt, cfg.grid_x, cfg.grid_y, out=f.bev))
     res["map2bev"] = {"us": us, "bytes": 2 * 4 * C * V + 16 * V, "calls_per_frame": 1, "scope": "next",
                       "contract_bytes": 4 * C * (cfg.grid_x * cfg.grid_y + V)}
@@ -363,8 +372,8 @@ def plugin_breakdown(slot, cfg, peaks, reps=5):
     # (dsvt_attention_tail_ffn_launch), timed on the workspace a QKV + core launch pair has just filled; bytes = core rows in,
     # x in, src out, y out (+ the block input for the third norm)
     gs0, plan0 = f.gs[0], f.plans[(0, 0)]
-    capi.set_attention_fused(w.attn[0], x, f.pos_out[0][0], gs0.global_index_in_set[0], gs0.mask_expand_0[0], gs0.set_num, Vt, axis=0,
-                             out=f.src_b, precision=f.precision, workspace=f.attn_ws, plan=plan0, stages=3)
+    capi.set_attention_fused(w.attn[0], x, None, gs0.global_index_in_set[0], gs0.mask_expand_0[0], gs0.set_num, Vt, axis=0,
+                             out=f.src_b, precision=f.precision, workspace=f.attn_ws, plan=plan0, stages=3, pos_table=f.attn_pos(0, 0)[1])
     for n_st, st in ((2, st2), (3, st3)):
         us = timed(lambda: capi.attention_tail_ffn(w.attn[0], fc1, fc2, x, gs0.global_index_in_set[0], Vt, 0, plan0, f.attn_ws,
                                                    (w.gamma[0], w.beta[0], cfg.layer_norm_eps), st, cfg.layer_norm_eps,
@@ -378,9 +387,9 @@ def plugin_breakdown(slot, cfg, peaks, reps=5):
         gs = f.gs[i]
         plan = f.plans.get((i, 0)) if getattr(f, "plans", None) else None
         call = lambda stages=7: capi.set_attention_fused(
-            w.attn[i], x, f.pos_out[i][0], gs.global_index_in_set[0], gs.mask_expand_0[0], gs.set_num, Vt, axis=0,
+            w.attn[i], x, f.attn_pos(i, 0)[0], gs.global_index_in_set[0], gs.mask_expand_0[0], gs.set_num, Vt, axis=0,
             out=f.src_b, precision=f.precision, workspace=f.attn_ws, plan=plan,
-            norm=(x, w.gamma[0], w.beta[0], cfg.layer_norm_eps), stages=stages)
+            norm=(x, w.gamma[0], w.beta[0], cfg.layer_norm_eps), stages=stages, pos_table=f.attn_pos(i, 0)[1])
         if plan is not None:      # one plan per (partition, axis) serves two layers: 4 plan builds per frame
             pus = timed(lambda: capi.set_attention_plan(gs.global_index_in_set[0], gs.mask_expand_0[0], gs.set_num, 0,
                                                         cfg.max_pillars_num, cfg.num_heads, cfg.channel_num, out=plan))

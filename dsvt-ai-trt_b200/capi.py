@@ -334,15 +334,18 @@ def set_attention_plan(global_index_in_set, mask, set_num, axis, max_pillars, he
 
 
 def set_attention_fused(weights, x, pos, global_index_in_set, mask, set_num, voxel_num, axis, out=None,
-                        precision=DSVT_ATTN_FP32, zero_tails=1, workspace=None, plan=None, norm=None, stages=7):
+                        precision=DSVT_ATTN_FP32, zero_tails=1, workspace=None, plan=None, norm=None, stages=7, pos_table=None):
     """Fused gather + attention + scatter: x,pos [B,max_pillars,C], global_index_in_set [B,2,max_sets,S].
     `workspace`: uint8 device tensor of dsvt_set_attention_workspace_size bytes (allocated here when None and the
     precision needs one; pass a persistent buffer when capturing CUDA graphs).
     `norm` = (residual, gamma, beta, eps): out = LayerNorm(attention + residual) in the out-projection's epilogue
     (dsvt_set_attention_fused_norm_launch; GEMM-pipeline precisions).
-    `stages` != 7: dsvt_set_attention_fused_stages_launch -- only the named kernels (1 QKV GEMM, 2 core, 4 out-projection)."""
+    `stages` != 7: dsvt_set_attention_fused_stages_launch -- only the named kernels (1 QKV GEMM, 2 core, 4 out-projection).
+    `pos_table` = (table [win_x * win_y, C], coors_in_win_2d [max_pillars, 3] int32, win_x): the position embedding as a table over
+    the cells of a window (dsvt_set_attention_fused_table_launch; `pos` is then ignored and may be None)."""
     _need(x, torch.float32, "x")
-    _need(pos, torch.float32, "pos")
+    if pos_table is None:
+        _need(pos, torch.float32, "pos")
     _need(global_index_in_set, torch.int32, "global_index_in_set")
     _need(mask, torch.float32, "mask")
     B = x.shape[0] if x.dim() == 3 else 1
@@ -353,6 +356,17 @@ def set_attention_fused(weights, x, pos, global_index_in_set, mask, set_num, vox
     ws_bytes = int(_lib().dsvt_set_attention_workspace_size(ctypes.byref(p)))
     if ws_bytes and workspace is None:
         workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    if pos_table is not None:
+        tab, cells, win_x = pos_table
+        _need(tab, torch.float32, "pos_table")
+        _need(cells, torch.int32, "coors_in_win_2d")
+        res, gamma, beta, eps = norm if norm is not None else (None, None, None, 0.0)
+        rc = _lib().dsvt_set_attention_fused_table_launch(
+            ctypes.byref(p), c_void_p(weights.handle), _ptr(x), _ptr(tab), _ptr(cells), c_int32(win_x), _ptr(global_index_in_set),
+            _ptr(mask), _ptr(set_num), _ptr(voxel_num), _ptr(res), _ptr(gamma), _ptr(beta), c_float(eps), _ptr(out), _ptr(plan),
+            _ptr(workspace), c_size_t(workspace.numel() if workspace is not None else 0), c_int32(stages), _stream())
+        _check(rc, "dsvt_set_attention_fused_table_launch")
+        return out
     if stages != 7:
         res, gamma, beta, eps = norm if norm is not None else (None, None, None, 0.0)
         rc = _lib().dsvt_set_attention_fused_stages_launch(

@@ -96,8 +96,12 @@ static int attn_dispatch(const dsvt_set_attention_params* p, const dsvt_attentio
                          const float* q, const float* k, const float* v, const float* pos, const int* idx,
                          const float* mask, const int* set_num, const int* voxel_num, float* out, const void* plan,
                          void* workspace, size_t workspace_bytes, cudaStream_t st, const AttnNorm* norm = nullptr,
-                         int stages = 7)
+                         int stages = 7, const AttnPosTable* pos_table = nullptr)
 {
+    if (pos_table && !(fused && p->precision == DSVT_ATTN_FP32_TC)) {
+        set_last_error("set attention: the position-embedding table form exists for the fused DSVT_ATTN_FP32_TC entry only");
+        return DSVT_ERR_UNSUPPORTED;
+    }
     if (stages != 7 && p->precision != DSVT_ATTN_FP32_TC && p->precision != DSVT_ATTN_FP16_GEMM) {
         set_last_error("set attention: single-stage launches exist for the GEMM-pipeline precisions only");
         return DSVT_ERR_UNSUPPORTED;
@@ -121,7 +125,7 @@ static int attn_dispatch(const dsvt_set_attention_params* p, const dsvt_attentio
                                                   q, k, v, mask, set_num, out, workspace, workspace_bytes, st);
             return set_attention_split_fused(p, w->split_blob, w->split_out_mul, p->precision == DSVT_ATTN_FP32_TC,
                                              q, pos, idx, mask, set_num, voxel_num, out, plan, workspace, workspace_bytes, st, norm,
-                                             stages);
+                                             stages, pos_table);
         case DSVT_ATTN_FP32:
             // fused form: these two kernels scatter set rows into `out`; a voxel that belongs to no set (a set dropped by a
             // capacity guard upstream) must read exactly 0 like the reference's zero-filled tensor (mapSetFeature2voxel.cu:312)
@@ -158,7 +162,7 @@ static int fused_common(const dsvt_set_attention_params* p, const dsvt_attention
                         const float* x, const float* pos, const int32_t* global_index_in_set, const float* mask,
                         const int32_t* set_num, const int32_t* voxel_num, float* out, const void* plan,
                         void* workspace, size_t workspace_bytes, dsvt_stream_t stream, const AttnNorm* norm = nullptr,
-                        int stages = 7)
+                        int stages = 7, const AttnPosTable* pos_table = nullptr)
 {
     int rc = attn_check(p, w);
     if (rc != DSVT_OK) return rc;
@@ -167,7 +171,7 @@ static int fused_common(const dsvt_set_attention_params* p, const dsvt_attention
     DSVT_CHECK_ARG(p->axis_id == 0 || p->axis_id == 1, "axis_id");
     DSVT_CHECK_ARG(!(((uintptr_t) x | (uintptr_t) pos | (uintptr_t) out) & 15), "16-B alignment");
     return attn_dispatch(p, w, true, x, nullptr, nullptr, pos, global_index_in_set, mask, set_num, voxel_num,
-                         out, plan, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream), norm, stages);
+                         out, plan, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream), norm, stages, pos_table);
 }
 
 extern "C" int dsvt_set_attention_fused_launch(const dsvt_set_attention_params* p, const dsvt_attention_weights* w,
@@ -217,6 +221,23 @@ extern "C" int dsvt_set_attention_fused_stages_launch(const dsvt_set_attention_p
     const AttnNorm norm{residual, gamma, beta, eps};
     return fused_common(p, w, x, pos, global_index_in_set, mask, set_num, voxel_num, out, plan, workspace, workspace_bytes,
                         stream, residual ? &norm : nullptr, stages);
+}
+
+extern "C" int dsvt_set_attention_fused_table_launch(const dsvt_set_attention_params* p, const dsvt_attention_weights* w,
+                                                     const float* x, const float* pos_table, const int32_t* coors_in_win_2d,
+                                                     int32_t win_shape_x, const int32_t* global_index_in_set, const float* mask,
+                                                     const int32_t* set_num, const int32_t* voxel_num, const float* residual,
+                                                     const float* gamma, const float* beta, float eps, float* out,
+                                                     const void* plan, void* workspace, size_t workspace_bytes,
+                                                     int32_t stages, dsvt_stream_t stream)
+{
+    DSVT_CHECK_ARG(stages >= 1 && stages <= 7, "stages: bit 0 QKV projection, bit 1 per-set core, bit 2 out-projection");
+    DSVT_CHECK_ARG(plan != nullptr, "a prebuilt plan is required");
+    DSVT_CHECK_ARG(coors_in_win_2d && win_shape_x >= 1, "coors_in_win_2d / win_shape_x");
+    const AttnNorm norm{residual, gamma, beta, eps};
+    const AttnPosTable pt{coors_in_win_2d, win_shape_x};
+    return fused_common(p, w, x, pos_table, global_index_in_set, mask, set_num, voxel_num, out, plan, workspace, workspace_bytes,
+                        stream, residual ? &norm : nullptr, stages, &pt);
 }
 
 extern "C" size_t dsvt_set_attention_plan_size(const dsvt_set_attention_params* p) {

@@ -32,11 +32,13 @@ int attention_split_plan(const dsvt_set_attention_params* p, const int* idx, con
                          void* plan, size_t plan_bytes, cudaStream_t st);
 // optional epilogue of the out-projection: out = LayerNorm(attention + residual) (norm1 of the encoder layer)
 struct AttnNorm { const float* residual; const float* gamma; const float* beta; float eps; };
+// position embedding given as a table over the cells of a window (pos = table[cy * win_x + cx]) instead of one row per voxel
+struct AttnPosTable { const int* cell; int win_x; };
 int set_attention_split_fused(const dsvt_set_attention_params* p, const void* split_blob, const float* out_mul,
                               bool split, const float* x, const float* pos, const int* idx, const float* mask,
                               const int* set_num, const int* voxel_num, float* out, const void* plan,
                               void* workspace, size_t workspace_bytes, cudaStream_t st, const AttnNorm* norm = nullptr,
-                              int stages = 7);
+                              int stages = 7, const AttnPosTable* pos_table = nullptr);
 
 // the same pipeline for pre-gathered q / k / v [B, max_sets, S, 192] (the drop-in for multHeadAttention() itself)
 size_t attention_split_plugin_workspace(const dsvt_set_attention_params* p);

@@ -1369,10 +1369,14 @@ int attention_split_plan(const dsvt_set_attention_params* p, const int* idx, con
 int set_attention_split_fused(const dsvt_set_attention_params* p, const void* split_blob, const float* out_mul,
                               bool split, const float* x, const float* pos, const int* idx, const float* mask,
                               const int* set_num, const int* voxel_num, float* out, const void* plan_in,
-                              void* workspace, size_t workspace_bytes, cudaStream_t st, const AttnNorm* norm, int stages)
+                              void* workspace, size_t workspace_bytes, cudaStream_t st, const AttnNorm* norm, int stages,
+                              const AttnPosTable* pos_table)
 {
     int rc = split_check(p);
-    if (rc != DSVT_OK) return rc;
+    if (pos_table && (stages & 1) && (!split || !pos_table->cell || pos_table->win_x < 1)) {
+        set_last_error("set attention: the position-embedding table form is built for DSVT_ATTN_FP32_TC (cell map and win_x required)");
+        return DSVT_ERR_UNSUPPORTED;
+    }
     if (!split_blob) {
         set_last_error("set attention (GEMM pipeline): weights were not prepared");
         return DSVT_ERR_INVALID_ARGUMENT;
@@ -1448,6 +1452,7 @@ int set_attention_split_fused(const dsvt_set_attention_params* p, const void* sp
         if (split) {                               // FP32 configuration: one tile-wide CTA for the three roles (qkv_fused.cuh)
             QkvArgs qa;
             qa.x = x; qa.pos = pos; qa.wimg = img; qa.bias = bias;
+            qa.pos_cell = pos_table ? pos_table->cell : nullptr; qa.win_x = pos_table ? pos_table->win_x : 0;
             for (int r = 0; r < 3; ++r) qa.out_mul[r] = out_mul[r];
             qa.q_post_mul = 1.0f / sqrtf((float) (kC / kH));
             qa.qbuf = qbuf; qa.kvbuf = kvbuf; qa.plan = plan; qa.plan_stride = plan_stride;

@@ -20,7 +20,10 @@ constexpr int kQWorkerWarps = 16, kQWorkers = kQWorkerWarps * 32, kQThreads = kQ
 
 struct QkvArgs {
     const float* x;           // [B, max_pillars, 192]
-    const float* pos;         // [B, max_pillars, 192]
+    const float* pos;         // [B, max_pillars, 192]; or, with pos_cell != nullptr, a TABLE [win_x * win_y, 192] indexed by the
+                              // voxel's cell in its window: the position embedding is a function of (cx, cy) only
+    const int* pos_cell;      // [B, max_pillars, 3] (cz, cy, cx) = WindowPartitionPlugin output 4 (coors_in_win_2d), or nullptr
+    int win_x;
     const uint8_t* wimg;      // roles Q, K, V: 3 x 6 chunk images of 24 KB
     const float* bias;        // [3][192]
     float out_mul[3];
@@ -45,7 +48,8 @@ qkv_fused_kernel(const __grid_constant__ QkvArgs a, const int* __restrict__ voxe
     const int row_base = tile * kBM;
     if (row_base >= V) return;                              // q / k|v rows beyond the valid count are never read
     const float* x = a.x + (size_t) b * max_pillars * kC;
-    const float* pos = a.pos + (size_t) b * max_pillars * kC;
+    const bool table = a.pos_cell != nullptr;
+    const float* pos = table ? a.pos : a.pos + (size_t) b * max_pillars * kC;
     if (tid == 0) TP(0);
 
     if (tid == 0) {
@@ -63,6 +67,11 @@ qkv_fused_kernel(const __grid_constant__ QkvArgs a, const int* __restrict__ voxe
 
     if (warp < kQWorkerWarps) {
         const int rl = warp * 8 + (lane & 7), c16 = lane >> 3, srow = row_base + rl;      // staging: row, 16-byte K piece
+        size_t prow = (size_t) srow * kC;                   // this row's position embedding: its own row, or the table row of its cell
+        if (table && srow < V) {
+            const int* cell = a.pos_cell + ((size_t) b * max_pillars + srow) * 3;
+            prow = (size_t) (__ldg(cell + 1) * a.win_x + __ldg(cell + 2)) * kC;
+        }
         // stage(): the tile's rows x + pos -> FP16 hi / lo chunk images (the x-alone image for V is staged from registers below)
         auto stage = [&](bool with_pos) {
             constexpr int kDepth = 3;
@@ -70,7 +79,7 @@ qkv_fused_kernel(const __grid_constant__ QkvArgs a, const int* __restrict__ voxe
             auto issue = [&](int kc, float (&d)[16]) {
                 if (srow < V) {
                     ldg256(x + (size_t) srow * kC + kc * kBK + c16 * 8, &d[0]);
-                    if (with_pos) ldg256(pos + (size_t) srow * kC + kc * kBK + c16 * 8, &d[8]);
+                    if (with_pos) ldg256(pos + prow + kc * kBK + c16 * 8, &d[8]);
                     else {
 #pragma unroll
                         for (int e = 8; e < 16; ++e) d[e] = 0.f;
@@ -230,7 +239,7 @@ qkv_fused_kernel(const __grid_constant__ QkvArgs a, const int* __restrict__ voxe
             const int nrows = V - row_base < kBM ? V - row_base : kBM;
             const uint32_t bytes = (uint32_t) (nrows * kC * sizeof(float));
             l2_prefetch(x + (size_t) row_base * kC, bytes);
-            l2_prefetch(pos + (size_t) row_base * kC, bytes);
+            if (!table) l2_prefetch(pos + (size_t) row_base * kC, bytes);
 #pragma unroll 1
             for (int L = 0; L < 3 * kNumK; ++L) {
                 const int slot = L % kQWSlots;

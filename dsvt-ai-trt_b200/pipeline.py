@@ -226,8 +226,21 @@ class HotPathFrame:
             if not vfe_one:
                 self.pfn0_out = torch.empty(Pm, cfg.pfn_channels[0], device=device)
                 self.pfn1_out = torch.empty(Pm, cfg.pfn_channels[1], device=device)
-            self.pos_hidden = torch.empty(mp, C, device=device)
-            self.pos_out = [[torch.empty(mp, C, device=device) for _ in range(2)] for _ in range(cfg.num_blocks)]
+            self.pos_hidden = None if vfe_one else torch.empty(mp, C, device=device)
+            self.pos_out = None if ffn == "layer" else [[torch.empty(mp, C, device=device) for _ in range(2)] for _ in range(cfg.num_blocks)]
+            if ffn == "layer":
+                # position embedding as a TABLE over the cells of a window (its MLP's input is a function of (cx, cy) only,
+                # windowPartition.cu:358-359): evaluated per frame on the list of cells, looked up by the QKV kernel
+                ncell = max(wx * wy for wx, wy, _ in cfg.win_shapes)
+                self.pos_cells = []
+                for wx, wy, _ in cfg.win_shapes:
+                    c = np.zeros((ncell, 2), np.float32)
+                    cy, cx = np.divmod(np.arange(wx * wy), wx)
+                    c[: wx * wy, 0] = cx.astype(np.float32) - np.float32(wx) / 2
+                    c[: wx * wy, 1] = cy.astype(np.float32) - np.float32(wy) / 2
+                    self.pos_cells.append(torch.from_numpy(c).to(device))
+                self.pos_rows = torch.tensor([ncell], dtype=torch.int32, device=device)
+                self.pos_tab = [[torch.empty(ncell, C, device=device) for _ in range(2)] for _ in range(cfg.num_blocks)]
         self.x_a = torch.empty(mp, C, device=device)
         self.x_b = torch.empty(mp, C, device=device)
         self.blk_out = [torch.empty(mp, C, device=device) for _ in range(2)]
@@ -258,6 +271,12 @@ class HotPathFrame:
             self.nms = capi.RotatedNms(cfg.max_top_k, 0.01, device=device, zero_tails=self.zero_tails)      # NMS_THRESH, params.h:334
         self.launches_per_frame = None
         self.vfe_ws = None
+
+    def attn_pos(self, blk, enc):
+        """(pos, pos_table) arguments of capi.set_attention_fused for encoder layer (blk, enc) in this frame kind."""
+        if self.ffn == "layer":
+            return None, (self.pos_tab[blk][enc], self.wp[enc].coors_in_win_2d[0], self.cfg.win_shapes[enc][0])
+        return self.pos_out[blk][enc], None
 
     def calibrate_head(self, n_above=250):
         """head="conv" only, random weights: shift the heat-map bias so that n_above cells of THIS frame's map score above
@@ -320,7 +339,14 @@ class HotPathFrame:
         else:
             x = self.max_voxel[-1]                         # VFE output: per-pillar max of PFN layer 1 (:589, output 1)
             pos = self.pos_out
-            if self.ffn in ("kernel", "layer") and "pos" not in skip:   # all MLPs of the frame in one launch (they depend on the coordinates only)
+            if self.ffn == "layer" and "pos" not in skip:    # the MLPs on the cells of a window: tables of <= 24 x 24 rows
+                pairs = [(blk, enc) for blk in range(cfg.num_blocks) for enc in (0, 1)]
+                for i0 in range(0, len(pairs), 8):
+                    grp = pairs[i0:i0 + 8]
+                    capi.pos_embed_mlp_batch([w.glue["pos"][b_][e_][0] for b_, e_ in grp], [w.glue["pos"][b_][e_][1] for b_, e_ in grp],
+                                             [self.pos_cells[e_] for b_, e_ in grp], self.pos_rows,
+                                             [self.pos_tab[b_][e_] for b_, e_ in grp], zero_tails=0)
+            if self.ffn == "kernel" and "pos" not in skip:   # all MLPs of the frame in one launch (they depend on the coordinates only)
                 pairs = [(blk, enc) for blk in range(cfg.num_blocks) for enc in (0, 1)]
                 for i0 in range(0, len(pairs), 8):
                     grp = pairs[i0:i0 + 8]
@@ -345,9 +371,10 @@ class HotPathFrame:
                     aw, plan = w.attn[blk * 2 + enc], self.plans.get((blk % 2, enc))
                     st3 = 3 - sum(bit for g_, bit in (("attn_qkv", 1), ("attn_core", 2)) if g_ in skip)
                     if "attn" not in skip and st3:
-                        capi.set_attention_fused(aw, x, pos[blk][enc], gs.global_index_in_set[0], gs.mask_expand_0[0], gs.set_num, V,
+                        capi.set_attention_fused(aw, x, None, gs.global_index_in_set[0], gs.mask_expand_0[0], gs.set_num, V,
                                                  axis=enc, out=self.src, precision=self.precision, workspace=self.attn_ws,
-                                                 plan=plan, zero_tails=zt, stages=st3)
+                                                 plan=plan, zero_tails=zt, stages=st3,
+                                                 pos_table=(self.pos_tab[blk][enc], self.wp[enc].coors_in_win_2d[0], cfg.win_shapes[enc][0]))
                     fc1, fc2 = w.ffn[blk * 2 + enc]
                     norm1 = (w.gamma[ln], w.beta[ln], cfg.layer_norm_eps)
                     stages = [(self.src, w.gamma[ln + 1], w.beta[ln + 1]), (x, w.gamma[ln + 2], w.beta[ln + 2])]

@@ -324,6 +324,23 @@ int dsvt_set_attention_fused_stages_launch(const dsvt_set_attention_params* p, c
                                            float* out, const void* plan, void* workspace, size_t workspace_bytes,
                                            int32_t stages, dsvt_stream_t stream);
 
+/*
+ * dsvt_set_attention_fused_stages_launch with the position embedding given as a TABLE: the embedding of a voxel is a function
+ * of its cell (cx, cy) in its window only (the MLP's input is coors_in_win_x_y = (cx - win_x / 2, cy - win_y / 2),
+ * src/dsvt-ai-trt.cpp:603-637, windowPartition.cu:358-359), so the MLP needs evaluating once per cell -- at most 12 x 12 or
+ * 24 x 24 rows -- instead of once per voxel.  pos_table [win_x * win_y, 192] f32, row cy * win_x + cx (the MLP's output for that
+ * cell, e.g. from dsvt_pos_embed_mlp_batch_launch on the list of cells); coors_in_win_2d [B,max_pillars_num,3] i32 =
+ * WindowPartitionPlugin output 4 (cz, cy, cx).  Results = the per-voxel form with pos[v] = pos_table[cell(v)].
+ * DSVT_ATTN_FP32_TC only.
+ */
+int dsvt_set_attention_fused_table_launch(const dsvt_set_attention_params* p, const dsvt_attention_weights* w,
+                                          const float* x, const float* pos_table, const int32_t* coors_in_win_2d,
+                                          int32_t win_shape_x, const int32_t* global_index_in_set, const float* mask,
+                                          const int32_t* set_num, const int32_t* voxel_num, const float* residual,
+                                          const float* gamma, const float* beta, float eps, float* out,
+                                          const void* plan, void* workspace, size_t workspace_bytes,
+                                          int32_t stages, dsvt_stream_t stream);
+
 /* ------------------------------------------------------------------------ *
  * (next #4) dense linear layer  y = x * W^T + b on tcgen05 -- replaces the TensorRT FullyConnected
  * layers next to the plugins (fullyConnected_gelu_fullyConnected, src/dsvt-ai-trt.cpp:494-529).

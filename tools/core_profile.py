@@ -12,8 +12,9 @@ f.load_points(pkg.synth.ring_lidar(200000, seed=0))
 f.run(); torch.cuda.synchronize()
 V, gs, x = f.vox.pillar_num, f.gs[0], f.blk_out[0]
 attn = lambda stages: capi.set_attention_fused(
-    w.attn[0], x, f.pos_out[0][0], gs.global_index_in_set[0], gs.mask_expand_0[0], gs.set_num, V, axis=0, out=f.src_b,
-    precision=f.precision, workspace=f.attn_ws, plan=f.plans[(0, 0)], norm=(x, w.gamma[0], w.beta[0], cfg.layer_norm_eps), stages=stages)
+    w.attn[0], x, f.attn_pos(0, 0)[0], gs.global_index_in_set[0], gs.mask_expand_0[0], gs.set_num, V, axis=0, out=f.src_b,
+    precision=f.precision, workspace=f.attn_ws, plan=f.plans[(0, 0)], norm=(x, w.gamma[0], w.beta[0], cfg.layer_norm_eps), stages=stages,
+    pos_table=f.attn_pos(0, 0)[1])
 attn(1); torch.cuda.synchronize()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda"); flush_r = torch.zeros(64 << 20, dtype=torch.int32, device="cuda")
 for cold in (True, False):

@@ -52,7 +52,7 @@ def main(rep, table, js):
         elif "ffn_fused_kernel" in o["name"]: k = "ffn_fused"
         elif "qkv_fused_kernel" in o["name"]: k = "set_attention.qkv_proj_gemm"
         elif "vfe_fused_kernel" in o["name"]: k = "vfe_fused"
-        elif "pos_fused_kernel" in o["name"]: k = "pos_embed_mlp_x8"
+        elif "pos_fused_kernel" in o["name"]: k = "pos_embed_tables_x8"
         o["key"] = k or o["name"]
         keys[o["key"]].append(o)
     with open(table, "w") as f:
